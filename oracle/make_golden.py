@@ -1,0 +1,257 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.pt from the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference):
+
+    python -m oracle.make_golden
+
+For every case it builds the reference ``build_encoder(cfg)`` / ``build_decoder(cfg)`` and the three
+head MLPs exactly as ``STCATNet.__init__`` wires them (pipeline.py:37-50), overwrites every parameter
+with ``stcat_b200.synthetic.fill_param`` (so that the weights never have to be stored), runs the
+reference forward (pipeline.py:72-121), the reference ``VideoSTGLoss`` and ``PostProcess``, and a
+backward pass, and stores the outputs / selected gradients.  Inputs come from
+``stcat_b200.synthetic.make_inputs`` and are stored only as checksums.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle.ref_import import import_reference, import_reference_map2d  # noqa: E402
+from stcat_b200 import synthetic  # noqa: E402
+from stcat_b200.config import get_default_cfg  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+CASES = {
+    # BASELINE.json configs[0]: T=8, res=224 (7x7), 8 text tokens, one video, no padding
+    "b1_T8_res224_L8": dict(durations=[8], H=7, W=7, L=8, ragged=False, max_video_len=200, seed=1),
+    # two videos of different length, non-square map, padded columns and padded text tokens
+    "b2_ragged_T5_3": dict(durations=[5, 3], H=4, W=6, L=6, ragged=True, max_video_len=200, seed=2),
+    # three videos, very ragged, one of length 1
+    "b3_ragged_T4_1_6": dict(durations=[4, 1, 6], H=3, W=5, L=5, ragged=True, max_video_len=300, seed=3),
+    # a larger single clip (res 320 -> 10x10), 16 tokens
+    "b1_T12_res320_L16": dict(durations=[12], H=10, W=10, L=16, ragged=False, max_video_len=300, seed=4),
+}
+
+
+class RefHotPath(torch.nn.Module):
+    """The hot-path slice of the reference STCATNet (pipeline.py:37-50, 72-121), built from the
+    reference's own constructors."""
+
+    def __init__(self, ref, cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.ground_encoder = ref.build_encoder(cfg)
+        self.ground_decoder = ref.build_decoder(cfg)
+        hd = cfg.MODEL.STCAT.HIDDEN
+        self.temp_embed = ref.MLP(hd, hd, 2, 2, dropout=0.3)
+        self.bbox_embed = ref.MLP(hd, hd, 4, 3)
+        self.action_embed = ref.MLP(hd, hd, 1, 2, dropout=0.3)
+        self.ground_decoder.decoder.bbox_embed = self.bbox_embed
+        self.ref = ref
+
+    def forward(self, inp):
+        ref, cfg = self.ref, self.cfg
+        vis = ref.NestedTensor(inp["vis_features"], inp["vis_mask"].clone(), list(inp["durations"]))
+        texts = (inp["text_mask"], inp["text_memory"], None)
+        cache = self.ground_encoder(videos=vis, vis_pos=inp["vis_pos"], texts=texts)
+        outputs, outputs_temp = self.ground_decoder(memory_cache=cache, vis_pos=inp["vis_pos"], text_cls=None)
+        out = {}
+        time_hs, weights = outputs_temp
+        out["weights"] = weights[-1]
+        hs, reference = outputs
+        tmp = self.bbox_embed(hs)
+        tmp[..., :4] += ref.inverse_sigmoid(reference)
+        coord = tmp.sigmoid().flatten(1, 2)
+        out["pred_boxes"] = coord[-1]
+        sted = self.temp_embed(time_hs)
+        out["pred_sted"] = sted[-1]
+        act = self.action_embed(time_hs)
+        out["pred_actioness"] = act[-1]
+        out["aux_outputs"] = [
+            {"pred_sted": a, "pred_boxes": b_, "weights": weights[i], "pred_actioness": act[i]}
+            for i, (a, b_) in enumerate(zip(sted[:-1], coord[:-1]))
+        ]
+        extra = dict(cache=cache, hs=hs, reference=reference, time_hs=time_hs, weights_all=weights)
+        return out, extra
+
+
+class _Boxes:
+    """Minimal stand-in for utils.bounding_box.BoxList: criterion.py reads ``.bbox`` and ``len()``."""
+
+    def __init__(self, bbox):
+        self.bbox = bbox
+
+    def __len__(self):
+        return self.bbox.shape[0]
+
+
+def make_cfg(ref, max_video_len):
+    cfg = ref.cfg.clone()
+    cfg.defrost() if hasattr(cfg, "defrost") else None
+    cfg.merge_from_list(["INPUT.MAX_VIDEO_LEN", max_video_len, "MODEL.STCAT.DROPOUT", 0.0])
+    return cfg
+
+
+def checksum(t: torch.Tensor):
+    t = t.double()
+    return torch.tensor([t.sum(), t.abs().sum(), (t * t).sum()])
+
+
+def run_case(ref, name, spec):
+    cfg = make_cfg(ref, spec["max_video_len"])
+    torch.manual_seed(0)
+    model = RefHotPath(ref, cfg).eval()  # eval: the 0.3 head dropout is identity; grads still flow
+    sd = synthetic.fill_state_dict(model.state_dict(), seed=spec["seed"])
+    for k in list(sd):  # decoder.bbox_embed is the same module object as the top-level bbox_embed (pipeline.py:50)
+        if k.startswith("ground_decoder.decoder.bbox_embed."):
+            sd[k] = sd[k[len("ground_decoder.decoder."):]].clone()
+    model.load_state_dict(sd)
+    from stcat_b200.param_spec import hot_path_spec
+    spec_shapes = hot_path_spec(cfg)
+    ref_shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert dict(spec_shapes) == ref_shapes, set(spec_shapes) ^ set(ref_shapes)
+    inp = synthetic.make_inputs(spec["durations"], spec["H"], spec["W"], spec["L"], seed=spec["seed"],
+                                ragged=spec["ragged"])
+    tg = synthetic.make_targets(spec["durations"], seed=spec["seed"])
+    vis = inp["vis_features"].clone().requires_grad_(True)
+    txt = inp["text_memory"].clone().requires_grad_(True)
+    inp_run = dict(inp, vis_features=vis, text_memory=txt)
+    out, extra = model(inp_run)
+
+    fx = {"spec": spec, "inputs_checksum": {k: checksum(v) for k, v in inp.items() if torch.is_tensor(v) and v.is_floating_point()}}
+    fx["out"] = {k: v.detach().clone() for k, v in out.items() if torch.is_tensor(v)}
+    fx["aux"] = [{k: v.detach().clone() for k, v in a.items()} for a in out["aux_outputs"]]
+    c = extra["cache"]
+    fx["cache"] = {k: c[k].detach().clone() for k in ("encoded_memory", "mask", "frames_cls", "videos_cls")}
+    fx["hs"] = extra["hs"].detach().clone()
+    fx["reference"] = extra["reference"].detach().clone()
+    fx["time_hs"] = extra["time_hs"].detach().clone()
+    fx["weights_all"] = extra["weights_all"].detach().clone()
+
+    # reference post-process (post_processor.py:17-55)
+    n = len(spec["durations"]) * max(spec["durations"])  # pred_boxes is padded to b*t rows (pipeline.py:92)
+    sizes = torch.tensor([[240.0 + 8 * i, 320.0 + 4 * i] for i in range(n)])
+    frames_id = [[10 + 3 * j for j in range(max(spec["durations"]))] for _ in spec["durations"]]
+    pp = ref.PostProcess()
+    boxes, steds = pp({"pred_sted": out["pred_sted"].detach(), "pred_boxes": out["pred_boxes"].detach()},
+                      sizes, frames_id, spec["durations"])
+    fx["post"] = {"target_sizes": sizes, "frames_id": frames_id, "boxes": boxes.clone(), "steds": steds}
+
+    # reference loss + backward (criterion.py:151-207), yaml coefficients of the VidSTG config
+    cfg.merge_from_list(["SOLVER.GIOU_COEF", 3, "SOLVER.TEMP_COEF", 10, "SOLVER.EOS_COEF", 0.3])
+    crit = ref.VideoSTGLoss(cfg, ["boxes", "sted", "guided_attn", "actioness"])
+    targets, s = [], 0
+    for i, dur in enumerate(spec["durations"]):
+        k = int(tg["actioness"][i].sum())
+        targets.append({"actioness": tg["actioness"][i], "boxs": _Boxes(tg["boxes"][s:s + k])})
+        s += k
+    loss_dict = crit(out, targets, spec["durations"])
+    S = cfg.SOLVER
+    wd = {"loss_bbox": S.BBOX_COEF, "loss_giou": S.GIOU_COEF, "loss_sted": S.TEMP_COEF,
+          "loss_actioness": S.ACTIONESS_COEF, "loss_guided_attn": S.ATTN_COEF}
+    base = dict(wd)
+    for i in range(cfg.MODEL.STCAT.DEC_LAYERS - 1):
+        wd.update({f"{k}_{i}": v for k, v in base.items()})
+    total = sum(loss_dict[k] * wd[k] for k in loss_dict if k in wd)
+    total.backward()
+    fx["loss"] = {k: v.detach().clone() for k, v in loss_dict.items()}
+    fx["loss_total"] = total.detach().clone()
+    fx["loss_cfg"] = {"GIOU_COEF": 3, "TEMP_COEF": 10, "EOS_COEF": 0.3}
+    fx["grad"] = {"vis_features": vis.grad.clone(), "text_memory": txt.grad.clone()}
+    gn, full = {}, {}
+    keep_full = ("ground_decoder.template_generator.anchor_proj.weight", "bbox_embed.layers.2.weight",
+                 "ground_encoder.encoder.frame_cls.weight", "ground_encoder.encoder.video_cls.weight",
+                 "ground_encoder.encoder.spatial_layers.0.norm1.weight",
+                 "ground_encoder.encoder.temporal_layers.5.self_attn.in_proj_bias",
+                 "ground_decoder.decoder.layers.0.ca_qpos_proj.bias",
+                 "ground_decoder.temp_decoder.layers.3.cross_attn_image.out_proj.bias",
+                 "ground_decoder.decoder.ref_point_head.layers.1.bias",
+                 "ground_decoder.decoder.query_scale.layers.1.bias",
+                 "temp_embed.layers.1.weight", "action_embed.layers.1.weight")
+    for k, p in model.named_parameters():
+        if p.grad is None:
+            gn[k] = torch.tensor(float("nan"))  # unused parameter
+        else:
+            gn[k] = p.grad.double().norm().float()
+            if k in keep_full:
+                full[k] = p.grad.clone()
+    fx["grad_norm"] = gn
+    fx["grad_full"] = full
+
+    # The same thing once more with the reference run in float64 (torch default dtype switched, the
+    # reference allocates its zero paddings with the default dtype).  The fp32 backward of the reference
+    # is itself noisy at the 1e-3 level on some frames (measured: case b3, frame 6), so the semantic
+    # pin for gradients is the fp64 run.
+    torch.set_default_dtype(torch.float64)
+    try:
+        m64 = RefHotPath(ref, cfg).eval()
+        m64.load_state_dict(sd)
+        m64 = m64.double()
+        vis64 = inp["vis_features"].double().requires_grad_(True)
+        txt64 = inp["text_memory"].double().requires_grad_(True)
+        out64, extra64 = m64(dict(inp, vis_features=vis64, text_memory=txt64, vis_pos=inp["vis_pos"].double()))
+        fx["out64"] = {k: v.detach().clone() for k, v in out64.items() if torch.is_tensor(v)}
+        fx["encoded_memory64"] = extra64["cache"]["encoded_memory"].detach().clone()
+        t64 = [{"actioness": t_["actioness"].double(), "boxs": _Boxes(t_["boxs"].bbox.double())} for t_ in targets]
+        ld64 = crit(out64, t64, spec["durations"])
+        tot64 = sum(ld64[k] * wd[k] for k in ld64 if k in wd)
+        tot64.backward()
+        fx["loss_total64"] = tot64.detach().clone()
+        fx["grad64"] = {"vis_features": vis64.grad.clone(), "text_memory": txt64.grad.clone()}
+        fx["grad_norm64"] = {k: (p.grad.norm() if p.grad is not None else torch.tensor(float("nan")))
+                             for k, p in m64.named_parameters()}
+    finally:
+        torch.set_default_dtype(torch.float32)
+    path = os.path.join(GOLDEN_DIR, f"{name}.pt")
+    torch.save(fx, path)
+    print(f"{name}: loss={float(total.detach()):.6f}  -> {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
+def run_map2d():
+    """Standalone fixture for the orphaned map2d head, small map (N=16)."""
+    ref, m2d = import_reference_map2d()
+    cfg = ref.cfg.clone()
+    cfg.merge_from_list(["MODEL.STCAT.MAX_MAP_SIZE", 16, "MODEL.STCAT.POOLING_COUNTS", [3, 2, 2],
+                         "MODEL.STCAT.TEMP_HEAD", "conv", "MODEL.STCAT.KERNAL_SIZE", 5,
+                         "MODEL.STCAT.CONV_LAYERS", 2, "MODEL.STCAT.DROPOUT", 0.0])
+    cfg.MODEL.TEMPFORMER = cfg.MODEL.STCAT  # map2d_head.py reads a node that defaults.py never defines
+    torch.manual_seed(0)
+    head = m2d.TempPredictionHead(cfg).eval()
+    sd = synthetic.fill_state_dict(head.state_dict(), seed=7)
+    head.load_state_dict(sd)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, 1, 20, 256, generator=g)  # T=20 > N=16 exercises the adaptive avg-pool
+    x2 = torch.randn(2, 1, 12, 256, generator=g)  # T=12 < N exercises adaptive max-pool upsampling
+    fx = {"cfg": dict(MAX_MAP_SIZE=16, POOLING_COUNTS=[3, 2, 2], KERNAL_SIZE=5, CONV_LAYERS=2), "seed": 7}
+    with torch.no_grad():
+        fx["x"], fx["x2"] = x, x2
+        fx["map2d"] = head.map_maker(x.view(-1, 20, 256)).clone()
+        fx["map2d_2"] = head.map_maker(x2.view(-1, 12, 256)).clone()
+        fx["scores_eval"] = head(x).clone()
+        head.train()
+        fx["scores_train"] = head(x).clone()
+    fx["mask2d"] = head.mask_2d.clone()
+    path = os.path.join(GOLDEN_DIR, "map2d_N16.pt")
+    torch.save(fx, path)
+    print(f"map2d: -> {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
+def main():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.set_num_threads(8)
+    ref = import_reference()
+    for name, spec in CASES.items():
+        run_case(ref, name, spec)
+    run_map2d()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,667 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement (the "oracle") of the STCAT hot path.
+
+This file is the checker the CUDA path is compared with.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference`` legs may import
+it; nothing under ``stcat_b200/`` does (the product path has no CPU fallback).
+
+Parity status: the reference ships no tests or golden vectors for this path (SURVEY.md 4, 8c:
+"parity unpinned by the reference").  This restatement is therefore pinned against **outputs of the
+reference itself run in the build container**: ``oracle/make_golden.py`` imports the unmodified
+reference from /root/reference, runs it on seeded inputs/weights and commits inputs-by-recipe and
+outputs under ``tests/golden/``; ``tests/test_oracle_golden.py`` checks this file against those
+fixtures (and against the live reference when /root/reference exists).
+
+It is a *restatement*, not a copy: a purely functional implementation over a flat ``{name: tensor}``
+parameter dict that uses the reference's ``state_dict`` key names.  Every function cites the
+reference lines whose arithmetic it follows.  All arithmetic is floating point; ``Prec`` selects the
+dtype (fp32 like the reference, or fp64) and optionally emulates bf16 rounding of matmul operands
+(used to gate the bf16 tensor-core kernels).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+Params = Dict[str, Tensor]
+
+
+@dataclass
+class Prec:
+    dtype: torch.dtype = torch.float32
+    round_operands: Optional[str] = None  # None | "bf16": round every matmul operand to bf16 first
+
+    def r(self, x: Tensor) -> Tensor:
+        if self.round_operands == "bf16":
+            return x.to(torch.bfloat16).to(x.dtype)
+        return x
+
+
+FP32 = Prec()
+
+
+# ----------------------------------------------------------------------------------------------
+# small building blocks
+# ----------------------------------------------------------------------------------------------
+def linear(x: Tensor, w: Tensor, b: Optional[Tensor], prec: Prec = FP32) -> Tensor:
+    """y = x W^T + b  (torch.nn.Linear; used everywhere on the path)."""
+    y = prec.r(x) @ prec.r(w).t()
+    return y if b is None else y + b
+
+
+def layer_norm(x: Tensor, w: Tensor, b: Tensor, eps: float = 1e-5) -> Tensor:
+    """nn.LayerNorm(256), eps 1e-5 (modal_encoder.py:218-219, query_decoder.py:296-299,573-576)."""
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * w + b
+
+
+def mlp(P: Params, prefix: str, x: Tensor, num_layers: int, prec: Prec = FP32) -> Tensor:
+    """Linear-ReLU stack, no activation after the last layer (net_utils.py:7-26; dropout omitted: eval)."""
+    for i in range(num_layers):
+        x = linear(x, P[f"{prefix}.layers.{i}.weight"], P[f"{prefix}.layers.{i}.bias"], prec)
+        if i < num_layers - 1:
+            x = torch.relu(x)
+    return x
+
+
+def inverse_sigmoid(x: Tensor, eps: float = 1e-3) -> Tensor:
+    """logit with clamps (net_utils.py:59-63)."""
+    x = x.clamp(0, 1)
+    return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
+
+
+def seq_sine_table(max_len: int, d_model: int, dtype=torch.float32) -> Tensor:
+    """SeqEmbeddingSine buffer ``te`` [max_len,1,d] (position_encoding.py:21-33).
+
+    The reference builds the table in fp32 with torch.exp / sin / cos; we do the same in fp32 and
+    cast, so the table is bit-identical to the reference's buffer.
+    """
+    position = torch.arange(max_len).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+    te = torch.zeros(max_len, 1, d_model)
+    te[:, 0, 0::2] = torch.sin(position * div_term)
+    te[:, 0, 1::2] = torch.cos(position * div_term)
+    return te.to(dtype)
+
+
+def anchor_sine_embed(anchor: Tensor) -> Tensor:
+    """gen_sineembed_for_position for 4-d anchors (net_utils.py:29-56).
+
+    anchor [..., 4] = (cx, cy, w, h) in (0,1).  Output [..., 512] ordered (y, x, w, h), 128 dims each,
+    dims interleaved sin (even k) / cos (odd k) with frequency 10000^(2*floor(k/2)/128), scale 2*pi.
+    """
+    scale = 2 * math.pi
+    k = torch.arange(128, dtype=torch.float32)
+    dim_t = (10000 ** (2 * torch.div(k, 2, rounding_mode="floor") / 128)).to(anchor.dtype)
+
+    def emb(c):
+        p = (c * scale)[..., None] / dim_t
+        return torch.stack((p[..., 0::2].sin(), p[..., 1::2].cos()), dim=-1).flatten(-2)
+
+    return torch.cat((emb(anchor[..., 1]), emb(anchor[..., 0]), emb(anchor[..., 2]), emb(anchor[..., 3])), dim=-1)
+
+
+def image_sine_pos(mask: Tensor, num_pos_feats: int = 128, temperature: float = 10000.0,
+                   dtype=torch.float32) -> Tensor:
+    """PositionEmbeddingSine(128, normalize=True) (vision_model/position_encoding.py:70-94).
+
+    Upstream of the hot path (it arrives as ``vis_pos``); restated here only so that synthetic inputs
+    have the real positional structure.  mask [n,H,W] bool (True = padded) -> [n, 256, H, W].
+    """
+    not_mask = ~mask
+    y_embed = not_mask.cumsum(1, dtype=torch.float32)
+    x_embed = not_mask.cumsum(2, dtype=torch.float32)
+    eps, scale = 1e-6, 2 * math.pi
+    y_embed = y_embed / (y_embed[:, -1:, :] + eps) * scale
+    x_embed = x_embed / (x_embed[:, :, -1:] + eps) * scale
+    dim_t = torch.arange(num_pos_feats, dtype=torch.float32)
+    dim_t = temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / num_pos_feats)
+    pos_x = x_embed[:, :, :, None] / dim_t
+    pos_y = y_embed[:, :, :, None] / dim_t
+    pos_x = torch.stack((pos_x[..., 0::2].sin(), pos_x[..., 1::2].cos()), dim=4).flatten(3)
+    pos_y = torch.stack((pos_y[..., 0::2].sin(), pos_y[..., 1::2].cos()), dim=4).flatten(3)
+    return torch.cat((pos_y, pos_x), dim=3).permute(0, 3, 1, 2).to(dtype)
+
+
+# ----------------------------------------------------------------------------------------------
+# attention
+# ----------------------------------------------------------------------------------------------
+def attention_core(q: Tensor, k: Tensor, v: Tensor, nhead: int, key_padding_mask: Optional[Tensor],
+                   scaling: float, prec: Prec = FP32) -> Tuple[Tensor, Tensor]:
+    """softmax((q*scaling) k^T + mask) v per head.
+
+    q [Lq,N,Eq], k [Lk,N,Eq], v [Lk,N,Ev] (seq-first); key_padding_mask [N,Lk] bool, True -> -inf.
+    Returns (o [Lq,N,Ev], P [N,h,Lq,Lk]).  Follows torch F.multi_head_attention_forward
+    (nn/functional.py:6630-6665 in torch 2.11: q scaled first, bmm, masked -inf, softmax, bmm) and the
+    reference's custom variant attention.py:283-383 (explicit max-subtraction :379-380, which does
+    not change the value of the softmax).
+    """
+    Lq, N, Eq = q.shape
+    Lk = k.shape[0]
+    Ev = v.shape[2]
+    dq, dv = Eq // nhead, Ev // nhead
+    qh = prec.r(q * scaling).reshape(Lq, N, nhead, dq).permute(1, 2, 0, 3)  # [N,h,Lq,dq]
+    kh = prec.r(k).reshape(Lk, N, nhead, dq).permute(1, 2, 0, 3)
+    vh = prec.r(v).reshape(Lk, N, nhead, dv).permute(1, 2, 0, 3)
+    s = qh @ kh.transpose(-1, -2)  # [N,h,Lq,Lk]
+    if key_padding_mask is not None:
+        s = s.masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
+    p = torch.softmax(s - s.max(dim=-1, keepdim=True)[0], dim=-1)
+    o = prec.r(p) @ vh  # [N,h,Lq,dv]
+    o = o.permute(2, 0, 1, 3).reshape(Lq, N, Ev)
+    return o, p
+
+
+def torch_mha(P: Params, prefix: str, query: Tensor, key: Tensor, value: Tensor, nhead: int,
+              key_padding_mask: Optional[Tensor], prec: Prec = FP32) -> Tuple[Tensor, Tensor]:
+    """torch.nn.MultiheadAttention forward with packed in_proj (used at modal_encoder.py:212,236;
+    query_decoder.py:269,341,565-566,604,633).  Returns (out [Lq,N,E], head-averaged P [N,Lq,Lk])."""
+    E = query.shape[-1]
+    W, b = P[f"{prefix}.in_proj_weight"], P[f"{prefix}.in_proj_bias"]
+    q = linear(query, W[:E], b[:E], prec)
+    k = linear(key, W[E:2 * E], b[E:2 * E], prec)
+    v = linear(value, W[2 * E:], b[2 * E:], prec)
+    o, p = attention_core(q, k, v, nhead, key_padding_mask, float(E // nhead) ** -0.5, prec)
+    out = linear(o, P[f"{prefix}.out_proj.weight"], P[f"{prefix}.out_proj.bias"], prec)
+    return out, p.mean(dim=1)
+
+
+def custom_mha(P: Params, prefix: str, query: Tensor, key: Tensor, value: Tensor, nhead: int,
+               key_padding_mask: Optional[Tensor], prec: Prec = FP32) -> Tuple[Tensor, Tensor]:
+    """Reference attention.MultiheadAttention: no in-projection, embed 2d (dk=64/head), vdim d (dv=32),
+    scaling = dk^-0.5, out_proj Linear(d,d) (attention.py:86-113,275-393)."""
+    Eq = query.shape[-1]
+    o, p = attention_core(query, key, value, nhead, key_padding_mask, float(Eq // nhead) ** -0.5, prec)
+    out = linear(o, P[f"{prefix}.out_proj.weight"], P[f"{prefix}.out_proj.bias"], prec)
+    return out, p.mean(dim=1)
+
+
+# ----------------------------------------------------------------------------------------------
+# encoder  (modal_encoder.py)
+# ----------------------------------------------------------------------------------------------
+def encoder_layer(P: Params, prefix: str, src: Tensor, mask: Optional[Tensor], pos: Tensor, nhead: int,
+                  prec: Prec = FP32) -> Tensor:
+    """Post-norm TransformerEncoderLayer.forward (modal_encoder.py:228-242), dropout = identity."""
+    qk = src + pos
+    a, _ = torch_mha(P, f"{prefix}.self_attn", qk, qk, src, nhead, mask, prec)
+    src = layer_norm(src + a, P[f"{prefix}.norm1.weight"], P[f"{prefix}.norm1.bias"])
+    h = torch.relu(linear(src, P[f"{prefix}.linear1.weight"], P[f"{prefix}.linear1.bias"], prec))
+    y = linear(h, P[f"{prefix}.linear2.weight"], P[f"{prefix}.linear2.bias"], prec)
+    return layer_norm(src + y, P[f"{prefix}.norm2.weight"], P[f"{prefix}.norm2.bias"])
+
+
+def encoder_forward(P: Params, cfg, vis_features: Tensor, vis_mask: Tensor, durations: Sequence[int],
+                    vis_pos: Tensor, text_mask: Tensor, text_memory: Tensor, prec: Prec = FP32,
+                    prefix: str = "ground_encoder") -> dict:
+    """CrossModalEncoder.forward (modal_encoder.py:40-101) + SpatialTemporalEncoder.forward (:130-204).
+
+    vis_features [n,d,H,W], vis_mask [n,H,W] bool, vis_pos [n,d,H,W], text_mask [b,L] bool (True = pad),
+    text_memory [L,b,d].  Returns the ``memory_cache`` dict of :92-99.
+    """
+    S = cfg.MODEL.STCAT
+    d, nhead, nlayers = S.HIDDEN, S.HEADS, S.ENC_LAYERS
+    durations = list(durations)
+    b, n, t = len(durations), sum(durations), max(durations)
+    dt = prec.dtype
+    vis_features, vis_pos, text_memory = vis_features.to(dt), vis_pos.to(dt), text_memory.to(dt)
+    assert vis_pos.shape[0] == n
+    _, _, H, W = vis_features.shape
+    vis_mask = vis_mask.clone()
+    vis_mask[:, 0, 0] = False  # :46
+    x_v = vis_features.flatten(2).permute(2, 0, 1)  # [HW,n,d]  :52
+    pos_v = vis_pos.flatten(2).permute(2, 0, 1)
+    m_v = vis_mask.flatten(1)  # [n,HW]
+    frame_to_video = torch.repeat_interleave(torch.arange(b), torch.tensor(durations))
+    m_t = text_mask[frame_to_video]  # [n,L]   :62-68
+    x_t = text_memory[:, frame_to_video]  # [L,n,d] :71-77
+    x = torch.cat([x_v, x_t], 0)  # :80
+    mask = torch.cat([m_v, m_t], 1)  # :81
+    pos = torch.cat([pos_v, torch.zeros_like(x_t)], 0)  # :82  text tokens get pos = 0
+
+    ep = f"{prefix}.encoder"
+    # SpatialTemporalEncoder.forward :145-159
+    frame_cls = P[f"{ep}.frame_cls.weight"].to(dt)  # [1,d]
+    x = torch.cat([frame_cls[None].expand(1, n, d), x], 0)  # [S,n,d]
+    pos = torch.cat([P[f"{ep}.local_pos_embed.weight"].to(dt)[None].expand(1, n, d), pos], 0)
+    kp_mask = torch.cat([torch.zeros(n, 1, dtype=torch.bool), mask], 1)  # [n,S]
+    video_src = P[f"{ep}.video_cls.weight"].to(dt).expand(b, d).clone()  # [b,d]
+    temp_pos = P[f"{ep}.time_embed.te"].to(dt)[: t + 1].expand(t + 1, b, d)
+    temp_mask = torch.ones(b, t + 1, dtype=torch.bool)
+    temp_mask[:, 0] = False
+    for i, dur in enumerate(durations):
+        temp_mask[i, 1:1 + dur] = False
+    starts = [0]
+    for dur in durations:
+        starts.append(starts[-1] + dur)
+
+    for li in range(nlayers):
+        x = encoder_layer(P, f"{ep}.spatial_layers.{li}", x, kp_mask, pos, nhead, prec)  # :163-168
+        y = torch.zeros(t + 1, b, d, dtype=dt)  # :170-177 (seq-first directly)
+        for i, dur in enumerate(durations):
+            y[0, i] = video_src[i]
+            y[1:1 + dur, i] = x[0, starts[i]:starts[i + 1]]
+        y = encoder_layer(P, f"{ep}.temporal_layers.{li}", y, temp_mask, temp_pos, nhead, prec)  # :180-185
+        video_src = y[0].clone()  # :191
+        cls_new = torch.cat([y[1:1 + dur, i] for i, dur in enumerate(durations)], 0)  # :192-194
+        x = torch.cat([cls_new[None], x[1:]], 0)  # :195  (in-place row replacement, restated functionally)
+
+    return {
+        "encoded_memory": x[1:],  # [HW+L,n,d]
+        "mask": mask,  # [n,HW+L]
+        "frames_cls": x[0],  # [n,d]
+        "videos_cls": video_src,  # [b,d]
+        "durations": durations,
+        "fea_map_size": (H, W),
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+# decoder  (query_decoder.py)
+# ----------------------------------------------------------------------------------------------
+def template_generator(P: Params, prefix: str, frames_cls: Tensor, videos_cls: Tensor,
+                       durations: Sequence[int], prec: Prec = FP32) -> Tuple[Tensor, Tensor]:
+    """TemplateGenerator.forward (query_decoder.py:451-475).  Returns (pos_query [n,4] pre-sigmoid,
+    temp_query [n,d])."""
+    b = len(durations)
+    f2v = torch.repeat_interleave(torch.arange(b), torch.tensor(list(durations)))
+    content = linear(videos_cls, P[f"{prefix}.content_proj.weight"], P[f"{prefix}.content_proj.bias"], prec)
+    gamma = torch.tanh(linear(videos_cls, P[f"{prefix}.gamma_proj.weight"], P[f"{prefix}.gamma_proj.bias"], prec))
+    beta = torch.tanh(linear(videos_cls, P[f"{prefix}.beta_proj.weight"], P[f"{prefix}.beta_proj.bias"], prec))
+    pos_query = linear(gamma[f2v] * frames_cls + beta[f2v], P[f"{prefix}.anchor_proj.weight"],
+                       P[f"{prefix}.anchor_proj.bias"], prec)
+    return pos_query, content[f2v]
+
+
+def _pad_per_video(x: Tensor, durations: Sequence[int], t: int) -> Tensor:
+    """[n, c] -> [t, b, c], zero padded (query_decoder.py:108-119)."""
+    out = x.new_zeros(t, len(durations), x.shape[-1])
+    s = 0
+    for i, dur in enumerate(durations):
+        out[:dur, i] = x[s:s + dur]
+        s += dur
+    return out
+
+
+def _frames_from_padded(x: Tensor, durations: Sequence[int]) -> Tensor:
+    """[t, b, c] -> [1, n, c] (query_decoder.py:386-398, 618-629)."""
+    return torch.cat([x[:dur, i] for i, dur in enumerate(durations)], 0)[None]
+
+
+def _padded_from_frames(x: Tensor, durations: Sequence[int], t: int) -> Tensor:
+    """[1, n, c] -> [t, b, c] zero padded (query_decoder.py:419-429, 641-651)."""
+    return _pad_per_video(x[0], durations, t)
+
+
+def box_decoder_layer(P: Params, prefix: str, tgt, memory, query_mask, memory_mask, pos, query_pos,
+                      query_time, query_sine, durations, is_first: bool, nhead: int, prec: Prec = FP32):
+    """TransformerDecoderLayer.forward, FROM_SCRATCH=True branch (query_decoder.py:310-438)."""
+    L = lambda name, x: linear(x, P[f"{prefix}.{name}.weight"], P[f"{prefix}.{name}.bias"], prec)
+    t, b, c = tgt.shape
+    # self attention over the t queries of each video :329-345
+    q = L("sa_qcontent_proj", tgt) + L("sa_qtime_proj", query_time) + L("sa_qpos_proj", query_pos)
+    k = L("sa_kcontent_proj", tgt) + L("sa_ktime_proj", query_time) + L("sa_kpos_proj", query_pos)
+    v = L("sa_v_proj", tgt)
+    a, weights = torch_mha(P, f"{prefix}.self_attn", q, k, v, nhead, query_mask, prec)
+    tgt = layer_norm(tgt + a, P[f"{prefix}.norm1.weight"], P[f"{prefix}.norm1.bias"])
+    # time-aligned cross attention :350-429
+    n_tok, n, f = memory.shape
+    qc = L("ca_qcontent_proj", tgt)
+    kc = L("ca_kcontent_proj", memory)
+    vv = L("ca_v_proj", memory)
+    kp = L("ca_kpos_proj", pos)
+    if is_first:
+        qc = qc + L("ca_qpos_proj", query_pos)
+        kc = kc + kp
+    dh = c // nhead
+    qs = L("ca_qpos_sine_proj", query_sine)
+    q2 = torch.cat([qc.view(t, b, nhead, dh), qs.view(t, b, nhead, dh)], 3).reshape(t, b, 2 * c)
+    k2 = torch.cat([kc.view(n_tok, n, nhead, dh), kp.view(n_tok, n, nhead, dh)], 3).reshape(n_tok, n, 2 * c)
+    q_cross = _frames_from_padded(q2, durations)  # [1,n,2c]
+    o, _ = custom_mha(P, f"{prefix}.cross_attn", q_cross, k2, vv, nhead, memory_mask, prec)
+    o = _padded_from_frames(o, durations, t)
+    tgt = layer_norm(tgt + o, P[f"{prefix}.norm3.weight"], P[f"{prefix}.norm3.bias"])
+    # FFN :435-437
+    y = L("linear2", torch.relu(L("linear1", tgt)))
+    tgt = layer_norm(tgt + y, P[f"{prefix}.norm4.weight"], P[f"{prefix}.norm4.bias"])
+    return tgt, weights
+
+
+def box_decoder(P: Params, prefix: str, bbox_prefix: str, tgt, memory, query_mask, memory_mask, pos, anchor,
+                query_time, durations, nlayers: int, nhead: int, prec: Prec = FP32):
+    """TransformerDecoder.forward with bbox_embed set (query_decoder.py:169-247).
+    Returns (hs [nl,b,t,d], refs [nl,b,t,4])."""
+    d = tgt.shape[-1]
+    out = tgt
+    inter, refs = [], [anchor]
+    for li in range(nlayers):
+        sine = anchor_sine_embed(anchor)  # [t,b,512] :191
+        query_pos = mlp(P, f"{prefix}.ref_point_head", sine, 2, prec)  # :192
+        scale = 1 if li == 0 else mlp(P, f"{prefix}.query_scale", out, 2, prec)  # :195-198
+        qsine = sine[..., :d] * scale  # :201
+        out, _ = box_decoder_layer(P, f"{prefix}.layers.{li}", out, memory, query_mask, memory_mask, pos,
+                                   query_pos, query_time, qsine, durations, li == 0, nhead, prec)
+        new_anchor = torch.sigmoid(mlp(P, bbox_prefix, out, 3, prec) + inverse_sigmoid(anchor))  # :213-215
+        if li != nlayers - 1:
+            refs.append(new_anchor)
+        anchor = new_anchor.detach()  # :219
+        inter.append(layer_norm(out, P[f"{prefix}.norm.weight"], P[f"{prefix}.norm.bias"]))  # :222
+    return torch.stack(inter).transpose(1, 2), torch.stack(refs).transpose(1, 2)
+
+
+def time_decoder_layer(P: Params, prefix: str, tgt, memory, query_mask, memory_mask, pos, query_pos,
+                       query_time_pos, durations, nhead: int, prec: Prec = FP32):
+    """TimeDecoderLayer.forward (query_decoder.py:587-660)."""
+    t, b, c = tgt.shape
+    qk = tgt + query_pos + query_time_pos
+    a, weights = torch_mha(P, f"{prefix}.self_attn", qk, qk, tgt, nhead, query_mask, prec)
+    tgt = layer_norm(tgt + a, P[f"{prefix}.norm1.weight"], P[f"{prefix}.norm1.bias"])
+    q_cross = _frames_from_padded(tgt, durations) + _frames_from_padded(query_pos, durations)
+    o, _ = torch_mha(P, f"{prefix}.cross_attn_image", q_cross, memory + pos, memory, nhead, memory_mask, prec)
+    o = _padded_from_frames(o, durations, t)
+    tgt = layer_norm(tgt + o, P[f"{prefix}.norm3.weight"], P[f"{prefix}.norm3.bias"])
+    L = lambda name, x: linear(x, P[f"{prefix}.{name}.weight"], P[f"{prefix}.{name}.bias"], prec)
+    y = L("linear2", torch.relu(L("linear1", tgt)))
+    tgt = layer_norm(tgt + y, P[f"{prefix}.norm4.weight"], P[f"{prefix}.norm4.bias"])
+    return tgt, weights
+
+
+def time_decoder(P: Params, prefix: str, tgt, memory, query_mask, memory_mask, pos, query_pos,
+                 query_time_pos, durations, nlayers: int, nhead: int, prec: Prec = FP32):
+    """TimeDecoder.forward, return_intermediate & return_weights (query_decoder.py:494-550)."""
+    out = tgt
+    inter, ws = [], []
+    for li in range(nlayers):
+        out, w = time_decoder_layer(P, f"{prefix}.layers.{li}", out, memory, query_mask, memory_mask, pos,
+                                    query_pos, query_time_pos, durations, nhead, prec)
+        inter.append(layer_norm(out, P[f"{prefix}.norm.weight"], P[f"{prefix}.norm.bias"]))
+        ws.append(w)
+    return torch.stack(inter).transpose(1, 2), torch.stack(ws)
+
+
+def decoder_forward(P: Params, cfg, memory_cache: dict, vis_pos: Tensor, prec: Prec = FP32,
+                    prefix: str = "ground_decoder", bbox_prefix: str = "bbox_embed"):
+    """QueryDecoder.forward (query_decoder.py:83-147).  ``text_cls`` is accepted by the reference and
+    never used (:451-475), so it is not an argument here."""
+    S = cfg.MODEL.STCAT
+    d, nhead, nlayers = S.HIDDEN, S.HEADS, S.DEC_LAYERS
+    dt = prec.dtype
+    memory = memory_cache["encoded_memory"]
+    memory_mask = memory_cache["mask"]
+    durations = list(memory_cache["durations"])
+    H, W = memory_cache["fea_map_size"]
+    n_vis = H * W
+    b, t = len(durations), max(durations)
+    pos_query, temp_query = template_generator(P, f"{prefix}.template_generator", memory_cache["frames_cls"],
+                                               memory_cache["videos_cls"], durations, prec)
+    anchors = _pad_per_video(torch.sigmoid(pos_query), durations, t)  # [t,b,4]
+    query_temporal = _pad_per_video(temp_query, durations, t)  # [t,b,d]
+    query_mask = torch.ones(b, t, dtype=torch.bool)
+    query_mask[:, 0] = False
+    for i, dur in enumerate(durations):
+        query_mask[i, :dur] = False
+    query_time = P[f"{prefix}.time_embed.te"].to(dt)[:t].expand(t, b, d)
+    mem_pos = vis_pos.to(dt).flatten(2).permute(2, 0, 1)
+    mem_pos = torch.cat([mem_pos, torch.zeros_like(memory[n_vis:])], 0)
+    tgt = torch.zeros(t, b, d, dtype=dt)
+    outputs = box_decoder(P, f"{prefix}.decoder", bbox_prefix, tgt, memory, query_mask, memory_mask, mem_pos,
+                          anchors, query_time, durations, nlayers, nhead, prec)
+    outputs_temp = time_decoder(P, f"{prefix}.temp_decoder", tgt.clone(), memory, query_mask, memory_mask,
+                                mem_pos, query_temporal, query_time, durations, nlayers, nhead, prec)
+    return outputs, outputs_temp
+
+
+# ----------------------------------------------------------------------------------------------
+# heads, post-process  (pipeline.py, post_processor.py)
+# ----------------------------------------------------------------------------------------------
+def heads_forward(P: Params, cfg, outputs, outputs_temp, prec: Prec = FP32) -> dict:
+    """The prediction tail of STCATNet.forward (pipeline.py:82-121), eval mode (dropout identity)."""
+    hs, reference = outputs
+    time_hs, weights = outputs_temp
+    out = {}
+    if cfg.SOLVER.USE_ATTN:
+        out["weights"] = weights[-1]
+    coord = torch.sigmoid(mlp(P, "bbox_embed", hs, 3, prec) + inverse_sigmoid(reference)).flatten(1, 2)
+    out["pred_boxes"] = coord[-1]
+    sted = mlp(P, "temp_embed", time_hs, 2, prec)
+    out["pred_sted"] = sted[-1]
+    if cfg.MODEL.STCAT.USE_ACTION:
+        act = mlp(P, "action_embed", time_hs, 2, prec)
+        out["pred_actioness"] = act[-1]
+    if cfg.SOLVER.USE_AUX_LOSS:
+        out["aux_outputs"] = []
+        for i in range(hs.shape[0] - 1):
+            a = {"pred_sted": sted[i], "pred_boxes": coord[i]}
+            if cfg.SOLVER.USE_ATTN:
+                a["weights"] = weights[i]
+            if cfg.MODEL.STCAT.USE_ACTION:
+                a["pred_actioness"] = act[i]
+            out["aux_outputs"].append(a)
+    return out
+
+
+def hot_path_forward(P: Params, cfg, vis_features, vis_mask, durations, vis_pos, text_mask, text_memory,
+                     prec: Prec = FP32) -> dict:
+    """encoder -> decoder -> heads: everything between ``input_proj``/text encoder and the loss
+    (pipeline.py:72-121)."""
+    cache = encoder_forward(P, cfg, vis_features, vis_mask, durations, vis_pos, text_mask, text_memory, prec)
+    outputs, outputs_temp = decoder_forward(P, cfg, cache, vis_pos, prec)
+    out = heads_forward(P, cfg, outputs, outputs_temp, prec)
+    out["_memory_cache"] = cache
+    out["_hs"], out["_reference"] = outputs
+    out["_time_hs"], out["_weights_all"] = outputs_temp
+    return out
+
+
+def post_process(pred_sted: Tensor, pred_boxes: Tensor, target_sizes: Tensor, frames_id, durations):
+    """PostProcess.forward (post_processor.py:17-55).
+
+    score[i,j] = logsoftmax_t(sted[:,0])[i] + logsoftmax_t(sted[:,1])[j] - 1e32 * [j<=i or i>=dur or j>=dur]
+    (the reference's ``.tril(0)`` masks the diagonal too, :37); flat argmax -> (start, end+1) frame ids.
+    Returns (boxes_xyxy_scaled [n,4], steds list, score_map [b,t,t]).
+    """
+    cx, cy, w, h = pred_boxes.unbind(-1)
+    boxes = torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], -1)
+    img_h, img_w = target_sizes.unbind(1)
+    boxes = (boxes * torch.stack([img_w, img_h, img_w, img_h], 1)).clamp(min=0)
+    b, t, _ = pred_sted.shape
+    neg = -1e32
+    ii = torch.arange(t)[:, None]
+    jj = torch.arange(t)[None, :]
+    maps = []
+    for i_b in range(b):
+        dur = durations[i_b]
+        m = torch.zeros(t, t, dtype=pred_sted.dtype)
+        m[(jj <= ii) | (ii >= dur) | (jj >= dur)] = neg
+        maps.append(m)
+    score = torch.stack(maps) + F.log_softmax(pred_sted[:, :, 0], dim=1)[:, :, None] \
+        + F.log_softmax(pred_sted[:, :, 1], dim=1)[:, None, :]
+    steds = []
+    for i_b in range(b):
+        idx = int(score[i_b].flatten().argmax())
+        s, e = idx // t, idx % t
+        steds.append([frames_id[i_b][s], frames_id[i_b][e] + 1])
+    return boxes, steds, score
+
+
+# ----------------------------------------------------------------------------------------------
+# loss (criterion.py) -- downstream of the hot path; restated so fwd+bwd has the reference's entry
+# gradient.  Used by bench.py's CPU baseline and by gradient-parity tests.
+# ----------------------------------------------------------------------------------------------
+def _box_cxcywh_to_xyxy(x):
+    cx, cy, w, h = x.unbind(-1)
+    return torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], -1)
+
+
+def _giou_diag(b1, b2):
+    """diag of generalized_box_iou (utils/box_utils.py:94-115) computed pairwise-aligned."""
+    a1 = (b1[:, 2] - b1[:, 0]) * (b1[:, 3] - b1[:, 1])
+    a2 = (b2[:, 2] - b2[:, 0]) * (b2[:, 3] - b2[:, 1])
+    lt = torch.max(b1[:, :2], b2[:, :2])
+    rb = torch.min(b1[:, 2:], b2[:, 2:])
+    wh = (rb - lt).clamp(min=0)
+    inter = wh[:, 0] * wh[:, 1]
+    union = a1 + a2 - inter
+    iou = inter / union
+    lt2 = torch.min(b1[:, :2], b2[:, :2])
+    rb2 = torch.max(b1[:, 2:], b2[:, 2:])
+    wh2 = (rb2 - lt2).clamp(min=0)
+    area = wh2[:, 0] * wh2[:, 1]
+    return iou - (area - union) / area
+
+
+def stg_loss(cfg, out: dict, target_boxes: Tensor, actioness: Tensor, durations: Sequence[int],
+             weight_dict: Optional[dict] = None) -> Tuple[Tensor, dict]:
+    """VideoSTGLoss.forward (criterion.py:151-207) for b videos, world size 1.
+
+    target_boxes: [num_gt_frames_total, 4] cxcywh for the frames with actioness==1 (video-major order);
+    actioness: [b, t] {0,1}.  Returns (weighted total, dict of the individual losses)."""
+    S = cfg.SOLVER
+    b, t = actioness.shape
+    dev = out["pred_boxes"].device
+    bounds, sl = [], []
+    for i in range(b):
+        idx = torch.nonzero(actioness[i].cpu()).flatten().tolist()
+        bounds.append((idx[0], idx[-1]))
+        sl.extend(range(i * t + idx[0], i * t + idx[-1] + 1))
+    sl = torch.tensor(sl, dtype=torch.long, device=dev)
+    num_boxes = max(float(target_boxes.shape[0]), 1.0)
+    time_mask = torch.zeros(b, t, dtype=torch.bool, device=dev)
+    for i, dur in enumerate(durations):
+        time_mask[i, :dur] = True
+    positive = torch.zeros(b, t, dtype=torch.bool, device=dev)
+    for i, (s, e) in enumerate(bounds):
+        positive[i, s:e + 1] = True
+    eps = 1e-6
+    ar = torch.arange(t, device=dev)[None, :]
+    tstart = torch.tensor([x[0] for x in bounds], device=dev)[:, None]
+    tend = torch.tensor([x[1] for x in bounds], device=dev)[:, None]
+
+    def one(o):
+        L = {}
+        pb = o["pred_boxes"][sl]
+        L["loss_bbox"] = (pb - target_boxes).abs().sum() / num_boxes  # criterion.py:26-39
+        L["loss_giou"] = (1 - _giou_diag(_box_cxcywh_to_xyxy(pb), _box_cxcywh_to_xyxy(target_boxes))).sum() / num_boxes
+        sted = o["pred_sted"].masked_fill(~time_mask[:, :, None], -1e32)  # :64-109
+        tot = 0
+        for ch, tt in ((0, tstart), (1, tend)):
+            distrib = F.normalize((-((ar - tt) ** 2) / (2 * S.SIGMA ** 2)).exp() + eps, p=1, dim=1)
+            prob = sted[:, :, ch].softmax(1)
+            tot = tot + prob * ((prob + eps) / distrib).log() * time_mask
+        L["loss_sted"] = tot.mean()
+        if S.USE_ATTN:  # :111-130
+            w = o["weights"]
+            pm = positive | (~time_mask)
+            la = -(1 - w + eps).log()
+            la = la.masked_fill(pm[:, :, None], 0)
+            nb_neg = (~pm).sum(1) + eps
+            L["loss_guided_attn"] = (la.sum(2) / nb_neg[:, None]).sum(1).mean()
+        if cfg.MODEL.STCAT.USE_ACTION:  # :46-62
+            pa = o["pred_actioness"].squeeze(-1)
+            wgt = torch.full(pa.shape, float(S.EOS_COEF), device=dev, dtype=pa.dtype)
+            for i, (s, e) in enumerate(bounds):
+                wgt[i, s:e + 1] = 1
+            la = F.binary_cross_entropy_with_logits(pa, actioness.to(pa.dtype), weight=wgt, reduction="none")
+            L["loss_actioness"] = (la * time_mask).mean()
+        return L
+
+    losses = one(out)
+    for i, aux in enumerate(out.get("aux_outputs", [])):
+        losses.update({f"{k}_{i}": v for k, v in one(aux).items()})
+    if weight_dict is None:
+        weight_dict = loss_weight_dict(cfg)
+    total = sum(losses[k] * weight_dict[k] for k in losses if k in weight_dict)
+    return total, losses
+
+
+def loss_weight_dict(cfg) -> dict:
+    """build_model's weight_dict (models/__init__.py:12-29)."""
+    S = cfg.SOLVER
+    wd = {"loss_bbox": S.BBOX_COEF, "loss_giou": S.GIOU_COEF, "loss_sted": S.TEMP_COEF}
+    if cfg.MODEL.STCAT.USE_ACTION:
+        wd["loss_actioness"] = S.ACTIONESS_COEF
+    if S.USE_ATTN:
+        wd["loss_guided_attn"] = S.ATTN_COEF
+    if S.USE_AUX_LOSS:
+        base = dict(wd)
+        for i in range(cfg.MODEL.STCAT.DEC_LAYERS - 1):
+            wd.update({f"{k}_{i}": v for k, v in base.items()})
+    return wd
+
+
+# ----------------------------------------------------------------------------------------------
+# map2d_head.py (orphaned in the reference, named by north_star): the 2-D proposal map + conv head
+# ----------------------------------------------------------------------------------------------
+def map2d_masks(N: int, pooling_counts: Sequence[int]):
+    """Gen2DMap.__init__ (map2d_head.py:11-37): valid-cell mask and the (i, j) index lists of every
+    super-diagonal, plus the pooling schedule as (kernel, stride) pairs."""
+    mask2d = torch.zeros(N, N, dtype=torch.bool)
+    mask2d[range(N), range(N)] = True
+    stride, offset = 1, 0
+    maskij = []
+    for c in pooling_counts:
+        for _ in range(c):
+            offset += stride
+            i, j = list(range(0, N - offset, stride)), list(range(offset, N, stride))
+            mask2d[i, j] = True
+            maskij.append((i, j))
+        stride *= 2
+    poolers = [(2, 1)] * pooling_counts[0]
+    for c in pooling_counts[1:]:
+        poolers += [(3, 2)] + [(2, 1)] * (c - 1)
+    return mask2d, maskij, poolers
+
+
+def gen_2d_map(x: Tensor, N: int, pooling_counts: Sequence[int]) -> Tensor:
+    """Gen2DMap.forward (map2d_head.py:39-62).  x [B,T,d] -> map2d [B,d,N,N]."""
+    mask2d, maskij, poolers = map2d_masks(N, pooling_counts)
+    x = x.permute(0, 2, 1)
+    if x.shape[-1] > N:
+        x = F.adaptive_avg_pool1d(x, N)
+    x = F.adaptive_max_pool1d(x, N)
+    B, d, _ = x.shape
+    m = x.new_zeros(B, d, N, N)
+    m[:, :, range(N), range(N)] = x
+    for (kk, ss), (i, j) in zip(poolers, maskij):
+        x = F.max_pool1d(x, kk, ss)
+        m[:, :, i, j] = x
+    return m
+
+
+def map2d_conv_weights(mask2d: Tensor, k: int, num_layers: int) -> List[Tensor]:
+    """mask2weight cascade of TempConvInteraction.__init__ (map2d_head.py:221-245)."""
+    kernel = torch.ones(1, 1, k, k)
+    first_padding = (k - 1) * num_layers // 2
+
+    def m2w(m, padding):
+        w = torch.conv2d(m[None, None].float(), kernel, padding=padding)[0, 0]
+        w[w > 0] = 1 / w[w > 0]
+        return w
+
+    ws = [m2w(mask2d, first_padding)]
+    for _ in range(num_layers - 1):
+        ws.append(m2w(ws[-1] > 0, 0))
+    return ws
+
+
+def map2d_conv_head(P: Params, prefix: str, x: Tensor, cfg_stcat, training: bool = False,
+                    prec: Prec = FP32) -> Tensor:
+    """TempPredictionHead.forward with TEMP_HEAD='conv' (map2d_head.py:105-127, 228-250).
+    x [layers,b,T,d] -> scores [layers,b,N,N]."""
+    N, counts = cfg_stcat.MAX_MAP_SIZE, cfg_stcat.POOLING_COUNTS
+    k, nconv = cfg_stcat.KERNAL_SIZE, cfg_stcat.CONV_LAYERS
+    nl, b, t, d = x.shape
+    mask2d, _, _ = map2d_masks(N, counts)
+    m = gen_2d_map(x.reshape(-1, t, d), N, counts)
+    ws = map2d_conv_weights(mask2d, k, nconv)
+    first_padding = (k - 1) * nconv // 2
+    for i in range(nconv):
+        m = F.conv2d(prec.r(m), prec.r(P[f"{prefix}.encoder.convs.{i}.weight"]), P[f"{prefix}.encoder.convs.{i}.bias"],
+                     padding=first_padding if i == 0 else 0).relu() * ws[i].to(m.dtype)
+    s = F.conv2d(m, P[f"{prefix}.predictor.weight"], P[f"{prefix}.predictor.bias"]).squeeze(1)
+    s = s.view(nl, b, N, N)
+    return s if training else torch.sigmoid(s) * mask2d
