@@ -1,0 +1,131 @@
+/*
+ * stcat_b200.h -- C ABI of libstcat_sm100.so: the B200 (sm_100a) kernels behind the STCAT hot path.
+ *
+ * The reference (jy0205/STCAT) has NO native / FFI interface: its hot path is pure-Python torch.nn
+ * (SURVEY.md 2.B, 8b).  The seam that this library is dropped in behind is therefore the Python one
+ * (models/grounding_model/__init__.py:5-9 build_encoder / build_decoder); each entry point below
+ * replaces the torch.nn / ATen calls of the cited reference lines.  The host-side mirror of the
+ * reference interface (same class/function names, arguments and errors) lives in stcat_b200/*.py
+ * and binds these symbols with ctypes (see INTEGRATION.md for the binding a maintainer would add).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless said otherwise;
+ *  - matrices are row-major with an explicit leading dimension (elements);
+ *  - dtype codes: STCAT_F32 = 0, STCAT_BF16 = 1;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises,
+ *    nothing allocates (workspaces are caller-provided), so every call is CUDA-graph capturable;
+ *  - return 0 on success, a negative STCAT_E* for argument errors, a positive cudaError_t otherwise;
+ *    stcat_last_error() returns a thread-local message.  There is no CPU fallback.
+ */
+#ifndef STCAT_B200_H_
+#define STCAT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define STCAT_API __attribute__((visibility("default")))
+#else
+#define STCAT_API
+#endif
+
+#define STCAT_F32 0
+#define STCAT_BF16 1
+
+#define STCAT_EINVAL (-1)   /* bad argument (null pointer, non-positive size, bad dtype) */
+#define STCAT_ESHAPE (-2)   /* shape not supported by this build (message says which) */
+#define STCAT_EALIGN (-3)   /* pointer / leading dimension alignment requirement violated */
+
+STCAT_API int stcat_abi_version(void);
+STCAT_API const char* stcat_last_error(void);
+/* compute capability major*10+minor of the current device, or <0; 100 expected */
+STCAT_API int stcat_device_arch(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Linear layers (nn.Linear at modal_encoder.py:214-216,239; query_decoder.py:262-278,292-294,
+ * 329-335,354-369,435,446-449,657; packed MHA in-projections torch functional.py:5866-5873; MLP
+ * net_utils.py:14-25; heads pipeline.py:42-47).
+ *   fwd       : y[M,N]   = act(x[M,K] . w[N,K]^T + bias[N])   (+ y if accumulate)
+ *   bwd_data  : dx[M,K]  = dy[M,N] . w[N,K]                    (+ dx if accumulate)
+ *   bwd_weight: dw[N,K] (+)= dy[M,N]^T . x[M,K];  db[N] (+)= column sums of dy   (db may be NULL)
+ * fp32 operands run the exact-fp32 SIMT kernel; bf16 operands run the tcgen05/TMA kernel (fp32
+ * accumulate).  y/dx/dw dtype is given separately.  relu: 0/1.  bias may be NULL.
+ * ---------------------------------------------------------------------------------------------- */
+STCAT_API int stcat_linear_fwd(const void* x, int64_t ldx, int x_dtype, const void* w, int64_t ldw, int w_dtype,
+                     const float* bias, void* y, int64_t ldy, int y_dtype, int M, int N, int K, int relu,
+                     int accumulate, void* stream);
+STCAT_API int stcat_linear_bwd_data(const void* dy, int64_t lddy, int dy_dtype, const void* w, int64_t ldw, int w_dtype,
+                          void* dx, int64_t lddx, int dx_dtype, int M, int N, int K, int accumulate, void* stream);
+STCAT_API int stcat_linear_bwd_weight(const void* dy, int64_t lddy, int dy_dtype, const void* x, int64_t ldx, int x_dtype,
+                            float* dw, int64_t lddw, float* db, int M, int N, int K, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Residual + LayerNorm (modal_encoder.py:237-238,240-241; query_decoder.py:344-345,431-432,436-437,
+ * 612-613,653-654,658-659 and the final norms :222,527).  d must be 256 (cfg.MODEL.STCAT.HIDDEN).
+ *   fwd: z = x + res (res may be NULL);  y = (z - mean) * rstd * gamma + beta;  mean/rstd [rows] saved.
+ *        y_bf16 (may be NULL) additionally receives y rounded to bf16 (operand copy for the next GEMM).
+ *   bwd: dz[rows,d] = LN backward; dgamma[d], dbeta[d] are ACCUMULATED (atomicAdd) into.
+ * ---------------------------------------------------------------------------------------------- */
+STCAT_API int stcat_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y,
+                        void* y_bf16, float* mean, float* rstd, int rows, int d, float eps, void* stream);
+STCAT_API int stcat_layernorm_bwd(const float* dy, const float* x, const float* res, const float* gamma, const float* mean,
+                        const float* rstd, float* dz, float* dgamma, float* dbeta, int rows, int d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-head attention core, batch-major (torch functional.py:6630-6665 bmm/softmax/bmm; reference
+ * attention.py:328-391).  For b in [0,B), h in [0,H):
+ *   s[i,j] = scale * ( q1[b,i,h,:] . k1[b,j,h,:]  +  q2[b,i,h,:] . k2[b,j,h,:] )     (q2/k2 may be NULL)
+ *   s[i,j] = -inf where key_mask[b,j] != 0;   p = softmax_j(s);   o[b,i,h,:] = sum_j p[i,j] v[b,j,h,:]
+ * Row (b,i) of q1 starts at q1 + (b*Lq+i)*ldq, head h at column h*dh; same for the other operands
+ * (rows of k1, k2 and v are (b*Lk+j)).  dh (per part) and the value head dim must both be 32.
+ * The two-part form is the reference's per-head concat [content(32) ; positional(32)] of the box
+ * decoder's cross attention (query_decoder.py:368-384) without materialising the concat.
+ *   lse[B,H,Lq]     : log-sum-exp of each row (saved for backward)
+ *   p_avg[B,Lq,Lk]  : optional (may be NULL); receives mean over heads of p (the `weights` output,
+ *                     query_decoder.py:341,604; must be zero-filled by the caller)
+ * bwd: dq1, dq2, dk1, dk2, dv get the gradients (fully overwritten); dp_avg (may be NULL) is the gradient
+ *      flowing into p_avg.  delta[B,H,Lq] is caller-provided scratch.
+ * ---------------------------------------------------------------------------------------------- */
+STCAT_API int stcat_attention_fwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2, int64_t ldk,
+                        const void* v, int64_t ldv, void* o, int64_t ldo, int dtype, const uint8_t* key_mask,
+                        float* lse, float* p_avg, int B, int H, int Lq, int Lk, int dh, float scale, void* stream);
+STCAT_API int stcat_attention_bwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2, int64_t ldk,
+                        const void* v, int64_t ldv, const void* d_o, int64_t lddo, int dtype,
+                        const uint8_t* key_mask, const float* lse, const float* dp_avg, float* delta,
+                        void* dq1, void* dq2, int64_t lddq, void* dk1, void* dk2, int64_t lddk, void* dv,
+                        int64_t lddv, int B, int H, int Lq, int Lk, int dh, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Element-wise helpers on [rows, cols] fp32 matrices (contiguous).
+ *   add       : out = a + b  (q = k = src + pos, modal_encoder.py:225-226,235); out_bf16 optional copy
+ *   relu_bwd  : dx = dy * (y > 0)                          (F.relu backward)
+ *   cast_bf16 : fp32 -> bf16 operand copy (optionally transposed [cols, rows])
+ * ---------------------------------------------------------------------------------------------- */
+STCAT_API int stcat_add(const float* a, const float* b, float* out, void* out_bf16, int64_t n, void* stream);
+STCAT_API int stcat_relu_bwd(const void* y, int y_dtype, void* dy_inout, int dy_dtype, int64_t n, void* stream);
+STCAT_API int stcat_cast_bf16(const float* x, void* out_bf16, int64_t rows, int64_t cols, int transpose, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Temporal start/end scoring (post_processor.py:30-53), one launch for b videos:
+ *   score[v,i,j] = logsoftmax_t(sted[v,:,0])[i] + logsoftmax_t(sted[v,:,1])[j] + penalty(i,j)
+ *   penalty = -1e32 where j <= i or i >= dur[v] or j >= dur[v]
+ *   best[v] = flat index of the first maximum of score[v]   (start = best / t, end = best % t)
+ * score (may be NULL) is [b,t,t]; durations is a device int32 array [b].
+ * ---------------------------------------------------------------------------------------------- */
+STCAT_API int stcat_sted_score(const float* sted, const int32_t* durations, float* score, int32_t* best, int b, int t,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 2-D temporal proposal map (map2d_head.py:39-62, orphaned in the reference -- SURVEY.md 0-2):
+ *   map[B,d,N,N]: cell (i,j) of the valid set = max_t x[B, i..j, d]; other cells 0.
+ * x is [B, N, d] (already pooled to N positions); valid[N*N] uint8 is the reference's mask2d.
+ * ---------------------------------------------------------------------------------------------- */
+STCAT_API int stcat_map2d_pool(const float* x, const uint8_t* valid, float* map, int B, int N, int d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STCAT_B200_H_ */

@@ -1,0 +1,234 @@
+"""ctypes binding of libstcat_sm100.so (include/stcat_b200.h) and the tensor-level backend object.
+
+There is deliberately NO fallback here: if the library is missing, or a tensor is not on a CUDA
+device, the call raises.  ``tests/emu_backend.py`` provides a torch-CPU emulation of the same
+methods for *testing the host-side composition without a GPU*; it is installed only by tests via
+``ops.set_backend`` and never selected by product code.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+from typing import Optional
+
+import torch
+
+LIB_NAME = "libstcat_sm100.so"
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", LIB_NAME)
+
+F32, BF16 = 0, 1
+
+#: every symbol declared in include/stcat_b200.h: name -> (restype, argtypes)
+_P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
+SIGNATURES = {
+    "stcat_abi_version": (c_int, []),
+    "stcat_last_error": (c_char_p, []),
+    "stcat_device_arch": (c_int, []),
+    "stcat_linear_fwd": (c_int, [_P, _L, _I, _P, _L, _I, _P, _P, _L, _I, _I, _I, _I, _I, _I, _P]),
+    "stcat_linear_bwd_data": (c_int, [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P]),
+    "stcat_linear_bwd_weight": (c_int, [_P, _L, _I, _P, _L, _I, _P, _L, _P, _I, _I, _I, _I, _P]),
+    "stcat_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P]),
+    "stcat_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "stcat_attention_fwd": (c_int, [_P, _P, _L, _P, _P, _L, _P, _L, _P, _L, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
+    "stcat_attention_bwd": (c_int, [_P, _P, _L, _P, _P, _L, _P, _L, _P, _L, _I, _P, _P, _P, _P, _P, _P, _L, _P, _P, _L,
+                                    _P, _L, _I, _I, _I, _I, _I, _F, _P]),
+    "stcat_add": (c_int, [_P, _P, _P, _P, _L, _P]),
+    "stcat_relu_bwd": (c_int, [_P, _I, _P, _I, _L, _P]),
+    "stcat_cast_bf16": (c_int, [_P, _P, _L, _L, _I, _P]),
+    "stcat_sted_score": (c_int, [_P, _P, _P, _P, _I, _I, _P]),
+    "stcat_map2d_pool": (c_int, [_P, _P, _P, _I, _I, _I, _P]),
+}
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None) -> ctypes.CDLL:
+    """dlopen the kernel library and bind every symbol of the header.  Raises if it is not built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or os.environ.get("STCAT_B200_LIB", LIB_PATH)
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{LIB_NAME} not found at {path}: build it with `python -m stcat_b200.build` "
+            "(there is no CPU / PyTorch fallback for the STCAT hot path)")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class StcatError(RuntimeError):
+    pass
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise StcatError(f"unsupported dtype {t.dtype}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class CudaBackend:
+    """Tensor-level calls into the C ABI on the current CUDA stream."""
+
+    name = "cuda"
+
+    def __init__(self):
+        self.lib = load_library()
+        self.launches = 0  # kernels launched through this backend (bench.py reports it)
+
+    # -- helpers -------------------------------------------------------
+    def _rc(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.lib.stcat_last_error()
+            raise StcatError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    @staticmethod
+    def _mat(t: torch.Tensor, name: str):
+        if not t.is_cuda:
+            raise StcatError(f"{name}: tensor is on {t.device}; the STCAT hot path has no CPU fallback")
+        if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+            raise StcatError(f"{name}: expected a 2-D row-major view, got shape {tuple(t.shape)} stride {t.stride()}")
+        ld = t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+        return t.data_ptr(), ld, _dt(t)
+
+    @staticmethod
+    def _flat(t: Optional[torch.Tensor], name: str, dtype=None):
+        if t is None:
+            return None
+        if not t.is_cuda or not t.is_contiguous():
+            raise StcatError(f"{name}: must be a contiguous CUDA tensor")
+        if dtype is not None and t.dtype != dtype:
+            raise StcatError(f"{name}: expected {dtype}, got {t.dtype}")
+        return t.data_ptr()
+
+    # -- linear --------------------------------------------------------
+    def linear_fwd(self, x, w, bias, y, relu=False, accumulate=False):
+        (xp, ldx, xd), (wp, ldw, wd), (yp, ldy, yd) = self._mat(x, "x"), self._mat(w, "w"), self._mat(y, "y")
+        M, K = x.shape
+        N = w.shape[0]
+        assert w.shape[1] == K and tuple(y.shape) == (M, N)
+        self._rc(self.lib.stcat_linear_fwd(xp, ldx, xd, wp, ldw, wd, self._flat(bias, "bias", torch.float32), yp, ldy,
+                                           yd, M, N, K, int(relu), int(accumulate), self._stream()), "linear_fwd")
+        self.launches += 1
+
+    def linear_bwd_data(self, dy, w, dx, accumulate=False):
+        (gp, ldg, gd), (wp, ldw, wd), (xp, ldx, xd) = self._mat(dy, "dy"), self._mat(w, "w"), self._mat(dx, "dx")
+        M, N = dy.shape
+        K = w.shape[1]
+        assert w.shape[0] == N and tuple(dx.shape) == (M, K)
+        self._rc(self.lib.stcat_linear_bwd_data(gp, ldg, gd, wp, ldw, wd, xp, ldx, xd, M, N, K, int(accumulate),
+                                                self._stream()), "linear_bwd_data")
+        self.launches += 1
+
+    def linear_bwd_weight(self, dy, x, dw, db, accumulate=False):
+        (gp, ldg, gd), (xp, ldx, xd), (wp, ldw, wd) = self._mat(dy, "dy"), self._mat(x, "x"), self._mat(dw, "dw")
+        M, N = dy.shape
+        K = x.shape[1]
+        assert x.shape[0] == M and tuple(dw.shape) == (N, K) and wd == F32
+        self._rc(self.lib.stcat_linear_bwd_weight(gp, ldg, gd, xp, ldx, xd, wp, ldw, self._flat(db, "db", torch.float32),
+                                                  M, N, K, int(accumulate), self._stream()), "linear_bwd_weight")
+        self.launches += 1 + (db is not None)
+
+    # -- layernorm -----------------------------------------------------
+    def layernorm_fwd(self, x, res, gamma, beta, y, y_bf16, mean, rstd, eps=1e-5):
+        rows, d = x.shape
+        f = torch.float32
+        self._rc(self.lib.stcat_layernorm_fwd(self._flat(x, "x", f), self._flat(res, "res", f), self._flat(gamma, "gamma", f),
+                                              self._flat(beta, "beta", f), self._flat(y, "y", f),
+                                              self._flat(y_bf16, "y_bf16", torch.bfloat16), self._flat(mean, "mean", f),
+                                              self._flat(rstd, "rstd", f), rows, d, float(eps), self._stream()),
+                 "layernorm_fwd")
+        self.launches += 1
+
+    def layernorm_bwd(self, dy, x, res, gamma, mean, rstd, dz, dgamma, dbeta):
+        rows, d = x.shape
+        f = torch.float32
+        self._rc(self.lib.stcat_layernorm_bwd(self._flat(dy, "dy", f), self._flat(x, "x", f), self._flat(res, "res", f),
+                                              self._flat(gamma, "gamma", f), self._flat(mean, "mean", f),
+                                              self._flat(rstd, "rstd", f), self._flat(dz, "dz", f),
+                                              self._flat(dgamma, "dgamma", f), self._flat(dbeta, "dbeta", f), rows, d,
+                                              self._stream()), "layernorm_bwd")
+        self.launches += 1
+
+    # -- attention -----------------------------------------------------
+    def attention_fwd(self, q1, q2, k1, k2, v, o, key_mask, lse, p_avg, B, H, Lq, Lk, scale):
+        """q*: [B*Lq, H*32] views, k*/v: [B*Lk, H*32] views, o: [B*Lq, H*32]; q2/k2 share q1/k1's leading dim."""
+        (qp, ldq, qd) = self._mat(q1, "q1")
+        (kp, ldk, _), (vp, ldv, _), (op, ldo, _) = self._mat(k1, "k1"), self._mat(v, "v"), self._mat(o, "o")
+        q2p = k2p = None
+        if q2 is not None:
+            q2p, ldq2, _ = self._mat(q2, "q2")
+            k2p, ldk2, _ = self._mat(k2, "k2")
+            assert ldq2 == ldq and ldk2 == ldk
+        assert q1.shape == (B * Lq, H * 32) and k1.shape == (B * Lk, H * 32) and v.shape == (B * Lk, H * 32)
+        self._rc(self.lib.stcat_attention_fwd(qp, q2p, ldq, kp, k2p, ldk, vp, ldv, op, ldo, qd,
+                                              self._flat(key_mask, "key_mask", torch.uint8), self._flat(lse, "lse", torch.float32),
+                                              self._flat(p_avg, "p_avg", torch.float32), B, H, Lq, Lk, 32, float(scale),
+                                              self._stream()), "attention_fwd")
+        self.launches += 1
+
+    def attention_bwd(self, q1, q2, k1, k2, v, d_o, key_mask, lse, dp_avg, delta, dq1, dq2, dk1, dk2, dv, B, H, Lq, Lk,
+                      scale):
+        (qp, ldq, qd) = self._mat(q1, "q1")
+        (kp, ldk, _), (vp, ldv, _), (gp, ldg, _) = self._mat(k1, "k1"), self._mat(v, "v"), self._mat(d_o, "d_o")
+        (dqp, lddq, _), (dkp, lddk, _), (dvp, lddv, _) = self._mat(dq1, "dq1"), self._mat(dk1, "dk1"), self._mat(dv, "dv")
+        q2p = k2p = dq2p = dk2p = None
+        if q2 is not None:
+            q2p, ldq2, _ = self._mat(q2, "q2")
+            k2p, ldk2, _ = self._mat(k2, "k2")
+            dq2p, lddq2, _ = self._mat(dq2, "dq2")
+            dk2p, lddk2, _ = self._mat(dk2, "dk2")
+            assert ldq2 == ldq and ldk2 == ldk and lddq2 == lddq and lddk2 == lddk
+        self._rc(self.lib.stcat_attention_bwd(qp, q2p, ldq, kp, k2p, ldk, vp, ldv, gp, ldg, qd,
+                                              self._flat(key_mask, "key_mask", torch.uint8), self._flat(lse, "lse", torch.float32),
+                                              self._flat(dp_avg, "dp_avg", torch.float32), self._flat(delta, "delta", torch.float32),
+                                              dqp, dq2p, lddq, dkp, dk2p, lddk, dvp, lddv, B, H, Lq, Lk, 32, float(scale),
+                                              self._stream()), "attention_bwd")
+        self.launches += 2
+
+    # -- element-wise --------------------------------------------------
+    def add(self, a, b, out, out_bf16=None):
+        f = torch.float32
+        self._rc(self.lib.stcat_add(self._flat(a, "a", f), self._flat(b, "b", f), self._flat(out, "out", f),
+                                    self._flat(out_bf16, "out_bf16", torch.bfloat16), a.numel(), self._stream()), "add")
+        self.launches += 1
+
+    def relu_bwd(self, y, dy):
+        self._rc(self.lib.stcat_relu_bwd(self._flat(y, "y"), _dt(y), self._flat(dy, "dy"), _dt(dy), y.numel(),
+                                         self._stream()), "relu_bwd")
+        self.launches += 1
+
+    def cast_bf16(self, x, out, transpose=False):
+        rows, cols = x.shape
+        self._rc(self.lib.stcat_cast_bf16(self._flat(x, "x", torch.float32), self._flat(out, "out", torch.bfloat16), rows,
+                                          cols, int(transpose), self._stream()), "cast_bf16")
+        self.launches += 1
+
+    # -- post-process / map2d -------------------------------------------
+    def sted_score(self, sted, durations, score, best):
+        b, t, _ = sted.shape
+        self._rc(self.lib.stcat_sted_score(self._flat(sted, "sted", torch.float32), self._flat(durations, "durations", torch.int32),
+                                           self._flat(score, "score", torch.float32), self._flat(best, "best", torch.int32), b, t,
+                                           self._stream()), "sted_score")
+        self.launches += 1
+
+    def map2d_pool(self, x, valid, out):
+        B, N, d = x.shape
+        self._rc(self.lib.stcat_map2d_pool(self._flat(x, "x", torch.float32), self._flat(valid, "valid", torch.uint8),
+                                           self._flat(out, "map", torch.float32), B, N, d, self._stream()), "map2d_pool")
+        self.launches += 1

@@ -1,0 +1,431 @@
+// Exact-fp32 SIMT multi-head attention core (forward + backward), batch-major, head dim 32 per part.
+//
+// Correctness path and on-device checker for the tcgen05 attention kernel.  Generic in Lq / Lk (online
+// softmax over 64-key chunks), optional second score part (per-head concat of content and positional
+// halves, reference query_decoder.py:368-384), optional key-padding mask, optional head-averaged
+// probability output with its gradient (reference query_decoder.py:604-610 -> criterion.py:111-130).
+//
+// Work split: one warp owns R query rows (fwd, bwd_dq) or R key rows (bwd_dkv); inside a chunk a lane
+// owns one key (resp. query) for the dot products and one feature dim for the accumulations.
+#include "common.cuh"
+#include <math.h>
+
+namespace stcat {
+
+constexpr int DH = 32;       // head dim per part, and value head dim
+constexpr int CH = 64;       // chunk of keys (fwd/dq) or queries (dkv) staged in shared memory
+constexpr int WARPS = 4;
+constexpr int R = 4;         // rows per warp
+constexpr int TILE = WARPS * R;
+
+template <typename T>
+__device__ __forceinline__ void stage_chunk(float (*dst)[DH + 1], const T* __restrict__ src, int64_t ld, int row0,
+                                            int nrows_total, int64_t base_row, int col0) {
+    // 64 rows x 32 dims, 128 threads -> 16 elements each; a warp reads one 32-wide row segment
+    for (int i = threadIdx.x; i < CH * DH; i += WARPS * 32) {
+        int r = i >> 5, d = i & 31;
+        int gr = row0 + r;
+        float v = 0.f;
+        if (gr < nrows_total) v = to_f32<T>(src[(base_row + gr) * ld + col0 + d]);
+        dst[r][d] = v;
+    }
+}
+
+template <typename T, bool TWO>
+__global__ void __launch_bounds__(WARPS * 32)
+attn_fwd_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t ldq, const T* __restrict__ k1,
+                const T* __restrict__ k2, int64_t ldk, const T* __restrict__ v, int64_t ldv, T* __restrict__ o,
+                int64_t ldo, const uint8_t* __restrict__ key_mask, float* __restrict__ lse, float* __restrict__ p_avg,
+                int H, int Lq, int Lk, float scale) {
+    __shared__ float Ks1[CH][DH + 1];
+    __shared__ float Ks2[TWO ? CH : 1][DH + 1];
+    __shared__ float Vs[CH][DH + 1];
+    __shared__ float qs[WARPS][R][2 * DH];
+    __shared__ uint8_t msk[CH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int i0 = blockIdx.x * TILE + warp * R;
+    const int col = h * DH;
+    const int64_t qbase = (int64_t)b * Lq, kbase = (int64_t)b * Lk;
+
+    float m[R], l[R], acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        m[r] = -INFINITY; l[r] = 0.f; acc[r] = 0.f;
+        int i = i0 + r;
+        float a = 0.f, c = 0.f;
+        if (i < Lq) {
+            a = to_f32<T>(q1[(qbase + i) * ldq + col + lane]);
+            if (TWO) c = to_f32<T>(q2[(qbase + i) * ldq + col + lane]);
+        }
+        qs[warp][r][lane] = a;
+        qs[warp][r][DH + lane] = c;
+    }
+    const int npass = p_avg ? 2 : 1;
+    float lse_r[R];
+    for (int pass = 0; pass < npass; ++pass) {
+        for (int c0 = 0; c0 < Lk; c0 += CH) {
+            __syncthreads();
+            stage_chunk<T>(Ks1, k1, ldk, c0, Lk, kbase, col);
+            if (TWO) stage_chunk<T>(Ks2, k2, ldk, c0, Lk, kbase, col);
+            if (pass == 0) stage_chunk<T>(Vs, v, ldv, c0, Lk, kbase, col);
+            if (threadIdx.x < CH) {
+                int j = c0 + threadIdx.x;
+                msk[threadIdx.x] = (j >= Lk) || (key_mask && key_mask[(int64_t)b * Lk + j]);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = i0 + r;
+                if (i >= Lq) continue;  // warp-uniform
+                float s[2];
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    const int key = lane + 32 * kk;
+                    float d = 0.f;
+#pragma unroll
+                    for (int e = 0; e < DH; ++e) d = fmaf(qs[warp][r][e], Ks1[key][e], d);
+                    if (TWO) {
+#pragma unroll
+                        for (int e = 0; e < DH; ++e) d = fmaf(qs[warp][r][DH + e], Ks2[key][e], d);
+                    }
+                    s[kk] = msk[key] ? -INFINITY : d * scale;
+                }
+                if (pass == 0) {
+                    float mx = warp_max(fmaxf(s[0], s[1]));
+                    float mnew = fmaxf(m[r], mx);
+                    float p0 = 0.f, p1 = 0.f, corr = 0.f;
+                    if (mnew != -INFINITY) {
+                        p0 = expf(s[0] - mnew);
+                        p1 = expf(s[1] - mnew);
+                        corr = expf(m[r] - mnew);
+                    }
+                    l[r] = l[r] * corr + warp_sum(p0 + p1);
+                    float a = acc[r] * corr;
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) a = fmaf(__shfl_sync(0xffffffffu, p0, jj), Vs[jj][lane], a);
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) a = fmaf(__shfl_sync(0xffffffffu, p1, jj), Vs[32 + jj][lane], a);
+                    acc[r] = a;
+                    m[r] = mnew;
+                } else {
+                    const float invH = 1.f / (float)H;
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const int j = c0 + lane + 32 * kk;
+                        if (j < Lk) {
+                            float p = (s[kk] == -INFINITY) ? 0.f : expf(s[kk] - lse_r[r]);
+                            atomicAdd(p_avg + ((int64_t)b * Lq + i) * Lk + j, p * invH);
+                        }
+                    }
+                }
+            }
+        }
+        if (pass == 0) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = i0 + r;
+                lse_r[r] = (l[r] > 0.f) ? m[r] + logf(l[r]) : -INFINITY;
+                if (i < Lq) {
+                    float inv = (l[r] > 0.f) ? 1.f / l[r] : 0.f;
+                    o[(qbase + i) * ldo + col + lane] = from_f32<T>(acc[r] * inv);
+                    if (lane == 0) lse[((int64_t)b * H + h) * Lq + i] = lse_r[r];
+                }
+            }
+        }
+    }
+}
+
+// dq for R rows per warp; also writes delta[b,h,i] = sum_j p_ij * dp_ij
+template <typename T, bool TWO>
+__global__ void __launch_bounds__(WARPS * 32)
+attn_bwd_dq_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t ldq, const T* __restrict__ k1,
+                   const T* __restrict__ k2, int64_t ldk, const T* __restrict__ v, int64_t ldv,
+                   const T* __restrict__ d_o, int64_t lddo, const uint8_t* __restrict__ key_mask,
+                   const float* __restrict__ lse, const float* __restrict__ dp_avg, float* __restrict__ delta,
+                   T* __restrict__ dq1, T* __restrict__ dq2, int64_t lddq, int H, int Lq, int Lk, float scale) {
+    __shared__ float Ks1[CH][DH + 1];
+    __shared__ float Ks2[TWO ? CH : 1][DH + 1];
+    __shared__ float Vs[CH][DH + 1];
+    __shared__ float qs[WARPS][R][2 * DH];
+    __shared__ float dos[WARPS][R][DH];
+    __shared__ uint8_t msk[CH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int i0 = blockIdx.x * TILE + warp * R;
+    const int col = h * DH;
+    const int64_t qbase = (int64_t)b * Lq, kbase = (int64_t)b * Lk;
+    const float invH = 1.f / (float)H;
+
+    float lse_r[R], D[R], a1[R], a2[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        int i = i0 + r;
+        float a = 0.f, c = 0.f, g = 0.f;
+        lse_r[r] = 0.f;
+        if (i < Lq) {
+            a = to_f32<T>(q1[(qbase + i) * ldq + col + lane]);
+            if (TWO) c = to_f32<T>(q2[(qbase + i) * ldq + col + lane]);
+            g = to_f32<T>(d_o[(qbase + i) * lddo + col + lane]);
+            lse_r[r] = lse[((int64_t)b * H + h) * Lq + i];
+        }
+        qs[warp][r][lane] = a;
+        qs[warp][r][DH + lane] = c;
+        dos[warp][r][lane] = g;
+        D[r] = 0.f; a1[r] = 0.f; a2[r] = 0.f;
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int c0 = 0; c0 < Lk; c0 += CH) {
+            __syncthreads();
+            stage_chunk<T>(Ks1, k1, ldk, c0, Lk, kbase, col);
+            if (TWO) stage_chunk<T>(Ks2, k2, ldk, c0, Lk, kbase, col);
+            stage_chunk<T>(Vs, v, ldv, c0, Lk, kbase, col);
+            if (threadIdx.x < CH) {
+                int j = c0 + threadIdx.x;
+                msk[threadIdx.x] = (j >= Lk) || (key_mask && key_mask[(int64_t)b * Lk + j]);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = i0 + r;
+                if (i >= Lq) continue;
+                float p[2], dp[2];
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    const int key = lane + 32 * kk;
+                    float d = 0.f, e2 = 0.f;
+#pragma unroll
+                    for (int e = 0; e < DH; ++e) {
+                        d = fmaf(qs[warp][r][e], Ks1[key][e], d);
+                        e2 = fmaf(dos[warp][r][e], Vs[key][e], e2);
+                    }
+                    if (TWO) {
+#pragma unroll
+                        for (int e = 0; e < DH; ++e) d = fmaf(qs[warp][r][DH + e], Ks2[key][e], d);
+                    }
+                    const int j = c0 + key;
+                    if (msk[key] || lse_r[r] == -INFINITY) { p[kk] = 0.f; dp[kk] = 0.f; }
+                    else {
+                        p[kk] = expf(d * scale - lse_r[r]);
+                        dp[kk] = e2 + (dp_avg ? dp_avg[((int64_t)b * Lq + i) * Lk + j] * invH : 0.f);
+                    }
+                }
+                if (pass == 0) {
+                    D[r] += p[0] * dp[0] + p[1] * dp[1];
+                } else {
+                    float ds0 = p[0] * (dp[0] - D[r]) * scale;
+                    float ds1 = p[1] * (dp[1] - D[r]) * scale;
+                    float x1 = a1[r], x2 = a2[r];
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) {
+                        float w0 = __shfl_sync(0xffffffffu, ds0, jj), w1 = __shfl_sync(0xffffffffu, ds1, jj);
+                        x1 = fmaf(w0, Ks1[jj][lane], x1);
+                        x1 = fmaf(w1, Ks1[32 + jj][lane], x1);
+                        if (TWO) {
+                            x2 = fmaf(w0, Ks2[jj][lane], x2);
+                            x2 = fmaf(w1, Ks2[32 + jj][lane], x2);
+                        }
+                    }
+                    a1[r] = x1; a2[r] = x2;
+                }
+            }
+        }
+        if (pass == 0) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                D[r] = warp_sum(D[r]);
+                int i = i0 + r;
+                if (i < Lq && lane == 0) delta[((int64_t)b * H + h) * Lq + i] = D[r];
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        int i = i0 + r;
+        if (i < Lq) {
+            dq1[(qbase + i) * lddq + col + lane] = from_f32<T>(a1[r]);
+            if (TWO) dq2[(qbase + i) * lddq + col + lane] = from_f32<T>(a2[r]);
+        }
+    }
+}
+
+// dk, dv for R key rows per warp
+template <typename T, bool TWO>
+__global__ void __launch_bounds__(WARPS * 32)
+attn_bwd_dkv_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t ldq, const T* __restrict__ k1,
+                    const T* __restrict__ k2, int64_t ldk, const T* __restrict__ v, int64_t ldv,
+                    const T* __restrict__ d_o, int64_t lddo, const uint8_t* __restrict__ key_mask,
+                    const float* __restrict__ lse, const float* __restrict__ dp_avg, const float* __restrict__ delta,
+                    T* __restrict__ dk1, T* __restrict__ dk2, int64_t lddk, T* __restrict__ dv, int64_t lddv, int H,
+                    int Lq, int Lk, float scale) {
+    __shared__ float Qs1[CH][DH + 1];
+    __shared__ float Qs2[TWO ? CH : 1][DH + 1];
+    __shared__ float dOs[CH][DH + 1];
+    __shared__ float ks[WARPS][R][2 * DH];
+    __shared__ float vs[WARPS][R][DH];
+    __shared__ float lses[CH], dels[CH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int j0 = blockIdx.x * TILE + warp * R;
+    const int col = h * DH;
+    const int64_t qbase = (int64_t)b * Lq, kbase = (int64_t)b * Lk;
+    const float invH = 1.f / (float)H;
+
+    float ak1[R], ak2[R], av[R];
+    bool masked[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        int j = j0 + r;
+        float a = 0.f, c = 0.f, g = 0.f;
+        masked[r] = true;
+        if (j < Lk) {
+            a = to_f32<T>(k1[(kbase + j) * ldk + col + lane]);
+            if (TWO) c = to_f32<T>(k2[(kbase + j) * ldk + col + lane]);
+            g = to_f32<T>(v[(kbase + j) * ldv + col + lane]);
+            masked[r] = key_mask && key_mask[(int64_t)b * Lk + j];
+        }
+        ks[warp][r][lane] = a;
+        ks[warp][r][DH + lane] = c;
+        vs[warp][r][lane] = g;
+        ak1[r] = 0.f; ak2[r] = 0.f; av[r] = 0.f;
+    }
+    for (int c0 = 0; c0 < Lq; c0 += CH) {
+        __syncthreads();
+        stage_chunk<T>(Qs1, q1, ldq, c0, Lq, qbase, col);
+        if (TWO) stage_chunk<T>(Qs2, q2, ldq, c0, Lq, qbase, col);
+        stage_chunk<T>(dOs, d_o, lddo, c0, Lq, qbase, col);
+        if (threadIdx.x < CH) {
+            int i = c0 + threadIdx.x;
+            lses[threadIdx.x] = (i < Lq) ? lse[((int64_t)b * H + h) * Lq + i] : -INFINITY;
+            dels[threadIdx.x] = (i < Lq) ? delta[((int64_t)b * H + h) * Lq + i] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int j = j0 + r;
+            if (j >= Lk || masked[r]) continue;  // warp-uniform
+            float p[2], ds[2];
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                const int qi = lane + 32 * kk;
+                const int i = c0 + qi;
+                float d = 0.f, e2 = 0.f;
+#pragma unroll
+                for (int e = 0; e < DH; ++e) {
+                    d = fmaf(Qs1[qi][e], ks[warp][r][e], d);
+                    e2 = fmaf(dOs[qi][e], vs[warp][r][e], e2);
+                }
+                if (TWO) {
+#pragma unroll
+                    for (int e = 0; e < DH; ++e) d = fmaf(Qs2[qi][e], ks[warp][r][DH + e], d);
+                }
+                if (i < Lq && lses[qi] != -INFINITY) {
+                    p[kk] = expf(d * scale - lses[qi]);
+                    float dp = e2 + (dp_avg ? dp_avg[((int64_t)b * Lq + i) * Lk + j] * invH : 0.f);
+                    ds[kk] = p[kk] * (dp - dels[qi]) * scale;
+                } else { p[kk] = 0.f; ds[kk] = 0.f; }
+            }
+            float x1 = ak1[r], x2 = ak2[r], xv = av[r];
+#pragma unroll
+            for (int ii = 0; ii < 32; ++ii) {
+                float p0 = __shfl_sync(0xffffffffu, p[0], ii), p1 = __shfl_sync(0xffffffffu, p[1], ii);
+                float s0 = __shfl_sync(0xffffffffu, ds[0], ii), s1 = __shfl_sync(0xffffffffu, ds[1], ii);
+                xv = fmaf(p0, dOs[ii][lane], xv);
+                xv = fmaf(p1, dOs[32 + ii][lane], xv);
+                x1 = fmaf(s0, Qs1[ii][lane], x1);
+                x1 = fmaf(s1, Qs1[32 + ii][lane], x1);
+                if (TWO) {
+                    x2 = fmaf(s0, Qs2[ii][lane], x2);
+                    x2 = fmaf(s1, Qs2[32 + ii][lane], x2);
+                }
+            }
+            ak1[r] = x1; ak2[r] = x2; av[r] = xv;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        int j = j0 + r;
+        if (j < Lk) {
+            dk1[(kbase + j) * lddk + col + lane] = from_f32<T>(ak1[r]);
+            if (TWO) dk2[(kbase + j) * lddk + col + lane] = from_f32<T>(ak2[r]);
+            dv[(kbase + j) * lddv + col + lane] = from_f32<T>(av[r]);
+        }
+    }
+}
+
+template <typename T, bool TWO>
+static int launch_fwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2, int64_t ldk,
+                      const void* v, int64_t ldv, void* o, int64_t ldo, const uint8_t* key_mask, float* lse,
+                      float* p_avg, int B, int H, int Lq, int Lk, float scale, cudaStream_t st) {
+    dim3 grid((Lq + TILE - 1) / TILE, H, B);
+    attn_fwd_kernel<T, TWO><<<grid, WARPS * 32, 0, st>>>((const T*)q1, (const T*)q2, ldq, (const T*)k1, (const T*)k2,
+                                                         ldk, (const T*)v, ldv, (T*)o, ldo, key_mask, lse, p_avg, H,
+                                                         Lq, Lk, scale);
+    return check_launch("attn_fwd_kernel");
+}
+
+template <typename T, bool TWO>
+static int launch_bwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2, int64_t ldk,
+                      const void* v, int64_t ldv, const void* d_o, int64_t lddo, const uint8_t* key_mask,
+                      const float* lse, const float* dp_avg, float* delta, void* dq1, void* dq2, int64_t lddq,
+                      void* dk1, void* dk2, int64_t lddk, void* dv, int64_t lddv, int B, int H, int Lq, int Lk,
+                      float scale, cudaStream_t st) {
+    dim3 gq((Lq + TILE - 1) / TILE, H, B);
+    attn_bwd_dq_kernel<T, TWO><<<gq, WARPS * 32, 0, st>>>((const T*)q1, (const T*)q2, ldq, (const T*)k1, (const T*)k2,
+                                                          ldk, (const T*)v, ldv, (const T*)d_o, lddo, key_mask, lse,
+                                                          dp_avg, delta, (T*)dq1, (T*)dq2, lddq, H, Lq, Lk, scale);
+    int rc = check_launch("attn_bwd_dq_kernel");
+    if (rc) return rc;
+    dim3 gk((Lk + TILE - 1) / TILE, H, B);
+    attn_bwd_dkv_kernel<T, TWO><<<gk, WARPS * 32, 0, st>>>((const T*)q1, (const T*)q2, ldq, (const T*)k1,
+                                                           (const T*)k2, ldk, (const T*)v, ldv, (const T*)d_o, lddo,
+                                                           key_mask, lse, dp_avg, delta, (T*)dk1, (T*)dk2, lddk,
+                                                           (T*)dv, lddv, H, Lq, Lk, scale);
+    return check_launch("attn_bwd_dkv_kernel");
+}
+
+}  // namespace stcat
+
+using namespace stcat;
+
+extern "C" int stcat_attention_fwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2,
+                                   int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo, int dtype,
+                                   const uint8_t* key_mask, float* lse, float* p_avg, int B, int H, int Lq, int Lk,
+                                   int dh, float scale, void* stream) {
+    STCAT_REQUIRE(q1 && k1 && v && o && lse, STCAT_EINVAL, "attention_fwd: null pointer");
+    STCAT_REQUIRE((q2 == nullptr) == (k2 == nullptr), STCAT_EINVAL, "attention_fwd: q2/k2 must both be set or both NULL");
+    STCAT_REQUIRE(dh == DH, STCAT_ESHAPE, "attention_fwd: head dim %d unsupported (must be 32 = HIDDEN/HEADS)", dh);
+    STCAT_REQUIRE(B >= 0 && H > 0 && Lq >= 0 && Lk > 0, STCAT_EINVAL, "attention_fwd: bad sizes B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk);
+    STCAT_REQUIRE(B <= 65535 && H <= 65535, STCAT_ESHAPE, "attention_fwd: B/H exceed grid limits");
+    if (B == 0 || Lq == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == STCAT_F32)
+        return q2 ? launch_fwd<float, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st)
+                  : launch_fwd<float, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st);
+    if (dtype == STCAT_BF16)
+        return q2 ? launch_fwd<__nv_bfloat16, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st)
+                  : launch_fwd<__nv_bfloat16, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st);
+    return set_err(STCAT_EINVAL, "attention_fwd: bad dtype %d", dtype);
+}
+
+extern "C" int stcat_attention_bwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2,
+                                   int64_t ldk, const void* v, int64_t ldv, const void* d_o, int64_t lddo, int dtype,
+                                   const uint8_t* key_mask, const float* lse, const float* dp_avg, float* delta,
+                                   void* dq1, void* dq2, int64_t lddq, void* dk1, void* dk2, int64_t lddk, void* dv,
+                                   int64_t lddv, int B, int H, int Lq, int Lk, int dh, float scale, void* stream) {
+    STCAT_REQUIRE(q1 && k1 && v && d_o && lse && delta && dq1 && dk1 && dv, STCAT_EINVAL, "attention_bwd: null pointer");
+    STCAT_REQUIRE((q2 == nullptr) == (k2 == nullptr), STCAT_EINVAL, "attention_bwd: q2/k2 must both be set or both NULL");
+    STCAT_REQUIRE(!q2 || (dq2 && dk2), STCAT_EINVAL, "attention_bwd: dq2/dk2 required with q2/k2");
+    STCAT_REQUIRE(dh == DH, STCAT_ESHAPE, "attention_bwd: head dim %d unsupported (must be 32)", dh);
+    STCAT_REQUIRE(B >= 0 && H > 0 && Lq >= 0 && Lk > 0, STCAT_EINVAL, "attention_bwd: bad sizes");
+    STCAT_REQUIRE(B <= 65535 && H <= 65535, STCAT_ESHAPE, "attention_bwd: B/H exceed grid limits");
+    if (B == 0 || Lq == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == STCAT_F32)
+        return q2 ? launch_bwd<float, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st)
+                  : launch_bwd<float, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st);
+    if (dtype == STCAT_BF16)
+        return q2 ? launch_bwd<__nv_bfloat16, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st)
+                  : launch_bwd<__nv_bfloat16, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st);
+    return set_err(STCAT_EINVAL, "attention_bwd: bad dtype %d", dtype);
+}

@@ -1,0 +1,236 @@
+// HBM-bound element-wise helpers: 128-bit loads/stores, grid sized in multiples of the SM count.
+#include "common.cuh"
+
+namespace stcat {
+
+__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    return make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+}
+
+__global__ void __launch_bounds__(256)
+add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+           __nv_bfloat16* __restrict__ out_bf16, int64_t n4, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 x = reinterpret_cast<const float4*>(a)[i];
+        float4 y = reinterpret_cast<const float4*>(b)[i];
+        float4 z = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+        if (out) reinterpret_cast<float4*>(out)[i] = z;
+        if (out_bf16) reinterpret_cast<uint2*>(out_bf16)[i] = pack_bf16x4(z.x, z.y, z.z, z.w);
+    }
+    // tail (n not a multiple of 4)
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float z = a[i] + b[i];
+        if (out) out[i] = z;
+        if (out_bf16) out_bf16[i] = __float2bfloat16_rn(z);
+    }
+}
+
+template <typename TY, typename TD>
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const TY* __restrict__ y, TD* __restrict__ dy, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        if (!(to_f32<TY>(y[i]) > 0.f)) dy[i] = from_f32<TD>(0.f);
+}
+
+__global__ void __launch_bounds__(256)
+cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t n4, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 v = reinterpret_cast<const float4*>(x)[i];
+        reinterpret_cast<uint2*>(out)[i] = pack_bf16x4(v.x, v.y, v.z, v.w);
+    }
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = __float2bfloat16_rn(x[i]);
+}
+
+// out[c, r] = bf16(x[r, c]); 32x32 tiles through shared memory so both sides are coalesced
+__global__ void __launch_bounds__(256)
+cast_bf16_transpose_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t rows, int64_t cols) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+    for (int i = ty; i < 32; i += 8) {
+        int64_t r = r0 + i, c = c0 + tx;
+        tile[i][tx] = (r < rows && c < cols) ? x[r * cols + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        int64_t c = c0 + i, r = r0 + tx;
+        if (r < rows && c < cols) out[c * rows + r] = __float2bfloat16_rn(tile[tx][i]);
+    }
+}
+
+static int grid_for(int64_t work_items) {
+    int64_t blocks = (work_items + 255) / 256;
+    int64_t cap = (int64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sted scoring (post_processor.py:30-53): one block per video
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sted_score_kernel(const float* __restrict__ sted, const int32_t* __restrict__ durations, float* __restrict__ score,
+                  int32_t* __restrict__ best, int t) {
+    extern __shared__ float sm[];  // ls[t], le[t]
+    __shared__ float red[8];
+    __shared__ float redv[8];
+    __shared__ int redi[8];
+    float* ls = sm;
+    float* le = sm + t;
+    const int v = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* s = sted + (int64_t)v * t * 2;
+    const int dur = durations[v];
+    // log-softmax over ALL t positions (padded ones included, as in the reference), both channels
+    for (int ch = 0; ch < 2; ++ch) {
+        float mx = -INFINITY;
+        for (int i = tid; i < t; i += 256) mx = fmaxf(mx, s[i * 2 + ch]);
+        mx = warp_max(mx);
+        if (lane == 0) red[warp] = mx;
+        __syncthreads();
+        mx = red[0];
+        for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+        __syncthreads();
+        float sum = 0.f;
+        for (int i = tid; i < t; i += 256) sum += expf(s[i * 2 + ch] - mx);
+        sum = warp_sum(sum);
+        if (lane == 0) red[warp] = sum;
+        __syncthreads();
+        sum = 0.f;
+        for (int w = 0; w < 8; ++w) sum += red[w];
+        __syncthreads();
+        const float lz = mx + logf(sum);
+        float* dst = ch ? le : ls;
+        for (int i = tid; i < t; i += 256) dst[i] = s[i * 2 + ch] - lz;
+    }
+    __syncthreads();
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    const int tt = t * t;
+    for (int idx = tid; idx < tt; idx += 256) {
+        int i = idx / t, j = idx - i * t;
+        float pen = (j <= i || i >= dur || j >= dur) ? -1e32f : 0.f;
+        float val = pen + (ls[i] + le[j]);  // same association as the reference: mask + (ls + le)
+        if (score) score[(int64_t)v * tt + idx] = val;
+        if (val > bv || (val == bv && idx < bi)) { bv = val; bi = idx; }
+    }
+    // block arg-max, first index on ties
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { redv[warp] = bv; redi[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (redv[w] > bv || (redv[w] == bv && redi[w] < bi)) { bv = redv[w]; bi = redi[w]; }
+        best[v] = bi;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// map2d pooling (map2d_head.py:39-62): valid cell (i,j) = max_{i<=t<=j} x[B,t,c]; cascaded MaxPool1d
+// in the reference is exactly this range maximum (max is exact, so results are bit-identical).
+// One block per (B, i): thread = channel; walks j upward keeping a running max -> O(N) per row and
+// coalesced reads of x[B, j, :]; writes map[B, c, i, j] (strided by N*N over c: the layout the
+// reference's conv head expects).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+map2d_pool_kernel(const float* __restrict__ x, const uint8_t* __restrict__ valid, float* __restrict__ map, int N, int d) {
+    // block = (map row i, batch B, 256-channel slab); thread = channel for the running max (coalesced
+    // reads of x[B, j, c0:c0+256]); 32-column tiles are transposed through shared memory so that the
+    // writes map[B, c, i, j0:j0+32] are 128-byte segments.
+    __shared__ float tile[256][33];
+    const int bidx = blockIdx.y, i = blockIdx.x, c0 = blockIdx.z * 256;
+    const int c = c0 + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float run = -INFINITY;
+    for (int j0 = 0; j0 < N; j0 += 32) {
+#pragma unroll 4
+        for (int jj = 0; jj < 32; ++jj) {
+            const int j = j0 + jj;
+            float out = 0.f;
+            if (j < N && j >= i && c < d) {
+                run = fmaxf(run, x[((int64_t)bidx * N + j) * d + c]);
+                out = valid[i * N + j] ? run : 0.f;
+            }
+            tile[threadIdx.x][jj] = out;
+        }
+        __syncthreads();
+        for (int cc = warp; cc < 256; cc += 8) {
+            const int j = j0 + lane;
+            if (c0 + cc < d && j < N) map[(((int64_t)bidx * d + c0 + cc) * N + i) * N + j] = tile[cc][lane];
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace stcat
+
+using namespace stcat;
+
+extern "C" int stcat_add(const float* a, const float* b, float* out, void* out_bf16, int64_t n, void* stream) {
+    STCAT_REQUIRE(a && b && (out || out_bf16), STCAT_EINVAL, "add: null pointer");
+    STCAT_REQUIRE(n >= 0, STCAT_EINVAL, "add: n<0");
+    if (n == 0) return 0;
+    STCAT_REQUIRE(((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)out_bf16 % 8 == 0),
+                  STCAT_EALIGN, "add: pointers must be 16-byte aligned");
+    add_kernel<<<grid_for(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(a, b, out, (__nv_bfloat16*)out_bf16, n / 4, n);
+    return check_launch("add_kernel");
+}
+
+extern "C" int stcat_relu_bwd(const void* y, int y_dtype, void* dy, int dy_dtype, int64_t n, void* stream) {
+    STCAT_REQUIRE(y && dy, STCAT_EINVAL, "relu_bwd: null pointer");
+    if (n <= 0) return n == 0 ? 0 : set_err(STCAT_EINVAL, "relu_bwd: n<0");
+    cudaStream_t st = (cudaStream_t)stream;
+    int g = grid_for(n);
+    if (y_dtype == STCAT_F32 && dy_dtype == STCAT_F32)
+        relu_bwd_kernel<float, float><<<g, 256, 0, st>>>((const float*)y, (float*)dy, n);
+    else if (y_dtype == STCAT_BF16 && dy_dtype == STCAT_F32)
+        relu_bwd_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)y, (float*)dy, n);
+    else if (y_dtype == STCAT_BF16 && dy_dtype == STCAT_BF16)
+        relu_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)y, (__nv_bfloat16*)dy, n);
+    else
+        return set_err(STCAT_EINVAL, "relu_bwd: bad dtype %d/%d", y_dtype, dy_dtype);
+    return check_launch("relu_bwd_kernel");
+}
+
+extern "C" int stcat_cast_bf16(const float* x, void* out, int64_t rows, int64_t cols, int transpose, void* stream) {
+    STCAT_REQUIRE(x && out, STCAT_EINVAL, "cast_bf16: null pointer");
+    STCAT_REQUIRE(rows >= 0 && cols >= 0, STCAT_EINVAL, "cast_bf16: negative size");
+    if (rows == 0 || cols == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!transpose) {
+        int64_t n = rows * cols;
+        STCAT_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 8 == 0), STCAT_EALIGN, "cast_bf16: alignment");
+        cast_bf16_kernel<<<grid_for(n / 4 + 1), 256, 0, st>>>(x, (__nv_bfloat16*)out, n / 4, n);
+        return check_launch("cast_bf16_kernel");
+    }
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+    STCAT_REQUIRE(grid.y <= 65535, STCAT_ESHAPE, "cast_bf16: too many rows for transpose");
+    cast_bf16_transpose_kernel<<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)out, rows, cols);
+    return check_launch("cast_bf16_transpose_kernel");
+}
+
+extern "C" int stcat_sted_score(const float* sted, const int32_t* durations, float* score, int32_t* best, int b, int t,
+                                void* stream) {
+    STCAT_REQUIRE(sted && durations && best, STCAT_EINVAL, "sted_score: null pointer");
+    STCAT_REQUIRE(b >= 0 && t > 0 && t <= 4096, STCAT_ESHAPE, "sted_score: b=%d t=%d unsupported", b, t);
+    if (b == 0) return 0;
+    sted_score_kernel<<<b, 256, 2 * t * sizeof(float), (cudaStream_t)stream>>>(sted, durations, score, best, t);
+    return check_launch("sted_score_kernel");
+}
+
+extern "C" int stcat_map2d_pool(const float* x, const uint8_t* valid, float* map, int B, int N, int d, void* stream) {
+    STCAT_REQUIRE(x && valid && map, STCAT_EINVAL, "map2d_pool: null pointer");
+    STCAT_REQUIRE(B >= 0 && N > 0 && d > 0 && B <= 65535, STCAT_ESHAPE, "map2d_pool: bad sizes");
+    if (B == 0) return 0;
+    dim3 grid(N, B, (d + 255) / 256);
+    map2d_pool_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, valid, map, N, d);
+    return check_launch("map2d_pool_kernel");
+}

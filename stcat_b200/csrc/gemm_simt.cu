@@ -1,0 +1,145 @@
+// Exact-fp32 SIMT GEMM family behind stcat_linear_{fwd,bwd_data,bwd_weight} for fp32 operands.
+//
+// This is the *correctness* path: plain FFMA, fp32 accumulate, no TF32, so the
+// result matches the fp32 reference to summation-order rounding.  The production path for the same
+// entry points is the tcgen05/TMA bf16 kernel in gemm_tcgen05.cu; this kernel is also its on-device
+// checker.  C[m,n] = sum_k A(m,k) * B(n,k) with fully general element strides, which covers
+//   fwd        A = x  (k contiguous)        B = w  (k contiguous)
+//   bwd_data   A = dy (k = N contiguous)    B(k_out, n) = w[n, k_out]   (n index strided)
+//   bwd_weight A(n, m) = dy[m, n]           B(k, m) = x[m, k]           (both "m-major")
+#include "common.cuh"
+
+namespace stcat {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const TIn* __restrict__ A, int64_t sam, int64_t sak, const TIn* __restrict__ B, int64_t sbn,
+                 int64_t sbk, TOut* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int M, int N,
+                 int K, int relu, int accumulate) {
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const bool a_kfast = (sak == 1);
+    const bool b_kfast = (sbk == 1);
+    for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int idx = tid + i * 256;
+            int k, m;
+            if (a_kfast) { k = idx & 15; m = idx >> 4; } else { m = idx & 63; k = idx >> 6; }
+            int gm = m0 + m, gk = k0 + k;
+            float v = 0.f;
+            if (gm < M && gk < K) v = to_f32<TIn>(A[(int64_t)gm * sam + (int64_t)gk * sak]);
+            As[k][m] = v;
+            int n;
+            if (b_kfast) { k = idx & 15; n = idx >> 4; } else { n = idx & 63; k = idx >> 6; }
+            int gn = n0 + n;
+            gk = k0 + k;
+            v = 0.f;
+            if (gn < N && gk < K) v = to_f32<TIn>(B[(int64_t)gn * sbn + (int64_t)gk * sbk]);
+            Bs[k][n] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            float av[4] = {a.x, a.y, a.z, a.w};
+            float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            float v = acc[i][j];
+            if (bias) v += bias[gn];
+            TOut* p = C + (int64_t)gm * ldc + gn;
+            if (accumulate) v += to_f32<TOut>(*p);
+            if (relu) v = fmaxf(v, 0.f);
+            *p = from_f32<TOut>(v);
+        }
+    }
+}
+
+// db[n] += sum_m dy[m, n]
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ dy, int64_t ld, float* __restrict__ db,
+                                                     int M, int N, int rows_per_block) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + tx;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(M, r0 + rows_per_block);
+    float s = 0.f;
+    if (n < N)
+        for (int r = r0 + ty; r < r1; r += 8) s += to_f32<T>(dy[(int64_t)r * ld + n]);
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][tx];
+        atomicAdd(db + n, t);
+    }
+}
+
+template <typename TIn, typename TOut>
+static int launch_gemm(const void* A, int64_t sam, int64_t sak, const void* B, int64_t sbn, int64_t sbk, void* C,
+                       int64_t ldc, const float* bias, int M, int N, int K, int relu, int accumulate,
+                       cudaStream_t st) {
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+    gemm_simt_kernel<TIn, TOut><<<grid, 256, 0, st>>>((const TIn*)A, sam, sak, (const TIn*)B, sbn, sbk, (TOut*)C,
+                                                      ldc, bias, M, N, K, relu, accumulate);
+    return check_launch("gemm_simt_kernel");
+}
+
+int gemm_simt(const void* A, int64_t sam, int64_t sak, const void* B, int64_t sbn, int64_t sbk, int in_dtype,
+              void* C, int64_t ldc, int out_dtype, const float* bias, int M, int N, int K, int relu,
+              int accumulate, cudaStream_t st) {
+    if (in_dtype == STCAT_F32 && out_dtype == STCAT_F32)
+        return launch_gemm<float, float>(A, sam, sak, B, sbn, sbk, C, ldc, bias, M, N, K, relu, accumulate, st);
+    if (in_dtype == STCAT_BF16 && out_dtype == STCAT_F32)
+        return launch_gemm<__nv_bfloat16, float>(A, sam, sak, B, sbn, sbk, C, ldc, bias, M, N, K, relu, accumulate, st);
+    if (in_dtype == STCAT_BF16 && out_dtype == STCAT_BF16)
+        return launch_gemm<__nv_bfloat16, __nv_bfloat16>(A, sam, sak, B, sbn, sbk, C, ldc, bias, M, N, K, relu,
+                                                         accumulate, st);
+    if (in_dtype == STCAT_F32 && out_dtype == STCAT_BF16)
+        return launch_gemm<float, __nv_bfloat16>(A, sam, sak, B, sbn, sbk, C, ldc, bias, M, N, K, relu, accumulate, st);
+    return set_err(STCAT_EINVAL, "gemm_simt: bad dtype %d/%d", in_dtype, out_dtype);
+}
+
+int colsum(const void* dy, int64_t ld, int dtype, float* db, int M, int N, int accumulate, cudaStream_t st) {
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(db, 0, sizeof(float) * N, st);
+        if (e != cudaSuccess) return set_err((int)e, "colsum memset: %s", cudaGetErrorString(e));
+    }
+    int rows_per_block = 512;
+    dim3 grid((N + 31) / 32, (M + rows_per_block - 1) / rows_per_block);
+    if (dtype == STCAT_F32)
+        colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, ld, db, M, N, rows_per_block);
+    else
+        colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, ld, db, M, N, rows_per_block);
+    return check_launch("colsum_kernel");
+}
+
+}  // namespace stcat

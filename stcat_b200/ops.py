@@ -1,0 +1,281 @@
+"""autograd operators of the hot path: each one is a forward/backward pair of C-ABI kernels.
+
+These replace the torch.nn calls the reference makes (nn.Linear, nn.LayerNorm, the bmm/softmax/bmm
+core of nn.MultiheadAttention and of the reference's own attention.py).  They are composed by
+``encoder.py`` / ``decoder.py`` into modules with the reference's interface.
+
+Precision:
+  * ``"fp32"``: exact-fp32 SIMT kernels; gated <= 1e-3 (measured ~1e-5) against the fp32 reference.
+  * ``"bf16"``: GEMM / attention operands rounded to bf16 (tcgen05 tensor cores, fp32 accumulation),
+    fp32 residual stream, LayerNorm and softmax statistics.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+_backend = None
+_precision = "fp32"
+
+
+def get_backend():
+    global _backend
+    if _backend is None:
+        from .cabi import CudaBackend
+
+        _backend = CudaBackend()
+    return _backend
+
+
+def set_backend(b):
+    """Install a backend object.  Product code never calls this; tests use it to drive the host-side
+    composition with the torch-CPU emulation in tests/emu_backend.py."""
+    global _backend
+    _backend = b
+
+
+def set_precision(p: str):
+    global _precision
+    if p not in ("fp32", "bf16"):
+        raise ValueError(f"precision must be 'fp32' or 'bf16', got {p!r}")
+    _precision = p
+
+
+def get_precision() -> str:
+    return _precision
+
+
+# bf16 shadows of the fp32 master weights, refreshed when the parameter changes (optimizer.step bumps
+# ``_version``); keyed by storage pointer so slices of a packed in_proj_weight get their own entry.
+_wcache = {}
+
+
+def clear_weight_cache():
+    _wcache.clear()
+
+
+def _operand(t: torch.Tensor, is_weight: bool = False) -> torch.Tensor:
+    """GEMM operand in the active precision (2-D, row-major)."""
+    if _precision == "fp32" or t.dtype == torch.bfloat16:
+        return t
+    be = get_backend()
+    if is_weight:
+        key = (t.data_ptr(), tuple(t.shape), t.stride(0))
+        hit = _wcache.get(key)
+        if hit is not None and hit[0] == t._version:
+            return hit[1]
+    src = t if t.is_contiguous() else t.contiguous()
+    out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    be.cast_bf16(src, out)
+    if is_weight:
+        _wcache[key] = (t._version, out)
+    return out
+
+
+def _rows(x: torch.Tensor, k: int) -> torch.Tensor:
+    """[..., k] -> contiguous-row 2-D view [M, k] (copy only if rows are not unit-stride)."""
+    x2 = x.reshape(-1, k)
+    if x2.shape[0] > 0 and (x2.stride(1) != 1 or (x2.shape[0] > 1 and x2.stride(0) < k)):
+        x2 = x2.contiguous()
+    return x2
+
+
+class LinearFn(Function):
+    """y = act(x W^T + b)"""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu: bool, out_bf16: bool):
+        be = get_backend()
+        N, K = weight.shape
+        x2 = _rows(x.detach(), K)
+        xo = _operand(x2)
+        wo = _operand(weight.detach(), True)
+        M = x2.shape[0]
+        odt = torch.bfloat16 if (out_bf16 and _precision == "bf16") else torch.float32
+        y = torch.empty(M, N, dtype=odt, device=x.device)
+        be.linear_fwd(xo, wo, None if bias is None else bias.detach(), y, relu=relu)
+        ctx.relu = relu
+        ctx.x_shape = x.shape
+        ctx.x_dtype = x.dtype
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(xo, weight, y if relu else None)
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        be = get_backend()
+        xo, weight, y = ctx.saved_tensors
+        N, K = weight.shape
+        dy2 = _rows(dy, N)
+        if ctx.relu:
+            dy2 = dy2.clone() if dy2.data_ptr() == dy.data_ptr() else dy2
+            be.relu_bwd(y, dy2)
+        dyo = _operand(dy2)
+        M = dy2.shape[0]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, K, dtype=ctx.x_dtype, device=dy.device)
+            be.linear_bwd_data(dyo, _operand(weight.detach(), True), dx)
+            dx = dx.view(ctx.x_shape)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty(N, K, dtype=torch.float32, device=dy.device)
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                db = torch.empty(N, dtype=torch.float32, device=dy.device)
+            be.linear_bwd_weight(dyo, xo, dw, db)
+        return dx, dw, db, None, None
+
+
+def linear(x, weight, bias=None, relu: bool = False, out_bf16: bool = False):
+    return LinearFn.apply(x, weight, bias, relu, out_bf16)
+
+
+class LayerNormFn(Function):
+    """y = LayerNorm(x + res) over the last dim (d = 256), eps 1e-5; fp32 in / out."""
+
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, eps: float):
+        be = get_backend()
+        d = x.shape[-1]
+        x2 = _rows(x.detach().float(), d)
+        x2 = x2 if x2.is_contiguous() else x2.contiguous()
+        r2 = None
+        if res is not None:
+            r2 = _rows(res.detach().float(), d)
+            r2 = r2 if r2.is_contiguous() else r2.contiguous()
+        rows = x2.shape[0]
+        y = torch.empty(rows, d, dtype=torch.float32, device=x.device)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        be.layernorm_fwd(x2, r2, gamma.detach(), beta.detach(), y, None, mean, rstd, eps)
+        ctx.save_for_backward(x2, r2, gamma, mean, rstd)
+        ctx.shape = x.shape
+        ctx.dtypes = (x.dtype, None if res is None else res.dtype)
+        return y.view(x.shape)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        be = get_backend()
+        x2, r2, gamma, mean, rstd = ctx.saved_tensors
+        d = x2.shape[1]
+        dy2 = _rows(dy, d)
+        dy2 = dy2 if dy2.is_contiguous() else dy2.contiguous()
+        dz = torch.empty_like(x2)
+        dg = torch.zeros(d, dtype=torch.float32, device=dy.device)
+        db = torch.zeros(d, dtype=torch.float32, device=dy.device)
+        be.layernorm_bwd(dy2, x2, r2, gamma.detach(), mean, rstd, dz, dg, db)
+        dzv = dz.view(ctx.shape)
+        dx = dzv.to(ctx.dtypes[0]) if ctx.needs_input_grad[0] else None
+        dr = dzv.to(ctx.dtypes[1]) if (r2 is not None and ctx.needs_input_grad[1]) else None
+        return dx, dr, dg, db, None
+
+
+def layer_norm(x, res, gamma, beta, eps: float = 1e-5):
+    return LayerNormFn.apply(x, res, gamma, beta, eps)
+
+
+class AttentionFn(Function):
+    """Batch-major multi-head attention core; see include/stcat_b200.h (stcat_attention_fwd)."""
+
+    @staticmethod
+    def forward(ctx, q1, q2, k1, k2, v, key_mask, B, H, Lq, Lk, scale, need_pavg):
+        be = get_backend()
+        E = H * 32
+        two = q2 is not None
+
+        def prep(t, L):
+            t2 = t.detach()
+            assert t2.shape == (B * L, E), (t2.shape, B, L, E)
+            if _precision == "bf16" and t2.dtype != torch.bfloat16:
+                t2 = _operand(t2)
+            elif t2.stride(1) != 1:
+                t2 = t2.contiguous()
+            return t2
+
+        tq1, tk1, tv = prep(q1, Lq), prep(k1, Lk), prep(v, Lk)
+        tq2, tk2 = (prep(q2, Lq), prep(k2, Lk)) if two else (None, None)
+        if two:  # the kernel takes one leading dimension per operand pair
+            if tq2.stride(0) != tq1.stride(0):
+                tq1, tq2 = tq1.contiguous(), tq2.contiguous()
+            if tk2.stride(0) != tk1.stride(0):
+                tk1, tk2 = tk1.contiguous(), tk2.contiguous()
+        o = torch.empty(B * Lq, E, dtype=tq1.dtype, device=q1.device)
+        lse = torch.empty(B, H, Lq, dtype=torch.float32, device=q1.device)
+        pavg = torch.zeros(B, Lq, Lk, dtype=torch.float32, device=q1.device) if need_pavg else None
+        be.attention_fwd(tq1, tq2, tk1, tk2, tv, o, key_mask, lse, pavg, B, H, Lq, Lk, scale)
+        ctx.save_for_backward(tq1, tq2, tk1, tk2, tv, key_mask, lse)
+        ctx.dims = (B, H, Lq, Lk, scale)
+        ctx.in_dtypes = (q1.dtype, k1.dtype, v.dtype)
+        if need_pavg:
+            return o, pavg
+        ctx.mark_non_differentiable()
+        return o, None
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_o, d_pavg):
+        be = get_backend()
+        tq1, tq2, tk1, tk2, tv, key_mask, lse = ctx.saved_tensors
+        B, H, Lq, Lk, scale = ctx.dims
+        E = H * 32
+        two = tq2 is not None
+        dt = tq1.dtype
+        g = d_o.detach()
+        if g.dtype != dt:
+            g = _operand(g) if dt == torch.bfloat16 else g.float()
+        g = _rows(g, E)
+        if d_pavg is not None:
+            d_pavg = d_pavg.contiguous().float()
+        delta = torch.empty(B, H, Lq, dtype=torch.float32, device=g.device)
+        mk = lambda L: torch.empty(B * L, E, dtype=dt, device=g.device)
+        dq1, dk1, dv = mk(Lq), mk(Lk), mk(Lk)
+        dq2, dk2 = (mk(Lq), mk(Lk)) if two else (None, None)
+        be.attention_bwd(tq1, tq2, tk1, tk2, tv, g, key_mask, lse, d_pavg, delta, dq1, dq2, dk1, dk2, dv, B, H, Lq, Lk,
+                         scale)
+        qd, kd, vd = ctx.in_dtypes
+        cast = lambda t, d: None if t is None else (t if t.dtype == d else t.to(d))
+        return (cast(dq1, qd), cast(dq2, qd), cast(dk1, kd), cast(dk2, kd), cast(dv, vd), None, None, None, None, None,
+                None, None)
+
+
+def attention(q1, k1, v, B, H, Lq, Lk, scale, key_mask=None, q2=None, k2=None, need_pavg=False):
+    """Returns (o [B*Lq, H*32], p_avg [B,Lq,Lk] or None).  key_mask: uint8 [B, Lk], nonzero = masked."""
+    return AttentionFn.apply(q1, q2, k1, k2, v, key_mask, B, H, Lq, Lk, float(scale), need_pavg)
+
+
+class AddFn(Function):
+    """out = a + b for same-shape contiguous fp32 tensors (q = k = src + pos)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        be = get_backend()
+        a2 = a.detach().contiguous()
+        b2 = b.detach().contiguous()
+        out = torch.empty_like(a2)
+        be.add(a2, b2, out, None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def add(a, b):
+    assert a.shape == b.shape and a.dtype == torch.float32 and b.dtype == torch.float32
+    return AddFn.apply(a, b)
+
+
+def sted_score(pred_sted: torch.Tensor, durations, return_map: bool = False):
+    """Temporal start/end scoring (post_processor.py:30-53).  Returns (best flat index [b] int32 on
+    device, score map or None)."""
+    be = get_backend()
+    b, t, _ = pred_sted.shape
+    dur = torch.as_tensor(list(durations), dtype=torch.int32).to(pred_sted.device, non_blocking=True)
+    score = torch.empty(b, t, t, dtype=torch.float32, device=pred_sted.device) if return_map else None
+    best = torch.empty(b, dtype=torch.int32, device=pred_sted.device)
+    be.sted_score(pred_sted.detach().float().contiguous(), dur, score, best)
+    return best, score

@@ -1,0 +1,217 @@
+"""-m gpu: every C-ABI entry point against a CPU (oracle / torch float64) reference of the same op.
+
+Tolerances are written next to each check.  fp32 kernels: 2e-5 relative (summation order only)."""
+import math
+
+import pytest
+import torch
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL32 = 2e-5
+
+
+@pytest.fixture(scope="module")
+def be():
+    from stcat_b200.cabi import CudaBackend
+
+    b = CudaBackend()
+    assert b.lib.stcat_device_arch() >= 100, "expected a Blackwell (sm_100) device"
+    return b
+
+
+def g(*shape, seed=0, scale=1.0):
+    gen = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=gen) * scale
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 4, 256), (64, 256, 256), (213 * 3, 96, 70), (500, 2048, 256), (129, 256, 2048)])
+def test_linear_fp32(be, M, N, K):
+    x, w, b = g(M, K, seed=1), g(N, K, seed=2, scale=K ** -0.5), g(N, seed=3)
+    dy = g(M, N, seed=4)
+    xd, wd, bd, dyd = x.cuda(), w.cuda(), b.cuda(), dy.cuda()
+    ref = x.double() @ w.double().t() + b.double()
+    y = torch.empty(M, N, device="cuda")
+    be.linear_fwd(xd, wd, bd, y)
+    assert rel_err(y, ref) < TOL32
+    be.linear_fwd(xd, wd, bd, y, relu=True)
+    assert rel_err(y, ref.relu()) < TOL32
+    y2 = torch.ones(M, N, device="cuda")
+    be.linear_fwd(xd, wd, None, y2, accumulate=True)
+    assert rel_err(y2, ref - b.double() + 1) < TOL32
+    dx = torch.empty(M, K, device="cuda")
+    be.linear_bwd_data(dyd, wd, dx)
+    assert rel_err(dx, dy.double() @ w.double()) < TOL32
+    dw = torch.empty(N, K, device="cuda")
+    db = torch.empty(N, device="cuda")
+    be.linear_bwd_weight(dyd, xd, dw, db)
+    assert rel_err(dw, dy.double().t() @ x.double()) < TOL32
+    assert rel_err(db, dy.double().sum(0)) < TOL32
+    be.linear_bwd_weight(dyd, xd, dw, db, accumulate=True)
+    assert rel_err(dw, 2 * (dy.double().t() @ x.double())) < TOL32
+    assert rel_err(db, 2 * dy.double().sum(0)) < TOL32
+
+
+def test_linear_strided_views(be):
+    """column slices of a wider buffer (packed in_proj outputs) and row slices of a packed weight"""
+    M, K = 77, 256
+    x = g(M, K, seed=5).cuda()
+    w = g(768, K, seed=6, scale=1 / 16).cuda()
+    buf = torch.zeros(M, 768, device="cuda")
+    be.linear_fwd(x, w[:512], None, buf[:, :512])
+    be.linear_fwd(x, w[512:], None, buf[:, 512:])
+    assert rel_err(buf, x.cpu().double() @ w.cpu().double().t()) < TOL32
+    dx = torch.empty(M, K, device="cuda")
+    be.linear_bwd_data(buf[:, 256:512], w[256:512], dx)
+    assert rel_err(dx, buf[:, 256:512].cpu().double() @ w[256:512].cpu().double()) < TOL32
+
+
+@pytest.mark.parametrize("rows", [1, 7, 1000, 13632])
+def test_layernorm(be, rows):
+    d = 256
+    x, r = g(rows, d, seed=1), g(rows, d, seed=2)
+    gm, bt = 1 + 0.1 * g(d, seed=3), 0.1 * g(d, seed=4)
+    dy = g(rows, d, seed=5)
+    xd, rd = x.double().requires_grad_(True), r.double().requires_grad_(True)
+    gd, bd = gm.double().requires_grad_(True), bt.double().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xd + rd, (d,), gd, bd, 1e-5)
+    ref.backward(dy.double())
+    y = torch.empty(rows, d, device="cuda")
+    yb = torch.empty(rows, d, device="cuda", dtype=torch.bfloat16)
+    mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    be.layernorm_fwd(x.cuda(), r.cuda(), gm.cuda(), bt.cuda(), y, yb, mean, rstd)
+    assert rel_err(y, ref) < TOL32
+    assert torch.equal(yb, y.to(torch.bfloat16))
+    dz = torch.empty(rows, d, device="cuda")
+    dg, dbt = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+    be.layernorm_bwd(dy.cuda(), x.cuda(), r.cuda(), gm.cuda(), mean, rstd, dz, dg, dbt)
+    assert rel_err(dz, xd.grad) < TOL32
+    assert rel_err(dg, gd.grad) < 1e-4  # atomics over many rows
+    assert rel_err(dbt, bd.grad) < 1e-4
+    # no residual
+    be.layernorm_fwd(x.cuda(), None, gm.cuda(), bt.cuda(), y, None, mean, rstd)
+    assert rel_err(y, torch.nn.functional.layer_norm(x.double(), (d,), gm.double(), bt.double(), 1e-5)) < TOL32
+
+
+def attn_ref(q1, q2, k1, k2, v, mask, B, H, Lq, Lk, scale):
+    """float64 batch-major reference with the same contract as stcat_attention_fwd"""
+    def heads(t, L):
+        return t.view(B, L, H, 32).permute(0, 2, 1, 3)
+
+    s = heads(q1, Lq) @ heads(k1, Lk).transpose(-1, -2)
+    if q2 is not None:
+        s = s + heads(q2, Lq) @ heads(k2, Lk).transpose(-1, -2)
+    s = s * scale
+    if mask is not None:
+        s = s.masked_fill(mask.bool()[:, None, None, :], float("-inf"))
+    p = torch.softmax(s, -1)
+    o = (p @ heads(v, Lk)).permute(0, 2, 1, 3).reshape(B * Lq, H * 32)
+    return o, p.mean(1), torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,two,use_mask,use_pavg", [
+    (3, 8, 50, 77, False, True, False),
+    (2, 8, 213, 213, False, False, False),
+    (5, 8, 1, 212, True, True, False),
+    (2, 8, 65, 65, False, True, True),
+    (2, 4, 17, 130, True, True, True),
+])
+def test_attention_fp32(be, B, H, Lq, Lk, two, use_mask, use_pavg):
+    E = H * 32
+    scale = (64 if two else 32) ** -0.5
+    t = lambda L, s: g(B * L, E, seed=s)
+    q1, k1, v = t(Lq, 1), t(Lk, 2), t(Lk, 3)
+    q2, k2 = (t(Lq, 4), t(Lk, 5)) if two else (None, None)
+    mask = None
+    if use_mask:
+        mask = torch.zeros(B, Lk, dtype=torch.uint8)
+        for b in range(B):
+            mask[b, Lk - 1 - 3 * b:] = 1
+            mask[b, 0] = 0
+    d_o = t(Lq, 6)
+    dpavg = g(B, Lq, Lk, seed=7) if use_pavg else None
+    leaves = [x.double().requires_grad_(True) if x is not None else None for x in (q1, q2, k1, k2, v)]
+    o_ref, pavg_ref, lse_ref = attn_ref(*leaves, mask, B, H, Lq, Lk, scale)
+    loss = (o_ref * d_o.double()).sum()
+    if use_pavg:
+        loss = loss + (pavg_ref * dpavg.double()).sum()
+    loss.backward()
+
+    c = lambda x: None if x is None else x.cuda()
+    o = torch.empty(B * Lq, E, device="cuda")
+    lse = torch.empty(B, H, Lq, device="cuda")
+    pavg = torch.zeros(B, Lq, Lk, device="cuda") if use_pavg else None
+    be.attention_fwd(c(q1), c(q2), c(k1), c(k2), c(v), o, c(mask), lse, pavg, B, H, Lq, Lk, scale)
+    assert rel_err(o, o_ref) < TOL32
+    assert rel_err(lse, lse_ref) < TOL32
+    if use_pavg:
+        assert rel_err(pavg, pavg_ref) < TOL32
+    delta = torch.empty(B, H, Lq, device="cuda")
+    e = lambda L: torch.empty(B * L, E, device="cuda")
+    dq1, dk1, dv = e(Lq), e(Lk), e(Lk)
+    dq2, dk2 = (e(Lq), e(Lk)) if two else (None, None)
+    be.attention_bwd(c(q1), c(q2), c(k1), c(k2), c(v), c(d_o), c(mask), lse, c(dpavg), delta, dq1, dq2, dk1, dk2, dv,
+                     B, H, Lq, Lk, scale)
+    tol = 5e-5
+    assert rel_err(dq1, leaves[0].grad) < tol
+    assert rel_err(dk1, leaves[2].grad) < tol
+    assert rel_err(dv, leaves[4].grad) < tol
+    if two:
+        assert rel_err(dq2, leaves[1].grad) < tol
+        assert rel_err(dk2, leaves[3].grad) < tol
+
+
+def test_elementwise(be):
+    a, b = g(1001, 256, seed=1), g(1001, 256, seed=2)
+    out = torch.empty(1001, 256, device="cuda")
+    ob = torch.empty(1001, 256, device="cuda", dtype=torch.bfloat16)
+    be.add(a.cuda(), b.cuda(), out, ob)
+    assert torch.equal(out.cpu(), a + b)
+    assert torch.equal(ob.cpu(), (a + b).to(torch.bfloat16))
+    y = g(333, 2048, seed=3).relu()
+    dy = g(333, 2048, seed=4)
+    dyd = dy.cuda()
+    be.relu_bwd(y.cuda(), dyd)
+    assert torch.equal(dyd.cpu(), dy * (y > 0))
+    x = g(300, 70, seed=5)
+    o1 = torch.empty(300, 70, device="cuda", dtype=torch.bfloat16)
+    o2 = torch.empty(70, 300, device="cuda", dtype=torch.bfloat16)
+    be.cast_bf16(x.cuda(), o1)
+    be.cast_bf16(x.cuda(), o2, transpose=True)
+    assert torch.equal(o1.cpu(), x.to(torch.bfloat16))
+    assert torch.equal(o2.cpu(), x.t().to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("b,t,durs", [(1, 64, [64]), (3, 20, [20, 7, 1]), (2, 300, [300, 123])])
+def test_sted_score(be, b, t, durs):
+    from oracle import stcat_oracle as O
+
+    sted = g(b, t, 2, seed=9, scale=3.0)
+    boxes = torch.rand(b * t, 4)
+    sizes = torch.ones(b * t, 2)
+    frames = [list(range(t)) for _ in range(b)]
+    _, steds, score_ref = O.post_process(sted, boxes, sizes, frames, durs)
+    score = torch.empty(b, t, t, device="cuda")
+    best = torch.empty(b, dtype=torch.int32, device="cuda")
+    be.sted_score(sted.cuda(), torch.tensor(durs, dtype=torch.int32, device="cuda"), score, best)
+    valid = score_ref > -1e31
+    assert torch.allclose(score.cpu()[valid], score_ref[valid], rtol=1e-5, atol=1e-5)
+    assert bool((score.cpu()[~valid] < -1e31).all())
+    for i in range(b):
+        idx = int(best[i])
+        if durs[i] > 1:  # with a single valid frame every cell is masked; the reference argmax is then arbitrary (0)
+            assert [idx // t, idx % t + 1] == steds[i]
+
+
+def test_map2d_pool(be):
+    from oracle import stcat_oracle as O
+
+    N, counts, d, B = 32, [7, 4, 4], 256, 3
+    x = g(B, N, d, seed=11)
+    ref = O.gen_2d_map(x, N, counts)
+    mask2d, _, _ = O.map2d_masks(N, counts)
+    out = torch.empty(B, d, N, N, device="cuda")
+    be.map2d_pool(x.cuda(), mask2d.to(torch.uint8).cuda(), out)
+    assert torch.equal(out.cpu(), ref)
