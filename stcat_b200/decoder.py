@@ -1,0 +1,339 @@
+"""B200 query decoder: drop-in for the reference ``build_decoder(cfg)``.
+
+Interface mirrored (reference models/grounding_model/query_decoder.py):
+  ``QueryDecoder(cfg).forward(memory_cache, vis_pos=None, text_cls=None)
+      -> ([hs [nl,b,t,d], reference [nl,b,t,4]], (time_hs [nl,b,t,d], weights [nl,b,t,t]))`` (:83-147),
+  ``self.decoder.bbox_embed`` assigned from outside (pipeline.py:50), and the state_dict keys of
+  SURVEY.md 8b.
+
+Layout: queries are kept batch-major ``[b*t, d]`` (row = video * t + frame slot) and the encoder
+memory frame-major ``[n*M, d]`` (row = frame * M + token), so the time-aligned cross attention
+(one query per frame against the M = HW+L tokens of that frame, query_decoder.py:350-429, 615-651) is
+a batch of n single-query attentions over contiguous key blocks; the per-head concat
+[content(32) ; positional(32)] of the box decoder is never materialised (two-part score in the
+attention kernel).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from .encoder import batch_indices, _check_cfg
+from .params import LinearP, MHAP, MLPP, NormP, OutProjOnly, SineTable, LearnedTable, xavier_reset
+
+_const_cache = {}
+
+
+def _anchor_freq(device) -> torch.Tensor:
+    key = ("anchor_freq", str(device))
+    t = _const_cache.get(key)
+    if t is None:
+        k = torch.arange(128, dtype=torch.float32, device=device)
+        t = 10000 ** (2 * torch.div(k, 2, rounding_mode="floor") / 128)
+        _const_cache[key] = t
+    return t
+
+
+def anchor_sine_embed(anchor: torch.Tensor) -> torch.Tensor:
+    """[..., 4] (cx, cy, w, h) -> [..., 512] ordered (y, x, w, h); 128 dims per coordinate, sin on even /
+    cos on odd dims of 2*pi*c / 10000^(2*floor(k/2)/128)  (net_utils.py:29-56)."""
+    p = (anchor * (2 * math.pi))[..., None] / _anchor_freq(anchor.device)  # [..., 4, 128]
+    e = torch.stack((p[..., 0::2].sin(), p[..., 1::2].cos()), dim=-1).flatten(-2)  # [..., 4, 128]
+    return torch.cat((e[..., 1, :], e[..., 0, :], e[..., 2, :], e[..., 3, :]), dim=-1)
+
+
+def inverse_sigmoid(x: torch.Tensor, eps: float = 1e-3) -> torch.Tensor:
+    """clamped logit (net_utils.py:59-63)."""
+    x = x.clamp(min=0, max=1)
+    return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
+
+
+def run_mlp(m: MLPP, x: torch.Tensor, training: bool = False) -> torch.Tensor:
+    """Linear-ReLU stack (net_utils.py:20-26)."""
+    p = getattr(m, "dropout_p", None)
+    if p is None:  # the reference's own MLP module (net_utils.py:7-19) assigned from outside
+        dm = getattr(m, "dropout", 0)
+        p = dm.p if isinstance(dm, nn.Dropout) else float(dm or 0)
+    for i, layer in enumerate(m.layers):
+        x = ops.linear(x, layer.weight, layer.bias, relu=i < m.num_layers - 1)
+        if training and p:
+            # the reference applies dropout after EVERY layer of temp_embed / action_embed, the output
+            # layer included (net_utils.py:23-25, p = 0.3 hard-wired at pipeline.py:42-47).  These are
+            # [nl*b*t, <=256] tensors; the mask comes from torch's Philox stream like the reference's.
+            x = torch.nn.functional.dropout(x, p, True)
+    return x
+
+
+def _lin(p: LinearP, x, **kw):
+    return ops.linear(x, p.weight, p.bias, **kw)
+
+
+def _mha_weights(a: MHAP):
+    d = a.embed_dim
+    W, b = a.in_proj_weight, a.in_proj_bias
+    return (W[:d], b[:d]), (W[d:2 * d], b[d:2 * d]), (W[2 * d:], b[2 * d:])
+
+
+class _Ctx:
+    """Per-forward shared tensors of the decoder (memory-side operands are built once and reused by all
+    12 layers)."""
+
+    def __init__(self, idx, mem, mem_pos, key_mask, n_mem_tokens):
+        self.idx = idx
+        self.b, self.t, self.n = idx["b"], idx["t"], idx["n"]
+        self.M = n_mem_tokens
+        self.key_mask = key_mask
+        self.query_mask = idx["query_mask"]
+        self.mem_op = ops.to_operand(mem)  # [n*M, d]
+        self.pos_op = ops.to_operand(mem_pos)
+        self.mempos_op = ops.add(mem, mem_pos, as_operand=True)
+
+    def frames(self, x):
+        """padded [b*t, c] -> frames [n, c]"""
+        return x if self.idx["identity"] else x.index_select(0, self.idx["dec_scatter"])
+
+    def padded(self, x):
+        """frames [n, c] -> zero-padded [b*t, c]"""
+        if self.idx["identity"]:
+            return x
+        return torch.cat([x, x.new_zeros(1, x.shape[1])], 0).index_select(0, self.idx["dec_gather"])
+
+
+class TransformerDecoderLayer(nn.Module):
+    """Box-decoder layer parameters + forward (query_decoder.py:250-438, FROM_SCRATCH branch)."""
+
+    def __init__(self, d: int, nhead: int, ffn: int, first: bool):
+        super().__init__()
+        for nm in ("sa_qcontent_proj", "sa_qpos_proj", "sa_qtime_proj", "sa_kcontent_proj", "sa_kpos_proj",
+                   "sa_ktime_proj", "sa_v_proj"):
+            setattr(self, nm, LinearP(d, d))
+        self.self_attn = MHAP(d, nhead)
+        self.ca_qcontent_proj = LinearP(d, d)
+        self.ca_qpos_proj = LinearP(d, d) if first else None  # layers >= 1: None (query_decoder.py:166-167)
+        for nm in ("ca_kcontent_proj", "ca_kpos_proj", "ca_qtime_proj", "ca_v_proj", "ca_qpos_sine_proj"):
+            setattr(self, nm, LinearP(d, d))
+        self.cross_attn = OutProjOnly(d)
+        self.linear1 = LinearP(d, ffn)
+        self.linear2 = LinearP(ffn, d)
+        self.norm1, self.norm3, self.norm4 = NormP(d), NormP(d), NormP(d)
+        self.nhead = nhead
+        self.d = d
+
+    def run(self, c: _Ctx, tgt, query_pos, query_time, query_sine, is_first: bool):
+        d, H = self.d, self.nhead
+        # ---- temporal self attention over the t queries of each video (:329-345) ----
+        q = ops.linear_sum([(tgt, self.sa_qcontent_proj.weight, self.sa_qcontent_proj.bias),
+                            (query_time, self.sa_qtime_proj.weight, self.sa_qtime_proj.bias),
+                            (query_pos, self.sa_qpos_proj.weight, self.sa_qpos_proj.bias)])
+        k = ops.linear_sum([(tgt, self.sa_kcontent_proj.weight, self.sa_kcontent_proj.bias),
+                            (query_time, self.sa_ktime_proj.weight, self.sa_ktime_proj.bias),
+                            (query_pos, self.sa_kpos_proj.weight, self.sa_kpos_proj.bias)])
+        v = _lin(self.sa_v_proj, tgt)
+        (wq, bq), (wk, bk), (wv, bv) = _mha_weights(self.self_attn)
+        Q = ops.linear(q, wq, bq, out_bf16=True)
+        K = ops.linear(k, wk, bk, out_bf16=True)
+        V = ops.linear(v, wv, bv, out_bf16=True)
+        o, _ = ops.attention(Q, K, V, c.b, H, c.t, c.t, float(d // H) ** -0.5, key_mask=c.query_mask)
+        a = _lin(self.self_attn.out_proj, o)
+        tgt = ops.layer_norm(a, tgt, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        # ---- time-aligned cross attention: query of frame f sees only frame f's tokens (:350-429) ----
+        kp = _lin(self.ca_kpos_proj, c.pos_op, out_bf16=True)  # [n*M, d]
+        vv = _lin(self.ca_v_proj, c.mem_op, out_bf16=True)
+        if is_first:
+            qc = ops.linear_sum([(tgt, self.ca_qcontent_proj.weight, self.ca_qcontent_proj.bias),
+                                 (query_pos, self.ca_qpos_proj.weight, self.ca_qpos_proj.bias)])
+            kc = ops.linear_sum([(c.mem_op, self.ca_kcontent_proj.weight, self.ca_kcontent_proj.bias),
+                                 (c.pos_op, self.ca_kpos_proj.weight, self.ca_kpos_proj.bias)], out_bf16=True)
+        else:
+            qc = _lin(self.ca_qcontent_proj, tgt)
+            kc = _lin(self.ca_kcontent_proj, c.mem_op, out_bf16=True)
+        qs = _lin(self.ca_qpos_sine_proj, query_sine)
+        o, _ = ops.attention(c.frames(qc), kc, vv, c.n, H, 1, c.M, float(2 * d // H) ** -0.5, key_mask=c.key_mask,
+                             q2=c.frames(qs), k2=kp)
+        o = _lin(self.cross_attn.out_proj, o)
+        tgt = ops.layer_norm(c.padded(o), tgt, self.norm3.weight, self.norm3.bias, self.norm3.eps)
+        # ---- FFN (:435-437) ----
+        tgt, _ = ops.ffn_block(tgt, None, self.linear1.weight, self.linear1.bias, self.linear2.weight,
+                               self.linear2.bias, self.norm4.weight, self.norm4.bias, self.norm4.eps)
+        return tgt
+
+
+class TransformerDecoder(nn.Module):
+    """Anchor-refining box decoder (query_decoder.py:150-247)."""
+
+    def __init__(self, d: int, nhead: int, ffn: int, num_layers: int, query_dim: int):
+        super().__init__()
+        self.layers = nn.ModuleList(TransformerDecoderLayer(d, nhead, ffn, first=i == 0) for i in range(num_layers))
+        self.num_layers = num_layers
+        self.norm = NormP(d)
+        self.query_scale = MLPP(d, d, d, 2)
+        self.ref_point_head = MLPP(query_dim // 2 * d, d, d, 2)
+        self.bbox_embed = None  # assigned by the pipeline (pipeline.py:50)
+        self.query_dim = query_dim
+        self.d_model = d
+
+    def run(self, c: _Ctx, tgt, anchor, query_time):
+        d = self.d_model
+        out = tgt
+        inter, refs = [], [anchor]
+        for li, layer in enumerate(self.layers):
+            sine = anchor_sine_embed(anchor[..., : self.query_dim])  # [b*t, 512]
+            query_pos = run_mlp(self.ref_point_head, sine)
+            qsine = sine[..., :d] if li == 0 else sine[..., :d] * run_mlp(self.query_scale, out)
+            out = layer.run(c, out, query_pos, query_time, qsine, li == 0)
+            if self.bbox_embed is not None:
+                new_anchor = torch.sigmoid(run_mlp(self.bbox_embed, out) + inverse_sigmoid(anchor))
+                if li != self.num_layers - 1:
+                    refs.append(new_anchor)
+                anchor = new_anchor.detach()
+            inter.append(ops.layer_norm(out, None, self.norm.weight, self.norm.bias, self.norm.eps))
+        hs = torch.stack(inter).view(self.num_layers, c.b, c.t, d)
+        if self.bbox_embed is not None:
+            ref = torch.stack(refs).view(len(refs), c.b, c.t, -1)
+        else:
+            ref = anchor.view(1, c.b, c.t, -1)
+        return [hs, ref]
+
+
+class TimeDecoderLayer(nn.Module):
+    """Temporal decoder layer (query_decoder.py:553-660)."""
+
+    def __init__(self, d: int, nhead: int, ffn: int):
+        super().__init__()
+        self.self_attn = MHAP(d, nhead)
+        self.cross_attn_image = MHAP(d, nhead)
+        self.linear1 = LinearP(d, ffn)
+        self.linear2 = LinearP(ffn, d)
+        self.norm1, self.norm3, self.norm4 = NormP(d), NormP(d), NormP(d)
+        self.nhead = nhead
+        self.d = d
+
+    def run(self, c: _Ctx, tgt, query_pos, query_pos_frames, qpos_plus_time):
+        d, H = self.d, self.nhead
+        scale = float(d // H) ** -0.5
+        qk = tgt + qpos_plus_time
+        (wq, bq), (wk, bk), (wv, bv) = _mha_weights(self.self_attn)
+        Q = ops.linear(qk, wq, bq, out_bf16=True)
+        K = ops.linear(qk, wk, bk, out_bf16=True)
+        V = ops.linear(tgt, wv, bv, out_bf16=True)
+        o, weights = ops.attention(Q, K, V, c.b, H, c.t, c.t, scale, key_mask=c.query_mask, need_pavg=True)
+        a = _lin(self.self_attn.out_proj, o)
+        tgt = ops.layer_norm(a, tgt, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        # cross attention, one query per frame (:615-651)
+        (wq, bq), (wk, bk), (wv, bv) = _mha_weights(self.cross_attn_image)
+        Q = ops.linear(c.frames(tgt) + query_pos_frames, wq, bq, out_bf16=True)
+        K = ops.linear(c.mempos_op, wk, bk, out_bf16=True)
+        V = ops.linear(c.mem_op, wv, bv, out_bf16=True)
+        o, _ = ops.attention(Q, K, V, c.n, H, 1, c.M, scale, key_mask=c.key_mask)
+        o = _lin(self.cross_attn_image.out_proj, o)
+        tgt = ops.layer_norm(c.padded(o), tgt, self.norm3.weight, self.norm3.bias, self.norm3.eps)
+        tgt, _ = ops.ffn_block(tgt, None, self.linear1.weight, self.linear1.bias, self.linear2.weight,
+                               self.linear2.bias, self.norm4.weight, self.norm4.bias, self.norm4.eps)
+        return tgt, weights
+
+
+class TimeDecoder(nn.Module):
+    def __init__(self, d: int, nhead: int, ffn: int, num_layers: int):
+        super().__init__()
+        self.layers = nn.ModuleList(TimeDecoderLayer(d, nhead, ffn) for _ in range(num_layers))
+        self.num_layers = num_layers
+        self.norm = NormP(d)
+        self.d_model = d
+
+    def run(self, c: _Ctx, tgt, query_pos, query_time):
+        out = tgt
+        inter, ws = [], []
+        qpt = query_pos + query_time
+        qpf = c.frames(query_pos)
+        for layer in self.layers:
+            out, w = layer.run(c, out, query_pos, qpf, qpt)
+            inter.append(ops.layer_norm(out, None, self.norm.weight, self.norm.bias, self.norm.eps))
+            ws.append(w)
+        return torch.stack(inter).view(self.num_layers, c.b, c.t, self.d_model), torch.stack(ws)
+
+
+class TemplateGenerator(nn.Module):
+    """FiLM-style anchors and temporal content query (query_decoder.py:441-475)."""
+
+    def __init__(self, d: int, query_dim: int):
+        super().__init__()
+        self.content_proj = LinearP(d, d)
+        self.gamma_proj = LinearP(d, d)
+        self.beta_proj = LinearP(d, d)
+        self.anchor_proj = LinearP(d, query_dim)
+
+    def run(self, idx, frames_cls, videos_cls):
+        content = _lin(self.content_proj, videos_cls)
+        gamma = torch.tanh(_lin(self.gamma_proj, videos_cls))
+        beta = torch.tanh(_lin(self.beta_proj, videos_cls))
+        if idx["identity"]:
+            mod = gamma * frames_cls + beta
+            temp_query = content.expand(idx["n"], -1)
+        else:
+            f2v = idx["f2v"]
+            mod = gamma.index_select(0, f2v) * frames_cls + beta.index_select(0, f2v)
+            temp_query = content.index_select(0, f2v)
+        return _lin(self.anchor_proj, mod), temp_query
+
+
+class QueryDecoder(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        _check_cfg(cfg)
+        S = cfg.MODEL.STCAT
+        if not S.FROM_SCRATCH:
+            raise NotImplementedError("MODEL.STCAT.FROM_SCRATCH=False (the MDETR-initialised cross_attn_image branch, "
+                                      "query_decoder.py:285-288) is not implemented by stcat_b200")
+        d = S.HIDDEN
+        self.d_model = d
+        self.query_pos_dim = S.QUERY_DIM
+        self.nhead = S.HEADS
+        self.video_max_len = cfg.INPUT.MAX_VIDEO_LEN
+        self.return_weights = cfg.SOLVER.USE_ATTN
+        self.dropout_p = float(S.DROPOUT)
+        self.template_generator = TemplateGenerator(d, S.QUERY_DIM)
+        self.decoder = TransformerDecoder(d, S.HEADS, S.FFN_DIM, S.DEC_LAYERS, S.QUERY_DIM)
+        self.temp_decoder = TimeDecoder(d, S.HEADS, S.FFN_DIM, S.DEC_LAYERS)
+        max_len = self.video_max_len + 1
+        self.time_embed = LearnedTable(max_len, d) if S.USE_LEARN_TIME_EMBED else SineTable(max_len, d)
+        xavier_reset(self)
+
+    def forward(self, memory_cache: dict, vis_pos: Optional[torch.Tensor] = None, text_cls=None):
+        if self.training and self.dropout_p > 0:
+            raise NotImplementedError(
+                "train-mode dropout is not implemented by the sm_100a kernels yet: set MODEL.STCAT.DROPOUT 0.0")
+        d = self.d_model
+        mem_sf = memory_cache["encoded_memory"]  # [M, n, d]
+        memory_mask = memory_cache["mask"]  # [n, M] bool
+        durations = list(memory_cache["durations"])
+        H, W = memory_cache["fea_map_size"]
+        n_vis = H * W
+        M, n, _ = mem_sf.shape
+        idx = batch_indices(durations, mem_sf.device)
+        b, t = idx["b"], idx["t"]
+        if t > self.video_max_len + 1:
+            raise ValueError(f"clip of {t} frames exceeds INPUT.MAX_VIDEO_LEN={self.video_max_len}")
+        mem = mem_sf.transpose(0, 1).reshape(n * M, d).float()  # frame-major copy (one pass over 14 MB)
+        p_v = vis_pos.flatten(2).transpose(1, 2)  # [n, HW, d]
+        mem_pos = torch.cat([p_v, p_v.new_zeros(n, M - n_vis, d)], 1).reshape(n * M, d).float()
+        key_mask = memory_mask.to(torch.uint8).contiguous()
+        c = _Ctx(idx, mem, mem_pos, key_mask, M)
+        # templates (:97-120)
+        pos_query, temp_query = self.template_generator.run(idx, memory_cache["frames_cls"], memory_cache["videos_cls"])
+        anchors = c.padded(torch.sigmoid(pos_query))  # [b*t, 4]
+        query_temporal = c.padded(temp_query)  # [b*t, d]
+        qt = self.time_embed.rows(t)
+        query_time = (qt if b == 1 else qt.repeat(b, 1)).contiguous()
+        tgt = mem.new_zeros(b * t, d)
+        outputs = self.decoder.run(c, tgt, anchors, query_time)
+        outputs_temp = self.temp_decoder.run(c, tgt.clone(), query_temporal, query_time)
+        return outputs, outputs_temp
+
+
+def build_decoder(cfg) -> QueryDecoder:
+    """Mirror of models/grounding_model/__init__.py:8-9."""
+    return QueryDecoder(cfg)

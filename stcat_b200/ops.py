@@ -133,6 +133,74 @@ def linear(x, weight, bias=None, relu: bool = False, out_bf16: bool = False):
     return LinearFn.apply(x, weight, bias, relu, out_bf16)
 
 
+class LinearSumFn(Function):
+    """y = sum_i (x_i W_i^T + b_i): several Linear layers whose outputs the reference adds
+    (query_decoder.py:329-339 q = q_content + q_time + q_pos; :355-366 k = k_content + k_pos), run as
+    GEMMs accumulating into one output so the partial results never round-trip through HBM."""
+
+    @staticmethod
+    def forward(ctx, out_bf16, nterms, *args):
+        be = get_backend()
+        xs, ws, bs = args[:nterms], args[nterms:2 * nterms], args[2 * nterms:3 * nterms]
+        N, _ = ws[0].shape
+        lead = xs[0].shape[:-1]
+        odt = torch.bfloat16 if (out_bf16 and _precision == "bf16") else torch.float32
+        y = None
+        saved = []
+        for i, (x, w, b) in enumerate(zip(xs, ws, bs)):
+            K = w.shape[1]
+            x2 = _rows(x.detach(), K)
+            xo = _operand(x2)
+            if y is None:
+                y = torch.empty(x2.shape[0], N, dtype=odt, device=x.device)
+            be.linear_fwd(xo, _operand(w.detach(), True), None if b is None else b.detach(), y, accumulate=i > 0)
+            saved += [xo, w]
+        ctx.nterms = nterms
+        ctx.meta = [(x.shape, x.dtype, b is not None) for x, b in zip(xs, bs)]
+        ctx.save_for_backward(*saved)
+        return y.view(*lead, N)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        be = get_backend()
+        n = ctx.nterms
+        saved = ctx.saved_tensors
+        N = saved[1].shape[0]
+        dyo = _operand(_rows(dy, N))
+        M = dyo.shape[0]
+        dxs, dws, dbs = [], [], []
+        db_shared = None
+        for i in range(n):
+            xo, w = saved[2 * i], saved[2 * i + 1]
+            xshape, xdtype, has_b = ctx.meta[i]
+            K = w.shape[1]
+            dx = dw = db = None
+            if ctx.needs_input_grad[2 + i]:
+                dx = torch.empty(M, K, dtype=xdtype, device=dy.device)
+                be.linear_bwd_data(dyo, _operand(w.detach(), True), dx)
+                dx = dx.view(xshape)
+            if ctx.needs_input_grad[2 + n + i]:
+                dw = torch.empty(N, K, dtype=torch.float32, device=dy.device)
+                want_b = has_b and ctx.needs_input_grad[2 + 2 * n + i]
+                if want_b and db_shared is None:
+                    db_shared = torch.empty(N, dtype=torch.float32, device=dy.device)
+                    be.linear_bwd_weight(dyo, xo, dw, db_shared)
+                else:
+                    be.linear_bwd_weight(dyo, xo, dw, None)
+                db = (db_shared if not any(d is db_shared for d in dbs) else db_shared.clone()) if want_b else None
+            dxs.append(dx)
+            dws.append(dw)
+            dbs.append(db)
+        return (None, None, *dxs, *dws, *dbs)
+
+
+def linear_sum(terms, out_bf16: bool = False):
+    """terms: list of (x, weight, bias)."""
+    xs, ws, bs = zip(*terms)
+    return LinearSumFn.apply(out_bf16, len(terms), *xs, *ws, *bs)
+
+
 class LayerNormFn(Function):
     """y = LayerNorm(x + res) over the last dim (d = 256), eps 1e-5; fp32 in / out."""
 
@@ -248,25 +316,236 @@ def attention(q1, k1, v, B, H, Lq, Lk, scale, key_mask=None, q2=None, k2=None, n
 
 
 class AddFn(Function):
-    """out = a + b for same-shape contiguous fp32 tensors (q = k = src + pos)."""
+    """out = a + b for same-shape fp32 tensors (q = k = src + pos); with ``as_operand`` the sum is
+    written directly in the GEMM-operand dtype (bf16 in bf16 mode) by the same kernel."""
 
     @staticmethod
-    def forward(ctx, a, b):
+    def forward(ctx, a, b, as_operand):
         be = get_backend()
         a2 = a.detach().contiguous()
         b2 = b.detach().contiguous()
-        out = torch.empty_like(a2)
-        be.add(a2, b2, out, None)
+        if as_operand and _precision == "bf16":
+            out = torch.empty(a2.shape, dtype=torch.bfloat16, device=a2.device)
+            be.add(a2, b2, None, out)
+        else:
+            out = torch.empty_like(a2)
+            be.add(a2, b2, out, None)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        return g, g
+        g = g if g.dtype == torch.float32 else g.float()
+        return g, g, None
 
 
-def add(a, b):
+def add(a, b, as_operand: bool = False):
     assert a.shape == b.shape and a.dtype == torch.float32 and b.dtype == torch.float32
-    return AddFn.apply(a, b)
+    return AddFn.apply(a, b, as_operand)
+
+
+class CastFn(Function):
+    """fp32 -> GEMM operand in the active precision, hoisted out of the consumers (one cast kernel for a
+    tensor that feeds many GEMMs, e.g. the encoder memory read by all 12 decoder layers).  Backward
+    hands the fp32 gradient through unchanged (consumers produce fp32 dx)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x2 = x.detach()
+        x2 = x2 if x2.is_contiguous() else x2.contiguous()
+        out = torch.empty(x2.shape, dtype=torch.bfloat16, device=x.device)
+        get_backend().cast_bf16(x2.view(-1, x2.shape[-1]), out.view(-1, x2.shape[-1]))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.float() if g.dtype != torch.float32 else g
+
+
+def to_operand(x):
+    """Identity in fp32 mode; one fp32->bf16 cast kernel in bf16 mode."""
+    if _precision == "fp32" or x.dtype == torch.bfloat16:
+        return x
+    return CastFn.apply(x)
+
+
+def _new(rows, cols, dtype, like):
+    return torch.empty(rows, cols, dtype=dtype, device=like.device)
+
+
+def _opdtype():
+    return torch.bfloat16 if _precision == "bf16" else torch.float32
+
+
+def _cast_op(be, t):
+    """fp32 [R,C] contiguous -> operand dtype (no-op in fp32 mode)."""
+    if _precision == "fp32":
+        return t
+    out = torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
+    be.cast_bf16(t, out)
+    return out
+
+
+class SelfAttnBlockFn(Function):
+    """y = LayerNorm(x + MHA(q = k = x + pos, v = x)) for B sequences of L tokens, rows batch-major.
+
+    One fused forward/backward pair for the attention half of the post-norm encoder layer
+    (reference modal_encoder.py:228-238 via torch nn.MultiheadAttention, functional.py:5798-5873,
+    6630-6665): packed in-projection (q,k from x+pos: one N=512 GEMM; v from x), softmax(QK^T/sqrt(dh)
+    + key-padding mask) V without materialising P, out-projection, residual, LayerNorm.
+    x [B*L, d] fp32; pos [B*L, d] fp32; key_mask uint8 [B, L] or None.
+    Returns (y fp32, y_op): y_op is the bf16 GEMM-operand copy of y in bf16 mode, None in fp32 mode.
+    """
+
+    @staticmethod
+    def forward(ctx, x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps):
+        be = get_backend()
+        R, d = x.shape
+        assert R == B * L and x.is_contiguous() and pos.shape == x.shape
+        od = _opdtype()
+        bf = od == torch.bfloat16
+        xd, posd = x.detach(), pos.detach()
+        posd = posd if posd.is_contiguous() else posd.contiguous()
+        if bf:
+            qk_in = _new(R, d, od, x)
+            be.add(xd, posd, None, qk_in)
+            xo = x_op.detach() if (x_op is not None and x_op.dtype == od) else _cast_op(be, xd)
+        else:
+            qk_in = _new(R, d, od, x)
+            be.add(xd, posd, qk_in, None)
+            xo = xd
+        wi = _operand(w_in.detach(), True)
+        wo = _operand(w_out.detach(), True)
+        bi = b_in.detach()
+        qkv = _new(R, 3 * d, od, x)
+        be.linear_fwd(qk_in, wi[: 2 * d], bi[: 2 * d], qkv[:, : 2 * d])
+        be.linear_fwd(xo, wi[2 * d:], bi[2 * d:], qkv[:, 2 * d:])
+        o = _new(R, d, od, x)
+        lse = torch.empty(B, H, L, dtype=torch.float32, device=x.device)
+        scale = float(d // H) ** -0.5
+        be.attention_fwd(qkv[:, :d], None, qkv[:, d:2 * d], None, qkv[:, 2 * d:], o, key_mask, lse, None, B, H, L, L,
+                         scale)
+        a = _new(R, d, torch.float32, x)
+        be.linear_fwd(o, wo, b_out.detach(), a)
+        y = _new(R, d, torch.float32, x)
+        y_op = _new(R, d, od, x) if bf else None
+        mean = torch.empty(R, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(R, dtype=torch.float32, device=x.device)
+        be.layernorm_fwd(a, xd, gamma.detach(), beta.detach(), y, y_op, mean, rstd, eps)
+        ctx.save_for_backward(xd, xo, qk_in, qkv, o, lse, a, mean, rstd, key_mask, w_in, w_out, gamma)
+        ctx.dims = (B, L, H, scale)
+        if bf:
+            ctx.mark_non_differentiable(y_op)
+        return y, y_op
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy, _unused):
+        be = get_backend()
+        xd, xo, qk_in, qkv, o, lse, a, mean, rstd, key_mask, w_in, w_out, gamma = ctx.saved_tensors
+        B, L, H, scale = ctx.dims
+        R, d = xd.shape
+        od = qkv.dtype
+        f32 = torch.float32
+        dy = dy if (dy.is_contiguous() and dy.dtype == f32) else dy.contiguous().float()
+        wi = _operand(w_in.detach(), True)
+        wo = _operand(w_out.detach(), True)
+        dz = _new(R, d, f32, dy)  # grad wrt (a) and wrt the residual x
+        dg = torch.zeros(d, dtype=f32, device=dy.device)
+        dbt = torch.zeros(d, dtype=f32, device=dy.device)
+        be.layernorm_bwd(dy, a, xd, gamma.detach(), mean, rstd, dz, dg, dbt)
+        dz_op = _cast_op(be, dz)
+        dwo = _new(d, d, f32, dy)
+        dbo = torch.empty(d, dtype=f32, device=dy.device)
+        be.linear_bwd_weight(dz_op, o, dwo, dbo)
+        d_o = _new(R, d, od, dy)
+        be.linear_bwd_data(dz_op, wo, d_o)
+        dqkv = _new(R, 3 * d, od, dy)
+        delta = torch.empty(B, H, L, dtype=f32, device=dy.device)
+        be.attention_bwd(qkv[:, :d], None, qkv[:, d:2 * d], None, qkv[:, 2 * d:], d_o, key_mask, lse, None, delta,
+                         dqkv[:, :d], None, dqkv[:, d:2 * d], None, dqkv[:, 2 * d:], B, H, L, L, scale)
+        dwi = _new(3 * d, d, f32, dy)
+        dbi = torch.empty(3 * d, dtype=f32, device=dy.device)
+        be.linear_bwd_weight(dqkv[:, : 2 * d], qk_in, dwi[: 2 * d], dbi[: 2 * d])
+        be.linear_bwd_weight(dqkv[:, 2 * d:], xo, dwi[2 * d:], dbi[2 * d:])
+        need_pos = ctx.needs_input_grad[2]
+        dpos = None
+        if need_pos:
+            dpos = _new(R, d, f32, dy)
+            be.linear_bwd_data(dqkv[:, : 2 * d], wi[: 2 * d], dpos)
+            be.add(dz, dpos, dz, None)
+        else:
+            be.linear_bwd_data(dqkv[:, : 2 * d], wi[: 2 * d], dz, accumulate=True)
+        be.linear_bwd_data(dqkv[:, 2 * d:], wi[2 * d:], dz, accumulate=True)
+        return dz, None, dpos, None, dwi, dbi, dwo, dbo, dg, dbt, None, None, None, None
+
+
+class FFNBlockFn(Function):
+    """y = LayerNorm(x + W2 relu(W1 x + b1) + b2)  (modal_encoder.py:239-241; query_decoder.py:435-437,
+    657-659).  x [R, d] fp32.  Returns (y, y_op) like SelfAttnBlockFn."""
+
+    @staticmethod
+    def forward(ctx, x, x_op, w1, b1, w2, b2, gamma, beta, eps):
+        be = get_backend()
+        R, d = x.shape
+        F_ = w1.shape[0]
+        od = _opdtype()
+        bf = od == torch.bfloat16
+        xd = x.detach()
+        xd = xd if xd.is_contiguous() else xd.contiguous()
+        if bf:
+            xo = x_op.detach() if (x_op is not None and x_op.dtype == od) else _cast_op(be, xd)
+        else:
+            xo = xd
+        w1o, w2o = _operand(w1.detach(), True), _operand(w2.detach(), True)
+        h = _new(R, F_, od, x)
+        be.linear_fwd(xo, w1o, b1.detach(), h, relu=True)
+        yl = _new(R, d, torch.float32, x)
+        be.linear_fwd(h, w2o, b2.detach(), yl)
+        y = _new(R, d, torch.float32, x)
+        y_op = _new(R, d, od, x) if bf else None
+        mean = torch.empty(R, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(R, dtype=torch.float32, device=x.device)
+        be.layernorm_fwd(yl, xd, gamma.detach(), beta.detach(), y, y_op, mean, rstd, eps)
+        ctx.save_for_backward(xd, xo, h, yl, mean, rstd, w1, w2, gamma)
+        if bf:
+            ctx.mark_non_differentiable(y_op)
+        return y, y_op
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy, _unused):
+        be = get_backend()
+        xd, xo, h, yl, mean, rstd, w1, w2, gamma = ctx.saved_tensors
+        R, d = xd.shape
+        F_ = w1.shape[0]
+        od = h.dtype
+        f32 = torch.float32
+        dy = dy if (dy.is_contiguous() and dy.dtype == f32) else dy.contiguous().float()
+        w1o, w2o = _operand(w1.detach(), True), _operand(w2.detach(), True)
+        dz = _new(R, d, f32, dy)
+        dg = torch.zeros(d, dtype=f32, device=dy.device)
+        dbt = torch.zeros(d, dtype=f32, device=dy.device)
+        be.layernorm_bwd(dy, yl, xd, gamma.detach(), mean, rstd, dz, dg, dbt)
+        dz_op = _cast_op(be, dz)
+        dw2 = _new(d, F_, f32, dy)
+        db2 = torch.empty(d, dtype=f32, device=dy.device)
+        be.linear_bwd_weight(dz_op, h, dw2, db2)
+        dh = _new(R, F_, od, dy)
+        be.linear_bwd_data(dz_op, w2o, dh)
+        be.relu_bwd(h, dh)
+        dw1 = _new(F_, d, f32, dy)
+        db1 = torch.empty(F_, dtype=f32, device=dy.device)
+        be.linear_bwd_weight(dh, xo, dw1, db1)
+        be.linear_bwd_data(dh, w1o, dz, accumulate=True)
+        return dz, None, dw1, db1, dw2, db2, dg, dbt, None
+
+
+def self_attn_block(x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps=1e-5):
+    return SelfAttnBlockFn.apply(x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps)
+
+
+def ffn_block(x, x_op, w1, b1, w2, b2, gamma, beta, eps=1e-5):
+    return FFNBlockFn.apply(x, x_op, w1, b1, w2, b2, gamma, beta, eps)
 
 
 def sted_score(pred_sted: torch.Tensor, durations, return_map: bool = False):

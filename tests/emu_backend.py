@@ -1,0 +1,166 @@
+"""TEST INFRASTRUCTURE ONLY: a torch-CPU emulation of ``stcat_b200.cabi.CudaBackend``.
+
+It implements the *contract* of every C-ABI entry point (include/stcat_b200.h) with plain torch ops so
+that the host-side composition (stcat_b200/{ops,encoder,decoder,pipeline}.py: layouts, index maps,
+hand-written backward chains) can be checked against the oracle in the GPU-less build container.
+It is installed only by tests through ``ops.set_backend``; product code never selects it and
+``CudaBackend`` raises on CPU tensors.
+"""
+import torch
+
+
+def _f(t):
+    return t.float() if t.dtype != torch.float32 else t
+
+
+def _store(dst, val):
+    dst.copy_(val.to(dst.dtype))
+
+
+class EmuBackend:
+    name = "emu"
+
+    def __init__(self):
+        self.launches = 0
+
+    # -- linear --------------------------------------------------------
+    def linear_fwd(self, x, w, bias, y, relu=False, accumulate=False):
+        v = _f(x) @ _f(w).t()
+        if bias is not None:
+            v = v + bias
+        if accumulate:
+            v = v + _f(y)
+        if relu:
+            v = v.relu()
+        _store(y, v)
+        self.launches += 1
+
+    def linear_bwd_data(self, dy, w, dx, accumulate=False):
+        v = _f(dy) @ _f(w)
+        if accumulate:
+            v = v + _f(dx)
+        _store(dx, v)
+        self.launches += 1
+
+    def linear_bwd_weight(self, dy, x, dw, db, accumulate=False):
+        v = _f(dy).t() @ _f(x)
+        s = _f(dy).sum(0)
+        if accumulate:
+            v = v + dw
+            if db is not None:
+                s = s + db
+        _store(dw, v)
+        if db is not None:
+            _store(db, s)
+        self.launches += 1
+
+    # -- layernorm -----------------------------------------------------
+    def layernorm_fwd(self, x, res, gamma, beta, y, y_bf16, mean, rstd, eps=1e-5):
+        z = x if res is None else x + res
+        mu = z.mean(-1)
+        var = ((z - mu[:, None]) ** 2).mean(-1)
+        rs = torch.rsqrt(var + eps)
+        out = (z - mu[:, None]) * rs[:, None] * gamma + beta
+        y.copy_(out)
+        if y_bf16 is not None:
+            y_bf16.copy_(out.to(torch.bfloat16))
+        mean.copy_(mu)
+        rstd.copy_(rs)
+        self.launches += 1
+
+    def layernorm_bwd(self, dy, x, res, gamma, mean, rstd, dz, dgamma, dbeta):
+        z = x if res is None else x + res
+        xh = (z - mean[:, None]) * rstd[:, None]
+        dg = dy * gamma
+        s1 = dg.mean(-1, keepdim=True)
+        s2 = (dg * xh).mean(-1, keepdim=True)
+        dz.copy_(rstd[:, None] * (dg - s1 - xh * s2))
+        dgamma.add_((dy * xh).sum(0))
+        dbeta.add_(dy.sum(0))
+        self.launches += 1
+
+    # -- attention -----------------------------------------------------
+    @staticmethod
+    def _scores(q1, q2, k1, k2, key_mask, B, H, Lq, Lk, scale):
+        hd = lambda t, L: _f(t).reshape(B, L, H, 32).permute(0, 2, 1, 3)
+        s = hd(q1, Lq) @ hd(k1, Lk).transpose(-1, -2)
+        if q2 is not None:
+            s = s + hd(q2, Lq) @ hd(k2, Lk).transpose(-1, -2)
+        s = s * scale
+        if key_mask is not None:
+            s = s.masked_fill(key_mask.bool()[:, None, None, :], float("-inf"))
+        return s, hd
+
+    def attention_fwd(self, q1, q2, k1, k2, v, o, key_mask, lse, p_avg, B, H, Lq, Lk, scale):
+        s, hd = self._scores(q1, q2, k1, k2, key_mask, B, H, Lq, Lk, scale)
+        p = torch.softmax(s, -1)
+        out = (p @ hd(v, Lk)).permute(0, 2, 1, 3).reshape(B * Lq, H * 32)
+        _store(o, out)
+        lse.copy_(torch.logsumexp(s, -1))
+        if p_avg is not None:
+            p_avg.add_(p.mean(1))
+        self.launches += 1
+
+    def attention_bwd(self, q1, q2, k1, k2, v, d_o, key_mask, lse, dp_avg, delta, dq1, dq2, dk1, dk2, dv, B, H, Lq, Lk,
+                      scale):
+        s, hd = self._scores(q1, q2, k1, k2, key_mask, B, H, Lq, Lk, scale)
+        p = torch.exp(s - lse[..., None])
+        g = hd(d_o, Lq)
+        dp = g @ hd(v, Lk).transpose(-1, -2)
+        if dp_avg is not None:
+            dp = dp + dp_avg[:, None] / H
+        dl = (p * dp).sum(-1, keepdim=True)
+        delta.copy_(dl.squeeze(-1))
+        ds = p * (dp - dl) * scale
+        un = lambda t, L: t.permute(0, 2, 1, 3).reshape(B * L, H * 32)
+        _store(dv, un(p.transpose(-1, -2) @ g, Lk))
+        _store(dq1, un(ds @ hd(k1, Lk), Lq))
+        _store(dk1, un(ds.transpose(-1, -2) @ hd(q1, Lq), Lk))
+        if q2 is not None:
+            _store(dq2, un(ds @ hd(k2, Lk), Lq))
+            _store(dk2, un(ds.transpose(-1, -2) @ hd(q2, Lq), Lk))
+        self.launches += 2
+
+    # -- element-wise --------------------------------------------------
+    def add(self, a, b, out, out_bf16=None):
+        z = a + b
+        if out is not None:
+            out.copy_(z)
+        if out_bf16 is not None:
+            out_bf16.copy_(z.to(torch.bfloat16))
+        self.launches += 1
+
+    def relu_bwd(self, y, dy):
+        dy.masked_fill_(~(_f(y) > 0), 0)
+        self.launches += 1
+
+    def cast_bf16(self, x, out, transpose=False):
+        out.copy_((x.t() if transpose else x).to(torch.bfloat16))
+        self.launches += 1
+
+    def sted_score(self, sted, durations, score, best):
+        b, t, _ = sted.shape
+        ls = torch.log_softmax(sted[:, :, 0], 1)
+        le = torch.log_softmax(sted[:, :, 1], 1)
+        ii = torch.arange(t)[:, None]
+        jj = torch.arange(t)[None, :]
+        for v in range(b):
+            dur = int(durations[v])
+            pen = torch.zeros(t, t)
+            pen[(jj <= ii) | (ii >= dur) | (jj >= dur)] = -1e32
+            sc = pen + (ls[v][:, None] + le[v][None, :])
+            if score is not None:
+                score[v].copy_(sc)
+            best[v] = int(sc.flatten().argmax())
+        self.launches += 1
+
+    def map2d_pool(self, x, valid, out):
+        B, N, d = x.shape
+        out.zero_()
+        for i in range(N):
+            run = torch.full((B, d), float("-inf"))
+            for j in range(i, N):
+                run = torch.maximum(run, x[:, j])
+                if valid.view(N, N)[i, j]:
+                    out[:, :, i, j] = run
+        self.launches += 1

@@ -1,0 +1,148 @@
+"""CPU (-m "not gpu"): the host-side composition of stcat_b200 (layouts, index maps, hand-written
+backward chains of the fused blocks) driven through the torch-CPU emulation of the C ABI
+(tests/emu_backend.py) and compared with the oracle and the golden fixtures of the reference.
+The CUDA kernels themselves are compared with the same oracle in the -m gpu tests."""
+import pytest
+import torch
+
+from oracle import stcat_oracle as O
+from helpers import GOLDEN_CASES, load_golden, cfg_for, case_inputs, case_params, rel_err
+from stcat_b200 import ops, synthetic
+from stcat_b200.nested import NestedTensor
+from stcat_b200.pipeline import STCATHotPath
+from stcat_b200.param_spec import hot_path_spec
+from emu_backend import EmuBackend
+
+
+@pytest.fixture(autouse=True)
+def emu():
+    ops.set_backend(EmuBackend())
+    ops.set_precision("fp32")
+    yield
+    ops.set_backend(None)
+    ops.set_precision("fp32")
+    ops.clear_weight_cache()
+
+
+def build(cfg, P):
+    m = STCATHotPath(cfg)
+    m.load_flat_params(P)
+    return m
+
+
+def run_model(m, inp, grad=False):
+    vis = inp["vis_features"].clone().requires_grad_(grad)
+    txt = inp["text_memory"].clone().requires_grad_(grad)
+    videos = NestedTensor(vis, inp["vis_mask"].clone(), inp["durations"])
+    out = m(videos, inp["vis_pos"], (inp["text_mask"], txt, None))
+    return out, vis, txt
+
+
+def test_state_dict_matches_contract():
+    cfg = cfg_for({"max_video_len": 20})
+    m = STCATHotPath(cfg)
+    sd = m.state_dict()
+    spec = hot_path_spec(cfg)
+    assert set(sd.keys()) == set(spec.keys())
+    for k, shape in spec.items():
+        assert tuple(sd[k].shape) == tuple(shape), k
+    # the alias of pipeline.py:50
+    assert m.ground_decoder.decoder.bbox_embed is m.bbox_embed
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_forward_matches_golden(name):
+    fx = load_golden(name)
+    spec = fx["spec"]
+    cfg = cfg_for(spec)
+    inp = case_inputs(spec)
+    m = build(cfg, case_params(cfg, spec)).eval()
+    with torch.no_grad():
+        out, _, _ = run_model(m, inp)
+    TOL = 5e-5
+    c = out["_memory_cache"]
+    assert torch.equal(c["mask"], fx["cache"]["mask"])
+    for k in ("encoded_memory", "frames_cls", "videos_cls"):
+        assert c[k].shape == fx["cache"][k].shape, k
+        assert rel_err(c[k], fx["cache"][k]) < TOL, k
+    assert rel_err(out["_hs"], fx["hs"]) < TOL
+    assert rel_err(out["_reference"], fx["reference"]) < TOL
+    assert rel_err(out["_time_hs"], fx["time_hs"]) < TOL
+    assert rel_err(out["_weights_all"], fx["weights_all"]) < TOL
+    for k in ("pred_boxes", "pred_sted", "pred_actioness", "weights"):
+        assert out[k].shape == fx["out"][k].shape, k
+        assert rel_err(out[k], fx["out"][k]) < TOL, k
+    for a, g in zip(out["aux_outputs"], fx["aux"]):
+        for k in g:
+            assert rel_err(a[k], g[k]) < TOL, k
+
+
+@pytest.mark.parametrize("name", ["b1_T8_res224_L8", "b3_ragged_T4_1_6"])
+def test_gradients_match_golden(name):
+    fx = load_golden(name)
+    spec = fx["spec"]
+    cfg = cfg_for(spec)
+    cfg.merge_from_list(["SOLVER.GIOU_COEF", 3, "SOLVER.TEMP_COEF", 10, "SOLVER.EOS_COEF", 0.3])
+    inp = case_inputs(spec)
+    m = build(cfg, case_params(cfg, spec)).eval()  # eval like the fixture: the 0.3 head dropout is identity
+    out, vis, txt = run_model(m, inp, grad=True)
+    tg = synthetic.make_targets(spec["durations"], seed=spec["seed"])
+    total, losses = O.stg_loss(cfg, out, tg["boxes"], tg["actioness"], spec["durations"])
+    assert abs(float(total.detach()) - float(fx["loss_total"])) <= 5e-5 * abs(float(fx["loss_total"]))
+    total.backward()
+    assert rel_err(vis.grad, fx["grad64"]["vis_features"]) < 5e-3
+    assert rel_err(txt.grad, fx["grad64"]["text_memory"]) < 5e-3
+    named = dict(m.named_parameters())
+    for k, g in fx["grad_full"].items():
+        assert rel_err(named[k].grad, g) < 5e-3, k
+    for k, gn in fx["grad_norm"].items():
+        if k.startswith("ground_decoder.decoder.bbox_embed."):
+            continue
+        p = named[k]
+        if torch.isnan(gn):
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+        else:
+            assert p.grad is not None, k
+            got = float(p.grad.double().norm())
+            assert abs(got - float(gn)) <= 5e-3 * float(gn) + 2e-6, (k, got, float(gn))  # abs floor: fp32 noise on ~0 grads
+
+
+def test_bf16_mode_tracks_rounded_oracle():
+    """bf16 operand mode vs the oracle with bf16-rounded matmul operands (SURVEY.md 7.3-1 policy)."""
+    fx = load_golden("b1_T8_res224_L8")
+    spec = fx["spec"]
+    cfg = cfg_for(spec)
+    inp = case_inputs(spec)
+    P = case_params(cfg, spec)
+    m = build(cfg, P).eval()
+    ops.set_precision("bf16")
+    with torch.no_grad():
+        out, _, _ = run_model(m, inp)
+        ref = O.hot_path_forward(P, cfg, inp["vis_features"], inp["vis_mask"], inp["durations"], inp["vis_pos"],
+                                 inp["text_mask"], inp["text_memory"], prec=O.Prec(round_operands="bf16"))
+    for k in ("pred_boxes", "pred_sted", "pred_actioness", "weights"):
+        assert rel_err(out[k], ref[k]) < 2e-2, k  # loose: rounding points differ slightly
+
+
+@pytest.mark.parametrize("name", ["b1_T8_res224_L8", "b2_ragged_T5_3"])
+def test_device_loss_matches_oracle_loss(name):
+    from stcat_b200.loss import STGLossPlan, loss_weight_dict
+
+    fx = load_golden(name)
+    spec = fx["spec"]
+    cfg = cfg_for(spec)
+    cfg.merge_from_list(["SOLVER.GIOU_COEF", 3, "SOLVER.TEMP_COEF", 10, "SOLVER.EOS_COEF", 0.3])
+    inp = case_inputs(spec)
+    m = build(cfg, case_params(cfg, spec)).eval()
+    with torch.no_grad():
+        out, _, _ = run_model(m, inp)
+    tg = synthetic.make_targets(spec["durations"], seed=spec["seed"])
+    plan = STGLossPlan(cfg, tg["boxes"], tg["actioness"], spec["durations"], "cpu")
+    total, named = plan(out)
+    ref_total, ref_named = O.stg_loss(cfg, out, tg["boxes"], tg["actioness"], spec["durations"])
+    assert loss_weight_dict(cfg) == O.loss_weight_dict(cfg)
+    assert set(named) == set(ref_named)
+    for k in ref_named:
+        assert abs(float(named[k]) - float(ref_named[k])) <= 1e-5 * max(1.0, abs(float(ref_named[k]))), k
+    assert abs(float(total) - float(ref_total)) <= 1e-5 * abs(float(ref_total))
+    assert abs(float(total) - float(fx["loss_total"])) <= 5e-5 * abs(float(fx["loss_total"]))
