@@ -1,16 +1,448 @@
-// bf16 tcgen05/TMA GEMM (placeholder until the tensor-core kernel lands: reports "unsupported" so
-// the dispatcher uses the SIMT kernel for bf16 operands as well).
+// bf16 tensor-core GEMM for sm_100a: TMA -> shared memory (128B swizzle) -> tcgen05.mma (fp32 accumulators in
+// TMEM) -> tcgen05.ld epilogue (bias / ReLU / dtype) -> swizzled shared staging -> TMA store or TMA reduce-add.
+//
+//   C[M,N] (+)= A(M,K) . B(N,K)^T      A, B bf16; C fp32 or bf16; fp32 accumulation
+//
+// One kernel serves the three GEMMs of a Linear layer (stcat_linear_{fwd,bwd_data,bwd_weight}) by letting
+// either operand be "K-major" (contraction index contiguous in memory) or "MN-major" (row index contiguous):
+//   fwd        y  = x . w^T        A = x  [M,K]  K-major     B = w  [N,K]  K-major
+//   bwd_data   dx = dy . w         A = dy [M,N'] K-major     B(k,n') = w[n',k]    MN-major
+//   bwd_weight dw = dy^T . x       A(n,m) = dy[m,n] MN-major B(k,m) = x[m,k]      MN-major
+// so no transposed copies of activations are ever materialised.
+//
+// Structure (persistent, warp-specialised, 256 threads, 1 CTA / SM):
+//   warp 0      TMA producer  : 4-stage ring of {A 128x64, B 256x64} bf16 tiles (48 KB / stage), mbarrier full/empty
+//   warp 1      MMA issuer    : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 128x256x16, 4 per stage;
+//                               tcgen05.commit releases the stage / publishes the accumulator
+//   warp 2      TMEM allocator: 512 columns = 2 accumulator stages of 128 lanes x 256 fp32 columns
+//   warps 4..7  epilogue      : tcgen05.ld 32 lanes x 32 columns per warp, bias/ReLU, convert, st.shared into a
+//                               128B-swizzled [128 x 128 B] staging tile (double buffered), TMA store / reduce-add
+// M/N/K tails need no code: TMA zero-fills out-of-bounds loads and clips out-of-bounds stores.
+// Split-K (needed by bwd_weight, whose contraction runs over all M = T*S tokens while the output is one
+// or a few tiles) uses the TMA reduce-add epilogue on a pre-zeroed fp32 output.
 #include "common.cuh"
+#include <cuda.h>
+#include <stdlib.h>
 
 namespace stcat {
 
-int gemm_tc_supported(int, int, int, int64_t, int64_t, int64_t, const void*, const void*, const void*, int, int) {
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 64;  // tile; BK * 2 B = 128 B = one swizzle row
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_BYTES = BN * BK * 2;   // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int EPI_BYTES = BM * 128;    // one staging chunk: 128 rows x 128 B
+constexpr int EPI_BUFS = 2;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BUFS * EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int THREADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    asm volatile("trap;");
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), 128B swizzle, sm_100 version field
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    return d;
+}
+
+struct Params {
+    const float* bias;  // [N] or null (added by k-split 0)
+    int M, N, K;
+    int tiles_m, tiles_n, splits, kb_per_split, kb_total;
+    int relu;
+    int reduce_add;  // epilogue uses TMA reduce-add instead of store
+};
+
+template <bool A_MN, bool B_MN, bool OUT_BF16>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B-swizzle atoms need 1024 B alignment
+    const uint32_t epi_base = base + STAGES * STAGE_BYTES;
+    const uint32_t bar_base = epi_base + EPI_BUFS * EPI_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto accf_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto acce_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = p.tiles_m * p.tiles_n * p.splits;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(accf_bar(s), 1); mbar_init(acce_bar(s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < total; w += gridDim.x) {
+                const int split = w % p.splits;
+                const int t = w / p.splits;
+                const int m_blk = t % p.tiles_m, n_blk = t / p.tiles_m;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                    if (!A_MN) {
+                        tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j)
+                            tma_load_2d(sa + j * (BK * 128), &tmA, full_bar(stage), m_blk * BM + j * 64, kb * BK);
+                    }
+                    if (!B_MN) {
+                        tma_load_2d(sb, &tmB, full_bar(stage), kb * BK, n_blk * BN);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j)
+                            tma_load_2d(sb + j * (BK * 128), &tmB, full_bar(stage), n_blk * BN + j * 64, kb * BK);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = bf16, majors, N >> 3, M >> 4
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int w = blockIdx.x; w < total; w += gridDim.x) {
+                const int split = w % p.splits;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                mbar_wait(acce_bar(as), aphase ^ 1);  // epilogue has drained this accumulator stage
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // K-major: 16 bf16 = 32 B inside the 128 B swizzle row; 8-row groups 1024 B apart (SBO).
+                        // MN-major: 16 k-rows = 2 swizzle atoms of 8 rows x 128 B (SBO = 1024 B); successive
+                        //           64-element MN blocks are BK*128 B apart (LBO).
+                        const uint64_t ad = A_MN ? make_desc(sa + k * 2048, BK * 128, 1024) : make_desc(sa + k * 32, 16, 1024);
+                        const uint64_t bd = B_MN ? make_desc(sb + k * 2048, BK * 128, 1024) : make_desc(sb + k * 32, 16, 1024);
+                        umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(accf_bar(as));  // accumulator complete -> epilogue
+                if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue (warps 4..7 <-> TMEM lane quadrants 0..3) =================
+        const int q = warp - 4;
+        const int row = q * 32 + lane;  // row of the 128-row tile owned by this thread
+        const int et = threadIdx.x - 128;
+        constexpr int CHUNK_COLS = OUT_BF16 ? 64 : 32;  // 128 B of output per row per chunk
+        constexpr int NCHUNK = BN / CHUNK_COLS;
+        int as = 0, buf = 0;
+        uint32_t aphase = 0;
+        for (int w = blockIdx.x; w < total; w += gridDim.x) {
+            const int split = w % p.splits;
+            const int t = w / p.splits;
+            const int m_blk = t % p.tiles_m, n_blk = t / p.tiles_m;
+            mbar_wait(accf_bar(as), aphase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+            const bool add_bias = p.bias != nullptr && split == 0;
+            const int n_valid = min(BN, p.N - n_blk * BN);
+            for (int c = 0; c < NCHUNK; ++c) {
+                if (c * CHUNK_COLS >= n_valid) break;  // whole chunk out of range (uniform across the CTA)
+                // staging buffer `buf` must have been read by its previous TMA store
+                if (et == 0) tma_wait_read<EPI_BUFS - 1>();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const uint32_t sbuf = epi_base + buf * EPI_BYTES + row * 128;
+#pragma unroll
+                for (int h = 0; h < CHUNK_COLS / 32; ++h) {
+                    uint32_t r[32];
+                    tmem_ld32(t_row + c * CHUNK_COLS + h * 32, r);
+                    tmem_ld_wait();
+                    const int col0 = n_blk * BN + c * CHUNK_COLS + h * 32;
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float x = __uint_as_float(r[i]);
+                        if (add_bias && col0 + i < p.N) x += __ldg(p.bias + col0 + i);
+                        if (p.relu) x = fmaxf(x, 0.f);
+                        v[i] = x;
+                    }
+                    if (OUT_BF16) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {  // 4 x 16 B chunks = 32 bf16
+                            uint32_t w0, w1, w2, w3;
+                            __nv_bfloat162 b0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
+                            __nv_bfloat162 b1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+                            __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+                            __nv_bfloat162 b3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+                            w0 = *reinterpret_cast<uint32_t*>(&b0); w1 = *reinterpret_cast<uint32_t*>(&b1);
+                            w2 = *reinterpret_cast<uint32_t*>(&b2); w3 = *reinterpret_cast<uint32_t*>(&b3);
+                            const int chunk = (h * 4 + j) ^ (row & 7);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbuf + chunk * 16), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {  // 8 x 16 B chunks = 32 fp32
+                            const int chunk = j ^ (row & 7);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbuf + chunk * 16),
+                                         "r"(__float_as_uint(v[4 * j + 0])), "r"(__float_as_uint(v[4 * j + 1])),
+                                         "r"(__float_as_uint(v[4 * j + 2])), "r"(__float_as_uint(v[4 * j + 3])) : "memory");
+                        }
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) {
+                    const uint32_t src = epi_base + buf * EPI_BYTES;
+                    if (p.reduce_add) tma_reduce_add_2d(&tmC, src, n_blk * BN + c * CHUNK_COLS, m_blk * BM);
+                    else tma_store_2d(&tmC, src, n_blk * BN + c * CHUNK_COLS, m_blk * BM);
+                    tma_commit();
+                }
+                buf ^= 1;
+            }
+            // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acce_bar(as));
+            if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+        }
+        if (et == 0) tma_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2-D row-major tensor [rows, cols] with leading dimension ld (elements); box = {box_cols, box_rows}
+static int make_map(CUtensorMap* tm, const void* ptr, bool bf16, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                    int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return set_err(STCAT_EINVAL, "gemm_tc: cuTensorMapEncodeTiled not available from the driver");
+    const int es = bf16 ? 2 : 4;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr),
+                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(STCAT_EINVAL, "gemm_tc: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, (long long)rows, (long long)cols, (long long)ld);
     return 0;
 }
 
-int gemm_tc(const void*, int64_t, int, const void*, int64_t, int, void*, int64_t, int, const float*, int, int, int,
-            int, int, cudaStream_t) {
-    return set_err(STCAT_ESHAPE, "gemm_tc: not built");
+}  // namespace tc
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+// Shapes / alignments the tensor-core kernel takes; everything else (tiny heads such as N = 1, 2, 4, odd leading
+// dimensions) stays on the exact SIMT kernel.
+int gemm_tc_supported(int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc, const void* A, const void* B,
+                      const void* C, int a_mn_major, int b_mn_major) {
+    (void)a_mn_major; (void)b_mn_major;
+    if (getenv("STCAT_DISABLE_TC")) return 0;
+    if (M < 1 || N < 8 || K < 8) return 0;
+    if ((int64_t)M * N * K < (int64_t)(1 << 18)) return 0;  // launch-latency regime: SIMT kernel is as fast
+    if (!aligned16(A) || !aligned16(B) || !aligned16(C)) return 0;
+    if ((lda % 8) || (ldb % 8) || (ldc % 8)) return 0;  // 16 B row pitch for bf16 (fp32 C: 32 B, stricter than needed)
+    return 1;
+}
+
+int gemm_tc(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* C,
+            int64_t ldc, int out_dtype, const float* bias, int M, int N, int K, int relu, int accumulate,
+            cudaStream_t st) {
+    using namespace tc;
+    const bool out_bf16 = out_dtype == STCAT_BF16;
+    CUtensorMap tmA, tmB, tmC;
+    int rc;
+    // A: K-major -> tensor [M rows, K cols], box {BK, BM};  MN-major -> tensor [K rows, M cols], box {64, BK}
+    rc = a_mn_major ? make_map(&tmA, A, true, K, M, lda, 64, BK) : make_map(&tmA, A, true, M, K, lda, BK, BM);
+    if (rc) return rc;
+    rc = b_mn_major ? make_map(&tmB, B, true, K, N, ldb, 64, BK) : make_map(&tmB, B, true, N, K, ldb, BK, BN);
+    if (rc) return rc;
+    rc = make_map(&tmC, C, out_bf16, M, N, ldc, out_bf16 ? 64 : 32, BM);
+    if (rc) return rc;
+
+    Params p;
+    p.bias = bias;
+    p.M = M; p.N = N; p.K = K;
+    p.tiles_m = (M + BM - 1) / BM;
+    p.tiles_n = (N + BN - 1) / BN;
+    p.kb_total = (K + BK - 1) / BK;
+    const int tiles = p.tiles_m * p.tiles_n;
+    const int sms = num_sms();
+    int splits = 1;
+    if (!relu && !out_bf16 && tiles * 2 <= sms && p.kb_total >= 8) {
+        splits = sms / tiles;
+        const int max_by_k = p.kb_total / 4;  // at least 4 k-blocks (256 contraction elements) per split
+        if (splits > max_by_k) splits = max_by_k;
+        if (splits < 1) splits = 1;
+    }
+    p.kb_per_split = (p.kb_total + splits - 1) / splits;
+    p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    p.relu = relu;
+    p.reduce_add = (accumulate || p.splits > 1) ? 1 : 0;
+    if (p.splits > 1 && !accumulate) {
+        cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st);
+        if (e != cudaSuccess) return set_err((int)e, "gemm_tc memset: %s", cudaGetErrorString(e));
+    }
+    if (relu && accumulate) return set_err(STCAT_ESHAPE, "gemm_tc: relu with accumulate is not supported");
+    const int total = tiles * p.splits;
+    const int grid = total < sms ? total : sms;
+
+#define STCAT_TC_LAUNCH(AMN, BMN, OBF)                                                                              \
+    do {                                                                                                            \
+        static bool attr_set = false;                                                                               \
+        if (!attr_set) {                                                                                            \
+            cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AMN, BMN, OBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); \
+            if (e != cudaSuccess) return set_err((int)e, "gemm_tc: smem attribute: %s", cudaGetErrorString(e));     \
+            attr_set = true;                                                                                        \
+        }                                                                                                           \
+        gemm_tc_kernel<AMN, BMN, OBF><<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmB, tmC, p);                          \
+    } while (0)
+
+    if (!a_mn_major && !b_mn_major) { if (out_bf16) STCAT_TC_LAUNCH(false, false, true); else STCAT_TC_LAUNCH(false, false, false); }
+    else if (!a_mn_major && b_mn_major) { if (out_bf16) STCAT_TC_LAUNCH(false, true, true); else STCAT_TC_LAUNCH(false, true, false); }
+    else if (a_mn_major && b_mn_major) { if (out_bf16) STCAT_TC_LAUNCH(true, true, true); else STCAT_TC_LAUNCH(true, true, false); }
+    else return set_err(STCAT_ESHAPE, "gemm_tc: A MN-major with B K-major is not instantiated");
+#undef STCAT_TC_LAUNCH
+    return check_launch("gemm_tc_kernel");
 }
 
 }  // namespace stcat
