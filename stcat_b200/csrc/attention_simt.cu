@@ -384,6 +384,12 @@ static int launch_bwd(const void* q1, const void* q2, int64_t ldq, const void* k
     return check_launch("attn_bwd_dkv_kernel");
 }
 
+// attention_tc.cu: tcgen05 kernel for the spatial encoder's shape class
+int attn_tc_fwd_supported(int dtype, const void* q2, const void* p_avg, int B, int H, int Lq, int Lk, const void* q,
+                          const void* k, const void* v, const void* o, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo);
+int attn_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                const uint8_t* key_mask, float* lse, int B, int H, int S, float scale, cudaStream_t st);
+
 }  // namespace stcat
 
 using namespace stcat;
@@ -399,6 +405,8 @@ extern "C" int stcat_attention_fwd(const void* q1, const void* q2, int64_t ldq, 
     STCAT_REQUIRE(B <= 65535 && H <= 65535, STCAT_ESHAPE, "attention_fwd: B/H exceed grid limits");
     if (B == 0 || Lq == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    if (attn_tc_fwd_supported(dtype, q2, p_avg, B, H, Lq, Lk, q1, k1, v, o, ldq, ldk, ldv, ldo))
+        return attn_tc_fwd(q1, ldq, k1, ldk, v, ldv, o, ldo, key_mask, lse, B, H, Lq, scale, st);
     if (dtype == STCAT_F32)
         return q2 ? launch_fwd<float, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st)
                   : launch_fwd<float, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st);

@@ -1,0 +1,290 @@
+// tcgen05 self-attention core for the spatial encoder (reference modal_encoder.py:161-168 -> torch
+// nn.MultiheadAttention bmm/softmax/bmm, functional.py:6630-6665): B = T frames x H = 8 heads of
+// softmax(Q K^T * scale + key mask) V with head dim 32 and S = 1 + HW + L <= 256 tokens per frame.
+//
+// Forward.  Work item = (frame, head, 128-query tile).  Per item
+//   TMA    : Q tile [128 x 32], K [256 x 32], V [256 x 32] bf16 head slices of the packed qkv buffer via 3-D
+//            tensor maps {cols, S, frames} (64B swizzle).  Rows >= S of a frame are out of bounds -> zero-filled,
+//            so a tile never sees its neighbour frame and padded keys contribute exactly 0.
+//   MMA    : S = Q K^T        tcgen05.mma 128 x Npad x 16 (x2 for dh = 32) -> 256 fp32 TMEM columns
+//   softmax: one thread per query row (128 threads): tcgen05.ld the row, masked max, exp2, row sum, P as bf16 into
+//            a 128B-swizzled K-major smem tile [128 x 256]
+//   MMA    : O = P V          tcgen05.mma 128 x 32 x 16, ceil(S/16) steps, V as MN-major operand (no transpose)
+//   epilog : tcgen05.ld O (32 columns), * 1/rowsum, bf16, 64 B per row straight to global; lse for the backward
+// Two buffer sets (smem Q/K/V/P + 256 TMEM columns each) ping-pong between two softmax warpgroups so the tensor
+// pipe and TMA run under the softmax of the other item (exp2 on the MUFU pipe is the bound: head dim 32 gives
+// only 64 MMA FLOP per exponential).
+//
+// Backward: see attn_tc_bwd_kernel below.
+#include "tc_common.cuh"
+#include <math.h>
+#include <stdlib.h>
+
+namespace stcat {
+namespace tc {
+
+constexpr int AT_DH = 32;
+constexpr int AT_QT = 128;          // query rows per item
+constexpr int AT_KMAX = 256;        // max keys (= max S)
+constexpr int AT_Q_BYTES = AT_QT * AT_DH * 2;      // 8 KB
+constexpr int AT_KV_BYTES = AT_KMAX * AT_DH * 2;   // 16 KB
+constexpr int AT_P_BYTES = AT_QT * AT_KMAX * 2;    // 64 KB
+constexpr int AT_SET_BYTES = AT_Q_BYTES + 2 * AT_KV_BYTES + AT_P_BYTES;  // 104 KB
+constexpr int AT_FWD_SMEM = 2 * AT_SET_BYTES + 1024 + 256;
+constexpr int AT_FWD_THREADS = 384;
+
+struct AttnFwdParams {
+    __nv_bfloat16* o;
+    int64_t ldo;
+    const uint8_t* key_mask;  // [B, S] or null
+    float* lse;               // [B, H, S]
+    int B, H, S, nqt;
+    float scale;
+};
+
+__global__ void __launch_bounds__(AT_FWD_THREADS, 1)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = base + 2 * AT_SET_BYTES;
+    // per set: 0 load_full, 1 load_free, 2 s_full, 3 p_full, 4 o_full, 5 tmem_free
+    auto bar = [&](int set, int which) { return bar_base + 8u * (set * 6 + which); };
+    const uint32_t tmem_slot = bar_base + 8u * 12;
+    auto sQ = [&](int set) { return base + set * AT_SET_BYTES; };
+    auto sK = [&](int set) { return base + set * AT_SET_BYTES + AT_Q_BYTES; };
+    auto sV = [&](int set) { return base + set * AT_SET_BYTES + AT_Q_BYTES + AT_KV_BYTES; };
+    auto sP = [&](int set) { return base + set * AT_SET_BYTES + AT_Q_BYTES + 2 * AT_KV_BYTES; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = p.B * p.H * p.nqt;
+    const int n_mine = (total > (int)blockIdx.x) ? (total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int S = p.S;
+    const int nk16 = (S + 15) >> 4;          // PV contraction steps
+    const int npad = nk16 << 4;              // N of the score MMA
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmK)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar(s, 0), 1); mbar_init(bar(s, 1), 1); mbar_init(bar(s, 2), 1);
+            mbar_init(bar(s, 3), 128); mbar_init(bar(s, 4), 1); mbar_init(bar(s, 5), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // P tiles start as zeros: key columns the softmax never writes must not hold NaN bit patterns
+    for (int i = threadIdx.x; i < 2 * AT_P_BYTES / 16; i += AT_FWD_THREADS) {
+        const int set = i / (AT_P_BYTES / 16), off = i % (AT_P_BYTES / 16);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sP(set) + off * 16), "r"(0) : "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    auto decode = [&](int i, int& b, int& h, int& qt) {
+        const int w = blockIdx.x + i * gridDim.x;
+        qt = w % p.nqt;
+        const int t = w / p.nqt;
+        h = t % p.H;
+        b = t / p.H;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < n_mine; ++i) {
+                const int set = i & 1, k = i >> 1;
+                int b, h, qt;
+                decode(i, b, h, qt);
+                mbar_wait(bar(set, 1), (k & 1) ^ 1);
+                mbar_expect_tx(bar(set, 0), AT_Q_BYTES + 2 * AT_KV_BYTES);
+                tma_load_3d(sQ(set), &tmQ, bar(set, 0), h * AT_DH, qt * AT_QT, b);
+                tma_load_3d(sK(set), &tmK, bar(set, 0), h * AT_DH, 0, b);
+                tma_load_3d(sV(set), &tmV, bar(set, 0), h * AT_DH, 0, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_s = make_idesc(128, npad, false, false);
+            const uint32_t idesc_o = make_idesc(128, AT_DH, false, true);
+            for (int i = 0; i <= n_mine; ++i) {
+                if (i < n_mine) {
+                    const int set = i & 1, k = i >> 1;
+                    mbar_wait(bar(set, 0), k & 1);
+                    mbar_wait(bar(set, 5), (k & 1) ^ 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int kk = 0; kk < AT_DH / 16; ++kk) {
+                        const uint64_t ad = make_desc(sQ(set) + kk * 32, 16, 512, LAYOUT_SW64);
+                        const uint64_t bd = make_desc(sK(set) + kk * 32, 16, 512, LAYOUT_SW64);
+                        umma_bf16(tmem_base + set * 256, ad, bd, idesc_s, kk > 0 ? 1u : 0u);
+                    }
+                    umma_commit(bar(set, 2));
+                }
+                if (i >= 1) {
+                    const int j = i - 1, set = j & 1, k = j >> 1;
+                    mbar_wait(bar(set, 3), k & 1);
+                    tc_fence_after();
+                    for (int t = 0; t < nk16; ++t) {
+                        const uint64_t ad = make_desc(sP(set) + (t >> 2) * 16384 + (t & 3) * 32, 16, 1024, LAYOUT_SW128);
+                        const uint64_t bd = make_desc(sV(set) + t * 1024, 512, 512, LAYOUT_SW64);
+                        umma_bf16(tmem_base + set * 256, ad, bd, idesc_o, t > 0 ? 1u : 0u);
+                    }
+                    umma_commit(bar(set, 4));
+                    umma_commit(bar(set, 1));
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int g = (warp - 4) >> 2;      // softmax warpgroup = buffer set
+        const int q4 = warp & 3;            // TMEM lane quadrant
+        const int row = q4 * 32 + lane;
+        const float sc = p.scale * 1.4426950408889634f;
+        const int nchunk = (S + 31) >> 5;
+        for (int i = g; i < n_mine; i += 2) {
+            const int set = g, k = i >> 1;
+            int b, h, qt;
+            decode(i, b, h, qt);
+            // key mask -> one bit per key (1 = masked), 32 keys per word, identical in every warp
+            uint32_t mw[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int key = c * 32 + lane;
+                bool m = key >= S;
+                if (!m && p.key_mask) m = p.key_mask[(int64_t)b * S + key] != 0;
+                mw[c] = __ballot_sync(0xffffffffu, m);
+            }
+            mbar_wait(bar(set, 2), k & 1);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + set * 256 + ((uint32_t)(q4 * 32) << 16);
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (c < nchunk) {  // warp-uniform
+                    uint32_t r[32];
+                    tmem_ld32(t_row + c * 32, r);
+                    tmem_ld_wait();
+                    const uint32_t w = mw[c];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (!((w >> e) & 1u)) mx = fmaxf(mx, __uint_as_float(r[e]));
+                }
+            }
+            const float ms = (mx == -INFINITY) ? 0.f : mx * sc;
+            float sum = 0.f;
+            const uint32_t prow = sP(set) + row * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (c >= nchunk) break;  // warp-uniform
+                uint32_t r[32];
+                tmem_ld32(t_row + c * 32, r);
+                tmem_ld_wait();
+                const uint32_t w = mw[c];
+                uint32_t pk[16];
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    float p0 = ((w >> e) & 1u) ? 0.f : ex2_approx(fmaf(__uint_as_float(r[e]), sc, -ms));
+                    float p1 = ((w >> (e + 1)) & 1u) ? 0.f : ex2_approx(fmaf(__uint_as_float(r[e + 1]), sc, -ms));
+                    sum += p0 + p1;
+                    __nv_bfloat162 bb = __floats2bfloat162_rn(p0, p1);
+                    pk[e >> 1] = *reinterpret_cast<uint32_t*>(&bb);
+                }
+                const uint32_t blk = prow + (c >> 1) * 16384;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int chunk = ((c & 1) * 4 + j) ^ (row & 7);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + chunk * 16), "r"(pk[4 * j]),
+                                 "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(bar(set, 3));
+            // ---- epilogue ----
+            mbar_wait(bar(set, 4), k & 1);
+            tc_fence_after();
+            uint32_t r[32];
+            tmem_ld32(t_row, r);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(bar(set, 5));
+            const int q = qt * AT_QT + row;
+            if (q < S) {
+                const float inv = sum > 0.f ? 1.f / sum : 0.f;
+                uint32_t ob[16];
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    __nv_bfloat162 bb = __floats2bfloat162_rn(__uint_as_float(r[e]) * inv, __uint_as_float(r[e + 1]) * inv);
+                    ob[e >> 1] = *reinterpret_cast<uint32_t*>(&bb);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(p.o + ((int64_t)b * S + q) * p.ldo + h * AT_DH);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
+                p.lse[((int64_t)b * p.H + h) * S + q] = sum > 0.f ? mx * p.scale + logf(sum) : -INFINITY;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
+}  // namespace tc
+
+// --------------------------------------------------------------------------------------------------
+// dispatch (called from stcat_attention_fwd)
+// --------------------------------------------------------------------------------------------------
+int attn_tc_fwd_supported(int dtype, const void* q2, const void* p_avg, int B, int H, int Lq, int Lk, const void* q,
+                          const void* k, const void* v, const void* o, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo) {
+    if (getenv("STCAT_DISABLE_TC_ATTN")) return 0;
+    if (dtype != STCAT_BF16 || q2 || p_avg) return 0;
+    if (Lq != Lk || Lq < 64 || Lq > tc::AT_KMAX) return 0;
+    if (B * H < 16) return 0;
+    auto al = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+    if (!al(q) || !al(k) || !al(v) || !al(o)) return 0;
+    if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return 0;
+    return 1;
+}
+
+int attn_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                const uint8_t* key_mask, float* lse, int B, int H, int S, float scale, cudaStream_t st) {
+    using namespace tc;
+    CUtensorMap tmQ, tmK, tmV;
+    int rc;
+    if ((rc = make_map_3d(&tmQ, q, B, S, (int64_t)H * AT_DH, ldq, AT_DH, AT_QT, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_map_3d(&tmK, k, B, S, (int64_t)H * AT_DH, ldk, AT_DH, AT_KMAX, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_map_3d(&tmV, v, B, S, (int64_t)H * AT_DH, ldv, AT_DH, AT_KMAX, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    AttnFwdParams p;
+    p.o = (__nv_bfloat16*)o;
+    p.ldo = ldo;
+    p.key_mask = key_mask;
+    p.lse = lse;
+    p.B = B; p.H = H; p.S = S;
+    p.nqt = (S + AT_QT - 1) / AT_QT;
+    p.scale = scale;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
+        if (e != cudaSuccess) return set_err((int)e, "attn_tc_fwd: smem attribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int total = B * H * p.nqt;
+    const int sms = num_sms();
+    const int grid = total < sms ? total : sms;
+    attn_tc_fwd_kernel<<<grid, AT_FWD_THREADS, AT_FWD_SMEM, st>>>(tmQ, tmK, tmV, p);
+    return check_launch("attn_tc_fwd_kernel");
+}
+
+}  // namespace stcat
