@@ -87,13 +87,16 @@ STCAT_API int stcat_layernorm_bwd(const float* dy, const float* x, const float* 
  *   p_avg[B,Lq,Lk]  : optional (may be NULL); receives mean over heads of p (the `weights` output,
  *                     query_decoder.py:341,604; must be zero-filled by the caller)
  * bwd: dq1, dq2, dk1, dk2, dv get the gradients (fully overwritten); dp_avg (may be NULL) is the gradient
- *      flowing into p_avg.  delta[B,H,Lq] is caller-provided scratch.
+ *      flowing into p_avg.  delta[B,H,Lq] is caller-provided scratch.  o (may be NULL) is the forward output:
+ *      with it the tensor-core kernel takes delta_i = dO_i . O_i instead of a second pass over the keys.
+ * bf16 operands with Lq = Lk in [64, 256], a single score part and no p_avg (the spatial encoder's shape class)
+ * run the tcgen05 kernels of attention_tc.cu; everything else runs the exact SIMT kernels.
  * ---------------------------------------------------------------------------------------------- */
 STCAT_API int stcat_attention_fwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2, int64_t ldk,
                         const void* v, int64_t ldv, void* o, int64_t ldo, int dtype, const uint8_t* key_mask,
                         float* lse, float* p_avg, int B, int H, int Lq, int Lk, int dh, float scale, void* stream);
 STCAT_API int stcat_attention_bwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2, int64_t ldk,
-                        const void* v, int64_t ldv, const void* d_o, int64_t lddo, int dtype,
+                        const void* v, int64_t ldv, const void* o, int64_t ldo, const void* d_o, int64_t lddo, int dtype,
                         const uint8_t* key_mask, const float* lse, const float* dp_avg, float* delta,
                         void* dq1, void* dq2, int64_t lddq, void* dk1, void* dk2, int64_t lddk, void* dv,
                         int64_t lddv, int B, int H, int Lq, int Lk, int dh, float scale, void* stream);

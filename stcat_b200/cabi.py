@@ -31,8 +31,8 @@ SIGNATURES = {
     "stcat_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P]),
     "stcat_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "stcat_attention_fwd": (c_int, [_P, _P, _L, _P, _P, _L, _P, _L, _P, _L, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
-    "stcat_attention_bwd": (c_int, [_P, _P, _L, _P, _P, _L, _P, _L, _P, _L, _I, _P, _P, _P, _P, _P, _P, _L, _P, _P, _L,
-                                    _P, _L, _I, _I, _I, _I, _I, _F, _P]),
+    "stcat_attention_bwd": (c_int, [_P, _P, _L, _P, _P, _L, _P, _L, _P, _L, _P, _L, _I, _P, _P, _P, _P, _P, _P, _L, _P, _P,
+                                    _L, _P, _L, _I, _I, _I, _I, _I, _F, _P]),
     "stcat_add": (c_int, [_P, _P, _P, _P, _L, _P]),
     "stcat_relu_bwd": (c_int, [_P, _I, _P, _I, _L, _P]),
     "stcat_cast_bf16": (c_int, [_P, _P, _L, _L, _I, _P]),
@@ -183,7 +183,7 @@ class CudaBackend:
         self.launches += 1
 
     def attention_bwd(self, q1, q2, k1, k2, v, d_o, key_mask, lse, dp_avg, delta, dq1, dq2, dk1, dk2, dv, B, H, Lq, Lk,
-                      scale):
+                      scale, o=None):
         (qp, ldq, qd) = self._mat(q1, "q1")
         (kp, ldk, _), (vp, ldv, _), (gp, ldg, _) = self._mat(k1, "k1"), self._mat(v, "v"), self._mat(d_o, "d_o")
         (dqp, lddq, _), (dkp, lddk, _), (dvp, lddv, _) = self._mat(dq1, "dq1"), self._mat(dk1, "dk1"), self._mat(dv, "dv")
@@ -194,7 +194,8 @@ class CudaBackend:
             dq2p, lddq2, _ = self._mat(dq2, "dq2")
             dk2p, lddk2, _ = self._mat(dk2, "dk2")
             assert ldq2 == ldq and ldk2 == ldk and lddq2 == lddq and lddk2 == lddk
-        self._rc(self.lib.stcat_attention_bwd(qp, q2p, ldq, kp, k2p, ldk, vp, ldv, gp, ldg, qd,
+        op, ldo = (None, 0) if o is None else self._mat(o, "o")[:2]
+        self._rc(self.lib.stcat_attention_bwd(qp, q2p, ldq, kp, k2p, ldk, vp, ldv, op, ldo, gp, ldg, qd,
                                               self._flat(key_mask, "key_mask", torch.uint8), self._flat(lse, "lse", torch.float32),
                                               self._flat(dp_avg, "dp_avg", torch.float32), self._flat(delta, "delta", torch.float32),
                                               dqp, dq2p, lddq, dkp, dk2p, lddk, dvp, lddv, B, H, Lq, Lk, 32, float(scale),

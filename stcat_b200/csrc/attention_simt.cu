@@ -390,6 +390,15 @@ int attn_tc_fwd_supported(int dtype, const void* q2, const void* p_avg, int B, i
 int attn_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
                 const uint8_t* key_mask, float* lse, int B, int H, int S, float scale, cudaStream_t st);
 
+int attn_tc_bwd_supported(int dtype, const void* q2, const void* dp_avg, const void* o, int B, int H, int Lq, int Lk,
+                          const void* q, const void* k, const void* v, const void* d_o, const void* dq, const void* dk,
+                          const void* dv, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddo, int64_t lddq,
+                          int64_t lddk, int64_t lddv);
+int attn_tc_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o,
+                int64_t ldo, const void* d_o, int64_t lddo, const uint8_t* key_mask, const float* lse, void* dq,
+                int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int S, float scale,
+                cudaStream_t st);
+
 }  // namespace stcat
 
 using namespace stcat;
@@ -417,7 +426,8 @@ extern "C" int stcat_attention_fwd(const void* q1, const void* q2, int64_t ldq, 
 }
 
 extern "C" int stcat_attention_bwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2,
-                                   int64_t ldk, const void* v, int64_t ldv, const void* d_o, int64_t lddo, int dtype,
+                                   int64_t ldk, const void* v, int64_t ldv, const void* o, int64_t ldo,
+                                   const void* d_o, int64_t lddo, int dtype,
                                    const uint8_t* key_mask, const float* lse, const float* dp_avg, float* delta,
                                    void* dq1, void* dq2, int64_t lddq, void* dk1, void* dk2, int64_t lddk, void* dv,
                                    int64_t lddv, int B, int H, int Lq, int Lk, int dh, float scale, void* stream) {
@@ -429,6 +439,10 @@ extern "C" int stcat_attention_bwd(const void* q1, const void* q2, int64_t ldq, 
     STCAT_REQUIRE(B <= 65535 && H <= 65535, STCAT_ESHAPE, "attention_bwd: B/H exceed grid limits");
     if (B == 0 || Lq == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    if (attn_tc_bwd_supported(dtype, q2, dp_avg, o, B, H, Lq, Lk, q1, k1, v, d_o, dq1, dk1, dv, ldq, ldk, ldv, ldo, lddo,
+                              lddq, lddk, lddv))
+        return attn_tc_bwd(q1, ldq, k1, ldk, v, ldv, o, ldo, d_o, lddo, key_mask, lse, dq1, lddq, dk1, lddk, dv, lddv, B, H,
+                           Lq, scale, st);
     if (dtype == STCAT_F32)
         return q2 ? launch_bwd<float, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st)
                   : launch_bwd<float, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st);

@@ -241,6 +241,294 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
 }
 
+
+// ==================================================================================================
+// Backward.  Work item = (frame, head): all S <= 256 queries and keys.  TMA brings Q, K, V, dO head slices
+// [256 x 32] (64B swizzle, rows >= S zero-filled).  For every (128-query tile qt, 128-key tile kt) block:
+//   MMA     S  = Q_qt K_kt^T, dP = dO_qt V_kt^T                 2 x (128 x 128 x 32) -> 2 x 128 TMEM columns
+//   threads p  = exp2(s*scale*log2e - lse*log2e), ds = p (dp - delta) scale, delta_i = dO_i . O_i;
+//           256 threads: a (row, 64-column half) each; P and dS as bf16 into 128B-swizzled smem tiles [128 x 128]
+//   MMA     dV_kt += P^T dO_qt, dK_kt += dS^T Q_qt   (the P / dS tiles read as MN-major A operands: no transpose)
+//           dQ_qt += dS K_kt                           (the dS tile read as K-major A operand)
+// dQ (per qt) and dK, dV (per item) accumulate in TMEM and are written as bf16, 64 B per row, straight to global.
+// TMEM columns: S 0..127 | dP 128..255 | dQ 256..287 | dK 288..351 | dV 352..415.
+// ==================================================================================================
+constexpr int AB_LOAD_BYTES = 4 * AT_KV_BYTES;             // Q, K, V, dO: 64 KB per item
+constexpr int AB_TILE_BYTES = 128 * 128 * 2;               // P or dS tile: 32 KB
+constexpr int AB_SMEM = 2 * AB_LOAD_BYTES + 2 * AB_TILE_BYTES + 1024 + 256;
+constexpr int AB_THREADS = 384;
+constexpr uint32_t AB_COL_S = 0, AB_COL_DP = 128, AB_COL_DQ = 256, AB_COL_DK = 288, AB_COL_DV = 352;
+
+struct AttnBwdParams {
+    const __nv_bfloat16* o;    // forward output [B*S, ldo]
+    const __nv_bfloat16* d_o;  // [B*S, lddo]
+    int64_t ldo, lddo;
+    __nv_bfloat16 *dq, *dk, *dv;
+    int64_t lddq, lddk, lddv;
+    const uint8_t* key_mask;
+    const float* lse;
+    int B, H, S;
+    float scale;
+};
+
+__device__ __forceinline__ void store_row_bf16x32(__nv_bfloat16* dst, const uint32_t (&r)[32]) {
+    uint32_t ob[16];
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) {
+        __nv_bfloat162 bb = __floats2bfloat162_rn(__uint_as_float(r[e]), __uint_as_float(r[e + 1]));
+        ob[e >> 1] = *reinterpret_cast<uint32_t*>(&bb);
+    }
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d4[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
+}
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                   const AttnBwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    auto sQ = [&](int set) { return base + set * AB_LOAD_BYTES; };
+    auto sK = [&](int set) { return base + set * AB_LOAD_BYTES + AT_KV_BYTES; };
+    auto sV = [&](int set) { return base + set * AB_LOAD_BYTES + 2 * AT_KV_BYTES; };
+    auto sDO = [&](int set) { return base + set * AB_LOAD_BYTES + 3 * AT_KV_BYTES; };
+    const uint32_t sP = base + 2 * AB_LOAD_BYTES;
+    const uint32_t sDS = sP + AB_TILE_BYTES;
+    const uint32_t bar_base = sDS + AB_TILE_BYTES;
+    // 0,1 load_full[set]; 2,3 load_free[set]; 4 sd_full; 5 sd_free; 6 pds_full; 7 pds_free; 8 dq_full; 9 dq_free;
+    // 10 dkv_full; 11 dkv_free
+    auto bar = [&](int which) { return bar_base + 8u * which; };
+    const uint32_t tmem_slot = bar_base + 8u * 12;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = p.B * p.H;
+    const int n_mine = (total > (int)blockIdx.x) ? (total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int S = p.S;
+    const int nqt = (S + 127) >> 7;  // query tiles == key tiles
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmK)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmDO)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(bar(i), 1);
+        mbar_init(bar(4), 1); mbar_init(bar(5), 256); mbar_init(bar(6), 256); mbar_init(bar(7), 1);
+        mbar_init(bar(8), 1); mbar_init(bar(9), 256); mbar_init(bar(10), 1); mbar_init(bar(11), 256);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < n_mine; ++it) {
+                const int set = it & 1, k = it >> 1;
+                const int w = blockIdx.x + it * gridDim.x;
+                const int h = w % p.H, b = w / p.H;
+                mbar_wait(bar(2 + set), (k & 1) ^ 1);
+                mbar_expect_tx(bar(set), AB_LOAD_BYTES);
+                tma_load_3d(sQ(set), &tmQ, bar(set), h * AT_DH, 0, b);
+                tma_load_3d(sK(set), &tmK, bar(set), h * AT_DH, 0, b);
+                tma_load_3d(sV(set), &tmV, bar(set), h * AT_DH, 0, b);
+                tma_load_3d(sDO(set), &tmDO, bar(set), h * AT_DH, 0, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_s = make_idesc(128, 128, false, false);   // S, dP: A K-major, B K-major
+            const uint32_t idesc_t = make_idesc(128, AT_DH, true, true);   // dV, dK: A MN-major (tile^T), B MN-major
+            const uint32_t idesc_q = make_idesc(128, AT_DH, false, true);  // dQ: A K-major, B MN-major
+            uint32_t nb = 0, nq = 0;
+            for (int it = 0; it < n_mine; ++it) {
+                const int set = it & 1;
+                mbar_wait(bar(set), (it >> 1) & 1);
+                for (int qt = 0; qt < nqt; ++qt) {
+                    const int nq16 = min(8, (S - qt * 128 + 15) >> 4);  // 16-row groups of valid queries
+                    for (int kt = 0; kt < nqt; ++kt) {
+                        const int nk16 = min(8, (S - kt * 128 + 15) >> 4);
+                        mbar_wait(bar(5), (nb & 1) ^ 1);
+                        tc_fence_after();
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const uint64_t aq = make_desc(sQ(set) + qt * 8192 + kk * 32, 16, 512, LAYOUT_SW64);
+                            const uint64_t bk = make_desc(sK(set) + kt * 8192 + kk * 32, 16, 512, LAYOUT_SW64);
+                            umma_bf16(tmem_base + AB_COL_S, aq, bk, idesc_s, kk);
+                        }
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const uint64_t ad = make_desc(sDO(set) + qt * 8192 + kk * 32, 16, 512, LAYOUT_SW64);
+                            const uint64_t bv = make_desc(sV(set) + kt * 8192 + kk * 32, 16, 512, LAYOUT_SW64);
+                            umma_bf16(tmem_base + AB_COL_DP, ad, bv, idesc_s, kk);
+                        }
+                        umma_commit(bar(4));
+                        mbar_wait(bar(6), nb & 1);
+                        if (qt == 0 && kt == 0) mbar_wait(bar(11), (it & 1) ^ 1);
+                        if (kt == 0) mbar_wait(bar(9), (nq & 1) ^ 1);
+                        tc_fence_after();
+                        for (int t = 0; t < nq16; ++t) {  // contraction over the queries of this tile
+                            const uint64_t ap = make_desc(sP + t * 2048, 16384, 1024, LAYOUT_SW128);
+                            const uint64_t bd = make_desc(sDO(set) + (qt * 128 + t * 16) * 64, 512, 512, LAYOUT_SW64);
+                            umma_bf16(tmem_base + AB_COL_DV + kt * 32, ap, bd, idesc_t, (qt > 0 || t > 0) ? 1u : 0u);
+                            const uint64_t as = make_desc(sDS + t * 2048, 16384, 1024, LAYOUT_SW128);
+                            const uint64_t bq = make_desc(sQ(set) + (qt * 128 + t * 16) * 64, 512, 512, LAYOUT_SW64);
+                            umma_bf16(tmem_base + AB_COL_DK + kt * 32, as, bq, idesc_t, (qt > 0 || t > 0) ? 1u : 0u);
+                        }
+                        for (int t = 0; t < nk16; ++t) {  // contraction over the keys of this tile
+                            const uint64_t as = make_desc(sDS + (t >> 2) * 16384 + (t & 3) * 32, 16, 1024, LAYOUT_SW128);
+                            const uint64_t bk = make_desc(sK(set) + (kt * 128 + t * 16) * 64, 512, 512, LAYOUT_SW64);
+                            umma_bf16(tmem_base + AB_COL_DQ, as, bk, idesc_q, (kt > 0 || t > 0) ? 1u : 0u);
+                        }
+                        umma_commit(bar(7));
+                        if (kt == nqt - 1) { umma_commit(bar(8)); ++nq; }
+                        ++nb;
+                    }
+                }
+                umma_commit(bar(10));
+                umma_commit(bar(2 + set));
+            }
+        }
+    } else if (warp >= 4) {
+        const int wg = (warp - 4) >> 2;   // column half of the block: keys [wg*64, wg*64+64)
+        const int q4 = warp & 3;
+        const int row = q4 * 32 + lane;
+        const float sc = p.scale * 1.4426950408889634f;
+        const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+        uint32_t nb = 0, nq = 0;
+        for (int it = 0; it < n_mine; ++it) {
+            const int w = blockIdx.x + it * gridDim.x;
+            const int h = w % p.H, b = w / p.H;
+            uint32_t mw[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int key = c * 32 + lane;
+                bool m = key >= S;
+                if (!m && p.key_mask) m = p.key_mask[(int64_t)b * S + key] != 0;
+                mw[c] = __ballot_sync(0xffffffffu, m);
+            }
+#pragma unroll
+            for (int qt = 0; qt < 2; ++qt) {
+                if (qt >= nqt) break;
+                const int q = qt * 128 + row;
+                const bool qvalid = q < S;
+                float delta = 0.f, lse2 = 0.f;
+                if (qvalid) {
+                    const uint4* po = reinterpret_cast<const uint4*>(p.o + ((int64_t)b * S + q) * p.ldo + h * AT_DH);
+                    const uint4* pg = reinterpret_cast<const uint4*>(p.d_o + ((int64_t)b * S + q) * p.lddo + h * AT_DH);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 a = __ldg(po + j), g = __ldg(pg + j);
+                        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[e]));
+                            const float2 fg = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[e]));
+                            delta = fmaf(fa.x, fg.x, delta);
+                            delta = fmaf(fa.y, fg.y, delta);
+                        }
+                    }
+                    lse2 = p.lse[((int64_t)b * p.H + h) * S + q] * 1.4426950408889634f;
+                }
+                const bool dead = !qvalid || lse2 == -INFINITY;  // padded query row or fully masked row
+#pragma unroll
+                for (int kt = 0; kt < 2; ++kt) {
+                    if (kt >= nqt) break;
+                    mbar_wait(bar(4), nb & 1);
+                    mbar_wait(bar(7), (nb & 1) ^ 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t rs[32], rd[32];
+                        const uint32_t col = wg * 64 + c * 32;
+                        tmem_ld32(tmem_base + lane_off + AB_COL_S + col, rs);
+                        tmem_ld32(tmem_base + lane_off + AB_COL_DP + col, rd);
+                        tmem_ld_wait();
+                        const uint32_t wmask = dead ? 0xffffffffu : (wg ? mw[kt * 4 + 2 + c] : mw[kt * 4 + c]);
+                        uint32_t pp[16], pd[16];
+#pragma unroll
+                        for (int e = 0; e < 32; e += 2) {
+                            float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
+                            if (!((wmask >> e) & 1u)) {
+                                p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), sc, -lse2));
+                                d0 = p0 * (__uint_as_float(rd[e]) - delta) * p.scale;
+                            }
+                            if (!((wmask >> (e + 1)) & 1u)) {
+                                p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), sc, -lse2));
+                                d1 = p1 * (__uint_as_float(rd[e + 1]) - delta) * p.scale;
+                            }
+                            __nv_bfloat162 bp = __floats2bfloat162_rn(p0, p1), bd = __floats2bfloat162_rn(d0, d1);
+                            pp[e >> 1] = *reinterpret_cast<uint32_t*>(&bp);
+                            pd[e >> 1] = *reinterpret_cast<uint32_t*>(&bd);
+                        }
+                        const uint32_t off = wg * 16384 + row * 128;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int chunk = (c * 4 + j) ^ (row & 7);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + off + chunk * 16), "r"(pp[4 * j]),
+                                         "r"(pp[4 * j + 1]), "r"(pp[4 * j + 2]), "r"(pp[4 * j + 3]) : "memory");
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off + chunk * 16), "r"(pd[4 * j]),
+                                         "r"(pd[4 * j + 1]), "r"(pd[4 * j + 2]), "r"(pd[4 * j + 3]) : "memory");
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(bar(5));
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(bar(6));
+                    ++nb;
+                }
+                // dQ of this query tile: wg 0 -> dims 0..15, wg 1 -> dims 16..31
+                mbar_wait(bar(8), nq & 1);
+                tc_fence_after();
+                uint32_t r16[16];
+                tmem_ld16(tmem_base + lane_off + AB_COL_DQ + wg * 16, r16);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(bar(9));
+                ++nq;
+                if (qvalid) {
+                    uint32_t ob[8];
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) {
+                        __nv_bfloat162 bb = __floats2bfloat162_rn(__uint_as_float(r16[e]), __uint_as_float(r16[e + 1]));
+                        ob[e >> 1] = *reinterpret_cast<uint32_t*>(&bb);
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(p.dq + ((int64_t)b * S + q) * p.lddq + h * AT_DH + wg * 16);
+                    dst[0] = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+                    dst[1] = make_uint4(ob[4], ob[5], ob[6], ob[7]);
+                }
+            }
+            // dK (wg 0) and dV (wg 1) of the whole item: thread row = key
+            mbar_wait(bar(10), it & 1);
+            tc_fence_after();
+            uint32_t r0[32], r1[32];
+            tmem_ld32(tmem_base + lane_off + (wg ? AB_COL_DV : AB_COL_DK), r0);
+            if (nqt > 1) tmem_ld32(tmem_base + lane_off + (wg ? AB_COL_DV : AB_COL_DK) + 32, r1);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(bar(11));
+            __nv_bfloat16* dst = wg ? p.dv : p.dk;
+            const int64_t ldd = wg ? p.lddv : p.lddk;
+            if (row < S) store_row_bf16x32(dst + ((int64_t)b * S + row) * ldd + h * AT_DH, r0);
+            if (nqt > 1 && 128 + row < S) store_row_bf16x32(dst + ((int64_t)b * S + 128 + row) * ldd + h * AT_DH, r1);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
 }  // namespace tc
 
 // --------------------------------------------------------------------------------------------------
@@ -285,6 +573,54 @@ int attn_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
     const int grid = total < sms ? total : sms;
     attn_tc_fwd_kernel<<<grid, AT_FWD_THREADS, AT_FWD_SMEM, st>>>(tmQ, tmK, tmV, p);
     return check_launch("attn_tc_fwd_kernel");
+}
+
+int attn_tc_bwd_supported(int dtype, const void* q2, const void* dp_avg, const void* o, int B, int H, int Lq, int Lk,
+                          const void* q, const void* k, const void* v, const void* d_o, const void* dq, const void* dk,
+                          const void* dv, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddo, int64_t lddq,
+                          int64_t lddk, int64_t lddv) {
+    if (getenv("STCAT_DISABLE_TC_ATTN") || getenv("STCAT_DISABLE_TC_ATTN_BWD")) return 0;
+    if (dtype != STCAT_BF16 || q2 || dp_avg || !o) return 0;
+    if (Lq != Lk || Lq < 64 || Lq > tc::AT_KMAX) return 0;
+    if (B * H < 16) return 0;
+    auto al = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+    if (!al(q) || !al(k) || !al(v) || !al(o) || !al(d_o) || !al(dq) || !al(dk) || !al(dv)) return 0;
+    if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8) || (lddo % 8) || (lddq % 8) || (lddk % 8) || (lddv % 8)) return 0;
+    return 1;
+}
+
+int attn_tc_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o,
+                int64_t ldo, const void* d_o, int64_t lddo, const uint8_t* key_mask, const float* lse, void* dq,
+                int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int S, float scale,
+                cudaStream_t st) {
+    using namespace tc;
+    CUtensorMap tmQ, tmK, tmV, tmDO;
+    int rc;
+    const int64_t E = (int64_t)H * AT_DH;
+    if ((rc = make_map_3d(&tmQ, q, B, S, E, ldq, AT_DH, AT_KMAX, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_map_3d(&tmK, k, B, S, E, ldk, AT_DH, AT_KMAX, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_map_3d(&tmV, v, B, S, E, ldv, AT_DH, AT_KMAX, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_map_3d(&tmDO, d_o, B, S, E, lddo, AT_DH, AT_KMAX, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    AttnBwdParams p;
+    p.o = (const __nv_bfloat16*)o; p.d_o = (const __nv_bfloat16*)d_o;
+    p.ldo = ldo; p.lddo = lddo;
+    p.dq = (__nv_bfloat16*)dq; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
+    p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
+    p.key_mask = key_mask;
+    p.lse = lse;
+    p.B = B; p.H = H; p.S = S;
+    p.scale = scale;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+        if (e != cudaSuccess) return set_err((int)e, "attn_tc_bwd: smem attribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int total = B * H;
+    const int sms = num_sms();
+    const int grid = total < sms ? total : sms;
+    attn_tc_bwd_kernel<<<grid, AB_THREADS, AB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, p);
+    return check_launch("attn_tc_bwd_kernel");
 }
 
 }  // namespace stcat

@@ -462,7 +462,7 @@ class SelfAttnBlockFn(Function):
         dqkv = _new(R, 3 * d, od, dy)
         delta = torch.empty(B, H, L, dtype=f32, device=dy.device)
         be.attention_bwd(qkv[:, :d], None, qkv[:, d:2 * d], None, qkv[:, 2 * d:], d_o, key_mask, lse, None, delta,
-                         dqkv[:, :d], None, dqkv[:, d:2 * d], None, dqkv[:, 2 * d:], B, H, L, L, scale)
+                         dqkv[:, :d], None, dqkv[:, d:2 * d], None, dqkv[:, 2 * d:], B, H, L, L, scale, o=o)
         dwi = _new(3 * d, d, f32, dy)
         dbi = torch.empty(3 * d, dtype=f32, device=dy.device)
         be.linear_bwd_weight(dqkv[:, : 2 * d], qk_in, dwi[: 2 * d], dbi[: 2 * d])

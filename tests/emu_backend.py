@@ -102,7 +102,7 @@ class EmuBackend:
         self.launches += 1
 
     def attention_bwd(self, q1, q2, k1, k2, v, d_o, key_mask, lse, dp_avg, delta, dq1, dq2, dk1, dk2, dv, B, H, Lq, Lk,
-                      scale):
+                      scale, o=None):
         s, hd = self._scores(q1, q2, k1, k2, key_mask, B, H, Lq, Lk, scale)
         p = torch.exp(s - lse[..., None])
         g = hd(d_o, Lq)

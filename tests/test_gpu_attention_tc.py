@@ -64,7 +64,7 @@ def test_attention_bf16_fwd_bwd(be, B, H, S, use_mask):
     dqkv = torch.full((B * S, 3 * E), float("nan"), device="cuda", dtype=torch.bfloat16)
     delta = torch.empty(B, H, S, device="cuda")
     be.attention_bwd(qd, None, kd, None, vd, d_o.cuda(), md, lse, None, delta, dqkv[:, :E], None, dqkv[:, E:2 * E], None,
-                     dqkv[:, 2 * E:], B, H, S, S, scale)
+                     dqkv[:, 2 * E:], B, H, S, S, scale, o=o)
     errs = (rel_err(dqkv[:, :E], leaves[0].grad), rel_err(dqkv[:, E:2 * E], leaves[1].grad),
             rel_err(dqkv[:, 2 * E:], leaves[2].grad))
     print(f"B={B} S={S}: o {rel_err(o, o_ref):.2e} lse {rel_err(lse, lse_ref):.2e} dq/dk/dv {errs}")
@@ -89,3 +89,18 @@ def test_fully_masked_rows_and_timing(be):
     us = e0.elapsed_time(e1) * 100
     print(f"spatial attention fwd (T=64, S=213): {us:.1f} us/launch, {4.0 * B * H * S * S * 32 / us / 1e6:.1f} TFLOP/s (unpadded)")
     assert torch.isfinite(o.float()).all()
+    d_o = gb(B * S, E, seed=4).cuda()
+    dqkv = torch.empty(B * S, 3 * E, device="cuda", dtype=torch.bfloat16)
+    delta = torch.empty(B, H, S, device="cuda")
+    args = (q, None, k, None, v, d_o, None, lse, None, delta, dqkv[:, :E], None, dqkv[:, E:2 * E], None, dqkv[:, 2 * E:],
+            B, H, S, S, 32 ** -0.5)
+    for _ in range(3):
+        be.attention_bwd(*args, o=o)
+    e0.record()
+    for _ in range(10):
+        be.attention_bwd(*args, o=o)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 100
+    print(f"spatial attention bwd (T=64, S=213): {us:.1f} us/launch, {10.0 * B * H * S * S * 32 / us / 1e6:.1f} TFLOP/s (unpadded)")
+    assert torch.isfinite(dqkv.float()).all()
