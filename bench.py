@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step from a CUDA graph")
     ap.add_argument("--cpu-steps", type=int, default=2, help="timed CPU-baseline steps (bounded sample)")
+    ap.add_argument("--profile", default=None, help="write a per-kernel device-time table of 3 steps to this file")
     return ap.parse_args()
 
 
@@ -473,6 +474,24 @@ def run_b200_arm(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * args.steps / (float(t.item()) * 1e-3)
+
+    if args.profile and rank == 0:
+        from torch.profiler import profile, ProfilerActivity
+
+        torch.cuda.synchronize(device)
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize(device)
+        evs = [e for e in prof.key_averages() if getattr(e, "device_time_total", 0) > 0]
+        evs.sort(key=lambda e: -e.device_time_total)
+        tot = sum(e.device_time_total for e in evs)
+        with open(args.profile, "w") as f:
+            f.write(f"# 3 steps ({'CUDA graph replay' if graph is not None else 'eager'}), precision {args.precision}: "
+                    f"sum of kernel device time {tot / 3e3:.3f} ms/step; timed step {ms_total / args.steps:.3f} ms\n")
+            f.write("| kernel | launches/step | us/step | share |\n|---|---|---|---|\n")
+            for e in evs[:60]:
+                f.write(f"| `{e.key[:100]}` | {e.count / 3:.1f} | {e.device_time_total / 3:.1f} | {100 * e.device_time_total / tot:.1f}% |\n")
 
     line = None
     if rank == 0:

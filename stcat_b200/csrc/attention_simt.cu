@@ -390,6 +390,16 @@ int attn_tc_fwd_supported(int dtype, const void* q2, const void* p_avg, int B, i
 int attn_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
                 const uint8_t* key_mask, float* lse, int B, int H, int S, float scale, cudaStream_t st);
 
+// attention_sq.cu: single-query (Lq = 1) kernels for the decoders' time-aligned cross attention
+int attn_sq_supported(int dtype, int Lq, int Lk, const void* p_avg, const void* dp_avg, const void* const* ptrs,
+                      const int64_t* lds, int n);
+int attn_sq_fwd(int dtype, const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2, int64_t ldk,
+                const void* v, int64_t ldv, void* o, int64_t ldo, const uint8_t* key_mask, float* lse, int B, int H, int Lk,
+                float scale, cudaStream_t st);
+int attn_sq_bwd(int dtype, const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2, int64_t ldk,
+                const void* v, int64_t ldv, const void* d_o, int64_t lddo, const uint8_t* key_mask, const float* lse,
+                float* delta, void* dq1, void* dq2, int64_t lddq, void* dk1, void* dk2, int64_t lddk, void* dv, int64_t lddv,
+                int B, int H, int Lk, float scale, cudaStream_t st);
 int attn_tc_bwd_supported(int dtype, const void* q2, const void* dp_avg, const void* o, int B, int H, int Lq, int Lk,
                           const void* q, const void* k, const void* v, const void* d_o, const void* dq, const void* dk,
                           const void* dv, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddo, int64_t lddq,
@@ -414,6 +424,13 @@ extern "C" int stcat_attention_fwd(const void* q1, const void* q2, int64_t ldq, 
     STCAT_REQUIRE(B <= 65535 && H <= 65535, STCAT_ESHAPE, "attention_fwd: B/H exceed grid limits");
     if (B == 0 || Lq == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    STCAT_REQUIRE(dtype == STCAT_F32 || dtype == STCAT_BF16, STCAT_EINVAL, "attention_fwd: bad dtype %d", dtype);
+    {
+        const void* ptrs[6] = {q1, q2, k1, k2, v, o};
+        const int64_t lds[6] = {ldq, ldq, ldk, ldk, ldv, ldo};
+        if (attn_sq_supported(dtype, Lq, Lk, p_avg, nullptr, ptrs, lds, 6))
+            return attn_sq_fwd(dtype, q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, B, H, Lk, scale, st);
+    }
     if (attn_tc_fwd_supported(dtype, q2, p_avg, B, H, Lq, Lk, q1, k1, v, o, ldq, ldk, ldv, ldo))
         return attn_tc_fwd(q1, ldq, k1, ldk, v, ldv, o, ldo, key_mask, lse, B, H, Lq, scale, st);
     if (dtype == STCAT_F32)
@@ -439,6 +456,14 @@ extern "C" int stcat_attention_bwd(const void* q1, const void* q2, int64_t ldq, 
     STCAT_REQUIRE(B <= 65535 && H <= 65535, STCAT_ESHAPE, "attention_bwd: B/H exceed grid limits");
     if (B == 0 || Lq == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    STCAT_REQUIRE(dtype == STCAT_F32 || dtype == STCAT_BF16, STCAT_EINVAL, "attention_bwd: bad dtype %d", dtype);
+    {
+        const void* ptrs[11] = {q1, q2, k1, k2, v, d_o, dq1, dq2, dk1, dk2, dv};
+        const int64_t lds[11] = {ldq, ldq, ldk, ldk, ldv, lddo, lddq, lddq, lddk, lddk, lddv};
+        if (attn_sq_supported(dtype, Lq, Lk, nullptr, dp_avg, ptrs, lds, 11))
+            return attn_sq_bwd(dtype, q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, delta, dq1, dq2, lddq, dk1,
+                               dk2, lddk, dv, lddv, B, H, Lk, scale, st);
+    }
     if (attn_tc_bwd_supported(dtype, q2, dp_avg, o, B, H, Lq, Lk, q1, k1, v, d_o, dq1, dk1, dv, ldq, ldk, ldv, ldo, lddo,
                               lddq, lddk, lddv))
         return attn_tc_bwd(q1, ldq, k1, ldk, v, ldv, o, ldo, d_o, lddo, key_mask, lse, dq1, lddq, dk1, lddk, dv, lddv, B, H,

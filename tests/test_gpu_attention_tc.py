@@ -104,3 +104,46 @@ def test_fully_masked_rows_and_timing(be):
     us = e0.elapsed_time(e1) * 100
     print(f"spatial attention bwd (T=64, S=213): {us:.1f} us/launch, {10.0 * B * H * S * S * 32 / us / 1e6:.1f} TFLOP/s (unpadded)")
     assert torch.isfinite(dqkv.float()).all()
+
+
+@pytest.mark.parametrize("B,H,Lk,two,use_mask,dt", [
+    (64, 8, 212, True, True, torch.bfloat16),
+    (64, 8, 212, False, False, torch.bfloat16),
+    (9, 8, 65, True, True, torch.float32),
+    (3, 8, 416, False, True, torch.float32),
+])
+def test_single_query_attention(be, B, H, Lk, two, use_mask, dt):
+    """Lq = 1 (the decoders' time-aligned cross attention) in both dtypes; bf16 results are one bf16 rounding
+    away from the float64 reference of the same bf16 inputs (4e-3), fp32 results 5e-5."""
+    E = H * 32
+    scale = (64 if two else 32) ** -0.5
+    mk = lambda L, s: gb(B * L, E, seed=s).to(dt)
+    q1, k1, v, d_o = mk(1, 1), mk(Lk, 2), mk(Lk, 3), mk(1, 6)
+    q2, k2 = (mk(1, 4), mk(Lk, 5)) if two else (None, None)
+    mask = None
+    if use_mask:
+        mask = torch.zeros(B, Lk, dtype=torch.uint8)
+        for b in range(B):
+            mask[b, Lk - 1 - (3 * b) % 30:] = 1
+    leaves = [x.double().requires_grad_(True) if x is not None else None for x in (q1, q2, k1, k2, v)]
+    o_ref, _, lse_ref = attn_ref(*leaves, mask, B, H, 1, Lk, scale)
+    (o_ref * d_o.double()).sum().backward()
+    c = lambda x: None if x is None else x.cuda()
+    o = torch.empty(B, E, device="cuda", dtype=dt)
+    lse = torch.empty(B, H, 1, device="cuda")
+    be.attention_fwd(c(q1), c(q2), c(k1), c(k2), c(v), o, c(mask), lse, None, B, H, 1, Lk, scale)
+    tol = 4e-3 if dt == torch.bfloat16 else 5e-5
+    assert rel_err(o, o_ref) < tol
+    assert rel_err(lse, lse_ref) < 2e-5
+    e = lambda L: torch.full((B * L, E), float("nan"), device="cuda", dtype=dt)
+    dq1, dk1, dv = e(1), e(Lk), e(Lk)
+    dq2, dk2 = (e(1), e(Lk)) if two else (None, None)
+    delta = torch.empty(B, H, 1, device="cuda")
+    be.attention_bwd(c(q1), c(q2), c(k1), c(k2), c(v), c(d_o), c(mask), lse, None, delta, dq1, dq2, dk1, dk2, dv, B, H, 1,
+                     Lk, scale, o=o)
+    assert rel_err(dq1, leaves[0].grad) < tol
+    assert rel_err(dk1, leaves[2].grad) < tol
+    assert rel_err(dv, leaves[4].grad) < tol
+    if two:
+        assert rel_err(dq2, leaves[1].grad) < tol
+        assert rel_err(dk2, leaves[3].grad) < tol
