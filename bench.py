@@ -250,6 +250,7 @@ def build_b200(args, device):
     vis_mask = inp["vis_mask"].to(device)
     text_mask = inp["text_mask"].to(device)
     grads = FlatGrads(model)
+    ops.set_grad_fusion(True)  # wgrad kernels accumulate straight into the flat buffer (no per-parameter adds)
 
     def fwd_bwd(vis, pos, txt):
         grads.zero()

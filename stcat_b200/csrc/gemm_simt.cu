@@ -74,6 +74,10 @@ gemm_simt_kernel(const TIn* __restrict__ A, int64_t sam, int64_t sak, const TIn*
             float v = acc[i][j];
             if (bias) v += bias[gn];
             TOut* p = C + (int64_t)gm * ldc + gn;
+            if constexpr (sizeof(TOut) == 4) {
+                // fp32 accumulation is atomic: with gradient fusion two streams may add into the same .grad
+                if (accumulate && !relu) { atomicAdd(reinterpret_cast<float*>(p), v); continue; }
+            }
             if (accumulate) v += to_f32<TOut>(*p);
             if (relu) v = fmaxf(v, 0.f);
             *p = from_f32<TOut>(v);

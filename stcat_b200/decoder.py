@@ -26,6 +26,23 @@ from .encoder import batch_indices, _check_cfg
 from .params import LinearP, MHAP, MLPP, NormP, OutProjOnly, SineTable, LearnedTable, xavier_reset
 
 _const_cache = {}
+_MULTI_STREAM = True
+_stream_cache = {}
+
+
+def set_multi_stream(on: bool):
+    """Run the decoder's three independent branches on side streams (default on)."""
+    global _MULTI_STREAM
+    _MULTI_STREAM = bool(on)
+
+
+def _side_streams(device):
+    key = str(device)
+    st = _stream_cache.get(key)
+    if st is None:
+        st = tuple(torch.cuda.Stream(device) for _ in range(3))
+        _stream_cache[key] = st
+    return st
 
 
 def _anchor_freq(device) -> torch.Tensor:
@@ -72,10 +89,10 @@ def _lin(p: LinearP, x, **kw):
     return ops.linear(x, p.weight, p.bias, **kw)
 
 
-def _mha_weights(a: MHAP):
+def _mha_proj(a: MHAP, which: int, x, **kw):
+    """x W_part^T + b_part for part 0/1/2 = q/k/v of the packed nn.MultiheadAttention in-projection."""
     d = a.embed_dim
-    W, b = a.in_proj_weight, a.in_proj_bias
-    return (W[:d], b[:d]), (W[d:2 * d], b[d:2 * d]), (W[2 * d:], b[2 * d:])
+    return ops.linear(x, a.in_proj_weight, a.in_proj_bias, rows=(which * d, (which + 1) * d), **kw)
 
 
 class _Ctx:
@@ -123,7 +140,19 @@ class TransformerDecoderLayer(nn.Module):
         self.nhead = nhead
         self.d = d
 
-    def run(self, c: _Ctx, tgt, query_pos, query_time, query_sine, is_first: bool):
+    def memory_side(self, c: _Ctx, is_first: bool):
+        """Key / value projections of the encoder memory for this layer (query_decoder.py:355-366).  They do not
+        depend on the queries, so the decoder computes them for all layers up front on a side stream."""
+        kp = _lin(self.ca_kpos_proj, c.pos_op, out_bf16=True)  # [n*M, d]
+        vv = _lin(self.ca_v_proj, c.mem_op, out_bf16=True)
+        if is_first:
+            kc = ops.linear_sum([(c.mem_op, self.ca_kcontent_proj.weight, self.ca_kcontent_proj.bias),
+                                 (c.pos_op, self.ca_kpos_proj.weight, self.ca_kpos_proj.bias)], out_bf16=True)
+        else:
+            kc = _lin(self.ca_kcontent_proj, c.mem_op, out_bf16=True)
+        return kc, kp, vv
+
+    def run(self, c: _Ctx, tgt, query_pos, query_time, query_sine, is_first: bool, mem_kv):
         d, H = self.d, self.nhead
         # ---- temporal self attention over the t queries of each video (:329-345) ----
         q = ops.linear_sum([(tgt, self.sa_qcontent_proj.weight, self.sa_qcontent_proj.bias),
@@ -133,24 +162,19 @@ class TransformerDecoderLayer(nn.Module):
                             (query_time, self.sa_ktime_proj.weight, self.sa_ktime_proj.bias),
                             (query_pos, self.sa_kpos_proj.weight, self.sa_kpos_proj.bias)])
         v = _lin(self.sa_v_proj, tgt)
-        (wq, bq), (wk, bk), (wv, bv) = _mha_weights(self.self_attn)
-        Q = ops.linear(q, wq, bq, out_bf16=True)
-        K = ops.linear(k, wk, bk, out_bf16=True)
-        V = ops.linear(v, wv, bv, out_bf16=True)
+        Q = _mha_proj(self.self_attn, 0, q, out_bf16=True)
+        K = _mha_proj(self.self_attn, 1, k, out_bf16=True)
+        V = _mha_proj(self.self_attn, 2, v, out_bf16=True)
         o, _ = ops.attention(Q, K, V, c.b, H, c.t, c.t, float(d // H) ** -0.5, key_mask=c.query_mask)
         a = _lin(self.self_attn.out_proj, o)
         tgt = ops.layer_norm(a, tgt, self.norm1.weight, self.norm1.bias, self.norm1.eps)
         # ---- time-aligned cross attention: query of frame f sees only frame f's tokens (:350-429) ----
-        kp = _lin(self.ca_kpos_proj, c.pos_op, out_bf16=True)  # [n*M, d]
-        vv = _lin(self.ca_v_proj, c.mem_op, out_bf16=True)
+        kc, kp, vv = mem_kv() if callable(mem_kv) else mem_kv
         if is_first:
             qc = ops.linear_sum([(tgt, self.ca_qcontent_proj.weight, self.ca_qcontent_proj.bias),
                                  (query_pos, self.ca_qpos_proj.weight, self.ca_qpos_proj.bias)])
-            kc = ops.linear_sum([(c.mem_op, self.ca_kcontent_proj.weight, self.ca_kcontent_proj.bias),
-                                 (c.pos_op, self.ca_kpos_proj.weight, self.ca_kpos_proj.bias)], out_bf16=True)
         else:
             qc = _lin(self.ca_qcontent_proj, tgt)
-            kc = _lin(self.ca_kcontent_proj, c.mem_op, out_bf16=True)
         qs = _lin(self.ca_qpos_sine_proj, query_sine)
         o, _ = ops.attention(c.frames(qc), kc, vv, c.n, H, 1, c.M, float(2 * d // H) ** -0.5, key_mask=c.key_mask,
                              q2=c.frames(qs), k2=kp)
@@ -176,7 +200,7 @@ class TransformerDecoder(nn.Module):
         self.query_dim = query_dim
         self.d_model = d
 
-    def run(self, c: _Ctx, tgt, anchor, query_time):
+    def run(self, c: _Ctx, tgt, anchor, query_time, mem_kv):
         d = self.d_model
         out = tgt
         inter, refs = [], [anchor]
@@ -184,7 +208,7 @@ class TransformerDecoder(nn.Module):
             sine = anchor_sine_embed(anchor[..., : self.query_dim])  # [b*t, 512]
             query_pos = run_mlp(self.ref_point_head, sine)
             qsine = sine[..., :d] if li == 0 else sine[..., :d] * run_mlp(self.query_scale, out)
-            out = layer.run(c, out, query_pos, query_time, qsine, li == 0)
+            out = layer.run(c, out, query_pos, query_time, qsine, li == 0, mem_kv[li])
             if self.bbox_embed is not None:
                 new_anchor = torch.sigmoid(run_mlp(self.bbox_embed, out) + inverse_sigmoid(anchor))
                 if li != self.num_layers - 1:
@@ -212,22 +236,25 @@ class TimeDecoderLayer(nn.Module):
         self.nhead = nhead
         self.d = d
 
-    def run(self, c: _Ctx, tgt, query_pos, query_pos_frames, qpos_plus_time):
+    def memory_side(self, c: _Ctx):
+        """nn.MultiheadAttention in-projection of key = memory + pos and value = memory (:633-639)."""
+        K = _mha_proj(self.cross_attn_image, 1, c.mempos_op, out_bf16=True)
+        V = _mha_proj(self.cross_attn_image, 2, c.mem_op, out_bf16=True)
+        return K, V
+
+    def run(self, c: _Ctx, tgt, query_pos, query_pos_frames, qpos_plus_time, mem_kv):
         d, H = self.d, self.nhead
         scale = float(d // H) ** -0.5
         qk = tgt + qpos_plus_time
-        (wq, bq), (wk, bk), (wv, bv) = _mha_weights(self.self_attn)
-        Q = ops.linear(qk, wq, bq, out_bf16=True)
-        K = ops.linear(qk, wk, bk, out_bf16=True)
-        V = ops.linear(tgt, wv, bv, out_bf16=True)
+        Q = _mha_proj(self.self_attn, 0, qk, out_bf16=True)
+        K = _mha_proj(self.self_attn, 1, qk, out_bf16=True)
+        V = _mha_proj(self.self_attn, 2, tgt, out_bf16=True)
         o, weights = ops.attention(Q, K, V, c.b, H, c.t, c.t, scale, key_mask=c.query_mask, need_pavg=True)
         a = _lin(self.self_attn.out_proj, o)
         tgt = ops.layer_norm(a, tgt, self.norm1.weight, self.norm1.bias, self.norm1.eps)
         # cross attention, one query per frame (:615-651)
-        (wq, bq), (wk, bk), (wv, bv) = _mha_weights(self.cross_attn_image)
-        Q = ops.linear(c.frames(tgt) + query_pos_frames, wq, bq, out_bf16=True)
-        K = ops.linear(c.mempos_op, wk, bk, out_bf16=True)
-        V = ops.linear(c.mem_op, wv, bv, out_bf16=True)
+        Q = _mha_proj(self.cross_attn_image, 0, c.frames(tgt) + query_pos_frames, out_bf16=True)
+        K, V = mem_kv() if callable(mem_kv) else mem_kv
         o, _ = ops.attention(Q, K, V, c.n, H, 1, c.M, scale, key_mask=c.key_mask)
         o = _lin(self.cross_attn_image.out_proj, o)
         tgt = ops.layer_norm(c.padded(o), tgt, self.norm3.weight, self.norm3.bias, self.norm3.eps)
@@ -244,13 +271,13 @@ class TimeDecoder(nn.Module):
         self.norm = NormP(d)
         self.d_model = d
 
-    def run(self, c: _Ctx, tgt, query_pos, query_time):
+    def run(self, c: _Ctx, tgt, query_pos, query_time, mem_kv):
         out = tgt
         inter, ws = [], []
         qpt = query_pos + query_time
         qpf = c.frames(query_pos)
-        for layer in self.layers:
-            out, w = layer.run(c, out, query_pos, qpf, qpt)
+        for li, layer in enumerate(self.layers):
+            out, w = layer.run(c, out, query_pos, qpf, qpt, mem_kv[li])
             inter.append(ops.layer_norm(out, None, self.norm.weight, self.norm.bias, self.norm.eps))
             ws.append(w)
         return torch.stack(inter).view(self.num_layers, c.b, c.t, self.d_model), torch.stack(ws)
@@ -321,16 +348,70 @@ class QueryDecoder(nn.Module):
         p_v = vis_pos.flatten(2).transpose(1, 2)  # [n, HW, d]
         mem_pos = torch.cat([p_v, p_v.new_zeros(n, M - n_vis, d)], 1).reshape(n * M, d).float()
         key_mask = memory_mask.to(torch.uint8).contiguous()
-        c = _Ctx(idx, mem, mem_pos, key_mask, M)
         # templates (:97-120)
         pos_query, temp_query = self.template_generator.run(idx, memory_cache["frames_cls"], memory_cache["videos_cls"])
-        anchors = c.padded(torch.sigmoid(pos_query))  # [b*t, 4]
-        query_temporal = c.padded(temp_query)  # [b*t, d]
         qt = self.time_embed.rows(t)
         query_time = (qt if b == 1 else qt.repeat(b, 1)).contiguous()
         tgt = mem.new_zeros(b * t, d)
-        outputs = self.decoder.run(c, tgt, anchors, query_time)
-        outputs_temp = self.temp_decoder.run(c, tgt.clone(), query_temporal, query_time)
+        nl = self.decoder.num_layers
+        use_streams = mem.is_cuda and _MULTI_STREAM
+        if not use_streams:
+            c = _Ctx(idx, mem, mem_pos, key_mask, M)
+            anchors = c.padded(torch.sigmoid(pos_query))  # [b*t, 4]
+            query_temporal = c.padded(temp_query)  # [b*t, d]
+            box_kv = [(lambda l=l, i=i: l.memory_side(c, i == 0)) for i, l in enumerate(self.decoder.layers)]
+            time_kv = [(lambda l=l: l.memory_side(c)) for l in self.temp_decoder.layers]
+            outputs = self.decoder.run(c, tgt, anchors, query_time, box_kv)
+            outputs_temp = self.temp_decoder.run(c, tgt.clone(), query_temporal, query_time, time_kv)
+            return outputs, outputs_temp
+        # Three concurrent branches (they only share read-only inputs): (M) the memory-side key/value projections of
+        # all 12 layers -- big GEMMs that do not depend on the queries; (A) the box decoder's query chain; (B) the time
+        # decoder's query chain.  A and B are chains of tiny [t, 256] ops (launch-latency bound), so running them side
+        # by side with M fills the machine.  autograd replays each node's backward on its forward stream, so the
+        # backward pass has the same concurrency.
+        cur = torch.cuda.current_stream()
+        sM, sA, sB = _side_streams(mem.device)
+        fork = cur.record_event()
+        for st_ in (sM, sA, sB):
+            st_.wait_event(fork)
+        with torch.cuda.stream(sM):
+            c = _Ctx(idx, mem, mem_pos, key_mask, M)
+            ctx_ready = sM.record_event()
+            box_kv, time_kv, ev_box, ev_time = [], [], [], []
+            for i in range(nl):
+                box_kv.append(self.decoder.layers[i].memory_side(c, i == 0))
+                ev_box.append(sM.record_event())
+                time_kv.append(self.temp_decoder.layers[i].memory_side(c))
+                ev_time.append(sM.record_event())
+
+        def waiter(stream, evs, vals):
+            def mk(i):
+                def get():
+                    stream.wait_event(evs[i])
+                    for tns in vals[i]:  # allocated on sM, consumed here (and in backward) on another stream
+                        tns.record_stream(stream)
+                    return vals[i]
+                return get
+            return [mk(i) for i in range(len(vals))]
+
+        for tns in (pos_query, temp_query, query_time, tgt):  # allocated on `cur`, consumed on the side streams
+            tns.record_stream(sA)
+            tns.record_stream(sB)
+        for tns in (mem, mem_pos):
+            tns.record_stream(sM)
+
+        with torch.cuda.stream(sA):
+            sA.wait_event(ctx_ready)
+            anchors = c.padded(torch.sigmoid(pos_query))
+            outputs = self.decoder.run(c, tgt, anchors, query_time, waiter(sA, ev_box, box_kv))
+        with torch.cuda.stream(sB):
+            sB.wait_event(ctx_ready)
+            query_temporal = c.padded(temp_query)
+            outputs_temp = self.temp_decoder.run(c, tgt.clone(), query_temporal, query_time, waiter(sB, ev_time, time_kv))
+        for st_ in (sM, sA, sB):
+            cur.wait_stream(st_)
+        for tns in (*outputs, *outputs_temp):
+            tns.record_stream(cur)
         return outputs, outputs_temp
 
 

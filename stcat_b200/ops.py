@@ -19,6 +19,51 @@ from torch.autograd.function import once_differentiable
 
 _backend = None
 _precision = "fp32"
+_fuse_grads = False
+
+
+def set_grad_fusion(on: bool):
+    """When on, weight / bias / LayerNorm-affine gradients are accumulated by the wgrad kernels straight into
+    ``param.grad`` (which must already exist, e.g. as views of one flat buffer) and autograd is handed ``None``:
+    no per-parameter temporaries, fills or ``grad += dw`` kernels (about 700 tiny launches per step).  Off by
+    default because it bypasses AccumulateGrad hooks (torch DDP relies on them); ``bench.py`` turns it on and
+    all-reduces the flat buffer itself."""
+    global _fuse_grads
+    _fuse_grads = bool(on)
+
+
+def _wgrad(be, dyo, xo, W, b, need_w, need_b, r0=None, r1=None):
+    """dW (+)= dy^T x, db (+)= colsum(dy) for rows [r0, r1) of W / b.  Returns (dw, db) for autograd, or Nones when
+    the result was accumulated in place into W.grad / b.grad."""
+    if not need_w:
+        return None, None
+    want_b = b is not None and need_b
+    if _fuse_grads and W.grad is not None and (not want_b or b.grad is not None):
+        gw = W.grad if r0 is None else W.grad[r0:r1]
+        gb = None if not want_b else (b.grad if r0 is None else b.grad[r0:r1])
+        be.linear_bwd_weight(dyo, xo, gw, gb, accumulate=True)
+        return None, None
+    if r0 is None:
+        dw = torch.empty(W.shape, dtype=torch.float32, device=dyo.device)
+        db = torch.empty(b.shape, dtype=torch.float32, device=dyo.device) if want_b else None
+        be.linear_bwd_weight(dyo, xo, dw, db)
+        return dw, db
+    dw = torch.zeros(W.shape, dtype=torch.float32, device=dyo.device)
+    db = torch.zeros(b.shape, dtype=torch.float32, device=dyo.device) if want_b else None
+    be.linear_bwd_weight(dyo, xo, dw[r0:r1], None if db is None else db[r0:r1])
+    return dw, db
+
+
+def _ln_bwd(be, dy, x, res, gamma, beta, mean, rstd, dz):
+    """LayerNorm backward; returns (dgamma, dbeta) for autograd or Nones when accumulated into .grad."""
+    d = x.shape[1]
+    if _fuse_grads and gamma.grad is not None and beta is not None and beta.grad is not None:
+        be.layernorm_bwd(dy, x, res, gamma.detach(), mean, rstd, dz, gamma.grad, beta.grad)
+        return None, None
+    dg = torch.zeros(d, dtype=torch.float32, device=dy.device)
+    dbt = torch.zeros(d, dtype=torch.float32, device=dy.device)
+    be.layernorm_bwd(dy, x, res, gamma.detach(), mean, rstd, dz, dg, dbt)
+    return dg, dbt
 
 
 def get_backend():
@@ -84,53 +129,58 @@ def _rows(x: torch.Tensor, k: int) -> torch.Tensor:
 
 
 class LinearFn(Function):
-    """y = act(x W^T + b)"""
+    """y = act(x W[r0:r1]^T + b[r0:r1])  (r0/r1 = None: the whole parameter).  The row range lets the packed
+    ``in_proj_weight`` of an MHA be used slice by slice without autograd slicing nodes."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, relu: bool, out_bf16: bool):
+    def forward(ctx, x, weight, bias, relu: bool, out_bf16: bool, r0, r1):
         be = get_backend()
-        N, K = weight.shape
+        wd = weight.detach()
+        bd = None if bias is None else bias.detach()
+        if r0 is not None:
+            wd = wd[r0:r1]
+            bd = None if bd is None else bd[r0:r1]
+        N, K = wd.shape
         x2 = _rows(x.detach(), K)
         xo = _operand(x2)
-        wo = _operand(weight.detach(), True)
+        wo = _operand(wd, True)
         M = x2.shape[0]
         odt = torch.bfloat16 if (out_bf16 and _precision == "bf16") else torch.float32
         y = torch.empty(M, N, dtype=odt, device=x.device)
-        be.linear_fwd(xo, wo, None if bias is None else bias.detach(), y, relu=relu)
+        be.linear_fwd(xo, wo, bd, y, relu=relu)
         ctx.relu = relu
         ctx.x_shape = x.shape
         ctx.x_dtype = x.dtype
-        ctx.has_bias = bias is not None
-        ctx.save_for_backward(xo, weight, y if relu else None)
+        ctx.rows = (r0, r1)
+        ctx.save_for_backward(xo, weight, bias, y if relu else None)
         return y.view(*x.shape[:-1], N)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
         be = get_backend()
-        xo, weight, y = ctx.saved_tensors
-        N, K = weight.shape
+        xo, weight, bias, y = ctx.saved_tensors
+        r0, r1 = ctx.rows
+        wd = weight.detach() if r0 is None else weight.detach()[r0:r1]
+        N, K = wd.shape
         dy2 = _rows(dy, N)
         if ctx.relu:
             dy2 = dy2.clone() if dy2.data_ptr() == dy.data_ptr() else dy2
             be.relu_bwd(y, dy2)
         dyo = _operand(dy2)
         M = dy2.shape[0]
-        dx = dw = db = None
+        dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(M, K, dtype=ctx.x_dtype, device=dy.device)
-            be.linear_bwd_data(dyo, _operand(weight.detach(), True), dx)
+            be.linear_bwd_data(dyo, _operand(wd, True), dx)
             dx = dx.view(ctx.x_shape)
-        if ctx.needs_input_grad[1]:
-            dw = torch.empty(N, K, dtype=torch.float32, device=dy.device)
-            if ctx.has_bias and ctx.needs_input_grad[2]:
-                db = torch.empty(N, dtype=torch.float32, device=dy.device)
-            be.linear_bwd_weight(dyo, xo, dw, db)
-        return dx, dw, db, None, None
+        dw, db = _wgrad(be, dyo, xo, weight, bias, ctx.needs_input_grad[1], ctx.needs_input_grad[2], r0, r1)
+        return dx, dw, db, None, None, None, None
 
 
-def linear(x, weight, bias=None, relu: bool = False, out_bf16: bool = False):
-    return LinearFn.apply(x, weight, bias, relu, out_bf16)
+def linear(x, weight, bias=None, relu: bool = False, out_bf16: bool = False, rows=None):
+    r0, r1 = rows if rows is not None else (None, None)
+    return LinearFn.apply(x, weight, bias, relu, out_bf16, r0, r1)
 
 
 class LinearSumFn(Function):
@@ -156,6 +206,7 @@ class LinearSumFn(Function):
             be.linear_fwd(xo, _operand(w.detach(), True), None if b is None else b.detach(), y, accumulate=i > 0)
             saved += [xo, w]
         ctx.nterms = nterms
+        ctx.biases = bs
         ctx.meta = [(x.shape, x.dtype, b is not None) for x, b in zip(xs, bs)]
         ctx.save_for_backward(*saved)
         return y.view(*lead, N)
@@ -171,6 +222,7 @@ class LinearSumFn(Function):
         M = dyo.shape[0]
         dxs, dws, dbs = [], [], []
         db_shared = None
+        biases = ctx.biases
         for i in range(n):
             xo, w = saved[2 * i], saved[2 * i + 1]
             xshape, xdtype, has_b = ctx.meta[i]
@@ -181,14 +233,19 @@ class LinearSumFn(Function):
                 be.linear_bwd_data(dyo, _operand(w.detach(), True), dx)
                 dx = dx.view(xshape)
             if ctx.needs_input_grad[2 + n + i]:
-                dw = torch.empty(N, K, dtype=torch.float32, device=dy.device)
                 want_b = has_b and ctx.needs_input_grad[2 + 2 * n + i]
-                if want_b and db_shared is None:
-                    db_shared = torch.empty(N, dtype=torch.float32, device=dy.device)
-                    be.linear_bwd_weight(dyo, xo, dw, db_shared)
+                b = biases[i]
+                if _fuse_grads and w.grad is not None and (not want_b or b.grad is not None):
+                    be.linear_bwd_weight(dyo, xo, w.grad, b.grad if want_b else None, accumulate=True)
                 else:
-                    be.linear_bwd_weight(dyo, xo, dw, None)
-                db = (db_shared if not any(d is db_shared for d in dbs) else db_shared.clone()) if want_b else None
+                    dw = torch.empty(N, K, dtype=torch.float32, device=dy.device)
+                    if want_b and db_shared is None:
+                        db_shared = torch.empty(N, dtype=torch.float32, device=dy.device)
+                        be.linear_bwd_weight(dyo, xo, dw, db_shared)
+                        db = db_shared
+                    else:
+                        be.linear_bwd_weight(dyo, xo, dw, None)
+                        db = db_shared.clone() if want_b else None
             dxs.append(dx)
             dws.append(dw)
             dbs.append(db)
@@ -220,6 +277,7 @@ class LayerNormFn(Function):
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
         be.layernorm_fwd(x2, r2, gamma.detach(), beta.detach(), y, None, mean, rstd, eps)
         ctx.save_for_backward(x2, r2, gamma, mean, rstd)
+        ctx.beta = beta
         ctx.shape = x.shape
         ctx.dtypes = (x.dtype, None if res is None else res.dtype)
         return y.view(x.shape)
@@ -233,9 +291,7 @@ class LayerNormFn(Function):
         dy2 = _rows(dy, d)
         dy2 = dy2 if dy2.is_contiguous() else dy2.contiguous()
         dz = torch.empty_like(x2)
-        dg = torch.zeros(d, dtype=torch.float32, device=dy.device)
-        db = torch.zeros(d, dtype=torch.float32, device=dy.device)
-        be.layernorm_bwd(dy2, x2, r2, gamma.detach(), mean, rstd, dz, dg, db)
+        dg, db = _ln_bwd(be, dy2, x2, r2, gamma, ctx.beta, mean, rstd, dz)
         dzv = dz.view(ctx.shape)
         dx = dzv.to(ctx.dtypes[0]) if ctx.needs_input_grad[0] else None
         dr = dzv.to(ctx.dtypes[1]) if (r2 is not None and ctx.needs_input_grad[1]) else None
@@ -432,6 +488,7 @@ class SelfAttnBlockFn(Function):
         rstd = torch.empty(R, dtype=torch.float32, device=x.device)
         be.layernorm_fwd(a, xd, gamma.detach(), beta.detach(), y, y_op, mean, rstd, eps)
         ctx.save_for_backward(xd, xo, qk_in, qkv, o, lse, a, mean, rstd, key_mask, w_in, w_out, gamma)
+        ctx.extra = (b_in, b_out, beta)
         ctx.dims = (B, L, H, scale)
         if bf:
             ctx.mark_non_differentiable(y_op)
@@ -449,24 +506,26 @@ class SelfAttnBlockFn(Function):
         dy = dy if (dy.is_contiguous() and dy.dtype == f32) else dy.contiguous().float()
         wi = _operand(w_in.detach(), True)
         wo = _operand(w_out.detach(), True)
+        b_in, b_out, beta = ctx.extra
         dz = _new(R, d, f32, dy)  # grad wrt (a) and wrt the residual x
-        dg = torch.zeros(d, dtype=f32, device=dy.device)
-        dbt = torch.zeros(d, dtype=f32, device=dy.device)
-        be.layernorm_bwd(dy, a, xd, gamma.detach(), mean, rstd, dz, dg, dbt)
+        dg, dbt = _ln_bwd(be, dy, a, xd, gamma, beta, mean, rstd, dz)
         dz_op = _cast_op(be, dz)
-        dwo = _new(d, d, f32, dy)
-        dbo = torch.empty(d, dtype=f32, device=dy.device)
-        be.linear_bwd_weight(dz_op, o, dwo, dbo)
+        dwo, dbo = _wgrad(be, dz_op, o, w_out, b_out, True, True)
         d_o = _new(R, d, od, dy)
         be.linear_bwd_data(dz_op, wo, d_o)
         dqkv = _new(R, 3 * d, od, dy)
         delta = torch.empty(B, H, L, dtype=f32, device=dy.device)
         be.attention_bwd(qkv[:, :d], None, qkv[:, d:2 * d], None, qkv[:, 2 * d:], d_o, key_mask, lse, None, delta,
                          dqkv[:, :d], None, dqkv[:, d:2 * d], None, dqkv[:, 2 * d:], B, H, L, L, scale, o=o)
-        dwi = _new(3 * d, d, f32, dy)
-        dbi = torch.empty(3 * d, dtype=f32, device=dy.device)
-        be.linear_bwd_weight(dqkv[:, : 2 * d], qk_in, dwi[: 2 * d], dbi[: 2 * d])
-        be.linear_bwd_weight(dqkv[:, 2 * d:], xo, dwi[2 * d:], dbi[2 * d:])
+        if _fuse_grads and w_in.grad is not None and b_in.grad is not None:
+            be.linear_bwd_weight(dqkv[:, : 2 * d], qk_in, w_in.grad[: 2 * d], b_in.grad[: 2 * d], accumulate=True)
+            be.linear_bwd_weight(dqkv[:, 2 * d:], xo, w_in.grad[2 * d:], b_in.grad[2 * d:], accumulate=True)
+            dwi = dbi = None
+        else:
+            dwi = _new(3 * d, d, f32, dy)
+            dbi = torch.empty(3 * d, dtype=f32, device=dy.device)
+            be.linear_bwd_weight(dqkv[:, : 2 * d], qk_in, dwi[: 2 * d], dbi[: 2 * d])
+            be.linear_bwd_weight(dqkv[:, 2 * d:], xo, dwi[2 * d:], dbi[2 * d:])
         need_pos = ctx.needs_input_grad[2]
         dpos = None
         if need_pos:
@@ -507,6 +566,7 @@ class FFNBlockFn(Function):
         rstd = torch.empty(R, dtype=torch.float32, device=x.device)
         be.layernorm_fwd(yl, xd, gamma.detach(), beta.detach(), y, y_op, mean, rstd, eps)
         ctx.save_for_backward(xd, xo, h, yl, mean, rstd, w1, w2, gamma)
+        ctx.extra = (b1, b2, beta)
         if bf:
             ctx.mark_non_differentiable(y_op)
         return y, y_op
@@ -522,20 +582,15 @@ class FFNBlockFn(Function):
         f32 = torch.float32
         dy = dy if (dy.is_contiguous() and dy.dtype == f32) else dy.contiguous().float()
         w1o, w2o = _operand(w1.detach(), True), _operand(w2.detach(), True)
+        b1, b2, beta = ctx.extra
         dz = _new(R, d, f32, dy)
-        dg = torch.zeros(d, dtype=f32, device=dy.device)
-        dbt = torch.zeros(d, dtype=f32, device=dy.device)
-        be.layernorm_bwd(dy, yl, xd, gamma.detach(), mean, rstd, dz, dg, dbt)
+        dg, dbt = _ln_bwd(be, dy, yl, xd, gamma, beta, mean, rstd, dz)
         dz_op = _cast_op(be, dz)
-        dw2 = _new(d, F_, f32, dy)
-        db2 = torch.empty(d, dtype=f32, device=dy.device)
-        be.linear_bwd_weight(dz_op, h, dw2, db2)
+        dw2, db2 = _wgrad(be, dz_op, h, w2, b2, True, True)
         dh = _new(R, F_, od, dy)
         be.linear_bwd_data(dz_op, w2o, dh)
         be.relu_bwd(h, dh)
-        dw1 = _new(F_, d, f32, dy)
-        db1 = torch.empty(F_, dtype=f32, device=dy.device)
-        be.linear_bwd_weight(dh, xo, dw1, db1)
+        dw1, db1 = _wgrad(be, dh, xo, w1, b1, True, True)
         be.linear_bwd_data(dh, w1o, dz, accumulate=True)
         return dz, None, dw1, db1, dw2, db2, dg, dbt, None
 

@@ -146,3 +146,38 @@ def test_device_loss_matches_oracle_loss(name):
         assert abs(float(named[k]) - float(ref_named[k])) <= 1e-5 * max(1.0, abs(float(ref_named[k]))), k
     assert abs(float(total) - float(ref_total)) <= 1e-5 * abs(float(ref_total))
     assert abs(float(total) - float(fx["loss_total"])) <= 5e-5 * abs(float(fx["loss_total"]))
+
+
+def test_grad_fusion_matches_autograd_accumulation():
+    """ops.set_grad_fusion(True): wgrad kernels accumulate straight into pre-allocated .grad views of one flat
+    buffer; the result must equal the ordinary autograd accumulation."""
+    fx = load_golden("b2_ragged_T5_3")
+    spec = fx["spec"]
+    cfg = cfg_for(spec)
+    inp = case_inputs(spec)
+    tg = synthetic.make_targets(spec["durations"], seed=spec["seed"])
+    grads = []
+    for fused in (False, True):
+        m = build(cfg, case_params(cfg, spec)).eval()
+        params = list(dict.fromkeys(m.parameters()))
+        if fused:
+            flat = torch.zeros(sum(p.numel() for p in params))
+            o = 0
+            for p in params:
+                p.grad = flat[o:o + p.numel()].view_as(p)
+                o += p.numel()
+        ops.set_grad_fusion(fused)
+        try:
+            out, vis, txt = run_model(m, inp, grad=True)
+            total, _ = O.stg_loss(cfg, out, tg["boxes"], tg["actioness"], spec["durations"])
+            total.backward()
+        finally:
+            ops.set_grad_fusion(False)
+        grads.append({k: (None if p.grad is None else p.grad.clone()) for k, p in m.named_parameters()})
+        grads[-1]["__vis"] = vis.grad.clone()
+    for k, g in grads[0].items():
+        g2 = grads[1][k]
+        if g is None:
+            assert g2 is None or float(g2.abs().max()) == 0.0, k
+        else:
+            assert rel_err(g2, g) < 1e-5 or float((g2 - g).abs().max()) < 1e-7, k
