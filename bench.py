@@ -207,31 +207,9 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
-class FlatGrads:
-    """All hot-path gradients as views of one contiguous fp32 buffer: one memset to clear, one NCCL
-    all-reduce per step (the reference uses DDP buckets + find_unused_parameters, train_net.py:31-36;
-    parameters the forward never uses simply keep their zero slice here)."""
-
-    def __init__(self, model):
-        seen, params = set(), []
-        for p in model.parameters():
-            if id(p) not in seen:
-                seen.add(id(p))
-                params.append(p)
-        n = sum(p.numel() for p in params)
-        self.buf = torch.zeros(n, dtype=torch.float32, device=params[0].device)
-        o = 0
-        for p in params:
-            p.grad = self.buf[o:o + p.numel()].view_as(p)
-            o += p.numel()
-        self.numel = n
-
-    def zero(self):
-        self.buf.zero_()
-
-
 def build_b200(args, device):
     from stcat_b200 import ops, synthetic
+    from stcat_b200.dp import FlatGrads
     from stcat_b200.loss import STGLossPlan
     from stcat_b200.nested import NestedTensor
     from stcat_b200.param_spec import synthetic_params
@@ -484,6 +462,8 @@ def run_b200_arm(args):
             for _ in range(3):
                 step()
             torch.cuda.synchronize(device)
+        if os.environ.get("STCAT_TRACE"):
+            prof.export_chrome_trace(os.environ["STCAT_TRACE"])
         evs = [e for e in prof.key_averages() if getattr(e, "device_time_total", 0) > 0]
         evs.sort(key=lambda e: -e.device_time_total)
         tot = sum(e.device_time_total for e in evs)

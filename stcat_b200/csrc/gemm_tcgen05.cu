@@ -10,13 +10,16 @@
 //   bwd_weight dw = dy^T . x       A(n,m) = dy[m,n] MN-major B(k,m) = x[m,k]      MN-major
 // so no transposed copies of activations are ever materialised.
 //
-// Structure (persistent, warp-specialised, 256 threads, 1 CTA / SM):
+// Structure (persistent, warp-specialised, 384 threads, 1 CTA / SM):
 //   warp 0      TMA producer  : 4-stage ring of {A 128x64, B 256x64} bf16 tiles (48 KB / stage), mbarrier full/empty
 //   warp 1      MMA issuer    : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 128x256x16, 4 per stage;
 //                               tcgen05.commit releases the stage / publishes the accumulator
 //   warp 2      TMEM allocator: 512 columns = 2 accumulator stages of 128 lanes x 256 fp32 columns
-//   warps 4..7  epilogue      : tcgen05.ld 32 lanes x 32 columns per warp, bias/ReLU, convert, st.shared into a
-//                               128B-swizzled [128 x 128 B] staging tile (double buffered), TMA store / reduce-add
+//   warps 4..11 epilogue      : two groups of 4 warps, one per 128-column half of the accumulator; each warp
+//                               tcgen05.ld's 32 lanes x 32 columns at a time, adds the bias slice staged in shared
+//                               memory, ReLU, converts, st.shared into the group's 128B-swizzled [128 x 128 B]
+//                               staging tile, one thread issues the TMA store / reduce-add; the next chunk's
+//                               TMEM loads are in flight while the previous store drains the staging tile
 // M/N/K tails need no code: TMA zero-fills out-of-bounds loads and clips out-of-bounds stores.
 // Split-K (needed by bwd_weight, whose contraction runs over all M = T*S tokens while the output is one
 // or a few tiles) uses the TMA reduce-add epilogue on a pre-zeroed fp32 output.
@@ -27,17 +30,26 @@ namespace stcat {
 
 namespace tc {
 
-constexpr int BM = 128, BN = 256, BK = 64;  // tile; BK * 2 B = 128 B = one swizzle row
-constexpr int STAGES = 4;
+constexpr int BM = 128, BK = 64;  // BK * 2 B = 128 B = one swizzle row
 constexpr int A_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_BYTES = BN * BK * 2;   // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int EPI_BYTES = BM * 128;    // one staging chunk: 128 rows x 128 B
-constexpr int EPI_BUFS = 2;
 constexpr int ACC_STAGES = 2;
-constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BUFS * EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int THREADS = 256;
+constexpr int THREADS = 384;
+
+// Two tile shapes.  BN = 256 is the throughput shape (128 x 256 accumulator, two epilogue groups).  BN = 64 is the
+// latency shape for GEMMs with so few 128 x 256 tiles that most SMs would idle (the decoder's [t, 256] query-side
+// layers): 4x as many CTAs, each with a short K loop, and -- unlike split-K -- a deterministic summation order.
+template <int BN> struct Cfg {
+    static constexpr int STAGES = BN >= 256 ? 4 : 8;   // ~192 KB of operands in flight either way (latency x bandwidth)
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int GROUPS = BN >= 256 ? 2 : 1;   // epilogue groups (4 warps each)
+    static constexpr int GC = BN / GROUPS;             // accumulator columns per group
+    static constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512 / 128 (power of two >= 32)
+    static constexpr int BIAS_BYTES = BN * 4;          // the tile's bias slice, staged once per tile
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GROUPS * EPI_BYTES + BIAS_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
+};
 
 struct Params {
     const float* bias;  // [N] or null (added by k-split 0)
@@ -47,14 +59,17 @@ struct Params {
     int reduce_add;  // epilogue uses TMA reduce-add instead of store
 };
 
-template <bool A_MN, bool B_MN, bool OUT_BF16>
+template <bool A_MN, bool B_MN, bool OUT_BF16, int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B-swizzle atoms need 1024 B alignment
+    using C = Cfg<BN>;
+    constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, GROUPS = C::GROUPS, GC = C::GC, TMEM_COLS = C::TMEM_COLS;
     const uint32_t epi_base = base + STAGES * STAGE_BYTES;
-    const uint32_t bar_base = epi_base + EPI_BUFS * EPI_BYTES;
+    const uint32_t bias_base = epi_base + GROUPS * EPI_BYTES;
+    const uint32_t bar_base = bias_base + C::BIAS_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto accf_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
@@ -71,7 +86,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(accf_bar(s), 1); mbar_init(acce_bar(s), 4); }
+        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(accf_bar(s), 1); mbar_init(acce_bar(s), 4 * GROUPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -151,84 +166,104 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
             }
         }
-    } else if (warp >= 4) {
-        // ================= epilogue (warps 4..7 <-> TMEM lane quadrants 0..3) =================
-        const int q = warp - 4;
-        const int row = q * 32 + lane;  // row of the 128-row tile owned by this thread
-        const int et = threadIdx.x - 128;
-        constexpr int CHUNK_COLS = OUT_BF16 ? 64 : 32;  // 128 B of output per row per chunk
-        constexpr int NCHUNK = BN / CHUNK_COLS;
-        int as = 0, buf = 0;
+    } else if (warp >= 4 && warp < 4 + 4 * GROUPS) {
+        // ================= epilogue: GROUPS column groups x 4 TMEM lane quadrants =================
+        // Group g (warps 4+4g .. 7+4g) drains columns [GC g, GC g + GC) of the accumulator; warp (q = warp & 3)
+        // of a group reads TMEM lanes [32 q, 32 q + 32) (the hardware ties a warp to lane quadrant warp % 4).
+        const int ew = warp - 4;
+        const int q = ew & 3;
+        const int g = ew >> 2;
+        const int row = q * 32 + lane;             // row of the 128-row tile owned by this thread
+        const int gt = threadIdx.x - 128 - g * 128;  // thread index inside the group
+        const uint32_t bar_id = 1 + g;
+        const uint32_t sbuf_base = epi_base + g * EPI_BYTES;  // one 128 x 128 B staging tile per group
+        const uint32_t sbias = bias_base + g * GC * 4;  // this group's GC bias values (fp32)
+        constexpr int CHUNK_COLS = OUT_BF16 ? 64 : 32;        // 128 B of output per row per chunk
+        constexpr int NCHUNK = GC / CHUNK_COLS;               // chunks per group
+        int as = 0;
         uint32_t aphase = 0;
         for (int w = blockIdx.x; w < total; w += gridDim.x) {
             const int split = w % p.splits;
             const int t = w / p.splits;
             const int m_blk = t % p.tiles_m, n_blk = t / p.tiles_m;
+            const int n_valid = min(BN, p.N - n_blk * BN) - g * GC;  // valid columns of this group's share
+            {   // stage the bias slice (zero where there is none / out of range): no per-element predicates below.
+                // Safe to overwrite: every thread of the group passed the previous tile's last bar.sync, which
+                // follows all of that tile's bias reads.
+                const int col = n_blk * BN + g * GC + gt;
+                const float bv = (p.bias != nullptr && split == 0 && col < p.N) ? __ldg(p.bias + col) : 0.f;
+                if (gt < GC) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + gt * 4), "f"(bv) : "memory");
+            }
             mbar_wait(accf_bar(as), aphase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
-            const bool add_bias = p.bias != nullptr && split == 0;
-            const int n_valid = min(BN, p.N - n_blk * BN);
+            const uint32_t t_row = tmem_base + as * BN + g * GC + ((uint32_t)(q * 32) << 16);
+            bool released = false;
+            auto release_acc = [&]() {  // all TMEM reads of this accumulator stage are complete
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acce_bar(as));
+                released = true;
+            };
+#pragma unroll 1
             for (int c = 0; c < NCHUNK; ++c) {
-                if (c * CHUNK_COLS >= n_valid) break;  // whole chunk out of range (uniform across the CTA)
-                // staging buffer `buf` must have been read by its previous TMA store
-                if (et == 0) tma_wait_read<EPI_BUFS - 1>();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const uint32_t sbuf = epi_base + buf * EPI_BYTES + row * 128;
+                if (c * CHUNK_COLS >= n_valid) break;  // uniform across the group
+                uint32_t r[CHUNK_COLS];
 #pragma unroll
-                for (int h = 0; h < CHUNK_COLS / 32; ++h) {
-                    uint32_t r[32];
-                    tmem_ld32(t_row + c * CHUNK_COLS + h * 32, r);
+                for (int h = 0; h < CHUNK_COLS / 32; ++h)
+                    tmem_ld32(t_row + c * CHUNK_COLS + h * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[h * 32]));
+                // the staging tile must have been read by the previous TMA store of this group
+                if (gt == 0) tma_wait_read<0>();
+                if (c == NCHUNK - 1 || (c + 1) * CHUNK_COLS >= n_valid) {
+                    // last TMEM read of this accumulator stage: hand it back to the MMA warp as early as possible
                     tmem_ld_wait();
-                    const int col0 = n_blk * BN + c * CHUNK_COLS + h * 32;
-                    float v[32];
+                    release_acc();
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                tmem_ld_wait();
+                const uint32_t srow = sbuf_base + row * 128;
+                const uint32_t sb = sbias + c * CHUNK_COLS * 4;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float x = __uint_as_float(r[i]);
-                        if (add_bias && col0 + i < p.N) x += __ldg(p.bias + col0 + i);
-                        if (p.relu) x = fmaxf(x, 0.f);
-                        v[i] = x;
+                for (int j = 0; j < CHUNK_COLS / 4; ++j) {
+                    float b0, b1, b2, b3;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(sb + j * 16));
+                    float x0 = __uint_as_float(r[4 * j + 0]) + b0, x1 = __uint_as_float(r[4 * j + 1]) + b1;
+                    float x2 = __uint_as_float(r[4 * j + 2]) + b2, x3 = __uint_as_float(r[4 * j + 3]) + b3;
+                    if (p.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+                    r[4 * j + 0] = __float_as_uint(x0); r[4 * j + 1] = __float_as_uint(x1);
+                    r[4 * j + 2] = __float_as_uint(x2); r[4 * j + 3] = __float_as_uint(x3);
+                }
+                if (OUT_BF16) {
+#pragma unroll
+                    for (int j = 0; j < CHUNK_COLS / 8; ++j) {  // 16 B = 8 bf16 per store
+                        uint32_t wv[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            __nv_bfloat162 bb = __floats2bfloat162_rn(__uint_as_float(r[8 * j + 2 * e]), __uint_as_float(r[8 * j + 2 * e + 1]));
+                            wv[e] = *reinterpret_cast<uint32_t*>(&bb);
+                        }
+                        const int chunk = j ^ (row & 7);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + chunk * 16), "r"(wv[0]), "r"(wv[1]), "r"(wv[2]), "r"(wv[3]) : "memory");
                     }
-                    if (OUT_BF16) {
+                } else {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {  // 4 x 16 B chunks = 32 bf16
-                            uint32_t w0, w1, w2, w3;
-                            __nv_bfloat162 b0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
-                            __nv_bfloat162 b1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-                            __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-                            __nv_bfloat162 b3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-                            w0 = *reinterpret_cast<uint32_t*>(&b0); w1 = *reinterpret_cast<uint32_t*>(&b1);
-                            w2 = *reinterpret_cast<uint32_t*>(&b2); w3 = *reinterpret_cast<uint32_t*>(&b3);
-                            const int chunk = (h * 4 + j) ^ (row & 7);
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbuf + chunk * 16), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {  // 8 x 16 B chunks = 32 fp32
-                            const int chunk = j ^ (row & 7);
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbuf + chunk * 16),
-                                         "r"(__float_as_uint(v[4 * j + 0])), "r"(__float_as_uint(v[4 * j + 1])),
-                                         "r"(__float_as_uint(v[4 * j + 2])), "r"(__float_as_uint(v[4 * j + 3])) : "memory");
-                        }
+                    for (int j = 0; j < CHUNK_COLS / 4; ++j) {  // 16 B = 4 fp32 per store
+                        const int chunk = j ^ (row & 7);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + chunk * 16), "r"(r[4 * j + 0]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (et == 0) {
-                    const uint32_t src = epi_base + buf * EPI_BYTES;
-                    if (p.reduce_add) tma_reduce_add_2d(&tmC, src, n_blk * BN + c * CHUNK_COLS, m_blk * BM);
-                    else tma_store_2d(&tmC, src, n_blk * BN + c * CHUNK_COLS, m_blk * BM);
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                if (gt == 0) {
+                    const int c0 = n_blk * BN + g * GC + c * CHUNK_COLS;
+                    if (p.reduce_add) tma_reduce_add_2d(&tmC, sbuf_base, c0, m_blk * BM);
+                    else tma_store_2d(&tmC, sbuf_base, c0, m_blk * BM);
                     tma_commit();
                 }
-                buf ^= 1;
             }
-            // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above)
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acce_bar(as));
+            if (!released) release_acc();  // this group's half lies entirely outside N
             if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
         }
-        if (et == 0) tma_wait_all();
+        if (gt == 0) tma_wait_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -303,9 +338,24 @@ int gemm_tc_supported(int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc
     return 1;
 }
 
-int gemm_tc(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* C,
-            int64_t ldc, int out_dtype, const float* bias, int M, int N, int K, int relu, int accumulate,
-            cudaStream_t st) {
+template <bool AMN, bool BMN, bool OBF, int BN>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const tc::Params& p, int grid,
+                     cudaStream_t st) {
+    using namespace tc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AMN, BMN, OBF, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
+        if (e != cudaSuccess) return set_err((int)e, "gemm_tc: smem attribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    gemm_tc_kernel<AMN, BMN, OBF, BN><<<grid, THREADS, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, tmC, p);
+    return check_launch("gemm_tc_kernel");
+}
+
+template <int BN>
+static int gemm_tc_bn(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* C,
+                      int64_t ldc, int out_dtype, const float* bias, int M, int N, int K, int relu, int accumulate,
+                      cudaStream_t st) {
     using namespace tc;
     const bool out_bf16 = out_dtype == STCAT_BF16;
     CUtensorMap tmA, tmB, tmC;
@@ -327,12 +377,17 @@ int gemm_tc(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t l
     const int tiles = p.tiles_m * p.tiles_n;
     const int sms = num_sms();
     int splits = 1;
-    if (!relu && !out_bf16 && tiles * 2 <= sms && p.kb_total >= 8) {
+    // Split-K only for weight gradients (A MN-major: the contraction runs over all tokens while the output is a
+    // few tiles); they are accumulated into fp32 gradient buffers anyway.  Forward / data-gradient GEMMs keep a
+    // fixed summation order (bit-reproducible results); their few-tile cases use the BN = 64 shape instead.
+    if (a_mn_major && !relu && !out_bf16 && tiles * 2 <= sms && p.kb_total >= 8) {
         splits = sms / tiles;
         const int max_by_k = p.kb_total / 4;  // at least 4 k-blocks (256 contraction elements) per split
         if (splits > max_by_k) splits = max_by_k;
         if (splits < 1) splits = 1;
     }
+    static const bool no_splitk = getenv("STCAT_NO_SPLITK") != nullptr;  // diagnosis: deterministic summation order
+    if (no_splitk) splits = 1;
     p.kb_per_split = (p.kb_total + splits - 1) / splits;
     p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
     p.relu = relu;
@@ -345,23 +400,25 @@ int gemm_tc(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t l
     const int total = tiles * p.splits;
     const int grid = total < sms ? total : sms;
 
-#define STCAT_TC_LAUNCH(AMN, BMN, OBF)                                                                              \
-    do {                                                                                                            \
-        static bool attr_set = false;                                                                               \
-        if (!attr_set) {                                                                                            \
-            cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AMN, BMN, OBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); \
-            if (e != cudaSuccess) return set_err((int)e, "gemm_tc: smem attribute: %s", cudaGetErrorString(e));     \
-            attr_set = true;                                                                                        \
-        }                                                                                                           \
-        gemm_tc_kernel<AMN, BMN, OBF><<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmB, tmC, p);                          \
-    } while (0)
+    if (!a_mn_major && !b_mn_major)
+        return out_bf16 ? launch_tc<false, false, true, BN>(tmA, tmB, tmC, p, grid, st) : launch_tc<false, false, false, BN>(tmA, tmB, tmC, p, grid, st);
+    if (!a_mn_major && b_mn_major)
+        return out_bf16 ? launch_tc<false, true, true, BN>(tmA, tmB, tmC, p, grid, st) : launch_tc<false, true, false, BN>(tmA, tmB, tmC, p, grid, st);
+    if (a_mn_major && b_mn_major)
+        return out_bf16 ? launch_tc<true, true, true, BN>(tmA, tmB, tmC, p, grid, st) : launch_tc<true, true, false, BN>(tmA, tmB, tmC, p, grid, st);
+    return set_err(STCAT_ESHAPE, "gemm_tc: A MN-major with B K-major is not instantiated");
+}
 
-    if (!a_mn_major && !b_mn_major) { if (out_bf16) STCAT_TC_LAUNCH(false, false, true); else STCAT_TC_LAUNCH(false, false, false); }
-    else if (!a_mn_major && b_mn_major) { if (out_bf16) STCAT_TC_LAUNCH(false, true, true); else STCAT_TC_LAUNCH(false, true, false); }
-    else if (a_mn_major && b_mn_major) { if (out_bf16) STCAT_TC_LAUNCH(true, true, true); else STCAT_TC_LAUNCH(true, true, false); }
-    else return set_err(STCAT_ESHAPE, "gemm_tc: A MN-major with B K-major is not instantiated");
-#undef STCAT_TC_LAUNCH
-    return check_launch("gemm_tc_kernel");
+int gemm_tc(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* C,
+            int64_t ldc, int out_dtype, const float* bias, int M, int N, int K, int relu, int accumulate,
+            cudaStream_t st) {
+    // tile shape: the latency shape when the 128 x 256 tiling would leave most SMs idle and the K loop is short
+    const int tiles256 = ((M + tc::BM - 1) / tc::BM) * ((N + 255) / 256);
+    const int kb = (K + tc::BK - 1) / tc::BK;
+    static const int force_bn = getenv("STCAT_TC_BN") ? atoi(getenv("STCAT_TC_BN")) : 0;
+    const bool skinny = force_bn ? force_bn == 64 : (tiles256 * 4 <= num_sms() && kb <= 64);
+    if (skinny) return gemm_tc_bn<64>(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, out_dtype, bias, M, N, K, relu, accumulate, st);
+    return gemm_tc_bn<256>(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, out_dtype, bias, M, N, K, relu, accumulate, st);
 }
 
 }  // namespace stcat

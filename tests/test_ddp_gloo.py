@@ -1,0 +1,127 @@
+"""CPU (-m "not gpu"), world_size 2 over gloo: the N>1 path of the hot path (DESIGN.md "Multi-GPU").
+
+Each rank runs fwd + loss + bwd of its own clip with the wgrad kernels accumulating into the flat gradient buffer
+(stcat_b200/dp.py), then ONE all-reduce of that buffer.  The result must equal the sum of the two clips' gradients
+computed in a single process, and parameters the forward never uses (fusion.*, ca_qtime_proj.*) must stay zero
+without any unused-parameter search (the reference needs find_unused_parameters=True, train_net.py:34).
+The kernels are emulated on CPU (tests/emu_backend.py); the kernels themselves are covered by the -m gpu tests.
+"""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _clip_grads(rank_seed, fused_flat):
+    from helpers import cfg_for
+    from emu_backend import EmuBackend
+    from stcat_b200 import ops, synthetic
+    from stcat_b200.dp import FlatGrads
+    from stcat_b200.loss import STGLossPlan
+    from stcat_b200.nested import NestedTensor
+    from stcat_b200.param_spec import synthetic_params
+    from stcat_b200.pipeline import STCATHotPath
+
+    ops.set_backend(EmuBackend())
+    ops.set_precision("fp32")
+    cfg = cfg_for({"max_video_len": 16})
+    model = STCATHotPath(cfg).load_flat_params(synthetic_params(cfg, seed=0)).eval()  # same weights on every rank
+    T = 5
+    inp = synthetic.make_inputs([T], 3, 3, 4, seed=rank_seed)  # rank-seeded clip (bench.py: seed = 42 + rank)
+    tg = synthetic.make_targets([T], seed=rank_seed)
+    plan = STGLossPlan(cfg, tg["boxes"], tg["actioness"], [T], "cpu")
+    grads = FlatGrads(model) if fused_flat else None
+    ops.set_grad_fusion(fused_flat)
+    try:
+        vis = inp["vis_features"].clone().requires_grad_(True)
+        out = model(NestedTensor(vis, inp["vis_mask"], [T]), inp["vis_pos"], (inp["text_mask"], inp["text_memory"], None))
+        total, _ = plan(out)
+        total.backward()
+    finally:
+        ops.set_grad_fusion(False)
+    return model, grads, float(total.detach())
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model, grads, loss = _clip_grads(42 + rank, fused_flat=True)
+        local = grads.buf.clone()
+        grads.all_reduce()
+        # every .grad is still a view of the reduced buffer
+        for p in grads.params:
+            assert p.grad.untyped_storage().data_ptr() == grads.buf.untyped_storage().data_ptr()
+        gathered = [torch.zeros_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        expect = sum(gathered)
+        assert torch.allclose(grads.buf, expect, rtol=0, atol=0)
+        # max-over-ranks timing idiom of bench.py works over gloo too
+        t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert float(t) == float(world)
+        named = {k: p.grad.clone() for k, p in model.named_parameters()}
+        q.put((rank, loss, named))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_flat_gradient_allreduce_world2():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        rank, loss, named = q.get(timeout=240)
+        res[rank] = (loss, named)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    # both ranks hold the same reduced gradients
+    for k, g in res[0][1].items():
+        assert torch.equal(g, res[1][1][k]), k
+    # ... equal to the single-process sum of the two clips' ordinary autograd gradients
+    sys.path.insert(0, HERE)
+    singles = [_clip_grads(42 + r, fused_flat=False) for r in range(world)]
+    from stcat_b200 import ops
+
+    ops.set_backend(None)
+    assert res[0][0] != res[1][0]  # different clips per rank
+    for r in range(world):
+        assert abs(singles[r][2] - res[r][0]) < 1e-6 * abs(singles[r][2])
+    unused = 0
+    for k, g in res[0][1].items():
+        parts = [dict(m.named_parameters())[k].grad for m, _, _ in singles]
+        if all(p is None for p in parts):
+            assert float(g.abs().max()) == 0.0, k  # unused parameter: zero slice, no search needed
+            unused += 1
+            continue
+        ref = sum(p for p in parts if p is not None)
+        err = float((g - ref).abs().max())
+        assert err <= 1e-5 * float(ref.abs().max()) + 1e-7, (k, err)
+    assert unused >= 8  # fusion.{weight,bias} + 6 x ca_qtime_proj.{weight,bias} at least
