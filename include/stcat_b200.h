@@ -50,6 +50,10 @@ STCAT_API int stcat_device_arch(void);
  * net_utils.py:14-25; heads pipeline.py:42-47).
  *   fwd       : y[M,N]   = act(x[M,K] . w[N,K]^T + bias[N])   (+ y if accumulate)
  *   bwd_data  : dx[M,K]  = dy[M,N] . w[N,K]                    (+ dx if accumulate)
+ *               relu_y [M,K] (may be NULL): forward output of the ReLU layer that produced this Linear's input;
+ *               dx is zeroed where relu_y <= 0 (F.relu backward fused into the epilogue, modal_encoder.py:239).
+ *               dbias [K] fp32 (may be NULL): ACCUMULATED with the column sums of the stored dx, i.e. the bias
+ *               gradient of that layer below (its dy is this dx).
  *   bwd_weight: dw[N,K] (+)= dy[M,N]^T . x[M,K];  db[N] (+)= column sums of dy   (db may be NULL)
  * fp32 operands run the exact-fp32 SIMT kernel; bf16 operands run the tcgen05/TMA kernel (fp32
  * accumulate).  y/dx/dw dtype is given separately.  relu: 0/1.  bias may be NULL.
@@ -58,7 +62,8 @@ STCAT_API int stcat_linear_fwd(const void* x, int64_t ldx, int x_dtype, const vo
                      const float* bias, void* y, int64_t ldy, int y_dtype, int M, int N, int K, int relu,
                      int accumulate, void* stream);
 STCAT_API int stcat_linear_bwd_data(const void* dy, int64_t lddy, int dy_dtype, const void* w, int64_t ldw, int w_dtype,
-                          void* dx, int64_t lddx, int dx_dtype, int M, int N, int K, int accumulate, void* stream);
+                          void* dx, int64_t lddx, int dx_dtype, const void* relu_y, int64_t ldy, int y_dtype,
+                          float* dbias, int M, int N, int K, int accumulate, void* stream);
 STCAT_API int stcat_linear_bwd_weight(const void* dy, int64_t lddy, int dy_dtype, const void* x, int64_t ldx, int x_dtype,
                             float* dw, int64_t lddw, float* db, int M, int N, int K, int accumulate, void* stream);
 
@@ -68,11 +73,15 @@ STCAT_API int stcat_linear_bwd_weight(const void* dy, int64_t lddy, int dy_dtype
  *   fwd: z = x + res (res may be NULL);  y = (z - mean) * rstd * gamma + beta;  mean/rstd [rows] saved.
  *        y_bf16 (may be NULL) additionally receives y rounded to bf16 (operand copy for the next GEMM).
  *   bwd: dz[rows,d] = LN backward; dgamma[d], dbeta[d] are ACCUMULATED (atomicAdd) into.
+ *        dz_bf16 (may be NULL) additionally receives dz rounded to bf16 (operand copy for the dgrad / wgrad GEMMs
+ *        that consume it); dbias[d] (may be NULL) is ACCUMULATED with the column sums of dz, i.e. the gradient of
+ *        the bias of the Linear whose output is x (out_proj / linear2 in every block of the reference).
  * ---------------------------------------------------------------------------------------------- */
 STCAT_API int stcat_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y,
                         void* y_bf16, float* mean, float* rstd, int rows, int d, float eps, void* stream);
 STCAT_API int stcat_layernorm_bwd(const float* dy, const float* x, const float* res, const float* gamma, const float* mean,
-                        const float* rstd, float* dz, float* dgamma, float* dbeta, int rows, int d, void* stream);
+                        const float* rstd, float* dz, void* dz_bf16, float* dgamma, float* dbeta, float* dbias, int rows,
+                        int d, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-head attention core, batch-major (torch functional.py:6630-6665 bmm/softmax/bmm; reference

@@ -26,10 +26,10 @@ SIGNATURES = {
     "stcat_last_error": (c_char_p, []),
     "stcat_device_arch": (c_int, []),
     "stcat_linear_fwd": (c_int, [_P, _L, _I, _P, _L, _I, _P, _P, _L, _I, _I, _I, _I, _I, _I, _P]),
-    "stcat_linear_bwd_data": (c_int, [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P]),
+    "stcat_linear_bwd_data": (c_int, [_P, _L, _I, _P, _L, _I, _P, _L, _I, _P, _L, _I, _P, _I, _I, _I, _I, _P]),
     "stcat_linear_bwd_weight": (c_int, [_P, _L, _I, _P, _L, _I, _P, _L, _P, _I, _I, _I, _I, _P]),
     "stcat_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P]),
-    "stcat_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "stcat_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "stcat_attention_fwd": (c_int, [_P, _P, _L, _P, _P, _L, _P, _L, _P, _L, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
     "stcat_attention_bwd": (c_int, [_P, _P, _L, _P, _P, _L, _P, _L, _P, _L, _P, _L, _I, _P, _P, _P, _P, _P, _P, _L, _P, _P,
                                     _L, _P, _L, _I, _I, _I, _I, _I, _F, _P]),
@@ -126,12 +126,17 @@ class CudaBackend:
                                            yd, M, N, K, int(relu), int(accumulate), self._stream()), "linear_fwd")
         self.launches += 1
 
-    def linear_bwd_data(self, dy, w, dx, accumulate=False):
+    def linear_bwd_data(self, dy, w, dx, accumulate=False, relu_y=None, dbias=None):
+        """dx = dy . w (+ dx); with relu_y ([M, K], the forward activation of the layer below) the result is zeroed
+        where relu_y <= 0, and with dbias ([K] fp32) the column sums of the stored dx are accumulated into it."""
         (gp, ldg, gd), (wp, ldw, wd), (xp, ldx, xd) = self._mat(dy, "dy"), self._mat(w, "w"), self._mat(dx, "dx")
         M, N = dy.shape
         K = w.shape[1]
         assert w.shape[0] == N and tuple(dx.shape) == (M, K)
-        self._rc(self.lib.stcat_linear_bwd_data(gp, ldg, gd, wp, ldw, wd, xp, ldx, xd, M, N, K, int(accumulate),
+        yp, ldy, yd = (None, 0, F32) if relu_y is None else self._mat(relu_y, "relu_y")
+        assert relu_y is None or tuple(relu_y.shape) == (M, K)
+        self._rc(self.lib.stcat_linear_bwd_data(gp, ldg, gd, wp, ldw, wd, xp, ldx, xd, yp, ldy, yd,
+                                                self._flat(dbias, "dbias", torch.float32), M, N, K, int(accumulate),
                                                 self._stream()), "linear_bwd_data")
         self.launches += 1
 
@@ -155,13 +160,15 @@ class CudaBackend:
                  "layernorm_fwd")
         self.launches += 1
 
-    def layernorm_bwd(self, dy, x, res, gamma, mean, rstd, dz, dgamma, dbeta):
+    def layernorm_bwd(self, dy, x, res, gamma, mean, rstd, dz, dgamma, dbeta, dz_bf16=None, dbias=None):
         rows, d = x.shape
         f = torch.float32
         self._rc(self.lib.stcat_layernorm_bwd(self._flat(dy, "dy", f), self._flat(x, "x", f), self._flat(res, "res", f),
                                               self._flat(gamma, "gamma", f), self._flat(mean, "mean", f),
                                               self._flat(rstd, "rstd", f), self._flat(dz, "dz", f),
-                                              self._flat(dgamma, "dgamma", f), self._flat(dbeta, "dbeta", f), rows, d,
+                                              self._flat(dz_bf16, "dz_bf16", torch.bfloat16),
+                                              self._flat(dgamma, "dgamma", f), self._flat(dbeta, "dbeta", f),
+                                              self._flat(dbias, "dbias", f), rows, d,
                                               self._stream()), "layernorm_bwd")
         self.launches += 1
 

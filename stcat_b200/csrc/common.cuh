@@ -44,6 +44,13 @@ template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// optional epilogue extras of the tensor-core GEMM (gemm_tcgen05.cu), used by stcat_linear_bwd_data
+struct GemmEpilogue {
+    const void* relu_mask = nullptr;   // bf16 [M, N]: C is zeroed where relu_mask <= 0
+    int64_t ld_mask = 0;
+    float* colsum = nullptr;           // [N] fp32: accumulated with the column sums of the stored C
+};
+
 inline int num_sms() {
     static int n = 0;
     if (n == 0) {

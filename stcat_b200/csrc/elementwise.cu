@@ -170,6 +170,37 @@ map2d_pool_kernel(const float* __restrict__ x, const uint8_t* __restrict__ valid
     }
 }
 
+
+// dx[m, n] = 0 where y[m, n] <= 0 (strided 2-D form of relu_bwd; unfused tail of stcat_linear_bwd_data)
+template <typename TY, typename TD>
+__global__ void __launch_bounds__(256) relu_mask_2d_kernel(const TY* __restrict__ y, int64_t ldy, TD* __restrict__ dx,
+                                                           int64_t lddx, int M, int N) {
+    const int64_t total = (int64_t)M * N;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / N, n = i % N;
+        if (!(to_f32<TY>(y[m * ldy + n]) > 0.f)) dx[m * lddx + n] = from_f32<TD>(0.f);
+    }
+}
+
+int relu_mask_2d(const void* y, int64_t ldy, int y_dtype, void* dx, int64_t lddx, int dx_dtype, int M, int N, cudaStream_t st) {
+    const int64_t total = (int64_t)M * N;
+    int g = (int)((total + 255) / 256);
+    const int cap = num_sms() * 8;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    if (y_dtype == STCAT_F32 && dx_dtype == STCAT_F32)
+        relu_mask_2d_kernel<float, float><<<g, 256, 0, st>>>((const float*)y, ldy, (float*)dx, lddx, M, N);
+    else if (y_dtype == STCAT_BF16 && dx_dtype == STCAT_F32)
+        relu_mask_2d_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)y, ldy, (float*)dx, lddx, M, N);
+    else if (y_dtype == STCAT_BF16 && dx_dtype == STCAT_BF16)
+        relu_mask_2d_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)y, ldy, (__nv_bfloat16*)dx, lddx, M, N);
+    else if (y_dtype == STCAT_F32 && dx_dtype == STCAT_BF16)
+        relu_mask_2d_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)y, ldy, (__nv_bfloat16*)dx, lddx, M, N);
+    else
+        return set_err(STCAT_EINVAL, "relu_mask_2d: bad dtype %d/%d", y_dtype, dx_dtype);
+    return check_launch("relu_mask_2d_kernel");
+}
+
 }  // namespace stcat
 
 using namespace stcat;

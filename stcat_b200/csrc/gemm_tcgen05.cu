@@ -57,6 +57,9 @@ struct Params {
     int tiles_m, tiles_n, splits, kb_per_split, kb_total;
     int relu;
     int reduce_add;  // epilogue uses TMA reduce-add instead of store
+    const __nv_bfloat16* mask;  // optional [M, N] bf16: C is zeroed where mask <= 0 (ReLU backward), else null
+    int64_t ld_mask;
+    float* colsum;              // optional [N]: accumulated (atomicAdd) with the column sums of the stored C
 };
 
 template <bool A_MN, bool B_MN, bool OUT_BF16, int BN>
@@ -211,6 +214,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int h = 0; h < CHUNK_COLS / 32; ++h)
                     tmem_ld32(t_row + c * CHUNK_COLS + h * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[h * 32]));
+                uint4 mk[CHUNK_COLS / 8];  // this row's slice of the ReLU mask (bf16), in flight with the TMEM loads
+                if (p.mask) {
+                    const int gr = m_blk * BM + row;
+                    const uint4* mp = reinterpret_cast<const uint4*>(p.mask + (int64_t)gr * p.ld_mask + n_blk * BN + g * GC + c * CHUNK_COLS);
+#pragma unroll
+                    for (int j = 0; j < CHUNK_COLS / 8; ++j) mk[j] = gr < p.M ? __ldg(mp + j) : make_uint4(0, 0, 0, 0);
+                }
                 // the staging tile must have been read by the previous TMA store of this group
                 if (gt == 0) tma_wait_read<0>();
                 if (c == NCHUNK - 1 || (c + 1) * CHUNK_COLS >= n_valid) {
@@ -231,6 +241,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (p.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
                     r[4 * j + 0] = __float_as_uint(x0); r[4 * j + 1] = __float_as_uint(x1);
                     r[4 * j + 2] = __float_as_uint(x2); r[4 * j + 3] = __float_as_uint(x3);
+                }
+                if (p.mask) {  // y > 0 for a bf16 y  <=>  its bits, read as int16, are > 0
+#pragma unroll
+                    for (int j = 0; j < CHUNK_COLS / 8; ++j) {
+                        const uint32_t w4[4] = {mk[j].x, mk[j].y, mk[j].z, mk[j].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if ((int16_t)(w4[e] & 0xffffu) <= 0) r[8 * j + 2 * e] = 0u;
+                            if ((int16_t)(w4[e] >> 16) <= 0) r[8 * j + 2 * e + 1] = 0u;
+                        }
+                    }
                 }
                 if (OUT_BF16) {
 #pragma unroll
@@ -253,11 +274,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                const int c0 = n_blk * BN + g * GC + c * CHUNK_COLS;
                 if (gt == 0) {
-                    const int c0 = n_blk * BN + g * GC + c * CHUNK_COLS;
                     if (p.reduce_add) tma_reduce_add_2d(&tmC, sbuf_base, c0, m_blk * BM);
                     else tma_store_2d(&tmC, sbuf_base, c0, m_blk * BM);
                     tma_commit();
+                }
+                if (p.colsum) {
+                    // column sums of the staged (rounded) tile: 128 threads = CHUNK_COLS columns x (128 / CHUNK_COLS)
+                    // row slabs; rows past M hold zeros (TMA zero-fills A).  The next chunk overwrites the staging
+                    // tile only after the group's next bar.sync, which this thread reaches after its reads.
+                    constexpr int SLABS = 128 / CHUNK_COLS, ROWS = BM / SLABS;
+                    const int cc = gt % CHUNK_COLS, r0 = (gt / CHUNK_COLS) * ROWS;
+                    float sum = 0.f;
+#pragma unroll 8
+                    for (int rr = r0; rr < r0 + ROWS; ++rr) {
+                        if (OUT_BF16) {
+                            uint16_t hv;
+                            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(sbuf_base + rr * 128 + (((cc >> 3) ^ (rr & 7)) << 4) + (cc & 7) * 2));
+                            sum += __uint_as_float((uint32_t)hv << 16);
+                        } else {
+                            float fv;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(fv) : "r"(sbuf_base + rr * 128 + (((cc >> 2) ^ (rr & 7)) << 4) + (cc & 3) * 4));
+                            sum += fv;
+                        }
+                    }
+                    if (c0 + cc < p.N) atomicAdd(p.colsum + c0 + cc, sum);
                 }
             }
             if (!released) release_acc();  // this group's half lies entirely outside N
@@ -355,7 +397,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
 template <int BN>
 static int gemm_tc_bn(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* C,
                       int64_t ldc, int out_dtype, const float* bias, int M, int N, int K, int relu, int accumulate,
-                      cudaStream_t st) {
+                      cudaStream_t st, const GemmEpilogue* epi) {
     using namespace tc;
     const bool out_bf16 = out_dtype == STCAT_BF16;
     CUtensorMap tmA, tmB, tmC;
@@ -391,6 +433,11 @@ static int gemm_tc_bn(const void* A, int64_t lda, int a_mn_major, const void* B,
     p.kb_per_split = (p.kb_total + splits - 1) / splits;
     p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
     p.relu = relu;
+    p.mask = epi ? (const __nv_bfloat16*)epi->relu_mask : nullptr;
+    p.ld_mask = epi ? epi->ld_mask : 0;
+    p.colsum = epi ? epi->colsum : nullptr;
+    if ((p.mask || p.colsum) && (a_mn_major || accumulate || N % 64 != 0))
+        return set_err(STCAT_ESHAPE, "gemm_tc: fused ReLU-mask / column-sum epilogue needs N %% 64 == 0, no accumulate, K-major A");
     p.reduce_add = (accumulate || p.splits > 1) ? 1 : 0;
     if (p.splits > 1 && !accumulate) {
         cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st);
@@ -411,14 +458,14 @@ static int gemm_tc_bn(const void* A, int64_t lda, int a_mn_major, const void* B,
 
 int gemm_tc(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* C,
             int64_t ldc, int out_dtype, const float* bias, int M, int N, int K, int relu, int accumulate,
-            cudaStream_t st) {
+            cudaStream_t st, const GemmEpilogue* epi) {
     // tile shape: the latency shape when the 128 x 256 tiling would leave most SMs idle and the K loop is short
     const int tiles256 = ((M + tc::BM - 1) / tc::BM) * ((N + 255) / 256);
     const int kb = (K + tc::BK - 1) / tc::BK;
     static const int force_bn = getenv("STCAT_TC_BN") ? atoi(getenv("STCAT_TC_BN")) : 0;
     const bool skinny = force_bn ? force_bn == 64 : (tiles256 * 4 <= num_sms() && kb <= 64);
-    if (skinny) return gemm_tc_bn<64>(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, out_dtype, bias, M, N, K, relu, accumulate, st);
-    return gemm_tc_bn<256>(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, out_dtype, bias, M, N, K, relu, accumulate, st);
+    if (skinny) return gemm_tc_bn<64>(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, out_dtype, bias, M, N, K, relu, accumulate, st, epi);
+    return gemm_tc_bn<256>(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, out_dtype, bias, M, N, K, relu, accumulate, st, epi);
 }
 
 }  // namespace stcat

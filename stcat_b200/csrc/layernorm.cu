@@ -2,7 +2,8 @@
 // 128-bit loads per lane per operand, shuffle reductions, no shared memory in the forward).
 //
 // Algorithmic bytes per row (fp32): fwd reads x, res (2*1 KB) and writes y (1 KB) [+0.5 KB bf16 copy];
-// bwd reads dy, x, res (3 KB) and writes dz (1 KB).
+// bwd reads dy, x, res (3 KB) and writes dz (1 KB) [+0.5 KB bf16 copy]; the column sums it keeps anyway for
+// dgamma / dbeta also give the bias gradient of the Linear in front of the norm (db = colsum(dz)) for free.
 #include "common.cuh"
 
 namespace stcat {
@@ -65,15 +66,17 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ res,
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ res,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
-                     float* __restrict__ dz, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows) {
+                     float* __restrict__ dz, __nv_bfloat16* __restrict__ dz_bf16, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, float* __restrict__ dbias, int rows) {
     __shared__ float sg[LN_ROWS_PER_BLOCK][LN_D];
     __shared__ float sb[LN_ROWS_PER_BLOCK][LN_D];
+    __shared__ float sz[LN_ROWS_PER_BLOCK][LN_D];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float g[8];
     load_row(gamma, lane, g);
-    float ag[8], ab[8];
+    float ag[8], ab[8], az[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
+    for (int i = 0; i < 8; ++i) { ag[i] = 0.f; ab[i] = 0.f; az[i] = 0.f; }
     for (int row = blockIdx.x * LN_ROWS_PER_BLOCK + warp; row < rows; row += gridDim.x * LN_ROWS_PER_BLOCK) {
         float z[8], d[8];
         load_row(x + (int64_t)row * LN_D, lane, z);
@@ -100,11 +103,19 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
         s2 = warp_sum(s2) * (1.f / LN_D);
         float o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = rs * (dg[i] - s1 - xh[i] * s2);
+        for (int i = 0; i < 8; ++i) { o[i] = rs * (dg[i] - s1 - xh[i] * s2); az[i] += o[i]; }
         store_row(dz + (int64_t)row * LN_D, lane, o);
+        if (dz_bf16) {  // GEMM-operand copy for the dgrad / wgrad that consume dz next
+            __nv_bfloat16* zb = dz_bf16 + (int64_t)row * LN_D;
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(o[4], o[5]), p3 = __floats2bfloat162_rn(o[6], o[7]);
+            *reinterpret_cast<uint2*>(zb + lane * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
+            *reinterpret_cast<uint2*>(zb + 128 + lane * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+        }
     }
     store_row(sg[warp], lane, ag);
     store_row(sb[warp], lane, ab);
+    if (dbias) store_row(sz[warp], lane, az);
     __syncthreads();
     const int c = threadIdx.x;  // 256 threads == 256 columns
     float tg = 0.f, tb = 0.f;
@@ -112,6 +123,12 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     for (int w = 0; w < LN_ROWS_PER_BLOCK; ++w) { tg += sg[w][c]; tb += sb[w][c]; }
     atomicAdd(dgamma + c, tg);
     atomicAdd(dbeta + c, tb);
+    if (dbias) {  // column sums of dz = gradient of the bias of the Linear that produced x
+        float tz = 0.f;
+#pragma unroll
+        for (int w = 0; w < LN_ROWS_PER_BLOCK; ++w) tz += sz[w][c];
+        atomicAdd(dbias + c, tz);
+    }
 }
 
 }  // namespace stcat
@@ -133,14 +150,15 @@ extern "C" int stcat_layernorm_fwd(const float* x, const float* res, const float
 }
 
 extern "C" int stcat_layernorm_bwd(const float* dy, const float* x, const float* res, const float* gamma,
-                                   const float* mean, const float* rstd, float* dz, float* dgamma, float* dbeta,
-                                   int rows, int d, void* stream) {
+                                   const float* mean, const float* rstd, float* dz, void* dz_bf16, float* dgamma,
+                                   float* dbeta, float* dbias, int rows, int d, void* stream) {
     STCAT_REQUIRE(dy && x && gamma && mean && rstd && dz && dgamma && dbeta, STCAT_EINVAL, "layernorm_bwd: null pointer");
     STCAT_REQUIRE(d == LN_D, STCAT_ESHAPE, "layernorm_bwd: d=%d unsupported (HIDDEN must be 256)", d);
     if (rows <= 0) return rows == 0 ? 0 : set_err(STCAT_EINVAL, "layernorm_bwd: rows=%d", rows);
     int blocks = (rows + LN_ROWS_PER_BLOCK - 1) / LN_ROWS_PER_BLOCK;
     int cap = num_sms() * 2;
     if (blocks > cap) blocks = cap;
-    layernorm_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dy, x, res, gamma, mean, rstd, dz, dgamma, dbeta, rows);
+    layernorm_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dy, x, res, gamma, mean, rstd, dz, (__nv_bfloat16*)dz_bf16,
+                                                                   dgamma, dbeta, dbias, rows);
     return check_launch("layernorm_bwd_kernel");
 }

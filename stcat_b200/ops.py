@@ -54,16 +54,22 @@ def _wgrad(be, dyo, xo, W, b, need_w, need_b, r0=None, r1=None):
     return dw, db
 
 
-def _ln_bwd(be, dy, x, res, gamma, beta, mean, rstd, dz):
-    """LayerNorm backward; returns (dgamma, dbeta) for autograd or Nones when accumulated into .grad."""
+def _ln_bwd(be, dy, x, res, gamma, beta, mean, rstd, dz, dz_op=None, lin_bias=None):
+    """LayerNorm backward; returns (dgamma, dbeta, dbias) for autograd, each None when it was accumulated into
+    .grad.  ``dz_op`` (bf16 [rows, d]) receives the GEMM-operand copy of dz; ``lin_bias`` is the bias parameter of
+    the Linear whose output is ``x``: its gradient is colsum(dz), which the kernel sums anyway."""
     d = x.shape[1]
-    if _fuse_grads and gamma.grad is not None and beta is not None and beta.grad is not None:
-        be.layernorm_bwd(dy, x, res, gamma.detach(), mean, rstd, dz, gamma.grad, beta.grad)
-        return None, None
+    fused = _fuse_grads and gamma.grad is not None and beta is not None and beta.grad is not None and \
+        (lin_bias is None or lin_bias.grad is not None)
+    if fused:
+        be.layernorm_bwd(dy, x, res, gamma.detach(), mean, rstd, dz, gamma.grad, beta.grad, dz_bf16=dz_op,
+                         dbias=None if lin_bias is None else lin_bias.grad)
+        return None, None, None
     dg = torch.zeros(d, dtype=torch.float32, device=dy.device)
     dbt = torch.zeros(d, dtype=torch.float32, device=dy.device)
-    be.layernorm_bwd(dy, x, res, gamma.detach(), mean, rstd, dz, dg, dbt)
-    return dg, dbt
+    dlb = None if lin_bias is None else torch.zeros(d, dtype=torch.float32, device=dy.device)
+    be.layernorm_bwd(dy, x, res, gamma.detach(), mean, rstd, dz, dg, dbt, dz_bf16=dz_op, dbias=dlb)
+    return dg, dbt, dlb
 
 
 def get_backend():
@@ -291,7 +297,7 @@ class LayerNormFn(Function):
         dy2 = _rows(dy, d)
         dy2 = dy2 if dy2.is_contiguous() else dy2.contiguous()
         dz = torch.empty_like(x2)
-        dg, db = _ln_bwd(be, dy2, x2, r2, gamma, ctx.beta, mean, rstd, dz)
+        dg, db, _ = _ln_bwd(be, dy2, x2, r2, gamma, ctx.beta, mean, rstd, dz)
         dzv = dz.view(ctx.shape)
         dx = dzv.to(ctx.dtypes[0]) if ctx.needs_input_grad[0] else None
         dr = dzv.to(ctx.dtypes[1]) if (r2 is not None and ctx.needs_input_grad[1]) else None
@@ -508,9 +514,10 @@ class SelfAttnBlockFn(Function):
         wo = _operand(w_out.detach(), True)
         b_in, b_out, beta = ctx.extra
         dz = _new(R, d, f32, dy)  # grad wrt (a) and wrt the residual x
-        dg, dbt = _ln_bwd(be, dy, a, xd, gamma, beta, mean, rstd, dz)
-        dz_op = _cast_op(be, dz)
-        dwo, dbo = _wgrad(be, dz_op, o, w_out, b_out, True, True)
+        bf = od == torch.bfloat16
+        dz_op = _new(R, d, od, dy) if bf else dz  # LayerNorm backward writes the bf16 operand copy itself
+        dg, dbt, dbo = _ln_bwd(be, dy, a, xd, gamma, beta, mean, rstd, dz, dz_op if bf else None, b_out)
+        dwo, _ = _wgrad(be, dz_op, o, w_out, None, True, False)
         d_o = _new(R, d, od, dy)
         be.linear_bwd_data(dz_op, wo, d_o)
         dqkv = _new(R, 3 * d, od, dy)
@@ -584,13 +591,19 @@ class FFNBlockFn(Function):
         w1o, w2o = _operand(w1.detach(), True), _operand(w2.detach(), True)
         b1, b2, beta = ctx.extra
         dz = _new(R, d, f32, dy)
-        dg, dbt = _ln_bwd(be, dy, yl, xd, gamma, beta, mean, rstd, dz)
-        dz_op = _cast_op(be, dz)
-        dw2, db2 = _wgrad(be, dz_op, h, w2, b2, True, True)
+        bf = od == torch.bfloat16
+        dz_op = _new(R, d, od, dy) if bf else dz
+        dg, dbt, db2 = _ln_bwd(be, dy, yl, xd, gamma, beta, mean, rstd, dz, dz_op if bf else None, b2)
+        dw2, _ = _wgrad(be, dz_op, h, w2, None, True, False)
+        # dh = (dz W2) * (h > 0) with db1 = colsum(dh): ReLU backward and the bias gradient ride in the dgrad epilogue
         dh = _new(R, F_, od, dy)
-        be.linear_bwd_data(dz_op, w2o, dh)
-        be.relu_bwd(h, dh)
-        dw1, db1 = _wgrad(be, dh, xo, w1, b1, True, True)
+        if _fuse_grads and b1.grad is not None:
+            db1 = None
+            be.linear_bwd_data(dz_op, w2o, dh, relu_y=h, dbias=b1.grad)
+        else:
+            db1 = torch.zeros(F_, dtype=f32, device=dy.device)
+            be.linear_bwd_data(dz_op, w2o, dh, relu_y=h, dbias=db1)
+        dw1, _ = _wgrad(be, dh, xo, w1, None, True, False)
         be.linear_bwd_data(dh, w1o, dz, accumulate=True)
         return dz, None, dw1, db1, dw2, db2, dg, dbt, None
 

@@ -35,11 +35,15 @@ class EmuBackend:
         _store(y, v)
         self.launches += 1
 
-    def linear_bwd_data(self, dy, w, dx, accumulate=False):
+    def linear_bwd_data(self, dy, w, dx, accumulate=False, relu_y=None, dbias=None):
         v = _f(dy) @ _f(w)
         if accumulate:
             v = v + _f(dx)
+        if relu_y is not None:
+            v = v * (_f(relu_y) > 0)
         _store(dx, v)
+        if dbias is not None:
+            dbias.add_(_f(dx).sum(0))
         self.launches += 1
 
     def linear_bwd_weight(self, dy, x, dw, db, accumulate=False):
@@ -68,7 +72,7 @@ class EmuBackend:
         rstd.copy_(rs)
         self.launches += 1
 
-    def layernorm_bwd(self, dy, x, res, gamma, mean, rstd, dz, dgamma, dbeta):
+    def layernorm_bwd(self, dy, x, res, gamma, mean, rstd, dz, dgamma, dbeta, dz_bf16=None, dbias=None):
         z = x if res is None else x + res
         xh = (z - mean[:, None]) * rstd[:, None]
         dg = dy * gamma
@@ -77,6 +81,10 @@ class EmuBackend:
         dz.copy_(rstd[:, None] * (dg - s1 - xh * s2))
         dgamma.add_((dy * xh).sum(0))
         dbeta.add_(dy.sum(0))
+        if dz_bf16 is not None:
+            dz_bf16.copy_(dz.to(torch.bfloat16))
+        if dbias is not None:
+            dbias.add_(dz.sum(0))
         self.launches += 1
 
     # -- attention -----------------------------------------------------

@@ -57,7 +57,7 @@ def _clip_grads(rank_seed, fused_flat):
     return model, grads, float(total.detach())
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, outdir):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -80,28 +80,29 @@ def _worker(rank, world, port, q):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         assert float(t) == float(world)
         named = {k: p.grad.clone() for k, p in model.named_parameters()}
-        q.put((rank, loss, named))
+        torch.save({"loss": loss, "grads": named}, os.path.join(outdir, f"rank{rank}.pt"))
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.timeout(300)
-def test_flat_gradient_allreduce_world2():
+def test_flat_gradient_allreduce_world2(tmp_path):
     world = 2
     port = _free_port()
     ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, str(tmp_path))) for r in range(world)]
     for p in procs:
         p.start()
-    res = {}
-    for _ in range(world):
-        rank, loss, named = q.get(timeout=240)
-        res[rank] = (loss, named)
     for p in procs:
-        p.join(60)
+        p.join(240)
+        if p.is_alive():
+            p.kill()
         assert p.exitcode == 0
+    res = {}
+    for r in range(world):
+        d = torch.load(os.path.join(str(tmp_path), f"rank{r}.pt"))
+        res[r] = (d["loss"], d["grads"])
     # both ranks hold the same reduced gradients
     for k, g in res[0][1].items():
         assert torch.equal(g, res[1][1][k]), k

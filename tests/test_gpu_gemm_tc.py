@@ -78,6 +78,30 @@ def test_bwd_bf16(be, M, N, K):
     assert rel_err(dw, 2 * ref_dw) < TOL_F32
 
 
+@pytest.mark.parametrize("M,N,K,odt", [(1000, 256, 2048, "bf16"), (13632, 256, 2048, "bf16"), (64, 256, 2048, "bf16"),
+                                         (500, 256, 128, "f32"), (300, 64, 192, "f32")])
+def test_bwd_data_fused_relu_mask_and_bias_grad(be, M, N, K, odt):
+    """dx = (dy W) * (y > 0) and dbias += colsum(dx) in the dgrad epilogue (F.relu backward + bias gradient of the
+    layer below, modal_encoder.py:239).  N = out features of the upper Linear, K = width of the ReLU layer."""
+    w, dy = g(N, K, seed=2, scale=N ** -0.5), g(M, N, seed=4)
+    y = g(M, K, seed=7).relu()  # forward activation of the ReLU layer (zeros where it was clamped)
+    ref = (dy.double() @ w.double()) * (y.double() > 0)
+    dt = torch.bfloat16 if odt == "bf16" else torch.float32
+    dx = torch.full((M, K), float("nan"), device="cuda", dtype=dt)
+    db = torch.ones(K, device="cuda")
+    be.linear_bwd_data(dy.cuda(), w.cuda(), dx, relu_y=y.cuda(), dbias=db)
+    assert rel_err(dx, ref) < (TOL_BF16 if odt == "bf16" else TOL_F32)
+    assert bool(((dx != 0) <= (y.cuda() > 0)).all())  # exact zeros where the ReLU was inactive
+    # the bias gradient is the column sum of what was STORED (bf16-rounded in bf16 mode), on top of the old content
+    assert rel_err(db - 1, dx.double().sum(0)) < 2e-5
+    # column sums alone (no mask)
+    db2 = torch.zeros(K, device="cuda")
+    dx2 = torch.empty(M, K, device="cuda", dtype=dt)
+    be.linear_bwd_data(dy.cuda(), w.cuda(), dx2, dbias=db2)
+    assert rel_err(dx2, dy.double() @ w.double()) < (TOL_BF16 if odt == "bf16" else TOL_F32)
+    assert rel_err(db2, dx2.double().sum(0)) < 2e-5
+
+
 def test_strided_operands_bf16(be):
     """column slices of the packed qkv buffer (ld = 768) and row slices of the packed in_proj weight"""
     M, d = 777, 256

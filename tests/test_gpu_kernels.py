@@ -90,6 +90,14 @@ def test_layernorm(be, rows):
     assert rel_err(dz, xd.grad) < TOL32
     assert rel_err(dg, gd.grad) < 1e-4  # atomics over many rows
     assert rel_err(dbt, bd.grad) < 1e-4
+    # optional extras: bf16 operand copy of dz and the bias gradient of the Linear in front (colsum of dz), accumulated
+    dz2 = torch.empty(rows, d, device="cuda")
+    dzb = torch.empty(rows, d, device="cuda", dtype=torch.bfloat16)
+    dlb = torch.ones(d, device="cuda")
+    dg2, dbt2 = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+    be.layernorm_bwd(dy.cuda(), x.cuda(), r.cuda(), gm.cuda(), mean, rstd, dz2, dg2, dbt2, dz_bf16=dzb, dbias=dlb)
+    assert torch.equal(dz2, dz) and torch.equal(dzb, dz.to(torch.bfloat16))
+    assert rel_err(dlb - 1, xd.grad.sum(0)) < 1e-4
     # no residual
     be.layernorm_fwd(x.cuda(), None, gm.cuda(), bt.cuda(), y, None, mean, rstd)
     assert rel_err(y, torch.nn.functional.layer_norm(x.double(), (d,), gm.double(), bt.double(), 1e-5)) < TOL32
