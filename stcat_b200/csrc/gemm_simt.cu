@@ -85,6 +85,39 @@ gemm_simt_kernel(const TIn* __restrict__ A, int64_t sam, int64_t sak, const TIn*
     }
 }
 
+// Few-output GEMMs (the 4 / 2 / 1-wide prediction heads and anchor projection, pipeline.py:42-47, query_decoder.py:
+// 446-449): one warp per output element, lanes stride the contraction index, shuffle reduction.  The 64 x 64 tile
+// kernel above would run them on a single CTA with a serial K loop (15-20 us); this is launch-latency bound instead.
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256)
+gemm_warpdot_kernel(const TIn* __restrict__ A, int64_t sam, int64_t sak, const TIn* __restrict__ B, int64_t sbn,
+                    int64_t sbk, TOut* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int M, int N,
+                    int K, int relu, int accumulate) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= (int64_t)M * N) return;
+    const int m = (int)(w / N), n = (int)(w % N);
+    const TIn* a = A + (int64_t)m * sam;
+    const TIn* b = B + (int64_t)n * sbn;
+    float acc0 = 0.f, acc1 = 0.f;
+    int k = lane;
+    for (; k + 32 < K; k += 64) {
+        acc0 = fmaf(to_f32<TIn>(a[(int64_t)k * sak]), to_f32<TIn>(b[(int64_t)k * sbk]), acc0);
+        acc1 = fmaf(to_f32<TIn>(a[(int64_t)(k + 32) * sak]), to_f32<TIn>(b[(int64_t)(k + 32) * sbk]), acc1);
+    }
+    if (k < K) acc0 = fmaf(to_f32<TIn>(a[(int64_t)k * sak]), to_f32<TIn>(b[(int64_t)k * sbk]), acc0);
+    float v = warp_sum(acc0 + acc1);
+    if (lane != 0) return;
+    if (bias) v += bias[n];
+    TOut* p = C + (int64_t)m * ldc + n;
+    if constexpr (sizeof(TOut) == 4) {
+        if (accumulate && !relu) { atomicAdd(reinterpret_cast<float*>(p), v); return; }
+    }
+    if (accumulate) v += to_f32<TOut>(*p);
+    if (relu) v = fmaxf(v, 0.f);
+    *p = from_f32<TOut>(v);
+}
+
 // db[n] += sum_m dy[m, n]
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ dy, int64_t ld, float* __restrict__ db,
@@ -111,6 +144,12 @@ template <typename TIn, typename TOut>
 static int launch_gemm(const void* A, int64_t sam, int64_t sak, const void* B, int64_t sbn, int64_t sbk, void* C,
                        int64_t ldc, const float* bias, int M, int N, int K, int relu, int accumulate,
                        cudaStream_t st) {
+    if ((int64_t)M * N <= 8192 && K >= 32) {  // few outputs: one warp each
+        const int64_t warps = (int64_t)M * N;
+        gemm_warpdot_kernel<TIn, TOut><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>((const TIn*)A, sam, sak, (const TIn*)B, sbn, sbk,
+                                                                                     (TOut*)C, ldc, bias, M, N, K, relu, accumulate);
+        return check_launch("gemm_warpdot_kernel");
+    }
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
     gemm_simt_kernel<TIn, TOut><<<grid, 256, 0, st>>>((const TIn*)A, sam, sak, (const TIn*)B, sbn, sbk, (TOut*)C,
                                                       ldc, bias, M, N, K, relu, accumulate);

@@ -125,6 +125,10 @@ def attn_ref(q1, q2, k1, k2, v, mask, B, H, Lq, Lk, scale):
     (5, 8, 1, 212, True, True, False),
     (2, 8, 65, 65, False, True, True),
     (2, 4, 17, 130, True, True, True),
+    (1, 8, 64, 64, False, False, False),    # decoder self-attention over T = 64 queries (short-sequence kernel)
+    (1, 8, 128, 128, False, True, True),    # short-sequence kernel at its size limit, with the weights output
+    (2, 8, 5, 3, False, True, True),
+    (2, 8, 150, 140, False, True, True),    # generic SIMT path (too long for the short-sequence kernel)
 ])
 def test_attention_fp32(be, B, H, Lq, Lk, two, use_mask, use_pavg):
     E = H * 32
@@ -169,6 +173,28 @@ def test_attention_fp32(be, B, H, Lq, Lk, two, use_mask, use_pavg):
     if two:
         assert rel_err(dq2, leaves[1].grad) < tol
         assert rel_err(dk2, leaves[3].grad) < tol
+
+
+def test_short_sequence_attention_bf16(be):
+    """bf16 operands through the short-sequence kernels (fp32 math on the rounded operands)"""
+    B, H, L = 1, 8, 65
+    E = H * 32
+    tb = lambda s: g(B * L, E, seed=s).to(torch.bfloat16)
+    q, k, v, d_o = tb(1), tb(2), tb(3), tb(6)
+    leaves = [x.double().requires_grad_(True) for x in (q, k, v)]
+    o_ref, pavg_ref, lse_ref = attn_ref(leaves[0], None, leaves[1], None, leaves[2], None, B, H, L, L, 32 ** -0.5)
+    (o_ref * d_o.double()).sum().backward()
+    o = torch.empty(B * L, E, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B, H, L, device="cuda")
+    pavg = torch.zeros(B, L, L, device="cuda")
+    be.attention_fwd(q.cuda(), None, k.cuda(), None, v.cuda(), o, None, lse, pavg, B, H, L, L, 32 ** -0.5)
+    assert rel_err(o, o_ref) < 4e-3 and rel_err(lse, lse_ref) < TOL32 and rel_err(pavg, pavg_ref) < TOL32
+    e = lambda: torch.empty(B * L, E, device="cuda", dtype=torch.bfloat16)
+    dq, dk, dv = e(), e(), e()
+    be.attention_bwd(q.cuda(), None, k.cuda(), None, v.cuda(), d_o.cuda(), None, lse, None, torch.empty(B, H, L, device="cuda"),
+                     dq, None, dk, None, dv, B, H, L, L, 32 ** -0.5)
+    for got, leaf in ((dq, leaves[0]), (dk, leaves[1]), (dv, leaves[2])):
+        assert rel_err(got, leaf.grad) < 6e-3
 
 
 def test_elementwise(be):
