@@ -67,6 +67,35 @@ STCAT_API int stcat_linear_bwd_data(const void* dy, int64_t lddy, int dy_dtype, 
 STCAT_API int stcat_linear_bwd_weight(const void* dy, int64_t lddy, int dy_dtype, const void* x, int64_t ldx, int x_dtype,
                             float* dw, int64_t lddw, float* db, int M, int N, int K, int accumulate, void* stream);
 
+/* Grouped launch: up to 12 independent Linear GEMMs in ONE kernel launch, each the SUM of up to 3 terms.  The
+ * reference's decoder layers are chains of [t, 256] Linears whose outputs it adds (q = q_content + q_time + q_pos,
+ * query_decoder.py:329-339; k likewise; cross-attention q/k :355-366): launch latency, not FLOPs, bounds them, so the
+ * independent ones share a launch and the added ones share an accumulator.  `kind` selects what a term means:
+ *   0 fwd        out[rows=M, cols=N]  = act( sum_t a_t[M,k_t] . b_t[N,k_t]^T + bias_t[N] )      a = x,  b = w
+ *   1 bwd_data   out[rows=M, cols=K]  =      sum_t a_t[M,k_t] . b_t[k_t,K]                      a = dy, b = w  (k_t = N_t)
+ *   2 bwd_weight out[rows=N, cols=K] (+)=    a[k,N]^T . b[k,K];  dbias[N] += colsum(a)          a = dy, b = x  (k = M)
+ * All jobs of a call share in_dtype; out_dtype / accumulate are per job.  bf16 operands run the tcgen05 kernel (one
+ * launch when all jobs qualify), fp32 operands the exact SIMT kernel job by job. */
+typedef struct stcat_linear_term {
+    const void* a;
+    int64_t lda;
+    const void* b;
+    int64_t ldb;
+    const float* bias; /* kind 0 only; may be NULL */
+    int32_t k;         /* contraction length of this term */
+    int32_t reserved;
+} stcat_linear_term;
+typedef struct stcat_linear_job {
+    stcat_linear_term term[3];
+    int32_t nterms;
+    int32_t rows, cols;
+    int32_t relu, accumulate, out_dtype;
+    void* out;
+    int64_t ldo;
+    float* dbias;      /* kind 2 only; ACCUMULATED; may be NULL */
+} stcat_linear_job;
+STCAT_API int stcat_linear_group(int kind, int in_dtype, const stcat_linear_job* jobs, int njobs, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Residual + LayerNorm (modal_encoder.py:237-238,240-241; query_decoder.py:344-345,431-432,436-437,
  * 612-613,653-654,658-659 and the final norms :222,527).  d must be 256 (cfg.MODEL.STCAT.HIDDEN).

@@ -40,6 +40,22 @@ SIGNATURES = {
     "stcat_map2d_pool": (c_int, [_P, _P, _P, _I, _I, _I, _P]),
 }
 
+
+
+class _Term(ctypes.Structure):
+    _fields_ = [("a", c_void_p), ("lda", c_int64), ("b", c_void_p), ("ldb", c_int64), ("bias", c_void_p),
+                ("k", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class _Job(ctypes.Structure):
+    _fields_ = [("term", _Term * 3), ("nterms", ctypes.c_int32), ("rows", ctypes.c_int32), ("cols", ctypes.c_int32),
+                ("relu", ctypes.c_int32), ("accumulate", ctypes.c_int32), ("out_dtype", ctypes.c_int32),
+                ("out", c_void_p), ("ldo", c_int64), ("dbias", c_void_p)]
+
+
+SIGNATURES["stcat_linear_group"] = (c_int, [_I, _I, ctypes.POINTER(_Job), _I, _P])
+MAX_GROUP_JOBS = 12
+
 _lib = None
 
 
@@ -148,6 +164,43 @@ class CudaBackend:
         self._rc(self.lib.stcat_linear_bwd_weight(gp, ldg, gd, xp, ldx, xd, wp, ldw, self._flat(db, "db", torch.float32),
                                                   M, N, K, int(accumulate), self._stream()), "linear_bwd_weight")
         self.launches += 1 + (db is not None)
+
+    def linear_group(self, kind: int, jobs):
+        """One launch for up to 12 independent multi-term Linear GEMMs (include/stcat_b200.h, stcat_linear_group).
+        kind 0 fwd / 1 bwd_data / 2 bwd_weight; each job is a dict with ``terms`` = [(a, b, bias-or-None), ...]
+        (meaning per kind as in the header), ``out``, and optional ``relu``, ``accumulate``, ``dbias``."""
+        assert 1 <= len(jobs) <= MAX_GROUP_JOBS
+        arr = (_Job * len(jobs))()
+        in_dt = None
+        for j, job in enumerate(jobs):
+            J = arr[j]
+            terms = job["terms"]
+            assert 1 <= len(terms) <= 3
+            op, ldo, od = self._mat(job["out"], "out")
+            rows, cols = job["out"].shape
+            for t, (a, b, bias) in enumerate(terms):
+                (ap, lda, ad), (bp, ldb, bd) = self._mat(a, "a"), self._mat(b, "b")
+                assert ad == bd and (in_dt is None or in_dt == ad), "operands of a grouped launch share one dtype"
+                in_dt = ad
+                if kind == 0:
+                    k = a.shape[1]
+                    assert a.shape[0] == rows and tuple(b.shape) == (cols, k)
+                elif kind == 1:
+                    k = a.shape[1]
+                    assert a.shape[0] == rows and tuple(b.shape) == (k, cols)
+                else:
+                    k = a.shape[0]
+                    assert tuple(a.shape) == (k, rows) and tuple(b.shape) == (k, cols)
+                T = J.term[t]
+                T.a, T.lda, T.b, T.ldb, T.k = ap, lda, bp, ldb, k
+                T.bias = self._flat(bias, "bias", torch.float32) if bias is not None else None
+            J.nterms, J.rows, J.cols = len(terms), rows, cols
+            J.relu, J.accumulate, J.out_dtype = int(job.get("relu", False)), int(job.get("accumulate", False)), od
+            J.out, J.ldo = op, ldo
+            db = job.get("dbias")
+            J.dbias = self._flat(db, "dbias", torch.float32) if db is not None else None
+        self._rc(self.lib.stcat_linear_group(kind, in_dt, arr, len(jobs), self._stream()), "linear_group")
+        self.launches += 1 + (kind == 2 and any(j.get("dbias") is not None for j in jobs))
 
     # -- layernorm -----------------------------------------------------
     def layernorm_fwd(self, x, res, gamma, beta, y, y_bf16, mean, rstd, eps=1e-5):

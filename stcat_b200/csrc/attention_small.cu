@@ -15,7 +15,7 @@ namespace stcat {
 
 constexpr int SM_DH = 32;
 constexpr int SM_LMAX = 128;
-constexpr int SM_THREADS = 256;
+constexpr int SM_THREADS = 1024;  // 32 warps: the phases are shared-memory-latency bound, so occupancy is what counts
 constexpr int SM_LDV = SM_DH + 1;  // padded row of the [L][32] operand tiles
 
 // [L][33] fp32 tile <- rows (base_row .. base_row + L) of a [*, ld] matrix, columns [col0, col0 + 32); rows >= L are zero
@@ -28,53 +28,55 @@ __device__ __forceinline__ void sm_load_tile(float* dst, const T* __restrict__ s
     }
 }
 
-// C[i][j] (+)= sum_e A[i][e] * B[j][e] over the 32-wide head dim, for an Lq x Lk output held in `out` (row pitch ldo);
-// 4 x 4 register tiles, tiles strided over the CTA
+// C[i][j] = sum_e A[i][e] * B[j][e] over the 32-wide head dim for all i < LqPad, j < LkPad; 2 x 2 register tiles,
+// one (or a few) per thread
 template <typename F>
 __device__ __forceinline__ void sm_outer_32(const float* A, const float* B, int LqPad, int LkPad, F&& store) {
-    const int tq = LqPad >> 2, tk = LkPad >> 2;
+    const int tq = LqPad >> 1, tk = LkPad >> 1;
     for (int t = threadIdx.x; t < tq * tk; t += SM_THREADS) {
-        // rows i0..i0+3 (same for most of a warp: broadcast), columns jl + tk*y (consecutive lanes -> consecutive
-        // rows of B, pitch 33 words: conflict-free)
-        const int i0 = (t / tk) * 4, jl = t % tk;
-        float acc[4][4] = {};
-#pragma unroll 8
+        // rows i0, i0+1 (shared by most of a warp: broadcast), columns jl and jl + tk (consecutive lanes ->
+        // consecutive rows of B, pitch 33 words: conflict-free)
+        const int i0 = (t / tk) * 2, jl = t % tk;
+        const float* a0 = A + i0 * SM_LDV;
+        const float* b0 = B + jl * SM_LDV;
+        const float* b1 = B + (jl + tk) * SM_LDV;
+        float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
+#pragma unroll
         for (int e = 0; e < SM_DH; ++e) {
-            float a[4], b[4];
-#pragma unroll
-            for (int x = 0; x < 4; ++x) { a[x] = A[(i0 + x) * SM_LDV + e]; b[x] = B[(jl + tk * x) * SM_LDV + e]; }
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+            const float x0 = a0[e], x1 = a0[SM_LDV + e], y0 = b0[e], y1 = b1[e];
+            c00 = fmaf(x0, y0, c00); c01 = fmaf(x0, y1, c01);
+            c10 = fmaf(x1, y0, c10); c11 = fmaf(x1, y1, c11);
         }
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) store(i0 + x, jl + tk * y, acc[x][y]);
+        store(i0, jl, c00); store(i0, jl + tk, c01);
+        store(i0 + 1, jl, c10); store(i0 + 1, jl + tk, c11);
     }
 }
 
 // O[r][e] = sum_c W[r][c] * X[c][e] (TRANS = false, W row-major [R][ldw]) or sum_c W[c][r] * X[c][e] (TRANS = true);
-// R x 32 outputs in 4 x 2 register tiles; C = contraction length
+// R x 32 outputs, 1 x 2 per thread; C = contraction length
 template <bool TRANS, typename F>
 __device__ __forceinline__ void sm_apply(const float* W, int ldw, const float* X, int Rpad, int C, F&& store) {
-    const int tr = Rpad >> 2;
-    for (int t = threadIdx.x; t < tr * (SM_DH / 2); t += SM_THREADS) {
-        const int r0 = (t / (SM_DH / 2)) * 4, e0 = (t % (SM_DH / 2)) * 2;
-        float acc[4][2] = {};
-#pragma unroll 4
-        for (int c = 0; c < C; ++c) {
-            const float x0 = X[c * SM_LDV + e0], x1 = X[c * SM_LDV + e0 + 1];
-#pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                const float w = TRANS ? W[c * ldw + r0 + x] : W[(r0 + x) * ldw + c];
-                acc[x][0] = fmaf(w, x0, acc[x][0]);
-                acc[x][1] = fmaf(w, x1, acc[x][1]);
-            }
+    for (int t = threadIdx.x; t < Rpad * (SM_DH / 2); t += SM_THREADS) {
+        const int r = t / (SM_DH / 2), e0 = (t % (SM_DH / 2)) * 2;
+        const float* wp = TRANS ? W + r : W + r * ldw;
+        const int ws = TRANS ? ldw : 1;
+        const float* xp = X + e0;
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        int c = 0;
+        for (; c + 1 < C; c += 2) {  // two independent accumulator pairs
+            const float w0 = wp[c * ws], w1 = wp[(c + 1) * ws];
+            acc0 = fmaf(w0, xp[c * SM_LDV], acc0);
+            acc1 = fmaf(w0, xp[c * SM_LDV + 1], acc1);
+            acc2 = fmaf(w1, xp[(c + 1) * SM_LDV], acc2);
+            acc3 = fmaf(w1, xp[(c + 1) * SM_LDV + 1], acc3);
         }
-#pragma unroll
-        for (int x = 0; x < 4; ++x) { store(r0 + x, e0, acc[x][0]); store(r0 + x, e0 + 1, acc[x][1]); }
+        if (c < C) {
+            const float w0 = wp[c * ws];
+            acc0 = fmaf(w0, xp[c * SM_LDV], acc0);
+            acc1 = fmaf(w0, xp[c * SM_LDV + 1], acc1);
+        }
+        store(r, e0, acc0 + acc2);
+        store(r, e0 + 1, acc1 + acc3);
     }
 }
 

@@ -30,6 +30,19 @@ int gemm_tc(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t l
             int64_t ldc, int out_dtype, const float* bias, int M, int N, int K, int relu, int accumulate,
             cudaStream_t st, const GemmEpilogue* epi = nullptr);
 
+// gemm_tcgen05.cu: grouped launch
+struct TcTerm { const void* A; int64_t lda; const void* B; int64_t ldb; const float* bias; int K; };
+struct TcJob {
+    TcTerm term[3];
+    int nterms;
+    void* C; int64_t ldc; int M, N;
+    int relu, accumulate;
+    GemmEpilogue epi;
+};
+int gemm_tc_group(const TcJob* jobs, int njobs, int a_mn_major, int b_mn_major, int out_dtype, cudaStream_t st);
+int colsum_group(const void* const* dy, const int64_t* ld, float* const* db, const int* M, const int* N, int njobs, int dtype,
+                 cudaStream_t st);
+
 }  // namespace stcat
 
 using namespace stcat;
@@ -121,5 +134,75 @@ extern "C" int stcat_linear_bwd_weight(const void* dy, int64_t lddy, int dy_dtyp
         rc = gemm_simt(dy, 1, lddy, x, 1, ldx, dy_dtype, dw, lddw, STCAT_F32, nullptr, N, K, M, 0, accumulate, st);
     if (rc) return rc;
     if (db) return colsum(dy, lddy, dy_dtype, db, M, N, accumulate, st);
+    return 0;
+}
+
+extern "C" int stcat_linear_group(int kind, int in_dtype, const stcat_linear_job* jobs, int njobs, void* stream) {
+    STCAT_REQUIRE(jobs && njobs >= 1 && njobs <= 12, STCAT_EINVAL, "linear_group: njobs=%d (1..12)", njobs);
+    STCAT_REQUIRE(kind >= 0 && kind <= 2 && dtype_ok(in_dtype), STCAT_EINVAL, "linear_group: kind=%d in_dtype=%d", kind, in_dtype);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int a_mn = kind == 2, b_mn = kind != 0;
+    bool all_tc = in_dtype == STCAT_BF16;
+    for (int j = 0; j < njobs; ++j) {
+        const stcat_linear_job& J = jobs[j];
+        STCAT_REQUIRE(J.out && J.nterms >= 1 && J.nterms <= 3 && J.rows > 0 && J.cols > 0 && dtype_ok(J.out_dtype), STCAT_EINVAL,
+                      "linear_group: job %d malformed", j);
+        STCAT_REQUIRE(kind != 2 || (J.nterms == 1 && J.out_dtype == STCAT_F32), STCAT_EINVAL, "linear_group: bwd_weight jobs have one term and fp32 output");
+        STCAT_REQUIRE(J.out_dtype == jobs[0].out_dtype, STCAT_EINVAL, "linear_group: jobs of one call share out_dtype");
+        for (int t = 0; t < J.nterms; ++t) {
+            const stcat_linear_term& T = J.term[t];
+            STCAT_REQUIRE(T.a && T.b && T.k > 0, STCAT_EINVAL, "linear_group: job %d term %d malformed", j, t);
+            all_tc = all_tc && gemm_tc_supported(J.rows, J.cols, T.k, T.lda, T.ldb, J.ldo, T.a, T.b, J.out, a_mn, b_mn);
+        }
+        if (J.relu && J.accumulate) all_tc = false;
+    }
+    if (all_tc) {
+        TcJob tj[12];
+        for (int j = 0; j < njobs; ++j) {
+            const stcat_linear_job& J = jobs[j];
+            tj[j] = TcJob();
+            for (int t = 0; t < J.nterms; ++t)
+                tj[j].term[t] = TcTerm{J.term[t].a, J.term[t].lda, J.term[t].b, J.term[t].ldb, kind == 0 ? J.term[t].bias : nullptr, J.term[t].k};
+            tj[j].nterms = J.nterms;
+            tj[j].C = J.out; tj[j].ldc = J.ldo; tj[j].M = J.rows; tj[j].N = J.cols;
+            tj[j].relu = J.relu; tj[j].accumulate = J.accumulate;
+        }
+        int rc = gemm_tc_group(tj, njobs, a_mn, b_mn, jobs[0].out_dtype, st);
+        if (rc) return rc;
+    } else {
+        // job by job, term by term (exact-fp32 SIMT kernel, or shapes the tensor-core kernel does not take)
+        for (int j = 0; j < njobs; ++j) {
+            const stcat_linear_job& J = jobs[j];
+            for (int t = 0; t < J.nterms; ++t) {
+                const stcat_linear_term& T = J.term[t];
+                const int acc = J.accumulate || t > 0;
+                const int relu = (t == J.nterms - 1) ? J.relu : 0;
+                STCAT_REQUIRE(!(relu && J.nterms > 1 && J.out_dtype != STCAT_F32), STCAT_ESHAPE,
+                              "linear_group: multi-term ReLU job needs fp32 output on the unfused path");
+                int rc;
+                const float* bias = kind == 0 ? T.bias : nullptr;
+                if (in_dtype == STCAT_BF16 && gemm_tc_supported(J.rows, J.cols, T.k, T.lda, T.ldb, J.ldo, T.a, T.b, J.out, a_mn, b_mn) &&
+                    !(relu && acc))
+                    rc = gemm_tc(T.a, T.lda, a_mn, T.b, T.ldb, b_mn, J.out, J.ldo, J.out_dtype, bias, J.rows, J.cols, T.k, relu, acc, st);
+                else if (kind == 0)
+                    rc = gemm_simt(T.a, T.lda, 1, T.b, T.ldb, 1, in_dtype, J.out, J.ldo, J.out_dtype, bias, J.rows, J.cols, T.k, relu, acc, st);
+                else if (kind == 1)
+                    rc = gemm_simt(T.a, T.lda, 1, T.b, 1, T.ldb, in_dtype, J.out, J.ldo, J.out_dtype, nullptr, J.rows, J.cols, T.k, 0, acc, st);
+                else
+                    rc = gemm_simt(T.a, 1, T.lda, T.b, 1, T.ldb, in_dtype, J.out, J.ldo, STCAT_F32, nullptr, J.rows, J.cols, T.k, 0, acc, st);
+                if (rc) return rc;
+            }
+        }
+    }
+    if (kind == 2) {
+        const void* dy[12]; int64_t ld[12]; float* db[12]; int Ms[12], Ns[12];
+        int n = 0;
+        for (int j = 0; j < njobs; ++j)
+            if (jobs[j].dbias) {
+                dy[n] = jobs[j].term[0].a; ld[n] = jobs[j].term[0].lda; db[n] = jobs[j].dbias;
+                Ms[n] = jobs[j].term[0].k; Ns[n] = jobs[j].rows; ++n;
+            }
+        if (n) return colsum_group(dy, ld, db, Ms, Ns, n, in_dtype, st);
+    }
     return 0;
 }

@@ -171,6 +171,51 @@ int gemm_simt(const void* A, int64_t sam, int64_t sak, const void* B, int64_t sb
     return set_err(STCAT_EINVAL, "gemm_simt: bad dtype %d/%d", in_dtype, out_dtype);
 }
 
+// several (dy, db) pairs in one launch: blockIdx.y = pair, blockIdx.x = 32-column slab, all rows in one block
+struct ColsumGroup { const void* dy[12]; int64_t ld[12]; float* db[12]; int M[12]; int N[12]; };
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_group_kernel(const ColsumGroup g) {
+    __shared__ float red[8][33];
+    const int j = blockIdx.y;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + tx;
+    const int M = g.M[j], N = g.N[j];
+    if (blockIdx.x * 32 >= N) return;
+    const T* dy = (const T*)g.dy[j];
+    float s = 0.f;
+    if (n < N)
+        for (int r = ty; r < M; r += 8) s += to_f32<T>(dy[(int64_t)r * g.ld[j] + n]);
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][tx];
+        atomicAdd(g.db[j] + n, t);
+    }
+}
+
+int colsum(const void* dy, int64_t ld, int dtype, float* db, int M, int N, int accumulate, cudaStream_t st);
+
+int colsum_group(const void* const* dy, const int64_t* ld, float* const* db, const int* M, const int* N, int njobs, int dtype,
+                 cudaStream_t st) {
+    int maxM = 0, maxN = 0;
+    for (int j = 0; j < njobs; ++j) { maxM = M[j] > maxM ? M[j] : maxM; maxN = N[j] > maxN ? N[j] : maxN; }
+    if (maxM > 2048) {  // long column sums: the row-parallel kernel, pair by pair
+        for (int j = 0; j < njobs; ++j) {
+            int rc = colsum(dy[j], ld[j], dtype, db[j], M[j], N[j], 1, st);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    ColsumGroup g;
+    for (int j = 0; j < njobs; ++j) { g.dy[j] = dy[j]; g.ld[j] = ld[j]; g.db[j] = db[j]; g.M[j] = M[j]; g.N[j] = N[j]; }
+    dim3 grid((maxN + 31) / 32, njobs);
+    if (dtype == STCAT_F32) colsum_group_kernel<float><<<grid, 256, 0, st>>>(g);
+    else colsum_group_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(g);
+    return check_launch("colsum_group_kernel");
+}
+
 int colsum(const void* dy, int64_t ld, int dtype, float* db, int M, int N, int accumulate, cudaStream_t st) {
     if (!accumulate) {
         cudaError_t e = cudaMemsetAsync(db, 0, sizeof(float) * N, st);

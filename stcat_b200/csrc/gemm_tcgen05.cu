@@ -25,6 +25,7 @@
 // or a few tiles) uses the TMA reduce-add epilogue on a pre-zeroed fp32 output.
 #include "tc_common.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 namespace stcat {
 
@@ -51,21 +52,34 @@ template <int BN> struct Cfg {
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 };
 
-struct Params {
-    const float* bias;  // [N] or null (added by k-split 0)
-    int M, N, K;
-    int tiles_m, tiles_n, splits, kb_per_split, kb_total;
+constexpr int MAX_TERMS = 3;   // y = sum_t A_t . B_t^T: the reference adds up to three Linear outputs (query_decoder.py:329-339)
+constexpr int MAX_JOBS = 12;   // independent GEMMs served by one launch (grouped launch)
+
+// One GEMM of a launch: C[M,N] (+)= sum_t A_t(M,K_t) . B_t(N,K_t)^T (+ sum_t bias_t) with its own tensor maps.
+struct alignas(64) Job {
+    CUtensorMap tmA[MAX_TERMS];
+    CUtensorMap tmB[MAX_TERMS];
+    CUtensorMap tmC;
+    const float* bias[MAX_TERMS];  // [N] or null; all are added (by k-split 0)
+    int kb[MAX_TERMS];             // k-blocks of each term
+    int nterms;
+    int M, N;
+    int tiles_m, tiles_n, splits, kb_per_split;  // splits > 1 only with nterms == 1
+    int work0;                     // first work item (tile x split) of this job in the launch
     int relu;
-    int reduce_add;  // epilogue uses TMA reduce-add instead of store
-    const __nv_bfloat16* mask;  // optional [M, N] bf16: C is zeroed where mask <= 0 (ReLU backward), else null
+    int reduce_add;                // epilogue uses TMA reduce-add instead of store
+    const __nv_bfloat16* mask;     // optional [M, N] bf16: C is zeroed where mask <= 0 (ReLU backward), else null
     int64_t ld_mask;
-    float* colsum;              // optional [N]: accumulated (atomicAdd) with the column sums of the stored C
+    float* colsum;                 // optional [N]: accumulated (atomicAdd) with the column sums of the stored C
+};
+template <int NJ> struct GroupParams {
+    Job jobs[NJ];
+    int njobs, total;
 };
 
-template <bool A_MN, bool B_MN, bool OUT_BF16, int BN>
+template <bool A_MN, bool B_MN, bool OUT_BF16, int BN, int NJ>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const Params p) {
+gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B-swizzle atoms need 1024 B alignment
     using C = Cfg<BN>;
@@ -80,12 +94,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total = p.tiles_m * p.tiles_n * p.splits;
+    const int total = gp.total;
+    // work item -> (job, split, m_blk, n_blk); jobs are few, a linear scan of the prefix table is enough
+    auto find_job = [&](int w) {
+        int j = 0;
+        if (NJ > 1) while (j + 1 < gp.njobs && w >= gp.jobs[j + 1].work0) ++j;
+        return j;
+    };
 
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&gp.jobs[0].tmA[0])) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&gp.jobs[0].tmB[0])) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&gp.jobs[0].tmC)) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -108,30 +128,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             for (int w = blockIdx.x; w < total; w += gridDim.x) {
-                const int split = w % p.splits;
-                const int t = w / p.splits;
-                const int m_blk = t % p.tiles_m, n_blk = t / p.tiles_m;
-                const int kb0 = split * p.kb_per_split;
-                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1);
-                    const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-                    if (!A_MN) {
-                        tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM);
-                    } else {
+                const Job& J = gp.jobs[find_job(w)];
+                const int lw = w - J.work0;
+                const int split = lw % J.splits;
+                const int t = lw / J.splits;
+                const int m_blk = t % J.tiles_m, n_blk = t / J.tiles_m;
+                for (int term = 0; term < J.nterms; ++term) {
+                    const int kb0 = split * J.kb_per_split;  // splits == 1 for multi-term jobs: kb0 = 0
+                    const int kb1 = min(J.kb[term], kb0 + J.kb_per_split);
+                    const CUtensorMap* tmA = &J.tmA[term];
+                    const CUtensorMap* tmB = &J.tmB[term];
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait(empty_bar(stage), phase ^ 1);
+                        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                        mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                        if (!A_MN) {
+                            tma_load_2d(sa, tmA, full_bar(stage), kb * BK, m_blk * BM);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < BM / 64; ++j)
-                            tma_load_2d(sa + j * (BK * 128), &tmA, full_bar(stage), m_blk * BM + j * 64, kb * BK);
-                    }
-                    if (!B_MN) {
-                        tma_load_2d(sb, &tmB, full_bar(stage), kb * BK, n_blk * BN);
-                    } else {
+                            for (int j = 0; j < BM / 64; ++j)
+                                tma_load_2d(sa + j * (BK * 128), tmA, full_bar(stage), m_blk * BM + j * 64, kb * BK);
+                        }
+                        if (!B_MN) {
+                            tma_load_2d(sb, tmB, full_bar(stage), kb * BK, n_blk * BN);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j)
-                            tma_load_2d(sb + j * (BK * 128), &tmB, full_bar(stage), n_blk * BN + j * 64, kb * BK);
+                            for (int j = 0; j < BN / 64; ++j)
+                                tma_load_2d(sb + j * (BK * 128), tmB, full_bar(stage), n_blk * BN + j * 64, kb * BK);
+                        }
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -143,27 +169,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
             for (int w = blockIdx.x; w < total; w += gridDim.x) {
-                const int split = w % p.splits;
-                const int kb0 = split * p.kb_per_split;
-                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                const Job& J = gp.jobs[find_job(w)];
+                const int split = (w - J.work0) % J.splits;
                 mbar_wait(acce_bar(as), aphase ^ 1);  // epilogue has drained this accumulator stage
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(full_bar(stage), phase);
-                    tc_fence_after();
-                    const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                uint32_t acc = 0;  // the first MMA of the tile overwrites the accumulator
+                for (int term = 0; term < J.nterms; ++term) {
+                    const int kb0 = split * J.kb_per_split;
+                    const int kb1 = min(J.kb[term], kb0 + J.kb_per_split);
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // K-major: 16 bf16 = 32 B inside the 128 B swizzle row; 8-row groups 1024 B apart (SBO).
-                        // MN-major: 16 k-rows = 2 swizzle atoms of 8 rows x 128 B (SBO = 1024 B); successive
-                        //           64-element MN blocks are BK*128 B apart (LBO).
-                        const uint64_t ad = A_MN ? make_desc(sa + k * 2048, BK * 128, 1024) : make_desc(sa + k * 32, 16, 1024);
-                        const uint64_t bd = B_MN ? make_desc(sb + k * 2048, BK * 128, 1024) : make_desc(sb + k * 32, 16, 1024);
-                        umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // K-major: 16 bf16 = 32 B inside the 128 B swizzle row; 8-row groups 1024 B apart (SBO).
+                            // MN-major: 16 k-rows = 2 swizzle atoms of 8 rows x 128 B (SBO = 1024 B); successive
+                            //           64-element MN blocks are BK*128 B apart (LBO).
+                            const uint64_t ad = A_MN ? make_desc(sa + k * 2048, BK * 128, 1024) : make_desc(sa + k * 32, 16, 1024);
+                            const uint64_t bd = B_MN ? make_desc(sb + k * 2048, BK * 128, 1024) : make_desc(sb + k * 32, 16, 1024);
+                            umma_bf16(d_tmem, ad, bd, idesc, acc);
+                            acc = 1u;
+                        }
+                        umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(accf_bar(as));  // accumulator complete -> epilogue
                 if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
@@ -186,15 +217,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int as = 0;
         uint32_t aphase = 0;
         for (int w = blockIdx.x; w < total; w += gridDim.x) {
-            const int split = w % p.splits;
-            const int t = w / p.splits;
+            const Job& p = gp.jobs[find_job(w)];
+            const CUtensorMap& tmC = p.tmC;
+            const int lw = w - p.work0;
+            const int split = lw % p.splits;
+            const int t = lw / p.splits;
             const int m_blk = t % p.tiles_m, n_blk = t / p.tiles_m;
             const int n_valid = min(BN, p.N - n_blk * BN) - g * GC;  // valid columns of this group's share
             {   // stage the bias slice (zero where there is none / out of range): no per-element predicates below.
                 // Safe to overwrite: every thread of the group passed the previous tile's last bar.sync, which
                 // follows all of that tile's bias reads.
                 const int col = n_blk * BN + g * GC + gt;
-                const float bv = (p.bias != nullptr && split == 0 && col < p.N) ? __ldg(p.bias + col) : 0.f;
+                float bv = 0.f;
+                if (split == 0 && col < p.N && gt < GC)
+                    for (int term = 0; term < p.nterms; ++term)
+                        if (p.bias[term] != nullptr) bv += __ldg(p.bias[term] + col);
                 if (gt < GC) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + gt * 4), "f"(bv) : "memory");
             }
             mbar_wait(accf_bar(as), aphase);
@@ -380,92 +417,142 @@ int gemm_tc_supported(int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc
     return 1;
 }
 
-template <bool AMN, bool BMN, bool OBF, int BN>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const tc::Params& p, int grid,
-                     cudaStream_t st) {
+// one GEMM of a grouped launch as the C-ABI layer describes it (capi.cu)
+struct TcTerm { const void* A; int64_t lda; const void* B; int64_t ldb; const float* bias; int K; };
+struct TcJob {
+    TcTerm term[tc::MAX_TERMS];
+    int nterms;
+    void* C; int64_t ldc; int M, N;
+    int relu, accumulate;
+    GemmEpilogue epi;
+};
+
+template <bool AMN, bool BMN, bool OBF, int BN, int NJ>
+static int launch_tc(const tc::GroupParams<NJ>& gp, int grid, cudaStream_t st) {
     using namespace tc;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AMN, BMN, OBF, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AMN, BMN, OBF, BN, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
         if (e != cudaSuccess) return set_err((int)e, "gemm_tc: smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    gemm_tc_kernel<AMN, BMN, OBF, BN><<<grid, THREADS, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, tmC, p);
+    gemm_tc_kernel<AMN, BMN, OBF, BN, NJ><<<grid, THREADS, Cfg<BN>::SMEM_BYTES, st>>>(gp);
     return check_launch("gemm_tc_kernel");
 }
 
+// Fills one device-side Job.  `work0` is the running prefix of work items; returns <0 on error via set_err code.
 template <int BN>
-static int gemm_tc_bn(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* C,
-                      int64_t ldc, int out_dtype, const float* bias, int M, int N, int K, int relu, int accumulate,
-                      cudaStream_t st, const GemmEpilogue* epi) {
+static int fill_job(tc::Job& J, const TcJob& in, int a_mn_major, int b_mn_major, bool out_bf16, int& work, cudaStream_t st) {
     using namespace tc;
-    const bool out_bf16 = out_dtype == STCAT_BF16;
-    CUtensorMap tmA, tmB, tmC;
     int rc;
-    // A: K-major -> tensor [M rows, K cols], box {BK, BM};  MN-major -> tensor [K rows, M cols], box {64, BK}
-    rc = a_mn_major ? make_map(&tmA, A, true, K, M, lda, 64, BK) : make_map(&tmA, A, true, M, K, lda, BK, BM);
+    const int M = in.M, N = in.N;
+    memset(&J, 0, sizeof(J));
+    int kb_max = 0;
+    for (int t = 0; t < in.nterms; ++t) {
+        const TcTerm& T = in.term[t];
+        // A: K-major -> tensor [M rows, K cols], box {BK, BM};  MN-major -> tensor [K rows, M cols], box {64, BK}
+        rc = a_mn_major ? make_map(&J.tmA[t], T.A, true, T.K, M, T.lda, 64, BK) : make_map(&J.tmA[t], T.A, true, M, T.K, T.lda, BK, BM);
+        if (rc) return rc;
+        rc = b_mn_major ? make_map(&J.tmB[t], T.B, true, T.K, N, T.ldb, 64, BK) : make_map(&J.tmB[t], T.B, true, N, T.K, T.ldb, BK, BN);
+        if (rc) return rc;
+        J.bias[t] = T.bias;
+        J.kb[t] = (T.K + BK - 1) / BK;
+        kb_max = J.kb[t] > kb_max ? J.kb[t] : kb_max;
+    }
+    rc = make_map(&J.tmC, in.C, out_bf16, M, N, in.ldc, out_bf16 ? 64 : 32, BM);
     if (rc) return rc;
-    rc = b_mn_major ? make_map(&tmB, B, true, K, N, ldb, 64, BK) : make_map(&tmB, B, true, N, K, ldb, BK, BN);
-    if (rc) return rc;
-    rc = make_map(&tmC, C, out_bf16, M, N, ldc, out_bf16 ? 64 : 32, BM);
-    if (rc) return rc;
-
-    Params p;
-    p.bias = bias;
-    p.M = M; p.N = N; p.K = K;
-    p.tiles_m = (M + BM - 1) / BM;
-    p.tiles_n = (N + BN - 1) / BN;
-    p.kb_total = (K + BK - 1) / BK;
-    const int tiles = p.tiles_m * p.tiles_n;
+    J.nterms = in.nterms;
+    J.M = M; J.N = N;
+    J.tiles_m = (M + BM - 1) / BM;
+    J.tiles_n = (N + BN - 1) / BN;
+    const int tiles = J.tiles_m * J.tiles_n;
     const int sms = num_sms();
     int splits = 1;
     // Split-K only for weight gradients (A MN-major: the contraction runs over all tokens while the output is a
     // few tiles); they are accumulated into fp32 gradient buffers anyway.  Forward / data-gradient GEMMs keep a
     // fixed summation order (bit-reproducible results); their few-tile cases use the BN = 64 shape instead.
-    if (a_mn_major && !relu && !out_bf16 && tiles * 2 <= sms && p.kb_total >= 8) {
+    if (in.nterms == 1 && a_mn_major && !in.relu && !out_bf16 && tiles * 2 <= sms && kb_max >= 8) {
         splits = sms / tiles;
-        const int max_by_k = p.kb_total / 4;  // at least 4 k-blocks (256 contraction elements) per split
+        const int max_by_k = kb_max / 4;  // at least 4 k-blocks (256 contraction elements) per split
         if (splits > max_by_k) splits = max_by_k;
         if (splits < 1) splits = 1;
     }
     static const bool no_splitk = getenv("STCAT_NO_SPLITK") != nullptr;  // diagnosis: deterministic summation order
     if (no_splitk) splits = 1;
-    p.kb_per_split = (p.kb_total + splits - 1) / splits;
-    p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
-    p.relu = relu;
-    p.mask = epi ? (const __nv_bfloat16*)epi->relu_mask : nullptr;
-    p.ld_mask = epi ? epi->ld_mask : 0;
-    p.colsum = epi ? epi->colsum : nullptr;
-    if ((p.mask || p.colsum) && (a_mn_major || accumulate || N % 64 != 0))
+    J.kb_per_split = (kb_max + splits - 1) / splits;
+    J.splits = (kb_max + J.kb_per_split - 1) / J.kb_per_split;
+    J.relu = in.relu;
+    J.mask = (const __nv_bfloat16*)in.epi.relu_mask;
+    J.ld_mask = in.epi.ld_mask;
+    J.colsum = in.epi.colsum;
+    if ((J.mask || J.colsum) && (a_mn_major || in.accumulate || N % 64 != 0))
         return set_err(STCAT_ESHAPE, "gemm_tc: fused ReLU-mask / column-sum epilogue needs N %% 64 == 0, no accumulate, K-major A");
-    p.reduce_add = (accumulate || p.splits > 1) ? 1 : 0;
-    if (p.splits > 1 && !accumulate) {
-        cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st);
+    if (in.relu && in.accumulate) return set_err(STCAT_ESHAPE, "gemm_tc: relu with accumulate is not supported");
+    J.reduce_add = (in.accumulate || J.splits > 1) ? 1 : 0;
+    if (J.splits > 1 && !in.accumulate) {
+        cudaError_t e = cudaMemset2DAsync(in.C, (size_t)in.ldc * 4, 0, (size_t)N * 4, (size_t)M, st);
         if (e != cudaSuccess) return set_err((int)e, "gemm_tc memset: %s", cudaGetErrorString(e));
     }
-    if (relu && accumulate) return set_err(STCAT_ESHAPE, "gemm_tc: relu with accumulate is not supported");
-    const int total = tiles * p.splits;
-    const int grid = total < sms ? total : sms;
+    J.work0 = work;
+    work += tiles * J.splits;
+    return 0;
+}
 
+template <int BN, int NJ>
+static int gemm_tc_launch_jobs(const TcJob* jobs, int njobs, int a_mn_major, int b_mn_major, int out_dtype, cudaStream_t st) {
+    using namespace tc;
+    const bool out_bf16 = out_dtype == STCAT_BF16;
+    static thread_local GroupParams<NJ> gp;  // ~1 KB per job: kept off the stack, rebuilt per call
+    int work = 0;
+    for (int j = 0; j < njobs; ++j) {
+        int rc = fill_job<BN>(gp.jobs[j], jobs[j], a_mn_major, b_mn_major, out_bf16, work, st);
+        if (rc) return rc;
+    }
+    gp.njobs = njobs;
+    gp.total = work;
+    const int sms = num_sms();
+    const int grid = work < sms ? work : sms;
     if (!a_mn_major && !b_mn_major)
-        return out_bf16 ? launch_tc<false, false, true, BN>(tmA, tmB, tmC, p, grid, st) : launch_tc<false, false, false, BN>(tmA, tmB, tmC, p, grid, st);
+        return out_bf16 ? launch_tc<false, false, true, BN, NJ>(gp, grid, st) : launch_tc<false, false, false, BN, NJ>(gp, grid, st);
     if (!a_mn_major && b_mn_major)
-        return out_bf16 ? launch_tc<false, true, true, BN>(tmA, tmB, tmC, p, grid, st) : launch_tc<false, true, false, BN>(tmA, tmB, tmC, p, grid, st);
+        return out_bf16 ? launch_tc<false, true, true, BN, NJ>(gp, grid, st) : launch_tc<false, true, false, BN, NJ>(gp, grid, st);
     if (a_mn_major && b_mn_major)
-        return out_bf16 ? launch_tc<true, true, true, BN>(tmA, tmB, tmC, p, grid, st) : launch_tc<true, true, false, BN>(tmA, tmB, tmC, p, grid, st);
+        return out_bf16 ? launch_tc<true, true, true, BN, NJ>(gp, grid, st) : launch_tc<true, true, false, BN, NJ>(gp, grid, st);
     return set_err(STCAT_ESHAPE, "gemm_tc: A MN-major with B K-major is not instantiated");
+}
+
+// tile shape: the latency shape when the 128 x 256 tiling would leave most SMs idle and the K loops are short
+static bool pick_skinny(const TcJob* jobs, int njobs) {
+    static const int force_bn = getenv("STCAT_TC_BN") ? atoi(getenv("STCAT_TC_BN")) : 0;
+    if (force_bn) return force_bn == 64;
+    int tiles256 = 0, kb = 0;
+    for (int j = 0; j < njobs; ++j) {
+        tiles256 += ((jobs[j].M + tc::BM - 1) / tc::BM) * ((jobs[j].N + 255) / 256);
+        int k = 0;
+        for (int t = 0; t < jobs[j].nterms; ++t) k += (jobs[j].term[t].K + tc::BK - 1) / tc::BK;
+        kb = k > kb ? k : kb;
+    }
+    return tiles256 * 4 <= num_sms() && kb <= 64;
 }
 
 int gemm_tc(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* C,
             int64_t ldc, int out_dtype, const float* bias, int M, int N, int K, int relu, int accumulate,
             cudaStream_t st, const GemmEpilogue* epi) {
-    // tile shape: the latency shape when the 128 x 256 tiling would leave most SMs idle and the K loop is short
-    const int tiles256 = ((M + tc::BM - 1) / tc::BM) * ((N + 255) / 256);
-    const int kb = (K + tc::BK - 1) / tc::BK;
-    static const int force_bn = getenv("STCAT_TC_BN") ? atoi(getenv("STCAT_TC_BN")) : 0;
-    const bool skinny = force_bn ? force_bn == 64 : (tiles256 * 4 <= num_sms() && kb <= 64);
-    if (skinny) return gemm_tc_bn<64>(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, out_dtype, bias, M, N, K, relu, accumulate, st, epi);
-    return gemm_tc_bn<256>(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, out_dtype, bias, M, N, K, relu, accumulate, st, epi);
+    TcJob job;
+    job.term[0] = TcTerm{A, lda, B, ldb, bias, K};
+    job.nterms = 1;
+    job.C = C; job.ldc = ldc; job.M = M; job.N = N;
+    job.relu = relu; job.accumulate = accumulate;
+    if (epi) job.epi = *epi;
+    if (pick_skinny(&job, 1)) return gemm_tc_launch_jobs<64, 1>(&job, 1, a_mn_major, b_mn_major, out_dtype, st);
+    return gemm_tc_launch_jobs<256, 1>(&job, 1, a_mn_major, b_mn_major, out_dtype, st);
+}
+
+// Grouped launch: up to MAX_JOBS independent multi-term GEMMs sharing operand majors and output dtype.
+int gemm_tc_group(const TcJob* jobs, int njobs, int a_mn_major, int b_mn_major, int out_dtype, cudaStream_t st) {
+    if (njobs < 1 || njobs > tc::MAX_JOBS) return set_err(STCAT_EINVAL, "gemm_tc_group: njobs=%d (1..%d)", njobs, tc::MAX_JOBS);
+    if (pick_skinny(jobs, njobs)) return gemm_tc_launch_jobs<64, tc::MAX_JOBS>(jobs, njobs, a_mn_major, b_mn_major, out_dtype, st);
+    return gemm_tc_launch_jobs<256, tc::MAX_JOBS>(jobs, njobs, a_mn_major, b_mn_major, out_dtype, st);
 }
 
 }  // namespace stcat

@@ -69,14 +69,18 @@ def inverse_sigmoid(x: torch.Tensor, eps: float = 1e-3) -> torch.Tensor:
     return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
 
 
-def run_mlp(m: MLPP, x: torch.Tensor, training: bool = False) -> torch.Tensor:
-    """Linear-ReLU stack (net_utils.py:20-26)."""
+def run_mlp(m: MLPP, x: torch.Tensor, training: bool = False, x_op=None) -> torch.Tensor:
+    """Linear-ReLU stack (net_utils.py:20-26).  Hidden activations feed exactly one GEMM, so without dropout they are
+    written in the GEMM-operand dtype by the producing epilogue (no cast kernels); ``x_op`` is the caller's operand
+    copy of ``x``."""
     p = getattr(m, "dropout_p", None)
     if p is None:  # the reference's own MLP module (net_utils.py:7-19) assigned from outside
         dm = getattr(m, "dropout", 0)
         p = dm.p if isinstance(dm, nn.Dropout) else float(dm or 0)
     for i, layer in enumerate(m.layers):
-        x = ops.linear(x, layer.weight, layer.bias, relu=i < m.num_layers - 1)
+        hidden = i < m.num_layers - 1
+        x = ops.linear(x, layer.weight, layer.bias, relu=hidden, out_bf16=hidden and not (training and p),
+                       x_op=x_op if i == 0 else None)
         if training and p:
             # the reference applies dropout after EVERY layer of temp_embed / action_embed, the output
             # layer included (net_utils.py:23-25, p = 0.3 hard-wired at pipeline.py:42-47).  These are
@@ -152,38 +156,39 @@ class TransformerDecoderLayer(nn.Module):
             kc = _lin(self.ca_kcontent_proj, c.mem_op, out_bf16=True)
         return kc, kp, vv
 
-    def run(self, c: _Ctx, tgt, query_pos, query_time, query_sine, is_first: bool, mem_kv):
+    def run(self, c: _Ctx, tgt, tgt_op, query_pos, query_time, time_op, query_sine, sine_op, is_first: bool, mem_kv):
+        """``*_op`` are the (non-differentiable) GEMM-operand copies of the tensors before them: every activation is
+        cast once, by its producer where possible, not once per consuming Linear.  Intermediates that feed exactly
+        one GEMM / attention (q, k, v, qc, qs) are written in the operand dtype by the producing epilogue."""
         d, H = self.d, self.nhead
+        pos_op = ops.operand_copy(query_pos)
         # ---- temporal self attention over the t queries of each video (:329-345) ----
-        q = ops.linear_sum([(tgt, self.sa_qcontent_proj.weight, self.sa_qcontent_proj.bias),
-                            (query_time, self.sa_qtime_proj.weight, self.sa_qtime_proj.bias),
-                            (query_pos, self.sa_qpos_proj.weight, self.sa_qpos_proj.bias)])
-        k = ops.linear_sum([(tgt, self.sa_kcontent_proj.weight, self.sa_kcontent_proj.bias),
-                            (query_time, self.sa_ktime_proj.weight, self.sa_ktime_proj.bias),
-                            (query_pos, self.sa_kpos_proj.weight, self.sa_kpos_proj.bias)])
-        v = _lin(self.sa_v_proj, tgt)
-        Q = _mha_proj(self.self_attn, 0, q, out_bf16=True)
-        K = _mha_proj(self.self_attn, 1, k, out_bf16=True)
-        V = _mha_proj(self.self_attn, 2, v, out_bf16=True)
+        L = lambda p: (p.weight, p.bias)
+        q, k, v = ops.linear_group(
+            [(tgt, tgt_op), (query_time, time_op), (query_pos, pos_op)],
+            [{"terms": [(0, *L(self.sa_qcontent_proj)), (1, *L(self.sa_qtime_proj)), (2, *L(self.sa_qpos_proj))], "out_bf16": True},
+             {"terms": [(0, *L(self.sa_kcontent_proj)), (1, *L(self.sa_ktime_proj)), (2, *L(self.sa_kpos_proj))], "out_bf16": True},
+             {"terms": [(0, *L(self.sa_v_proj))], "out_bf16": True}])
+        sa = self.self_attn
+        Q, K, V = ops.linear_group(
+            [(q, None), (k, None), (v, None)],
+            [{"terms": [(i, sa.in_proj_weight, sa.in_proj_bias, (i * d, (i + 1) * d))], "out_bf16": True} for i in range(3)])
         o, _ = ops.attention(Q, K, V, c.b, H, c.t, c.t, float(d // H) ** -0.5, key_mask=c.query_mask)
         a = _lin(self.self_attn.out_proj, o)
-        tgt = ops.layer_norm(a, tgt, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        tgt, tgt_op = ops.layer_norm(a, tgt, self.norm1.weight, self.norm1.bias, self.norm1.eps, want_op=True)
         # ---- time-aligned cross attention: query of frame f sees only frame f's tokens (:350-429) ----
         kc, kp, vv = mem_kv() if callable(mem_kv) else mem_kv
-        if is_first:
-            qc = ops.linear_sum([(tgt, self.ca_qcontent_proj.weight, self.ca_qcontent_proj.bias),
-                                 (query_pos, self.ca_qpos_proj.weight, self.ca_qpos_proj.bias)])
-        else:
-            qc = _lin(self.ca_qcontent_proj, tgt)
-        qs = _lin(self.ca_qpos_sine_proj, query_sine)
+        qc_terms = [(0, *L(self.ca_qcontent_proj))] + ([(1, *L(self.ca_qpos_proj))] if is_first else [])
+        qc, qs = ops.linear_group(
+            [(tgt, tgt_op), (query_pos, pos_op), (query_sine, sine_op)],
+            [{"terms": qc_terms, "out_bf16": True}, {"terms": [(2, *L(self.ca_qpos_sine_proj))], "out_bf16": True}])
         o, _ = ops.attention(c.frames(qc), kc, vv, c.n, H, 1, c.M, float(2 * d // H) ** -0.5, key_mask=c.key_mask,
                              q2=c.frames(qs), k2=kp)
         o = _lin(self.cross_attn.out_proj, o)
-        tgt = ops.layer_norm(c.padded(o), tgt, self.norm3.weight, self.norm3.bias, self.norm3.eps)
+        tgt, tgt_op = ops.layer_norm(c.padded(o), tgt, self.norm3.weight, self.norm3.bias, self.norm3.eps, want_op=True)
         # ---- FFN (:435-437) ----
-        tgt, _ = ops.ffn_block(tgt, None, self.linear1.weight, self.linear1.bias, self.linear2.weight,
-                               self.linear2.bias, self.norm4.weight, self.norm4.bias, self.norm4.eps)
-        return tgt
+        return ops.ffn_block(tgt, tgt_op, self.linear1.weight, self.linear1.bias, self.linear2.weight,
+                             self.linear2.bias, self.norm4.weight, self.norm4.bias, self.norm4.eps)
 
 
 class TransformerDecoder(nn.Module):
@@ -202,15 +207,28 @@ class TransformerDecoder(nn.Module):
 
     def run(self, c: _Ctx, tgt, anchor, query_time, mem_kv):
         d = self.d_model
-        out = tgt
+        out, out_op = tgt, None
         inter, refs = [], [anchor]
+        time_op = ops.operand_copy(query_time)
         for li, layer in enumerate(self.layers):
             sine = anchor_sine_embed(anchor[..., : self.query_dim])  # [b*t, 512]
-            query_pos = run_mlp(self.ref_point_head, sine)
-            qsine = sine[..., :d] if li == 0 else sine[..., :d] * run_mlp(self.query_scale, out)
-            out = layer.run(c, out, query_pos, query_time, qsine, li == 0, mem_kv[li])
+            sine_op = ops.operand_copy(sine)
+            rp, qsc = self.ref_point_head.layers, self.query_scale.layers
+            if li == 0:
+                query_pos = run_mlp(self.ref_point_head, sine, x_op=sine_op)
+                qsine, qsine_op = sine[..., :d], (None if sine_op is None else sine_op[..., :d])
+            else:
+                # ref_point_head(sine) and query_scale(out) are independent two-layer MLPs: layer by layer in one launch
+                h1, h2 = ops.linear_group([(sine, sine_op), (out, out_op)],
+                                          [{"terms": [(0, rp[0].weight, rp[0].bias)], "relu": True, "out_bf16": True},
+                                           {"terms": [(1, qsc[0].weight, qsc[0].bias)], "relu": True, "out_bf16": True}])
+                query_pos, scale = ops.linear_group([(h1, None), (h2, None)],
+                                                    [{"terms": [(0, rp[1].weight, rp[1].bias)]},
+                                                     {"terms": [(1, qsc[1].weight, qsc[1].bias)]}])
+                qsine, qsine_op = sine[..., :d] * scale, None
+            out, out_op = layer.run(c, out, out_op, query_pos, query_time, time_op, qsine, qsine_op, li == 0, mem_kv[li])
             if self.bbox_embed is not None:
-                new_anchor = torch.sigmoid(run_mlp(self.bbox_embed, out) + inverse_sigmoid(anchor))
+                new_anchor = torch.sigmoid(run_mlp(self.bbox_embed, out, x_op=out_op) + inverse_sigmoid(anchor))
                 if li != self.num_layers - 1:
                     refs.append(new_anchor)
                 anchor = new_anchor.detach()
@@ -242,13 +260,16 @@ class TimeDecoderLayer(nn.Module):
         V = _mha_proj(self.cross_attn_image, 2, c.mem_op, out_bf16=True)
         return K, V
 
-    def run(self, c: _Ctx, tgt, query_pos, query_pos_frames, qpos_plus_time, mem_kv):
+    def run(self, c: _Ctx, tgt, tgt_op, query_pos, query_pos_frames, qpos_plus_time, mem_kv):
         d, H = self.d, self.nhead
         scale = float(d // H) ** -0.5
         qk = tgt + qpos_plus_time
-        Q = _mha_proj(self.self_attn, 0, qk, out_bf16=True)
-        K = _mha_proj(self.self_attn, 1, qk, out_bf16=True)
-        V = _mha_proj(self.self_attn, 2, tgt, out_bf16=True)
+        qk_op = ops.operand_copy(qk)  # one cast for the q and k projections
+        sa = self.self_attn
+        Q, K, V = ops.linear_group(
+            [(qk, qk_op), (tgt, tgt_op)],
+            [{"terms": [(0 if i < 2 else 1, sa.in_proj_weight, sa.in_proj_bias, (i * d, (i + 1) * d))], "out_bf16": True}
+             for i in range(3)])
         o, weights = ops.attention(Q, K, V, c.b, H, c.t, c.t, scale, key_mask=c.query_mask, need_pavg=True)
         a = _lin(self.self_attn.out_proj, o)
         tgt = ops.layer_norm(a, tgt, self.norm1.weight, self.norm1.bias, self.norm1.eps)
@@ -257,10 +278,10 @@ class TimeDecoderLayer(nn.Module):
         K, V = mem_kv() if callable(mem_kv) else mem_kv
         o, _ = ops.attention(Q, K, V, c.n, H, 1, c.M, scale, key_mask=c.key_mask)
         o = _lin(self.cross_attn_image.out_proj, o)
-        tgt = ops.layer_norm(c.padded(o), tgt, self.norm3.weight, self.norm3.bias, self.norm3.eps)
-        tgt, _ = ops.ffn_block(tgt, None, self.linear1.weight, self.linear1.bias, self.linear2.weight,
-                               self.linear2.bias, self.norm4.weight, self.norm4.bias, self.norm4.eps)
-        return tgt, weights
+        tgt, tgt_op = ops.layer_norm(c.padded(o), tgt, self.norm3.weight, self.norm3.bias, self.norm3.eps, want_op=True)
+        tgt, tgt_op = ops.ffn_block(tgt, tgt_op, self.linear1.weight, self.linear1.bias, self.linear2.weight,
+                                    self.linear2.bias, self.norm4.weight, self.norm4.bias, self.norm4.eps)
+        return tgt, tgt_op, weights
 
 
 class TimeDecoder(nn.Module):
@@ -272,12 +293,12 @@ class TimeDecoder(nn.Module):
         self.d_model = d
 
     def run(self, c: _Ctx, tgt, query_pos, query_time, mem_kv):
-        out = tgt
+        out, out_op = tgt, None
         inter, ws = [], []
         qpt = query_pos + query_time
         qpf = c.frames(query_pos)
         for li, layer in enumerate(self.layers):
-            out, w = layer.run(c, out, query_pos, qpf, qpt, mem_kv[li])
+            out, out_op, w = layer.run(c, out, out_op, query_pos, qpf, qpt, mem_kv[li])
             inter.append(ops.layer_norm(out, None, self.norm.weight, self.norm.bias, self.norm.eps))
             ws.append(w)
         return torch.stack(inter).view(self.num_layers, c.b, c.t, self.d_model), torch.stack(ws)

@@ -139,7 +139,7 @@ class LinearFn(Function):
     ``in_proj_weight`` of an MHA be used slice by slice without autograd slicing nodes."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, relu: bool, out_bf16: bool, r0, r1):
+    def forward(ctx, x, weight, bias, relu: bool, out_bf16: bool, r0, r1, x_op=None):
         be = get_backend()
         wd = weight.detach()
         bd = None if bias is None else bias.detach()
@@ -148,7 +148,8 @@ class LinearFn(Function):
             bd = None if bd is None else bd[r0:r1]
         N, K = wd.shape
         x2 = _rows(x.detach(), K)
-        xo = _operand(x2)
+        # x_op: the caller's GEMM-operand copy of x (made once for all consumers of x); gradients still flow to x
+        xo = _rows(x_op.detach(), K) if (x_op is not None and _precision == "bf16") else _operand(x2)
         wo = _operand(wd, True)
         M = x2.shape[0]
         odt = torch.bfloat16 if (out_bf16 and _precision == "bf16") else torch.float32
@@ -181,12 +182,26 @@ class LinearFn(Function):
             be.linear_bwd_data(dyo, _operand(wd, True), dx)
             dx = dx.view(ctx.x_shape)
         dw, db = _wgrad(be, dyo, xo, weight, bias, ctx.needs_input_grad[1], ctx.needs_input_grad[2], r0, r1)
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
-def linear(x, weight, bias=None, relu: bool = False, out_bf16: bool = False, rows=None):
+def linear(x, weight, bias=None, relu: bool = False, out_bf16: bool = False, rows=None, x_op=None):
     r0, r1 = rows if rows is not None else (None, None)
-    return LinearFn.apply(x, weight, bias, relu, out_bf16, r0, r1)
+    return LinearFn.apply(x, weight, bias, relu, out_bf16, r0, r1, x_op)
+
+
+def operand_copy(x):
+    """Non-differentiable GEMM-operand copy of ``x`` (bf16 in bf16 mode, None in fp32 mode), to be handed as
+    ``x_op`` to every Linear that consumes ``x``: one cast kernel instead of one per consumer."""
+    if _precision == "fp32":
+        return None
+    xd = x.detach()
+    if xd.dtype == torch.bfloat16:
+        return xd
+    xd = xd if xd.is_contiguous() else xd.contiguous()
+    out = torch.empty(xd.shape, dtype=torch.bfloat16, device=xd.device)
+    get_backend().cast_bf16(xd.view(-1, xd.shape[-1]), out.view(-1, xd.shape[-1]))
+    return out
 
 
 class LinearSumFn(Function):
@@ -198,6 +213,7 @@ class LinearSumFn(Function):
     def forward(ctx, out_bf16, nterms, *args):
         be = get_backend()
         xs, ws, bs = args[:nterms], args[nterms:2 * nterms], args[2 * nterms:3 * nterms]
+        x_ops = args[3 * nterms:4 * nterms]
         N, _ = ws[0].shape
         lead = xs[0].shape[:-1]
         odt = torch.bfloat16 if (out_bf16 and _precision == "bf16") else torch.float32
@@ -206,7 +222,7 @@ class LinearSumFn(Function):
         for i, (x, w, b) in enumerate(zip(xs, ws, bs)):
             K = w.shape[1]
             x2 = _rows(x.detach(), K)
-            xo = _operand(x2)
+            xo = _rows(x_ops[i].detach(), K) if (x_ops[i] is not None and _precision == "bf16") else _operand(x2)
             if y is None:
                 y = torch.empty(x2.shape[0], N, dtype=odt, device=x.device)
             be.linear_fwd(xo, _operand(w.detach(), True), None if b is None else b.detach(), y, accumulate=i > 0)
@@ -255,20 +271,159 @@ class LinearSumFn(Function):
             dxs.append(dx)
             dws.append(dw)
             dbs.append(db)
-        return (None, None, *dxs, *dws, *dbs)
+        return (None, None, *dxs, *dws, *dbs, *([None] * n))
 
 
 def linear_sum(terms, out_bf16: bool = False):
-    """terms: list of (x, weight, bias)."""
-    xs, ws, bs = zip(*terms)
-    return LinearSumFn.apply(out_bf16, len(terms), *xs, *ws, *bs)
+    """terms: list of (x, weight, bias) or (x, weight, bias, x_op)."""
+    xs, ws, bs = zip(*[t[:3] for t in terms])
+    x_ops = [t[3] if len(t) > 3 else None for t in terms]
+    return LinearSumFn.apply(out_bf16, len(terms), *xs, *ws, *bs, *x_ops)
+
+
+class LinearGroupFn(Function):
+    """Several Linear layers over shared inputs in ONE kernel launch per pass (stcat_linear_group):
+        y_j = act_j( sum_{t in job j} x_{i(t)} W_t[r0:r1]^T + b_t[r0:r1] )
+    The decoder's query-side layers are chains of [t, 256] GEMMs bounded by launch latency; grouping the independent
+    ones (q / k / v projections, query_decoder.py:329-342) and summing the added ones in one accumulator turns ~10
+    forward and ~25 backward launches per self-attention block into 2 and 6.  Backward: one grouped dgrad launch
+    (dx_i = sum over the terms that read x_i), one grouped wgrad launch, one grouped bias column-sum launch."""
+
+    @staticmethod
+    def forward(ctx, spec, *tensors):
+        be = get_backend()
+        nin, jobs = spec["nin"], spec["jobs"]
+        xs, x_ops = tensors[:nin], tensors[nin:2 * nin]
+        nt = sum(len(j["terms"]) for j in jobs)
+        ws, bs = tensors[2 * nin:2 * nin + nt], tensors[2 * nin + nt:2 * nin + 2 * nt]
+        bf = _precision == "bf16"
+        xos, M = [], None
+        for x, xo in zip(xs, x_ops):
+            K = x.shape[-1]
+            x2 = _rows(x.detach(), K)
+            M = x2.shape[0] if M is None else M
+            assert x2.shape[0] == M, "inputs of a grouped Linear share their row count"
+            xos.append(_rows(xo.detach(), K) if (xo is not None and bf) else _operand(x2))
+        outs, calls, ti = [], {}, 0
+        wops = []
+        for j in jobs:
+            terms = []
+            for (i, rows) in j["terms"]:
+                w = ws[ti].detach()
+                b = None if bs[ti] is None else bs[ti].detach()
+                if rows is not None:
+                    w = w[rows[0]:rows[1]]
+                    b = None if b is None else b[rows[0]:rows[1]]
+                wo = _operand(w, True)
+                wops.append(wo)
+                terms.append((xos[i], wo, b))
+                ti += 1
+            N = terms[0][1].shape[0]
+            odt = torch.bfloat16 if (j.get("out_bf16") and bf) else torch.float32
+            y = torch.empty(M, N, dtype=odt, device=xs[0].device)
+            outs.append(y)
+            calls.setdefault(odt, []).append(dict(terms=terms, out=y, relu=bool(j.get("relu"))))
+        for group in calls.values():
+            be.linear_group(0, group)
+        ctx.spec = spec
+        ctx.biases = bs
+        ctx.x_meta = [(x.shape, x.dtype) for x in xs]
+        ctx.save_for_backward(*xos, *ws, *[y if j.get("relu") else None for y, j in zip(outs, jobs)])
+        lead = xs[0].shape[:-1]
+        return tuple(y.view(*lead, y.shape[-1]) for y in outs)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *dys):
+        be = get_backend()
+        spec = ctx.spec
+        nin, jobs = spec["nin"], spec["jobs"]
+        nt = sum(len(j["terms"]) for j in jobs)
+        saved = ctx.saved_tensors
+        xos, ws, relu_ys = saved[:nin], saved[nin:nin + nt], saved[nin + nt:]
+        bs = ctx.biases
+        f32 = torch.float32
+        dev = xos[0].device
+        M = xos[0].shape[0]
+        # upstream gradients as GEMM operands (ReLU backward first where the job had one)
+        dyos = []
+        for jx, (j, dy) in enumerate(zip(jobs, dys)):
+            N = dy.shape[-1]
+            dy2 = _rows(dy, N)
+            if j.get("relu"):
+                dy2 = dy2.clone() if dy2.data_ptr() == dy.data_ptr() else dy2
+                be.relu_bwd(relu_ys[jx], dy2)
+            dyos.append(_operand(dy2))
+        # term table: (job index, input index, weight slice view, bias, rows)
+        table, ti = [], 0
+        for jx, j in enumerate(jobs):
+            for (i, rows) in j["terms"]:
+                table.append((jx, i, ws[ti], bs[ti], rows))
+                ti += 1
+
+        def wslice(w, rows):
+            wd = w.detach()
+            return wd if rows is None else wd[rows[0]:rows[1]]
+
+        # ---- dgrad: dx_i = sum over terms reading x_i of dy_j . W_t ----
+        dxs = [None] * nin
+        dcalls = {}
+        for i in range(nin):
+            if not ctx.needs_input_grad[1 + i]:
+                continue
+            terms = [(dyos[jx], _operand(wslice(w, rows), True), None) for (jx, ii, w, b, rows) in table if ii == i]
+            if not terms:
+                continue
+            shape, xdt = ctx.x_meta[i]
+            dx = torch.empty(M, shape[-1], dtype=xdt, device=dev)
+            dxs[i] = dx.view(shape)
+            first = True
+            while terms:  # more than three readers of one input: further launches accumulate
+                dcalls.setdefault((xdt, first), []).append(dict(terms=terms[:3], out=dx, accumulate=not first))
+                terms = terms[3:]
+                first = False
+        for (_, first), group in sorted(dcalls.items(), key=lambda kv: not kv[0][1]):
+            be.linear_group(1, group)
+        # ---- wgrad + bias column sums ----
+        dws, dbs = [None] * nt, [None] * nt
+        wjobs = []
+        for tx, (jx, i, w, b, rows) in enumerate(table):
+            if not ctx.needs_input_grad[1 + 2 * nin + tx]:
+                continue
+            want_b = b is not None and ctx.needs_input_grad[1 + 2 * nin + nt + tx]
+            if _fuse_grads and w.grad is not None and (not want_b or b.grad is not None):
+                gw = w.grad if rows is None else w.grad[rows[0]:rows[1]]
+                gb = None if not want_b else (b.grad if rows is None else b.grad[rows[0]:rows[1]])
+            else:
+                dws[tx] = torch.zeros(w.shape, dtype=f32, device=dev)
+                gw = dws[tx] if rows is None else dws[tx][rows[0]:rows[1]]
+                gb = None
+                if want_b:
+                    dbs[tx] = torch.zeros(b.shape, dtype=f32, device=dev)
+                    gb = dbs[tx] if rows is None else dbs[tx][rows[0]:rows[1]]
+            wjobs.append(dict(terms=[(dyos[jx], xos[i], None)], out=gw, accumulate=True, dbias=gb))
+        for k in range(0, len(wjobs), 12):
+            be.linear_group(2, wjobs[k:k + 12])
+        return (None, *dxs, *([None] * nin), *dws, *dbs)
+
+
+def linear_group(inputs, jobs):
+    """inputs: list of (x, x_op-or-None); jobs: list of dicts {"terms": [(input index, weight, bias, rows-or-None), ...],
+    "relu": bool, "out_bf16": bool}.  Returns one output per job."""
+    spec = {"nin": len(inputs), "jobs": [{"terms": [(t[0], t[3] if len(t) > 3 else None) for t in j["terms"]],
+                                          "relu": j.get("relu", False), "out_bf16": j.get("out_bf16", False)} for j in jobs]}
+    xs = [x for x, _ in inputs]
+    x_ops = [xo for _, xo in inputs]
+    ws = [t[1] for j in jobs for t in j["terms"]]
+    bs = [t[2] for j in jobs for t in j["terms"]]
+    return LinearGroupFn.apply(spec, *xs, *x_ops, *ws, *bs)
 
 
 class LayerNormFn(Function):
     """y = LayerNorm(x + res) over the last dim (d = 256), eps 1e-5; fp32 in / out."""
 
     @staticmethod
-    def forward(ctx, x, res, gamma, beta, eps: float):
+    def forward(ctx, x, res, gamma, beta, eps: float, want_op: bool = False):
         be = get_backend()
         d = x.shape[-1]
         x2 = _rows(x.detach().float(), d)
@@ -281,16 +436,22 @@ class LayerNormFn(Function):
         y = torch.empty(rows, d, dtype=torch.float32, device=x.device)
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
-        be.layernorm_fwd(x2, r2, gamma.detach(), beta.detach(), y, None, mean, rstd, eps)
+        y_op = torch.empty(rows, d, dtype=torch.bfloat16, device=x.device) if (want_op and _precision == "bf16") else None
+        be.layernorm_fwd(x2, r2, gamma.detach(), beta.detach(), y, y_op, mean, rstd, eps)
         ctx.save_for_backward(x2, r2, gamma, mean, rstd)
         ctx.beta = beta
         ctx.shape = x.shape
         ctx.dtypes = (x.dtype, None if res is None else res.dtype)
-        return y.view(x.shape)
+        if not want_op:
+            return y.view(x.shape)
+        if y_op is not None:
+            y_op = y_op.view(x.shape)
+            ctx.mark_non_differentiable(y_op)
+        return y.view(x.shape), y_op
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, dy):
+    def backward(ctx, dy, *_unused):
         be = get_backend()
         x2, r2, gamma, mean, rstd = ctx.saved_tensors
         d = x2.shape[1]
@@ -301,10 +462,14 @@ class LayerNormFn(Function):
         dzv = dz.view(ctx.shape)
         dx = dzv.to(ctx.dtypes[0]) if ctx.needs_input_grad[0] else None
         dr = dzv.to(ctx.dtypes[1]) if (r2 is not None and ctx.needs_input_grad[1]) else None
-        return dx, dr, dg, db, None
+        return dx, dr, dg, db, None, None
 
 
-def layer_norm(x, res, gamma, beta, eps: float = 1e-5):
+def layer_norm(x, res, gamma, beta, eps: float = 1e-5, want_op: bool = False):
+    """LayerNorm(x + res).  With ``want_op`` returns (y, y_op): y_op is the bf16 operand copy written by the same
+    kernel (None in fp32 mode) for the Linears that consume y."""
+    if want_op:
+        return LayerNormFn.apply(x, res, gamma, beta, eps, True)
     return LayerNormFn.apply(x, res, gamma, beta, eps)
 
 

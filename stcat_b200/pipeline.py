@@ -48,11 +48,12 @@ class STCATHotPath(nn.Module):
         hs, reference = outputs
         coord = torch.sigmoid(run_mlp(self.bbox_embed, hs, self.training) + inverse_sigmoid(reference)).flatten(1, 2)
         out["pred_boxes"] = coord[-1]
-        sted = run_mlp(self.temp_embed, time_hs, self.training)
+        ths_op = ops.operand_copy(time_hs)  # one operand cast for both temporal heads
+        sted = run_mlp(self.temp_embed, time_hs, self.training, x_op=ths_op)
         out["pred_sted"] = sted[-1]
         act = None
         if self.use_actioness:
-            act = run_mlp(self.action_embed, time_hs, self.training)
+            act = run_mlp(self.action_embed, time_hs, self.training, x_op=ths_op)
             out["pred_actioness"] = act[-1]
         out["_coord_all"], out["_sted_all"], out["_act_all"] = coord, sted, act  # stacked over layers (loss.py)
         if self.use_aux_loss:

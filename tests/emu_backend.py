@@ -58,6 +58,27 @@ class EmuBackend:
             _store(db, s)
         self.launches += 1
 
+    def linear_group(self, kind, jobs):
+        for job in jobs:
+            out = job["out"]
+            v = _f(out) if job.get("accumulate") else None
+            for a, b, bias in job["terms"]:
+                if kind == 0:
+                    t = _f(a) @ _f(b).t()
+                    if bias is not None:
+                        t = t + bias
+                elif kind == 1:
+                    t = _f(a) @ _f(b)
+                else:
+                    t = _f(a).t() @ _f(b)
+                v = t if v is None else v + t
+            if job.get("relu"):
+                v = v.relu()
+            _store(out, v)
+            if kind == 2 and job.get("dbias") is not None:
+                job["dbias"].add_(_f(job["terms"][0][0]).sum(0))
+        self.launches += 1
+
     # -- layernorm -----------------------------------------------------
     def layernorm_fwd(self, x, res, gamma, beta, y, y_bf16, mean, rstd, eps=1e-5):
         z = x if res is None else x + res

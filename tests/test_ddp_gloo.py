@@ -124,5 +124,5 @@ def test_flat_gradient_allreduce_world2(tmp_path):
             continue
         ref = sum(p for p in parts if p is not None)
         err = float((g - ref).abs().max())
-        assert err <= 1e-5 * float(ref.abs().max()) + 1e-7, (k, err)
+        assert err <= 1e-5 * float(ref.abs().max()) + 1e-6, (k, err)  # abs floor: gradients that are zero in exact arithmetic (key-bias of a softmax) are fp32 noise
     assert unused >= 8  # fusion.{weight,bias} + 6 x ca_qtime_proj.{weight,bias} at least

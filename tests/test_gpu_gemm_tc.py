@@ -102,6 +102,54 @@ def test_bwd_data_fused_relu_mask_and_bias_grad(be, M, N, K, odt):
     assert rel_err(db2, dx2.double().sum(0)) < 2e-5
 
 
+@pytest.mark.parametrize("dt", ["bf16", "f32"])
+@pytest.mark.parametrize("M", [64, 200, 1000])
+def test_linear_group(be, M, dt):
+    """stcat_linear_group: several multi-term Linear GEMMs in one launch, all three kinds (decoder query side:
+    q = Wqc tgt + Wqt time + Wqp pos, k likewise, v; then the packed in-projection; and their backward)."""
+    d = 256
+    cvt = (lambda t: t) if dt == "bf16" else (lambda t: t.float())
+    tol = TOL_F32 if dt == "bf16" else 2e-5
+    xs = [cvt(g(M, d, seed=10 + i)).cuda() for i in range(3)]
+    ws = [cvt(g(d, d, seed=20 + i, scale=1 / 16)).cuda() for i in range(7)]
+    bs = [torch.randn(d, generator=torch.Generator().manual_seed(30 + i)).cuda() for i in range(7)]
+    layout = [[(0, 0), (1, 1), (2, 2)], [(0, 3), (1, 4), (2, 5)], [(0, 6)]]  # (input, weight) per term
+    odt = torch.bfloat16 if dt == "bf16" else torch.float32
+    outs = [torch.full((M, d), float("nan"), device="cuda", dtype=odt) for _ in layout]
+    be.linear_group(0, [dict(terms=[(xs[i], ws[w], bs[w]) for i, w in terms], out=o, relu=(j == 2)) for j, (terms, o) in enumerate(zip(layout, outs))])
+    refs = []
+    for j, terms in enumerate(layout):
+        r = sum(xs[i].double() @ ws[w].double().t() + bs[w].double() for i, w in terms)
+        refs.append(r.relu() if j == 2 else r)
+        assert rel_err(outs[j], refs[j]) < (TOL_BF16 if dt == "bf16" else tol), j
+    # packed in-projection rows as weight slices, strided output columns
+    wp = cvt(g(3 * d, d, seed=40, scale=1 / 16)).cuda()
+    qkv = torch.zeros(M, 3 * d, device="cuda", dtype=odt)
+    be.linear_group(0, [dict(terms=[(outs[i], wp[i * d:(i + 1) * d], None)], out=qkv[:, i * d:(i + 1) * d]) for i in range(3)])
+    for i in range(3):
+        assert rel_err(qkv[:, i * d:(i + 1) * d], outs[i].double() @ wp[i * d:(i + 1) * d].double().t()) < (TOL_BF16 if dt == "bf16" else tol)
+    # bwd_data: dx_i = sum over the terms reading x_i
+    dys = [cvt(g(M, d, seed=50 + j)).cuda() for j in range(3)]
+    dx = [torch.full((M, d), float("nan"), device="cuda") for _ in range(3)]
+    jobs = []
+    for i in range(3):
+        terms = [(dys[j], ws[w], None) for j, tl in enumerate(layout) for ii, w in tl if ii == i]
+        jobs.append(dict(terms=terms, out=dx[i]))
+    be.linear_group(1, jobs)
+    for i in range(3):
+        ref = sum(dys[j].double() @ ws[w].double() for j, tl in enumerate(layout) for ii, w in tl if ii == i)
+        assert rel_err(dx[i], ref) < tol, i
+    # bwd_weight (+ bias column sums), accumulating into existing gradients
+    dw = [torch.ones(d, d, device="cuda") for _ in range(7)]
+    db = [torch.ones(d, device="cuda") for _ in range(7)]
+    jobs = [dict(terms=[(dys[j], xs[i], None)], out=dw[w], accumulate=True, dbias=db[w]) for j, tl in enumerate(layout) for i, w in tl]
+    be.linear_group(2, jobs)
+    for j, tl in enumerate(layout):
+        for i, w in tl:
+            assert rel_err(dw[w] - 1, dys[j].double().t() @ xs[i].double()) < 5e-5, w
+            assert rel_err(db[w] - 1, dys[j].double().sum(0)) < 1e-4, w
+
+
 def test_strided_operands_bf16(be):
     """column slices of the packed qkv buffer (ld = 768) and row slices of the packed in_proj weight"""
     M, d = 777, 256
