@@ -214,7 +214,7 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 def build_b200(args, device):
     from stcat_b200 import ops, synthetic
-    from stcat_b200.dp import FlatGrads
+    from stcat_b200.dp import FlatGrads, GradSync, hot_path_groups
     from stcat_b200.loss import STGLossPlan
     from stcat_b200.nested import NestedTensor
     from stcat_b200.param_spec import synthetic_params
@@ -232,7 +232,15 @@ def build_b200(args, device):
     dev = {k: v.to(device) for k, v in host.items()}
     vis_mask = inp["vis_mask"].to(device)
     text_mask = inp["text_mask"].to(device)
-    grads = FlatGrads(model)
+    # gradient ranges in backward-completion order (decoder + heads, encoder blocks 5..0, rest): each is all-reduced on
+    # a side stream as soon as it is complete, overlapping the rest of the backward pass (stcat_b200/dp.py GradSync)
+    grads = FlatGrads(model, hot_path_groups(model))
+    sync = GradSync(grads, device)
+    sync.prepare(model)
+    if sync.active:
+        from stcat_b200.decoder import _side_streams
+
+        sync.extra_streams = _side_streams(device)
     ops.set_grad_fusion(True)  # wgrad kernels accumulate straight into the flat buffer (no per-parameter adds)
 
     def fwd_bwd(vis, pos, txt):
@@ -241,10 +249,14 @@ def build_b200(args, device):
         txt.grad = None
         out = model(NestedTensor(vis, vis_mask, [w["T"]]), pos, (text_mask, txt, None))
         total, _ = plan(out)
+        sync.begin_step()
+        sync.attach(out)
         total.backward()
+        sync.finish()  # sum over ranks; the 1/world factor folds into the optimizer's lr / clip step
         return total
 
-    return {"model": model, "cfg": cfg, "host": host, "dev": dev, "grads": grads, "fwd_bwd": fwd_bwd, "ops": ops, "w": w}
+    return {"model": model, "cfg": cfg, "host": host, "dev": dev, "grads": grads, "fwd_bwd": fwd_bwd, "ops": ops, "w": w,
+            "sync": sync}
 
 
 def kernel_breakdown(ctx, device):
@@ -365,10 +377,8 @@ def run_b200_arm(args):
     loss_out = torch.zeros((), device=device)
 
     def step_eager():
-        total = ctx["fwd_bwd"](vis, pos, txt)
+        total = ctx["fwd_bwd"](vis, pos, txt)  # includes the bucketed gradient all-reduce for world > 1
         loss_out.copy_(total.detach())
-        if world > 1:
-            dist.all_reduce(grads.buf)  # sum; the 1/world factor folds into the optimizer's lr/clip step
 
     graph = None
     launches_per_step = None
@@ -389,21 +399,24 @@ def run_b200_arm(args):
                 step_eager()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize(device)
-            with torch.cuda.graph(graph):
+            # thread_local: the NCCL watchdog thread polls events while the collectives are being captured
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 total = ctx["fwd_bwd"](vis, pos, txt)
                 loss_out.copy_(total.detach())
             torch.cuda.synchronize(device)
         except Exception as e:  # capture is an optimisation of launch overhead, not of the math
             if rank == 0:
+                import traceback
+
                 print(f"[bench] CUDA-graph capture unavailable ({type(e).__name__}: {e}); running eager", file=sys.stderr)
+                if os.environ.get("STCAT_BENCH_DEBUG"):
+                    traceback.print_exc()
             graph = None
             torch.cuda.synchronize(device)
 
     def step():
         if graph is not None:
-            graph.replay()
-            if world > 1:
-                dist.all_reduce(grads.buf)
+            graph.replay()  # the NCCL all-reduces were captured on their side stream with the rest of the step
         else:
             step_eager()
 
@@ -480,6 +493,7 @@ def run_b200_arm(args):
                 f.write(f"| `{e.key[:100]}` | {e.count / 3:.1f} | {e.device_time_total / 3:.1f} | {100 * e.device_time_total / tot:.1f}% |\n")
 
     line = None
+    ctx["sync"].active = False  # what follows runs on rank 0 alone: no collectives in it
     if rank == 0:
         peaks = {}
         pk = os.path.join(ROOT, "MEASURED_PEAKS.json")

@@ -89,12 +89,12 @@ class TransformerEncoderLayer(nn.Module):
         self.nhead = nhead
         self.dropout_p = dropout
 
-    def run(self, x, x_op, pos, key_mask, B: int, L: int):
+    def run(self, x, x_op, pos, key_mask, B: int, L: int, pos_cls=None):
         """x, pos: [B*L, d] batch-major rows.  Returns (y, y_op)."""
         a = self.self_attn
         x, x_op = ops.self_attn_block(x, x_op, pos, key_mask, a.in_proj_weight, a.in_proj_bias, a.out_proj.weight,
                                       a.out_proj.bias, self.norm1.weight, self.norm1.bias, B, L, self.nhead,
-                                      self.norm1.eps)
+                                      self.norm1.eps, pos_cls=pos_cls)
         return ops.ffn_block(x, x_op, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias,
                              self.norm2.weight, self.norm2.bias, self.norm2.eps)
 
@@ -117,8 +117,9 @@ class SpatialTemporalEncoder(nn.Module):
         self.num_layers = num_layers
         self.d_model = d
 
-    def run(self, X, POS, key_mask, n: int, S_len: int, durations):
-        """X, POS: [n*S, d] frame-major (row 0 of every frame = CLS slot).  Returns (X, video_src [b, d])."""
+    def run(self, X, POS, key_mask, n: int, S_len: int, durations, pos_cls=None):
+        """X, POS: [n*S, d] frame-major (row 0 of every frame = CLS slot).  Returns (X, video_src [b, d]).
+        ``pos_cls``: see ops.self_attn_block (POS is then a constant whose CLS rows equal this parameter)."""
         d = self.d_model
         idx = batch_indices(durations, X.device)
         b, t = idx["b"], idx["t"]
@@ -130,8 +131,13 @@ class SpatialTemporalEncoder(nn.Module):
         temp_pos = temp_pos if b == 1 else temp_pos.repeat(b, 1)
         temp_pos = temp_pos.contiguous()
         X_op = None
-        for sp, tp in zip(self.spatial_layers, self.temporal_layers):
-            X, X_op = sp.run(X, X_op, POS, key_mask, n, S_len)
+        # optional observer of every block's input (dp.GradSync hangs its bucketed all-reduce on their gradients);
+        # nothing is stored here: holding these tensors would keep the step's autograd graph alive
+        on_input = getattr(self, "layer_input_callback", None)
+        for li, (sp, tp) in enumerate(zip(self.spatial_layers, self.temporal_layers)):
+            if on_input is not None:
+                on_input(li, X)
+            X, X_op = sp.run(X, X_op, POS, key_mask, n, S_len, pos_cls=pos_cls)
             X3 = X.view(n, S_len, d)
             cls = X3[:, 0, :]
             if idx["identity"]:
@@ -189,12 +195,17 @@ class CrossModalEncoder(nn.Module):
             x_t = x_t.index_select(0, idx["f2v"])
             m_t = text_mask.index_select(0, idx["f2v"])
         X = torch.cat([enc.frame_cls.weight.expand(n, 1, d), x_v, x_t], 1).reshape(n * S_len, d)
-        POS = torch.cat([enc.local_pos_embed.weight.expand(n, 1, d), p_v, p_v.new_zeros(n, L, d)], 1).reshape(n * S_len, d)
+        # the positional stream is constant except its CLS row (local_pos_embed, a parameter): when vis_pos needs no
+        # gradient (it is the backbone's sine embedding) the big tensor is built detached and the parameter's gradient
+        # is taken from the CLS rows directly (ops.self_attn_block, pos_cls)
+        pos_cls = None if (vis_pos.requires_grad and torch.is_grad_enabled()) else enc.local_pos_embed.weight
+        lpe = enc.local_pos_embed.weight if pos_cls is None else enc.local_pos_embed.weight.detach()
+        POS = torch.cat([lpe.expand(n, 1, d), p_v, p_v.new_zeros(n, L, d)], 1).reshape(n * S_len, d)
         mask = torch.cat([vis_mask.flatten(1), m_t], 1)  # [n, HW+L] bool (returned)
         key_mask = torch.cat([mask.new_zeros(n, 1), mask], 1).to(torch.uint8).contiguous()  # [n, S]
         X = X.float()
         POS = POS.float()
-        X, video_src = enc.run(X, POS, key_mask, n, S_len, durations)
+        X, video_src = enc.run(X, POS, key_mask, n, S_len, durations, pos_cls=pos_cls)
         X3 = X.view(n, S_len, d)
         return {
             "encoded_memory": X3[:, 1:, :].transpose(0, 1),  # [HW+L, n, d] (view of the frame-major stream)

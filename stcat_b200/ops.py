@@ -624,8 +624,9 @@ class SelfAttnBlockFn(Function):
     """
 
     @staticmethod
-    def forward(ctx, x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps):
+    def forward(ctx, x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps, pos_cls=None):
         be = get_backend()
+        ctx.has_pos_cls = pos_cls is not None
         R, d = x.shape
         assert R == B * L and x.is_contiguous() and pos.shape == x.shape
         od = _opdtype()
@@ -644,8 +645,9 @@ class SelfAttnBlockFn(Function):
         wo = _operand(w_out.detach(), True)
         bi = b_in.detach()
         qkv = _new(R, 3 * d, od, x)
-        be.linear_fwd(qk_in, wi[: 2 * d], bi[: 2 * d], qkv[:, : 2 * d])
-        be.linear_fwd(xo, wi[2 * d:], bi[2 * d:], qkv[:, 2 * d:])
+        # q, k from x + pos (one N = 512 GEMM) and v from x: two jobs of one grouped launch
+        be.linear_group(0, [dict(terms=[(qk_in, wi[: 2 * d], bi[: 2 * d])], out=qkv[:, : 2 * d]),
+                            dict(terms=[(xo, wi[2 * d:], bi[2 * d:])], out=qkv[:, 2 * d:])])
         o = _new(R, d, od, x)
         lse = torch.empty(B, H, L, dtype=torch.float32, device=x.device)
         scale = float(d // H) ** -0.5
@@ -690,24 +692,33 @@ class SelfAttnBlockFn(Function):
         be.attention_bwd(qkv[:, :d], None, qkv[:, d:2 * d], None, qkv[:, 2 * d:], d_o, key_mask, lse, None, delta,
                          dqkv[:, :d], None, dqkv[:, d:2 * d], None, dqkv[:, 2 * d:], B, H, L, L, scale, o=o)
         if _fuse_grads and w_in.grad is not None and b_in.grad is not None:
-            be.linear_bwd_weight(dqkv[:, : 2 * d], qk_in, w_in.grad[: 2 * d], b_in.grad[: 2 * d], accumulate=True)
-            be.linear_bwd_weight(dqkv[:, 2 * d:], xo, w_in.grad[2 * d:], b_in.grad[2 * d:], accumulate=True)
+            gwi, gbi = w_in.grad, b_in.grad
             dwi = dbi = None
         else:
-            dwi = _new(3 * d, d, f32, dy)
-            dbi = torch.empty(3 * d, dtype=f32, device=dy.device)
-            be.linear_bwd_weight(dqkv[:, : 2 * d], qk_in, dwi[: 2 * d], dbi[: 2 * d])
-            be.linear_bwd_weight(dqkv[:, 2 * d:], xo, dwi[2 * d:], dbi[2 * d:])
+            gwi = dwi = torch.zeros(3 * d, d, dtype=f32, device=dy.device)
+            gbi = dbi = torch.zeros(3 * d, dtype=f32, device=dy.device)
+        be.linear_group(2, [dict(terms=[(dqkv[:, : 2 * d], qk_in, None)], out=gwi[: 2 * d], accumulate=True, dbias=gbi[: 2 * d]),
+                            dict(terms=[(dqkv[:, 2 * d:], xo, None)], out=gwi[2 * d:], accumulate=True, dbias=gbi[2 * d:])])
         need_pos = ctx.needs_input_grad[2]
         dpos = None
         if need_pos:
             dpos = _new(R, d, f32, dy)
             be.linear_bwd_data(dqkv[:, : 2 * d], wi[: 2 * d], dpos)
             be.add(dz, dpos, dz, None)
+            be.linear_bwd_data(dqkv[:, 2 * d:], wi[2 * d:], dz, accumulate=True)
         else:
-            be.linear_bwd_data(dqkv[:, : 2 * d], wi[: 2 * d], dz, accumulate=True)
-        be.linear_bwd_data(dqkv[:, 2 * d:], wi[2 * d:], dz, accumulate=True)
-        return dz, None, dpos, None, dwi, dbi, dwo, dbo, dg, dbt, None, None, None, None
+            # dz += dqk Wqk + dv Wv: one two-term accumulating job
+            be.linear_group(1, [dict(terms=[(dqkv[:, : 2 * d], wi[: 2 * d], None), (dqkv[:, 2 * d:], wi[2 * d:], None)],
+                                     out=dz, accumulate=True)])
+        dpc = None
+        if ctx.has_pos_cls and ctx.needs_input_grad[14]:
+            # pos is constant except its row 0 of every sequence, which is the learned token `pos_cls` ([1, d]):
+            # d pos_cls = (sum over sequences of dq,dk at row 0) . Wqk -- a [1, 512] x [512, 256] product instead of a
+            # full-size dpos GEMM, add and gradient accumulation per layer
+            srow = dqkv.view(B, L, 3 * d)[:, 0, : 2 * d].float().sum(0, keepdim=True)
+            dpc = torch.empty(1, d, dtype=f32, device=dy.device)
+            be.linear_bwd_data(srow, w_in.detach()[: 2 * d], dpc)
+        return dz, None, dpos, None, dwi, dbi, dwo, dbo, dg, dbt, None, None, None, None, dpc
 
 
 class FFNBlockFn(Function):
@@ -773,8 +784,10 @@ class FFNBlockFn(Function):
         return dz, None, dw1, db1, dw2, db2, dg, dbt, None
 
 
-def self_attn_block(x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps=1e-5):
-    return SelfAttnBlockFn.apply(x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps)
+def self_attn_block(x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps=1e-5, pos_cls=None):
+    """``pos_cls`` ([1, d], optional): the parameter that row 0 of every sequence of ``pos`` was copied from; when
+    given, ``pos`` itself is treated as a constant and the gradient goes to ``pos_cls`` directly."""
+    return SelfAttnBlockFn.apply(x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps, pos_cls)
 
 
 def ffn_block(x, x_op, w1, b1, w2, b2, gamma, beta, eps=1e-5):

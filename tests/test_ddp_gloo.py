@@ -27,11 +27,11 @@ def _free_port():
     return p
 
 
-def _clip_grads(rank_seed, fused_flat):
+def _clip_grads(rank_seed, fused_flat, overlapped=False):
     from helpers import cfg_for
     from emu_backend import EmuBackend
     from stcat_b200 import ops, synthetic
-    from stcat_b200.dp import FlatGrads
+    from stcat_b200.dp import FlatGrads, GradSync, hot_path_groups
     from stcat_b200.loss import STGLossPlan
     from stcat_b200.nested import NestedTensor
     from stcat_b200.param_spec import synthetic_params
@@ -45,13 +45,26 @@ def _clip_grads(rank_seed, fused_flat):
     inp = synthetic.make_inputs([T], 3, 3, 4, seed=rank_seed)  # rank-seeded clip (bench.py: seed = 42 + rank)
     tg = synthetic.make_targets([T], seed=rank_seed)
     plan = STGLossPlan(cfg, tg["boxes"], tg["actioness"], [T], "cpu")
-    grads = FlatGrads(model) if fused_flat else None
+    grads = FlatGrads(model, hot_path_groups(model)) if fused_flat else None
+    sync = GradSync(grads) if overlapped else None
+    if sync is not None:
+        sync.prepare(model)
     ops.set_grad_fusion(fused_flat)
     try:
         vis = inp["vis_features"].clone().requires_grad_(True)
         out = model(NestedTensor(vis, inp["vis_mask"], [T]), inp["vis_pos"], (inp["text_mask"], inp["text_memory"], None))
         total, _ = plan(out)
+        if sync is not None:
+            # bucketed all-reduce from autograd hooks DURING backward (bench.py's mode): a range reduced before its
+            # gradients were complete would show up as a mismatch against the single-process sums below
+            assert sync.active
+            sync.begin_step()
+            sync.attach(out)
         total.backward()
+        if sync is not None:
+            order = list(sync.done)
+            sync.finish()
+            assert "decoder" in order and "enc0" in order, order  # the hooks fired (not just finish())
     finally:
         ops.set_grad_fusion(False)
     return model, grads, float(total.detach())
@@ -65,16 +78,21 @@ def _worker(rank, world, port, outdir):
     torch.set_num_threads(1)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        model, grads, loss = _clip_grads(42 + rank, fused_flat=True)
-        local = grads.buf.clone()
-        grads.all_reduce()
+        # (a) one all-reduce of the whole flat buffer after backward
+        model_a, grads_a, loss_a = _clip_grads(42 + rank, fused_flat=True)
+        local = grads_a.buf.clone()
+        grads_a.all_reduce()
+        gathered = [torch.zeros_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        assert torch.equal(grads_a.buf, sum(gathered))
+        # (b) bucketed all-reduce overlapped with backward: same numbers
+        model, grads, loss = _clip_grads(42 + rank, fused_flat=True, overlapped=True)
+        assert loss == loss_a
+        assert torch.allclose(grads.buf, grads_a.buf, rtol=1e-6, atol=1e-7)
+        assert set(grads.ranges) >= {"decoder", "enc0", "enc5", "rest"}
         # every .grad is still a view of the reduced buffer
         for p in grads.params:
             assert p.grad.untyped_storage().data_ptr() == grads.buf.untyped_storage().data_ptr()
-        gathered = [torch.zeros_like(local) for _ in range(world)]
-        dist.all_gather(gathered, local)
-        expect = sum(gathered)
-        assert torch.allclose(grads.buf, expect, rtol=0, atol=0)
         # max-over-ranks timing idiom of bench.py works over gloo too
         t = torch.tensor([float(rank + 1)], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
