@@ -472,7 +472,7 @@ def run_b200_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * args.steps / (float(t.item()) * 1e-3)
 
-    if args.profile and rank == 0:
+    if args.profile and rank == 0 and world == 1:  # (the captured step holds collectives: never replay it on one rank alone)
         from torch.profiler import profile, ProfilerActivity
 
         torch.cuda.synchronize(device)

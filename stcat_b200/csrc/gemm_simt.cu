@@ -171,6 +171,40 @@ int gemm_simt(const void* A, int64_t sam, int64_t sak, const void* B, int64_t sb
     return set_err(STCAT_EINVAL, "gemm_simt: bad dtype %d/%d", in_dtype, out_dtype);
 }
 
+// bf16 column sums at HBM speed: a warp reads whole rows (16 B = 8 columns per lane, 256 columns per pass), a block
+// of 8 warps walks 8 row streams, partial sums meet in shared memory, one atomicAdd per column per block.
+__global__ void __launch_bounds__(256) colsum_bf16_wide_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld,
+                                                               float* __restrict__ db, int M, int N, int rows_per_block) {
+    __shared__ float red[8][256 + 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 256 + lane * 8;  // this lane's 8 columns
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(M, r0 + rows_per_block);
+    float acc[8] = {};
+    if (c0 < N) {  // N % 8 == 0 is checked by the host
+        for (int r = r0 + warp; r < r1; r += 8) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(dy + (int64_t)r * ld + c0));
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                acc[2 * e] += __uint_as_float(w[e] << 16);
+                acc[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[warp][lane * 8 + e] = acc[e];
+    __syncthreads();
+    const int c = threadIdx.x;  // 256 threads == 256 columns of this slab
+    const int gc = blockIdx.x * 256 + c;
+    if (gc < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][c];
+        atomicAdd(db + gc, t);
+    }
+}
+
 // several (dy, db) pairs in one launch: blockIdx.y = pair, blockIdx.x = 32-column slab, all rows in one block
 struct ColsumGroup { const void* dy[12]; int64_t ld[12]; float* db[12]; int M[12]; int N[12]; };
 template <typename T>
@@ -220,6 +254,14 @@ int colsum(const void* dy, int64_t ld, int dtype, float* db, int M, int N, int a
     if (!accumulate) {
         cudaError_t e = cudaMemsetAsync(db, 0, sizeof(float) * N, st);
         if (e != cudaSuccess) return set_err((int)e, "colsum memset: %s", cudaGetErrorString(e));
+    }
+    if (dtype == STCAT_BF16 && N % 8 == 0 && ld % 8 == 0 && ((uintptr_t)dy & 15) == 0 && M >= 512) {
+        // enough blocks to fill the machine, at least 32 rows each
+        int rpb = (int)(((int64_t)M * ((N + 255) / 256) + num_sms() * 4 - 1) / (num_sms() * 4));
+        rpb = rpb < 32 ? 32 : rpb;
+        dim3 g((N + 255) / 256, (M + rpb - 1) / rpb);
+        colsum_bf16_wide_kernel<<<g, 256, 0, st>>>((const __nv_bfloat16*)dy, ld, db, M, N, rpb);
+        return check_launch("colsum_bf16_wide_kernel");
     }
     int rows_per_block = 512;
     dim3 grid((N + 31) / 32, (M + rows_per_block - 1) / rows_per_block);

@@ -224,6 +224,11 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
             const int t = lw / p.splits;
             const int m_blk = t % p.tiles_m, n_blk = t / p.tiles_m;
             const int n_valid = min(BN, p.N - n_blk * BN) - g * GC;  // valid columns of this group's share
+            // job fields used per chunk, read once per tile (they live in the constant bank)
+            const int job_relu = p.relu, job_reduce = p.reduce_add, job_N = p.N, job_M = p.M;
+            const __nv_bfloat16* const job_mask = p.mask;
+            const int64_t job_ld_mask = p.ld_mask;
+            float* const job_colsum = p.colsum;
             {   // stage the bias slice (zero where there is none / out of range): no per-element predicates below.
                 // Safe to overwrite: every thread of the group passed the previous tile's last bar.sync, which
                 // follows all of that tile's bias reads.
@@ -252,11 +257,11 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
                 for (int h = 0; h < CHUNK_COLS / 32; ++h)
                     tmem_ld32(t_row + c * CHUNK_COLS + h * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[h * 32]));
                 uint4 mk[CHUNK_COLS / 8];  // this row's slice of the ReLU mask (bf16), in flight with the TMEM loads
-                if (p.mask) {
+                if (job_mask) {
                     const int gr = m_blk * BM + row;
-                    const uint4* mp = reinterpret_cast<const uint4*>(p.mask + (int64_t)gr * p.ld_mask + n_blk * BN + g * GC + c * CHUNK_COLS);
+                    const uint4* mp = reinterpret_cast<const uint4*>(job_mask + (int64_t)gr * job_ld_mask + n_blk * BN + g * GC + c * CHUNK_COLS);
 #pragma unroll
-                    for (int j = 0; j < CHUNK_COLS / 8; ++j) mk[j] = gr < p.M ? __ldg(mp + j) : make_uint4(0, 0, 0, 0);
+                    for (int j = 0; j < CHUNK_COLS / 8; ++j) mk[j] = gr < job_M ? __ldg(mp + j) : make_uint4(0, 0, 0, 0);
                 }
                 // the staging tile must have been read by the previous TMA store of this group
                 if (gt == 0) tma_wait_read<0>();
@@ -275,11 +280,11 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(sb + j * 16));
                     float x0 = __uint_as_float(r[4 * j + 0]) + b0, x1 = __uint_as_float(r[4 * j + 1]) + b1;
                     float x2 = __uint_as_float(r[4 * j + 2]) + b2, x3 = __uint_as_float(r[4 * j + 3]) + b3;
-                    if (p.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+                    if (job_relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
                     r[4 * j + 0] = __float_as_uint(x0); r[4 * j + 1] = __float_as_uint(x1);
                     r[4 * j + 2] = __float_as_uint(x2); r[4 * j + 3] = __float_as_uint(x3);
                 }
-                if (p.mask) {  // y > 0 for a bf16 y  <=>  its bits, read as int16, are > 0
+                if (job_mask) {  // y > 0 for a bf16 y  <=>  its bits, read as int16, are > 0
 #pragma unroll
                     for (int j = 0; j < CHUNK_COLS / 8; ++j) {
                         const uint32_t w4[4] = {mk[j].x, mk[j].y, mk[j].z, mk[j].w};
@@ -313,11 +318,11 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 const int c0 = n_blk * BN + g * GC + c * CHUNK_COLS;
                 if (gt == 0) {
-                    if (p.reduce_add) tma_reduce_add_2d(&tmC, sbuf_base, c0, m_blk * BM);
+                    if (job_reduce) tma_reduce_add_2d(&tmC, sbuf_base, c0, m_blk * BM);
                     else tma_store_2d(&tmC, sbuf_base, c0, m_blk * BM);
                     tma_commit();
                 }
-                if (p.colsum) {
+                if (job_colsum) {
                     // column sums of the staged (rounded) tile: 128 threads = CHUNK_COLS columns x (128 / CHUNK_COLS)
                     // row slabs; rows past M hold zeros (TMA zero-fills A).  The next chunk overwrites the staging
                     // tile only after the group's next bar.sync, which this thread reaches after its reads.
@@ -336,7 +341,7 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
                             sum += fv;
                         }
                     }
-                    if (c0 + cc < p.N) atomicAdd(p.colsum + c0 + cc, sum);
+                    if (c0 + cc < job_N) atomicAdd(job_colsum + c0 + cc, sum);
                 }
             }
             if (!released) release_acc();  // this group's half lies entirely outside N
