@@ -303,10 +303,78 @@ def kernel_breakdown(ctx, device):
     return {"step_ms_instrumented": total, "calls": {k: {"n": v[0], "ms": round(v[1], 4)} for k, v in agg.items()}}
 
 
+def _graph_time_ms(fn, iters, device):
+    """Device time per call of fn(i): `iters` calls captured into one CUDA graph, replayed, timed with CUDA events on the
+    replay stream (no host launch overhead inside the timed region)."""
+    torch.cuda.synchronize(device)
+    side = torch.cuda.Stream(device)
+    side.wait_stream(torch.cuda.current_stream())
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr, stream=side):
+        for i in range(iters):
+            fn(i)
+    gr.replay()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    gr.replay()
+    e1.record()
+    torch.cuda.synchronize(device)
+    return e0.elapsed_time(e1) / iters
+
+
+def encoder_attention_block(ctx, device, peaks):
+    """The BASELINE metric's second half: the spatial encoder's attention block (q = k = x + pos add, packed QK / V
+    in-projection, per-frame softmax(QK^T)V over S tokens, out-projection) forward at the step's shape, timed alone
+    from a CUDA graph; algorithmic FLOPs 8 N_s d^2 + 4 T S^2 d (no padding FLOPs), against the measured bf16 peak."""
+    be = ctx["ops"].get_backend()
+    w = ctx["w"]
+    T, S = w["T"], 1 + w["H"] * w["W"] + w["L"]
+    R, d, H = T * S, 256, 8
+    bf = torch.bfloat16
+    nbuf = 3
+    x = [torch.randn(R, d, device=device) for _ in range(nbuf)]
+    pos = torch.randn(R, d, device=device)
+    xo = [t.to(bf) for t in x]
+    wi = (torch.randn(3 * d, d, device=device) / 16).to(bf)
+    wo = (torch.randn(d, d, device=device) / 16).to(bf)
+    bi, bo = torch.zeros(3 * d, device=device), torch.zeros(d, device=device)
+    qk_in = torch.empty(R, d, device=device, dtype=bf)
+    qkv = torch.empty(R, 3 * d, device=device, dtype=bf)
+    o = torch.empty(R, d, device=device, dtype=bf)
+    a = torch.empty(R, d, device=device)
+    lse = torch.empty(T, H, S, device=device)
+    scale = 32 ** -0.5
+
+    def core(i):
+        be.attention_fwd(qkv[:, :d], None, qkv[:, d:2 * d], None, qkv[:, 2 * d:], o, None, lse, None, T, H, S, S, scale)
+
+    def block(i):
+        be.add(x[i % nbuf], pos, None, qk_in)
+        be.linear_group(0, [dict(terms=[(qk_in, wi[: 2 * d], bi[: 2 * d])], out=qkv[:, : 2 * d]),
+                            dict(terms=[(xo[i % nbuf], wi[2 * d:], bi[2 * d:])], out=qkv[:, 2 * d:])])
+        core(i)
+        be.linear_fwd(o, wo, bo, a)
+
+    for i in range(2):
+        block(i)
+    ms_block = _graph_time_ms(block, 12, device)
+    ms_core = _graph_time_ms(core, 12, device)
+    fl_block = 8.0 * R * d * d + 4.0 * T * S * S * d
+    fl_core = 4.0 * T * S * S * d
+    peak = peaks.get("bf16_tflops", 1590.0)
+    return {"us_block": ms_block * 1e3, "us_core": ms_core * 1e3, "tflops_block": fl_block / ms_block / 1e9,
+            "tflops_core": fl_core / ms_core / 1e9, "frac_of_bf16_peak_block": fl_block / ms_block / 1e9 / peak,
+            "frac_of_bf16_peak_core": fl_core / ms_core / 1e9 / peak, "peak": peak,
+            "shape": {"frames": T, "tokens_per_frame": S, "heads": H, "head_dim": 32},
+            "note": "forward, per layer; block = x+pos add, QK/V in-projection (one grouped launch), attention core, out-projection"}
+
+
 def dominant_kernel_roofline(ctx, device, peaks):
-    """The dominant kernel of the step is the FFN GEMM of the spatial encoder layers (SURVEY.md 2.B:
-    FFN = 28.6 of 38.7 GF per layer).  Time it alone (CUDA events, 20 launches over rotating buffers
-    larger than L2) at the step's exact shape: linear1 fwd, M = T*S rows, N = 2048, K = 256."""
+    """The dominant kernel of the step is the tcgen05 GEMM (45 % of the step's kernel time, profiles/); its largest
+    launch is the FFN linear1 of the spatial encoder layers (FFN = 28.6 of 38.7 GF per layer).  Time it
+    alone at the step's exact shape (M = T*S rows, N = 2048, K = 256, bias + ReLU, bf16 out): 20 launches over
+    rotating buffers larger than L2, replayed from a CUDA graph, CUDA events on the replay stream."""
     be = ctx["ops"].get_backend()
     w = ctx["w"]
     M = w["T"] * (1 + w["H"] * w["W"] + w["L"])
@@ -320,15 +388,7 @@ def dominant_kernel_roofline(ctx, device, peaks):
     bias = torch.zeros(N, device=device)
     for i in range(3):
         be.linear_fwd(xs[i % nbuf], wt, bias, ys[i % nbuf], relu=True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(device)
-    iters = 20
-    e0.record()
-    for i in range(iters):
-        be.linear_fwd(xs[i % nbuf], wt, bias, ys[i % nbuf], relu=True)
-    e1.record()
-    torch.cuda.synchronize(device)
-    ms = e0.elapsed_time(e1) / iters
+    ms = _graph_time_ms(lambda i: be.linear_fwd(xs[i % nbuf], wt, bias, ys[i % nbuf], relu=True), 20, device)
     flops = 2.0 * M * N * K
     achieved = flops / (ms * 1e-3) / 1e12
     peak = peaks.get("bf16_tflops", 1590.0)
@@ -502,6 +562,10 @@ def run_b200_arm(args):
         fl = flops_forward(w)
         breakdown = kernel_breakdown(ctx, device)
         roof = dominant_kernel_roofline(ctx, device, peaks)
+        try:
+            enc_attn = encoder_attention_block(ctx, device, peaks) if args.precision == "bf16" else None
+        except Exception as e:  # a diagnostic, never fatal for the bench line
+            enc_attn = {"error": f"{type(e).__name__}: {e}"}
         step_s = ms_total * 1e-3 / args.steps
         sustained = peaks.get("bf16_tflops_sustained", 1400.0)
         gemm_ms = sum(v["ms"] for k, v in breakdown["calls"].items() if k.startswith("linear"))
@@ -526,6 +590,7 @@ def run_b200_arm(args):
                            "achieved_tflops": 3 * fl["total"] / step_s / 1e12,
                            "frac_of_sustained_bf16_peak": 3 * fl["total"] / step_s / 1e12 / sustained,
                            "encoder_attn_block_fwd": fl["encoder_attn_block"]},
+            "encoder_attention": enc_attn,
             "kernel_breakdown": breakdown,
             "kernel_share": {"gemm": gemm_ms / breakdown["step_ms_instrumented"],
                              "attention": attn_ms / breakdown["step_ms_instrumented"]},
