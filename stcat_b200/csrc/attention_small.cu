@@ -86,6 +86,8 @@ attn_small_fwd_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict_
                       int64_t ldv, T* __restrict__ o, int64_t ldo, const uint8_t* __restrict__ key_mask,
                       float* __restrict__ lse, float* __restrict__ p_avg, int H, int Lq, int Lk, float scale) {
     extern __shared__ float smf[];
+    pdl_launch_dependents();
+    pdl_wait();
     const int LqP = (Lq + 3) & ~3, LkP = (Lk + 3) & ~3;
     const int lds = LkP + 1;
     float* Qs = smf;
@@ -142,6 +144,8 @@ attn_small_bwd_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict_
                       T* __restrict__ dk, int64_t lddk, T* __restrict__ dv, int64_t lddv, int H, int Lq, int Lk,
                       float scale) {
     extern __shared__ float smf[];
+    pdl_launch_dependents();
+    pdl_wait();
     const int LqP = (Lq + 3) & ~3, LkP = (Lk + 3) & ~3;
     const int lds = LkP + 1;
     float* Qs = smf;
@@ -217,8 +221,8 @@ static int sm_launch_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk,
         if (e != cudaSuccess) return set_err((int)e, "attn_small_fwd: smem attribute: %s", cudaGetErrorString(e));
         set_to = sm_fwd_bytes(SM_LMAX, SM_LMAX);
     }
-    attn_small_fwd_kernel<T><<<dim3(H, B), SM_THREADS, smem, st>>>((const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, (T*)o,
-                                                                   ldo, key_mask, lse, p_avg, H, Lq, Lk, scale);
+    launch_pdl(attn_small_fwd_kernel<T>, dim3(H, B), dim3(SM_THREADS), smem, st, (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, (T*)o,
+               ldo, key_mask, lse, p_avg, H, Lq, Lk, scale);
     return check_launch("attn_small_fwd_kernel");
 }
 
@@ -234,9 +238,8 @@ static int sm_launch_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk,
         if (e != cudaSuccess) return set_err((int)e, "attn_small_bwd: smem attribute: %s", cudaGetErrorString(e));
         set_to = sm_bwd_bytes(SM_LMAX, SM_LMAX);
     }
-    attn_small_bwd_kernel<T><<<dim3(H, B), SM_THREADS, smem, st>>>((const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv,
-                                                                   (const T*)d_o, lddo, key_mask, lse, dp_avg, (T*)dq, lddq,
-                                                                   (T*)dk, lddk, (T*)dv, lddv, H, Lq, Lk, scale);
+    launch_pdl(attn_small_bwd_kernel<T>, dim3(H, B), dim3(SM_THREADS), smem, st, (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv,
+               (const T*)d_o, lddo, key_mask, lse, dp_avg, (T*)dq, lddq, (T*)dk, lddk, (T*)dv, lddv, H, Lq, Lk, scale);
     return check_launch("attn_small_bwd_kernel");
 }
 

@@ -79,6 +79,8 @@ attn_sq_fwd_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t l
                    const T* __restrict__ k2, int64_t ldk, const T* __restrict__ v, int64_t ldv, T* __restrict__ o,
                    int64_t ldo, const uint8_t* __restrict__ key_mask, float* __restrict__ lse, int H, int Lk, float scale) {
     extern __shared__ float sm[];  // scores / probabilities [Lk]
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float red[SQ_THREADS / 32];
     __shared__ float part[SQ_THREADS / 32][32];
     const int b = blockIdx.x / H, h = blockIdx.x % H;
@@ -140,6 +142,8 @@ attn_sq_bwd_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t l
                    T* __restrict__ dk1, T* __restrict__ dk2, int64_t lddk, T* __restrict__ dv, int64_t lddv, int H, int Lk,
                    float scale) {
     extern __shared__ float sm[];  // p [Lk], dp [Lk]
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float red[SQ_THREADS / 32];
     __shared__ float part[SQ_THREADS / 32][64];
     float* sp = sm;
@@ -233,7 +237,7 @@ template <typename T, bool TWO>
 static int launch_sq_fwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2, int64_t ldk,
                          const void* v, int64_t ldv, void* o, int64_t ldo, const uint8_t* key_mask, float* lse, int B, int H,
                          int Lk, float scale, cudaStream_t st) {
-    attn_sq_fwd_kernel<T, TWO><<<B * H, SQ_THREADS, Lk * sizeof(float), st>>>(
+    launch_pdl(attn_sq_fwd_kernel<T, TWO>, dim3(B * H), dim3(SQ_THREADS), Lk * sizeof(float), st,
         (const T*)q1, (const T*)q2, ldq, (const T*)k1, (const T*)k2, ldk, (const T*)v, ldv, (T*)o, ldo, key_mask, lse, H, Lk, scale);
     return check_launch("attn_sq_fwd_kernel");
 }
@@ -243,7 +247,7 @@ static int launch_sq_bwd(const void* q1, const void* q2, int64_t ldq, const void
                          const void* v, int64_t ldv, const void* d_o, int64_t lddo, const uint8_t* key_mask, const float* lse,
                          float* delta, void* dq1, void* dq2, int64_t lddq, void* dk1, void* dk2, int64_t lddk, void* dv,
                          int64_t lddv, int B, int H, int Lk, float scale, cudaStream_t st) {
-    attn_sq_bwd_kernel<T, TWO><<<B * H, SQ_THREADS, 2 * Lk * sizeof(float), st>>>(
+    launch_pdl(attn_sq_bwd_kernel<T, TWO>, dim3(B * H), dim3(SQ_THREADS), 2 * Lk * sizeof(float), st,
         (const T*)q1, (const T*)q2, ldq, (const T*)k1, (const T*)k2, ldk, (const T*)v, ldv, (const T*)d_o, lddo, key_mask, lse,
         delta, (T*)dq1, (T*)dq2, lddq, (T*)dk1, (T*)dk2, lddk, (T*)dv, lddv, H, Lk, scale);
     return check_launch("attn_sq_bwd_kernel");

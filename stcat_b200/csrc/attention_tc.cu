@@ -90,6 +90,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_launch_dependents();
+    pdl_wait();
 
     auto decode = [&](int i, int& b, int& h, int& qt) {
         const int w = blockIdx.x + i * gridDim.x;
@@ -328,6 +330,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -571,7 +575,7 @@ int attn_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
     const int total = B * H * p.nqt;
     const int sms = num_sms();
     const int grid = total < sms ? total : sms;
-    attn_tc_fwd_kernel<<<grid, AT_FWD_THREADS, AT_FWD_SMEM, st>>>(tmQ, tmK, tmV, p);
+    launch_pdl(attn_tc_fwd_kernel, dim3(grid), dim3(AT_FWD_THREADS), AT_FWD_SMEM, st, tmQ, tmK, tmV, p);
     return check_launch("attn_tc_fwd_kernel");
 }
 
@@ -619,7 +623,7 @@ int attn_tc_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
     const int total = B * H;
     const int sms = num_sms();
     const int grid = total < sms ? total : sms;
-    attn_tc_bwd_kernel<<<grid, AB_THREADS, AB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, p);
+    launch_pdl(attn_tc_bwd_kernel, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, p);
     return check_launch("attn_tc_bwd_kernel");
 }
 

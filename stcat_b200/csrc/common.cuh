@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/stcat_b200.h"
 
@@ -50,6 +51,36 @@ struct GemmEpilogue {
     int64_t ld_mask = 0;
     float* colsum = nullptr;           // [N] fp32: accumulated with the column sums of the stored C
 };
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
+// One step is a dependent chain of ~10^3 short kernels; at a kernel boundary the GPU otherwise drains the grid, then
+// launches, then the next grid runs its prologue (barrier init, TMEM allocation, descriptor prefetch) before it touches
+// any data.  With the launch attribute below the next grid is scheduled as soon as every CTA of the previous one has
+// passed pdl_launch_dependents(), runs its prologue under the previous kernel's tail, and blocks in pdl_wait() until
+// the previous grid has completed and its writes are visible.  pdl_wait() must precede every global-memory access.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static const bool on = getenv("STCAT_NO_PDL") == nullptr;
+    return on;
+}
+
+// launch `kernel` (which calls pdl_wait() before its first global access) with programmatic stream serialization
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 inline int num_sms() {
     static int n = 0;

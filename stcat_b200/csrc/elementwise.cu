@@ -11,6 +11,8 @@ __device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d)
 __global__ void __launch_bounds__(256)
 add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
            __nv_bfloat16* __restrict__ out_bf16, int64_t n4, int64_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 x = reinterpret_cast<const float4*>(a)[i];
@@ -36,6 +38,8 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const TY* __restrict__ y,
 
 __global__ void __launch_bounds__(256)
 cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t n4, int64_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 v = reinterpret_cast<const float4*>(x)[i];
@@ -211,7 +215,7 @@ extern "C" int stcat_add(const float* a, const float* b, float* out, void* out_b
     if (n == 0) return 0;
     STCAT_REQUIRE(((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)out_bf16 % 8 == 0),
                   STCAT_EALIGN, "add: pointers must be 16-byte aligned");
-    add_kernel<<<grid_for(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(a, b, out, (__nv_bfloat16*)out_bf16, n / 4, n);
+    launch_pdl(add_kernel, dim3(grid_for(n / 4 + 1)), dim3(256), 0, (cudaStream_t)stream, a, b, out, (__nv_bfloat16*)out_bf16, n / 4, n);
     return check_launch("add_kernel");
 }
 
@@ -239,7 +243,7 @@ extern "C" int stcat_cast_bf16(const float* x, void* out, int64_t rows, int64_t 
     if (!transpose) {
         int64_t n = rows * cols;
         STCAT_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 8 == 0), STCAT_EALIGN, "cast_bf16: alignment");
-        cast_bf16_kernel<<<grid_for(n / 4 + 1), 256, 0, st>>>(x, (__nv_bfloat16*)out, n / 4, n);
+        launch_pdl(cast_bf16_kernel, dim3(grid_for(n / 4 + 1)), dim3(256), 0, st, x, (__nv_bfloat16*)out, n / 4, n);
         return check_launch("cast_bf16_kernel");
     }
     dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));

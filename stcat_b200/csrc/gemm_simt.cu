@@ -93,6 +93,8 @@ __global__ void __launch_bounds__(256)
 gemm_warpdot_kernel(const TIn* __restrict__ A, int64_t sam, int64_t sak, const TIn* __restrict__ B, int64_t sbn,
                     int64_t sbk, TOut* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int M, int N,
                     int K, int relu, int accumulate) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= (int64_t)M * N) return;
@@ -146,8 +148,8 @@ static int launch_gemm(const void* A, int64_t sam, int64_t sak, const void* B, i
                        cudaStream_t st) {
     if ((int64_t)M * N <= 8192 && K >= 32) {  // few outputs: one warp each
         const int64_t warps = (int64_t)M * N;
-        gemm_warpdot_kernel<TIn, TOut><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>((const TIn*)A, sam, sak, (const TIn*)B, sbn, sbk,
-                                                                                     (TOut*)C, ldc, bias, M, N, K, relu, accumulate);
+        launch_pdl(gemm_warpdot_kernel<TIn, TOut>, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, st, (const TIn*)A, sam, sak, (const TIn*)B, sbn, sbk,
+                   (TOut*)C, ldc, bias, M, N, K, relu, accumulate);
         return check_launch("gemm_warpdot_kernel");
     }
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
@@ -176,6 +178,8 @@ int gemm_simt(const void* A, int64_t sam, int64_t sak, const void* B, int64_t sb
 __global__ void __launch_bounds__(256) colsum_bf16_wide_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld,
                                                                float* __restrict__ db, int M, int N, int rows_per_block) {
     __shared__ float red[8][256 + 8];
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = blockIdx.x * 256 + lane * 8;  // this lane's 8 columns
     const int r0 = blockIdx.y * rows_per_block;
@@ -210,6 +214,8 @@ struct ColsumGroup { const void* dy[12]; int64_t ld[12]; float* db[12]; int M[12
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_group_kernel(const ColsumGroup g) {
     __shared__ float red[8][33];
+    pdl_launch_dependents();
+    pdl_wait();
     const int j = blockIdx.y;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int n = blockIdx.x * 32 + tx;
@@ -245,8 +251,8 @@ int colsum_group(const void* const* dy, const int64_t* ld, float* const* db, con
     ColsumGroup g;
     for (int j = 0; j < njobs; ++j) { g.dy[j] = dy[j]; g.ld[j] = ld[j]; g.db[j] = db[j]; g.M[j] = M[j]; g.N[j] = N[j]; }
     dim3 grid((maxN + 31) / 32, njobs);
-    if (dtype == STCAT_F32) colsum_group_kernel<float><<<grid, 256, 0, st>>>(g);
-    else colsum_group_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(g);
+    if (dtype == STCAT_F32) launch_pdl(colsum_group_kernel<float>, grid, dim3(256), 0, st, g);
+    else launch_pdl(colsum_group_kernel<__nv_bfloat16>, grid, dim3(256), 0, st, g);
     return check_launch("colsum_group_kernel");
 }
 
@@ -260,7 +266,7 @@ int colsum(const void* dy, int64_t ld, int dtype, float* db, int M, int N, int a
         int rpb = (int)(((int64_t)M * ((N + 255) / 256) + num_sms() * 4 - 1) / (num_sms() * 4));
         rpb = rpb < 32 ? 32 : rpb;
         dim3 g((N + 255) / 256, (M + rpb - 1) / rpb);
-        colsum_bf16_wide_kernel<<<g, 256, 0, st>>>((const __nv_bfloat16*)dy, ld, db, M, N, rpb);
+        launch_pdl(colsum_bf16_wide_kernel, g, dim3(256), 0, st, (const __nv_bfloat16*)dy, ld, db, M, N, rpb);
         return check_launch("colsum_bf16_wide_kernel");
     }
     int rows_per_block = 512;

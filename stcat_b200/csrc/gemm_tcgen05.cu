@@ -121,6 +121,9 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    // everything above (barriers, TMEM, descriptor prefetch) ran under the previous kernel's tail; its data is needed now
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -441,7 +444,8 @@ static int launch_tc(const tc::GroupParams<NJ>& gp, int grid, cudaStream_t st) {
         if (e != cudaSuccess) return set_err((int)e, "gemm_tc: smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    gemm_tc_kernel<AMN, BMN, OBF, BN, NJ><<<grid, THREADS, Cfg<BN>::SMEM_BYTES, st>>>(gp);
+    cudaError_t le = launch_pdl(gemm_tc_kernel<AMN, BMN, OBF, BN, NJ>, dim3(grid), dim3(THREADS), Cfg<BN>::SMEM_BYTES, st, gp);
+    if (le != cudaSuccess) return set_err((int)le, "gemm_tc_kernel launch: %s", cudaGetErrorString(le));
     return check_launch("gemm_tc_kernel");
 }
 

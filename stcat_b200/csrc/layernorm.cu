@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16,
                      float* __restrict__ mean, float* __restrict__ rstd, int rows, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float g[8], bt[8];
     load_row(gamma, lane, g);
@@ -71,6 +73,8 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     __shared__ float sg[LN_ROWS_PER_BLOCK][LN_D];
     __shared__ float sb[LN_ROWS_PER_BLOCK][LN_D];
     __shared__ float sz[LN_ROWS_PER_BLOCK][LN_D];
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float g[8];
     load_row(gamma, lane, g);
@@ -144,8 +148,8 @@ extern "C" int stcat_layernorm_fwd(const float* x, const float* res, const float
     int blocks = (rows + LN_ROWS_PER_BLOCK - 1) / LN_ROWS_PER_BLOCK;
     int cap = num_sms() * 8;
     if (blocks > cap) blocks = cap;
-    layernorm_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, res, gamma, beta, y, (__nv_bfloat16*)y_bf16, mean,
-                                                                  rstd, rows, eps);
+    launch_pdl(layernorm_fwd_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, res, gamma, beta, y, (__nv_bfloat16*)y_bf16, mean,
+               rstd, rows, eps);
     return check_launch("layernorm_fwd_kernel");
 }
 
@@ -158,7 +162,7 @@ extern "C" int stcat_layernorm_bwd(const float* dy, const float* x, const float*
     int blocks = (rows + LN_ROWS_PER_BLOCK - 1) / LN_ROWS_PER_BLOCK;
     int cap = num_sms() * 2;
     if (blocks > cap) blocks = cap;
-    layernorm_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dy, x, res, gamma, mean, rstd, dz, (__nv_bfloat16*)dz_bf16,
-                                                                   dgamma, dbeta, dbias, rows);
+    launch_pdl(layernorm_bwd_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, dy, x, res, gamma, mean, rstd, dz,
+               (__nv_bfloat16*)dz_bf16, dgamma, dbeta, dbias, rows);
     return check_launch("layernorm_bwd_kernel");
 }
