@@ -160,6 +160,21 @@ STCAT_API int stcat_sted_score(const float* sted, const int32_t* durations, floa
                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * VideoSTGLoss (criterion.py:26-207) for nl decoder layers in one launch: values AND gradients w.r.t. the predictions.
+ *   coord [nl,n,4] predicted boxes (cx,cy,w,h); sted [nl,b,t,2]; act [nl,b,t] or NULL; attn [nl,b,t,t] or NULL.
+ *   slice [K] int64 rows of coord with a ground-truth box, tgt_boxes [K,4]; time_mask [b,t] uint8 (1 = inside the
+ *   clip); distrib [b,t,2] target start/end distributions; neg_f [b,t], nb_neg [b] (guided attention, :111-130);
+ *   bce_weight, actioness [b,t] (:46-62).  coef5 = HOST array {bbox, giou, sted, guided_attn, actioness} weights.
+ *   losses [nl,5]: unweighted values in that order.  d_* : gradient of sum_l sum_k coef_k * loss[l,k] w.r.t. the
+ *   corresponding input (same shapes, fully overwritten; d_act / d_attn NULL iff act / attn NULL).
+ * ---------------------------------------------------------------------------------------------- */
+STCAT_API int stcat_stg_loss(const float* coord, const float* sted, const float* act, const float* attn, const int64_t* slice,
+                   const float* tgt_boxes, const uint8_t* time_mask, const float* distrib, const float* neg_f,
+                   const float* nb_neg, const float* bce_weight, const float* actioness, const float* coef5, float num_boxes,
+                   int nl, int n, int b, int t, int K, float* losses, float* d_coord, float* d_sted, float* d_act,
+                   float* d_attn, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * 2-D temporal proposal map (map2d_head.py:39-62, orphaned in the reference -- SURVEY.md 0-2):
  *   map[B,d,N,N]: cell (i,j) of the valid set = max_t x[B, i..j, d]; other cells 0.
  * x is [B, N, d] (already pooled to N positions); valid[N*N] uint8 is the reference's mask2d.

@@ -53,6 +53,7 @@ class _Job(ctypes.Structure):
                 ("out", c_void_p), ("ldo", c_int64), ("dbias", c_void_p)]
 
 
+SIGNATURES["stcat_stg_loss"] = (c_int, [_P] * 12 + [ctypes.POINTER(c_float), _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P])
 SIGNATURES["stcat_linear_group"] = (c_int, [_I, _I, ctypes.POINTER(_Job), _I, _P])
 MAX_GROUP_JOBS = 12
 
@@ -278,6 +279,24 @@ class CudaBackend:
         rows, cols = x.shape
         self._rc(self.lib.stcat_cast_bf16(self._flat(x, "x", torch.float32), self._flat(out, "out", torch.bfloat16), rows,
                                           cols, int(transpose), self._stream()), "cast_bf16")
+        self.launches += 1
+
+    # -- loss ----------------------------------------------------------
+    def stg_loss(self, coord, sted, act, attn, plan, coef5, losses, d_coord, d_sted, d_act, d_attn):
+        """VideoSTGLoss values + gradients for all layers in one launch (include/stcat_b200.h, stcat_stg_loss).  ``plan`` carries
+        the precomputed target tensors (loss.STGLossPlan)."""
+        f = torch.float32
+        nl, n, _ = coord.shape
+        b, t = plan.b, plan.t
+        carr = (c_float * 5)(*[float(c) for c in coef5])
+        self._rc(self.lib.stcat_stg_loss(
+            self._flat(coord, "coord", f), self._flat(sted, "sted", f), self._flat(act, "act", f), self._flat(attn, "attn", f),
+            self._flat(plan.slice, "slice", torch.int64), self._flat(plan.target_boxes, "target_boxes", f),
+            self._flat(plan.time_mask_u8, "time_mask", torch.uint8), self._flat(plan.distrib, "distrib", f),
+            self._flat(plan.neg_f, "neg_f", f), self._flat(plan.nb_neg, "nb_neg", f), self._flat(plan.bce_weight, "bce_weight", f),
+            self._flat(plan.actioness, "actioness", f), carr, float(plan.num_boxes), nl, n, b, t, int(plan.slice.numel()),
+            self._flat(losses, "losses", f), self._flat(d_coord, "d_coord", f), self._flat(d_sted, "d_sted", f),
+            self._flat(d_act, "d_act", f), self._flat(d_attn, "d_attn", f), self._stream()), "stg_loss")
         self.launches += 1
 
     # -- post-process / map2d -------------------------------------------

@@ -89,6 +89,7 @@ class STGLossPlan:
             ds.append(F.normalize((-((ar - tt) ** 2) / (2 * S.SIGMA ** 2)).exp() + eps, p=1, dim=1))
         self.distrib = torch.stack(ds, -1).to(device)  # [b, t, 2]
         self.time_mask = time_mask.to(device)
+        self.time_mask_u8 = time_mask.to(torch.uint8).to(device)
         self.time_mask_f = time_mask.float().to(device)
         pm = positive | (~time_mask)
         self.neg_f = (~pm).float().to(device)  # [b, t]
@@ -98,8 +99,40 @@ class STGLossPlan:
         self.weights = loss_weight_dict(cfg)
         self.b, self.t = b, t
 
+    ORDER = ("loss_bbox", "loss_giou", "loss_sted", "loss_guided_attn", "loss_actioness")
+
+    def _fused(self, out: dict):
+        """CUDA path: one kernel for the values and the gradients of all layers (csrc/stg_loss.cu)."""
+        nl = out["_hs"].shape[0]
+        first = 0 if self.use_aux else nl - 1
+        coord = out["_coord_all"][first:]
+        sted = out["_sted_all"][first:]
+        act = out["_act_all"][first:] if self.use_action else None
+        attn = out["_weights_all"][first:] if self.use_attn else None
+        coef = [self.weights["loss_bbox"], self.weights["loss_giou"], self.weights["loss_sted"],
+                self.weights.get("loss_guided_attn", 0.0) if self.use_attn else 0.0,
+                self.weights.get("loss_actioness", 0.0) if self.use_action else 0.0]
+        total, losses = FusedSTGLossFn.apply(self, tuple(coef), coord, sted, act, attn)
+        named = {}
+        k = losses.shape[0]
+        for ci, name in enumerate(self.ORDER):
+            if (name == "loss_guided_attn" and not self.use_attn) or (name == "loss_actioness" and not self.use_action):
+                continue
+            named[name] = losses[k - 1, ci]
+            if self.use_aux:
+                for i in range(k - 1):
+                    named[f"{name}_{i}"] = losses[i, ci]
+        return total, named
+
     def __call__(self, out: dict):
         """out: the dict of STCATHotPath.forward.  Returns (total, {reference loss name: scalar tensor})."""
+        if out["_coord_all"].is_cuda:
+            return self._fused(out)
+        return self.torch_restatement(out)
+
+    def torch_restatement(self, out: dict):
+        """The same loss with torch tensor ops: used on CPU by the tests of the host-side composition (no CUDA device in
+        the build container) and as the on-device checker of the fused kernel (tests/test_gpu_hotpath.py)."""
         eps = 1e-6
         nl = out["_hs"].shape[0]
         coord = out["_coord_all"]  # [nl, b*t, 4]
@@ -132,3 +165,36 @@ class STGLossPlan:
                 for i in range(nl - 1):
                     named[f"{k}_{i}"] = v[i]
         return total, named
+
+
+class FusedSTGLossFn(torch.autograd.Function):
+    """total = sum_l sum_k coef_k loss_{l,k}: values and gradients from ONE kernel launch (stcat_stg_loss); backward just
+    scales the stored gradients by the incoming scalar."""
+
+    @staticmethod
+    def forward(ctx, plan, coef, coord, sted, act, attn):
+        from . import ops
+
+        be = ops.get_backend()
+        f32 = torch.float32
+        c = coord.detach().to(f32).contiguous()
+        s = sted.detach().to(f32).contiguous()
+        a = None if act is None else act.detach().to(f32).contiguous()
+        w = None if attn is None else attn.detach().to(f32).contiguous()
+        k = c.shape[0]
+        losses = torch.empty(k, 5, dtype=f32, device=c.device)
+        dc, ds = torch.empty_like(c), torch.empty_like(s)
+        da = None if a is None else torch.empty_like(a)
+        dw = None if w is None else torch.empty_like(w)
+        be.stg_loss(c, s, None if a is None else a.view(k, plan.b, plan.t), w, plan, coef, losses, dc, ds, da, dw)
+        cvec = torch.tensor(coef, dtype=f32).to(c.device, non_blocking=True) if not hasattr(plan, "_coef_dev") else plan._coef_dev
+        plan._coef_dev = cvec
+        total = (losses * cvec).sum()
+        ctx.save_for_backward(dc, ds, da, dw)
+        ctx.mark_non_differentiable(losses)
+        return total, losses
+
+    @staticmethod
+    def backward(ctx, g, _unused):
+        dc, ds, da, dw = ctx.saved_tensors
+        return (None, None, dc * g, ds * g, None if da is None else da * g, None if dw is None else dw * g)

@@ -234,3 +234,35 @@ def test_grad_fusion_and_single_stream_agree(precision):
                 assert g1 is None or float(g1.abs().max()) == 0.0, (configs[ci], k)
             else:
                 assert rel_err(g1, g0) < tol or float((g1 - g0).abs().max()) < 1e-6, (configs[ci], k, rel_err(g1, g0))
+
+
+@pytest.mark.parametrize("durs,aux", [([12], True), ([7, 12, 3], True), ([9, 4], False)])
+def test_fused_loss_kernel_matches_torch_restatement(durs, aux):
+    """stcat_stg_loss (values + gradients of all layers in one launch) vs the torch restatement of VideoSTGLoss on the same
+    random predictions: boxes L1 + GIoU, start/end KL, guided attention, actioness BCE, ragged durations."""
+    from stcat_b200.loss import STGLossPlan
+
+    cfg = cfg_for({"max_video_len": 20})
+    cfg.merge_from_list(["SOLVER.GIOU_COEF", 3, "SOLVER.TEMP_COEF", 10, "SOLVER.EOS_COEF", 0.3, "SOLVER.USE_AUX_LOSS", aux])
+    b, t, nl = len(durs), max(durs), 6
+    tg = synthetic.make_targets(durs, seed=3)
+    plan = STGLossPlan(cfg, tg["boxes"], tg["actioness"], durs, "cuda")
+    gen = torch.Generator().manual_seed(5)
+    mk = lambda *shape: torch.randn(*shape, generator=gen)
+    leaves = {"_coord_all": torch.sigmoid(mk(nl, b * t, 4)), "_sted_all": 2 * mk(nl, b, t, 2), "_act_all": mk(nl, b, t, 1),
+              "_weights_all": torch.softmax(mk(nl, b, t, t), -1)}
+    res = []
+    for fused in (True, False):
+        out = {k: v.clone().cuda().requires_grad_(True) for k, v in leaves.items()}
+        out["_hs"] = torch.zeros(nl, 1, device="cuda")
+        total, named = plan(out) if fused else plan.torch_restatement(out)
+        total.backward()
+        res.append((total.detach(), {k: v.detach() for k, v in named.items()}, {k: out[k].grad for k in leaves}))
+    (tf, nf, gf), (tt, nt, gt) = res
+    assert abs(float(tf) - float(tt)) <= 2e-5 * abs(float(tt))
+    assert set(nf) == set(nt)
+    for k in nt:
+        assert abs(float(nf[k]) - float(nt[k])) <= 2e-5 * max(1.0, abs(float(nt[k]))), k
+    for k in leaves:
+        ref = gt[k] if gt[k] is not None else torch.zeros_like(gf[k])
+        assert rel_err(gf[k], ref) < 1e-4, k
