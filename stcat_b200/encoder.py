@@ -138,8 +138,7 @@ class SpatialTemporalEncoder(nn.Module):
             if on_input is not None:
                 on_input(li, X)
             X, X_op = sp.run(X, X_op, POS, key_mask, n, S_len, pos_cls=pos_cls)
-            X3 = X.view(n, S_len, d)
-            cls = X3[:, 0, :]
+            X3, cls = ops.take_rows(X.view(n, S_len, d), 0)  # frame-CLS rows (copy) + the stream itself
             if idx["identity"]:
                 Y = torch.cat([video_src, cls], 0)  # [(t+1), d]
             else:
@@ -148,7 +147,8 @@ class SpatialTemporalEncoder(nn.Module):
             Y3 = Y.view(b, t + 1, d)
             video_src = Y3[:, 0, :]
             cls_new = Y3[0, 1:, :] if idx["identity"] else Y.index_select(0, idx["enc_scatter"])
-            X3[:, 0, :] = cls_new  # the reference's in-place row replacement (modal_encoder.py:191-195)
+            # the reference's in-place row replacement (modal_encoder.py:191-195)
+            X = ops.put_rows(X3, cls_new, 0).view(n * S_len, d)
             if X_op is not None:
                 X_op.view(n, S_len, d)[:, 0, :] = cls_new.detach()
         return X, video_src

@@ -438,6 +438,7 @@ class LayerNormFn(Function):
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
         y_op = torch.empty(rows, d, dtype=torch.bfloat16, device=x.device) if (want_op and _precision == "bf16") else None
         be.layernorm_fwd(x2, r2, gamma.detach(), beta.detach(), y, y_op, mean, rstd, eps)
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(x2, r2, gamma, mean, rstd)
         ctx.beta = beta
         ctx.shape = x.shape
@@ -452,6 +453,8 @@ class LayerNormFn(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, dy, *_unused):
+        if dy is None:
+            return (None,) * 6
         be = get_backend()
         x2, r2, gamma, mean, rstd = ctx.saved_tensors
         d = x2.shape[1]
@@ -660,6 +663,7 @@ class SelfAttnBlockFn(Function):
         mean = torch.empty(R, dtype=torch.float32, device=x.device)
         rstd = torch.empty(R, dtype=torch.float32, device=x.device)
         be.layernorm_fwd(a, xd, gamma.detach(), beta.detach(), y, y_op, mean, rstd, eps)
+        ctx.set_materialize_grads(False)  # no full-size zero tensor for the non-differentiable y_op output
         ctx.save_for_backward(xd, xo, qk_in, qkv, o, lse, a, mean, rstd, key_mask, w_in, w_out, gamma)
         ctx.extra = (b_in, b_out, beta)
         ctx.dims = (B, L, H, scale)
@@ -670,6 +674,8 @@ class SelfAttnBlockFn(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, dy, _unused):
+        if dy is None:
+            return (None,) * 15
         be = get_backend()
         xd, xo, qk_in, qkv, o, lse, a, mean, rstd, key_mask, w_in, w_out, gamma = ctx.saved_tensors
         B, L, H, scale = ctx.dims
@@ -748,6 +754,7 @@ class FFNBlockFn(Function):
         mean = torch.empty(R, dtype=torch.float32, device=x.device)
         rstd = torch.empty(R, dtype=torch.float32, device=x.device)
         be.layernorm_fwd(yl, xd, gamma.detach(), beta.detach(), y, y_op, mean, rstd, eps)
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(xd, xo, h, yl, mean, rstd, w1, w2, gamma)
         ctx.extra = (b1, b2, beta)
         if bf:
@@ -757,6 +764,8 @@ class FFNBlockFn(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, dy, _unused):
+        if dy is None:
+            return (None,) * 9
         be = get_backend()
         xd, xo, h, yl, mean, rstd, w1, w2, gamma = ctx.saved_tensors
         R, d = xd.shape
@@ -792,6 +801,59 @@ def self_attn_block(x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, bet
 
 def ffn_block(x, x_op, w1, b1, w2, b2, gamma, beta, eps=1e-5):
     return FFNBlockFn.apply(x, x_op, w1, b1, w2, b2, gamma, beta, eps)
+
+
+class TakeRowsFn(Function):
+    """(base, rows) = (x, x[:, r, :]) for x [n, S, d]: hands out row r of every sequence (the frame-CLS tokens the
+    temporal encoder layer works on, modal_encoder.py:170-175) together with x itself.  One node with two outputs so
+    that the backward is a row-sized in-place add (d base[:, r, :] += d rows) instead of autograd's full-size zero
+    tensor + full-size sum for a select."""
+
+    @staticmethod
+    def forward(ctx, x, r: int):
+        ctx.r = r
+        ctx.set_materialize_grads(False)
+        # the base output aliases x's storage (detached alias, not an autograd view: it may be written in place later)
+        return x.detach(), x.detach()[:, r, :].clone()
+
+    @staticmethod
+    def backward(ctx, g_base, g_rows):
+        if g_base is None:
+            if g_rows is None:
+                return None, None
+            raise RuntimeError("TakeRowsFn: the base output must be used (it carries the sequence's gradient)")
+        if g_rows is not None:
+            g_base = g_base if g_base.is_contiguous() else g_base.contiguous()
+            g_base[:, ctx.r, :] += g_rows  # g_base is ours: produced for this node alone by PutRowsFn / the next block
+        return g_base, None
+
+
+class PutRowsFn(Function):
+    """x[:, r, :] = rows, in place on x's storage (the reference's ``output[0, :, :] = frames_src``,
+    modal_encoder.py:191-195).  Backward: d rows = g[:, r, :]; d x = g with those rows zeroed -- done in place on g
+    (row-sized kernels) where autograd's CopySlices clones the full tensor."""
+
+    @staticmethod
+    def forward(ctx, x, rows, r: int):
+        ctx.r = r
+        out = x.detach()  # same storage and version counter as x; a new autograd identity owned by this node
+        out[:, r, :] = rows.detach()
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g if g.is_contiguous() else g.contiguous()
+        g_rows = g[:, ctx.r, :].clone()
+        g[:, ctx.r, :] = 0  # g is the gradient tensor produced for this node by the next block's backward: ours to edit
+        return g, g_rows, None
+
+
+def take_rows(x, r: int = 0):
+    return TakeRowsFn.apply(x, r)
+
+
+def put_rows(x, rows, r: int = 0):
+    return PutRowsFn.apply(x, rows, r)
 
 
 def sted_score(pred_sted: torch.Tensor, durations, return_map: bool = False):
