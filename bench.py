@@ -606,7 +606,19 @@ def run_b200_arm(args):
                                         "sample": f"failed: {type(e).__name__}: {e}"}
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
+        # A communicator whose collectives live in a captured graph can block in ncclCommDestroy: release the graph first,
+        # and never let process teardown hang the job (the line above is already printed).
+        def _bail():
+            time.sleep(30)
+            os._exit(0)
+
+        threading.Thread(target=_bail, daemon=True).start()
         dist.barrier()
+        torch.cuda.synchronize(device)
+        if graph is not None:
+            graph.reset()
+            del graph
+        torch.cuda.synchronize(device)
         dist.destroy_process_group()
 
 
