@@ -3,7 +3,7 @@
 set -u
 mkdir -p gpurun_out
 if [ -n "${TESTS:-}" ]; then timeout 900 python -m pytest $TESTS -x -q > gpurun_out/pytest_sel.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_sel.log; fi
-STCAT_TRACE=gpurun_out/trace.json timeout 600 python bench.py --steps 10 --warmup 3 --precision bf16 --no-cpu-baseline --profile gpurun_out/profile_bf16.md > gpurun_out/bench_bf16.json 2> gpurun_out/bench_bf16.err; echo "bench rc=$?"
+STCAT_TRACE=gpurun_out/trace.json timeout 600 python bench.py --steps 20 --warmup 5 --precision bf16 --no-cpu-baseline --profile gpurun_out/profile_bf16.md > gpurun_out/bench_bf16.json 2> gpurun_out/bench_bf16.err; echo "bench rc=$?"
 python - <<'PY'
 import json
 try:

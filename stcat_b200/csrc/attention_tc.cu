@@ -175,10 +175,15 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     uint32_t r[32];
                     tmem_ld32(t_row + c * 32, r);
                     tmem_ld_wait();
-                    const uint32_t w = mw[c];
+                    const uint32_t w = mw[c];  // identical in every lane: the branch below is warp-uniform
+                    if (w == 0u) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e)
-                        if (!((w >> e) & 1u)) mx = fmaxf(mx, __uint_as_float(r[e]));
+                        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            if (!((w >> e) & 1u)) mx = fmaxf(mx, __uint_as_float(r[e]));
+                    }
                 }
             }
             const float ms = (mx == -INFINITY) ? 0.f : mx * sc;
@@ -192,13 +197,24 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 tmem_ld_wait();
                 const uint32_t w = mw[c];
                 uint32_t pk[16];
+                if (w == 0u) {  // no masked key in this chunk (the common case): no per-element predicates
 #pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    float p0 = ((w >> e) & 1u) ? 0.f : ex2_approx(fmaf(__uint_as_float(r[e]), sc, -ms));
-                    float p1 = ((w >> (e + 1)) & 1u) ? 0.f : ex2_approx(fmaf(__uint_as_float(r[e + 1]), sc, -ms));
-                    sum += p0 + p1;
-                    __nv_bfloat162 bb = __floats2bfloat162_rn(p0, p1);
-                    pk[e >> 1] = *reinterpret_cast<uint32_t*>(&bb);
+                    for (int e = 0; e < 32; e += 2) {
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(r[e]), sc, -ms));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(r[e + 1]), sc, -ms));
+                        sum += p0 + p1;
+                        __nv_bfloat162 bb = __floats2bfloat162_rn(p0, p1);
+                        pk[e >> 1] = *reinterpret_cast<uint32_t*>(&bb);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) {
+                        float p0 = ((w >> e) & 1u) ? 0.f : ex2_approx(fmaf(__uint_as_float(r[e]), sc, -ms));
+                        float p1 = ((w >> (e + 1)) & 1u) ? 0.f : ex2_approx(fmaf(__uint_as_float(r[e + 1]), sc, -ms));
+                        sum += p0 + p1;
+                        __nv_bfloat162 bb = __floats2bfloat162_rn(p0, p1);
+                        pk[e >> 1] = *reinterpret_cast<uint32_t*>(&bb);
+                    }
                 }
                 const uint32_t blk = prow + (c >> 1) * 16384;
 #pragma unroll
@@ -456,22 +472,40 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         tmem_ld32(tmem_base + lane_off + AB_COL_S + col, rs);
                         tmem_ld32(tmem_base + lane_off + AB_COL_DP + col, rd);
                         tmem_ld_wait();
-                        const uint32_t wmask = dead ? 0xffffffffu : (wg ? mw[kt * 4 + 2 + c] : mw[kt * 4 + c]);
+                        const uint32_t mwv = wg ? mw[kt * 4 + 2 + c] : mw[kt * 4 + c];  // warp-uniform
                         uint32_t pp[16], pd[16];
+                        if (mwv == 0u) {
+                            // no masked key in this chunk (the common case): no per-element predicates; a dead row
+                            // (padding / fully masked) has lse_eff = +inf, so every p and ds is exactly 0
+                            const float lse_eff = dead ? INFINITY : lse2;
+                            const float dsc = p.scale;
 #pragma unroll
-                        for (int e = 0; e < 32; e += 2) {
-                            float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
-                            if (!((wmask >> e) & 1u)) {
-                                p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), sc, -lse2));
-                                d0 = p0 * (__uint_as_float(rd[e]) - delta) * p.scale;
+                            for (int e = 0; e < 32; e += 2) {
+                                const float p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), sc, -lse_eff));
+                                const float p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), sc, -lse_eff));
+                                const float d0 = dead ? 0.f : p0 * (__uint_as_float(rd[e]) - delta) * dsc;
+                                const float d1 = dead ? 0.f : p1 * (__uint_as_float(rd[e + 1]) - delta) * dsc;
+                                __nv_bfloat162 bp = __floats2bfloat162_rn(p0, p1), bd = __floats2bfloat162_rn(d0, d1);
+                                pp[e >> 1] = *reinterpret_cast<uint32_t*>(&bp);
+                                pd[e >> 1] = *reinterpret_cast<uint32_t*>(&bd);
                             }
-                            if (!((wmask >> (e + 1)) & 1u)) {
-                                p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), sc, -lse2));
-                                d1 = p1 * (__uint_as_float(rd[e + 1]) - delta) * p.scale;
+                        } else {
+                            const uint32_t wmask = dead ? 0xffffffffu : mwv;
+#pragma unroll
+                            for (int e = 0; e < 32; e += 2) {
+                                float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
+                                if (!((wmask >> e) & 1u)) {
+                                    p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), sc, -lse2));
+                                    d0 = p0 * (__uint_as_float(rd[e]) - delta) * p.scale;
+                                }
+                                if (!((wmask >> (e + 1)) & 1u)) {
+                                    p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), sc, -lse2));
+                                    d1 = p1 * (__uint_as_float(rd[e + 1]) - delta) * p.scale;
+                                }
+                                __nv_bfloat162 bp = __floats2bfloat162_rn(p0, p1), bd = __floats2bfloat162_rn(d0, d1);
+                                pp[e >> 1] = *reinterpret_cast<uint32_t*>(&bp);
+                                pd[e >> 1] = *reinterpret_cast<uint32_t*>(&bd);
                             }
-                            __nv_bfloat162 bp = __floats2bfloat162_rn(p0, p1), bd = __floats2bfloat162_rn(d0, d1);
-                            pp[e >> 1] = *reinterpret_cast<uint32_t*>(&bp);
-                            pd[e >> 1] = *reinterpret_cast<uint32_t*>(&bd);
                         }
                         const uint32_t off = wg * 16384 + row * 128;
 #pragma unroll

@@ -747,8 +747,20 @@ class FFNBlockFn(Function):
         w1o, w2o = _operand(w1.detach(), True), _operand(w2.detach(), True)
         h = _new(R, F_, od, x)
         be.linear_fwd(xo, w1o, b1.detach(), h, relu=True)
-        yl = _new(R, d, torch.float32, x)
-        be.linear_fwd(h, w2o, b2.detach(), yl)
+        if bf and R <= 128 and F_ >= 1024 and F_ % 256 == 0 and F_ // 256 <= 12:
+            # few rows, long contraction (decoder / temporal FFN: [t, 2048] x [2048, 256]): one CTA per output tile would
+            # walk 32 k-blocks alone.  Split the contraction into 256-wide slices, one job each in ONE grouped launch
+            # (all slices run concurrently), and add the partial products in a fixed order: deterministic, unlike
+            # split-K with atomics.
+            nsp = F_ // 256
+            parts = torch.empty(nsp, R, d, dtype=torch.float32, device=x.device)
+            b2d = b2.detach()
+            be.linear_group(0, [dict(terms=[(h[:, s * 256:(s + 1) * 256], w2o[:, s * 256:(s + 1) * 256], b2d if s == 0 else None)],
+                                     out=parts[s]) for s in range(nsp)])
+            yl = parts.sum(0)
+        else:
+            yl = _new(R, d, torch.float32, x)
+            be.linear_fwd(h, w2o, b2.detach(), yl)
         y = _new(R, d, torch.float32, x)
         y_op = _new(R, d, od, x) if bf else None
         mean = torch.empty(R, dtype=torch.float32, device=x.device)
