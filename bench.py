@@ -592,8 +592,9 @@ def run_b200_arm(args):
                            "encoder_attn_block_fwd": fl["encoder_attn_block"]},
             "encoder_attention": enc_attn,
             "kernel_breakdown": breakdown,
-            "kernel_share": {"gemm": gemm_ms / breakdown["step_ms_instrumented"],
-                             "attention": attn_ms / breakdown["step_ms_instrumented"]},
+            # shares of the device time of the instrumented C-ABI calls (the instrumented step itself is host-bound)
+            "kernel_share": {"gemm": gemm_ms / max(sum(v["ms"] for v in breakdown["calls"].values()), 1e-9),
+                             "attention": attn_ms / max(sum(v["ms"] for v in breakdown["calls"].values()), 1e-9)},
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

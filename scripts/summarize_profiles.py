@@ -90,5 +90,7 @@ if v and "dram__bytes_read.sum" in v:
     t = to_bytes(*v["dram__bytes_read.sum"]) + to_bytes(*v["dram__bytes_write.sum"])
     json.dump({"kernel": "gemm_tc_kernel FFN linear1 fwd", "traffic_bytes_per_launch": t, "source": f"profiles/{tag}_ncu_ffn1_gemm.md (dram__bytes_read.sum + dram__bytes_write.sum)"},
               open(os.path.join(P, "dominant_kernel_traffic.json"), "w"))
+full("prof_attn_bwd.ncu-rep", "attn_bwd", "`ncu --set full --clock-control none -k regex:attn_tc_bwd -c 1 python bench.py --steps 1 --warmup 3 --no-graph`: spatial encoder attention "
+     "core backward (S, dP, dV, dK, dQ on tcgen05), 64 frames x 8 heads x (213 x 213 x 32), bf16.")
 full("prof_attn_fwd.ncu-rep", "attn_fwd", "`ncu --set full --clock-control none -k regex:attn_tc_fwd -c 1 python bench.py --steps 1 --warmup 3 --no-graph`: spatial encoder attention "
      "core forward, 64 frames x 8 heads x (213 x 213 x 32), bf16.")
