@@ -150,6 +150,21 @@ STCAT_API int stcat_relu_bwd(const void* y, int y_dtype, void* dy_inout, int dy_
 STCAT_API int stcat_cast_bf16(const float* x, void* out_bf16, int64_t rows, int64_t cols, int transpose, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Anchor glue of the box decoder (query_decoder.py:188-219; net_utils.py:29-63), fp32, one launch each:
+ *   anchor_sine : out[n,512] = gen_sineembed_for_position(anchor[n,4]) (order y,x,w,h; 128 dims per coordinate;
+ *                 sin on even / cos on odd dims of 2 pi c / 10000^(2 floor(k/2)/128)); out_bf16 optional operand copy.
+ *                 bwd: danchor[n,4] (fully written) from dy[n,512].
+ *   box_refine  : out = sigmoid(delta + inverse_sigmoid(anchor, eps)) over n elements (anchor refinement :212-219 and
+ *                 the box head pipeline.py:88-95); bwd: ddelta = g out (1 - out), danchor (may be NULL) likewise
+ *                 through the clamped logit.
+ * ---------------------------------------------------------------------------------------------- */
+STCAT_API int stcat_anchor_sine_fwd(const float* anchor, float* out, void* out_bf16, int64_t n, void* stream);
+STCAT_API int stcat_anchor_sine_bwd(const float* anchor, const float* dy, float* danchor, int64_t n, void* stream);
+STCAT_API int stcat_box_refine_fwd(const float* delta, const float* anchor, float* out, int64_t n, float eps, void* stream);
+STCAT_API int stcat_box_refine_bwd(const float* out, const float* anchor, const float* g, float* ddelta, float* danchor,
+                         int64_t n, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Temporal start/end scoring (post_processor.py:30-53), one launch for b videos:
  *   score[v,i,j] = logsoftmax_t(sted[v,:,0])[i] + logsoftmax_t(sted[v,:,1])[j] + penalty(i,j)
  *   penalty = -1e32 where j <= i or i >= dur[v] or j >= dur[v]

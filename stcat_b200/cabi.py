@@ -53,6 +53,10 @@ class _Job(ctypes.Structure):
                 ("out", c_void_p), ("ldo", c_int64), ("dbias", c_void_p)]
 
 
+SIGNATURES["stcat_anchor_sine_fwd"] = (c_int, [_P, _P, _P, _L, _P])
+SIGNATURES["stcat_anchor_sine_bwd"] = (c_int, [_P, _P, _P, _L, _P])
+SIGNATURES["stcat_box_refine_fwd"] = (c_int, [_P, _P, _P, _L, _F, _P])
+SIGNATURES["stcat_box_refine_bwd"] = (c_int, [_P, _P, _P, _P, _P, _L, _F, _P])
 SIGNATURES["stcat_stg_loss"] = (c_int, [_P] * 12 + [ctypes.POINTER(c_float), _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P])
 SIGNATURES["stcat_linear_group"] = (c_int, [_I, _I, ctypes.POINTER(_Job), _I, _P])
 MAX_GROUP_JOBS = 12
@@ -279,6 +283,33 @@ class CudaBackend:
         rows, cols = x.shape
         self._rc(self.lib.stcat_cast_bf16(self._flat(x, "x", torch.float32), self._flat(out, "out", torch.bfloat16), rows,
                                           cols, int(transpose), self._stream()), "cast_bf16")
+        self.launches += 1
+
+    # -- anchor glue ---------------------------------------------------
+    def anchor_sine_fwd(self, anchor, out, out_bf16=None):
+        f = torch.float32
+        self._rc(self.lib.stcat_anchor_sine_fwd(self._flat(anchor, "anchor", f), self._flat(out, "out", f),
+                                                self._flat(out_bf16, "out_bf16", torch.bfloat16), anchor.shape[0], self._stream()),
+                 "anchor_sine_fwd")
+        self.launches += 1
+
+    def anchor_sine_bwd(self, anchor, dy, danchor):
+        f = torch.float32
+        self._rc(self.lib.stcat_anchor_sine_bwd(self._flat(anchor, "anchor", f), self._flat(dy, "dy", f), self._flat(danchor, "danchor", f),
+                                                anchor.shape[0], self._stream()), "anchor_sine_bwd")
+        self.launches += 1
+
+    def box_refine_fwd(self, delta, anchor, out, eps=1e-3):
+        f = torch.float32
+        self._rc(self.lib.stcat_box_refine_fwd(self._flat(delta, "delta", f), self._flat(anchor, "anchor", f), self._flat(out, "out", f),
+                                               delta.numel(), float(eps), self._stream()), "box_refine_fwd")
+        self.launches += 1
+
+    def box_refine_bwd(self, out, anchor, g, ddelta, danchor, eps=1e-3):
+        f = torch.float32
+        self._rc(self.lib.stcat_box_refine_bwd(self._flat(out, "out", f), self._flat(anchor, "anchor", f), self._flat(g, "g", f),
+                                               self._flat(ddelta, "ddelta", f), self._flat(danchor, "danchor", f), out.numel(),
+                                               float(eps), self._stream()), "box_refine_bwd")
         self.launches += 1
 
     # -- loss ----------------------------------------------------------

@@ -205,6 +205,84 @@ int relu_mask_2d(const void* y, int64_t ldy, int y_dtype, void* dx, int64_t lddx
     return check_launch("relu_mask_2d_kernel");
 }
 
+
+// ---- box-decoder anchor glue (query_decoder.py:188-219, net_utils.py:29-63): one kernel each instead of ~8 ATen kernels ----
+// sine embedding of the (cx, cy, w, h) anchors: out[n, 512] ordered (y, x, w, h), 128 dims per coordinate,
+// e[k] = sin(2 pi c / 10000^(2 floor(k/2) / 128)) for even k, cos(...) for odd k; optional bf16 operand copy.
+__global__ void __launch_bounds__(256) anchor_sine_fwd_kernel(const float* __restrict__ anchor, float* __restrict__ out,
+                                                              __nv_bfloat16* __restrict__ out_bf16, int64_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t total = n * 512;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i >> 9;
+        const int j = (int)(i & 511), blk = j >> 7, k = j & 127;
+        const int c = blk == 0 ? 1 : (blk == 1 ? 0 : blk);  // output block 0 = y, 1 = x, 2 = w, 3 = h
+        const float freq = powf(10000.f, (float)(2 * (k >> 1)) / 128.f);
+        const float p = anchor[r * 4 + c] * 6.283185307179586f / freq;
+        const float v = (k & 1) ? cosf(p) : sinf(p);
+        out[i] = v;
+        if (out_bf16) out_bf16[i] = __float2bfloat16_rn(v);
+    }
+}
+
+// d anchor[r, c] = sum_k dy[r, blk(c), k] * d e_k / d c
+__global__ void __launch_bounds__(128) anchor_sine_bwd_kernel(const float* __restrict__ anchor, const float* __restrict__ dy,
+                                                              float* __restrict__ danchor, int64_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t rc = blockIdx.x;  // one block per (row, coordinate)
+    const int64_t r = rc >> 2;
+    const int c = (int)(rc & 3);
+    const int blk = c == 0 ? 1 : (c == 1 ? 0 : c);
+    const int k = threadIdx.x;
+    const float freq = powf(10000.f, (float)(2 * (k >> 1)) / 128.f);
+    const float w = 6.283185307179586f / freq;
+    const float p = anchor[r * 4 + c] * w;
+    const float g = dy[r * 512 + blk * 128 + k];
+    float v = g * w * ((k & 1) ? -sinf(p) : cosf(p));
+    v = warp_sum(v);
+    __shared__ float red[4];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) danchor[r * 4 + c] = red[0] + red[1] + red[2] + red[3];
+}
+
+// out = sigmoid(delta + logit_clamped(anchor)), logit_clamped(x) = log(max(x', eps) / max(1 - x', eps)), x' = clamp(x, 0, 1)
+__device__ __forceinline__ float logit_clamped(float x, float eps) {
+    x = fminf(fmaxf(x, 0.f), 1.f);
+    return logf(fmaxf(x, eps) / fmaxf(1.f - x, eps));
+}
+__global__ void __launch_bounds__(256) box_refine_fwd_kernel(const float* __restrict__ delta, const float* __restrict__ anchor,
+                                                             float* __restrict__ out, int64_t n, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float z = delta[i] + logit_clamped(anchor[i], eps);
+        out[i] = 1.f / (1.f + expf(-z));
+    }
+}
+__global__ void __launch_bounds__(256) box_refine_bwd_kernel(const float* __restrict__ out, const float* __restrict__ anchor,
+                                                             const float* __restrict__ g, float* __restrict__ ddelta,
+                                                             float* __restrict__ danchor, int64_t n, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float s = out[i];
+        const float dz = g[i] * s * (1.f - s);
+        ddelta[i] = dz;
+        if (danchor) {
+            const float x = anchor[i];
+            float d = 0.f;
+            if (x > 0.f && x < 1.f) {  // clamp(x, 0, 1) passes the gradient strictly inside (at the ends torch gives it too; measure zero)
+                if (x > eps) d += 1.f / x;
+                if (1.f - x > eps) d += 1.f / (1.f - x);
+            }
+            danchor[i] = dz * d;
+        }
+    }
+}
+
 }  // namespace stcat
 
 using namespace stcat;
@@ -268,4 +346,30 @@ extern "C" int stcat_map2d_pool(const float* x, const uint8_t* valid, float* map
     dim3 grid(N, B, (d + 255) / 256);
     map2d_pool_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, valid, map, N, d);
     return check_launch("map2d_pool_kernel");
+}
+
+extern "C" int stcat_anchor_sine_fwd(const float* anchor, float* out, void* out_bf16, int64_t n, void* stream) {
+    STCAT_REQUIRE(anchor && out && n >= 0, STCAT_EINVAL, "anchor_sine_fwd: bad arguments");
+    if (n == 0) return 0;
+    launch_pdl(anchor_sine_fwd_kernel, dim3(grid_for(n * 512)), dim3(256), 0, (cudaStream_t)stream, anchor, out, (__nv_bfloat16*)out_bf16, n);
+    return check_launch("anchor_sine_fwd_kernel");
+}
+extern "C" int stcat_anchor_sine_bwd(const float* anchor, const float* dy, float* danchor, int64_t n, void* stream) {
+    STCAT_REQUIRE(anchor && dy && danchor && n >= 0, STCAT_EINVAL, "anchor_sine_bwd: bad arguments");
+    if (n == 0) return 0;
+    launch_pdl(anchor_sine_bwd_kernel, dim3((unsigned)(n * 4)), dim3(128), 0, (cudaStream_t)stream, anchor, dy, danchor, n);
+    return check_launch("anchor_sine_bwd_kernel");
+}
+extern "C" int stcat_box_refine_fwd(const float* delta, const float* anchor, float* out, int64_t n, float eps, void* stream) {
+    STCAT_REQUIRE(delta && anchor && out && n >= 0, STCAT_EINVAL, "box_refine_fwd: bad arguments");
+    if (n == 0) return 0;
+    launch_pdl(box_refine_fwd_kernel, dim3(grid_for(n)), dim3(256), 0, (cudaStream_t)stream, delta, anchor, out, n, eps);
+    return check_launch("box_refine_fwd_kernel");
+}
+extern "C" int stcat_box_refine_bwd(const float* out, const float* anchor, const float* g, float* ddelta, float* danchor, int64_t n,
+                                    float eps, void* stream) {
+    STCAT_REQUIRE(out && anchor && g && ddelta && n >= 0, STCAT_EINVAL, "box_refine_bwd: bad arguments");
+    if (n == 0) return 0;
+    launch_pdl(box_refine_bwd_kernel, dim3(grid_for(n)), dim3(256), 0, (cudaStream_t)stream, out, anchor, g, ddelta, danchor, n, eps);
+    return check_launch("box_refine_bwd_kernel");
 }

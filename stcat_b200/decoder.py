@@ -69,6 +69,73 @@ def inverse_sigmoid(x: torch.Tensor, eps: float = 1e-3) -> torch.Tensor:
     return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
 
 
+class _AnchorSineFn(torch.autograd.Function):
+    """gen_sineembed_for_position (net_utils.py:29-56) as one kernel; also writes the bf16 GEMM-operand copy."""
+
+    @staticmethod
+    def forward(ctx, anchor):
+        be = ops.get_backend()
+        a = anchor.detach().float().contiguous().view(-1, 4)
+        n = a.shape[0]
+        out = torch.empty(n, 512, dtype=torch.float32, device=a.device)
+        out_op = torch.empty(n, 512, dtype=torch.bfloat16, device=a.device) if ops.get_precision() == "bf16" else None
+        be.anchor_sine_fwd(a, out, out_op)
+        ctx.save_for_backward(a)
+        ctx.shape = anchor.shape
+        ctx.set_materialize_grads(False)
+        lead = anchor.shape[:-1]
+        if out_op is not None:
+            out_op = out_op.view(*lead, 512)
+            ctx.mark_non_differentiable(out_op)
+        return out.view(*lead, 512), out_op
+
+    @staticmethod
+    def backward(ctx, g, _unused):
+        if g is None:
+            return None
+        (a,) = ctx.saved_tensors
+        da = torch.empty_like(a)
+        ops.get_backend().anchor_sine_bwd(a, g.contiguous().view(-1, 512).float(), da)
+        return da.view(ctx.shape)
+
+
+class _BoxRefineFn(torch.autograd.Function):
+    """sigmoid(delta + inverse_sigmoid(anchor)) (query_decoder.py:212-217; pipeline.py:88-95) as one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, delta, anchor):
+        be = ops.get_backend()
+        d = delta.detach().float().contiguous()
+        a = anchor.detach().float().expand_as(d).contiguous()
+        out = torch.empty_like(d)
+        be.box_refine_fwd(d, a, out)
+        ctx.save_for_backward(out, a)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        out, a = ctx.saved_tensors
+        g = g.contiguous().float()
+        dd = torch.empty_like(out)
+        da = torch.empty_like(out) if ctx.needs_input_grad[1] else None
+        ops.get_backend().box_refine_bwd(out, a, g, dd, da)
+        return dd, da
+
+
+def anchor_sine_embed_op(anchor: torch.Tensor):
+    """(sine embedding [..., 512], its GEMM-operand copy or None).  CUDA: one kernel; CPU tensors (the tests of the host-side
+    composition) take the torch restatement below."""
+    if anchor.is_cuda:
+        return _AnchorSineFn.apply(anchor)
+    return anchor_sine_embed(anchor), None
+
+
+def box_refine(delta: torch.Tensor, anchor: torch.Tensor) -> torch.Tensor:
+    if delta.is_cuda and delta.shape == anchor.shape:
+        return _BoxRefineFn.apply(delta, anchor)
+    return torch.sigmoid(delta + inverse_sigmoid(anchor))
+
+
 def run_mlp(m: MLPP, x: torch.Tensor, training: bool = False, x_op=None) -> torch.Tensor:
     """Linear-ReLU stack (net_utils.py:20-26).  Hidden activations feed exactly one GEMM, so without dropout they are
     written in the GEMM-operand dtype by the producing epilogue (no cast kernels); ``x_op`` is the caller's operand
@@ -211,8 +278,9 @@ class TransformerDecoder(nn.Module):
         inter, refs = [], [anchor]
         time_op = ops.operand_copy(query_time)
         for li, layer in enumerate(self.layers):
-            sine = anchor_sine_embed(anchor[..., : self.query_dim])  # [b*t, 512]
-            sine_op = ops.operand_copy(sine)
+            sine, sine_op = anchor_sine_embed_op(anchor[..., : self.query_dim])  # [b*t, 512] (+ operand copy)
+            if sine_op is None:
+                sine_op = ops.operand_copy(sine)
             rp, qsc = self.ref_point_head.layers, self.query_scale.layers
             if li == 0:
                 query_pos = run_mlp(self.ref_point_head, sine, x_op=sine_op)
@@ -228,7 +296,7 @@ class TransformerDecoder(nn.Module):
                 qsine, qsine_op = sine[..., :d] * scale, None
             out, out_op = layer.run(c, out, out_op, query_pos, query_time, time_op, qsine, qsine_op, li == 0, mem_kv[li])
             if self.bbox_embed is not None:
-                new_anchor = torch.sigmoid(run_mlp(self.bbox_embed, out, x_op=out_op) + inverse_sigmoid(anchor))
+                new_anchor = box_refine(run_mlp(self.bbox_embed, out, x_op=out_op), anchor)
                 if li != self.num_layers - 1:
                     refs.append(new_anchor)
                 anchor = new_anchor.detach()

@@ -18,7 +18,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .decoder import build_decoder, inverse_sigmoid, run_mlp
+from .decoder import box_refine, build_decoder, inverse_sigmoid, run_mlp
 from .encoder import build_encoder
 from .params import MLPP
 
@@ -46,7 +46,7 @@ class STCATHotPath(nn.Module):
         if self.use_attn:
             out["weights"] = weights[-1]
         hs, reference = outputs
-        coord = torch.sigmoid(run_mlp(self.bbox_embed, hs, self.training) + inverse_sigmoid(reference)).flatten(1, 2)
+        coord = box_refine(run_mlp(self.bbox_embed, hs, self.training), reference).flatten(1, 2)
         out["pred_boxes"] = coord[-1]
         ths_op = ops.operand_copy(time_hs)  # one operand cast for both temporal heads
         sted = run_mlp(self.temp_embed, time_hs, self.training, x_op=ths_op)

@@ -214,6 +214,41 @@ def test_short_sequence_attention_bf16(be, B, H, Lq, Lk, use_mask, use_pavg):
         assert rel_err(got, leaf.grad) < 1e-2
 
 
+def test_anchor_glue_kernels(be):
+    """anchor sine embedding and box refinement (one kernel each way) vs the torch restatement of net_utils.py:29-63"""
+    from stcat_b200.decoder import anchor_sine_embed, inverse_sigmoid, anchor_sine_embed_op, box_refine
+    from stcat_b200 import ops
+
+    gen = torch.Generator().manual_seed(11)
+    a = torch.rand(77, 4, generator=gen).clamp(1e-4, 1 - 1e-4)
+    a[0] = torch.tensor([0.0, 1.0, 5e-4, 1 - 5e-4])  # the clamps of the logit
+    dy = torch.randn(77, 512, generator=gen)
+    ar = a.clone().double().requires_grad_(True)
+    ref = anchor_sine_embed(ar)
+    ref.backward(dy.double())
+    for prec in ("fp32", "bf16"):
+        ops.set_precision(prec)
+        ac = a.clone().cuda().requires_grad_(True)
+        out, out_op = anchor_sine_embed_op(ac)
+        out.backward(dy.cuda())
+        assert rel_err(out, ref) < 2e-6 and rel_err(ac.grad, ar.grad) < 2e-5
+        assert (out_op is None) == (prec == "fp32")
+        if out_op is not None:
+            assert torch.equal(out_op, out.to(torch.bfloat16))
+    ops.set_precision("fp32")
+    d = torch.randn(77, 4, generator=gen)
+    g = torch.randn(77, 4, generator=gen)
+    dr, ar2 = d.clone().double().requires_grad_(True), a.clone().double().requires_grad_(True)
+    r = torch.sigmoid(dr + inverse_sigmoid(ar2))
+    r.backward(g.double())
+    dc, ac = d.clone().cuda().requires_grad_(True), a.clone().cuda().requires_grad_(True)
+    o = box_refine(dc, ac)
+    o.backward(g.cuda())
+    assert rel_err(o, r) < 2e-6 and rel_err(dc.grad, dr.grad) < 2e-5
+    interior = (a > 1e-3) & (a < 1 - 1e-3)
+    assert rel_err(ac.grad.cpu()[interior], ar2.grad[interior]) < 2e-5
+
+
 def test_elementwise(be):
     a, b = g(1001, 256, seed=1), g(1001, 256, seed=2)
     out = torch.empty(1001, 256, device="cuda")
