@@ -801,7 +801,15 @@ class FFNBlockFn(Function):
             db1 = torch.zeros(F_, dtype=f32, device=dy.device)
             be.linear_bwd_data(dz_op, w2o, dh, relu_y=h, dbias=db1)
         dw1, _ = _wgrad(be, dh, xo, w1, None, True, False)
-        be.linear_bwd_data(dh, w1o, dz, accumulate=True)
+        if bf and R <= 128 and F_ >= 1024 and F_ % 256 == 0 and F_ // 256 <= 12:
+            # same contraction split as the forward's linear2: dz += dh W1 as 256-wide slices of one grouped launch
+            nsp = F_ // 256
+            parts = torch.empty(nsp, R, d, dtype=f32, device=dy.device)
+            be.linear_group(1, [dict(terms=[(dh[:, s * 256:(s + 1) * 256], w1o[s * 256:(s + 1) * 256], None)], out=parts[s])
+                                for s in range(nsp)])
+            dz += parts.sum(0)
+        else:
+            be.linear_bwd_data(dh, w1o, dz, accumulate=True)
         return dz, None, dw1, db1, dw2, db2, dg, dbt, None
 
 
