@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--T", type=int, default=64)
     ap.add_argument("--res", type=int, default=448)
     ap.add_argument("--L", type=int, default=16)
+    ap.add_argument("--dropout", type=float, default=0.0,
+                    help="MODEL.STCAT.DROPOUT of the train-mode step (default 0 = the parity / headline configuration; the "
+                         "reference's training default is 0.1, which routes attention through the dropout-capable SIMT kernels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step from a CUDA graph")
     ap.add_argument("--cpu-steps", type=int, default=2, help="timed CPU-baseline steps (bounded sample)")
@@ -64,12 +67,12 @@ def workload(args):
     return {"T": args.T, "res": args.res, "H": hw, "W": hw, "L": args.L}
 
 
-def make_cfg(T):
+def make_cfg(T, dropout=0.0):
     from stcat_b200.config import get_default_cfg
 
     cfg = get_default_cfg()
     # the two shipped experiment files' loss coefficients (experiments/*.yaml) and dropout 0 (parity policy)
-    cfg.merge_from_list(["INPUT.MAX_VIDEO_LEN", max(200, T), "MODEL.STCAT.DROPOUT", 0.0, "SOLVER.GIOU_COEF", 3,
+    cfg.merge_from_list(["INPUT.MAX_VIDEO_LEN", max(200, T), "MODEL.STCAT.DROPOUT", float(dropout), "SOLVER.GIOU_COEF", 3,
                          "SOLVER.TEMP_COEF", 10, "SOLVER.EOS_COEF", 0.3])
     return cfg
 
@@ -158,6 +161,8 @@ def cpu_reference_step_fn(args):
     from stcat_b200.param_spec import synthetic_params
 
     w = workload(args)
+    if args.dropout:
+        raise SystemExit("the CPU arm restates the reference at dropout 0 (the oracle has no dropout): drop --dropout")
     cfg = make_cfg(w["T"])
     torch.set_num_threads(os.cpu_count() or 1)
     P = synthetic_params(cfg, seed=0)
@@ -225,7 +230,7 @@ def build_b200(args, device):
 
     w = workload(args)
     rank = int(os.environ.get("RANK", "0"))
-    cfg = make_cfg(w["T"])
+    cfg = make_cfg(w["T"], args.dropout)
     ops.set_precision(args.precision)
     model = STCATHotPath(cfg).load_flat_params(synthetic_params(cfg, seed=0)).to(device).train()
     inp = synthetic.make_inputs([w["T"]], w["H"], w["W"], w["L"], seed=42 + rank)
@@ -602,7 +607,7 @@ def run_b200_arm(args):
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {
                 "workload": f"STCAT hot path fwd+bwd (ground_encoder+ground_decoder+heads+loss), 1 clip/GPU, "
-                            f"T={w['T']} res={w['res']} ({w['H']}x{w['W']} tokens) L={w['L']}, dropout 0, "
+                            f"T={w['T']} res={w['res']} ({w['H']}x{w['W']} tokens) L={w['L']}, dropout {args.dropout:g}, "
                             f"{'bf16 operands / fp32 accumulate+residual' if args.precision == 'bf16' else 'exact fp32'}",
                 "parallelism": f"dp{world}", "cuda_graph": graph is not None,
                 "l2": "per-step activations (>1 GB) and rotating GEMM buffers exceed the 126 MB L2; no explicit flush",
@@ -625,7 +630,7 @@ def run_b200_arm(args):
             "kernel_share": {"gemm": gemm_ms / max(sum(v["ms"] for v in breakdown["calls"].values()), 1e-9),
                              "attention": attn_ms / max(sum(v["ms"] for v in breakdown["calls"].values()), 1e-9)},
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not args.dropout:  # the oracle (CPU arm) has no dropout
             try:
                 v, sec = time_cpu(args, args.cpu_steps, 1)
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",

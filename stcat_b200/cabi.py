@@ -53,6 +53,12 @@ class _Job(ctypes.Structure):
                 ("out", c_void_p), ("ldo", c_int64), ("dbias", c_void_p)]
 
 
+_U64 = ctypes.c_uint64
+SIGNATURES["stcat_dropout"] = (c_int, [_P, _P, _I, _L, _F, _U64, _U64, _P])
+SIGNATURES["stcat_attention_dropout_fwd"] = (c_int, [_P, _P, _L, _P, _P, _L, _P, _L, _P, _L, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F,
+                                                     _F, _U64, _U64, _P])
+SIGNATURES["stcat_attention_dropout_bwd"] = (c_int, [_P, _P, _L, _P, _P, _L, _P, _L, _P, _L, _I, _P, _P, _P, _P, _P, _P, _L, _P, _P,
+                                                     _L, _P, _L, _I, _I, _I, _I, _I, _F, _F, _U64, _U64, _P])
 SIGNATURES["stcat_anchor_sine_fwd"] = (c_int, [_P, _P, _P, _L, _P])
 SIGNATURES["stcat_anchor_sine_bwd"] = (c_int, [_P, _P, _P, _L, _P])
 SIGNATURES["stcat_box_refine_fwd"] = (c_int, [_P, _P, _P, _L, _F, _P])
@@ -231,7 +237,14 @@ class CudaBackend:
         self.launches += 1
 
     # -- attention -----------------------------------------------------
-    def attention_fwd(self, q1, q2, k1, k2, v, o, key_mask, lse, p_avg, B, H, Lq, Lk, scale):
+    def dropout(self, x, out, p, seed, offset):
+        """out = dropout mask(seed, offset) applied to x (same call on the gradient = backward); in place allowed"""
+        assert x.is_contiguous() and out.is_contiguous() and x.dtype == out.dtype and x.shape == out.shape
+        self._rc(self.lib.stcat_dropout(self._flat(x, "x"), self._flat(out, "out"), _dt(x), x.numel(), float(p), int(seed), int(offset),
+                                        self._stream()), "dropout")
+        self.launches += 1
+
+    def attention_fwd(self, q1, q2, k1, k2, v, o, key_mask, lse, p_avg, B, H, Lq, Lk, scale, drop=None):
         """q*: [B*Lq, H*32] views, k*/v: [B*Lk, H*32] views, o: [B*Lq, H*32]; q2/k2 share q1/k1's leading dim."""
         (qp, ldq, qd) = self._mat(q1, "q1")
         (kp, ldk, _), (vp, ldv, _), (op, ldo, _) = self._mat(k1, "k1"), self._mat(v, "v"), self._mat(o, "o")
@@ -241,6 +254,13 @@ class CudaBackend:
             k2p, ldk2, _ = self._mat(k2, "k2")
             assert ldq2 == ldq and ldk2 == ldk
         assert q1.shape == (B * Lq, H * 32) and k1.shape == (B * Lk, H * 32) and v.shape == (B * Lk, H * 32)
+        if drop is not None and drop[0] > 0:  # (p, seed, offset): dropout on the probabilities
+            self._rc(self.lib.stcat_attention_dropout_fwd(
+                qp, q2p, ldq, kp, k2p, ldk, vp, ldv, op, ldo, qd, self._flat(key_mask, "key_mask", torch.uint8),
+                self._flat(lse, "lse", torch.float32), self._flat(p_avg, "p_avg", torch.float32), B, H, Lq, Lk, 32, float(scale),
+                float(drop[0]), int(drop[1]), int(drop[2]), self._stream()), "attention_dropout_fwd")
+            self.launches += 1
+            return
         self._rc(self.lib.stcat_attention_fwd(qp, q2p, ldq, kp, k2p, ldk, vp, ldv, op, ldo, qd,
                                               self._flat(key_mask, "key_mask", torch.uint8), self._flat(lse, "lse", torch.float32),
                                               self._flat(p_avg, "p_avg", torch.float32), B, H, Lq, Lk, 32, float(scale),
@@ -248,7 +268,7 @@ class CudaBackend:
         self.launches += 1
 
     def attention_bwd(self, q1, q2, k1, k2, v, d_o, key_mask, lse, dp_avg, delta, dq1, dq2, dk1, dk2, dv, B, H, Lq, Lk,
-                      scale, o=None):
+                      scale, o=None, drop=None):
         (qp, ldq, qd) = self._mat(q1, "q1")
         (kp, ldk, _), (vp, ldv, _), (gp, ldg, _) = self._mat(k1, "k1"), self._mat(v, "v"), self._mat(d_o, "d_o")
         (dqp, lddq, _), (dkp, lddk, _), (dvp, lddv, _) = self._mat(dq1, "dq1"), self._mat(dk1, "dk1"), self._mat(dv, "dv")
@@ -260,6 +280,14 @@ class CudaBackend:
             dk2p, lddk2, _ = self._mat(dk2, "dk2")
             assert ldq2 == ldq and ldk2 == ldk and lddq2 == lddq and lddk2 == lddk
         op, ldo = (None, 0) if o is None else self._mat(o, "o")[:2]
+        if drop is not None and drop[0] > 0:
+            self._rc(self.lib.stcat_attention_dropout_bwd(
+                qp, q2p, ldq, kp, k2p, ldk, vp, ldv, gp, ldg, qd, self._flat(key_mask, "key_mask", torch.uint8),
+                self._flat(lse, "lse", torch.float32), self._flat(dp_avg, "dp_avg", torch.float32),
+                self._flat(delta, "delta", torch.float32), dqp, dq2p, lddq, dkp, dk2p, lddk, dvp, lddv, B, H, Lq, Lk, 32,
+                float(scale), float(drop[0]), int(drop[1]), int(drop[2]), self._stream()), "attention_dropout_bwd")
+            self.launches += 2
+            return
         self._rc(self.lib.stcat_attention_bwd(qp, q2p, ldq, kp, k2p, ldk, vp, ldv, op, ldo, gp, ldg, qd,
                                               self._flat(key_mask, "key_mask", torch.uint8), self._flat(lse, "lse", torch.float32),
                                               self._flat(dp_avg, "dp_avg", torch.float32), self._flat(delta, "delta", torch.float32),

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(WARPS * 32)
 attn_fwd_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t ldq, const T* __restrict__ k1,
                 const T* __restrict__ k2, int64_t ldk, const T* __restrict__ v, int64_t ldv, T* __restrict__ o,
                 int64_t ldo, const uint8_t* __restrict__ key_mask, float* __restrict__ lse, float* __restrict__ p_avg,
-                int H, int Lq, int Lk, float scale) {
+                int H, int Lq, int Lk, float scale, const DropArgs drop) {
     __shared__ float Ks1[CH][DH + 1];
     __shared__ float Ks2[TWO ? CH : 1][DH + 1];
     __shared__ float Vs[CH][DH + 1];
@@ -101,6 +101,11 @@ attn_fwd_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t ldq,
                         corr = expf(m[r] - mnew);
                     }
                     l[r] = l[r] * corr + warp_sum(p0 + p1);
+                    if (drop.thresh) {  // dropout on the (normalised) probabilities: the row sum above stays undropped
+                        const uint64_t rowi = (((uint64_t)b * H + h) * Lq + i) * (uint64_t)Lk + c0;
+                        p0 = drop_apply(drop, rowi + lane, p0);
+                        p1 = drop_apply(drop, rowi + lane + 32, p1);
+                    }
                     float a = acc[r] * corr;
 #pragma unroll
                     for (int jj = 0; jj < 32; ++jj) a = fmaf(__shfl_sync(0xffffffffu, p0, jj), Vs[jj][lane], a);
@@ -115,6 +120,7 @@ attn_fwd_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t ldq,
                         const int j = c0 + lane + 32 * kk;
                         if (j < Lk) {
                             float p = (s[kk] == -INFINITY) ? 0.f : expf(s[kk] - lse_r[r]);
+                            if (drop.thresh) p = drop_apply(drop, (((uint64_t)b * H + h) * Lq + i) * (uint64_t)Lk + j, p);
                             atomicAdd(p_avg + ((int64_t)b * Lq + i) * Lk + j, p * invH);
                         }
                     }
@@ -143,7 +149,8 @@ attn_bwd_dq_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t l
                    const T* __restrict__ k2, int64_t ldk, const T* __restrict__ v, int64_t ldv,
                    const T* __restrict__ d_o, int64_t lddo, const uint8_t* __restrict__ key_mask,
                    const float* __restrict__ lse, const float* __restrict__ dp_avg, float* __restrict__ delta,
-                   T* __restrict__ dq1, T* __restrict__ dq2, int64_t lddq, int H, int Lq, int Lk, float scale) {
+                   T* __restrict__ dq1, T* __restrict__ dq2, int64_t lddq, int H, int Lq, int Lk, float scale,
+                   const DropArgs drop) {
     __shared__ float Ks1[CH][DH + 1];
     __shared__ float Ks2[TWO ? CH : 1][DH + 1];
     __shared__ float Vs[CH][DH + 1];
@@ -208,6 +215,8 @@ attn_bwd_dq_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t l
                     else {
                         p[kk] = expf(d * scale - lse_r[r]);
                         dp[kk] = e2 + (dp_avg ? dp_avg[((int64_t)b * Lq + i) * Lk + j] * invH : 0.f);
+                        // o and p_avg were formed from the DROPPED probabilities: their gradient reaches p through the mask
+                        if (drop.thresh) dp[kk] = drop_apply(drop, (((uint64_t)b * H + h) * Lq + i) * (uint64_t)Lk + j, dp[kk]);
                     }
                 }
                 if (pass == 0) {
@@ -257,7 +266,7 @@ attn_bwd_dkv_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t 
                     const T* __restrict__ d_o, int64_t lddo, const uint8_t* __restrict__ key_mask,
                     const float* __restrict__ lse, const float* __restrict__ dp_avg, const float* __restrict__ delta,
                     T* __restrict__ dk1, T* __restrict__ dk2, int64_t lddk, T* __restrict__ dv, int64_t lddv, int H,
-                    int Lq, int Lk, float scale) {
+                    int Lq, int Lk, float scale, const DropArgs drop) {
     __shared__ float Qs1[CH][DH + 1];
     __shared__ float Qs2[TWO ? CH : 1][DH + 1];
     __shared__ float dOs[CH][DH + 1];
@@ -304,7 +313,7 @@ attn_bwd_dkv_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t 
         for (int r = 0; r < R; ++r) {
             const int j = j0 + r;
             if (j >= Lk || masked[r]) continue;  // warp-uniform
-            float p[2], ds[2];
+            float p[2], ds[2], pm[2];  // pm = dropped probabilities (what multiplied V in the forward)
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
                 const int qi = lane + 32 * kk;
@@ -322,13 +331,19 @@ attn_bwd_dkv_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t 
                 if (i < Lq && lses[qi] != -INFINITY) {
                     p[kk] = expf(d * scale - lses[qi]);
                     float dp = e2 + (dp_avg ? dp_avg[((int64_t)b * Lq + i) * Lk + j] * invH : 0.f);
+                    pm[kk] = p[kk];
+                    if (drop.thresh) {
+                        const uint64_t idx = (((uint64_t)b * H + h) * Lq + i) * (uint64_t)Lk + j;
+                        dp = drop_apply(drop, idx, dp);
+                        pm[kk] = drop_apply(drop, idx, p[kk]);
+                    }
                     ds[kk] = p[kk] * (dp - dels[qi]) * scale;
-                } else { p[kk] = 0.f; ds[kk] = 0.f; }
+                } else { p[kk] = 0.f; ds[kk] = 0.f; pm[kk] = 0.f; }
             }
             float x1 = ak1[r], x2 = ak2[r], xv = av[r];
 #pragma unroll
             for (int ii = 0; ii < 32; ++ii) {
-                float p0 = __shfl_sync(0xffffffffu, p[0], ii), p1 = __shfl_sync(0xffffffffu, p[1], ii);
+                float p0 = __shfl_sync(0xffffffffu, pm[0], ii), p1 = __shfl_sync(0xffffffffu, pm[1], ii);
                 float s0 = __shfl_sync(0xffffffffu, ds[0], ii), s1 = __shfl_sync(0xffffffffu, ds[1], ii);
                 xv = fmaf(p0, dOs[ii][lane], xv);
                 xv = fmaf(p1, dOs[32 + ii][lane], xv);
@@ -356,11 +371,11 @@ attn_bwd_dkv_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t 
 template <typename T, bool TWO>
 static int launch_fwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2, int64_t ldk,
                       const void* v, int64_t ldv, void* o, int64_t ldo, const uint8_t* key_mask, float* lse,
-                      float* p_avg, int B, int H, int Lq, int Lk, float scale, cudaStream_t st) {
+                      float* p_avg, int B, int H, int Lq, int Lk, float scale, cudaStream_t st, const DropArgs drop = DropArgs()) {
     dim3 grid((Lq + TILE - 1) / TILE, H, B);
     attn_fwd_kernel<T, TWO><<<grid, WARPS * 32, 0, st>>>((const T*)q1, (const T*)q2, ldq, (const T*)k1, (const T*)k2,
                                                          ldk, (const T*)v, ldv, (T*)o, ldo, key_mask, lse, p_avg, H,
-                                                         Lq, Lk, scale);
+                                                         Lq, Lk, scale, drop);
     return check_launch("attn_fwd_kernel");
 }
 
@@ -369,18 +384,18 @@ static int launch_bwd(const void* q1, const void* q2, int64_t ldq, const void* k
                       const void* v, int64_t ldv, const void* d_o, int64_t lddo, const uint8_t* key_mask,
                       const float* lse, const float* dp_avg, float* delta, void* dq1, void* dq2, int64_t lddq,
                       void* dk1, void* dk2, int64_t lddk, void* dv, int64_t lddv, int B, int H, int Lq, int Lk,
-                      float scale, cudaStream_t st) {
+                      float scale, cudaStream_t st, const DropArgs drop = DropArgs()) {
     dim3 gq((Lq + TILE - 1) / TILE, H, B);
     attn_bwd_dq_kernel<T, TWO><<<gq, WARPS * 32, 0, st>>>((const T*)q1, (const T*)q2, ldq, (const T*)k1, (const T*)k2,
                                                           ldk, (const T*)v, ldv, (const T*)d_o, lddo, key_mask, lse,
-                                                          dp_avg, delta, (T*)dq1, (T*)dq2, lddq, H, Lq, Lk, scale);
+                                                          dp_avg, delta, (T*)dq1, (T*)dq2, lddq, H, Lq, Lk, scale, drop);
     int rc = check_launch("attn_bwd_dq_kernel");
     if (rc) return rc;
     dim3 gk((Lk + TILE - 1) / TILE, H, B);
     attn_bwd_dkv_kernel<T, TWO><<<gk, WARPS * 32, 0, st>>>((const T*)q1, (const T*)q2, ldq, (const T*)k1,
                                                            (const T*)k2, ldk, (const T*)v, ldv, (const T*)d_o, lddo,
                                                            key_mask, lse, dp_avg, delta, (T*)dk1, (T*)dk2, lddk,
-                                                           (T*)dv, lddv, H, Lq, Lk, scale);
+                                                           (T*)dv, lddv, H, Lq, Lk, scale, drop);
     return check_launch("attn_bwd_dkv_kernel");
 }
 
@@ -511,4 +526,47 @@ extern "C" int stcat_attention_bwd(const void* q1, const void* q2, int64_t ldq, 
         return q2 ? launch_bwd<__nv_bfloat16, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st)
                   : launch_bwd<__nv_bfloat16, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st);
     return set_err(STCAT_EINVAL, "attention_bwd: bad dtype %d", dtype);
+}
+
+// Attention with dropout on the probabilities (nn.MultiheadAttention dropout=p in train mode, torch functional.py;
+// reference attention.py:381): the generic SIMT kernels with the counter-based mask of common.cuh.  The `weights`
+// output (p_avg) is the head average of the DROPPED probabilities, as in the reference.
+extern "C" int stcat_attention_dropout_fwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2,
+                                           int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo, int dtype,
+                                           const uint8_t* key_mask, float* lse, float* p_avg, int B, int H, int Lq, int Lk,
+                                           int dh, float scale, float drop_p, uint64_t seed, uint64_t offset, void* stream) {
+    STCAT_REQUIRE(q1 && k1 && v && o && lse, STCAT_EINVAL, "attention_dropout_fwd: null pointer");
+    STCAT_REQUIRE((q2 == nullptr) == (k2 == nullptr), STCAT_EINVAL, "attention_dropout_fwd: q2/k2 must both be set or both NULL");
+    STCAT_REQUIRE(dh == DH && B >= 0 && H > 0 && Lq >= 0 && Lk > 0 && B <= 65535 && H <= 65535, STCAT_ESHAPE, "attention_dropout_fwd: bad sizes");
+    STCAT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, STCAT_EINVAL, "attention_dropout_fwd: p=%f", (double)drop_p);
+    STCAT_REQUIRE(dtype == STCAT_F32 || dtype == STCAT_BF16, STCAT_EINVAL, "attention_dropout_fwd: bad dtype %d", dtype);
+    if (B == 0 || Lq == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const DropArgs d = make_drop(drop_p, seed, offset);
+    if (dtype == STCAT_F32)
+        return q2 ? launch_fwd<float, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st, d)
+                  : launch_fwd<float, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st, d);
+    return q2 ? launch_fwd<__nv_bfloat16, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st, d)
+              : launch_fwd<__nv_bfloat16, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st, d);
+}
+
+extern "C" int stcat_attention_dropout_bwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2,
+                                           int64_t ldk, const void* v, int64_t ldv, const void* d_o, int64_t lddo, int dtype,
+                                           const uint8_t* key_mask, const float* lse, const float* dp_avg, float* delta,
+                                           void* dq1, void* dq2, int64_t lddq, void* dk1, void* dk2, int64_t lddk, void* dv,
+                                           int64_t lddv, int B, int H, int Lq, int Lk, int dh, float scale, float drop_p,
+                                           uint64_t seed, uint64_t offset, void* stream) {
+    STCAT_REQUIRE(q1 && k1 && v && d_o && lse && delta && dq1 && dk1 && dv, STCAT_EINVAL, "attention_dropout_bwd: null pointer");
+    STCAT_REQUIRE((q2 == nullptr) == (k2 == nullptr) && (!q2 || (dq2 && dk2)), STCAT_EINVAL, "attention_dropout_bwd: second score part");
+    STCAT_REQUIRE(dh == DH && B >= 0 && H > 0 && Lq >= 0 && Lk > 0 && B <= 65535 && H <= 65535, STCAT_ESHAPE, "attention_dropout_bwd: bad sizes");
+    STCAT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, STCAT_EINVAL, "attention_dropout_bwd: p=%f", (double)drop_p);
+    STCAT_REQUIRE(dtype == STCAT_F32 || dtype == STCAT_BF16, STCAT_EINVAL, "attention_dropout_bwd: bad dtype %d", dtype);
+    if (B == 0 || Lq == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const DropArgs d = make_drop(drop_p, seed, offset);
+    if (dtype == STCAT_F32)
+        return q2 ? launch_bwd<float, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st, d)
+                  : launch_bwd<float, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st, d);
+    return q2 ? launch_bwd<__nv_bfloat16, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st, d)
+              : launch_bwd<__nv_bfloat16, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st, d);
 }

@@ -82,6 +82,38 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// ---- train-mode dropout (nn.Dropout / F.dropout sites of the reference, modal_encoder.py:237-240, query_decoder.py:344,
+// 431-436, 612, 653-658, attention.py:381) ---------------------------------------------------------------------------
+// Counter-based: element `idx` of a site whose forward drew (seed, offset) is kept iff the top 24 bits of
+// splitmix64(offset + idx + seed * golden) are >= thresh = p * 2^24.  Stateless, so the backward regenerates the mask of
+// the forward from the same (seed, offset) -- no mask tensors in HBM.  tests/emu_backend.py restates it bit for bit.
+__host__ __device__ __forceinline__ uint32_t drop_bits24(uint64_t seed, uint64_t idx) {
+    uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (uint32_t)(z >> 40);
+}
+struct DropArgs {            // thresh == 0: no dropout
+    uint32_t thresh = 0;
+    float scale = 1.f;       // 1 / keep probability
+    uint64_t seed = 0, offset = 0;
+};
+inline DropArgs make_drop(float p, uint64_t seed, uint64_t offset) {
+    DropArgs d;
+    if (p > 0.f) {
+        double t = (double)p * 16777216.0;
+        d.thresh = t >= 16777215.0 ? 16777215u : (uint32_t)t;
+        d.scale = (float)(16777216.0 / (16777216.0 - (double)d.thresh));
+        d.seed = seed;
+        d.offset = offset;
+    }
+    return d;
+}
+__device__ __forceinline__ float drop_apply(const DropArgs& d, uint64_t idx, float v) {
+    return drop_bits24(d.seed, d.offset + idx) >= d.thresh ? v * d.scale : 0.f;
+}
+
 inline int num_sms() {
     static int n = 0;
     if (n == 0) {

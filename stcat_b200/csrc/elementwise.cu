@@ -283,6 +283,16 @@ __global__ void __launch_bounds__(256) box_refine_bwd_kernel(const float* __rest
     }
 }
 
+
+// out[i] = keep(i) ? x[i] / (1 - p) : 0  (forward and, with the same seed / offset on dy, backward of a dropout site)
+template <typename T>
+__global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n, const DropArgs d) {
+    pdl_launch_dependents();
+    pdl_wait();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = from_f32<T>(drop_apply(d, (uint64_t)i, to_f32<T>(x[i])));
+}
+
 }  // namespace stcat
 
 using namespace stcat;
@@ -372,4 +382,16 @@ extern "C" int stcat_box_refine_bwd(const float* out, const float* anchor, const
     if (n == 0) return 0;
     launch_pdl(box_refine_bwd_kernel, dim3(grid_for(n)), dim3(256), 0, (cudaStream_t)stream, out, anchor, g, ddelta, danchor, n, eps);
     return check_launch("box_refine_bwd_kernel");
+}
+
+extern "C" int stcat_dropout(const void* x, void* out, int dtype, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
+    STCAT_REQUIRE(x && out && n >= 0 && p >= 0.f && p < 1.f, STCAT_EINVAL, "dropout: bad arguments (p=%f)", (double)p);
+    if (n == 0) return 0;
+    const DropArgs d = make_drop(p, seed, offset);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == STCAT_F32) launch_pdl(dropout_kernel<float>, dim3(grid_for(n)), dim3(256), 0, st, (const float*)x, (float*)out, n, d);
+    else if (dtype == STCAT_BF16)
+        launch_pdl(dropout_kernel<__nv_bfloat16>, dim3(grid_for(n)), dim3(256), 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)out, n, d);
+    else return set_err(STCAT_EINVAL, "dropout: bad dtype %d", dtype);
+    return check_launch("dropout_kernel");
 }

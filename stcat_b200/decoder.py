@@ -151,8 +151,8 @@ def run_mlp(m: MLPP, x: torch.Tensor, training: bool = False, x_op=None) -> torc
         if training and p:
             # the reference applies dropout after EVERY layer of temp_embed / action_embed, the output
             # layer included (net_utils.py:23-25, p = 0.3 hard-wired at pipeline.py:42-47).  These are
-            # [nl*b*t, <=256] tensors; the mask comes from torch's Philox stream like the reference's.
-            x = torch.nn.functional.dropout(x, p, True)
+            # [nl*b*t, <=256] tensors; masks from the same counter-based stream as every other site (stcat_dropout).
+            x = ops.dropout(x, p)
     return x
 
 
@@ -210,6 +210,7 @@ class TransformerDecoderLayer(nn.Module):
         self.norm1, self.norm3, self.norm4 = NormP(d), NormP(d), NormP(d)
         self.nhead = nhead
         self.d = d
+        self.dropout_p = 0.0  # set by QueryDecoder (MODEL.STCAT.DROPOUT); active in train mode only
 
     def memory_side(self, c: _Ctx, is_first: bool):
         """Key / value projections of the encoder memory for this layer (query_decoder.py:355-366).  They do not
@@ -228,6 +229,7 @@ class TransformerDecoderLayer(nn.Module):
         cast once, by its producer where possible, not once per consuming Linear.  Intermediates that feed exactly
         one GEMM / attention (q, k, v, qc, qs) are written in the operand dtype by the producing epilogue."""
         d, H = self.d, self.nhead
+        p = self.dropout_p if self.training else 0.0  # query_decoder.py:269,286,293-303: attention, dropout1/3/4, FFN inner
         pos_op = ops.operand_copy(query_pos)
         # ---- temporal self attention over the t queries of each video (:329-345) ----
         L = lambda p: (p.weight, p.bias)
@@ -240,8 +242,8 @@ class TransformerDecoderLayer(nn.Module):
         Q, K, V = ops.linear_group(
             [(q, None), (k, None), (v, None)],
             [{"terms": [(i, sa.in_proj_weight, sa.in_proj_bias, (i * d, (i + 1) * d))], "out_bf16": True} for i in range(3)])
-        o, _ = ops.attention(Q, K, V, c.b, H, c.t, c.t, float(d // H) ** -0.5, key_mask=c.query_mask)
-        a = _lin(self.self_attn.out_proj, o)
+        o, _ = ops.attention(Q, K, V, c.b, H, c.t, c.t, float(d // H) ** -0.5, key_mask=c.query_mask, drop_p=p)
+        a = ops.dropout(_lin(self.self_attn.out_proj, o), p)
         tgt, tgt_op = ops.layer_norm(a, tgt, self.norm1.weight, self.norm1.bias, self.norm1.eps, want_op=True)
         # ---- time-aligned cross attention: query of frame f sees only frame f's tokens (:350-429) ----
         kc, kp, vv = mem_kv() if callable(mem_kv) else mem_kv
@@ -250,12 +252,12 @@ class TransformerDecoderLayer(nn.Module):
             [(tgt, tgt_op), (query_pos, pos_op), (query_sine, sine_op)],
             [{"terms": qc_terms, "out_bf16": True}, {"terms": [(2, *L(self.ca_qpos_sine_proj))], "out_bf16": True}])
         o, _ = ops.attention(c.frames(qc), kc, vv, c.n, H, 1, c.M, float(2 * d // H) ** -0.5, key_mask=c.key_mask,
-                             q2=c.frames(qs), k2=kp)
-        o = _lin(self.cross_attn.out_proj, o)
+                             q2=c.frames(qs), k2=kp, drop_p=p)
+        o = ops.dropout(_lin(self.cross_attn.out_proj, o), p)
         tgt, tgt_op = ops.layer_norm(c.padded(o), tgt, self.norm3.weight, self.norm3.bias, self.norm3.eps, want_op=True)
         # ---- FFN (:435-437) ----
         return ops.ffn_block(tgt, tgt_op, self.linear1.weight, self.linear1.bias, self.linear2.weight,
-                             self.linear2.bias, self.norm4.weight, self.norm4.bias, self.norm4.eps)
+                             self.linear2.bias, self.norm4.weight, self.norm4.bias, self.norm4.eps, drop_p=p)
 
 
 class TransformerDecoder(nn.Module):
@@ -321,6 +323,7 @@ class TimeDecoderLayer(nn.Module):
         self.norm1, self.norm3, self.norm4 = NormP(d), NormP(d), NormP(d)
         self.nhead = nhead
         self.d = d
+        self.dropout_p = 0.0  # set by QueryDecoder
 
     def memory_side(self, c: _Ctx):
         """nn.MultiheadAttention in-projection of key = memory + pos and value = memory (:633-639)."""
@@ -331,6 +334,7 @@ class TimeDecoderLayer(nn.Module):
     def run(self, c: _Ctx, tgt, tgt_op, query_pos, query_pos_frames, qpos_plus_time, mem_kv):
         d, H = self.d, self.nhead
         scale = float(d // H) ** -0.5
+        p = self.dropout_p if self.training else 0.0  # query_decoder.py:565-580
         qk = tgt + qpos_plus_time
         qk_op = ops.operand_copy(qk)  # one cast for the q and k projections
         sa = self.self_attn
@@ -338,17 +342,17 @@ class TimeDecoderLayer(nn.Module):
             [(qk, qk_op), (tgt, tgt_op)],
             [{"terms": [(0 if i < 2 else 1, sa.in_proj_weight, sa.in_proj_bias, (i * d, (i + 1) * d))], "out_bf16": True}
              for i in range(3)])
-        o, weights = ops.attention(Q, K, V, c.b, H, c.t, c.t, scale, key_mask=c.query_mask, need_pavg=True)
-        a = _lin(self.self_attn.out_proj, o)
+        o, weights = ops.attention(Q, K, V, c.b, H, c.t, c.t, scale, key_mask=c.query_mask, need_pavg=True, drop_p=p)
+        a = ops.dropout(_lin(self.self_attn.out_proj, o), p)
         tgt = ops.layer_norm(a, tgt, self.norm1.weight, self.norm1.bias, self.norm1.eps)
         # cross attention, one query per frame (:615-651)
         Q = _mha_proj(self.cross_attn_image, 0, c.frames(tgt) + query_pos_frames, out_bf16=True)
         K, V = mem_kv() if callable(mem_kv) else mem_kv
-        o, _ = ops.attention(Q, K, V, c.n, H, 1, c.M, scale, key_mask=c.key_mask)
-        o = _lin(self.cross_attn_image.out_proj, o)
+        o, _ = ops.attention(Q, K, V, c.n, H, 1, c.M, scale, key_mask=c.key_mask, drop_p=p)
+        o = ops.dropout(_lin(self.cross_attn_image.out_proj, o), p)
         tgt, tgt_op = ops.layer_norm(c.padded(o), tgt, self.norm3.weight, self.norm3.bias, self.norm3.eps, want_op=True)
         tgt, tgt_op = ops.ffn_block(tgt, tgt_op, self.linear1.weight, self.linear1.bias, self.linear2.weight,
-                                    self.linear2.bias, self.norm4.weight, self.norm4.bias, self.norm4.eps)
+                                    self.linear2.bias, self.norm4.weight, self.norm4.bias, self.norm4.eps, drop_p=p)
         return tgt, tgt_op, weights
 
 
@@ -416,12 +420,11 @@ class QueryDecoder(nn.Module):
         self.temp_decoder = TimeDecoder(d, S.HEADS, S.FFN_DIM, S.DEC_LAYERS)
         max_len = self.video_max_len + 1
         self.time_embed = LearnedTable(max_len, d) if S.USE_LEARN_TIME_EMBED else SineTable(max_len, d)
+        for layer in (*self.decoder.layers, *self.temp_decoder.layers):
+            layer.dropout_p = self.dropout_p
         xavier_reset(self)
 
     def forward(self, memory_cache: dict, vis_pos: Optional[torch.Tensor] = None, text_cls=None):
-        if self.training and self.dropout_p > 0:
-            raise NotImplementedError(
-                "train-mode dropout is not implemented by the sm_100a kernels yet: set MODEL.STCAT.DROPOUT 0.0")
         d = self.d_model
         mem_sf = memory_cache["encoded_memory"]  # [M, n, d]
         memory_mask = memory_cache["mask"]  # [n, M] bool

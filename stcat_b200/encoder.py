@@ -90,13 +90,15 @@ class TransformerEncoderLayer(nn.Module):
         self.dropout_p = dropout
 
     def run(self, x, x_op, pos, key_mask, B: int, L: int, pos_cls=None):
-        """x, pos: [B*L, d] batch-major rows.  Returns (y, y_op)."""
+        """x, pos: [B*L, d] batch-major rows.  Returns (y, y_op).  In train mode the four dropout sites of the reference
+        layer (attention probabilities, dropout1, the FFN's inner dropout, dropout2; modal_encoder.py:212-241) are active."""
         a = self.self_attn
+        p = self.dropout_p if self.training else 0.0
         x, x_op = ops.self_attn_block(x, x_op, pos, key_mask, a.in_proj_weight, a.in_proj_bias, a.out_proj.weight,
                                       a.out_proj.bias, self.norm1.weight, self.norm1.bias, B, L, self.nhead,
-                                      self.norm1.eps, pos_cls=pos_cls)
+                                      self.norm1.eps, pos_cls=pos_cls, drop_p=p)
         return ops.ffn_block(x, x_op, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias,
-                             self.norm2.weight, self.norm2.bias, self.norm2.eps)
+                             self.norm2.weight, self.norm2.bias, self.norm2.eps, drop_p=p)
 
 
 class SpatialTemporalEncoder(nn.Module):
@@ -166,10 +168,6 @@ class CrossModalEncoder(nn.Module):
         xavier_reset(self)
 
     def forward(self, videos=None, vis_pos: Optional[torch.Tensor] = None, texts: Optional[Tuple] = None) -> dict:
-        if self.training and self.dropout_p > 0:
-            raise NotImplementedError(
-                "train-mode dropout is not implemented by the sm_100a kernels yet: set MODEL.STCAT.DROPOUT 0.0 "
-                "(eval mode is unaffected)")
         vis_features, vis_mask, durations = videos.decompose()
         durations = list(durations)
         n, d, H, W = vis_features.shape

@@ -134,6 +134,56 @@ def _rows(x: torch.Tensor, k: int) -> torch.Tensor:
     return x2
 
 
+# ---- train-mode dropout ---------------------------------------------------------------------------------------------
+# Counter-based masks (include/stcat_b200.h, stcat_dropout): every dropout site of a forward pass reserves a range of the
+# stream identified by (seed, offset); its backward regenerates the same mask from the saved pair.  The offset is host
+# state, so a CUDA-graph replay would repeat the masks of the captured step: train with dropout eagerly (or re-capture).
+_drop_state = {"seed": None, "offset": 0}
+
+
+def set_dropout_seed(seed: int):
+    """(Re)start the dropout stream (also resets the offset): same seed -> same masks, used by the tests."""
+    _drop_state["seed"] = int(seed) & ((1 << 63) - 1)
+    _drop_state["offset"] = 0
+
+
+def _drop_reserve(n: int):
+    if _drop_state["seed"] is None:
+        set_dropout_seed(torch.initial_seed())
+    off = _drop_state["offset"]
+    _drop_state["offset"] = off + int(n)
+    return _drop_state["seed"], off
+
+
+class DropoutFn(Function):
+    """y = dropout(x, p) (train mode), mask regenerated in backward."""
+
+    @staticmethod
+    def forward(ctx, x, p: float):
+        be = get_backend()
+        xd = x.detach()
+        xd = xd if xd.is_contiguous() else xd.contiguous()
+        seed, off = _drop_reserve(xd.numel())
+        out = torch.empty_like(xd)
+        be.dropout(xd, out, p, seed, off)
+        ctx.meta = (p, seed, off)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        p, seed, off = ctx.meta
+        g = g if g.is_contiguous() else g.contiguous()
+        dg = torch.empty_like(g)
+        get_backend().dropout(g, dg, p, seed, off)
+        return dg, None
+
+
+def dropout(x, p: float):
+    """Train-mode dropout site (callers pass p = 0 in eval mode)."""
+    return x if not p else DropoutFn.apply(x, float(p))
+
+
 class LinearFn(Function):
     """y = act(x W[r0:r1]^T + b[r0:r1])  (r0/r1 = None: the whole parameter).  The row range lets the packed
     ``in_proj_weight`` of an MHA be used slice by slice without autograd slicing nodes."""
@@ -480,9 +530,13 @@ class AttentionFn(Function):
     """Batch-major multi-head attention core; see include/stcat_b200.h (stcat_attention_fwd)."""
 
     @staticmethod
-    def forward(ctx, q1, q2, k1, k2, v, key_mask, B, H, Lq, Lk, scale, need_pavg):
+    def forward(ctx, q1, q2, k1, k2, v, key_mask, B, H, Lq, Lk, scale, need_pavg, drop_p=0.0):
         be = get_backend()
         E = H * 32
+        ctx.drop = None
+        if drop_p:
+            seed, off = _drop_reserve(B * H * Lq * Lk)
+            ctx.drop = (float(drop_p), seed, off)
         two = q2 is not None
 
         def prep(t, L):
@@ -504,7 +558,7 @@ class AttentionFn(Function):
         o = torch.empty(B * Lq, E, dtype=tq1.dtype, device=q1.device)
         lse = torch.empty(B, H, Lq, dtype=torch.float32, device=q1.device)
         pavg = torch.zeros(B, Lq, Lk, dtype=torch.float32, device=q1.device) if need_pavg else None
-        be.attention_fwd(tq1, tq2, tk1, tk2, tv, o, key_mask, lse, pavg, B, H, Lq, Lk, scale)
+        be.attention_fwd(tq1, tq2, tk1, tk2, tv, o, key_mask, lse, pavg, B, H, Lq, Lk, scale, drop=ctx.drop)
         ctx.save_for_backward(tq1, tq2, tk1, tk2, tv, key_mask, lse)
         ctx.dims = (B, H, Lq, Lk, scale)
         ctx.in_dtypes = (q1.dtype, k1.dtype, v.dtype)
@@ -533,16 +587,17 @@ class AttentionFn(Function):
         dq1, dk1, dv = mk(Lq), mk(Lk), mk(Lk)
         dq2, dk2 = (mk(Lq), mk(Lk)) if two else (None, None)
         be.attention_bwd(tq1, tq2, tk1, tk2, tv, g, key_mask, lse, d_pavg, delta, dq1, dq2, dk1, dk2, dv, B, H, Lq, Lk,
-                         scale)
+                         scale, drop=ctx.drop)
         qd, kd, vd = ctx.in_dtypes
         cast = lambda t, d: None if t is None else (t if t.dtype == d else t.to(d))
         return (cast(dq1, qd), cast(dq2, qd), cast(dk1, kd), cast(dk2, kd), cast(dv, vd), None, None, None, None, None,
-                None, None)
+                None, None, None)
 
 
-def attention(q1, k1, v, B, H, Lq, Lk, scale, key_mask=None, q2=None, k2=None, need_pavg=False):
-    """Returns (o [B*Lq, H*32], p_avg [B,Lq,Lk] or None).  key_mask: uint8 [B, Lk], nonzero = masked."""
-    return AttentionFn.apply(q1, q2, k1, k2, v, key_mask, B, H, Lq, Lk, float(scale), need_pavg)
+def attention(q1, k1, v, B, H, Lq, Lk, scale, key_mask=None, q2=None, k2=None, need_pavg=False, drop_p=0.0):
+    """Returns (o [B*Lq, H*32], p_avg [B,Lq,Lk] or None).  key_mask: uint8 [B, Lk], nonzero = masked.  drop_p > 0:
+    train-mode dropout on the probabilities (the returned p_avg then averages the dropped probabilities)."""
+    return AttentionFn.apply(q1, q2, k1, k2, v, key_mask, B, H, Lq, Lk, float(scale), need_pavg, float(drop_p))
 
 
 class AddFn(Function):
@@ -627,9 +682,16 @@ class SelfAttnBlockFn(Function):
     """
 
     @staticmethod
-    def forward(ctx, x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps, pos_cls=None):
+    def forward(ctx, x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps, pos_cls=None, drop_p=0.0):
         be = get_backend()
         ctx.has_pos_cls = pos_cls is not None
+        # train-mode dropout (modal_encoder.py:212,237): on the attention probabilities and on the block output before
+        # the residual; (p, seed, offset) per site, regenerated in backward
+        ctx.drop_attn = ctx.drop_out = None
+        if drop_p:
+            R_ = x.shape[0]
+            ctx.drop_attn = (float(drop_p),) + _drop_reserve(B * H * L * L)
+            ctx.drop_out = (float(drop_p),) + _drop_reserve(R_ * x.shape[1])
         R, d = x.shape
         assert R == B * L and x.is_contiguous() and pos.shape == x.shape
         od = _opdtype()
@@ -655,9 +717,11 @@ class SelfAttnBlockFn(Function):
         lse = torch.empty(B, H, L, dtype=torch.float32, device=x.device)
         scale = float(d // H) ** -0.5
         be.attention_fwd(qkv[:, :d], None, qkv[:, d:2 * d], None, qkv[:, 2 * d:], o, key_mask, lse, None, B, H, L, L,
-                         scale)
+                         scale, drop=ctx.drop_attn)
         a = _new(R, d, torch.float32, x)
         be.linear_fwd(o, wo, b_out.detach(), a)
+        if ctx.drop_out:
+            be.dropout(a, a, *ctx.drop_out)
         y = _new(R, d, torch.float32, x)
         y_op = _new(R, d, od, x) if bf else None
         mean = torch.empty(R, dtype=torch.float32, device=x.device)
@@ -675,7 +739,7 @@ class SelfAttnBlockFn(Function):
     @once_differentiable
     def backward(ctx, dy, _unused):
         if dy is None:
-            return (None,) * 15
+            return (None,) * 16
         be = get_backend()
         xd, xo, qk_in, qkv, o, lse, a, mean, rstd, key_mask, w_in, w_out, gamma = ctx.saved_tensors
         B, L, H, scale = ctx.dims
@@ -688,15 +752,24 @@ class SelfAttnBlockFn(Function):
         b_in, b_out, beta = ctx.extra
         dz = _new(R, d, f32, dy)  # grad wrt (a) and wrt the residual x
         bf = od == torch.bfloat16
-        dz_op = _new(R, d, od, dy) if bf else dz  # LayerNorm backward writes the bf16 operand copy itself
-        dg, dbt, dbo = _ln_bwd(be, dy, a, xd, gamma, beta, mean, rstd, dz, dz_op if bf else None, b_out)
-        dwo, _ = _wgrad(be, dz_op, o, w_out, None, True, False)
+        if ctx.drop_out:
+            # the out-projection branch sees dz through the dropout mask of the forward; the residual branch sees dz itself
+            dg, dbt, _ = _ln_bwd(be, dy, a, xd, gamma, beta, mean, rstd, dz)
+            dza = _new(R, d, f32, dy)
+            be.dropout(dz, dza, *ctx.drop_out)
+            dz_op = _cast_op(be, dza)
+            dwo, dbo = _wgrad(be, dz_op, o, w_out, b_out, True, True)
+        else:
+            dz_op = _new(R, d, od, dy) if bf else dz  # LayerNorm backward writes the bf16 operand copy itself
+            dg, dbt, dbo = _ln_bwd(be, dy, a, xd, gamma, beta, mean, rstd, dz, dz_op if bf else None, b_out)
+            dwo, _ = _wgrad(be, dz_op, o, w_out, None, True, False)
         d_o = _new(R, d, od, dy)
         be.linear_bwd_data(dz_op, wo, d_o)
         dqkv = _new(R, 3 * d, od, dy)
         delta = torch.empty(B, H, L, dtype=f32, device=dy.device)
         be.attention_bwd(qkv[:, :d], None, qkv[:, d:2 * d], None, qkv[:, 2 * d:], d_o, key_mask, lse, None, delta,
-                         dqkv[:, :d], None, dqkv[:, d:2 * d], None, dqkv[:, 2 * d:], B, H, L, L, scale, o=o)
+                         dqkv[:, :d], None, dqkv[:, d:2 * d], None, dqkv[:, 2 * d:], B, H, L, L, scale, o=o,
+                         drop=ctx.drop_attn)
         if _fuse_grads and w_in.grad is not None and b_in.grad is not None:
             gwi, gbi = w_in.grad, b_in.grad
             dwi = dbi = None
@@ -724,7 +797,7 @@ class SelfAttnBlockFn(Function):
             srow = dqkv.view(B, L, 3 * d)[:, 0, : 2 * d].float().sum(0, keepdim=True)
             dpc = torch.empty(1, d, dtype=f32, device=dy.device)
             be.linear_bwd_data(srow, w_in.detach()[: 2 * d], dpc)
-        return dz, None, dpos, None, dwi, dbi, dwo, dbo, dg, dbt, None, None, None, None, dpc
+        return dz, None, dpos, None, dwi, dbi, dwo, dbo, dg, dbt, None, None, None, None, dpc, None
 
 
 class FFNBlockFn(Function):
@@ -732,10 +805,16 @@ class FFNBlockFn(Function):
     657-659).  x [R, d] fp32.  Returns (y, y_op) like SelfAttnBlockFn."""
 
     @staticmethod
-    def forward(ctx, x, x_op, w1, b1, w2, b2, gamma, beta, eps):
+    def forward(ctx, x, x_op, w1, b1, w2, b2, gamma, beta, eps, drop_p=0.0):
         be = get_backend()
         R, d = x.shape
         F_ = w1.shape[0]
+        # train-mode dropout (modal_encoder.py:239-240; query_decoder.py:435-436, 657-658): on relu(linear1) and on the
+        # block output before the residual
+        ctx.drop_h = ctx.drop_out = None
+        if drop_p:
+            ctx.drop_h = (float(drop_p),) + _drop_reserve(R * F_)
+            ctx.drop_out = (float(drop_p),) + _drop_reserve(R * d)
         od = _opdtype()
         bf = od == torch.bfloat16
         xd = x.detach()
@@ -747,6 +826,8 @@ class FFNBlockFn(Function):
         w1o, w2o = _operand(w1.detach(), True), _operand(w2.detach(), True)
         h = _new(R, F_, od, x)
         be.linear_fwd(xo, w1o, b1.detach(), h, relu=True)
+        if ctx.drop_h:
+            be.dropout(h, h, *ctx.drop_h)
         if bf and R <= 128 and F_ >= 1024 and F_ % 256 == 0 and F_ // 256 <= 12:
             # few rows, long contraction (decoder / temporal FFN: [t, 2048] x [2048, 256]): one CTA per output tile would
             # walk 32 k-blocks alone.  Split the contraction into 256-wide slices, one job each in ONE grouped launch
@@ -761,6 +842,8 @@ class FFNBlockFn(Function):
         else:
             yl = _new(R, d, torch.float32, x)
             be.linear_fwd(h, w2o, b2.detach(), yl)
+        if ctx.drop_out:
+            be.dropout(yl, yl, *ctx.drop_out)
         y = _new(R, d, torch.float32, x)
         y_op = _new(R, d, od, x) if bf else None
         mean = torch.empty(R, dtype=torch.float32, device=x.device)
@@ -777,7 +860,7 @@ class FFNBlockFn(Function):
     @once_differentiable
     def backward(ctx, dy, _unused):
         if dy is None:
-            return (None,) * 9
+            return (None,) * 10
         be = get_backend()
         xd, xo, h, yl, mean, rstd, w1, w2, gamma = ctx.saved_tensors
         R, d = xd.shape
@@ -789,11 +872,24 @@ class FFNBlockFn(Function):
         b1, b2, beta = ctx.extra
         dz = _new(R, d, f32, dy)
         bf = od == torch.bfloat16
+        dh = _new(R, F_, od, dy)
+        if ctx.drop_out:
+            # dropout mode: the linear2 branch sees dz through the output mask; dh = (dza W2) * relu mask, then the
+            # hidden mask; bias gradients from the masked tensors (no fused column sums)
+            dg, dbt, _ = _ln_bwd(be, dy, yl, xd, gamma, beta, mean, rstd, dz)
+            dza = _new(R, d, f32, dy)
+            be.dropout(dz, dza, *ctx.drop_out)
+            dz_op = _cast_op(be, dza)
+            dw2, db2 = _wgrad(be, dz_op, h, w2, b2, True, True)
+            be.linear_bwd_data(dz_op, w2o, dh, relu_y=h)
+            be.dropout(dh, dh, *ctx.drop_h)
+            dw1, db1 = _wgrad(be, dh, xo, w1, b1, True, True)
+            be.linear_bwd_data(dh, w1o, dz, accumulate=True)
+            return dz, None, dw1, db1, dw2, db2, dg, dbt, None, None
         dz_op = _new(R, d, od, dy) if bf else dz
         dg, dbt, db2 = _ln_bwd(be, dy, yl, xd, gamma, beta, mean, rstd, dz, dz_op if bf else None, b2)
         dw2, _ = _wgrad(be, dz_op, h, w2, None, True, False)
         # dh = (dz W2) * (h > 0) with db1 = colsum(dh): ReLU backward and the bias gradient ride in the dgrad epilogue
-        dh = _new(R, F_, od, dy)
         if _fuse_grads and b1.grad is not None:
             db1 = None
             be.linear_bwd_data(dz_op, w2o, dh, relu_y=h, dbias=b1.grad)
@@ -810,17 +906,17 @@ class FFNBlockFn(Function):
             dz += parts.sum(0)
         else:
             be.linear_bwd_data(dh, w1o, dz, accumulate=True)
-        return dz, None, dw1, db1, dw2, db2, dg, dbt, None
+        return dz, None, dw1, db1, dw2, db2, dg, dbt, None, None
 
 
-def self_attn_block(x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps=1e-5, pos_cls=None):
+def self_attn_block(x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps=1e-5, pos_cls=None, drop_p=0.0):
     """``pos_cls`` ([1, d], optional): the parameter that row 0 of every sequence of ``pos`` was copied from; when
     given, ``pos`` itself is treated as a constant and the gradient goes to ``pos_cls`` directly."""
-    return SelfAttnBlockFn.apply(x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps, pos_cls)
+    return SelfAttnBlockFn.apply(x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps, pos_cls, float(drop_p))
 
 
-def ffn_block(x, x_op, w1, b1, w2, b2, gamma, beta, eps=1e-5):
-    return FFNBlockFn.apply(x, x_op, w1, b1, w2, b2, gamma, beta, eps)
+def ffn_block(x, x_op, w1, b1, w2, b2, gamma, beta, eps=1e-5, drop_p=0.0):
+    return FFNBlockFn.apply(x, x_op, w1, b1, w2, b2, gamma, beta, eps, float(drop_p))
 
 
 class TakeRowsFn(Function):

@@ -17,6 +17,33 @@ def _store(dst, val):
     dst.copy_(val.to(dst.dtype))
 
 
+_M64 = (1 << 64) - 1
+
+
+def _s64(v):
+    """python int (mod 2^64) -> the int64 with the same bit pattern"""
+    v &= _M64
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def _lsr(z, k):
+    """logical shift right of an int64 tensor (torch's >> is arithmetic)"""
+    return (z >> k) & ((1 << (64 - k)) - 1)
+
+
+def drop_keep_scale(n, p, seed, offset, device="cpu"):
+    """Bit-exact restatement of drop_bits24 / make_drop (csrc/common.cuh): (keep mask [n] bool, scale)."""
+    t = int(float(torch.tensor(p, dtype=torch.float32)) * 16777216.0)  # the C ABI takes p as a float
+    t = min(t, 16777215)
+    idx = torch.arange(n, dtype=torch.int64, device=device)
+    z = idx + _s64(offset + seed * 0x9E3779B97F4A7C15)
+    z = (z ^ _lsr(z, 30)) * _s64(0xBF58476D1CE4E5B9)
+    z = (z ^ _lsr(z, 27)) * _s64(0x94D049BB133111EB)
+    z = z ^ _lsr(z, 31)
+    bits = _lsr(z, 40)
+    return bits >= t, float(16777216.0 / (16777216.0 - t))
+
+
 class EmuBackend:
     name = "emu"
 
@@ -120,9 +147,24 @@ class EmuBackend:
             s = s.masked_fill(key_mask.bool()[:, None, None, :], float("-inf"))
         return s, hd
 
-    def attention_fwd(self, q1, q2, k1, k2, v, o, key_mask, lse, p_avg, B, H, Lq, Lk, scale):
+    def dropout(self, x, out, p, seed, offset):
+        keep, sc = drop_keep_scale(x.numel(), p, seed, offset, x.device)
+        _store(out, (_f(x).reshape(-1) * keep * sc).reshape(x.shape))
+        self.launches += 1
+
+    @staticmethod
+    def _pmask(drop, B, H, Lq, Lk, device):
+        if drop is None or drop[0] <= 0:
+            return None
+        keep, sc = drop_keep_scale(B * H * Lq * Lk, drop[0], drop[1], drop[2], device)
+        return keep.reshape(B, H, Lq, Lk).float() * sc
+
+    def attention_fwd(self, q1, q2, k1, k2, v, o, key_mask, lse, p_avg, B, H, Lq, Lk, scale, drop=None):
         s, hd = self._scores(q1, q2, k1, k2, key_mask, B, H, Lq, Lk, scale)
         p = torch.softmax(s, -1)
+        m = self._pmask(drop, B, H, Lq, Lk, p.device)
+        if m is not None:
+            p = p * m
         out = (p @ hd(v, Lk)).permute(0, 2, 1, 3).reshape(B * Lq, H * 32)
         _store(o, out)
         lse.copy_(torch.logsumexp(s, -1))
@@ -131,18 +173,23 @@ class EmuBackend:
         self.launches += 1
 
     def attention_bwd(self, q1, q2, k1, k2, v, d_o, key_mask, lse, dp_avg, delta, dq1, dq2, dk1, dk2, dv, B, H, Lq, Lk,
-                      scale, o=None):
+                      scale, o=None, drop=None):
         s, hd = self._scores(q1, q2, k1, k2, key_mask, B, H, Lq, Lk, scale)
         p = torch.exp(s - lse[..., None])
         g = hd(d_o, Lq)
         dp = g @ hd(v, Lk).transpose(-1, -2)
         if dp_avg is not None:
             dp = dp + dp_avg[:, None] / H
+        m = self._pmask(drop, B, H, Lq, Lk, p.device)
+        pm = p
+        if m is not None:  # o and p_avg were formed from p * m
+            dp = dp * m
+            pm = p * m
         dl = (p * dp).sum(-1, keepdim=True)
         delta.copy_(dl.squeeze(-1))
         ds = p * (dp - dl) * scale
         un = lambda t, L: t.permute(0, 2, 1, 3).reshape(B * L, H * 32)
-        _store(dv, un(p.transpose(-1, -2) @ g, Lk))
+        _store(dv, un(pm.transpose(-1, -2) @ g, Lk))
         _store(dq1, un(ds @ hd(k1, Lk), Lq))
         _store(dk1, un(ds.transpose(-1, -2) @ hd(q1, Lq), Lk))
         if q2 is not None:

@@ -266,3 +266,48 @@ def test_fused_loss_kernel_matches_torch_restatement(durs, aux):
     for k in leaves:
         ref = gt[k] if gt[k] is not None else torch.zeros_like(gf[k])
         assert rel_err(gf[k], ref) < 1e-4, k
+
+
+def test_train_mode_dropout_matches_host_emulation():
+    """Train mode with the reference's default MODEL.STCAT.DROPOUT 0.1 (+ the 0.3 of the temporal heads): the dropout masks
+    are a counter-based stream (stcat_dropout), so the CUDA path and the torch emulation of the C ABI (tests/emu_backend.py,
+    CPU) draw bit-identical masks for the same seed and must agree on the loss (1e-3) and on the gradients (1e-2, see the
+    module docstring) -- which pins every dropout site's forward scaling and its backward."""
+    from emu_backend import EmuBackend
+    from stcat_b200.loss import STGLossPlan
+    from stcat_b200.pipeline import STCATHotPath
+
+    spec = load_golden("b2_ragged_T5_3")["spec"]
+    cfg = cfg_for(spec, dropout=0.1)
+    inp = case_inputs(spec)
+    tg = synthetic.make_targets(spec["durations"], seed=spec["seed"])
+    P = case_params(cfg, spec)
+
+    def run(dev, seed):
+        ops.clear_weight_cache()
+        m = STCATHotPath(cfg).load_flat_params(P).to(dev).train()
+        ops.set_dropout_seed(seed)
+        mv = lambda x: x.to(dev)
+        vis = mv(inp["vis_features"]).requires_grad_(True)
+        out = m(NestedTensor(vis, mv(inp["vis_mask"]), inp["durations"]), mv(inp["vis_pos"]),
+                (mv(inp["text_mask"]), mv(inp["text_memory"]), None))
+        plan = STGLossPlan(cfg, tg["boxes"], tg["actioness"], spec["durations"], dev)
+        total = plan(out)[0] if dev == "cuda" else plan.torch_restatement(out)[0]
+        total.backward()
+        g = {k: p.grad.detach().cpu() for k, p in m.named_parameters() if p.grad is not None}
+        g["__vis"] = vis.grad.detach().cpu()
+        return float(total), g
+
+    l_gpu, g_gpu = run("cuda", 5)
+    l_gpu2, _ = run("cuda", 5)
+    l_gpu3, _ = run("cuda", 6)
+    assert l_gpu == l_gpu2 and l_gpu != l_gpu3  # the seed fixes the masks
+    ops.set_backend(EmuBackend())
+    try:
+        l_cpu, g_cpu = run("cpu", 5)
+    finally:
+        ops.set_backend(None)
+    assert abs(l_gpu - l_cpu) < TOL * abs(l_cpu), (l_gpu, l_cpu)
+    assert g_gpu.keys() == g_cpu.keys()
+    for k in g_cpu:
+        assert rel_err(g_gpu[k], g_cpu[k]) < 1e-2 or float((g_gpu[k] - g_cpu[k]).abs().max()) < 1e-6, (k, rel_err(g_gpu[k], g_cpu[k]))

@@ -301,3 +301,94 @@ def test_map2d_pool(be):
     out = torch.empty(B, d, N, N, device="cuda")
     be.map2d_pool(x.cuda(), mask2d.to(torch.uint8).cuda(), out)
     assert torch.equal(out.cpu(), ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dropout_mask_is_the_counter_based_stream(be, dtype):
+    """stcat_dropout keeps element i iff the top 24 bits of splitmix64(seed + offset + i) reach p * 2^24: bit-for-bit the
+    mask tests/emu_backend.drop_keep_scale builds on the host (which is checked against a pure-python splitmix64)."""
+    from emu_backend import drop_keep_scale
+
+    n, p, seed, off = 100003, 0.1, 0x1234567, 987654321
+    keep, sc = drop_keep_scale(n, p, seed, off)
+    x = g(n, seed=1).to(dtype)
+    out = torch.empty(n, device="cuda", dtype=dtype)
+    be.dropout(x.cuda(), out, p, seed, off)
+    want = (x.float() * keep.float() * sc).to(dtype)
+    assert torch.equal(out.cpu(), want)
+    assert abs(float(keep.float().mean()) - (1 - p)) < 5e-3
+    xin = x.cuda()
+    be.dropout(xin, xin, p, seed, off)  # in place
+    assert torch.equal(xin.cpu(), want)
+    be.dropout(x.cuda(), out, 0.0, seed, off)  # p = 0: identity
+    assert torch.equal(out.cpu(), x)
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,two,use_mask,use_pavg,bf16", [
+    (2, 8, 50, 77, False, True, True, False),
+    (2, 8, 213, 213, False, True, False, False),   # the encoder's spatial attention shape
+    (3, 8, 1, 212, True, True, False, False),      # time-aligned single-query cross-attention
+    (1, 8, 64, 64, False, False, True, False),     # decoder self-attention / time decoder with the weights output
+    (2, 4, 17, 130, True, True, True, False),
+    (2, 8, 65, 65, False, True, True, True),
+    (1, 8, 213, 213, False, False, False, True),
+])
+def test_attention_with_dropout(be, B, H, Lq, Lk, two, use_mask, use_pavg, bf16):
+    """stcat_attention_dropout_fwd/_bwd against float64 attention with the explicit keep mask multiplied into the
+    probabilities (torch's multi_head_attention_forward: dropout after the softmax, the returned weights are the dropped ones)."""
+    from emu_backend import drop_keep_scale
+
+    p, seed, off = 0.1, 77, 1 << 33
+    E = H * 32
+    dt = torch.bfloat16 if bf16 else torch.float32
+    scale = (64 if two else 32) ** -0.5
+    t = lambda L, s: g(B * L, E, seed=s).to(dt)
+    q1, k1, v = t(Lq, 1), t(Lk, 2), t(Lk, 3)
+    q2, k2 = (t(Lq, 4), t(Lk, 5)) if two else (None, None)
+    mask = None
+    if use_mask:
+        mask = torch.zeros(B, Lk, dtype=torch.uint8)
+        for b in range(B):
+            mask[b, Lk - 1 - 3 * b:] = 1
+            mask[b, 0] = 0
+    d_o = t(Lq, 6)
+    dpavg = g(B, Lq, Lk, seed=7) if use_pavg else None
+    keep, sc = drop_keep_scale(B * H * Lq * Lk, p, seed, off)
+    km = (keep.double() * sc).view(B, H, Lq, Lk)
+    leaves = [x.double().requires_grad_(True) if x is not None else None for x in (q1, q2, k1, k2, v)]
+    hd = lambda x, L: x.view(B, L, H, 32).permute(0, 2, 1, 3)
+    s = hd(leaves[0], Lq) @ hd(leaves[2], Lk).transpose(-1, -2)
+    if two:
+        s = s + hd(leaves[1], Lq) @ hd(leaves[3], Lk).transpose(-1, -2)
+    s = s * scale
+    if mask is not None:
+        s = s.masked_fill(mask.bool()[:, None, None, :], float("-inf"))
+    pr = torch.softmax(s, -1) * km
+    o_ref = (pr @ hd(leaves[4], Lk)).permute(0, 2, 1, 3).reshape(B * Lq, E)
+    loss = (o_ref * d_o.double()).sum()
+    if use_pavg:
+        loss = loss + (pr.mean(1) * dpavg.double()).sum()
+    loss.backward()
+
+    c = lambda x: None if x is None else x.cuda()
+    o = torch.empty(B * Lq, E, device="cuda", dtype=dt)
+    lse = torch.empty(B, H, Lq, device="cuda")
+    pavg = torch.zeros(B, Lq, Lk, device="cuda") if use_pavg else None
+    drop = (p, seed, off)
+    be.attention_fwd(c(q1), c(q2), c(k1), c(k2), c(v), o, c(mask), lse, pavg, B, H, Lq, Lk, scale, drop=drop)
+    tol_o, tol_g = (6e-3, 1e-2) if bf16 else (TOL32, 5e-5)
+    assert rel_err(o, o_ref) < tol_o
+    assert rel_err(lse, torch.logsumexp(s, -1)) < TOL32  # the statistics are those of the undropped softmax
+    if use_pavg:
+        assert rel_err(pavg, pr.mean(1)) < TOL32
+    e = lambda L: torch.empty(B * L, E, device="cuda", dtype=dt)
+    dq1, dk1, dv = e(Lq), e(Lk), e(Lk)
+    dq2, dk2 = (e(Lq), e(Lk)) if two else (None, None)
+    be.attention_bwd(c(q1), c(q2), c(k1), c(k2), c(v), c(d_o), c(mask), lse, c(dpavg), torch.empty(B, H, Lq, device="cuda"),
+                     dq1, dq2, dk1, dk2, dv, B, H, Lq, Lk, scale, drop=drop)
+    assert rel_err(dq1, leaves[0].grad) < tol_g
+    assert rel_err(dk1, leaves[2].grad) < tol_g
+    assert rel_err(dv, leaves[4].grad) < tol_g
+    if two:
+        assert rel_err(dq2, leaves[1].grad) < tol_g
+        assert rel_err(dk2, leaves[3].grad) < tol_g

@@ -131,3 +131,154 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "clips/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# train-mode dropout (counter-based masks regenerated in backward)
+# ---------------------------------------------------------------------------------------------------------------------
+def test_dropout_mask_statistics_and_backward_consistency():
+    ops.set_dropout_seed(7)
+    x = torch.ones(200, 256, requires_grad=True)
+    y = ops.dropout(x, 0.3)
+    kept = (y != 0).float().mean().item()
+    assert abs(kept - 0.7) < 0.01 and abs(y.mean().item() - 1.0) < 0.02
+    assert torch.allclose(y[y != 0], torch.full_like(y[y != 0], 1 / 0.7), rtol=1e-6)
+    g = torch.randn(200, 256, generator=torch.Generator().manual_seed(1))
+    y.backward(g)
+    assert torch.equal(x.grad != 0, y != 0)  # the backward mask is the forward mask
+    assert torch.allclose(x.grad, g * y.detach(), rtol=1e-6)  # y = mask * scale on ones
+    y2 = ops.dropout(x, 0.3)  # the next site draws a different part of the stream
+    assert not torch.equal(y2 != 0, y != 0)
+    ops.set_dropout_seed(7)
+    assert torch.equal(ops.dropout(x, 0.3), y)  # same seed -> same mask
+    assert ops.dropout(x, 0.0) is x
+
+
+def test_attention_dropout_matches_explicit_mask():
+    from emu_backend import drop_keep_scale
+
+    B, H, Lq, Lk, p = 2, 8, 5, 7, 0.25
+    E = H * 32
+    mk = lambda L, s: _leaf(B * L, E, seed=s)
+    q, k, v = mk(Lq, 1), mk(Lk, 2), mk(Lk, 3)
+    go = torch.randn(B * Lq, E, generator=torch.Generator().manual_seed(4))
+    gw = torch.randn(B, Lq, Lk, generator=torch.Generator().manual_seed(5))
+    ops.set_dropout_seed(99)
+    o, w = ops.attention(q, k, v, B, H, Lq, Lk, 32 ** -0.5, need_pavg=True, drop_p=p)
+    ((o * go).sum() + (w * gw).sum()).backward()
+    got = (o.detach(), w.detach(), q.grad.clone(), k.grad.clone(), v.grad.clone())
+    q.grad = k.grad = v.grad = None
+    keep, sc = drop_keep_scale(B * H * Lq * Lk, p, 99, 0)
+    m = keep.reshape(B, H, Lq, Lk).float() * sc
+    hd = lambda t, L: t.reshape(B, L, H, 32).permute(0, 2, 1, 3)
+    pr = torch.softmax(hd(q, Lq) @ hd(k, Lk).transpose(-1, -2) * 32 ** -0.5, -1) * m
+    o_ref = (pr @ hd(v, Lk)).permute(0, 2, 1, 3).reshape(B * Lq, E)
+    w_ref = pr.mean(1)
+    ((o_ref * go).sum() + (w_ref * gw).sum()).backward()
+    for a, b in zip(got, (o_ref, w_ref, q.grad, k.grad, v.grad)):
+        assert rel_err(a, b) < 1e-5
+
+
+def _masks(sizes, p, seed):
+    """the masks consecutive dropout sites of one forward draw (same reservation order as ops._drop_reserve)"""
+    from emu_backend import drop_keep_scale
+
+    out, off = [], 0
+    for n in sizes:
+        keep, sc = drop_keep_scale(n, p, seed, off)
+        out.append(keep.float() * sc)
+        off += n
+    return out
+
+
+def test_ffn_block_dropout_matches_explicit_masks():
+    R, d, F_, p = 6, 256, 512, 0.2
+    x = _leaf(R, d, seed=1)
+    w1, b1 = _leaf(F_, d, seed=2), _leaf(F_, seed=3)
+    w2, b2 = _leaf(d, F_, seed=4), _leaf(d, seed=5)
+    gm, bt = _leaf(d, seed=6), _leaf(d, seed=7)
+    with torch.no_grad():
+        w1.mul_(d ** -0.5); w2.mul_(F_ ** -0.5)
+    go = torch.randn(R, d, generator=torch.Generator().manual_seed(8))
+    leaves = (x, w1, b1, w2, b2, gm, bt)
+    ops.set_dropout_seed(21)
+    y, _ = ops.ffn_block(x, None, w1, b1, w2, b2, gm, bt, drop_p=p)
+    (y * go).sum().backward()
+    got = [y.detach()] + [t.grad.clone() for t in leaves]
+    for t in leaves:
+        t.grad = None
+    mh, mo = _masks([R * F_, R * d], p, 21)
+    h = (x @ w1.t() + b1).relu() * mh.view(R, F_)
+    yl = (h @ w2.t() + b2) * mo.view(R, d)
+    yr = torch.nn.functional.layer_norm(x + yl, (d,), gm, bt, 1e-5)
+    (yr * go).sum().backward()
+    for a_, b_ in zip(got, [yr] + [t.grad for t in leaves]):
+        assert rel_err(a_, b_) < 2e-5
+
+
+def test_self_attn_block_dropout_matches_explicit_masks():
+    B, L, H, d, p = 3, 5, 8, 256, 0.2
+    R = B * L
+    x, pos = _leaf(R, d, seed=1), _leaf(R, d, seed=2)
+    wi, bi = _leaf(3 * d, d, seed=3), _leaf(3 * d, seed=4)
+    wo, bo = _leaf(d, d, seed=5), _leaf(d, seed=6)
+    gm, bt = _leaf(d, seed=7), _leaf(d, seed=8)
+    with torch.no_grad():
+        wi.mul_(d ** -0.5); wo.mul_(d ** -0.5)
+    go = torch.randn(R, d, generator=torch.Generator().manual_seed(9))
+    leaves = (x, pos, wi, bi, wo, bo, gm, bt)
+    ops.set_dropout_seed(33)
+    y, _ = ops.self_attn_block(x, None, pos, None, wi, bi, wo, bo, gm, bt, B, L, H, drop_p=p)
+    (y * go).sum().backward()
+    got = [y.detach()] + [t.grad.clone() for t in leaves]
+    for t in leaves:
+        t.grad = None
+    ma, mo = _masks([B * H * L * L, R * d], p, 33)
+    qk = x + pos
+    q, k, v = qk @ wi[:d].t() + bi[:d], qk @ wi[d:2 * d].t() + bi[d:2 * d], x @ wi[2 * d:].t() + bi[2 * d:]
+    hd = lambda t: t.reshape(B, L, H, 32).permute(0, 2, 1, 3)
+    pr = torch.softmax(hd(q) @ hd(k).transpose(-1, -2) * 32 ** -0.5, -1) * ma.view(B, H, L, L)
+    o = (pr @ hd(v)).permute(0, 2, 1, 3).reshape(R, d)
+    a = (o @ wo.t() + bo) * mo.view(R, d)
+    yr = torch.nn.functional.layer_norm(x + a, (d,), gm, bt, 1e-5)
+    (yr * go).sum().backward()
+    for a_, b_ in zip(got, [yr] + [t.grad for t in leaves]):
+        assert rel_err(a_, b_) < 2e-5
+
+
+def test_hot_path_train_mode_dropout():
+    """The whole hot path in train mode with MODEL.STCAT.DROPOUT 0.1 (the reference's default) runs forward and backward,
+    is reproducible for a fixed seed, changes with the seed, and eval mode ignores dropout."""
+    from helpers import cfg_for
+    from stcat_b200 import synthetic
+    from stcat_b200.loss import STGLossPlan
+    from stcat_b200.nested import NestedTensor
+    from stcat_b200.param_spec import synthetic_params
+    from stcat_b200.pipeline import STCATHotPath
+
+    cfg = cfg_for({"max_video_len": 16}, dropout=0.1)
+    model = STCATHotPath(cfg).load_flat_params(synthetic_params(cfg, seed=3))
+    T = 4
+    inp = synthetic.make_inputs([T], 2, 3, 3, seed=5)
+    tg = synthetic.make_targets([T], seed=5)
+    plan = STGLossPlan(cfg, tg["boxes"], tg["actioness"], [T], "cpu")
+
+    def loss_of(vis, seed=11):
+        ops.set_dropout_seed(seed)
+        torch.manual_seed(0)  # the 0.3 dropout of the temporal heads draws from torch's stream
+        out = model(NestedTensor(vis, inp["vis_mask"].clone(), [T]), inp["vis_pos"], (inp["text_mask"], inp["text_memory"], None))
+        return plan.torch_restatement(out)[0]
+
+    model.train()
+    vis = inp["vis_features"].clone().requires_grad_(True)
+    L0 = loss_of(vis)
+    L0.backward()
+    assert torch.isfinite(vis.grad).all() and float(vis.grad.abs().max()) > 0
+    for name, prm in model.named_parameters():
+        assert prm.grad is None or torch.isfinite(prm.grad).all(), name
+    with torch.no_grad():
+        assert float(loss_of(vis)) == float(L0)                 # same seed, same masks
+        assert float(loss_of(vis, seed=12)) != float(L0)        # another seed, other masks
+        model.eval()
+        e1, e2 = float(loss_of(vis, seed=1)), float(loss_of(vis, seed=2))
+        assert e1 == e2 and e1 != float(L0)  # eval mode: no dropout anywhere
