@@ -146,15 +146,17 @@ STCAT_API int stcat_attention_bwd(const void* q1, const void* q2, int64_t ldq, c
  *   stcat_dropout               : out[i] = keep(i) ? x[i] * scale : 0   (fp32 or bf16, in place allowed)
  *   stcat_attention_dropout_fwd : stcat_attention_fwd with dropout on the normalised probabilities, element index
  *                                 ((b*H + h)*Lq + i)*Lk + j; p_avg is the head average of the DROPPED probabilities
- *   stcat_attention_dropout_bwd : its backward (same seed / offset)
- * These run the generic SIMT attention kernels for every shape (the tcgen05 / mma.sync kernels have no dropout yet). */
+ *   stcat_attention_dropout_bwd : its backward (same seed / offset; `o` = the forward output, optional like stcat_attention_bwd's)
+ * Kernel selection: the single-query and tcgen05 kernels apply the same mask for their shape classes, everything else runs
+ * the generic SIMT kernels (the short-sequence kernels have no dropout yet). */
 STCAT_API int stcat_dropout(const void* x, void* out, int dtype, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
 STCAT_API int stcat_attention_dropout_fwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2, int64_t ldk,
                                 const void* v, int64_t ldv, void* o, int64_t ldo, int dtype, const uint8_t* key_mask,
                                 float* lse, float* p_avg, int B, int H, int Lq, int Lk, int dh, float scale, float drop_p,
                                 uint64_t seed, uint64_t offset, void* stream);
 STCAT_API int stcat_attention_dropout_bwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2, int64_t ldk,
-                                const void* v, int64_t ldv, const void* d_o, int64_t lddo, int dtype, const uint8_t* key_mask,
+                                const void* v, int64_t ldv, const void* o, int64_t ldo, const void* d_o, int64_t lddo, int dtype,
+                                const uint8_t* key_mask,
                                 const float* lse, const float* dp_avg, float* delta, void* dq1, void* dq2, int64_t lddq,
                                 void* dk1, void* dk2, int64_t lddk, void* dv, int64_t lddv, int B, int H, int Lq, int Lk, int dh,
                                 float scale, float drop_p, uint64_t seed, uint64_t offset, void* stream);

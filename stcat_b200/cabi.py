@@ -57,8 +57,8 @@ _U64 = ctypes.c_uint64
 SIGNATURES["stcat_dropout"] = (c_int, [_P, _P, _I, _L, _F, _U64, _U64, _P])
 SIGNATURES["stcat_attention_dropout_fwd"] = (c_int, [_P, _P, _L, _P, _P, _L, _P, _L, _P, _L, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F,
                                                      _F, _U64, _U64, _P])
-SIGNATURES["stcat_attention_dropout_bwd"] = (c_int, [_P, _P, _L, _P, _P, _L, _P, _L, _P, _L, _I, _P, _P, _P, _P, _P, _P, _L, _P, _P,
-                                                     _L, _P, _L, _I, _I, _I, _I, _I, _F, _F, _U64, _U64, _P])
+SIGNATURES["stcat_attention_dropout_bwd"] = (c_int, [_P, _P, _L, _P, _P, _L, _P, _L, _P, _L, _P, _L, _I, _P, _P, _P, _P, _P, _P, _L,
+                                                     _P, _P, _L, _P, _L, _I, _I, _I, _I, _I, _F, _F, _U64, _U64, _P])
 SIGNATURES["stcat_anchor_sine_fwd"] = (c_int, [_P, _P, _P, _L, _P])
 SIGNATURES["stcat_anchor_sine_bwd"] = (c_int, [_P, _P, _P, _L, _P])
 SIGNATURES["stcat_box_refine_fwd"] = (c_int, [_P, _P, _P, _L, _F, _P])
@@ -282,7 +282,7 @@ class CudaBackend:
         op, ldo = (None, 0) if o is None else self._mat(o, "o")[:2]
         if drop is not None and drop[0] > 0:
             self._rc(self.lib.stcat_attention_dropout_bwd(
-                qp, q2p, ldq, kp, k2p, ldk, vp, ldv, gp, ldg, qd, self._flat(key_mask, "key_mask", torch.uint8),
+                qp, q2p, ldq, kp, k2p, ldk, vp, ldv, op, ldo, gp, ldg, qd, self._flat(key_mask, "key_mask", torch.uint8),
                 self._flat(lse, "lse", torch.float32), self._flat(dp_avg, "dp_avg", torch.float32),
                 self._flat(delta, "delta", torch.float32), dqp, dq2p, lddq, dkp, dk2p, lddk, dvp, lddv, B, H, Lq, Lk, 32,
                 float(scale), float(drop[0]), int(drop[1]), int(drop[2]), self._stream()), "attention_dropout_bwd")

@@ -403,7 +403,7 @@ static int launch_bwd(const void* q1, const void* q2, int64_t ldq, const void* k
 int attn_tc_fwd_supported(int dtype, const void* q2, const void* p_avg, int B, int H, int Lq, int Lk, const void* q,
                           const void* k, const void* v, const void* o, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo);
 int attn_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
-                const uint8_t* key_mask, float* lse, int B, int H, int S, float scale, cudaStream_t st);
+                const uint8_t* key_mask, float* lse, int B, int H, int S, float scale, cudaStream_t st, const DropArgs& drop);
 
 // attention_small.cu: whole-problem-in-shared-memory kernels for short sequences (temporal self-attention)
 int attn_small_supported(const void* q2, int B, int H, int Lq, int Lk);
@@ -428,11 +428,11 @@ int attn_sq_supported(int dtype, int Lq, int Lk, const void* p_avg, const void* 
                       const int64_t* lds, int n);
 int attn_sq_fwd(int dtype, const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2, int64_t ldk,
                 const void* v, int64_t ldv, void* o, int64_t ldo, const uint8_t* key_mask, float* lse, int B, int H, int Lk,
-                float scale, cudaStream_t st);
+                float scale, cudaStream_t st, const DropArgs& drop);
 int attn_sq_bwd(int dtype, const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2, int64_t ldk,
                 const void* v, int64_t ldv, const void* d_o, int64_t lddo, const uint8_t* key_mask, const float* lse,
                 float* delta, void* dq1, void* dq2, int64_t lddq, void* dk1, void* dk2, int64_t lddk, void* dv, int64_t lddv,
-                int B, int H, int Lk, float scale, cudaStream_t st);
+                int B, int H, int Lk, float scale, cudaStream_t st, const DropArgs& drop);
 int attn_tc_bwd_supported(int dtype, const void* q2, const void* dp_avg, const void* o, int B, int H, int Lq, int Lk,
                           const void* q, const void* k, const void* v, const void* d_o, const void* dq, const void* dk,
                           const void* dv, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddo, int64_t lddq,
@@ -440,47 +440,99 @@ int attn_tc_bwd_supported(int dtype, const void* q2, const void* dp_avg, const v
 int attn_tc_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o,
                 int64_t ldo, const void* d_o, int64_t lddo, const uint8_t* key_mask, const float* lse, void* dq,
                 int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int S, float scale,
-                cudaStream_t st);
+                cudaStream_t st, const DropArgs& drop);
 
 }  // namespace stcat
 
 using namespace stcat;
 
-extern "C" int stcat_attention_fwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2,
-                                   int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo, int dtype,
-                                   const uint8_t* key_mask, float* lse, float* p_avg, int B, int H, int Lq, int Lk,
-                                   int dh, float scale, void* stream) {
-    STCAT_REQUIRE(q1 && k1 && v && o && lse, STCAT_EINVAL, "attention_fwd: null pointer");
-    STCAT_REQUIRE((q2 == nullptr) == (k2 == nullptr), STCAT_EINVAL, "attention_fwd: q2/k2 must both be set or both NULL");
-    STCAT_REQUIRE(dh == DH, STCAT_ESHAPE, "attention_fwd: head dim %d unsupported (must be 32 = HIDDEN/HEADS)", dh);
-    STCAT_REQUIRE(B >= 0 && H > 0 && Lq >= 0 && Lk > 0, STCAT_EINVAL, "attention_fwd: bad sizes B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk);
-    STCAT_REQUIRE(B <= 65535 && H <= 65535, STCAT_ESHAPE, "attention_fwd: B/H exceed grid limits");
+// Kernel selection shared by the plain and the dropout entry points.  With dropout (drop.thresh != 0) the single-query,
+// tcgen05 and generic kernels apply the counter-based mask of common.cuh; the short-sequence kernels have no dropout.
+static int attention_fwd_impl(const char* who, const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2,
+                              int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo, int dtype, const uint8_t* key_mask,
+                              float* lse, float* p_avg, int B, int H, int Lq, int Lk, int dh, float scale, void* stream,
+                              const DropArgs& drop) {
+    STCAT_REQUIRE(q1 && k1 && v && o && lse, STCAT_EINVAL, "%s: null pointer", who);
+    STCAT_REQUIRE((q2 == nullptr) == (k2 == nullptr), STCAT_EINVAL, "%s: q2/k2 must both be set or both NULL", who);
+    STCAT_REQUIRE(dh == DH, STCAT_ESHAPE, "%s: head dim %d unsupported (must be 32 = HIDDEN/HEADS)", who, dh);
+    STCAT_REQUIRE(B >= 0 && H > 0 && Lq >= 0 && Lk > 0, STCAT_EINVAL, "%s: bad sizes B=%d H=%d Lq=%d Lk=%d", who, B, H, Lq, Lk);
+    STCAT_REQUIRE(B <= 65535 && H <= 65535, STCAT_ESHAPE, "%s: B/H exceed grid limits", who);
     if (B == 0 || Lq == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    STCAT_REQUIRE(dtype == STCAT_F32 || dtype == STCAT_BF16, STCAT_EINVAL, "attention_fwd: bad dtype %d", dtype);
+    STCAT_REQUIRE(dtype == STCAT_F32 || dtype == STCAT_BF16, STCAT_EINVAL, "%s: bad dtype %d", who, dtype);
+    const bool nodrop = drop.thresh == 0;
     {
         const void* ptrs[6] = {q1, q2, k1, k2, v, o};
         const int64_t lds[6] = {ldq, ldq, ldk, ldk, ldv, ldo};
         if (attn_sq_supported(dtype, Lq, Lk, p_avg, nullptr, ptrs, lds, 6))
-            return attn_sq_fwd(dtype, q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, B, H, Lk, scale, st);
+            return attn_sq_fwd(dtype, q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, B, H, Lk, scale, st, drop);
     }
     if (attn_tc_fwd_supported(dtype, q2, p_avg, B, H, Lq, Lk, q1, k1, v, o, ldq, ldk, ldv, ldo))
-        return attn_tc_fwd(q1, ldq, k1, ldk, v, ldv, o, ldo, key_mask, lse, B, H, Lq, scale, st);
-    {
+        return attn_tc_fwd(q1, ldq, k1, ldk, v, ldv, o, ldo, key_mask, lse, B, H, Lq, scale, st, drop);
+    if (nodrop) {
         const void* ptrs[4] = {q1, k1, v, o};
         const int64_t lds[4] = {ldq, ldk, ldv, ldo};
         if (attn_mma_supported(dtype, q2, B, H, Lq, Lk, ptrs, lds, 4))
             return attn_mma_fwd(q1, ldq, k1, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st);
     }
-    if (attn_small_supported(q2, B, H, Lq, Lk))
+    if (nodrop && attn_small_supported(q2, B, H, Lq, Lk))
         return attn_small_fwd(dtype, q1, ldq, k1, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st);
     if (dtype == STCAT_F32)
-        return q2 ? launch_fwd<float, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st)
-                  : launch_fwd<float, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st);
-    if (dtype == STCAT_BF16)
-        return q2 ? launch_fwd<__nv_bfloat16, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st)
-                  : launch_fwd<__nv_bfloat16, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st);
-    return set_err(STCAT_EINVAL, "attention_fwd: bad dtype %d", dtype);
+        return q2 ? launch_fwd<float, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st, drop)
+                  : launch_fwd<float, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st, drop);
+    return q2 ? launch_fwd<__nv_bfloat16, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st, drop)
+              : launch_fwd<__nv_bfloat16, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st, drop);
+}
+
+static int attention_bwd_impl(const char* who, const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2,
+                              int64_t ldk, const void* v, int64_t ldv, const void* o, int64_t ldo, const void* d_o, int64_t lddo,
+                              int dtype, const uint8_t* key_mask, const float* lse, const float* dp_avg, float* delta, void* dq1,
+                              void* dq2, int64_t lddq, void* dk1, void* dk2, int64_t lddk, void* dv, int64_t lddv, int B, int H,
+                              int Lq, int Lk, int dh, float scale, void* stream, const DropArgs& drop) {
+    STCAT_REQUIRE(q1 && k1 && v && d_o && lse && delta && dq1 && dk1 && dv, STCAT_EINVAL, "%s: null pointer", who);
+    STCAT_REQUIRE((q2 == nullptr) == (k2 == nullptr), STCAT_EINVAL, "%s: q2/k2 must both be set or both NULL", who);
+    STCAT_REQUIRE(!q2 || (dq2 && dk2), STCAT_EINVAL, "%s: dq2/dk2 required with q2/k2", who);
+    STCAT_REQUIRE(dh == DH, STCAT_ESHAPE, "%s: head dim %d unsupported (must be 32)", who, dh);
+    STCAT_REQUIRE(B >= 0 && H > 0 && Lq >= 0 && Lk > 0, STCAT_EINVAL, "%s: bad sizes", who);
+    STCAT_REQUIRE(B <= 65535 && H <= 65535, STCAT_ESHAPE, "%s: B/H exceed grid limits", who);
+    if (B == 0 || Lq == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    STCAT_REQUIRE(dtype == STCAT_F32 || dtype == STCAT_BF16, STCAT_EINVAL, "%s: bad dtype %d", who, dtype);
+    const bool nodrop = drop.thresh == 0;
+    {
+        const void* ptrs[11] = {q1, q2, k1, k2, v, d_o, dq1, dq2, dk1, dk2, dv};
+        const int64_t lds[11] = {ldq, ldq, ldk, ldk, ldv, lddo, lddq, lddq, lddk, lddk, lddv};
+        if (attn_sq_supported(dtype, Lq, Lk, nullptr, dp_avg, ptrs, lds, 11))
+            return attn_sq_bwd(dtype, q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, delta, dq1, dq2, lddq, dk1,
+                               dk2, lddk, dv, lddv, B, H, Lk, scale, st, drop);
+    }
+    if (attn_tc_bwd_supported(dtype, q2, dp_avg, o, B, H, Lq, Lk, q1, k1, v, d_o, dq1, dk1, dv, ldq, ldk, ldv, ldo, lddo,
+                              lddq, lddk, lddv))
+        return attn_tc_bwd(q1, ldq, k1, ldk, v, ldv, o, ldo, d_o, lddo, key_mask, lse, dq1, lddq, dk1, lddk, dv, lddv, B, H,
+                           Lq, scale, st, drop);
+    if (nodrop) {
+        const void* ptrs[7] = {q1, k1, v, d_o, dq1, dk1, dv};
+        const int64_t lds[7] = {ldq, ldk, ldv, lddo, lddq, lddk, lddv};
+        if (attn_mma_supported(dtype, q2, B, H, Lq, Lk, ptrs, lds, 7))
+            return attn_mma_bwd(q1, ldq, k1, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, dq1, lddq, dk1, lddk, dv, lddv, B, H,
+                                Lq, Lk, scale, st);
+    }
+    if (nodrop && attn_small_supported(q2, B, H, Lq, Lk))
+        return attn_small_bwd(dtype, q1, ldq, k1, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, dq1, lddq, dk1, lddk, dv, lddv,
+                              B, H, Lq, Lk, scale, st);
+    if (dtype == STCAT_F32)
+        return q2 ? launch_bwd<float, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st, drop)
+                  : launch_bwd<float, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st, drop);
+    return q2 ? launch_bwd<__nv_bfloat16, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st, drop)
+              : launch_bwd<__nv_bfloat16, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st, drop);
+}
+
+extern "C" int stcat_attention_fwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2,
+                                   int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo, int dtype,
+                                   const uint8_t* key_mask, float* lse, float* p_avg, int B, int H, int Lq, int Lk,
+                                   int dh, float scale, void* stream) {
+    return attention_fwd_impl("attention_fwd", q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, dtype, key_mask, lse, p_avg, B, H, Lq,
+                              Lk, dh, scale, stream, DropArgs());
 }
 
 extern "C" int stcat_attention_bwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2,
@@ -489,84 +541,33 @@ extern "C" int stcat_attention_bwd(const void* q1, const void* q2, int64_t ldq, 
                                    const uint8_t* key_mask, const float* lse, const float* dp_avg, float* delta,
                                    void* dq1, void* dq2, int64_t lddq, void* dk1, void* dk2, int64_t lddk, void* dv,
                                    int64_t lddv, int B, int H, int Lq, int Lk, int dh, float scale, void* stream) {
-    STCAT_REQUIRE(q1 && k1 && v && d_o && lse && delta && dq1 && dk1 && dv, STCAT_EINVAL, "attention_bwd: null pointer");
-    STCAT_REQUIRE((q2 == nullptr) == (k2 == nullptr), STCAT_EINVAL, "attention_bwd: q2/k2 must both be set or both NULL");
-    STCAT_REQUIRE(!q2 || (dq2 && dk2), STCAT_EINVAL, "attention_bwd: dq2/dk2 required with q2/k2");
-    STCAT_REQUIRE(dh == DH, STCAT_ESHAPE, "attention_bwd: head dim %d unsupported (must be 32)", dh);
-    STCAT_REQUIRE(B >= 0 && H > 0 && Lq >= 0 && Lk > 0, STCAT_EINVAL, "attention_bwd: bad sizes");
-    STCAT_REQUIRE(B <= 65535 && H <= 65535, STCAT_ESHAPE, "attention_bwd: B/H exceed grid limits");
-    if (B == 0 || Lq == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    STCAT_REQUIRE(dtype == STCAT_F32 || dtype == STCAT_BF16, STCAT_EINVAL, "attention_bwd: bad dtype %d", dtype);
-    {
-        const void* ptrs[11] = {q1, q2, k1, k2, v, d_o, dq1, dq2, dk1, dk2, dv};
-        const int64_t lds[11] = {ldq, ldq, ldk, ldk, ldv, lddo, lddq, lddq, lddk, lddk, lddv};
-        if (attn_sq_supported(dtype, Lq, Lk, nullptr, dp_avg, ptrs, lds, 11))
-            return attn_sq_bwd(dtype, q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, delta, dq1, dq2, lddq, dk1,
-                               dk2, lddk, dv, lddv, B, H, Lk, scale, st);
-    }
-    if (attn_tc_bwd_supported(dtype, q2, dp_avg, o, B, H, Lq, Lk, q1, k1, v, d_o, dq1, dk1, dv, ldq, ldk, ldv, ldo, lddo,
-                              lddq, lddk, lddv))
-        return attn_tc_bwd(q1, ldq, k1, ldk, v, ldv, o, ldo, d_o, lddo, key_mask, lse, dq1, lddq, dk1, lddk, dv, lddv, B, H,
-                           Lq, scale, st);
-    {
-        const void* ptrs[7] = {q1, k1, v, d_o, dq1, dk1, dv};
-        const int64_t lds[7] = {ldq, ldk, ldv, lddo, lddq, lddk, lddv};
-        if (attn_mma_supported(dtype, q2, B, H, Lq, Lk, ptrs, lds, 7))
-            return attn_mma_bwd(q1, ldq, k1, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, dq1, lddq, dk1, lddk, dv, lddv, B, H,
-                                Lq, Lk, scale, st);
-    }
-    if (attn_small_supported(q2, B, H, Lq, Lk))
-        return attn_small_bwd(dtype, q1, ldq, k1, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, dq1, lddq, dk1, lddk, dv, lddv,
-                              B, H, Lq, Lk, scale, st);
-    if (dtype == STCAT_F32)
-        return q2 ? launch_bwd<float, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st)
-                  : launch_bwd<float, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st);
-    if (dtype == STCAT_BF16)
-        return q2 ? launch_bwd<__nv_bfloat16, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st)
-                  : launch_bwd<__nv_bfloat16, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st);
-    return set_err(STCAT_EINVAL, "attention_bwd: bad dtype %d", dtype);
+    return attention_bwd_impl("attention_bwd", q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, d_o, lddo, dtype, key_mask, lse, dp_avg,
+                              delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, dh, scale, stream, DropArgs());
 }
 
 // Attention with dropout on the probabilities (nn.MultiheadAttention dropout=p in train mode, torch functional.py;
-// reference attention.py:381): the generic SIMT kernels with the counter-based mask of common.cuh.  The `weights`
-// output (p_avg) is the head average of the DROPPED probabilities, as in the reference.
+// reference attention.py:381) with the counter-based mask of common.cuh: element ((b*H + h)*Lq + i)*Lk + j of the site
+// that drew (seed, offset).  The `weights` output (p_avg) is the head average of the DROPPED probabilities, as in the
+// reference; lse is that of the undropped softmax.  `o` (the forward output, optional) lets the backward take
+// delta = dO . O instead of recomputing it.
 extern "C" int stcat_attention_dropout_fwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2,
                                            int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo, int dtype,
                                            const uint8_t* key_mask, float* lse, float* p_avg, int B, int H, int Lq, int Lk,
                                            int dh, float scale, float drop_p, uint64_t seed, uint64_t offset, void* stream) {
-    STCAT_REQUIRE(q1 && k1 && v && o && lse, STCAT_EINVAL, "attention_dropout_fwd: null pointer");
-    STCAT_REQUIRE((q2 == nullptr) == (k2 == nullptr), STCAT_EINVAL, "attention_dropout_fwd: q2/k2 must both be set or both NULL");
-    STCAT_REQUIRE(dh == DH && B >= 0 && H > 0 && Lq >= 0 && Lk > 0 && B <= 65535 && H <= 65535, STCAT_ESHAPE, "attention_dropout_fwd: bad sizes");
     STCAT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, STCAT_EINVAL, "attention_dropout_fwd: p=%f", (double)drop_p);
-    STCAT_REQUIRE(dtype == STCAT_F32 || dtype == STCAT_BF16, STCAT_EINVAL, "attention_dropout_fwd: bad dtype %d", dtype);
-    if (B == 0 || Lq == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    const DropArgs d = make_drop(drop_p, seed, offset);
-    if (dtype == STCAT_F32)
-        return q2 ? launch_fwd<float, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st, d)
-                  : launch_fwd<float, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st, d);
-    return q2 ? launch_fwd<__nv_bfloat16, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st, d)
-              : launch_fwd<__nv_bfloat16, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st, d);
+    return attention_fwd_impl("attention_dropout_fwd", q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, dtype, key_mask, lse, p_avg, B,
+                              H, Lq, Lk, dh, scale, stream, make_drop(drop_p, seed, offset));
 }
 
 extern "C" int stcat_attention_dropout_bwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2,
-                                           int64_t ldk, const void* v, int64_t ldv, const void* d_o, int64_t lddo, int dtype,
+                                           int64_t ldk, const void* v, int64_t ldv, const void* o, int64_t ldo,
+                                           const void* d_o, int64_t lddo, int dtype,
                                            const uint8_t* key_mask, const float* lse, const float* dp_avg, float* delta,
                                            void* dq1, void* dq2, int64_t lddq, void* dk1, void* dk2, int64_t lddk, void* dv,
                                            int64_t lddv, int B, int H, int Lq, int Lk, int dh, float scale, float drop_p,
                                            uint64_t seed, uint64_t offset, void* stream) {
-    STCAT_REQUIRE(q1 && k1 && v && d_o && lse && delta && dq1 && dk1 && dv, STCAT_EINVAL, "attention_dropout_bwd: null pointer");
-    STCAT_REQUIRE((q2 == nullptr) == (k2 == nullptr) && (!q2 || (dq2 && dk2)), STCAT_EINVAL, "attention_dropout_bwd: second score part");
-    STCAT_REQUIRE(dh == DH && B >= 0 && H > 0 && Lq >= 0 && Lk > 0 && B <= 65535 && H <= 65535, STCAT_ESHAPE, "attention_dropout_bwd: bad sizes");
     STCAT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, STCAT_EINVAL, "attention_dropout_bwd: p=%f", (double)drop_p);
-    STCAT_REQUIRE(dtype == STCAT_F32 || dtype == STCAT_BF16, STCAT_EINVAL, "attention_dropout_bwd: bad dtype %d", dtype);
-    if (B == 0 || Lq == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    const DropArgs d = make_drop(drop_p, seed, offset);
-    if (dtype == STCAT_F32)
-        return q2 ? launch_bwd<float, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st, d)
-                  : launch_bwd<float, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st, d);
-    return q2 ? launch_bwd<__nv_bfloat16, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st, d)
-              : launch_bwd<__nv_bfloat16, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st, d);
+    return attention_bwd_impl("attention_dropout_bwd", q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, d_o, lddo, dtype, key_mask, lse,
+                              dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, dh, scale, stream,
+                              make_drop(drop_p, seed, offset));
 }

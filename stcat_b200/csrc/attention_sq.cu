@@ -77,7 +77,8 @@ template <typename T, bool TWO>
 __global__ void __launch_bounds__(SQ_THREADS)
 attn_sq_fwd_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t ldq, const T* __restrict__ k1,
                    const T* __restrict__ k2, int64_t ldk, const T* __restrict__ v, int64_t ldv, T* __restrict__ o,
-                   int64_t ldo, const uint8_t* __restrict__ key_mask, float* __restrict__ lse, int H, int Lk, float scale) {
+                   int64_t ldo, const uint8_t* __restrict__ key_mask, float* __restrict__ lse, int H, int Lk, float scale,
+                   const DropArgs drop) {
     extern __shared__ float sm[];  // scores / probabilities [Lk]
     pdl_launch_dependents();
     pdl_wait();
@@ -113,7 +114,8 @@ attn_sq_fwd_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t l
     for (int j = threadIdx.x; j < Lk; j += SQ_THREADS) {
         const float s = sm[j];
         const float pj = (s == -INFINITY) ? 0.f : expf(s - mx);
-        sm[j] = pj;
+        // dropout on the probabilities: element (b, h, 0, j) of [B, H, 1, Lk]; the row sum stays undropped
+        sm[j] = drop.thresh ? drop_apply(drop, (uint64_t)blockIdx.x * Lk + j, pj) : pj;
         sum += pj;
     }
     sum = block_reduce(sum, red, false);  // (its barriers also publish sm[] to every thread)
@@ -140,7 +142,7 @@ attn_sq_bwd_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t l
                    int64_t lddo, const uint8_t* __restrict__ key_mask, const float* __restrict__ lse,
                    float* __restrict__ delta_out, T* __restrict__ dq1, T* __restrict__ dq2, int64_t lddq,
                    T* __restrict__ dk1, T* __restrict__ dk2, int64_t lddk, T* __restrict__ dv, int64_t lddv, int H, int Lk,
-                   float scale) {
+                   float scale, const DropArgs drop) {
     extern __shared__ float sm[];  // p [Lk], dp [Lk]
     pdl_launch_dependents();
     pdl_wait();
@@ -174,6 +176,8 @@ attn_sq_bwd_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t l
             Row32<T>::load(v + (kbase + j) * ldv + col, kr);
 #pragma unroll
             for (int e = 0; e < 32; ++e) dpj = fmaf(g[e], kr[e], dpj);
+            // o was formed from the DROPPED probabilities: its gradient reaches p through the mask
+            if (drop.thresh) dpj = drop_apply(drop, (uint64_t)blockIdx.x * Lk + j, dpj);
         }
         sp[j] = pj;
         sdp[j] = dpj;
@@ -195,8 +199,9 @@ attn_sq_bwd_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t l
             for (int e = 0; e < 32; ++e) r[e] = ds * qb[e];
             Row32<T>::store(dk2 + (kbase + j) * lddk + col, r);
         }
+        const float pm = drop.thresh ? drop_apply(drop, (uint64_t)blockIdx.x * Lk + j, pj) : pj;  // what multiplied V
 #pragma unroll
-        for (int e = 0; e < 32; ++e) r[e] = pj * g[e];
+        for (int e = 0; e < 32; ++e) r[e] = pm * g[e];
         Row32<T>::store(dv + (kbase + j) * lddv + col, r);
     }
     __syncthreads();
@@ -236,9 +241,9 @@ int attn_sq_supported(int dtype, int Lq, int Lk, const void* p_avg, const void* 
 template <typename T, bool TWO>
 static int launch_sq_fwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2, int64_t ldk,
                          const void* v, int64_t ldv, void* o, int64_t ldo, const uint8_t* key_mask, float* lse, int B, int H,
-                         int Lk, float scale, cudaStream_t st) {
+                         int Lk, float scale, cudaStream_t st, const DropArgs& drop) {
     launch_pdl(attn_sq_fwd_kernel<T, TWO>, dim3(B * H), dim3(SQ_THREADS), Lk * sizeof(float), st,
-        (const T*)q1, (const T*)q2, ldq, (const T*)k1, (const T*)k2, ldk, (const T*)v, ldv, (T*)o, ldo, key_mask, lse, H, Lk, scale);
+        (const T*)q1, (const T*)q2, ldq, (const T*)k1, (const T*)k2, ldk, (const T*)v, ldv, (T*)o, ldo, key_mask, lse, H, Lk, scale, drop);
     return check_launch("attn_sq_fwd_kernel");
 }
 
@@ -246,32 +251,32 @@ template <typename T, bool TWO>
 static int launch_sq_bwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2, int64_t ldk,
                          const void* v, int64_t ldv, const void* d_o, int64_t lddo, const uint8_t* key_mask, const float* lse,
                          float* delta, void* dq1, void* dq2, int64_t lddq, void* dk1, void* dk2, int64_t lddk, void* dv,
-                         int64_t lddv, int B, int H, int Lk, float scale, cudaStream_t st) {
+                         int64_t lddv, int B, int H, int Lk, float scale, cudaStream_t st, const DropArgs& drop) {
     launch_pdl(attn_sq_bwd_kernel<T, TWO>, dim3(B * H), dim3(SQ_THREADS), 2 * Lk * sizeof(float), st,
         (const T*)q1, (const T*)q2, ldq, (const T*)k1, (const T*)k2, ldk, (const T*)v, ldv, (const T*)d_o, lddo, key_mask, lse,
-        delta, (T*)dq1, (T*)dq2, lddq, (T*)dk1, (T*)dk2, lddk, (T*)dv, lddv, H, Lk, scale);
+        delta, (T*)dq1, (T*)dq2, lddq, (T*)dk1, (T*)dk2, lddk, (T*)dv, lddv, H, Lk, scale, drop);
     return check_launch("attn_sq_bwd_kernel");
 }
 
 int attn_sq_fwd(int dtype, const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2, int64_t ldk,
                 const void* v, int64_t ldv, void* o, int64_t ldo, const uint8_t* key_mask, float* lse, int B, int H, int Lk,
-                float scale, cudaStream_t st) {
+                float scale, cudaStream_t st, const DropArgs& drop) {
     if (dtype == STCAT_BF16)
-        return q2 ? launch_sq_fwd<__nv_bfloat16, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, B, H, Lk, scale, st)
-                  : launch_sq_fwd<__nv_bfloat16, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, B, H, Lk, scale, st);
-    return q2 ? launch_sq_fwd<float, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, B, H, Lk, scale, st)
-              : launch_sq_fwd<float, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, B, H, Lk, scale, st);
+        return q2 ? launch_sq_fwd<__nv_bfloat16, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, B, H, Lk, scale, st, drop)
+                  : launch_sq_fwd<__nv_bfloat16, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, B, H, Lk, scale, st, drop);
+    return q2 ? launch_sq_fwd<float, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, B, H, Lk, scale, st, drop)
+              : launch_sq_fwd<float, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, B, H, Lk, scale, st, drop);
 }
 
 int attn_sq_bwd(int dtype, const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2, int64_t ldk,
                 const void* v, int64_t ldv, const void* d_o, int64_t lddo, const uint8_t* key_mask, const float* lse,
                 float* delta, void* dq1, void* dq2, int64_t lddq, void* dk1, void* dk2, int64_t lddk, void* dv, int64_t lddv,
-                int B, int H, int Lk, float scale, cudaStream_t st) {
+                int B, int H, int Lk, float scale, cudaStream_t st, const DropArgs& drop) {
     if (dtype == STCAT_BF16)
-        return q2 ? launch_sq_bwd<__nv_bfloat16, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lk, scale, st)
-                  : launch_sq_bwd<__nv_bfloat16, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lk, scale, st);
-    return q2 ? launch_sq_bwd<float, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lk, scale, st)
-              : launch_sq_bwd<float, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lk, scale, st);
+        return q2 ? launch_sq_bwd<__nv_bfloat16, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lk, scale, st, drop)
+                  : launch_sq_bwd<__nv_bfloat16, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lk, scale, st, drop);
+    return q2 ? launch_sq_bwd<float, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lk, scale, st, drop)
+              : launch_sq_bwd<float, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lk, scale, st, drop);
 }
 
 }  // namespace stcat

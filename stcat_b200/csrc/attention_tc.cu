@@ -40,8 +40,10 @@ struct AttnFwdParams {
     float* lse;               // [B, H, S]
     int B, H, S, nqt;
     float scale;
+    DropArgs drop;            // dropout on the probabilities (DROP instantiation only)
 };
 
+template <bool DROP>
 __global__ void __launch_bounds__(AT_FWD_THREADS, 1)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
@@ -189,6 +191,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const float ms = (mx == -INFINITY) ? 0.f : mx * sc;
             float sum = 0.f;
             const uint32_t prow = sP(set) + row * 128;
+            // dropout: element index of (b, h, query, key 0) in the [B, H, S, S] probability tensor; the row sum (and so
+            // lse and the 1/sum of the epilogue) stays that of the undropped softmax
+            const uint64_t drow = DROP ? (((uint64_t)b * p.H + h) * S + (qt * AT_QT + row)) * (uint64_t)S : 0ull;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 if (c >= nchunk) break;  // warp-uniform
@@ -200,9 +205,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 if (w == 0u) {  // no masked key in this chunk (the common case): no per-element predicates
 #pragma unroll
                     for (int e = 0; e < 32; e += 2) {
-                        const float p0 = ex2_approx(fmaf(__uint_as_float(r[e]), sc, -ms));
-                        const float p1 = ex2_approx(fmaf(__uint_as_float(r[e + 1]), sc, -ms));
+                        float p0 = ex2_approx(fmaf(__uint_as_float(r[e]), sc, -ms));
+                        float p1 = ex2_approx(fmaf(__uint_as_float(r[e + 1]), sc, -ms));
                         sum += p0 + p1;
+                        if (DROP) {
+                            p0 *= drop_mult(p.drop, drow + c * 32 + e);
+                            p1 *= drop_mult(p.drop, drow + c * 32 + e + 1);
+                        }
                         __nv_bfloat162 bb = __floats2bfloat162_rn(p0, p1);
                         pk[e >> 1] = *reinterpret_cast<uint32_t*>(&bb);
                     }
@@ -212,6 +221,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         float p0 = ((w >> e) & 1u) ? 0.f : ex2_approx(fmaf(__uint_as_float(r[e]), sc, -ms));
                         float p1 = ((w >> (e + 1)) & 1u) ? 0.f : ex2_approx(fmaf(__uint_as_float(r[e + 1]), sc, -ms));
                         sum += p0 + p1;
+                        if (DROP) {
+                            p0 *= drop_mult(p.drop, drow + c * 32 + e);
+                            p1 *= drop_mult(p.drop, drow + c * 32 + e + 1);
+                        }
                         __nv_bfloat162 bb = __floats2bfloat162_rn(p0, p1);
                         pk[e >> 1] = *reinterpret_cast<uint32_t*>(&bb);
                     }
@@ -287,6 +300,7 @@ struct AttnBwdParams {
     const float* lse;
     int B, H, S;
     float scale;
+    DropArgs drop;             // dropout on the probabilities (DROP instantiation only)
 };
 
 __device__ __forceinline__ void store_row_bf16x32(__nv_bfloat16* dst, const uint32_t (&r)[32]) {
@@ -301,6 +315,7 @@ __device__ __forceinline__ void store_row_bf16x32(__nv_bfloat16* dst, const uint
     for (int j = 0; j < 4; ++j) d4[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -459,6 +474,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     lse2 = p.lse[((int64_t)b * p.H + h) * S + q] * 1.4426950408889634f;
                 }
                 const bool dead = !qvalid || lse2 == -INFINITY;  // padded query row or fully masked row
+                // dropout (o = (P o M) V): delta = dO . O still equals sum_j P_ij (M o dP)_ij; the P tile feeding dV is
+                // P o M, and dS = P o (M o dP - delta) * scale
+                const uint64_t drow = DROP ? (((uint64_t)b * p.H + h) * S + q) * (uint64_t)S : 0ull;
 #pragma unroll
                 for (int kt = 0; kt < 2; ++kt) {
                     if (kt >= nqt) break;
@@ -474,6 +492,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         tmem_ld_wait();
                         const uint32_t mwv = wg ? mw[kt * 4 + 2 + c] : mw[kt * 4 + c];  // warp-uniform
                         uint32_t pp[16], pd[16];
+                        const uint64_t dcol = drow + kt * 128 + col;
                         if (mwv == 0u) {
                             // no masked key in this chunk (the common case): no per-element predicates; a dead row
                             // (padding / fully masked) has lse_eff = +inf, so every p and ds is exactly 0
@@ -483,9 +502,11 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                             for (int e = 0; e < 32; e += 2) {
                                 const float p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), sc, -lse_eff));
                                 const float p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), sc, -lse_eff));
-                                const float d0 = dead ? 0.f : p0 * (__uint_as_float(rd[e]) - delta) * dsc;
-                                const float d1 = dead ? 0.f : p1 * (__uint_as_float(rd[e + 1]) - delta) * dsc;
-                                __nv_bfloat162 bp = __floats2bfloat162_rn(p0, p1), bd = __floats2bfloat162_rn(d0, d1);
+                                const float m0 = DROP ? drop_mult(p.drop, dcol + e) : 1.f;
+                                const float m1 = DROP ? drop_mult(p.drop, dcol + e + 1) : 1.f;
+                                const float d0 = dead ? 0.f : p0 * (__uint_as_float(rd[e]) * m0 - delta) * dsc;
+                                const float d1 = dead ? 0.f : p1 * (__uint_as_float(rd[e + 1]) * m1 - delta) * dsc;
+                                __nv_bfloat162 bp = __floats2bfloat162_rn(p0 * m0, p1 * m1), bd = __floats2bfloat162_rn(d0, d1);
                                 pp[e >> 1] = *reinterpret_cast<uint32_t*>(&bp);
                                 pd[e >> 1] = *reinterpret_cast<uint32_t*>(&bd);
                             }
@@ -495,12 +516,16 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                             for (int e = 0; e < 32; e += 2) {
                                 float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
                                 if (!((wmask >> e) & 1u)) {
+                                    const float m0 = DROP ? drop_mult(p.drop, dcol + e) : 1.f;
                                     p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), sc, -lse2));
-                                    d0 = p0 * (__uint_as_float(rd[e]) - delta) * p.scale;
+                                    d0 = p0 * (__uint_as_float(rd[e]) * m0 - delta) * p.scale;
+                                    p0 *= m0;
                                 }
                                 if (!((wmask >> (e + 1)) & 1u)) {
+                                    const float m1 = DROP ? drop_mult(p.drop, dcol + e + 1) : 1.f;
                                     p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), sc, -lse2));
-                                    d1 = p1 * (__uint_as_float(rd[e + 1]) - delta) * p.scale;
+                                    d1 = p1 * (__uint_as_float(rd[e + 1]) * m1 - delta) * p.scale;
+                                    p1 *= m1;
                                 }
                                 __nv_bfloat162 bp = __floats2bfloat162_rn(p0, p1), bd = __floats2bfloat162_rn(d0, d1);
                                 pp[e >> 1] = *reinterpret_cast<uint32_t*>(&bp);
@@ -585,7 +610,7 @@ int attn_tc_fwd_supported(int dtype, const void* q2, const void* p_avg, int B, i
 }
 
 int attn_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
-                const uint8_t* key_mask, float* lse, int B, int H, int S, float scale, cudaStream_t st) {
+                const uint8_t* key_mask, float* lse, int B, int H, int S, float scale, cudaStream_t st, const DropArgs& drop) {
     using namespace tc;
     CUtensorMap tmQ, tmK, tmV;
     int rc;
@@ -600,16 +625,19 @@ int attn_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
     p.B = B; p.H = H; p.S = S;
     p.nqt = (S + AT_QT - 1) / AT_QT;
     p.scale = scale;
+    p.drop = drop;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
         if (e != cudaSuccess) return set_err((int)e, "attn_tc_fwd: smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
     const int total = B * H * p.nqt;
     const int sms = num_sms();
     const int grid = total < sms ? total : sms;
-    launch_pdl(attn_tc_fwd_kernel, dim3(grid), dim3(AT_FWD_THREADS), AT_FWD_SMEM, st, tmQ, tmK, tmV, p);
+    if (drop.thresh) launch_pdl(attn_tc_fwd_kernel<true>, dim3(grid), dim3(AT_FWD_THREADS), AT_FWD_SMEM, st, tmQ, tmK, tmV, p);
+    else launch_pdl(attn_tc_fwd_kernel<false>, dim3(grid), dim3(AT_FWD_THREADS), AT_FWD_SMEM, st, tmQ, tmK, tmV, p);
     return check_launch("attn_tc_fwd_kernel");
 }
 
@@ -630,7 +658,7 @@ int attn_tc_bwd_supported(int dtype, const void* q2, const void* dp_avg, const v
 int attn_tc_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o,
                 int64_t ldo, const void* d_o, int64_t lddo, const uint8_t* key_mask, const float* lse, void* dq,
                 int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int S, float scale,
-                cudaStream_t st) {
+                cudaStream_t st, const DropArgs& drop) {
     using namespace tc;
     CUtensorMap tmQ, tmK, tmV, tmDO;
     int rc;
@@ -648,16 +676,19 @@ int attn_tc_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
     p.lse = lse;
     p.B = B; p.H = H; p.S = S;
     p.scale = scale;
+    p.drop = drop;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
         if (e != cudaSuccess) return set_err((int)e, "attn_tc_bwd: smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
     const int total = B * H;
     const int sms = num_sms();
     const int grid = total < sms ? total : sms;
-    launch_pdl(attn_tc_bwd_kernel, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, p);
+    if (drop.thresh) launch_pdl(attn_tc_bwd_kernel<true>, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, p);
+    else launch_pdl(attn_tc_bwd_kernel<false>, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, p);
     return check_launch("attn_tc_bwd_kernel");
 }
 

@@ -110,6 +110,9 @@ inline DropArgs make_drop(float p, uint64_t seed, uint64_t offset) {
     }
     return d;
 }
+__device__ __forceinline__ float drop_mult(const DropArgs& d, uint64_t idx) {  // the mask as a multiplier: 1/keep or 0
+    return drop_bits24(d.seed, d.offset + idx) >= d.thresh ? d.scale : 0.f;
+}
 __device__ __forceinline__ float drop_apply(const DropArgs& d, uint64_t idx, float v) {
     return drop_bits24(d.seed, d.offset + idx) >= d.thresh ? v * d.scale : 0.f;
 }
