@@ -161,6 +161,10 @@ STCAT_API int stcat_attention_dropout_bwd(const void* q1, const void* q2, int64_
                                 void* dk1, void* dk2, int64_t lddk, void* dv, int64_t lddv, int B, int H, int Lq, int Lk, int dh,
                                 float scale, float drop_p, uint64_t seed, uint64_t offset, void* stream);
 
+/* Diagnostics (not on the product path): SM-clock timestamps at the phase boundaries of the tcgen05 spatial-attention
+ * forward: CTA 0, its first 8 work items, 16 event slots per item (buf: 128 int64 in device memory; NULL = off). */
+STCAT_API int stcat_debug_attn_trace(void* buf);
+
 /* ------------------------------------------------------------------------------------------------
  * Element-wise helpers on [rows, cols] fp32 matrices (contiguous).
  *   add       : out = a + b  (q = k = src + pos, modal_encoder.py:225-226,235); out_bf16 optional copy

@@ -442,9 +442,18 @@ int attn_tc_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
                 int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int S, float scale,
                 cudaStream_t st, const DropArgs& drop);
 
+void attn_tc_set_trace(long long* buf);
+
 }  // namespace stcat
 
 using namespace stcat;
+
+// Diagnostics: SM-clock timestamps at the phase boundaries of the tcgen05 attention forward (CTA 0, first 8 work items,
+// 16 event slots per item; buf = 128 int64 in device memory, NULL switches it off).  See scripts/attn_fwd_timeline.py.
+extern "C" int stcat_debug_attn_trace(void* buf) {
+    attn_tc_set_trace((long long*)buf);
+    return 0;
+}
 
 // Kernel selection shared by the plain and the dropout entry points.  With dropout (drop.thresh != 0) the single-query,
 // tcgen05 and generic kernels apply the counter-based mask of common.cuh; the short-sequence kernels have no dropout.

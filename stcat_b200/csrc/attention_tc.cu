@@ -41,6 +41,7 @@ struct AttnFwdParams {
     int B, H, S, nqt;
     float scale;
     DropArgs drop;            // dropout on the probabilities (DROP instantiation only)
+    long long* trace;         // diagnostics (stcat_debug_attn_trace): SM clock at the phase boundaries of CTA 0's first 8 items
 };
 
 template <bool DROP>
@@ -50,9 +51,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = base + 2 * AT_SET_BYTES;
-    // per set: 0 load_full, 1 load_free, 2 s_full, 3 p_full, 4 o_full, 5 tmem_free
-    auto bar = [&](int set, int which) { return bar_base + 8u * (set * 6 + which); };
-    const uint32_t tmem_slot = bar_base + 8u * 12;
+    // per set: 0 qk_full (Q, K landed), 1 v_free (PV MMA done with V / P), 2 s_full (score MMA done: S readable, Q / K free),
+    //          3 p_full (P written), 4 o_full, 5 tmem_free (O read out), 6 v_full (V landed)
+    auto bar = [&](int set, int which) { return bar_base + 8u * (set * 7 + which); };
+    const uint32_t tmem_slot = bar_base + 8u * 14;
     auto sQ = [&](int set) { return base + set * AT_SET_BYTES; };
     auto sK = [&](int set) { return base + set * AT_SET_BYTES + AT_Q_BYTES; };
     auto sV = [&](int set) { return base + set * AT_SET_BYTES + AT_Q_BYTES + AT_KV_BYTES; };
@@ -74,6 +76,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar(s, 0), 1); mbar_init(bar(s, 1), 1); mbar_init(bar(s, 2), 1);
             mbar_init(bar(s, 3), 128); mbar_init(bar(s, 4), 1); mbar_init(bar(s, 5), 128);
+            mbar_init(bar(s, 6), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -103,17 +106,38 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         b = t / p.H;
     };
 
+    // diagnostics: event ev of item i -> trace[i * 16 + ev] (CTA 0, first 8 items, one lane per role)
+    auto T = [&](int i, int ev) {
+        if (p.trace != nullptr && blockIdx.x == 0 && i < 8) p.trace[i * 16 + ev] = clock64();
+    };
+
     if (warp == 0) {
+        // Q / K loader: the buffers of a set are free as soon as the score MMA of the set's previous item has completed
+        // (s_full), i.e. one whole softmax + PV + epilogue before they are needed again -> the load latency is hidden
+        if (lane == 0) {
+            for (int i = 0; i < n_mine; ++i) {
+                const int set = i & 1, k = i >> 1;
+                int b, h, qt;
+                decode(i, b, h, qt);
+                if (k > 0) mbar_wait(bar(set, 2), (k - 1) & 1);
+                T(i, 0);
+                mbar_expect_tx(bar(set, 0), AT_Q_BYTES + AT_KV_BYTES);
+                tma_load_3d(sQ(set), &tmQ, bar(set, 0), h * AT_DH, qt * AT_QT, b);
+                tma_load_3d(sK(set), &tmK, bar(set, 0), h * AT_DH, 0, b);
+            }
+        }
+    } else if (warp == 3) {
+        // V loader: V is read by the PV MMA only, after the softmax, so its load (issued when the previous PV of the set
+        // is done) runs under the score MMA and the softmax of its own item
         if (lane == 0) {
             for (int i = 0; i < n_mine; ++i) {
                 const int set = i & 1, k = i >> 1;
                 int b, h, qt;
                 decode(i, b, h, qt);
                 mbar_wait(bar(set, 1), (k & 1) ^ 1);
-                mbar_expect_tx(bar(set, 0), AT_Q_BYTES + 2 * AT_KV_BYTES);
-                tma_load_3d(sQ(set), &tmQ, bar(set, 0), h * AT_DH, qt * AT_QT, b);
-                tma_load_3d(sK(set), &tmK, bar(set, 0), h * AT_DH, 0, b);
-                tma_load_3d(sV(set), &tmV, bar(set, 0), h * AT_DH, 0, b);
+                T(i, 1);
+                mbar_expect_tx(bar(set, 6), AT_KV_BYTES);
+                tma_load_3d(sV(set), &tmV, bar(set, 6), h * AT_DH, 0, b);
             }
         }
     } else if (warp == 1) {
@@ -124,7 +148,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 if (i < n_mine) {
                     const int set = i & 1, k = i >> 1;
                     mbar_wait(bar(set, 0), k & 1);
+                    T(i, 2);
                     mbar_wait(bar(set, 5), (k & 1) ^ 1);
+                    T(i, 3);
                     tc_fence_after();
 #pragma unroll
                     for (int kk = 0; kk < AT_DH / 16; ++kk) {
@@ -137,6 +163,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 if (i >= 1) {
                     const int j = i - 1, set = j & 1, k = j >> 1;
                     mbar_wait(bar(set, 3), k & 1);
+                    T(j, 4);
+                    mbar_wait(bar(set, 6), k & 1);
+                    T(j, 5);
                     tc_fence_after();
                     for (int t = 0; t < nk16; ++t) {
                         const uint64_t ad = make_desc(sP(set) + (t >> 2) * 16384 + (t & 3) * 32, 16, 1024, LAYOUT_SW128);
@@ -145,6 +174,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     }
                     umma_commit(bar(set, 4));
                     umma_commit(bar(set, 1));
+                    T(j, 6);
                 }
             }
         }
@@ -154,10 +184,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int row = q4 * 32 + lane;
         const float sc = p.scale * 1.4426950408889634f;
         const int nchunk = (S + 31) >> 5;
+        const bool tr = (q4 == 0 && lane == 0);
         for (int i = g; i < n_mine; i += 2) {
             const int set = g, k = i >> 1;
             int b, h, qt;
             decode(i, b, h, qt);
+            if (tr) T(i, 7);
             // key mask -> one bit per key (1 = masked), 32 keys per word, identical in every warp
             uint32_t mw[8];
 #pragma unroll
@@ -167,67 +199,79 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 if (!m && p.key_mask) m = p.key_mask[(int64_t)b * S + key] != 0;
                 mw[c] = __ballot_sync(0xffffffffu, m);
             }
+            if (tr) T(i, 8);
             mbar_wait(bar(set, 2), k & 1);
+            if (tr) T(i, 9);
             tc_fence_after();
             const uint32_t t_row = tmem_base + set * 256 + ((uint32_t)(q4 * 32) << 16);
-            float mx = -INFINITY;
+            // Both passes read the score row from TMEM in 32-column chunks, double-buffered in registers (the load of
+            // chunk c+1 is in flight while chunk c is reduced), with four independent max / sum chains per thread.
+            uint32_t ra[32], rb[32];
+            // ---- pass 1: row max ----
+            float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+            auto max_chunk = [&](const uint32_t (&r)[32], const uint32_t w) {  // w identical in every lane
+                if (w == 0u) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                if (c < nchunk) {  // warp-uniform
-                    uint32_t r[32];
-                    tmem_ld32(t_row + c * 32, r);
-                    tmem_ld_wait();
-                    const uint32_t w = mw[c];  // identical in every lane: the branch below is warp-uniform
-                    if (w == 0u) {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e)
-                            if (!((w >> e) & 1u)) mx = fmaxf(mx, __uint_as_float(r[e]));
+                    for (int e = 0; e < 32; e += 4) {
+                        m0 = fmaxf(m0, __uint_as_float(r[e]));
+                        m1 = fmaxf(m1, __uint_as_float(r[e + 1]));
+                        m2 = fmaxf(m2, __uint_as_float(r[e + 2]));
+                        m3 = fmaxf(m3, __uint_as_float(r[e + 3]));
                     }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (!((w >> e) & 1u)) m0 = fmaxf(m0, __uint_as_float(r[e]));
+                }
+            };
+            tmem_ld32(t_row, ra);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+                if (c < nchunk) {  // warp-uniform
+                    if (c + 1 < nchunk) tmem_ld32(t_row + (c + 1) * 32, rb);
+                    max_chunk(ra, mw[c]);
+                    tmem_ld_wait();
+                }
+                if (c + 1 < nchunk) {
+                    if (c + 2 < nchunk) tmem_ld32(t_row + (c + 2) * 32, ra);
+                    max_chunk(rb, mw[c + 1]);
+                    tmem_ld_wait();
                 }
             }
+            const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+            if (tr) T(i, 10);
             const float ms = (mx == -INFINITY) ? 0.f : mx * sc;
-            float sum = 0.f;
+            // ---- pass 2: p = exp2(s * sc - ms), row sum, P as bf16 into the swizzled smem tile ----
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
             const uint32_t prow = sP(set) + row * 128;
             // dropout: element index of (b, h, query, key 0) in the [B, H, S, S] probability tensor; the row sum (and so
             // lse and the 1/sum of the epilogue) stays that of the undropped softmax
             const uint64_t drow = DROP ? (((uint64_t)b * p.H + h) * S + (qt * AT_QT + row)) * (uint64_t)S : 0ull;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                if (c >= nchunk) break;  // warp-uniform
-                uint32_t r[32];
-                tmem_ld32(t_row + c * 32, r);
-                tmem_ld_wait();
-                const uint32_t w = mw[c];
+            auto exp_chunk = [&](const uint32_t (&r)[32], const int c, const uint32_t w) {
                 uint32_t pk[16];
-                if (w == 0u) {  // no masked key in this chunk (the common case): no per-element predicates
 #pragma unroll
-                    for (int e = 0; e < 32; e += 2) {
-                        float p0 = ex2_approx(fmaf(__uint_as_float(r[e]), sc, -ms));
-                        float p1 = ex2_approx(fmaf(__uint_as_float(r[e + 1]), sc, -ms));
-                        sum += p0 + p1;
-                        if (DROP) {
-                            p0 *= drop_mult(p.drop, drow + c * 32 + e);
-                            p1 *= drop_mult(p.drop, drow + c * 32 + e + 1);
-                        }
-                        __nv_bfloat162 bb = __floats2bfloat162_rn(p0, p1);
-                        pk[e >> 1] = *reinterpret_cast<uint32_t*>(&bb);
+                for (int e = 0; e < 32; e += 4) {
+                    float p0 = ex2_approx(fmaf(__uint_as_float(r[e]), sc, -ms));
+                    float p1 = ex2_approx(fmaf(__uint_as_float(r[e + 1]), sc, -ms));
+                    float p2 = ex2_approx(fmaf(__uint_as_float(r[e + 2]), sc, -ms));
+                    float p3 = ex2_approx(fmaf(__uint_as_float(r[e + 3]), sc, -ms));
+                    if (w != 0u) {  // a chunk with masked keys (warp-uniform; rare: the padded tail / text padding)
+                        p0 = ((w >> e) & 1u) ? 0.f : p0;
+                        p1 = ((w >> (e + 1)) & 1u) ? 0.f : p1;
+                        p2 = ((w >> (e + 2)) & 1u) ? 0.f : p2;
+                        p3 = ((w >> (e + 3)) & 1u) ? 0.f : p3;
                     }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 32; e += 2) {
-                        float p0 = ((w >> e) & 1u) ? 0.f : ex2_approx(fmaf(__uint_as_float(r[e]), sc, -ms));
-                        float p1 = ((w >> (e + 1)) & 1u) ? 0.f : ex2_approx(fmaf(__uint_as_float(r[e + 1]), sc, -ms));
-                        sum += p0 + p1;
-                        if (DROP) {
-                            p0 *= drop_mult(p.drop, drow + c * 32 + e);
-                            p1 *= drop_mult(p.drop, drow + c * 32 + e + 1);
-                        }
-                        __nv_bfloat162 bb = __floats2bfloat162_rn(p0, p1);
-                        pk[e >> 1] = *reinterpret_cast<uint32_t*>(&bb);
+                    s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+                    if (DROP) {
+                        p0 *= drop_mult(p.drop, drow + c * 32 + e);
+                        p1 *= drop_mult(p.drop, drow + c * 32 + e + 1);
+                        p2 *= drop_mult(p.drop, drow + c * 32 + e + 2);
+                        p3 *= drop_mult(p.drop, drow + c * 32 + e + 3);
                     }
+                    __nv_bfloat162 b01 = __floats2bfloat162_rn(p0, p1), b23 = __floats2bfloat162_rn(p2, p3);
+                    pk[e >> 1] = *reinterpret_cast<uint32_t*>(&b01);
+                    pk[(e >> 1) + 1] = *reinterpret_cast<uint32_t*>(&b23);
                 }
                 const uint32_t blk = prow + (c >> 1) * 16384;
 #pragma unroll
@@ -236,12 +280,30 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + chunk * 16), "r"(pk[4 * j]),
                                  "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
                 }
+            };
+            tmem_ld32(t_row, ra);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+                if (c < nchunk) {
+                    if (c + 1 < nchunk) tmem_ld32(t_row + (c + 1) * 32, rb);
+                    exp_chunk(ra, c, mw[c]);
+                    tmem_ld_wait();
+                }
+                if (c + 1 < nchunk) {
+                    if (c + 2 < nchunk) tmem_ld32(t_row + (c + 2) * 32, ra);
+                    exp_chunk(rb, c + 1, mw[c + 1]);
+                    tmem_ld_wait();
+                }
             }
+            const float sum = (s0 + s1) + (s2 + s3);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             tc_fence_before();
+            if (tr) T(i, 11);
             mbar_arrive(bar(set, 3));
             // ---- epilogue ----
             mbar_wait(bar(set, 4), k & 1);
+            if (tr) T(i, 12);
             tc_fence_after();
             uint32_t r[32];
             tmem_ld32(t_row, r);
@@ -262,6 +324,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 for (int j = 0; j < 4; ++j) dst[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
                 p.lse[((int64_t)b * p.H + h) * S + q] = sum > 0.f ? mx * p.scale + logf(sum) : -INFINITY;
             }
+            if (tr) T(i, 13);
         }
     }
     tc_fence_before();
@@ -609,6 +672,9 @@ int attn_tc_fwd_supported(int dtype, const void* q2, const void* p_avg, int B, i
     return 1;
 }
 
+static long long* g_attn_trace = nullptr;
+void attn_tc_set_trace(long long* buf) { g_attn_trace = buf; }
+
 int attn_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
                 const uint8_t* key_mask, float* lse, int B, int H, int S, float scale, cudaStream_t st, const DropArgs& drop) {
     using namespace tc;
@@ -626,6 +692,7 @@ int attn_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
     p.nqt = (S + AT_QT - 1) / AT_QT;
     p.scale = scale;
     p.drop = drop;
+    p.trace = g_attn_trace;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
