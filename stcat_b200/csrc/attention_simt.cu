@@ -449,7 +449,7 @@ void attn_tc_set_trace(long long* buf);
 using namespace stcat;
 
 // Diagnostics: SM-clock timestamps at the phase boundaries of the tcgen05 attention forward (CTA 0, first 8 work items,
-// 16 event slots per item; buf = 128 int64 in device memory, NULL switches it off).  See scripts/attn_fwd_timeline.py.
+// 16 event slots per item; buf = 128 int64 in device memory, NULL switches it off).  See scripts/attn_timeline.py.
 extern "C" int stcat_debug_attn_trace(void* buf) {
     attn_tc_set_trace((long long*)buf);
     return 0;

@@ -44,7 +44,16 @@ struct AttnFwdParams {
     long long* trace;         // diagnostics (stcat_debug_attn_trace): SM clock at the phase boundaries of CTA 0's first 8 items
 };
 
-template <bool DROP>
+// two probabilities -> packed bf16x2 with integer ops (round half up on the magnitude; inputs are finite and >= 0), which
+// keeps the conversion off the XU pipe that the exponentials saturate (profiles/r1_k_attn_fwd_timeline.md)
+__device__ __forceinline__ uint32_t pack_prob_bf16x2(float lo, float hi) {
+    return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
+}
+
+// V2 (staged for round 2, selected by STCAT_ATTN_FWD_V2=1, S <= 224): integer bf16 pack, and O in its own TMEM columns
+// (S: set * 224, O: 448 + set * 32) so that the score MMA of the set's next item is issued right behind the PV MMA instead
+// of after the epilogue.
+template <bool DROP, bool V2>
 __global__ void __launch_bounds__(AT_FWD_THREADS, 1)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
@@ -59,6 +68,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     auto sK = [&](int set) { return base + set * AT_SET_BYTES + AT_Q_BYTES; };
     auto sV = [&](int set) { return base + set * AT_SET_BYTES + AT_Q_BYTES + AT_KV_BYTES; };
     auto sP = [&](int set) { return base + set * AT_SET_BYTES + AT_Q_BYTES + 2 * AT_KV_BYTES; };
+    // TMEM columns of a set's score tile and of its output accumulator
+    auto col_s = [&](int set) { return (uint32_t)(V2 ? set * 224 : set * 256); };
+    auto col_o = [&](int set) { return (uint32_t)(V2 ? 448 + set * 32 : set * 256); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total = p.B * p.H * p.nqt;
@@ -149,14 +161,16 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     const int set = i & 1, k = i >> 1;
                     mbar_wait(bar(set, 0), k & 1);
                     T(i, 2);
-                    mbar_wait(bar(set, 5), (k & 1) ^ 1);
+                    // V1: S and O share columns -> wait until the epilogue of the set's previous item has read O out.
+                    // V2: the S columns are free once the previous item's P is written (p_full, waited for before its PV)
+                    if (!V2) mbar_wait(bar(set, 5), (k & 1) ^ 1);
                     T(i, 3);
                     tc_fence_after();
 #pragma unroll
                     for (int kk = 0; kk < AT_DH / 16; ++kk) {
                         const uint64_t ad = make_desc(sQ(set) + kk * 32, 16, 512, LAYOUT_SW64);
                         const uint64_t bd = make_desc(sK(set) + kk * 32, 16, 512, LAYOUT_SW64);
-                        umma_bf16(tmem_base + set * 256, ad, bd, idesc_s, kk > 0 ? 1u : 0u);
+                        umma_bf16(tmem_base + col_s(set), ad, bd, idesc_s, kk > 0 ? 1u : 0u);
                     }
                     umma_commit(bar(set, 2));
                 }
@@ -165,12 +179,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     mbar_wait(bar(set, 3), k & 1);
                     T(j, 4);
                     mbar_wait(bar(set, 6), k & 1);
+                    if (V2) mbar_wait(bar(set, 5), (k & 1) ^ 1);  // O columns of the set read out by the previous epilogue
                     T(j, 5);
                     tc_fence_after();
                     for (int t = 0; t < nk16; ++t) {
                         const uint64_t ad = make_desc(sP(set) + (t >> 2) * 16384 + (t & 3) * 32, 16, 1024, LAYOUT_SW128);
                         const uint64_t bd = make_desc(sV(set) + t * 1024, 512, 512, LAYOUT_SW64);
-                        umma_bf16(tmem_base + set * 256, ad, bd, idesc_o, t > 0 ? 1u : 0u);
+                        umma_bf16(tmem_base + col_o(set), ad, bd, idesc_o, t > 0 ? 1u : 0u);
                     }
                     umma_commit(bar(set, 4));
                     umma_commit(bar(set, 1));
@@ -203,7 +218,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mbar_wait(bar(set, 2), k & 1);
             if (tr) T(i, 9);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + set * 256 + ((uint32_t)(q4 * 32) << 16);
+            const uint32_t t_row = tmem_base + col_s(set) + ((uint32_t)(q4 * 32) << 16);
             // Both passes read the score row from TMEM in 32-column chunks, double-buffered in registers (the load of
             // chunk c+1 is in flight while chunk c is reduced), with four independent max / sum chains per thread.
             uint32_t ra[32], rb[32];
@@ -269,9 +284,14 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         p2 *= drop_mult(p.drop, drow + c * 32 + e + 2);
                         p3 *= drop_mult(p.drop, drow + c * 32 + e + 3);
                     }
-                    __nv_bfloat162 b01 = __floats2bfloat162_rn(p0, p1), b23 = __floats2bfloat162_rn(p2, p3);
-                    pk[e >> 1] = *reinterpret_cast<uint32_t*>(&b01);
-                    pk[(e >> 1) + 1] = *reinterpret_cast<uint32_t*>(&b23);
+                    if (V2) {
+                        pk[e >> 1] = pack_prob_bf16x2(p0, p1);
+                        pk[(e >> 1) + 1] = pack_prob_bf16x2(p2, p3);
+                    } else {
+                        __nv_bfloat162 b01 = __floats2bfloat162_rn(p0, p1), b23 = __floats2bfloat162_rn(p2, p3);
+                        pk[e >> 1] = *reinterpret_cast<uint32_t*>(&b01);
+                        pk[(e >> 1) + 1] = *reinterpret_cast<uint32_t*>(&b23);
+                    }
                 }
                 const uint32_t blk = prow + (c >> 1) * 16384;
 #pragma unroll
@@ -306,7 +326,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             if (tr) T(i, 12);
             tc_fence_after();
             uint32_t r[32];
-            tmem_ld32(t_row, r);
+            tmem_ld32(tmem_base + col_o(set) + ((uint32_t)(q4 * 32) << 16), r);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(bar(set, 5));
@@ -364,6 +384,7 @@ struct AttnBwdParams {
     int B, H, S;
     float scale;
     DropArgs drop;             // dropout on the probabilities (DROP instantiation only)
+    long long* trace;          // diagnostics (TRACE instantiation only): SM clock at the phase boundaries of CTA 0's first item
 };
 
 __device__ __forceinline__ void store_row_bf16x32(__nv_bfloat16* dst, const uint32_t (&r)[32]) {
@@ -378,7 +399,7 @@ __device__ __forceinline__ void store_row_bf16x32(__nv_bfloat16* dst, const uint
     for (int j = 0; j < 4; ++j) d4[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
 }
 
-template <bool DROP>
+template <bool DROP, bool TRACE>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -426,6 +447,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     pdl_launch_dependents();
     pdl_wait();
+    // diagnostics: event ev of block blk (CTA 0, its first two work items = 8 blocks) -> trace[blk * 8 + ev]
+    auto T = [&](uint32_t blk, int ev) {
+        if (TRACE && p.trace != nullptr && blockIdx.x == 0 && blk < 16) p.trace[blk * 8 + ev] = clock64();
+    };
 
     if (warp == 0) {
         if (lane == 0) {
@@ -455,6 +480,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     for (int kt = 0; kt < nqt; ++kt) {
                         const int nk16 = min(8, (S - kt * 128 + 15) >> 4);
                         mbar_wait(bar(5), (nb & 1) ^ 1);
+                        T(nb, 0);  // S / dP columns free: score MMAs issued
                         tc_fence_after();
 #pragma unroll
                         for (int kk = 0; kk < 2; ++kk) {
@@ -470,8 +496,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         }
                         umma_commit(bar(4));
                         mbar_wait(bar(6), nb & 1);
+                        T(nb, 1);  // P / dS tiles written
                         if (qt == 0 && kt == 0) mbar_wait(bar(11), (it & 1) ^ 1);
                         if (kt == 0) mbar_wait(bar(9), (nq & 1) ^ 1);
+                        T(nb, 2);  // accumulators free: gradient MMAs issued
                         tc_fence_after();
                         for (int t = 0; t < nq16; ++t) {  // contraction over the queries of this tile
                             const uint64_t ap = make_desc(sP + t * 2048, 16384, 1024, LAYOUT_SW128);
@@ -543,8 +571,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
                 for (int kt = 0; kt < 2; ++kt) {
                     if (kt >= nqt) break;
+                    const bool tr = TRACE && warp == 4 && lane == 0;
+                    if (tr) T(nb, 3);  // threads ready for the block
                     mbar_wait(bar(4), nb & 1);
+                    if (tr) T(nb, 4);  // S / dP landed in TMEM
                     mbar_wait(bar(7), (nb & 1) ^ 1);
+                    if (tr) T(nb, 5);  // P / dS tiles free (gradient MMAs of the previous block done)
                     tc_fence_after();
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
@@ -608,6 +640,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     tc_fence_before();
                     mbar_arrive(bar(5));
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    if (tr) T(nb, 6);  // P / dS written
                     mbar_arrive(bar(6));
                     ++nb;
                 }
@@ -695,16 +728,21 @@ int attn_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
     p.trace = g_attn_trace;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
         if (e != cudaSuccess) return set_err((int)e, "attn_tc_fwd: smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
     const int total = B * H * p.nqt;
     const int sms = num_sms();
     const int grid = total < sms ? total : sms;
-    if (drop.thresh) launch_pdl(attn_tc_fwd_kernel<true>, dim3(grid), dim3(AT_FWD_THREADS), AT_FWD_SMEM, st, tmQ, tmK, tmV, p);
-    else launch_pdl(attn_tc_fwd_kernel<false>, dim3(grid), dim3(AT_FWD_THREADS), AT_FWD_SMEM, st, tmQ, tmK, tmV, p);
+    // V2 is staged for validation (profiles/r1_k_attn_fwd_timeline.md): opt-in, and only when the padded key count fits 224
+    const bool v2 = getenv("STCAT_ATTN_FWD_V2") != nullptr && ((S + 15) / 16) * 16 <= 224;
+    auto go = [&](auto kern) { launch_pdl(kern, dim3(grid), dim3(AT_FWD_THREADS), AT_FWD_SMEM, st, tmQ, tmK, tmV, p); };
+    if (v2) { if (drop.thresh) go(attn_tc_fwd_kernel<true, true>); else go(attn_tc_fwd_kernel<false, true>); }
+    else { if (drop.thresh) go(attn_tc_fwd_kernel<true, false>); else go(attn_tc_fwd_kernel<false, false>); }
     return check_launch("attn_tc_fwd_kernel");
 }
 
@@ -744,18 +782,21 @@ int attn_tc_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
     p.B = B; p.H = H; p.S = S;
     p.scale = scale;
     p.drop = drop;
+    p.trace = g_attn_trace;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_tc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
         if (e != cudaSuccess) return set_err((int)e, "attn_tc_bwd: smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
     const int total = B * H;
     const int sms = num_sms();
     const int grid = total < sms ? total : sms;
-    if (drop.thresh) launch_pdl(attn_tc_bwd_kernel<true>, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, p);
-    else launch_pdl(attn_tc_bwd_kernel<false>, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, p);
+    if (drop.thresh) launch_pdl(attn_tc_bwd_kernel<true, false>, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, p);
+    else if (g_attn_trace) launch_pdl(attn_tc_bwd_kernel<false, true>, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, p);
+    else launch_pdl(attn_tc_bwd_kernel<false, false>, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, p);
     return check_launch("attn_tc_bwd_kernel");
 }
 
