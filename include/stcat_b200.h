@@ -164,6 +164,9 @@ STCAT_API int stcat_attention_dropout_bwd(const void* q1, const void* q2, int64_
 /* Diagnostics (not on the product path): SM-clock timestamps at the phase boundaries of the tcgen05 spatial-attention
  * forward: CTA 0, its first 8 work items, 16 event slots per item (buf: 128 int64 in device memory; NULL = off). */
 STCAT_API int stcat_debug_attn_trace(void* buf);
+/* Same for the tcgen05 GEMM (stcat_linear_fwd with bf16 operands, 128 x 256 tiles): CTA 0, its first 8 tiles, 8 event
+ * slots per tile (buf: 64 int64 in device memory; NULL = off). */
+STCAT_API int stcat_debug_gemm_trace(void* buf);
 
 /* ------------------------------------------------------------------------------------------------
  * Element-wise helpers on [rows, cols] fp32 matrices (contiguous).

@@ -3,7 +3,7 @@
 #   gpurun --timeout 300 -- 'bash scripts/validate_staged.sh'
 # 1. the staged forward (STCAT_ATTN_FWD_V2=1: integer bf16 pack + O in its own TMEM columns) against the same parity tests
 #    as the default kernel, and its timeline / graph-timed duration next to the default's;
-# 2. the backward timeline (never measured yet).
+# 2. the backward timeline and the GEMM timeline (never measured yet).
 mkdir -p gpurun_out
 export PYTHONPATH=.
 echo "== default forward: parity + timeline"
@@ -14,6 +14,9 @@ STCAT_ATTN_FWD_V2=1 timeout 120 python -m pytest tests/test_gpu_attention_tc.py 
 STCAT_ATTN_FWD_V2=1 timeout 60 python scripts/attn_timeline.py 64 213 fwd | tee gpurun_out/attn_fwd_timeline_v2.txt | tail -9
 echo "== backward timeline"
 timeout 60 python scripts/attn_timeline.py 64 213 bwd | tee gpurun_out/attn_bwd_timeline.txt | tail -20
+echo "== GEMM timeline (FFN linear1 forward; FFN linear2 forward)"
+timeout 60 python scripts/gemm_timeline.py 13632 2048 256 | tee gpurun_out/gemm_timeline_ffn1.txt | tail -20
+timeout 60 python scripts/gemm_timeline.py 13632 256 2048 | tee gpurun_out/gemm_timeline_ffn2.txt | tail -8
 echo "== graph-timed attention core, default vs V2"
 for v in "" 1; do
   if [ -n "$v" ]; then export STCAT_ATTN_FWD_V2=1; fi

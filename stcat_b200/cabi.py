@@ -60,6 +60,7 @@ SIGNATURES["stcat_attention_dropout_fwd"] = (c_int, [_P, _P, _L, _P, _P, _L, _P,
 SIGNATURES["stcat_attention_dropout_bwd"] = (c_int, [_P, _P, _L, _P, _P, _L, _P, _L, _P, _L, _P, _L, _I, _P, _P, _P, _P, _P, _P, _L,
                                                      _P, _P, _L, _P, _L, _I, _I, _I, _I, _I, _F, _F, _U64, _U64, _P])
 SIGNATURES["stcat_debug_attn_trace"] = (c_int, [_P])
+SIGNATURES["stcat_debug_gemm_trace"] = (c_int, [_P])
 SIGNATURES["stcat_anchor_sine_fwd"] = (c_int, [_P, _P, _P, _L, _P])
 SIGNATURES["stcat_anchor_sine_bwd"] = (c_int, [_P, _P, _P, _L, _P])
 SIGNATURES["stcat_box_refine_fwd"] = (c_int, [_P, _P, _P, _L, _F, _P])

@@ -443,6 +443,7 @@ int attn_tc_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
                 cudaStream_t st, const DropArgs& drop);
 
 void attn_tc_set_trace(long long* buf);
+void gemm_tc_set_trace(long long* buf);
 
 }  // namespace stcat
 
@@ -452,6 +453,13 @@ using namespace stcat;
 // 16 event slots per item; buf = 128 int64 in device memory, NULL switches it off).  See scripts/attn_timeline.py.
 extern "C" int stcat_debug_attn_trace(void* buf) {
     attn_tc_set_trace((long long*)buf);
+    return 0;
+}
+
+// Same for the tcgen05 GEMM (plain forward GEMMs, 128 x 256 tiles): CTA 0, its first 8 tiles, 8 event slots per tile
+// (buf = 64 int64 in device memory).  See scripts/gemm_timeline.py.
+extern "C" int stcat_debug_gemm_trace(void* buf) {
+    gemm_tc_set_trace((long long*)buf);
     return 0;
 }
 

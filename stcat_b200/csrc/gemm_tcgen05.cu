@@ -75,9 +75,10 @@ struct alignas(64) Job {
 template <int NJ> struct GroupParams {
     Job jobs[NJ];
     int njobs, total;
+    long long* trace;  // diagnostics (TRACE instantiation only): SM clock at the phase boundaries of CTA 0's first 8 tiles
 };
 
-template <bool A_MN, bool B_MN, bool OUT_BF16, int BN, int NJ>
+template <bool A_MN, bool B_MN, bool OUT_BF16, int BN, int NJ, bool TRACE = false>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
     extern __shared__ uint8_t smem_raw[];
@@ -124,6 +125,10 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
     // everything above (barriers, TMEM, descriptor prefetch) ran under the previous kernel's tail; its data is needed now
     pdl_launch_dependents();
     pdl_wait();
+    // diagnostics: event ev of this CTA's ti-th tile -> trace[ti * 8 + ev] (CTA 0 only, one lane per role)
+    auto T = [&](int ti, int ev) {
+        if (TRACE && gp.trace != nullptr && blockIdx.x == 0 && ti < 8) gp.trace[ti * 8 + ev] = clock64();
+    };
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -131,6 +136,8 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
             int stage = 0;
             uint32_t phase = 0;
             for (int w = blockIdx.x; w < total; w += gridDim.x) {
+                const int ti = TRACE ? (w - (int)blockIdx.x) / (int)gridDim.x : 0;
+                bool first = true;
                 const Job& J = gp.jobs[find_job(w)];
                 const int lw = w - J.work0;
                 const int split = lw % J.splits;
@@ -143,6 +150,7 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
                     const CUtensorMap* tmB = &J.tmB[term];
                     for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(empty_bar(stage), phase ^ 1);
+                        if (TRACE && first) { T(ti, 0); first = false; }  // first stage of the tile free: loads start
                         const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
                         mbar_expect_tx(full_bar(stage), STAGE_BYTES);
                         if (!A_MN) {
@@ -162,6 +170,7 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
+                T(ti, 1);  // all loads of the tile issued
             }
         }
     } else if (warp == 1) {
@@ -172,9 +181,12 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
             for (int w = blockIdx.x; w < total; w += gridDim.x) {
+                const int ti = TRACE ? (w - (int)blockIdx.x) / (int)gridDim.x : 0;
+                bool first = true;
                 const Job& J = gp.jobs[find_job(w)];
                 const int split = (w - J.work0) % J.splits;
                 mbar_wait(acce_bar(as), aphase ^ 1);  // epilogue has drained this accumulator stage
+                T(ti, 2);  // accumulator stage free
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
                 uint32_t acc = 0;  // the first MMA of the tile overwrites the accumulator
@@ -183,6 +195,7 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
                     const int kb1 = min(J.kb[term], kb0 + J.kb_per_split);
                     for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(full_bar(stage), phase);
+                        if (TRACE && first) { T(ti, 3); first = false; }  // first k-block landed
                         tc_fence_after();
                         const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
@@ -200,6 +213,7 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
                     }
                 }
                 umma_commit(accf_bar(as));  // accumulator complete -> epilogue
+                T(ti, 4);  // all MMAs of the tile issued
                 if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
             }
         }
@@ -220,6 +234,8 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
         int as = 0;
         uint32_t aphase = 0;
         for (int w = blockIdx.x; w < total; w += gridDim.x) {
+            const int ti = TRACE ? (w - (int)blockIdx.x) / (int)gridDim.x : 0;
+            const bool tr = TRACE && ew == 0 && lane == 0;
             const Job& p = gp.jobs[find_job(w)];
             const CUtensorMap& tmC = p.tmC;
             const int lw = w - p.work0;
@@ -242,7 +258,9 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
                         if (p.bias[term] != nullptr) bv += __ldg(p.bias[term] + col);
                 if (gt < GC) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + gt * 4), "f"(bv) : "memory");
             }
+            if (tr) T(ti, 5);  // epilogue ready for the tile
             mbar_wait(accf_bar(as), aphase);
+            if (tr) T(ti, 6);  // accumulator complete
             tc_fence_after();
             const uint32_t t_row = tmem_base + as * BN + g * GC + ((uint32_t)(q * 32) << 16);
             bool released = false;
@@ -348,6 +366,7 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
                 }
             }
             if (!released) release_acc();  // this group's half lies entirely outside N
+            if (tr) T(ti, 7);  // last store of the tile issued
             if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
         }
         if (gt == 0) tma_wait_all();
@@ -435,9 +454,22 @@ struct TcJob {
     GemmEpilogue epi;
 };
 
+static long long* g_gemm_trace = nullptr;
+void gemm_tc_set_trace(long long* buf) { g_gemm_trace = buf; }
+
 template <bool AMN, bool BMN, bool OBF, int BN, int NJ>
 static int launch_tc(const tc::GroupParams<NJ>& gp, int grid, cudaStream_t st) {
     using namespace tc;
+    if constexpr (!AMN && !BMN && BN == 256 && NJ == 1) {  // diagnostics: traced instantiation of the plain forward GEMM
+        if (g_gemm_trace != nullptr) {
+            GroupParams<NJ> gt = gp;
+            gt.trace = g_gemm_trace;
+            cudaFuncSetAttribute(gemm_tc_kernel<AMN, BMN, OBF, BN, NJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
+            cudaError_t le = launch_pdl(gemm_tc_kernel<AMN, BMN, OBF, BN, NJ, true>, dim3(grid), dim3(THREADS), Cfg<BN>::SMEM_BYTES, st, gt);
+            if (le != cudaSuccess) return set_err((int)le, "gemm_tc_kernel<trace> launch: %s", cudaGetErrorString(le));
+            return check_launch("gemm_tc_kernel<trace>");
+        }
+    }
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AMN, BMN, OBF, BN, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
@@ -519,6 +551,7 @@ static int gemm_tc_launch_jobs(const TcJob* jobs, int njobs, int a_mn_major, int
     }
     gp.njobs = njobs;
     gp.total = work;
+    gp.trace = nullptr;
     const int sms = num_sms();
     const int grid = work < sms ? work : sms;
     if (!a_mn_major && !b_mn_major)
