@@ -12,16 +12,19 @@ timeout 60 python scripts/attn_timeline.py 64 213 fwd | tee gpurun_out/attn_fwd_
 echo "== staged forward V2: parity + timeline"
 STCAT_ATTN_FWD_V2=1 timeout 120 python -m pytest tests/test_gpu_attention_tc.py -x -q 2>&1 | tail -2
 STCAT_ATTN_FWD_V2=1 timeout 60 python scripts/attn_timeline.py 64 213 fwd | tee gpurun_out/attn_fwd_timeline_v2.txt | tail -9
+echo "== staged forward V2 + token-staggered softmax groups: parity + timeline"
+STCAT_ATTN_FWD_V2=2 timeout 120 python -m pytest tests/test_gpu_attention_tc.py -x -q 2>&1 | tail -2
+STCAT_ATTN_FWD_V2=2 timeout 60 python scripts/attn_timeline.py 64 213 fwd | tee gpurun_out/attn_fwd_timeline_v2s.txt | tail -9
 echo "== backward timeline"
 timeout 60 python scripts/attn_timeline.py 64 213 bwd | tee gpurun_out/attn_bwd_timeline.txt | tail -20
 echo "== GEMM timeline (FFN linear1 forward; FFN linear2 forward)"
 timeout 60 python scripts/gemm_timeline.py 13632 2048 256 | tee gpurun_out/gemm_timeline_ffn1.txt | tail -20
 timeout 60 python scripts/gemm_timeline.py 13632 256 2048 | tee gpurun_out/gemm_timeline_ffn2.txt | tail -8
 echo "== graph-timed attention core, default vs V2"
-for v in "" 1; do
-  if [ -n "$v" ]; then export STCAT_ATTN_FWD_V2=1; fi
+for v in "" 1 2; do
+  if [ -n "$v" ]; then export STCAT_ATTN_FWD_V2=$v; fi
   timeout 100 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
 import json, sys
 d = json.loads(sys.stdin.read()); e = d['encoder_attention']
-print('V2' if '$v' else 'V1', 'step ms', round(d['ms_per_step'], 3), 'core us', round(e['us_core'], 2), 'block us', round(e['us_block'], 2))"
+print('V2 level $v' if '$v' else 'V1', 'step ms', round(d['ms_per_step'], 3), 'core us', round(e['us_core'], 2), 'block us', round(e['us_block'], 2))"
 done

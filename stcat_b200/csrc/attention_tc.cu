@@ -53,7 +53,10 @@ __device__ __forceinline__ uint32_t pack_prob_bf16x2(float lo, float hi) {
 // V2 (staged for round 2, selected by STCAT_ATTN_FWD_V2=1, S <= 224): integer bf16 pack, and O in its own TMEM columns
 // (S: set * 224, O: 448 + set * 32) so that the score MMA of the set's next item is issued right behind the PV MMA instead
 // of after the epilogue.
-template <bool DROP, bool V2>
+// STAG (with V2, STCAT_ATTN_FWD_V2=2): the two softmax warpgroups pass a token (named barriers 1 / 2) so that only one of them
+// is in the XU-bound pass 2 at a time, in the order A0 B0 A1 B1 ...: the other group's MMA hand-offs, epilogue and row-max
+// pass then run under it instead of both groups idling the XU pipe together (they otherwise run in lock step).
+template <bool DROP, bool V2, bool STAG = false>
 __global__ void __launch_bounds__(AT_FWD_THREADS, 1)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
@@ -301,6 +304,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                                  "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
                 }
             };
+            if (STAG) {  // wait for the token: group 0's item k follows group 1's item k-1, group 1's item k follows group 0's
+                if (g == 0) { if (k > 0) asm volatile("bar.sync 1, 256;" ::: "memory"); }
+                else asm volatile("bar.sync 2, 256;" ::: "memory");
+            }
             tmem_ld32(t_row, ra);
             tmem_ld_wait();
 #pragma unroll
@@ -315,6 +322,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     exp_chunk(rb, c + 1, mw[c + 1]);
                     tmem_ld_wait();
                 }
+            }
+            if (STAG) {  // pass the token on, if the other group still has an item that waits for it
+                const int n0 = (n_mine + 1) >> 1, n1 = n_mine >> 1;
+                if (g == 0) { if (k < n1) asm volatile("bar.arrive 2, 256;" ::: "memory"); }
+                else { if (k + 1 < n0) asm volatile("bar.arrive 1, 256;" ::: "memory"); }
             }
             const float sum = (s0 + s1) + (s2 + s3);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -732,6 +744,8 @@ int attn_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
         if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
         if (e != cudaSuccess) return set_err((int)e, "attn_tc_fwd: smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
@@ -739,9 +753,11 @@ int attn_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
     const int sms = num_sms();
     const int grid = total < sms ? total : sms;
     // V2 is staged for validation (profiles/r1_k_attn_fwd_timeline.md): opt-in, and only when the padded key count fits 224
-    const bool v2 = getenv("STCAT_ATTN_FWD_V2") != nullptr && ((S + 15) / 16) * 16 <= 224;
+    const char* v2env = getenv("STCAT_ATTN_FWD_V2");
+    const bool v2 = v2env != nullptr && ((S + 15) / 16) * 16 <= 224;
     auto go = [&](auto kern) { launch_pdl(kern, dim3(grid), dim3(AT_FWD_THREADS), AT_FWD_SMEM, st, tmQ, tmK, tmV, p); };
-    if (v2) { if (drop.thresh) go(attn_tc_fwd_kernel<true, true>); else go(attn_tc_fwd_kernel<false, true>); }
+    if (v2 && atoi(v2env) >= 2) { if (drop.thresh) go(attn_tc_fwd_kernel<true, true, true>); else go(attn_tc_fwd_kernel<false, true, true>); }
+    else if (v2) { if (drop.thresh) go(attn_tc_fwd_kernel<true, true>); else go(attn_tc_fwd_kernel<false, true>); }
     else { if (drop.thresh) go(attn_tc_fwd_kernel<true, false>); else go(attn_tc_fwd_kernel<false, false>); }
     return check_launch("attn_tc_fwd_kernel");
 }
