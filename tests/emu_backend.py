@@ -44,6 +44,33 @@ def drop_keep_scale(n, p, seed, offset, device="cpu"):
     return bits >= t, float(16777216.0 / (16777216.0 - t))
 
 
+class LayoutError(AssertionError):
+    pass
+
+
+def _mat(t, name):
+    """the layout rule of CudaBackend._mat (2-D view with unit column stride), minus the device check: a view the C ABI
+    would reject must fail the CPU tests of the host composition too"""
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise LayoutError(f"{name}: expected a 2-D row-major view, got shape {tuple(t.shape)} stride {t.stride()}")
+    if t.dtype not in (torch.float32, torch.bfloat16):
+        raise LayoutError(f"{name}: unsupported dtype {t.dtype}")
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def _flat(t, name, dtype=None):
+    """CudaBackend._flat: contiguous, of the expected dtype (None passes)"""
+    if t is None:
+        return
+    if not t.is_contiguous():
+        raise LayoutError(f"{name}: must be contiguous, got shape {tuple(t.shape)} stride {t.stride()}")
+    if dtype is not None and t.dtype != dtype:
+        raise LayoutError(f"{name}: expected {dtype}, got {t.dtype}")
+
+
+F32, BF16 = torch.float32, torch.bfloat16
+
+
 class EmuBackend:
     name = "emu"
 
@@ -52,6 +79,8 @@ class EmuBackend:
 
     # -- linear --------------------------------------------------------
     def linear_fwd(self, x, w, bias, y, relu=False, accumulate=False):
+        _mat(x, "x"), _mat(w, "w"), _mat(y, "y"), _flat(bias, "bias", F32)
+        assert w.shape[1] == x.shape[1] and tuple(y.shape) == (x.shape[0], w.shape[0])
         v = _f(x) @ _f(w).t()
         if bias is not None:
             v = v + bias
@@ -63,6 +92,11 @@ class EmuBackend:
         self.launches += 1
 
     def linear_bwd_data(self, dy, w, dx, accumulate=False, relu_y=None, dbias=None):
+        _mat(dy, "dy"), _mat(w, "w"), _mat(dx, "dx"), _flat(dbias, "dbias", F32)
+        assert w.shape[0] == dy.shape[1] and tuple(dx.shape) == (dy.shape[0], w.shape[1])
+        if relu_y is not None:
+            _mat(relu_y, "relu_y")
+            assert relu_y.shape == dx.shape
         v = _f(dy) @ _f(w)
         if accumulate:
             v = v + _f(dx)
@@ -74,6 +108,8 @@ class EmuBackend:
         self.launches += 1
 
     def linear_bwd_weight(self, dy, x, dw, db, accumulate=False):
+        _mat(dy, "dy"), _mat(x, "x"), _mat(dw, "dw"), _flat(db, "db", F32)
+        assert x.shape[0] == dy.shape[0] and tuple(dw.shape) == (dy.shape[1], x.shape[1]) and dw.dtype == F32
         v = _f(dy).t() @ _f(x)
         s = _f(dy).sum(0)
         if accumulate:
@@ -86,8 +122,24 @@ class EmuBackend:
         self.launches += 1
 
     def linear_group(self, kind, jobs):
+        assert 1 <= len(jobs) <= 12
+        in_dt = None
         for job in jobs:
             out = job["out"]
+            _mat(out, "out")
+            rows, cols = out.shape
+            assert 1 <= len(job["terms"]) <= 3
+            _flat(job.get("dbias"), "dbias", F32)
+            for a, b, bias in job["terms"]:
+                _mat(a, "a"), _mat(b, "b"), _flat(bias, "bias", F32)
+                assert a.dtype == b.dtype and (in_dt is None or in_dt == a.dtype), "operands of a grouped launch share one dtype"
+                in_dt = a.dtype
+                if kind == 0:
+                    assert a.shape[0] == rows and tuple(b.shape) == (cols, a.shape[1])
+                elif kind == 1:
+                    assert a.shape[0] == rows and tuple(b.shape) == (a.shape[1], cols)
+                else:
+                    assert tuple(a.shape) == (a.shape[0], rows) and tuple(b.shape) == (a.shape[0], cols)
             v = _f(out) if job.get("accumulate") else None
             for a, b, bias in job["terms"]:
                 if kind == 0:
@@ -108,6 +160,9 @@ class EmuBackend:
 
     # -- layernorm -----------------------------------------------------
     def layernorm_fwd(self, x, res, gamma, beta, y, y_bf16, mean, rstd, eps=1e-5):
+        for t, nm in ((x, "x"), (res, "res"), (gamma, "gamma"), (beta, "beta"), (y, "y"), (mean, "mean"), (rstd, "rstd")):
+            _flat(t, nm, F32)
+        _flat(y_bf16, "y_bf16", BF16)
         z = x if res is None else x + res
         mu = z.mean(-1)
         var = ((z - mu[:, None]) ** 2).mean(-1)
@@ -121,6 +176,10 @@ class EmuBackend:
         self.launches += 1
 
     def layernorm_bwd(self, dy, x, res, gamma, mean, rstd, dz, dgamma, dbeta, dz_bf16=None, dbias=None):
+        for t, nm in ((dy, "dy"), (x, "x"), (res, "res"), (gamma, "gamma"), (mean, "mean"), (rstd, "rstd"), (dz, "dz"),
+                      (dgamma, "dgamma"), (dbeta, "dbeta"), (dbias, "dbias")):
+            _flat(t, nm, F32)
+        _flat(dz_bf16, "dz_bf16", BF16)
         z = x if res is None else x + res
         xh = (z - mean[:, None]) * rstd[:, None]
         dg = dy * gamma
@@ -148,6 +207,7 @@ class EmuBackend:
         return s, hd
 
     def dropout(self, x, out, p, seed, offset):
+        assert x.is_contiguous() and out.is_contiguous() and x.dtype == out.dtype and x.shape == out.shape
         keep, sc = drop_keep_scale(x.numel(), p, seed, offset, x.device)
         _store(out, (_f(x).reshape(-1) * keep * sc).reshape(x.shape))
         self.launches += 1
@@ -159,7 +219,20 @@ class EmuBackend:
         keep, sc = drop_keep_scale(B * H * Lq * Lk, drop[0], drop[1], drop[2], device)
         return keep.reshape(B, H, Lq, Lk).float() * sc
 
+    @staticmethod
+    def _attn_layout(q1, q2, k1, k2, B, H, Lq, Lk, others):
+        ldq, ldk = _mat(q1, "q1"), _mat(k1, "k1")
+        assert q1.shape == (B * Lq, H * 32) and k1.shape == (B * Lk, H * 32)
+        assert (q2 is None) == (k2 is None)
+        if q2 is not None:  # the second score part shares the leading dimensions of the first
+            assert _mat(q2, "q2") == ldq and _mat(k2, "k2") == ldk and q2.shape == q1.shape and k2.shape == k1.shape
+        for t, nm, L in others:
+            _mat(t, nm)
+            assert t.shape == (B * L, H * 32) and t.dtype == q1.dtype, nm
+
     def attention_fwd(self, q1, q2, k1, k2, v, o, key_mask, lse, p_avg, B, H, Lq, Lk, scale, drop=None):
+        self._attn_layout(q1, q2, k1, k2, B, H, Lq, Lk, ((v, "v", Lk), (o, "o", Lq)))
+        _flat(key_mask, "key_mask", torch.uint8), _flat(lse, "lse", F32), _flat(p_avg, "p_avg", F32)
         s, hd = self._scores(q1, q2, k1, k2, key_mask, B, H, Lq, Lk, scale)
         p = torch.softmax(s, -1)
         m = self._pmask(drop, B, H, Lq, Lk, p.device)
@@ -174,6 +247,11 @@ class EmuBackend:
 
     def attention_bwd(self, q1, q2, k1, k2, v, d_o, key_mask, lse, dp_avg, delta, dq1, dq2, dk1, dk2, dv, B, H, Lq, Lk,
                       scale, o=None, drop=None):
+        oth = [(v, "v", Lk), (d_o, "d_o", Lq), (dq1, "dq1", Lq), (dk1, "dk1", Lk), (dv, "dv", Lk)] + ([(o, "o", Lq)] if o is not None else [])
+        self._attn_layout(q1, q2, k1, k2, B, H, Lq, Lk, oth)
+        if q2 is not None:
+            assert _mat(dq2, "dq2") == _mat(dq1, "dq1") and _mat(dk2, "dk2") == _mat(dk1, "dk1")
+        _flat(key_mask, "key_mask", torch.uint8), _flat(lse, "lse", F32), _flat(dp_avg, "dp_avg", F32), _flat(delta, "delta", F32)
         s, hd = self._scores(q1, q2, k1, k2, key_mask, B, H, Lq, Lk, scale)
         p = torch.exp(s - lse[..., None])
         g = hd(d_o, Lq)
@@ -199,6 +277,7 @@ class EmuBackend:
 
     # -- element-wise --------------------------------------------------
     def add(self, a, b, out, out_bf16=None):
+        _flat(a, "a", F32), _flat(b, "b", F32), _flat(out, "out", F32), _flat(out_bf16, "out_bf16", BF16)
         z = a + b
         if out is not None:
             out.copy_(z)
@@ -207,10 +286,12 @@ class EmuBackend:
         self.launches += 1
 
     def relu_bwd(self, y, dy):
+        _flat(y, "y"), _flat(dy, "dy")
         dy.masked_fill_(~(_f(y) > 0), 0)
         self.launches += 1
 
     def cast_bf16(self, x, out, transpose=False):
+        _flat(x, "x", F32), _flat(out, "out", BF16)
         out.copy_((x.t() if transpose else x).to(torch.bfloat16))
         self.launches += 1
 
