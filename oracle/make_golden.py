@@ -38,6 +38,9 @@ CASES = {
     "b3_ragged_T4_1_6": dict(durations=[4, 1, 6], H=3, W=5, L=5, ragged=True, max_video_len=300, seed=3),
     # a larger single clip (res 320 -> 10x10), 16 tokens
     "b1_T12_res320_L16": dict(durations=[12], H=10, W=10, L=16, ragged=False, max_video_len=300, seed=4),
+    # MODEL.STCAT.FROM_SCRATCH False: the box decoder's cross attention is an nn.MultiheadAttention (MDETR initialisation
+    # branch, query_decoder.py:287-288, 372-376, 381-384, 409-416); ragged batch
+    "b2_ragged_T4_6_mdetr": dict(durations=[4, 6], H=5, W=4, L=7, ragged=True, max_video_len=200, seed=5, from_scratch=False),
 }
 
 
@@ -93,10 +96,11 @@ class _Boxes:
         return self.bbox.shape[0]
 
 
-def make_cfg(ref, max_video_len):
+def make_cfg(ref, max_video_len, from_scratch=True):
     cfg = ref.cfg.clone()
     cfg.defrost() if hasattr(cfg, "defrost") else None
-    cfg.merge_from_list(["INPUT.MAX_VIDEO_LEN", max_video_len, "MODEL.STCAT.DROPOUT", 0.0])
+    cfg.merge_from_list(["INPUT.MAX_VIDEO_LEN", max_video_len, "MODEL.STCAT.DROPOUT", 0.0,
+                         "MODEL.STCAT.FROM_SCRATCH", bool(from_scratch)])
     return cfg
 
 
@@ -106,7 +110,7 @@ def checksum(t: torch.Tensor):
 
 
 def run_case(ref, name, spec):
-    cfg = make_cfg(ref, spec["max_video_len"])
+    cfg = make_cfg(ref, spec["max_video_len"], spec.get("from_scratch", True))
     torch.manual_seed(0)
     model = RefHotPath(ref, cfg).eval()  # eval: the 0.3 head dropout is identity; grads still flow
     sd = synthetic.fill_state_dict(model.state_dict(), seed=spec["seed"])
@@ -248,9 +252,12 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(8)
     ref = import_reference()
+    only = sys.argv[1:]  # optional: regenerate just the named cases (the others are deterministic and stay as committed)
     for name, spec in CASES.items():
-        run_case(ref, name, spec)
-    run_map2d()
+        if not only or name in only:
+            run_case(ref, name, spec)
+    if not only or "map2d_N16" in only:
+        run_map2d()
 
 
 if __name__ == "__main__":

@@ -298,8 +298,11 @@ def _padded_from_frames(x: Tensor, durations: Sequence[int], t: int) -> Tensor:
 
 
 def box_decoder_layer(P: Params, prefix: str, tgt, memory, query_mask, memory_mask, pos, query_pos,
-                      query_time, query_sine, durations, is_first: bool, nhead: int, prec: Prec = FP32):
-    """TransformerDecoderLayer.forward, FROM_SCRATCH=True branch (query_decoder.py:310-438)."""
+                      query_time, query_sine, durations, is_first: bool, nhead: int, prec: Prec = FP32,
+                      from_scratch: bool = True):
+    """TransformerDecoderLayer.forward (query_decoder.py:310-438): the FROM_SCRATCH=True branch (custom attention over the
+    per-head [content ; position] concat) and the FROM_SCRATCH=False branch (MDETR-style nn.MultiheadAttention,
+    :372-376, 381-384, 409-416)."""
     L = lambda name, x: linear(x, P[f"{prefix}.{name}.weight"], P[f"{prefix}.{name}.bias"], prec)
     t, b, c = tgt.shape
     # self attention over the t queries of each video :329-345
@@ -319,10 +322,17 @@ def box_decoder_layer(P: Params, prefix: str, tgt, memory, query_mask, memory_ma
         kc = kc + kp
     dh = c // nhead
     qs = L("ca_qpos_sine_proj", query_sine)
-    q2 = torch.cat([qc.view(t, b, nhead, dh), qs.view(t, b, nhead, dh)], 3).reshape(t, b, 2 * c)
-    k2 = torch.cat([kc.view(n_tok, n, nhead, dh), kp.view(n_tok, n, nhead, dh)], 3).reshape(n_tok, n, 2 * c)
-    q_cross = _frames_from_padded(q2, durations)  # [1,n,2c]
-    o, _ = custom_mha(P, f"{prefix}.cross_attn", q_cross, k2, vv, nhead, memory_mask, prec)
+    if from_scratch:
+        q2 = torch.cat([qc.view(t, b, nhead, dh), qs.view(t, b, nhead, dh)], 3).reshape(t, b, 2 * c)
+        k2 = torch.cat([kc.view(n_tok, n, nhead, dh), kp.view(n_tok, n, nhead, dh)], 3).reshape(n_tok, n, 2 * c)
+        q_cross = _frames_from_padded(q2, durations)  # [1,n,2c]
+        o, _ = custom_mha(P, f"{prefix}.cross_attn", q_cross, k2, vv, nhead, memory_mask, prec)
+    else:
+        # :375-376 q = (q + sine) + ca_qtime_proj(time); :384 k = k + k_pos (a second time in the first layer)
+        q1 = (qc + qs) + L("ca_qtime_proj", query_time)
+        k1 = kc + kp
+        q_cross = _frames_from_padded(q1, durations)  # [1,n,c]
+        o, _ = torch_mha(P, f"{prefix}.cross_attn_image", q_cross, k1, vv, nhead, memory_mask, prec)
     o = _padded_from_frames(o, durations, t)
     tgt = layer_norm(tgt + o, P[f"{prefix}.norm3.weight"], P[f"{prefix}.norm3.bias"])
     # FFN :435-437
@@ -332,7 +342,7 @@ def box_decoder_layer(P: Params, prefix: str, tgt, memory, query_mask, memory_ma
 
 
 def box_decoder(P: Params, prefix: str, bbox_prefix: str, tgt, memory, query_mask, memory_mask, pos, anchor,
-                query_time, durations, nlayers: int, nhead: int, prec: Prec = FP32):
+                query_time, durations, nlayers: int, nhead: int, prec: Prec = FP32, from_scratch: bool = True):
     """TransformerDecoder.forward with bbox_embed set (query_decoder.py:169-247).
     Returns (hs [nl,b,t,d], refs [nl,b,t,4])."""
     d = tgt.shape[-1]
@@ -344,7 +354,7 @@ def box_decoder(P: Params, prefix: str, bbox_prefix: str, tgt, memory, query_mas
         scale = 1 if li == 0 else mlp(P, f"{prefix}.query_scale", out, 2, prec)  # :195-198
         qsine = sine[..., :d] * scale  # :201
         out, _ = box_decoder_layer(P, f"{prefix}.layers.{li}", out, memory, query_mask, memory_mask, pos,
-                                   query_pos, query_time, qsine, durations, li == 0, nhead, prec)
+                                   query_pos, query_time, qsine, durations, li == 0, nhead, prec, from_scratch)
         new_anchor = torch.sigmoid(mlp(P, bbox_prefix, out, 3, prec) + inverse_sigmoid(anchor))  # :213-215
         if li != nlayers - 1:
             refs.append(new_anchor)
@@ -409,7 +419,7 @@ def decoder_forward(P: Params, cfg, memory_cache: dict, vis_pos: Tensor, prec: P
     mem_pos = torch.cat([mem_pos, torch.zeros_like(memory[n_vis:])], 0)
     tgt = torch.zeros(t, b, d, dtype=dt)
     outputs = box_decoder(P, f"{prefix}.decoder", bbox_prefix, tgt, memory, query_mask, memory_mask, mem_pos,
-                          anchors, query_time, durations, nlayers, nhead, prec)
+                          anchors, query_time, durations, nlayers, nhead, prec, bool(S.FROM_SCRATCH))
     outputs_temp = time_decoder(P, f"{prefix}.temp_decoder", tgt.clone(), memory, query_mask, memory_mask,
                                 mem_pos, query_temporal, query_time, durations, nlayers, nhead, prec)
     return outputs, outputs_temp

@@ -192,9 +192,12 @@ class _Ctx:
 
 
 class TransformerDecoderLayer(nn.Module):
-    """Box-decoder layer parameters + forward (query_decoder.py:250-438, FROM_SCRATCH branch)."""
+    """Box-decoder layer parameters + forward (query_decoder.py:250-438).  ``from_scratch`` selects the cross attention:
+    True (both shipped experiment files): the reference's own attention without in-projections over the per-head
+    [content ; position] concat, run as a two-part score; False (the MDETR initialisation branch, :287-288): an
+    ``nn.MultiheadAttention`` named ``cross_attn_image`` over q = content + sine + time, k = content + position."""
 
-    def __init__(self, d: int, nhead: int, ffn: int, first: bool):
+    def __init__(self, d: int, nhead: int, ffn: int, first: bool, from_scratch: bool = True):
         super().__init__()
         for nm in ("sa_qcontent_proj", "sa_qpos_proj", "sa_qtime_proj", "sa_kcontent_proj", "sa_kpos_proj",
                    "sa_ktime_proj", "sa_v_proj"):
@@ -204,7 +207,9 @@ class TransformerDecoderLayer(nn.Module):
         self.ca_qpos_proj = LinearP(d, d) if first else None  # layers >= 1: None (query_decoder.py:166-167)
         for nm in ("ca_kcontent_proj", "ca_kpos_proj", "ca_qtime_proj", "ca_v_proj", "ca_qpos_sine_proj"):
             setattr(self, nm, LinearP(d, d))
-        self.cross_attn = OutProjOnly(d)
+        self.from_scratch = bool(from_scratch)
+        self.cross_attn = OutProjOnly(d) if from_scratch else None
+        self.cross_attn_image = None if from_scratch else MHAP(d, nhead)
         self.linear1 = LinearP(d, ffn)
         self.linear2 = LinearP(ffn, d)
         self.norm1, self.norm3, self.norm4 = NormP(d), NormP(d), NormP(d)
@@ -215,6 +220,15 @@ class TransformerDecoderLayer(nn.Module):
     def memory_side(self, c: _Ctx, is_first: bool):
         """Key / value projections of the encoder memory for this layer (query_decoder.py:355-366).  They do not
         depend on the queries, so the decoder computes them for all layers up front on a side stream."""
+        if not self.from_scratch:
+            # k = ca_kcontent(memory) + ca_kpos(pos), with ca_kpos(pos) a second time in the first layer (:365 and :384), then
+            # the in-projections of cross_attn_image (torch functional.py:5866-5873) on k and on v = ca_v(memory)
+            kpos = (c.pos_op, self.ca_kpos_proj.weight, self.ca_kpos_proj.bias)
+            k = ops.linear_sum([(c.mem_op, self.ca_kcontent_proj.weight, self.ca_kcontent_proj.bias), kpos] +
+                               ([kpos] if is_first else []), out_bf16=True)
+            v = _lin(self.ca_v_proj, c.mem_op, out_bf16=True)
+            return (_mha_proj(self.cross_attn_image, 1, k, out_bf16=True), None,
+                    _mha_proj(self.cross_attn_image, 2, v, out_bf16=True))
         kp = _lin(self.ca_kpos_proj, c.pos_op, out_bf16=True)  # [n*M, d]
         vv = _lin(self.ca_v_proj, c.mem_op, out_bf16=True)
         if is_first:
@@ -248,12 +262,23 @@ class TransformerDecoderLayer(nn.Module):
         # ---- time-aligned cross attention: query of frame f sees only frame f's tokens (:350-429) ----
         kc, kp, vv = mem_kv() if callable(mem_kv) else mem_kv
         qc_terms = [(0, *L(self.ca_qcontent_proj))] + ([(1, *L(self.ca_qpos_proj))] if is_first else [])
-        qc, qs = ops.linear_group(
-            [(tgt, tgt_op), (query_pos, pos_op), (query_sine, sine_op)],
-            [{"terms": qc_terms, "out_bf16": True}, {"terms": [(2, *L(self.ca_qpos_sine_proj))], "out_bf16": True}])
-        o, _ = ops.attention(c.frames(qc), kc, vv, c.n, H, 1, c.M, float(2 * d // H) ** -0.5, key_mask=c.key_mask,
-                             q2=c.frames(qs), k2=kp, drop_p=p)
-        o = ops.dropout(_lin(self.cross_attn.out_proj, o), p)
+        if self.from_scratch:
+            qc, qs = ops.linear_group(
+                [(tgt, tgt_op), (query_pos, pos_op), (query_sine, sine_op)],
+                [{"terms": qc_terms, "out_bf16": True}, {"terms": [(2, *L(self.ca_qpos_sine_proj))], "out_bf16": True}])
+            o, _ = ops.attention(c.frames(qc), kc, vv, c.n, H, 1, c.M, float(2 * d // H) ** -0.5, key_mask=c.key_mask,
+                                 q2=c.frames(qs), k2=kp, drop_p=p)
+            o = ops.dropout(_lin(self.cross_attn.out_proj, o), p)
+        else:
+            # q = ca_qcontent(tgt) [+ ca_qpos(query_pos)] + ca_qpos_sine(sine) + ca_qtime(time) (:355-376: the per-head views
+            # of :371-375 add element-wise), then nn.MultiheadAttention: in-projection, one query per frame, out-projection
+            qa, qt = ops.linear_group(
+                [(tgt, tgt_op), (query_pos, pos_op), (query_sine, sine_op), (query_time, time_op)],
+                [{"terms": qc_terms + [(2, *L(self.ca_qpos_sine_proj))]}, {"terms": [(3, *L(self.ca_qtime_proj))]}])
+            ca = self.cross_attn_image
+            Q = _mha_proj(ca, 0, c.frames(ops.add(qa, qt)), out_bf16=True)
+            o, _ = ops.attention(Q, kc, vv, c.n, H, 1, c.M, float(d // H) ** -0.5, key_mask=c.key_mask, drop_p=p)
+            o = ops.dropout(_lin(ca.out_proj, o), p)
         tgt, tgt_op = ops.layer_norm(c.padded(o), tgt, self.norm3.weight, self.norm3.bias, self.norm3.eps, want_op=True)
         # ---- FFN (:435-437) ----
         return ops.ffn_block(tgt, tgt_op, self.linear1.weight, self.linear1.bias, self.linear2.weight,
@@ -263,9 +288,10 @@ class TransformerDecoderLayer(nn.Module):
 class TransformerDecoder(nn.Module):
     """Anchor-refining box decoder (query_decoder.py:150-247)."""
 
-    def __init__(self, d: int, nhead: int, ffn: int, num_layers: int, query_dim: int):
+    def __init__(self, d: int, nhead: int, ffn: int, num_layers: int, query_dim: int, from_scratch: bool = True):
         super().__init__()
-        self.layers = nn.ModuleList(TransformerDecoderLayer(d, nhead, ffn, first=i == 0) for i in range(num_layers))
+        self.layers = nn.ModuleList(TransformerDecoderLayer(d, nhead, ffn, first=i == 0, from_scratch=from_scratch)
+                                    for i in range(num_layers))
         self.num_layers = num_layers
         self.norm = NormP(d)
         self.query_scale = MLPP(d, d, d, 2)
@@ -405,9 +431,6 @@ class QueryDecoder(nn.Module):
         super().__init__()
         _check_cfg(cfg)
         S = cfg.MODEL.STCAT
-        if not S.FROM_SCRATCH:
-            raise NotImplementedError("MODEL.STCAT.FROM_SCRATCH=False (the MDETR-initialised cross_attn_image branch, "
-                                      "query_decoder.py:285-288) is not implemented by stcat_b200")
         d = S.HIDDEN
         self.d_model = d
         self.query_pos_dim = S.QUERY_DIM
@@ -416,7 +439,7 @@ class QueryDecoder(nn.Module):
         self.return_weights = cfg.SOLVER.USE_ATTN
         self.dropout_p = float(S.DROPOUT)
         self.template_generator = TemplateGenerator(d, S.QUERY_DIM)
-        self.decoder = TransformerDecoder(d, S.HEADS, S.FFN_DIM, S.DEC_LAYERS, S.QUERY_DIM)
+        self.decoder = TransformerDecoder(d, S.HEADS, S.FFN_DIM, S.DEC_LAYERS, S.QUERY_DIM, bool(S.FROM_SCRATCH))
         self.temp_decoder = TimeDecoder(d, S.HEADS, S.FFN_DIM, S.DEC_LAYERS)
         max_len = self.video_max_len + 1
         self.time_embed = LearnedTable(max_len, d) if S.USE_LEARN_TIME_EMBED else SineTable(max_len, d)

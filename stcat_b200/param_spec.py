@@ -72,7 +72,10 @@ def decoder_spec(cfg, prefix: str = "ground_decoder", with_bbox_alias: bool = Tr
             _linear(out, f"{p}.ca_qpos_proj", d, d)  # layers >= 1 set it to None (query_decoder.py:166-167)
         for nm in ("ca_kcontent_proj", "ca_kpos_proj", "ca_qtime_proj", "ca_v_proj", "ca_qpos_sine_proj"):
             _linear(out, f"{p}.{nm}", d, d)
-        _linear(out, f"{p}.cross_attn.out_proj", d, d)
+        if S.FROM_SCRATCH:  # custom MHA without in-projections (query_decoder.py:285-286)
+            _linear(out, f"{p}.cross_attn.out_proj", d, d)
+        else:               # MDETR-initialised nn.MultiheadAttention (query_decoder.py:287-288)
+            _mha(out, f"{p}.cross_attn_image", d)
         _linear(out, f"{p}.linear1", F, d)
         _linear(out, f"{p}.linear2", d, F)
         for nm in ("norm1", "norm3", "norm4"):

@@ -8,7 +8,7 @@ from stcat_b200 import synthetic
 from stcat_b200.param_spec import synthetic_params
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_CASES = ["b1_T8_res224_L8", "b2_ragged_T5_3", "b3_ragged_T4_1_6", "b1_T12_res320_L16"]
+GOLDEN_CASES = ["b1_T8_res224_L8", "b2_ragged_T5_3", "b3_ragged_T4_1_6", "b1_T12_res320_L16", "b2_ragged_T4_6_mdetr"]
 
 
 def load_golden(name):
@@ -17,7 +17,8 @@ def load_golden(name):
 
 def cfg_for(spec, dropout=0.0):
     cfg = get_default_cfg()
-    cfg.merge_from_list(["INPUT.MAX_VIDEO_LEN", spec["max_video_len"], "MODEL.STCAT.DROPOUT", dropout])
+    cfg.merge_from_list(["INPUT.MAX_VIDEO_LEN", spec["max_video_len"], "MODEL.STCAT.DROPOUT", dropout,
+                         "MODEL.STCAT.FROM_SCRATCH", bool(spec.get("from_scratch", True))])
     return cfg
 
 

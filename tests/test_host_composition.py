@@ -77,7 +77,7 @@ def test_forward_matches_golden(name):
             assert rel_err(a[k], g[k]) < TOL, k
 
 
-@pytest.mark.parametrize("name", ["b1_T8_res224_L8", "b3_ragged_T4_1_6"])
+@pytest.mark.parametrize("name", ["b1_T8_res224_L8", "b3_ragged_T4_1_6", "b2_ragged_T4_6_mdetr"])
 def test_gradients_match_golden(name):
     fx = load_golden(name)
     spec = fx["spec"]
@@ -122,6 +122,33 @@ def test_bf16_mode_tracks_rounded_oracle():
                                  inp["text_mask"], inp["text_memory"], prec=O.Prec(round_operands="bf16"))
     for k in ("pred_boxes", "pred_sted", "pred_actioness", "weights"):
         assert rel_err(out[k], ref[k]) < 2e-2, k  # loose: rounding points differ slightly
+
+
+def test_mdetr_branch_bf16_mode_forward_and_backward():
+    """MODEL.STCAT.FROM_SCRATCH False (cross_attn_image branch of the box decoder) in bf16 operand mode: tracks the oracle with
+    bf16-rounded operands, and the backward chain runs through the operand-dtype plumbing of that branch."""
+    fx = load_golden("b2_ragged_T4_6_mdetr")
+    spec = fx["spec"]
+    cfg = cfg_for(spec)
+    assert not cfg.MODEL.STCAT.FROM_SCRATCH
+    inp = case_inputs(spec)
+    P = case_params(cfg, spec)
+    m = build(cfg, P).eval()
+    assert "ground_decoder.decoder.layers.0.cross_attn_image.in_proj_weight" in m.state_dict()
+    assert not any(".decoder.layers.0.cross_attn." in k for k in m.state_dict())
+    ops.set_precision("bf16")
+    out, vis, txt = run_model(m, inp, grad=True)
+    with torch.no_grad():
+        ref = O.hot_path_forward(P, cfg, inp["vis_features"], inp["vis_mask"], inp["durations"], inp["vis_pos"],
+                                 inp["text_mask"], inp["text_memory"], prec=O.Prec(round_operands="bf16"))
+    for k in ("pred_boxes", "pred_sted", "pred_actioness", "weights"):
+        assert rel_err(out[k], ref[k]) < 2e-2, k
+    (out["pred_boxes"].sum() + out["pred_sted"].sum()).backward()
+    named = dict(m.named_parameters())
+    for k in ("ground_decoder.decoder.layers.0.cross_attn_image.in_proj_weight", "ground_decoder.decoder.layers.3.ca_qtime_proj.weight",
+              "ground_decoder.decoder.layers.0.ca_kpos_proj.weight"):
+        assert named[k].grad is not None and torch.isfinite(named[k].grad).all() and float(named[k].grad.abs().max()) > 0, k
+    assert torch.isfinite(vis.grad).all() and torch.isfinite(txt.grad).all()
 
 
 @pytest.mark.parametrize("name", ["b1_T8_res224_L8", "b2_ragged_T5_3"])
