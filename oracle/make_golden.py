@@ -248,6 +248,31 @@ def run_map2d():
     print(f"map2d: -> {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
 
 
+def run_map2d_attn():
+    """The default TEMP_HEAD ('attn': row / column attention over the 2-D map) of the orphaned map2d head, small map."""
+    ref, m2d = import_reference_map2d()
+    cfg = ref.cfg.clone()
+    cfg.merge_from_list(["MODEL.STCAT.MAX_MAP_SIZE", 16, "MODEL.STCAT.POOLING_COUNTS", [3, 2, 2],
+                         "MODEL.STCAT.TEMP_HEAD", "attn", "MODEL.STCAT.TEMP_PRED_LAYERS", 2, "MODEL.STCAT.DROPOUT", 0.0])
+    cfg.MODEL.TEMPFORMER = cfg.MODEL.STCAT
+    torch.manual_seed(0)
+    head = m2d.TempPredictionHead(cfg).eval()
+    sd = synthetic.fill_state_dict(head.state_dict(), seed=9)
+    head.load_state_dict(sd)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 1, 20, 256, generator=g)
+    fx = {"cfg": dict(MAX_MAP_SIZE=16, POOLING_COUNTS=[3, 2, 2], TEMP_HEAD="attn", TEMP_PRED_LAYERS=2, HEADS=8, HIDDEN=256,
+                      FFN_DIM=2048), "seed": 9, "x": x,
+          "shapes": {k: tuple(v.shape) for k, v in head.state_dict().items()}}
+    with torch.no_grad():
+        fx["scores_eval"] = head(x).clone()
+        head.train()
+        fx["scores_train"] = head(x).clone()
+    path = os.path.join(GOLDEN_DIR, "map2d_attn_N16.pt")
+    torch.save(fx, path)
+    print(f"map2d attn: -> {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(8)
@@ -258,6 +283,8 @@ def main():
             run_case(ref, name, spec)
     if not only or "map2d_N16" in only:
         run_map2d()
+    if not only or "map2d_attn_N16" in only:
+        run_map2d_attn()
 
 
 if __name__ == "__main__":

@@ -675,3 +675,34 @@ def map2d_conv_head(P: Params, prefix: str, x: Tensor, cfg_stcat, training: bool
     s = F.conv2d(m, P[f"{prefix}.predictor.weight"], P[f"{prefix}.predictor.bias"]).squeeze(1)
     s = s.view(nl, b, N, N)
     return s if training else torch.sigmoid(s) * mask2d
+
+
+def map2d_attn_head(P: Params, prefix: str, x: Tensor, cfg_stcat, training: bool = False, prec: Prec = FP32) -> Tensor:
+    """TempPredictionHead.forward with TEMP_HEAD='attn' (map2d_head.py:105-127, 151-205), dropout = identity.
+    Per map [d,N,N] -> [N,N,d]; per layer: row attention (sequence = first axis, batch = second, key_padding_mask =
+    mask2d AS IS: the reference passes the *valid* mask where torch expects True = ignore, and indexes it [batch, key],
+    i.e. transposed w.r.t. the map -- both quirks are reproduced), column attention on the row output with the transposed
+    mask, residual + norm1, FFN + norm2.  x [layers,b,T,d] -> scores [layers,b,N,N]."""
+    N, counts = cfg_stcat.MAX_MAP_SIZE, cfg_stcat.POOLING_COUNTS
+    nhead, nlayers = cfg_stcat.HEADS, cfg_stcat.TEMP_PRED_LAYERS
+    nl, b, t, d = x.shape
+    mask2d, _, _ = map2d_masks(N, counts)
+    maps = gen_2d_map(x.reshape(-1, t, d), N, counts)  # [nl*b, d, N, N]
+    outs = []
+    for m in maps:
+        src = m.permute(1, 2, 0)  # [N,N,d]
+        for li in range(nlayers):
+            pf = f"{prefix}.encoder.layers.{li}"
+            a, _ = torch_mha(P, f"{pf}.self_attn_row", src, src, src, nhead, mask2d, prec)          # :181-185
+            a = a.permute(1, 0, 2)                                                                      # :188
+            a, _ = torch_mha(P, f"{pf}.self_attn_col", a, a, a, nhead, mask2d.permute(1, 0), prec)     # :189-193
+            a = a.permute(1, 0, 2)                                                                      # :194
+            src = layer_norm(src + a, P[f"{pf}.norm1.weight"], P[f"{pf}.norm1.bias"])
+            h = torch.relu(linear(src, P[f"{pf}.linear1.weight"], P[f"{pf}.linear1.bias"], prec))
+            y = linear(h, P[f"{pf}.linear2.weight"], P[f"{pf}.linear2.bias"], prec)
+            src = layer_norm(src + y, P[f"{pf}.norm2.weight"], P[f"{pf}.norm2.bias"])
+        outs.append(src.permute(2, 0, 1))
+    m = torch.stack(outs)
+    s = F.conv2d(m, P[f"{prefix}.predictor.weight"], P[f"{prefix}.predictor.bias"]).squeeze(1)
+    s = s.view(nl, b, N, N)
+    return s if training else torch.sigmoid(s) * mask2d

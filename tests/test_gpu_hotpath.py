@@ -311,3 +311,31 @@ def test_train_mode_dropout_matches_host_emulation():
     assert g_gpu.keys() == g_cpu.keys()
     for k in g_cpu:
         assert rel_err(g_gpu[k], g_cpu[k]) < 1e-2 or float((g_gpu[k] - g_cpu[k]).abs().max()) < 1e-6, (k, rel_err(g_gpu[k], g_cpu[k]))
+
+
+@pytest.mark.parametrize("variant", ["conv", "attn"])
+def test_map2d_head_matches_reference_fixture(variant):
+    """The 2-D temporal proposal head (map2d_head.py) on the B200 through the C ABI (stcat_map2d_pool, GEMMs
+    over the im2col of the map / packed in-projections, attention over map rows and columns, LayerNorm, FFN) against the
+    scores of the unmodified reference head: train-mode logits and eval-mode sigmoid * mask, exact-fp32 mode, 1e-3."""
+    from stcat_b200.config import get_default_cfg
+    from stcat_b200.map2d import TempPredictionHead
+    from stcat_b200.synthetic import fill_param
+
+    fx = load_golden("map2d_N16" if variant == "conv" else "map2d_attn_N16")
+    c = fx["cfg"]
+    cfg = get_default_cfg()
+    extra = (["MODEL.STCAT.TEMP_HEAD", "conv", "MODEL.STCAT.KERNAL_SIZE", c["KERNAL_SIZE"], "MODEL.STCAT.CONV_LAYERS", c["CONV_LAYERS"]]
+             if variant == "conv" else ["MODEL.STCAT.TEMP_HEAD", "attn", "MODEL.STCAT.TEMP_PRED_LAYERS", c["TEMP_PRED_LAYERS"]])
+    cfg.merge_from_list(["MODEL.STCAT.MAX_MAP_SIZE", c["MAX_MAP_SIZE"], "MODEL.STCAT.POOLING_COUNTS", c["POOLING_COUNTS"],
+                         "MODEL.STCAT.DROPOUT", 0.0] + extra)
+    head = TempPredictionHead(cfg)
+    head.load_state_dict({k: fill_param(k, tuple(v.shape), fx["seed"]) for k, v in head.state_dict().items()})
+    head = head.cuda()
+    before = ops.get_backend().launches
+    with torch.no_grad():
+        head.train()
+        assert rel_err(head(fx["x"].cuda()), fx["scores_train"]) < TOL
+        head.eval()
+        assert rel_err(head(fx["x"].cuda()), fx["scores_eval"]) < TOL
+    assert ops.get_backend().launches > before

@@ -208,3 +208,68 @@ def test_grad_fusion_matches_autograd_accumulation():
             assert g2 is None or float(g2.abs().max()) == 0.0, k
         else:
             assert rel_err(g2, g) < 1e-5 or float((g2 - g).abs().max()) < 1e-7, k
+
+
+def _map2d_head(fx, extra):
+    from stcat_b200.config import get_default_cfg
+    from stcat_b200.map2d import TempPredictionHead
+    from stcat_b200.synthetic import fill_param
+
+    cfg = get_default_cfg()
+    c = fx["cfg"]
+    cfg.merge_from_list(["MODEL.STCAT.MAX_MAP_SIZE", c["MAX_MAP_SIZE"], "MODEL.STCAT.POOLING_COUNTS", c["POOLING_COUNTS"],
+                         "MODEL.STCAT.DROPOUT", 0.0] + extra)
+    head = TempPredictionHead(cfg)
+    sd = {k: fill_param(k, tuple(v.shape), fx["seed"]) for k, v in head.state_dict().items()}
+    head.load_state_dict(sd)
+    return head
+
+
+@pytest.mark.parametrize("variant", ["conv", "attn"])
+def test_map2d_head_matches_reference_fixture(variant):
+    """stcat_b200.map2d.TempPredictionHead through the emulated C ABI vs the scores of the unmodified
+    reference head (tests/golden/map2d*_N16.pt), train-mode logits and eval-mode sigmoid * mask; same state-dict names."""
+    if variant == "conv":
+        fx = load_golden("map2d_N16")
+        c = fx["cfg"]
+        head = _map2d_head(fx, ["MODEL.STCAT.TEMP_HEAD", "conv", "MODEL.STCAT.KERNAL_SIZE", c["KERNAL_SIZE"],
+                                "MODEL.STCAT.CONV_LAYERS", c["CONV_LAYERS"]])
+        assert set(head.state_dict()) == {f"encoder.convs.{i}.{p}" for i in range(c["CONV_LAYERS"]) for p in ("weight", "bias")} | \
+            {"predictor.weight", "predictor.bias"}
+        with torch.no_grad():
+            m = head.map_maker(fx["x"].view(-1, 20, 256))
+            assert torch.equal(m, fx["map2d"])
+            assert torch.equal(head.map_maker(fx["x2"].view(-1, 12, 256)), fx["map2d_2"])  # T < N: adaptive max-pool upsampling
+    else:
+        fx = load_golden("map2d_attn_N16")
+        c = fx["cfg"]
+        head = _map2d_head(fx, ["MODEL.STCAT.TEMP_HEAD", "attn", "MODEL.STCAT.TEMP_PRED_LAYERS", c["TEMP_PRED_LAYERS"]])
+        assert {k: tuple(v.shape) for k, v in head.state_dict().items()} == fx["shapes"]
+    with torch.no_grad():
+        head.train()
+        assert rel_err(head(fx["x"]), fx["scores_train"]) < 1e-4
+        head.eval()
+        assert rel_err(head(fx["x"]), fx["scores_eval"]) < 1e-4
+
+
+@pytest.mark.parametrize("variant", ["conv", "attn"])
+def test_map2d_head_gradients_match_oracle(variant):
+    """backward of the head (parameters and clip features) vs autograd through the oracle restatement"""
+    from stcat_b200.config import CfgNode
+
+    fx = load_golden("map2d_N16" if variant == "conv" else "map2d_attn_N16")
+    c = fx["cfg"]
+    extra = (["MODEL.STCAT.TEMP_HEAD", "conv", "MODEL.STCAT.KERNAL_SIZE", c["KERNAL_SIZE"], "MODEL.STCAT.CONV_LAYERS", c["CONV_LAYERS"]]
+             if variant == "conv" else ["MODEL.STCAT.TEMP_HEAD", "attn", "MODEL.STCAT.TEMP_PRED_LAYERS", c["TEMP_PRED_LAYERS"]])
+    head = _map2d_head(fx, extra).train()
+    x = fx["x"].clone().requires_grad_(True)
+    g = torch.randn(fx["scores_train"].shape, generator=torch.Generator().manual_seed(3))
+    (head(x) * g).sum().backward()
+    P = {"head." + k: v.detach().clone().requires_grad_(True) for k, v in head.state_dict().items()}
+    xo = fx["x"].clone().requires_grad_(True)
+    node = CfgNode(dict(c, HEADS=8, HIDDEN=256, FFN_DIM=2048))
+    fn = O.map2d_conv_head if variant == "conv" else O.map2d_attn_head
+    (fn(P, "head", xo, node, training=True) * g).sum().backward()
+    assert rel_err(x.grad, xo.grad) < 1e-4
+    for k, prm in head.named_parameters():
+        assert rel_err(prm.grad, P["head." + k].grad) < 1e-4, k

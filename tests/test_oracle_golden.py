@@ -118,6 +118,20 @@ def test_map2d_matches_reference():
     assert rel_err(s_train, fx["scores_train"]) < 1e-4
 
 
+def test_map2d_attn_head_matches_reference():
+    """TEMP_HEAD 'attn' (the reference default): row / column attention over the map with the reference's mask quirks"""
+    fx = load_golden("map2d_attn_N16")
+    from stcat_b200.config import CfgNode
+    from stcat_b200.synthetic import fill_param
+
+    c = CfgNode(fx["cfg"])
+    P = {"head." + k: fill_param(k, shape, fx["seed"]) for k, shape in fx["shapes"].items()}
+    s_eval = O.map2d_attn_head(P, "head", fx["x"], c, training=False)
+    s_train = O.map2d_attn_head(P, "head", fx["x"], c, training=True)
+    assert rel_err(s_eval, fx["scores_eval"]) < 1e-4
+    assert rel_err(s_train, fx["scores_train"]) < 1e-4
+
+
 def test_fp64_oracle_matches_fp64_reference(case):
     """Semantic pin at 1e-6: oracle in float64 vs the reference run in float64 (forward and backward)."""
     fx, spec, cfg, inp, P = case
