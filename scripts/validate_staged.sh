@@ -15,6 +15,8 @@ STCAT_ATTN_FWD_V2=1 timeout 60 python scripts/attn_timeline.py 64 213 fwd | tee 
 echo "== staged forward V2 + token-staggered softmax groups: parity + timeline"
 STCAT_ATTN_FWD_V2=2 timeout 120 python -m pytest tests/test_gpu_attention_tc.py -x -q 2>&1 | tail -2
 STCAT_ATTN_FWD_V2=2 timeout 60 python scripts/attn_timeline.py 64 213 fwd | tee gpurun_out/attn_fwd_timeline_v2s.txt | tail -9
+echo "== staged backward (integer bf16 pack): parity + timing"
+STCAT_ATTN_BWD_V2=1 timeout 120 python -m pytest tests/test_gpu_attention_tc.py -x -q -s -k "bf16_fwd_bwd or timing or tcgen05" 2>&1 | grep -E "passed|failed|us/launch" | tail -6
 echo "== backward timeline"
 timeout 60 python scripts/attn_timeline.py 64 213 bwd | tee gpurun_out/attn_bwd_timeline.txt | tail -20
 echo "== GEMM timeline (FFN linear1 forward; FFN linear2 forward)"

@@ -44,8 +44,9 @@ struct AttnFwdParams {
     long long* trace;         // diagnostics (stcat_debug_attn_trace): SM clock at the phase boundaries of CTA 0's first 8 items
 };
 
-// two probabilities -> packed bf16x2 with integer ops (round half up on the magnitude; inputs are finite and >= 0), which
-// keeps the conversion off the XU pipe that the exponentials saturate (profiles/r1_k_attn_fwd_timeline.md)
+// two finite floats -> packed bf16x2 with integer ops (round half away from zero: +0x8000 on the bit pattern grows the
+// magnitude of either sign; differs from round-to-nearest-even only on exact ties), which keeps the conversion off the XU
+// pipe that the exponentials saturate (profiles/r1_k_attn_fwd_timeline.md)
 __device__ __forceinline__ uint32_t pack_prob_bf16x2(float lo, float hi) {
     return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
 }
@@ -411,7 +412,9 @@ __device__ __forceinline__ void store_row_bf16x32(__nv_bfloat16* dst, const uint
     for (int j = 0; j < 4; ++j) d4[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
 }
 
-template <bool DROP, bool TRACE>
+// IPACK (staged, STCAT_ATTN_BWD_V2=1): P and dS are packed to bf16 with integer ops (round half away from zero) instead of
+// F2FP, which shares the XU pipe with the exponentials (see pack_prob_bf16x2 and profiles/r1_k_attn_fwd_timeline.md).
+template <bool DROP, bool TRACE, bool IPACK = false>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -613,9 +616,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                                 const float m1 = DROP ? drop_mult(p.drop, dcol + e + 1) : 1.f;
                                 const float d0 = dead ? 0.f : p0 * (__uint_as_float(rd[e]) * m0 - delta) * dsc;
                                 const float d1 = dead ? 0.f : p1 * (__uint_as_float(rd[e + 1]) * m1 - delta) * dsc;
-                                __nv_bfloat162 bp = __floats2bfloat162_rn(p0 * m0, p1 * m1), bd = __floats2bfloat162_rn(d0, d1);
-                                pp[e >> 1] = *reinterpret_cast<uint32_t*>(&bp);
-                                pd[e >> 1] = *reinterpret_cast<uint32_t*>(&bd);
+                                if (IPACK) {
+                                    pp[e >> 1] = pack_prob_bf16x2(p0 * m0, p1 * m1);
+                                    pd[e >> 1] = pack_prob_bf16x2(d0, d1);
+                                } else {
+                                    __nv_bfloat162 bp = __floats2bfloat162_rn(p0 * m0, p1 * m1), bd = __floats2bfloat162_rn(d0, d1);
+                                    pp[e >> 1] = *reinterpret_cast<uint32_t*>(&bp);
+                                    pd[e >> 1] = *reinterpret_cast<uint32_t*>(&bd);
+                                }
                             }
                         } else {
                             const uint32_t wmask = dead ? 0xffffffffu : mwv;
@@ -634,9 +642,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                                     d1 = p1 * (__uint_as_float(rd[e + 1]) * m1 - delta) * p.scale;
                                     p1 *= m1;
                                 }
-                                __nv_bfloat162 bp = __floats2bfloat162_rn(p0, p1), bd = __floats2bfloat162_rn(d0, d1);
-                                pp[e >> 1] = *reinterpret_cast<uint32_t*>(&bp);
-                                pd[e >> 1] = *reinterpret_cast<uint32_t*>(&bd);
+                                if (IPACK) {
+                                    pp[e >> 1] = pack_prob_bf16x2(p0, p1);
+                                    pd[e >> 1] = pack_prob_bf16x2(d0, d1);
+                                } else {
+                                    __nv_bfloat162 bp = __floats2bfloat162_rn(p0, p1), bd = __floats2bfloat162_rn(d0, d1);
+                                    pp[e >> 1] = *reinterpret_cast<uint32_t*>(&bp);
+                                    pd[e >> 1] = *reinterpret_cast<uint32_t*>(&bd);
+                                }
                             }
                         }
                         const uint32_t off = wg * 16384 + row * 128;
@@ -804,13 +817,18 @@ int attn_tc_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
         cudaError_t e = cudaFuncSetAttribute(attn_tc_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_bwd_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_bwd_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
         if (e != cudaSuccess) return set_err((int)e, "attn_tc_bwd: smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
     const int total = B * H;
     const int sms = num_sms();
     const int grid = total < sms ? total : sms;
-    if (drop.thresh) launch_pdl(attn_tc_bwd_kernel<true, false>, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, p);
+    const bool ipack = getenv("STCAT_ATTN_BWD_V2") != nullptr && !g_attn_trace;  // staged, opt-in
+    if (ipack && drop.thresh) launch_pdl(attn_tc_bwd_kernel<true, false, true>, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, p);
+    else if (ipack) launch_pdl(attn_tc_bwd_kernel<false, false, true>, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, p);
+    else if (drop.thresh) launch_pdl(attn_tc_bwd_kernel<true, false>, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, p);
     else if (g_attn_trace) launch_pdl(attn_tc_bwd_kernel<false, true>, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, p);
     else launch_pdl(attn_tc_bwd_kernel<false, false>, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, p);
     return check_launch("attn_tc_bwd_kernel");
