@@ -161,6 +161,23 @@ STCAT_API int stcat_attention_dropout_bwd(const void* q1, const void* q2, int64_
                                 void* dk1, void* dk2, int64_t lddk, void* dv, int64_t lddv, int B, int H, int Lq, int Lk, int dh,
                                 float scale, float drop_p, uint64_t seed, uint64_t offset, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer-side step over a contiguous fp32 range of flat parameter / gradient / state buffers.
+ *   stcat_sumsq      : *accum += sum_i x[i]^2   (device scalar; the caller zeroes it once per step and may add the
+ *                      squared norms of parameters outside the flat buffer) -- the global gradient norm of
+ *                      torch.nn.utils.clip_grad_norm_ (train_net.py:139-140) without a host sync
+ *   stcat_adamw_step : per element, in this order (torch.optim.AdamW, engine/optimizer.py:44-46):
+ *                        g *= min(1, max_norm / (sqrt(*total_sumsq) + 1e-6))        if max_norm > 0
+ *                        p *= 1 - lr * weight_decay;  m += (g - m)(1 - beta1);  v = beta2 v + (1 - beta2) g^2
+ *                        p -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps)
+ *                      then, optionally, ema = ema * ema_decay + (1 - ema_decay) * p (engine/optimizer.py:5-22) and
+ *                      shadow_bf16 = bf16(p) (the GEMM-operand copy of the weights).  ema / shadow_bf16 / total_sumsq may
+ *                      be NULL.  One pass over HBM (38 B per parameter). */
+STCAT_API int stcat_sumsq(const float* x, int64_t n, float* accum, void* stream);
+STCAT_API int stcat_adamw_step(float* p, const float* g, float* m, float* v, float* ema, void* shadow_bf16, int64_t n, float lr,
+                               float beta1, float beta2, float eps, float weight_decay, int64_t step, const float* total_sumsq,
+                               float max_norm, float ema_decay, void* stream);
+
 /* Diagnostics (not on the product path): SM-clock timestamps at the phase boundaries of the tcgen05 spatial-attention
  * forward: CTA 0, its first 8 work items, 16 event slots per item (buf: 128 int64 in device memory; NULL = off). */
 STCAT_API int stcat_debug_attn_trace(void* buf);

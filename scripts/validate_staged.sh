@@ -6,6 +6,8 @@
 # 2. the backward timeline and the GEMM timeline (never measured yet).
 mkdir -p gpurun_out
 export PYTHONPATH=.
+echo "== staged kernels that have never run on the GPU (fused optimizer step)"
+timeout 120 python -m pytest tests -x -q -m gpu_staged 2>&1 | tail -3
 echo "== default forward: parity + timeline"
 timeout 120 python -m pytest tests/test_gpu_attention_tc.py -x -q 2>&1 | tail -2
 timeout 60 python scripts/attn_timeline.py 64 213 fwd | tee gpurun_out/attn_fwd_timeline_v1.txt | tail -9

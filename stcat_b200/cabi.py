@@ -59,6 +59,8 @@ SIGNATURES["stcat_attention_dropout_fwd"] = (c_int, [_P, _P, _L, _P, _P, _L, _P,
                                                      _F, _U64, _U64, _P])
 SIGNATURES["stcat_attention_dropout_bwd"] = (c_int, [_P, _P, _L, _P, _P, _L, _P, _L, _P, _L, _P, _L, _I, _P, _P, _P, _P, _P, _P, _L,
                                                      _P, _P, _L, _P, _L, _I, _I, _I, _I, _I, _F, _F, _U64, _U64, _P])
+SIGNATURES["stcat_sumsq"] = (c_int, [_P, _L, _P, _P])
+SIGNATURES["stcat_adamw_step"] = (c_int, [_P, _P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _L, _P, _F, _F, _P])
 SIGNATURES["stcat_debug_attn_trace"] = (c_int, [_P])
 SIGNATURES["stcat_debug_gemm_trace"] = (c_int, [_P])
 SIGNATURES["stcat_anchor_sine_fwd"] = (c_int, [_P, _P, _P, _L, _P])
@@ -358,6 +360,25 @@ class CudaBackend:
             self._flat(plan.actioness, "actioness", f), carr, float(plan.num_boxes), nl, n, b, t, int(plan.slice.numel()),
             self._flat(losses, "losses", f), self._flat(d_coord, "d_coord", f), self._flat(d_sted, "d_sted", f),
             self._flat(d_act, "d_act", f), self._flat(d_attn, "d_attn", f), self._stream()), "stg_loss")
+        self.launches += 1
+
+    # -- optimizer-side step ---------------------------------------------
+    def sumsq(self, x, accum):
+        """accum (1-element fp32 device tensor) += sum x^2"""
+        f = torch.float32
+        self._rc(self.lib.stcat_sumsq(self._flat(x, "x", f), x.numel(), self._flat(accum, "accum", f), self._stream()), "sumsq")
+        self.launches += 1
+
+    def adamw_step(self, p, g, m, v, ema, shadow, lr, beta1, beta2, eps, weight_decay, step, total_sumsq, max_norm, ema_decay):
+        """AdamW (+ global-norm clipping, EMA, bf16 shadow refresh) on one contiguous fp32 range; include/stcat_b200.h"""
+        f = torch.float32
+        n = p.numel()
+        assert g.numel() == n and m.numel() == n and v.numel() == n and (ema is None or ema.numel() == n)
+        assert shadow is None or shadow.numel() == n
+        self._rc(self.lib.stcat_adamw_step(
+            self._flat(p, "p", f), self._flat(g, "g", f), self._flat(m, "m", f), self._flat(v, "v", f), self._flat(ema, "ema", f),
+            self._flat(shadow, "shadow", torch.bfloat16), n, float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
+            int(step), self._flat(total_sumsq, "total_sumsq", f), float(max_norm), float(ema_decay), self._stream()), "adamw_step")
         self.launches += 1
 
     # -- post-process / map2d -------------------------------------------

@@ -49,6 +49,7 @@ class FlatGrads:
         n = o
         self.buf = torch.zeros(n, dtype=torch.float32, device=params[0].device)
         self.params = params
+        self.starts = list(starts)  # offset of every parameter of ``params`` in the flat buffer (optim.FusedAdamW)
         for p, st in zip(params, starts):
             p.grad = self.buf[st:st + p.numel()].view_as(p)
         starts.append(n)

@@ -108,11 +108,26 @@ def clear_weight_cache():
     _wcache.clear()
 
 
+# optional: maps a weight (or a contiguous slice of one) to its bf16 shadow kept up to date by the fused optimizer step
+# (optim.FusedAdamW writes the shadows in the same pass that updates the fp32 masters: no per-step cast kernels)
+_shadow_provider = None
+
+
+def set_shadow_provider(fn):
+    global _shadow_provider
+    _shadow_provider = fn
+    _wcache.clear()
+
+
 def _operand(t: torch.Tensor, is_weight: bool = False) -> torch.Tensor:
     """GEMM operand in the active precision (2-D, row-major)."""
     if _precision == "fp32" or t.dtype == torch.bfloat16:
         return t
     be = get_backend()
+    if is_weight and _shadow_provider is not None:
+        sh = _shadow_provider(t)
+        if sh is not None:
+            return sh
     if is_weight:
         key = (t.data_ptr(), tuple(t.shape), t.stride(0))
         hit = _wcache.get(key)

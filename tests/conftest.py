@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+    config.addinivalue_line("markers", "gpu_staged: GPU tests of kernels that have not run on a B200 yet (tests/test_gpu_staged.py); "
+                                       "deliberately outside `-m gpu`")
 
 
 def pytest_collection_modifyitems(config, items):

@@ -295,6 +295,32 @@ class EmuBackend:
         out.copy_((x.t() if transpose else x).to(torch.bfloat16))
         self.launches += 1
 
+    # -- optimizer-side step ---------------------------------------------
+    def sumsq(self, x, accum):
+        _flat(x, "x", F32), _flat(accum, "accum", F32)
+        accum.add_((x.double() ** 2).sum().float())
+        self.launches += 1
+
+    def adamw_step(self, p, g, m, v, ema, shadow, lr, beta1, beta2, eps, weight_decay, step, total_sumsq, max_norm, ema_decay):
+        """the per-element order of stcat_adamw_step (include/stcat_b200.h), in fp32"""
+        for t, nm in ((p, "p"), (g, "g"), (m, "m"), (v, "v"), (ema, "ema"), (total_sumsq, "total_sumsq")):
+            _flat(t, nm, F32)
+        _flat(shadow, "shadow", BF16)
+        g = g.clone()
+        if max_norm > 0:
+            g.mul_(torch.clamp(max_norm / (total_sumsq.sqrt() + 1e-6), max=1.0))
+        bc1 = 1.0 - beta1 ** step
+        bc2s = (1.0 - beta2 ** step) ** 0.5
+        p.mul_(1 - lr * weight_decay)
+        m.add_((g - m) * (1 - beta1))
+        v.mul_(beta2).add_((1 - beta2) * g * g)
+        p.sub_((lr / bc1) * (m / (v.sqrt() / bc2s + eps)))
+        if ema is not None:
+            ema.mul_(ema_decay).add_((1 - ema_decay) * p)
+        if shadow is not None:
+            shadow.copy_(p.to(torch.bfloat16))
+        self.launches += 1
+
     def sted_score(self, sted, durations, score, best):
         b, t, _ = sted.shape
         ls = torch.log_softmax(sted[:, :, 0], 1)

@@ -282,3 +282,67 @@ def test_hot_path_train_mode_dropout():
         model.eval()
         e1, e2 = float(loss_of(vis, seed=1)), float(loss_of(vis, seed=2))
         assert e1 == e2 and e1 != float(L0)  # eval mode: no dropout anywhere
+
+
+def test_fused_adamw_matches_torch_adamw_clip_and_ema():
+    """optim.FusedAdamW (one stcat_sumsq + one stcat_adamw_step per (lr, wd) run, emulated here) against the reference's
+    sequence: clip_grad_norm_ -> torch.optim.AdamW.step -> update_ema, over several steps, two LR groups, a parameter that
+    never receives a gradient (skipped by torch), a parameter optimised elsewhere that takes part in the norm, and the bf16
+    shadows served to ops."""
+    import copy
+
+    from stcat_b200.dp import FlatGrads
+    from stcat_b200.optim import FusedAdamW
+
+    torch.manual_seed(0)
+    net = torch.nn.ModuleDict({"a": torch.nn.Linear(40, 24), "b": torch.nn.Linear(24, 7), "never": torch.nn.Linear(5, 3)})
+    outside = torch.nn.Parameter(torch.randn(11))
+    ref = copy.deepcopy(net)
+    ref_out = torch.nn.Parameter(outside.detach().clone())
+    ref_ema = copy.deepcopy(ref)
+    ema_model = copy.deepcopy(net)
+    groups = lambda m: [{"params": list(m["a"].parameters()) + list(m["never"].parameters())},
+                        {"params": list(m["b"].parameters()), "lr": 3e-3, "weight_decay": 0.0}]
+    flat = FlatGrads(net)
+    opt = FusedAdamW(flat, groups(net), lr=1e-3, weight_decay=1e-2, max_grad_norm=0.1, ema_decay=0.99,
+                     frozen=list(net["never"].parameters()), extra_norm_params=[outside])
+    opt.attach_ema(net, ema_model)
+    ops.set_precision("bf16")
+    try:
+        opt.enable_shadows()
+        topt = torch.optim.AdamW(groups(ref), lr=1e-3, weight_decay=1e-2)
+        for step in range(4):
+            x = torch.randn(16, 40, generator=torch.Generator().manual_seed(step))
+            for m, o in ((net, outside), (ref, ref_out)):
+                if m is net:
+                    opt.zero_grad()
+                    o.grad = None
+                else:
+                    topt.zero_grad(set_to_none=True)
+                    o.grad = None
+                loss = (m["b"](torch.relu(m["a"](x))) ** 2).sum() * 50 + (o ** 2).sum()
+                loss.backward()
+            opt.step()
+            torch.nn.utils.clip_grad_norm_(list(ref.parameters()) + [ref_out], 0.1)
+            topt.step()
+            with torch.no_grad():
+                for k, e in ref_ema.state_dict().items():
+                    e.copy_(e * 0.99 + 0.01 * ref.state_dict()[k])
+            if step == 1:  # the LR schedule writes param_groups[i]["lr"] (train_net.py:142)
+                for o_ in (opt, topt):
+                    o_.param_groups[0]["lr"] = 5e-4
+        for (k, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+            assert rel_err(p, q) < 2e-6, k
+        for (k, p), (_, q) in zip(ema_model.named_parameters(), ref_ema.named_parameters()):
+            assert rel_err(p, q) < 2e-6, k
+        assert torch.equal(net["never"].weight, ref["never"].weight)  # untouched, like a grad-less parameter under torch
+        w = net["a"].weight
+        assert torch.equal(ops._operand(w, is_weight=True), w.detach().to(torch.bfloat16))  # shadow served, up to date
+        assert torch.equal(ops._operand(w[3:9], is_weight=True), w[3:9].detach().to(torch.bfloat16))
+        sd = opt.state_dict()
+        assert rel_err(sd["state"][0]["exp_avg"], topt.state_dict()["state"][0]["exp_avg"]) < 2e-6
+        opt.load_state_dict(sd)
+        assert opt.state[net["a"].weight]["exp_avg"].data_ptr() == opt.m.data_ptr()
+    finally:
+        ops.set_shadow_provider(None)
+        ops.set_precision("fp32")
