@@ -144,3 +144,75 @@ def test_flat_gradient_allreduce_world2(tmp_path):
         err = float((g - ref).abs().max())
         assert err <= 1e-5 * float(ref.abs().max()) + 1e-6, (k, err)  # abs floor: gradients that are zero in exact arithmetic (key-bias of a softmax) are fp32 noise
     assert unused >= 8  # fusion.{weight,bias} + 6 x ca_qtime_proj.{weight,bias} at least
+
+
+def _ddp_worker(rank, world, port, outdir):
+    """the reference's own wrapping (train_net.py:31-36): torch DistributedDataParallel(find_unused_parameters=True) around
+    modules whose arithmetic is stcat_b200's autograd Functions; gradients must come out averaged over the ranks"""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from helpers import cfg_for
+        from emu_backend import EmuBackend
+        from stcat_b200 import ops, synthetic
+        from stcat_b200.loss import STGLossPlan
+        from stcat_b200.nested import NestedTensor
+        from stcat_b200.param_spec import synthetic_params
+        from stcat_b200.pipeline import STCATHotPath
+
+        ops.set_backend(EmuBackend())
+        ops.set_precision("fp32")
+        cfg = cfg_for({"max_video_len": 16})
+        model = STCATHotPath(cfg).load_flat_params(synthetic_params(cfg, seed=0)).eval()
+        ddp = torch.nn.parallel.DistributedDataParallel(model, find_unused_parameters=True)
+        T = 5
+        inp = synthetic.make_inputs([T], 3, 3, 4, seed=42 + rank)
+        tg = synthetic.make_targets([T], seed=42 + rank)
+        plan = STGLossPlan(cfg, tg["boxes"], tg["actioness"], [T], "cpu")
+        out = ddp(NestedTensor(inp["vis_features"], inp["vis_mask"], [T]), inp["vis_pos"], (inp["text_mask"], inp["text_memory"], None))
+        total, _ = plan(out)
+        total.backward()
+        named = {k: (None if p.grad is None else p.grad.clone()) for k, p in model.named_parameters()}
+        torch.save({"loss": float(total.detach()), "grads": named}, os.path.join(outdir, f"ddp_rank{rank}.pt"))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_torch_ddp_wrapping_world2(tmp_path):
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_ddp_worker, args=(r, world, port, str(tmp_path))) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+        if p.is_alive():
+            p.kill()
+        assert p.exitcode == 0
+    res = [torch.load(os.path.join(str(tmp_path), f"ddp_rank{r}.pt")) for r in range(world)]
+    sys.path.insert(0, HERE)
+    singles = [_clip_grads(42 + r, fused_flat=False) for r in range(world)]
+    from stcat_b200 import ops
+
+    ops.set_backend(None)
+    checked = 0
+    for k, g0 in res[0]["grads"].items():
+        g1 = res[1]["grads"][k]
+        parts = [dict(m.named_parameters())[k].grad for m, _, _ in singles]
+        if all(p is None for p in parts):  # never used (fusion.*, ca_qtime_proj.*): DDP leaves None or zeros
+            assert g0 is None or float(g0.abs().max()) == 0.0, k
+            continue
+        assert torch.equal(g0, g1), k  # both ranks hold the same averaged gradient
+        mean = sum(p for p in parts if p is not None) / world
+        # thread count / summation order differ between the workers and this process: fp32 noise only
+        err = float((g0 - mean).abs().max())
+        assert err <= 1e-4 * float(mean.abs().max()) + 1e-6, (k, err)
+        checked += 1
+    assert checked > 300
