@@ -24,6 +24,11 @@ timeout 60 python scripts/attn_timeline.py 64 213 bwd | tee gpurun_out/attn_bwd_
 echo "== GEMM timeline (FFN linear1 forward; FFN linear2 forward)"
 timeout 60 python scripts/gemm_timeline.py 13632 2048 256 | tee gpurun_out/gemm_timeline_ffn1.txt | tail -20
 timeout 60 python scripts/gemm_timeline.py 13632 256 2048 | tee gpurun_out/gemm_timeline_ffn2.txt | tail -8
+echo "== staged GEMM epilogue with two staging tiles: parity + timeline + shape table"
+STCAT_GEMM_EPI2=1 timeout 200 python -m pytest tests/test_gpu_gemm_tc.py -x -q 2>&1 | tail -2
+STCAT_GEMM_EPI2=1 timeout 60 python scripts/gemm_timeline.py 13632 2048 256 | tee gpurun_out/gemm_timeline_ffn1_epi2.txt | tail -10
+timeout 120 python scripts/bench_gemm.py 2>/dev/null | head -12
+STCAT_GEMM_EPI2=1 timeout 120 python scripts/bench_gemm.py 2>/dev/null | head -12
 echo "== graph-timed attention core, default vs V2"
 for v in "" 1 2; do
   if [ -n "$v" ]; then export STCAT_ATTN_FWD_V2=$v; fi

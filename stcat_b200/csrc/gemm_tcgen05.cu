@@ -40,15 +40,19 @@ constexpr int THREADS = 384;
 // Two tile shapes.  BN = 256 is the throughput shape (128 x 256 accumulator, two epilogue groups).  BN = 64 is the
 // latency shape for GEMMs with so few 128 x 256 tiles that most SMs would idle (the decoder's [t, 256] query-side
 // layers): 4x as many CTAs, each with a short K loop, and -- unlike split-K -- a deterministic summation order.
-template <int BN> struct Cfg {
-    static constexpr int STAGES = BN >= 256 ? 4 : 8;   // ~192 KB of operands in flight either way (latency x bandwidth)
+// EPI2 (staged, STCAT_GEMM_EPI2=1, BN = 256 only): two staging tiles per epilogue group, so the conversion of chunk c+1 runs
+// while the TMA store of chunk c still reads its tile (with one tile the group waits for every store to drain); paid for
+// with one operand stage (3 instead of 4).
+template <int BN, bool EPI2 = false> struct Cfg {
+    static constexpr int STAGES = BN >= 256 ? (EPI2 ? 3 : 4) : 8;   // ~192 KB of operands in flight (latency x bandwidth)
+    static constexpr int EPI_BUFS = EPI2 ? 2 : 1;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int GROUPS = BN >= 256 ? 2 : 1;   // epilogue groups (4 warps each)
     static constexpr int GC = BN / GROUPS;             // accumulator columns per group
     static constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512 / 128 (power of two >= 32)
     static constexpr int BIAS_BYTES = BN * 4;          // the tile's bias slice, staged once per tile
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GROUPS * EPI_BYTES + BIAS_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GROUPS * EPI_BUFS * EPI_BYTES + BIAS_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 };
 
@@ -78,15 +82,15 @@ template <int NJ> struct GroupParams {
     long long* trace;  // diagnostics (TRACE instantiation only): SM clock at the phase boundaries of CTA 0's first 8 tiles
 };
 
-template <bool A_MN, bool B_MN, bool OUT_BF16, int BN, int NJ, bool TRACE = false>
+template <bool A_MN, bool B_MN, bool OUT_BF16, int BN, int NJ, bool TRACE = false, bool EPI2 = false>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B-swizzle atoms need 1024 B alignment
-    using C = Cfg<BN>;
+    using C = Cfg<BN, EPI2>;
     constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, GROUPS = C::GROUPS, GC = C::GC, TMEM_COLS = C::TMEM_COLS;
     const uint32_t epi_base = base + STAGES * STAGE_BYTES;
-    const uint32_t bias_base = epi_base + GROUPS * EPI_BYTES;
+    const uint32_t bias_base = epi_base + GROUPS * C::EPI_BUFS * EPI_BYTES;
     const uint32_t bar_base = bias_base + C::BIAS_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -227,7 +231,8 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
         const int row = q * 32 + lane;             // row of the 128-row tile owned by this thread
         const int gt = threadIdx.x - 128 - g * 128;  // thread index inside the group
         const uint32_t bar_id = 1 + g;
-        const uint32_t sbuf_base = epi_base + g * EPI_BYTES;  // one 128 x 128 B staging tile per group
+        const uint32_t sbuf_group = epi_base + g * C::EPI_BUFS * EPI_BYTES;  // the group's 128 x 128 B staging tile(s)
+        uint32_t nchunk_done = 0;  // running chunk count of this group (EPI2: selects the staging tile)
         const uint32_t sbias = bias_base + g * GC * 4;  // this group's GC bias values (fp32)
         constexpr int CHUNK_COLS = OUT_BF16 ? 64 : 32;        // 128 B of output per row per chunk
         constexpr int NCHUNK = GC / CHUNK_COLS;               // chunks per group
@@ -284,8 +289,10 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
 #pragma unroll
                     for (int j = 0; j < CHUNK_COLS / 8; ++j) mk[j] = gr < job_M ? __ldg(mp + j) : make_uint4(0, 0, 0, 0);
                 }
-                // the staging tile must have been read by the previous TMA store of this group
-                if (gt == 0) tma_wait_read<0>();
+                // the staging tile must have been read by the TMA store that used it last (EPI2: two tiles alternate, so
+                // the most recent store may still be in flight)
+                const uint32_t sbuf_base = sbuf_group + (EPI2 ? (nchunk_done & 1u) * EPI_BYTES : 0u);
+                if (gt == 0) { if (EPI2) tma_wait_read<1>(); else tma_wait_read<0>(); }
                 if (c == NCHUNK - 1 || (c + 1) * CHUNK_COLS >= n_valid) {
                     // last TMEM read of this accumulator stage: hand it back to the MMA warp as early as possible
                     tmem_ld_wait();
@@ -364,6 +371,7 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
                     }
                     if (c0 + cc < job_N) atomicAdd(job_colsum + c0 + cc, sum);
                 }
+                if (EPI2) ++nchunk_done;
             }
             if (!released) release_acc();  // this group's half lies entirely outside N
             if (tr) T(ti, 7);  // last store of the tile issued
@@ -460,14 +468,34 @@ void gemm_tc_set_trace(long long* buf) { g_gemm_trace = buf; }
 template <bool AMN, bool BMN, bool OBF, int BN, int NJ>
 static int launch_tc(const tc::GroupParams<NJ>& gp, int grid, cudaStream_t st) {
     using namespace tc;
-    if constexpr (!AMN && !BMN && BN == 256 && NJ == 1) {  // diagnostics: traced instantiation of the plain forward GEMM
-        if (g_gemm_trace != nullptr) {
-            GroupParams<NJ> gt = gp;
-            gt.trace = g_gemm_trace;
-            cudaFuncSetAttribute(gemm_tc_kernel<AMN, BMN, OBF, BN, NJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
-            cudaError_t le = launch_pdl(gemm_tc_kernel<AMN, BMN, OBF, BN, NJ, true>, dim3(grid), dim3(THREADS), Cfg<BN>::SMEM_BYTES, st, gt);
-            if (le != cudaSuccess) return set_err((int)le, "gemm_tc_kernel<trace> launch: %s", cudaGetErrorString(le));
-            return check_launch("gemm_tc_kernel<trace>");
+    if constexpr (BN == 256 && NJ == 1) {
+        static const bool epi2 = getenv("STCAT_GEMM_EPI2") != nullptr;  // staged variant (two staging tiles per group), opt-in
+        if constexpr (!AMN && !BMN) {  // diagnostics: traced instantiations of the plain forward GEMM
+            if (g_gemm_trace != nullptr) {
+                GroupParams<NJ> gt = gp;
+                gt.trace = g_gemm_trace;
+                cudaError_t le;
+                if (epi2) {
+                    cudaFuncSetAttribute(gemm_tc_kernel<AMN, BMN, OBF, BN, NJ, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, true>::SMEM_BYTES);
+                    le = launch_pdl(gemm_tc_kernel<AMN, BMN, OBF, BN, NJ, true, true>, dim3(grid), dim3(THREADS), Cfg<BN, true>::SMEM_BYTES, st, gt);
+                } else {
+                    cudaFuncSetAttribute(gemm_tc_kernel<AMN, BMN, OBF, BN, NJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
+                    le = launch_pdl(gemm_tc_kernel<AMN, BMN, OBF, BN, NJ, true>, dim3(grid), dim3(THREADS), Cfg<BN>::SMEM_BYTES, st, gt);
+                }
+                if (le != cudaSuccess) return set_err((int)le, "gemm_tc_kernel<trace> launch: %s", cudaGetErrorString(le));
+                return check_launch("gemm_tc_kernel<trace>");
+            }
+        }
+        if (epi2) {
+            static bool attr2 = false;
+            if (!attr2) {
+                cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AMN, BMN, OBF, BN, NJ, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, true>::SMEM_BYTES);
+                if (e != cudaSuccess) return set_err((int)e, "gemm_tc<epi2>: smem attribute: %s", cudaGetErrorString(e));
+                attr2 = true;
+            }
+            cudaError_t le = launch_pdl(gemm_tc_kernel<AMN, BMN, OBF, BN, NJ, false, true>, dim3(grid), dim3(THREADS), Cfg<BN, true>::SMEM_BYTES, st, gp);
+            if (le != cudaSuccess) return set_err((int)le, "gemm_tc_kernel<epi2> launch: %s", cudaGetErrorString(le));
+            return check_launch("gemm_tc_kernel<epi2>");
         }
     }
     static bool attr_set = false;
