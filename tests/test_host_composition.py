@@ -273,3 +273,17 @@ def test_map2d_head_gradients_match_oracle(variant):
     assert rel_err(x.grad, xo.grad) < 1e-4
     for k, prm in head.named_parameters():
         assert rel_err(prm.grad, P["head." + k].grad) < 1e-4, k
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_post_process_matches_reference_fixture(name):
+    """stcat_b200.pipeline.PostProcess (mirror of models/post_processor.py:17-55) against the reference's own PostProcess output
+    stored in the fixtures: scaled / clamped xyxy boxes and the (start, end) frame ids of the best T x T cell."""
+    from stcat_b200.pipeline import PostProcess
+
+    fx = load_golden(name)
+    post = fx["post"]
+    outputs = {"pred_boxes": fx["out"]["pred_boxes"], "pred_sted": fx["out"]["pred_sted"]}
+    boxes, steds = PostProcess()(outputs, post["target_sizes"], post["frames_id"], fx["spec"]["durations"])
+    assert torch.allclose(boxes, post["boxes"], rtol=1e-6, atol=1e-5)
+    assert steds == post["steds"]
