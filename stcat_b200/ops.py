@@ -11,8 +11,6 @@ Precision:
 """
 from __future__ import annotations
 
-from typing import Optional
-
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable

@@ -8,7 +8,7 @@ table, and ``oracle/make_golden.py`` checks the table against the reference's ow
 from __future__ import annotations
 
 from collections import OrderedDict
-from typing import Dict, Tuple
+from typing import Dict
 
 
 def _linear(out: OrderedDict, prefix: str, n_out: int, n_in: int):

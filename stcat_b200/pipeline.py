@@ -12,13 +12,13 @@ Inside the reference itself the drop-in is one level lower: ``build_encoder`` / 
 """
 from __future__ import annotations
 
-from typing import Optional, Sequence
+from typing import Sequence
 
 import torch
 from torch import nn
 
 from . import ops
-from .decoder import box_refine, build_decoder, inverse_sigmoid, run_mlp
+from .decoder import box_refine, build_decoder, run_mlp
 from .encoder import build_encoder
 from .params import MLPP
 
