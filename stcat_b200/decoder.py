@@ -504,7 +504,8 @@ class QueryDecoder(nn.Module):
                 def get():
                     stream.wait_event(evs[i])
                     for tns in vals[i]:  # allocated on sM, consumed here (and in backward) on another stream
-                        tns.record_stream(stream)
+                        if tns is not None:  # FROM_SCRATCH False has no separate positional key part
+                            tns.record_stream(stream)
                     return vals[i]
                 return get
             return [mk(i) for i in range(len(vals))]
