@@ -184,6 +184,10 @@ STCAT_API int stcat_debug_attn_trace(void* buf);
 /* Same for the tcgen05 GEMM (stcat_linear_fwd with bf16 operands, 128 x 256 tiles): CTA 0, its first 8 tiles, 8 event
  * slots per tile (buf: 64 int64 in device memory; NULL = off). */
 STCAT_API int stcat_debug_gemm_trace(void* buf);
+/* Host-side launch counters of stcat_attention_fwd / _bwd (+ dropout variants) per kernel family since the library was
+ * loaded: out5 = {single-query, tcgen05, mma.sync, shared-memory fp32, generic SIMT}.  Tests use it to assert that no
+ * BASELINE shape is served by the generic kernels. */
+STCAT_API int stcat_debug_attn_counts(long long* out5);
 
 /* ------------------------------------------------------------------------------------------------
  * Element-wise helpers on [rows, cols] fp32 matrices (contiguous).

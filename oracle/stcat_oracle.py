@@ -30,27 +30,59 @@ Tensor = torch.Tensor
 Params = Dict[str, Tensor]
 
 
+class _RoundBF16(torch.autograd.Function):
+    """round-to-nearest-even to bf16, kept in the working dtype; the gradient passes through unrounded (the oracle's
+    gradients are those of the working dtype -- fp64 in the gradient gates -- on bf16-rounded operands)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 @dataclass
 class Prec:
+    """dtype: working dtype.  round_operands="bf16": every matmul operand is rounded to bf16 first.
+    kernel_stores (with round_operands="bf16"): additionally round, to bf16, every intermediate that the B200 path keeps in
+    bf16 between kernels (projection outputs that feed only a GEMM / attention, the FFN hidden activation, the attention
+    output) and the probabilities where the attention kernels round them -- the rounding points are listed function by
+    function below and cite the kernel / host line that makes them ("kernel-matched oracle")."""
     dtype: torch.dtype = torch.float32
-    round_operands: Optional[str] = None  # None | "bf16": round every matmul operand to bf16 first
+    round_operands: Optional[str] = None
+    kernel_stores: bool = False
 
     def r(self, x: Tensor) -> Tensor:
         if self.round_operands == "bf16":
-            return x.to(torch.bfloat16).to(x.dtype)
+            return _RoundBF16.apply(x)
         return x
+
+    def s(self, x: Tensor) -> Tensor:
+        """a value the CUDA path stores as bf16 (identity unless kernel_stores)"""
+        if self.kernel_stores and self.round_operands == "bf16":
+            return _RoundBF16.apply(x)
+        return x
+
+    @property
+    def km(self) -> bool:
+        return bool(self.kernel_stores and self.round_operands == "bf16")
 
 
 FP32 = Prec()
+BF16_KERNEL = Prec(round_operands="bf16", kernel_stores=True)
 
 
 # ----------------------------------------------------------------------------------------------
 # small building blocks
 # ----------------------------------------------------------------------------------------------
-def linear(x: Tensor, w: Tensor, b: Optional[Tensor], prec: Prec = FP32) -> Tensor:
-    """y = x W^T + b  (torch.nn.Linear; used everywhere on the path)."""
+def linear(x: Tensor, w: Tensor, b: Optional[Tensor], prec: Prec = FP32, store: bool = False) -> Tensor:
+    """y = x W^T + b  (torch.nn.Linear; used everywhere on the path).  ``store``: the CUDA path writes this output in bf16
+    from the GEMM epilogue (``out_bf16=True`` at the call site in stcat_b200/{ops,decoder}.py)."""
     y = prec.r(x) @ prec.r(w).t()
-    return y if b is None else y + b
+    y = y if b is None else y + b
+    return prec.s(y) if store else y
 
 
 def layer_norm(x: Tensor, w: Tensor, b: Tensor, eps: float = 1e-5) -> Tensor:
@@ -65,7 +97,7 @@ def mlp(P: Params, prefix: str, x: Tensor, num_layers: int, prec: Prec = FP32) -
     for i in range(num_layers):
         x = linear(x, P[f"{prefix}.layers.{i}.weight"], P[f"{prefix}.layers.{i}.bias"], prec)
         if i < num_layers - 1:
-            x = torch.relu(x)
+            x = prec.s(torch.relu(x))  # hidden activations feed one GEMM: bf16 from the epilogue (decoder.py run_mlp)
     return x
 
 
@@ -131,8 +163,29 @@ def image_sine_pos(mask: Tensor, num_pos_feats: int = 128, temperature: float = 
 # ----------------------------------------------------------------------------------------------
 # attention
 # ----------------------------------------------------------------------------------------------
+def kernel_attention_variant(N: int, nhead: int, Lq: int, Lk: int, two_part: bool, need_weights: bool) -> str:
+    """Which bf16 attention kernel the C ABI runs for a shape (the dispatch order of csrc/attention_simt.cu:
+    attention_fwd_impl), reduced to what matters for rounding:
+      "tc"   tcgen05 kernel (csrc/attention_tc.cu: Lq == Lk in [64, 512], N*nhead >= 16, one score part, no weights output):
+             P = bf16(exp(s - rowmax)) un-normalised, O = (P V) / rowsum(fp32 exp); keys in tiles of 256 with a running max
+      "mma"  mma.sync kernel (csrc/attention_small_mma.cu: Lq, Lk <= 320, one part): P = bf16(softmax) then P V
+      "f32p" single-query / shared-memory / generic kernels: probabilities stay fp32
+    In every variant q is NOT pre-scaled (the kernels scale the fp32 scores) and the output is stored as bf16."""
+    if Lq == 1 and not need_weights and Lk <= 4096:
+        return "f32p"
+    if not two_part and not need_weights and Lq == Lk and 64 <= Lq <= 512 and N * nhead >= 16:
+        return "tc"
+    if not two_part and 2 <= Lq <= 320 and 1 <= Lk <= 320:
+        return "mma"
+    return "f32p"
+
+
+TC_KEY_TILE = 256  # keys per score tile of the tcgen05 kernel (csrc/attention_tc.cu AT_KT)
+
+
 def attention_core(q: Tensor, k: Tensor, v: Tensor, nhead: int, key_padding_mask: Optional[Tensor],
-                   scaling: float, prec: Prec = FP32) -> Tuple[Tensor, Tensor]:
+                   scaling: float, prec: Prec = FP32, q2: Optional[Tensor] = None, k2: Optional[Tensor] = None,
+                   need_weights: bool = True) -> Tuple[Tensor, Tensor]:
     """softmax((q*scaling) k^T + mask) v per head.
 
     q [Lq,N,Eq], k [Lk,N,Eq], v [Lk,N,Ev] (seq-first); key_padding_mask [N,Lk] bool, True -> -inf.
@@ -140,43 +193,92 @@ def attention_core(q: Tensor, k: Tensor, v: Tensor, nhead: int, key_padding_mask
     (nn/functional.py:6630-6665 in torch 2.11: q scaled first, bmm, masked -inf, softmax, bmm) and the
     reference's custom variant attention.py:283-383 (explicit max-subtraction :379-380, which does
     not change the value of the softmax).
+
+    q2 / k2 (kernel-matched mode only): a second score part, s = q.k + q2.k2 per head -- the reference's per-head
+    concat [content ; position] (query_decoder.py:371-384) as the CUDA path evaluates it (csrc/attention_sq.cu).
     """
     Lq, N, Eq = q.shape
     Lk = k.shape[0]
     Ev = v.shape[2]
     dq, dv = Eq // nhead, Ev // nhead
-    qh = prec.r(q * scaling).reshape(Lq, N, nhead, dq).permute(1, 2, 0, 3)  # [N,h,Lq,dq]
-    kh = prec.r(k).reshape(Lk, N, nhead, dq).permute(1, 2, 0, 3)
-    vh = prec.r(v).reshape(Lk, N, nhead, dv).permute(1, 2, 0, 3)
-    s = qh @ kh.transpose(-1, -2)  # [N,h,Lq,Lk]
+    heads = lambda t, L, dd: t.reshape(L, N, nhead, dd).permute(1, 2, 0, 3)
+    if not prec.km:
+        assert q2 is None
+        qh = heads(prec.r(q * scaling), Lq, dq)  # [N,h,Lq,dq]
+        kh = heads(prec.r(k), Lk, dq)
+        vh = heads(prec.r(v), Lk, dv)
+        s = qh @ kh.transpose(-1, -2)  # [N,h,Lq,Lk]
+        if key_padding_mask is not None:
+            s = s.masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
+        p = torch.softmax(s - s.max(dim=-1, keepdim=True)[0], dim=-1)
+        o = prec.r(p) @ vh  # [N,h,Lq,dv]
+        o = o.permute(2, 0, 1, 3).reshape(Lq, N, Ev)
+        return o, p
+    # ---- kernel-matched: bf16 q, k, v as stored by the projection epilogues; fp32 scores scaled after the product ----
+    variant = kernel_attention_variant(N, nhead, Lq, Lk, q2 is not None, need_weights)
+    s = heads(prec.r(q), Lq, dq) @ heads(prec.r(k), Lk, dq).transpose(-1, -2)
+    if q2 is not None:
+        s = s + heads(prec.r(q2), Lq, dq) @ heads(prec.r(k2), Lk, dq).transpose(-1, -2)
+    s = s * scaling
     if key_padding_mask is not None:
         s = s.masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
+    vh = heads(prec.r(v), Lk, dv)
     p = torch.softmax(s - s.max(dim=-1, keepdim=True)[0], dim=-1)
-    o = prec.r(p) @ vh  # [N,h,Lq,dv]
-    o = o.permute(2, 0, 1, 3).reshape(Lq, N, Ev)
+    if variant == "tc":
+        # attention_tc.cu: per 256-key tile, e = exp(s - m_run) with m_run the running row max up to and including the
+        # tile, rounded to bf16 for the P V product; earlier partial outputs are rescaled by exp(m_old - m_new) in fp32;
+        # the normaliser is the fp32 sum of the unrounded e
+        o = None
+        m_run = None
+        den = None
+        for k0 in range(0, Lk, TC_KEY_TILE):
+            st = s[..., k0:k0 + TC_KEY_TILE]
+            m_t = st.max(dim=-1, keepdim=True)[0]
+            m_new = m_t if m_run is None else torch.maximum(m_run, m_t)
+            m_safe = torch.where(torch.isinf(m_new), torch.zeros_like(m_new), m_new)
+            e = torch.exp(st - m_safe)
+            part = prec.r(e) @ vh[:, :, k0:k0 + TC_KEY_TILE]
+            if o is None:
+                o, den = part, e.sum(-1, keepdim=True)
+            else:
+                alpha = torch.exp(torch.where(torch.isinf(m_run), torch.zeros_like(m_run), m_run) - m_safe)
+                alpha = torch.where(torch.isinf(m_run), torch.zeros_like(alpha), alpha)
+                o, den = o * alpha + part, den * alpha + e.sum(-1, keepdim=True)
+            m_run = m_new
+        o = o / den.clamp_min(1e-300)
+    elif variant == "mma":
+        o = prec.r(p) @ vh
+    else:
+        o = p @ vh
+    o = prec.s(o.permute(2, 0, 1, 3).reshape(Lq, N, Ev))
     return o, p
 
 
 def torch_mha(P: Params, prefix: str, query: Tensor, key: Tensor, value: Tensor, nhead: int,
-              key_padding_mask: Optional[Tensor], prec: Prec = FP32) -> Tuple[Tensor, Tensor]:
+              key_padding_mask: Optional[Tensor], prec: Prec = FP32, need_weights: bool = True) -> Tuple[Tensor, Tensor]:
     """torch.nn.MultiheadAttention forward with packed in_proj (used at modal_encoder.py:212,236;
-    query_decoder.py:269,341,565-566,604,633).  Returns (out [Lq,N,E], head-averaged P [N,Lq,Lk])."""
+    query_decoder.py:269,341,565-566,604,633).  Returns (out [Lq,N,E], head-averaged P [N,Lq,Lk]).
+    ``need_weights``: whether the CUDA path asks the kernel for the head-averaged probabilities (it does only where the
+    reference uses them, query_decoder.py:604); selects the kernel in kernel-matched mode, the value is returned either way."""
     E = query.shape[-1]
     W, b = P[f"{prefix}.in_proj_weight"], P[f"{prefix}.in_proj_bias"]
-    q = linear(query, W[:E], b[:E], prec)
-    k = linear(key, W[E:2 * E], b[E:2 * E], prec)
-    v = linear(value, W[2 * E:], b[2 * E:], prec)
-    o, p = attention_core(q, k, v, nhead, key_padding_mask, float(E // nhead) ** -0.5, prec)
+    q = linear(query, W[:E], b[:E], prec, store=True)  # q, k, v feed only the attention kernel: bf16 from the epilogue
+    k = linear(key, W[E:2 * E], b[E:2 * E], prec, store=True)
+    v = linear(value, W[2 * E:], b[2 * E:], prec, store=True)
+    o, p = attention_core(q, k, v, nhead, key_padding_mask, float(E // nhead) ** -0.5, prec, need_weights=need_weights)
     out = linear(o, P[f"{prefix}.out_proj.weight"], P[f"{prefix}.out_proj.bias"], prec)
     return out, p.mean(dim=1)
 
 
 def custom_mha(P: Params, prefix: str, query: Tensor, key: Tensor, value: Tensor, nhead: int,
-               key_padding_mask: Optional[Tensor], prec: Prec = FP32) -> Tuple[Tensor, Tensor]:
+               key_padding_mask: Optional[Tensor], prec: Prec = FP32, q2: Optional[Tensor] = None,
+               k2: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     """Reference attention.MultiheadAttention: no in-projection, embed 2d (dk=64/head), vdim d (dv=32),
-    scaling = dk^-0.5, out_proj Linear(d,d) (attention.py:86-113,275-393)."""
-    Eq = query.shape[-1]
-    o, p = attention_core(query, key, value, nhead, key_padding_mask, float(Eq // nhead) ** -0.5, prec)
+    scaling = dk^-0.5, out_proj Linear(d,d) (attention.py:86-113,275-393).  With q2 / k2 (kernel-matched mode) the
+    per-head concat is given as its two 32-wide parts and ``query`` / ``key`` are the content parts."""
+    Eq = query.shape[-1] * (2 if q2 is not None else 1)
+    o, p = attention_core(query, key, value, nhead, key_padding_mask, float(Eq // nhead) ** -0.5, prec, q2=q2, k2=k2,
+                          need_weights=False)
     out = linear(o, P[f"{prefix}.out_proj.weight"], P[f"{prefix}.out_proj.bias"], prec)
     return out, p.mean(dim=1)
 
@@ -188,9 +290,9 @@ def encoder_layer(P: Params, prefix: str, src: Tensor, mask: Optional[Tensor], p
                   prec: Prec = FP32) -> Tensor:
     """Post-norm TransformerEncoderLayer.forward (modal_encoder.py:228-242), dropout = identity."""
     qk = src + pos
-    a, _ = torch_mha(P, f"{prefix}.self_attn", qk, qk, src, nhead, mask, prec)
+    a, _ = torch_mha(P, f"{prefix}.self_attn", qk, qk, src, nhead, mask, prec, need_weights=False)
     src = layer_norm(src + a, P[f"{prefix}.norm1.weight"], P[f"{prefix}.norm1.bias"])
-    h = torch.relu(linear(src, P[f"{prefix}.linear1.weight"], P[f"{prefix}.linear1.bias"], prec))
+    h = prec.s(torch.relu(linear(src, P[f"{prefix}.linear1.weight"], P[f"{prefix}.linear1.bias"], prec)))  # ops.FFNBlockFn: h bf16
     y = linear(h, P[f"{prefix}.linear2.weight"], P[f"{prefix}.linear2.bias"], prec)
     return layer_norm(src + y, P[f"{prefix}.norm2.weight"], P[f"{prefix}.norm2.bias"])
 
@@ -305,24 +407,29 @@ def box_decoder_layer(P: Params, prefix: str, tgt, memory, query_mask, memory_ma
     :372-376, 381-384, 409-416)."""
     L = lambda name, x: linear(x, P[f"{prefix}.{name}.weight"], P[f"{prefix}.{name}.bias"], prec)
     t, b, c = tgt.shape
-    # self attention over the t queries of each video :329-345
-    q = L("sa_qcontent_proj", tgt) + L("sa_qtime_proj", query_time) + L("sa_qpos_proj", query_pos)
-    k = L("sa_kcontent_proj", tgt) + L("sa_ktime_proj", query_time) + L("sa_kpos_proj", query_pos)
-    v = L("sa_v_proj", tgt)
-    a, weights = torch_mha(P, f"{prefix}.self_attn", q, k, v, nhead, query_mask, prec)
+    # self attention over the t queries of each video :329-345.  Kernel-matched mode: each sum of Linears is one
+    # multi-term GEMM whose epilogue writes bf16 (decoder.py TransformerDecoderLayer.run: linear_group, out_bf16)
+    q = prec.s(L("sa_qcontent_proj", tgt) + L("sa_qtime_proj", query_time) + L("sa_qpos_proj", query_pos))
+    k = prec.s(L("sa_kcontent_proj", tgt) + L("sa_ktime_proj", query_time) + L("sa_kpos_proj", query_pos))
+    v = prec.s(L("sa_v_proj", tgt))
+    a, weights = torch_mha(P, f"{prefix}.self_attn", q, k, v, nhead, query_mask, prec, need_weights=False)
     tgt = layer_norm(tgt + a, P[f"{prefix}.norm1.weight"], P[f"{prefix}.norm1.bias"])
     # time-aligned cross attention :350-429
     n_tok, n, f = memory.shape
     qc = L("ca_qcontent_proj", tgt)
     kc = L("ca_kcontent_proj", memory)
-    vv = L("ca_v_proj", memory)
+    vv = prec.s(L("ca_v_proj", memory))
     kp = L("ca_kpos_proj", pos)
     if is_first:
         qc = qc + L("ca_qpos_proj", query_pos)
         kc = kc + kp
     dh = c // nhead
     qs = L("ca_qpos_sine_proj", query_sine)
-    if from_scratch:
+    if from_scratch and prec.km:
+        # the CUDA path never builds the concat: two-part score over the bf16 projections (decoder.py memory_side / run)
+        o, _ = custom_mha(P, f"{prefix}.cross_attn", _frames_from_padded(prec.s(qc), durations), prec.s(kc), vv, nhead,
+                          memory_mask, prec, q2=_frames_from_padded(prec.s(qs), durations), k2=prec.s(kp))
+    elif from_scratch:
         q2 = torch.cat([qc.view(t, b, nhead, dh), qs.view(t, b, nhead, dh)], 3).reshape(t, b, 2 * c)
         k2 = torch.cat([kc.view(n_tok, n, nhead, dh), kp.view(n_tok, n, nhead, dh)], 3).reshape(n_tok, n, 2 * c)
         q_cross = _frames_from_padded(q2, durations)  # [1,n,2c]
@@ -330,13 +437,13 @@ def box_decoder_layer(P: Params, prefix: str, tgt, memory, query_mask, memory_ma
     else:
         # :375-376 q = (q + sine) + ca_qtime_proj(time); :384 k = k + k_pos (a second time in the first layer)
         q1 = (qc + qs) + L("ca_qtime_proj", query_time)
-        k1 = kc + kp
+        k1 = prec.s(kc + kp)
         q_cross = _frames_from_padded(q1, durations)  # [1,n,c]
-        o, _ = torch_mha(P, f"{prefix}.cross_attn_image", q_cross, k1, vv, nhead, memory_mask, prec)
+        o, _ = torch_mha(P, f"{prefix}.cross_attn_image", q_cross, k1, vv, nhead, memory_mask, prec, need_weights=False)
     o = _padded_from_frames(o, durations, t)
     tgt = layer_norm(tgt + o, P[f"{prefix}.norm3.weight"], P[f"{prefix}.norm3.bias"])
     # FFN :435-437
-    y = L("linear2", torch.relu(L("linear1", tgt)))
+    y = L("linear2", prec.s(torch.relu(L("linear1", tgt))))
     tgt = layer_norm(tgt + y, P[f"{prefix}.norm4.weight"], P[f"{prefix}.norm4.bias"])
     return tgt, weights
 
@@ -367,15 +474,16 @@ def time_decoder_layer(P: Params, prefix: str, tgt, memory, query_mask, memory_m
                        query_time_pos, durations, nhead: int, prec: Prec = FP32):
     """TimeDecoderLayer.forward (query_decoder.py:587-660)."""
     t, b, c = tgt.shape
-    qk = tgt + query_pos + query_time_pos
+    qk = tgt + (query_pos + query_time_pos)  # :597-599 (q = k = tgt + query_pos + time; the positional sum is formed once)
     a, weights = torch_mha(P, f"{prefix}.self_attn", qk, qk, tgt, nhead, query_mask, prec)
     tgt = layer_norm(tgt + a, P[f"{prefix}.norm1.weight"], P[f"{prefix}.norm1.bias"])
     q_cross = _frames_from_padded(tgt, durations) + _frames_from_padded(query_pos, durations)
-    o, _ = torch_mha(P, f"{prefix}.cross_attn_image", q_cross, memory + pos, memory, nhead, memory_mask, prec)
+    o, _ = torch_mha(P, f"{prefix}.cross_attn_image", q_cross, memory + pos, memory, nhead, memory_mask, prec,
+                     need_weights=False)
     o = _padded_from_frames(o, durations, t)
     tgt = layer_norm(tgt + o, P[f"{prefix}.norm3.weight"], P[f"{prefix}.norm3.bias"])
     L = lambda name, x: linear(x, P[f"{prefix}.{name}.weight"], P[f"{prefix}.{name}.bias"], prec)
-    y = L("linear2", torch.relu(L("linear1", tgt)))
+    y = L("linear2", prec.s(torch.relu(L("linear1", tgt))))
     tgt = layer_norm(tgt + y, P[f"{prefix}.norm4.weight"], P[f"{prefix}.norm4.bias"])
     return tgt, weights
 

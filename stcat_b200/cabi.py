@@ -63,6 +63,7 @@ SIGNATURES["stcat_sumsq"] = (c_int, [_P, _L, _P, _P])
 SIGNATURES["stcat_adamw_step"] = (c_int, [_P, _P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _L, _P, _F, _F, _P])
 SIGNATURES["stcat_debug_attn_trace"] = (c_int, [_P])
 SIGNATURES["stcat_debug_gemm_trace"] = (c_int, [_P])
+SIGNATURES["stcat_debug_attn_counts"] = (c_int, [ctypes.POINTER(ctypes.c_longlong)])
 SIGNATURES["stcat_anchor_sine_fwd"] = (c_int, [_P, _P, _P, _L, _P])
 SIGNATURES["stcat_anchor_sine_bwd"] = (c_int, [_P, _P, _P, _L, _P])
 SIGNATURES["stcat_box_refine_fwd"] = (c_int, [_P, _P, _P, _L, _F, _P])
@@ -127,6 +128,12 @@ class CudaBackend:
     @staticmethod
     def _stream():
         return torch.cuda.current_stream().cuda_stream
+
+    def attn_counts(self):
+        """launches of the attention entry points per kernel family (stcat_debug_attn_counts)"""
+        buf = (ctypes.c_longlong * 5)()
+        self._rc(self.lib.stcat_debug_attn_counts(buf), "debug_attn_counts")
+        return dict(zip(("sq", "tc", "mma", "small", "simt"), (int(x) for x in buf)))
 
     @staticmethod
     def _mat(t: torch.Tensor, name: str):

@@ -463,6 +463,15 @@ extern "C" int stcat_debug_gemm_trace(void* buf) {
     return 0;
 }
 
+// Launch counters per kernel family (host side; [0] single-query, [1] tcgen05, [2] mma.sync, [3] shared-memory fp32,
+// [4] generic SIMT): lets a test assert which kernel served a shape (tests/test_gpu_bf16_parity.py).
+static long long g_attn_counts[5] = {0, 0, 0, 0, 0};
+extern "C" int stcat_debug_attn_counts(long long* out5) {
+    STCAT_REQUIRE(out5, STCAT_EINVAL, "debug_attn_counts: null pointer");
+    for (int i = 0; i < 5; ++i) out5[i] = g_attn_counts[i];
+    return 0;
+}
+
 // Kernel selection shared by the plain and the dropout entry points.  With dropout (drop.thresh != 0) the single-query,
 // tcgen05 and generic kernels apply the counter-based mask of common.cuh; the short-sequence kernels have no dropout.
 static int attention_fwd_impl(const char* who, const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2,
@@ -482,18 +491,19 @@ static int attention_fwd_impl(const char* who, const void* q1, const void* q2, i
         const void* ptrs[6] = {q1, q2, k1, k2, v, o};
         const int64_t lds[6] = {ldq, ldq, ldk, ldk, ldv, ldo};
         if (attn_sq_supported(dtype, Lq, Lk, p_avg, nullptr, ptrs, lds, 6))
-            return attn_sq_fwd(dtype, q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, B, H, Lk, scale, st, drop);
+            return ++g_attn_counts[0], attn_sq_fwd(dtype, q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, B, H, Lk, scale, st, drop);
     }
     if (attn_tc_fwd_supported(dtype, q2, p_avg, B, H, Lq, Lk, q1, k1, v, o, ldq, ldk, ldv, ldo))
-        return attn_tc_fwd(q1, ldq, k1, ldk, v, ldv, o, ldo, key_mask, lse, B, H, Lq, scale, st, drop);
+        return ++g_attn_counts[1], attn_tc_fwd(q1, ldq, k1, ldk, v, ldv, o, ldo, key_mask, lse, B, H, Lq, scale, st, drop);
     if (nodrop) {
         const void* ptrs[4] = {q1, k1, v, o};
         const int64_t lds[4] = {ldq, ldk, ldv, ldo};
         if (attn_mma_supported(dtype, q2, B, H, Lq, Lk, ptrs, lds, 4))
-            return attn_mma_fwd(q1, ldq, k1, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st);
+            return ++g_attn_counts[2], attn_mma_fwd(q1, ldq, k1, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st);
     }
     if (nodrop && attn_small_supported(q2, B, H, Lq, Lk))
-        return attn_small_fwd(dtype, q1, ldq, k1, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st);
+        return ++g_attn_counts[3], attn_small_fwd(dtype, q1, ldq, k1, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st);
+    ++g_attn_counts[4];
     if (dtype == STCAT_F32)
         return q2 ? launch_fwd<float, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st, drop)
                   : launch_fwd<float, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st, drop);
@@ -520,23 +530,24 @@ static int attention_bwd_impl(const char* who, const void* q1, const void* q2, i
         const void* ptrs[11] = {q1, q2, k1, k2, v, d_o, dq1, dq2, dk1, dk2, dv};
         const int64_t lds[11] = {ldq, ldq, ldk, ldk, ldv, lddo, lddq, lddq, lddk, lddk, lddv};
         if (attn_sq_supported(dtype, Lq, Lk, nullptr, dp_avg, ptrs, lds, 11))
-            return attn_sq_bwd(dtype, q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, delta, dq1, dq2, lddq, dk1,
+            return ++g_attn_counts[0], attn_sq_bwd(dtype, q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, delta, dq1, dq2, lddq, dk1,
                                dk2, lddk, dv, lddv, B, H, Lk, scale, st, drop);
     }
     if (attn_tc_bwd_supported(dtype, q2, dp_avg, o, B, H, Lq, Lk, q1, k1, v, d_o, dq1, dk1, dv, ldq, ldk, ldv, ldo, lddo,
                               lddq, lddk, lddv))
-        return attn_tc_bwd(q1, ldq, k1, ldk, v, ldv, o, ldo, d_o, lddo, key_mask, lse, dq1, lddq, dk1, lddk, dv, lddv, B, H,
+        return ++g_attn_counts[1], attn_tc_bwd(q1, ldq, k1, ldk, v, ldv, o, ldo, d_o, lddo, key_mask, lse, dq1, lddq, dk1, lddk, dv, lddv, B, H,
                            Lq, scale, st, drop);
     if (nodrop) {
         const void* ptrs[7] = {q1, k1, v, d_o, dq1, dk1, dv};
         const int64_t lds[7] = {ldq, ldk, ldv, lddo, lddq, lddk, lddv};
         if (attn_mma_supported(dtype, q2, B, H, Lq, Lk, ptrs, lds, 7))
-            return attn_mma_bwd(q1, ldq, k1, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, dq1, lddq, dk1, lddk, dv, lddv, B, H,
+            return ++g_attn_counts[2], attn_mma_bwd(q1, ldq, k1, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, dq1, lddq, dk1, lddk, dv, lddv, B, H,
                                 Lq, Lk, scale, st);
     }
     if (nodrop && attn_small_supported(q2, B, H, Lq, Lk))
-        return attn_small_bwd(dtype, q1, ldq, k1, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, dq1, lddq, dk1, lddk, dv, lddv,
+        return ++g_attn_counts[3], attn_small_bwd(dtype, q1, ldq, k1, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, dq1, lddq, dk1, lddk, dv, lddv,
                               B, H, Lq, Lk, scale, st);
+    ++g_attn_counts[4];
     if (dtype == STCAT_F32)
         return q2 ? launch_bwd<float, true>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st, drop)
                   : launch_bwd<float, false>(q1, q2, ldq, k1, k2, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, scale, st, drop);

@@ -94,10 +94,14 @@ class GradSync:
     what is left and joins the side stream.  Works eagerly and under CUDA-graph capture (the collectives are captured
     on the side stream like any other kernel).  Without a process group every call is a no-op."""
 
-    def __init__(self, flat: FlatGrads, device=None):
+    def __init__(self, flat: FlatGrads, device=None, average: bool = True):
+        """``average`` (default): gradients are AVERAGED over the ranks, like the torch DistributedDataParallel wrapper
+        this replaces (train_net.py:31-36); the loss already divides by num_boxes / world_size (criterion.py:177-179),
+        which assumes that averaging.  ``average=False`` leaves the sum (then pass ``grad_scale=1/world`` to FusedAdamW)."""
         import torch.distributed as dist
 
         self.flat = flat
+        self.average = bool(average)
         self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.stream = torch.cuda.Stream(device) if (self.active and flat.buf.is_cuda) else None
         self.done = set()
@@ -125,14 +129,16 @@ class GradSync:
         lo, hi = self.flat.ranges[name]
         chunk = self.flat.buf[lo:hi]
         if self.stream is None:
-            dist.all_reduce(chunk)
+            dist.all_reduce(chunk)  # gloo (CPU tests): no AVG op
+            if self.average:
+                chunk.div_(dist.get_world_size())
             return
         cur = torch.cuda.current_stream()
         self.stream.wait_stream(cur)
         for st in self.extra_streams:  # gradient kernels of this range may have been enqueued on these too
             self.stream.wait_stream(st)
         with torch.cuda.stream(self.stream):
-            dist.all_reduce(chunk)
+            dist.all_reduce(chunk, op=dist.ReduceOp.AVG if self.average else dist.ReduceOp.SUM)
 
     def attach(self, out: dict):
         """Hook for one forward pass (``out`` = STCATHotPath's output dict): the decoder + heads range is complete

@@ -11,6 +11,8 @@ Precision:
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
@@ -98,7 +100,10 @@ def get_precision() -> str:
 
 
 # bf16 shadows of the fp32 master weights, refreshed when the parameter changes (optimizer.step bumps
-# ``_version``); keyed by storage pointer so slices of a packed in_proj_weight get their own entry.
+# ``_version``); keyed by address / shape so slices of a packed in_proj_weight get their own entry.  An address and a
+# version do not identify a weight (a new Parameter can be allocated where a freed one lived): every entry also holds a
+# weak reference to the storage object it was cast from and is dropped when that storage dies or is a different one.
+# Writers that update the masters through raw pointers (optim.FusedAdamW without shadows) call clear_weight_cache().
 _wcache = {}
 
 
@@ -128,14 +133,18 @@ def _operand(t: torch.Tensor, is_weight: bool = False) -> torch.Tensor:
             return sh
     if is_weight:
         key = (t.data_ptr(), tuple(t.shape), t.stride(0))
+        storage = t.untyped_storage()
         hit = _wcache.get(key)
-        if hit is not None and hit[0] == t._version:
+        if hit is not None and hit[0] == t._version and hit[2]() is storage:
             return hit[1]
     src = t if t.is_contiguous() else t.contiguous()
     out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
     be.cast_bf16(src, out)
     if is_weight:
-        _wcache[key] = (t._version, out)
+        if len(_wcache) > 4096:  # entries of dead storages (models that were freed) are not worth a sweep each call
+            for k in [k for k, v in _wcache.items() if v[2]() is None]:
+                del _wcache[k]
+        _wcache[key] = (t._version, out, weakref.ref(storage))
     return out
 
 

@@ -16,6 +16,7 @@ meaning; the moments are exposed per parameter as ``exp_avg`` / ``exp_avg_sq`` v
 """
 from __future__ import annotations
 
+import bisect
 from typing import Iterable, Optional
 
 import torch
@@ -34,16 +35,27 @@ class FusedAdamW(torch.optim.Optimizer):
     ema_decay     : keeps ``ema = ema * decay + (1 - decay) * p`` in the same pass; ``attach_ema(model, model_ema)``
                     makes a deep-copied EMA model's parameters views of it
     frozen        : parameters that never receive a gradient (the reference leaves ``.grad`` None for them, so torch's AdamW
-                    skips them: no weight decay, no moments); they are excluded from the fused ranges
+                    skips them: no weight decay, no moments); they are excluded from the fused ranges.  MANDATORY for the
+                    parameters the forward never uses (``ground_encoder.fusion.*``; ``ca_qtime_proj.*`` and
+                    ``cross_attn_image.*`` of the box decoder when FROM_SCRATCH is True): their flat gradient slice is
+                    all zero, which -- unlike torch's ``grad is None`` -- would still apply weight decay.
+                    ``unused_parameters(model, cfg)`` lists them.
+    grad_scale    : the gradients are multiplied by this before the norm / update (1/world_size after a SUM all-reduce;
+                    ``dp.GradSync`` averages by default, so 1)
+    extra_norm_params : their gradients enter the global norm AND are scaled in place by the clip coefficient in ``step()``
+                    (the reference's one ``clip_grad_norm_(model.parameters())`` call scales every gradient), so whatever
+                    optimises them afterwards sees clipped gradients; ``clip_coef()`` exposes the coefficient of the last step.
     """
 
     def __init__(self, flat: FlatGrads, param_groups, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 1e-2, max_grad_norm: float = 0.0, ema_decay: Optional[float] = None,
-                 frozen: Iterable[torch.nn.Parameter] = (), extra_norm_params: Iterable[torch.nn.Parameter] = ()):
+                 frozen: Iterable[torch.nn.Parameter] = (), extra_norm_params: Iterable[torch.nn.Parameter] = (),
+                 grad_scale: float = 1.0):
         defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
         super().__init__(param_groups, defaults)
         self.flat = flat
         self.max_grad_norm = float(max_grad_norm)
+        self.grad_scale = float(grad_scale)
         self.ema_decay = ema_decay
         self.extra_norm_params = list(extra_norm_params)
         self._frozen = {id(p) for p in frozen}
@@ -99,15 +111,45 @@ class FusedAdamW(torch.optim.Optimizer):
         of the weights (bf16 mode): no cast kernels after an optimizer step."""
         self.shadow = self.pbuf.to(torch.bfloat16)
         base, end = self.pbuf.data_ptr(), self.pbuf.data_ptr() + 4 * self.pbuf.numel()
+        starts = list(self.flat.starts)
+        params = self.flat.params
+        # The step kernel writes masters and shadows through raw pointers (no autograd version bump), so a parameter whose
+        # ``_version`` moved since the snapshot was written by something else -- load_state_dict (checkpoint resume happens
+        # AFTER the optimizer is built, train_net.py:60-75), load_flat_params, copying EMA weights in for evaluation --
+        # and its shadow is re-cast before it is served.
+        self._pver = [p._version for p in params]
 
         def provider(t):
             ptr = t.data_ptr()
             if t.dtype != torch.float32 or not (base <= ptr < end) or not t.is_contiguous():
                 return None
-            return self.shadow.as_strided(tuple(t.shape), tuple(t.stride()), (ptr - base) // 4)
+            off = (ptr - base) // 4
+            i = bisect.bisect_right(starts, off) - 1
+            if t._version != self._pver[i]:  # views / detach() share the parameter's version counter
+                n = params[i].numel()
+                self.shadow[starts[i]:starts[i] + n].copy_(self.pbuf[starts[i]:starts[i] + n])
+                self._pver[i] = t._version
+            return self.shadow.as_strided(tuple(t.shape), tuple(t.stride()), off)
 
         ops.set_shadow_provider(provider)
         return self
+
+    def refresh_shadows(self):
+        """Re-cast every bf16 shadow from the fp32 masters (after any bulk write that is not ``step()``; the provider also
+        detects such writes per parameter through the autograd version counter)."""
+        if self.shadow is not None:
+            self.shadow.copy_(self.pbuf)
+            self._pver = [p._version for p in self.flat.params]
+        else:
+            ops.clear_weight_cache()
+        return self
+
+    def clip_coef(self) -> torch.Tensor:
+        """Device scalar: the factor the last ``step()`` applied to every gradient (grad_scale x the global-norm clip)."""
+        c = torch.full((1,), self.grad_scale, dtype=torch.float32, device=self.sumsq.device)
+        if self.max_grad_norm > 0:  # sumsq is that of the already scaled gradients
+            c = c * torch.clamp(self.max_grad_norm / (self.sumsq.sqrt() + 1e-6), max=1.0)
+        return c
 
     # -- EMA -------------------------------------------------------------------------------------------------------
     def attach_ema(self, model, model_ema):
@@ -136,12 +178,22 @@ class FusedAdamW(torch.optim.Optimizer):
             self._runs = self._build_runs()
         self._steps += 1
         clip = self.max_grad_norm > 0
+        if self.grad_scale != 1.0:
+            self.flat.buf.mul_(self.grad_scale)
+            for q in self.extra_norm_params:
+                if q.grad is not None:
+                    q.grad.mul_(self.grad_scale)
         if clip:
             self.sumsq.zero_()
             be.sumsq(self.flat.buf, self.sumsq)
             for q in self.extra_norm_params:
                 if q.grad is not None:
                     self.sumsq.add_(q.grad.detach().float().pow(2).sum())
+            if self.extra_norm_params:
+                coef = torch.clamp(self.max_grad_norm / (self.sumsq.sqrt() + 1e-6), max=1.0)
+                for q in self.extra_norm_params:
+                    if q.grad is not None:
+                        q.grad.mul_(coef.to(q.grad.dtype))
         for g, runs in zip(self.param_groups, self._runs):
             b1, b2 = g["betas"]
             for lo, hi in runs:
@@ -151,6 +203,9 @@ class FusedAdamW(torch.optim.Optimizer):
                               self.max_grad_norm, 0.0 if self.ema_decay is None else self.ema_decay)
         for st in self.state.values():
             st["step"] += 1
+        if self.shadow is None:
+            # the masters moved under the version-keyed cast cache of ops (raw-pointer update, no version bump)
+            ops.clear_weight_cache()
         return None
 
     # -- checkpoints -----------------------------------------------------------------------------------------------
@@ -171,3 +226,21 @@ class FusedAdamW(torch.optim.Optimizer):
                 st["exp_avg"], st["exp_avg_sq"] = mv, vv
                 steps = max(steps, int(st["step"]))
         self._steps = steps
+        self.refresh_shadows()
+
+
+def unused_parameters(model, cfg=None):
+    """Parameters of the hot path that its forward never touches (the reason the reference needs
+    ``find_unused_parameters=True``): pass them as ``frozen`` so they get neither weight decay nor moments, like torch's
+    AdamW skipping ``grad is None``."""
+    from_scratch = True if cfg is None else bool(cfg.MODEL.STCAT.FROM_SCRATCH)
+    out = []
+    for name, p in model.named_parameters():
+        if ".fusion." in name or name.startswith("fusion."):
+            out.append(p)
+        elif "decoder.layers." in name and "temp_decoder" not in name:
+            if from_scratch and (".ca_qtime_proj." in name or ".cross_attn_image." in name):
+                out.append(p)
+            elif not from_scratch and ".cross_attn.out_proj." in name:
+                out.append(p)
+    return out

@@ -230,15 +230,50 @@ class EmuBackend:
             _mat(t, nm)
             assert t.shape == (B * L, H * 32) and t.dtype == q1.dtype, nm
 
+    @staticmethod
+    def _variant(q1, q2, want_pavg, B, H, Lq, Lk):
+        """the kernel the C ABI would run for bf16 operands, as far as rounding goes (oracle.kernel_attention_variant)"""
+        if q1.dtype != BF16:
+            return "f32p"
+        from oracle.stcat_oracle import kernel_attention_variant
+
+        return kernel_attention_variant(B, H, Lq, Lk, q2 is not None, want_pavg)
+
     def attention_fwd(self, q1, q2, k1, k2, v, o, key_mask, lse, p_avg, B, H, Lq, Lk, scale, drop=None):
         self._attn_layout(q1, q2, k1, k2, B, H, Lq, Lk, ((v, "v", Lk), (o, "o", Lq)))
         _flat(key_mask, "key_mask", torch.uint8), _flat(lse, "lse", F32), _flat(p_avg, "p_avg", F32)
         s, hd = self._scores(q1, q2, k1, k2, key_mask, B, H, Lq, Lk, scale)
         p = torch.softmax(s, -1)
         m = self._pmask(drop, B, H, Lq, Lk, p.device)
-        if m is not None:
-            p = p * m
-        out = (p @ hd(v, Lk)).permute(0, 2, 1, 3).reshape(B * Lq, H * 32)
+        variant = self._variant(q1, q2, p_avg is not None, B, H, Lq, Lk)
+        rb = lambda t: t.to(BF16).float()
+        if variant == "tc":
+            # un-normalised probabilities relative to the running row max, rounded to bf16 per 256-key tile; fp32 normaliser
+            from oracle.stcat_oracle import TC_KEY_TILE
+
+            vh = hd(v, Lk)
+            acc = den = m_run = None
+            for k0 in range(0, Lk, TC_KEY_TILE):
+                st = s[..., k0:k0 + TC_KEY_TILE]
+                m_new = st.max(-1, keepdim=True)[0] if m_run is None else torch.maximum(m_run, st.max(-1, keepdim=True)[0])
+                m_safe = torch.where(torch.isinf(m_new), torch.zeros_like(m_new), m_new)
+                e = torch.exp(st - m_safe)
+                em = e if m is None else e * m[..., k0:k0 + TC_KEY_TILE]
+                part = rb(em) @ vh[:, :, k0:k0 + TC_KEY_TILE]
+                if acc is None:
+                    acc, den = part, e.sum(-1, keepdim=True)
+                else:
+                    alpha = torch.where(torch.isinf(m_run), torch.zeros_like(m_run), torch.exp(m_run - m_safe))
+                    acc, den = acc * alpha + part, den * alpha + e.sum(-1, keepdim=True)
+                m_run = m_new
+            out = acc / den.clamp_min(1e-30)
+            if m is not None:
+                p = p * m
+        else:
+            if m is not None:
+                p = p * m
+            out = (rb(p) if variant == "mma" else p) @ hd(v, Lk)
+        out = out.permute(0, 2, 1, 3).reshape(B * Lq, H * 32)
         _store(o, out)
         lse.copy_(torch.logsumexp(s, -1))
         if p_avg is not None:
@@ -263,9 +298,15 @@ class EmuBackend:
         if m is not None:  # o and p_avg were formed from p * m
             dp = dp * m
             pm = p * m
-        dl = (p * dp).sum(-1, keepdim=True)
+        variant = self._variant(q1, q2, dp_avg is not None, B, H, Lq, Lk)
+        if variant == "tc" and o is not None:
+            dl = (hd(o, Lq) * g).sum(-1, keepdim=True)  # the tcgen05 backward takes delta = dO . O from the stored bf16 output
+        else:
+            dl = (p * dp).sum(-1, keepdim=True)
         delta.copy_(dl.squeeze(-1))
         ds = p * (dp - dl) * scale
+        if variant in ("tc", "mma"):  # P and dS are rounded to bf16 for the gradient products (attention_tc.cu, attention_small_mma.cu)
+            pm, ds = pm.to(BF16).float(), ds.to(BF16).float()
         un = lambda t, L: t.permute(0, 2, 1, 3).reshape(B * L, H * 32)
         _store(dv, un(pm.transpose(-1, -2) @ g, Lk))
         _store(dq1, un(ds @ hd(k1, Lk), Lq))

@@ -346,3 +346,83 @@ def test_fused_adamw_matches_torch_adamw_clip_and_ema():
     finally:
         ops.set_shadow_provider(None)
         ops.set_precision("fp32")
+
+
+def test_weight_cache_and_shadows_follow_the_masters():
+    """(i) the bf16 cast cache must not serve a freed model's weights to a new Parameter allocated at the same
+    address; (ii) FusedAdamW.step without shadows must invalidate it (raw-pointer update, no version bump); (iii) with
+    shadows, writes that are not step() -- load_state_dict after the optimizer was built, the reference's resume order --
+    must be seen; (iv) extra_norm_params' gradients are scaled by the clip coefficient."""
+    from stcat_b200.dp import FlatGrads
+    from stcat_b200.optim import FusedAdamW
+
+    ops.set_precision("bf16")
+    try:
+        ops.clear_weight_cache()
+        stale = 0
+        for trial in range(20):  # (i)
+            w = torch.nn.Parameter(torch.randn(64, 64))
+            a = ops._operand(w.detach(), True)
+            assert torch.equal(a, w.detach().to(torch.bfloat16))
+            ptr = w.data_ptr()
+            del w, a
+            w2 = torch.nn.Parameter(torch.randn(64, 64))
+            if w2.data_ptr() == ptr:
+                stale += 1
+            assert torch.equal(ops._operand(w2.detach(), True), w2.detach().to(torch.bfloat16))
+            del w2
+        torch.manual_seed(0)
+        net = torch.nn.Linear(16, 8)
+        outside = torch.nn.Parameter(torch.randn(5))
+        flat = FlatGrads(net)
+        opt = FusedAdamW(flat, list(net.parameters()), lr=1e-2, max_grad_norm=0.1, extra_norm_params=[outside])
+        before = ops._operand(net.weight.detach(), True).clone()
+        opt.zero_grad()
+        ((net(torch.randn(4, 16)) ** 2).sum() * 10 + (outside ** 2).sum()).backward()
+        g_out = outside.grad.clone()
+        opt.step()  # (ii)
+        now = ops._operand(net.weight.detach(), True)
+        assert torch.equal(now, net.weight.detach().to(torch.bfloat16)) and not torch.equal(now, before)
+        coef = float(opt.clip_coef())  # (iv)
+        assert coef < 1.0 and torch.allclose(outside.grad, g_out * coef, rtol=1e-6)
+        total = torch.sqrt(flat.buf.pow(2).sum() + g_out.pow(2).sum())
+        assert abs(coef - 0.1 / (float(total) + 1e-6)) < 1e-6
+        opt.enable_shadows()  # (iii)
+        sd = {k: torch.randn_like(v) for k, v in net.state_dict().items()}
+        net.load_state_dict(sd)
+        assert torch.equal(ops._operand(net.weight.detach(), True), sd["weight"].to(torch.bfloat16))
+        assert torch.equal(ops._operand(net.weight.detach()[2:5], True), sd["weight"][2:5].to(torch.bfloat16))
+        with torch.no_grad():
+            net.weight.mul_(2.0)
+        opt.refresh_shadows()
+        assert torch.equal(opt.shadow[:net.weight.numel()].view_as(net.weight), (sd["weight"] * 2).to(torch.bfloat16))
+    finally:
+        ops.set_shadow_provider(None)
+        ops.set_precision("fp32")
+        ops.clear_weight_cache()
+
+
+def test_unused_parameters_are_exactly_the_gradless_ones():
+    """optim.unused_parameters (the ``frozen`` list FusedAdamW needs) == the parameters the reference leaves without a
+    gradient, for both FROM_SCRATCH settings."""
+    from helpers import cfg_for
+    from stcat_b200 import synthetic
+    from stcat_b200.loss import STGLossPlan
+    from stcat_b200.nested import NestedTensor
+    from stcat_b200.optim import unused_parameters
+    from stcat_b200.param_spec import synthetic_params
+    from stcat_b200.pipeline import STCATHotPath
+
+    for fs in (True, False):
+        cfg = cfg_for({"max_video_len": 16, "from_scratch": fs})
+        model = STCATHotPath(cfg).load_flat_params(synthetic_params(cfg, seed=0)).eval()
+        T = 4
+        inp = synthetic.make_inputs([T], 2, 3, 4, seed=1)
+        tg = synthetic.make_targets([T], seed=1)
+        plan = STGLossPlan(cfg, tg["boxes"], tg["actioness"], [T], "cpu")
+        out = model(NestedTensor(inp["vis_features"], inp["vis_mask"], [T]), inp["vis_pos"], (inp["text_mask"], inp["text_memory"], None))
+        total, _ = plan(out)
+        total.backward()
+        gradless = {k for k, p in model.named_parameters() if p.grad is None}
+        listed = {k for k, p in model.named_parameters() if any(p is q for q in unused_parameters(model, cfg))}
+        assert listed == gradless, (fs, sorted(listed ^ gradless))
