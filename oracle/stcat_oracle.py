@@ -166,21 +166,21 @@ def image_sine_pos(mask: Tensor, num_pos_feats: int = 128, temperature: float = 
 def kernel_attention_variant(N: int, nhead: int, Lq: int, Lk: int, two_part: bool, need_weights: bool) -> str:
     """Which bf16 attention kernel the C ABI runs for a shape (the dispatch order of csrc/attention_simt.cu:
     attention_fwd_impl), reduced to what matters for rounding:
-      "tc"   tcgen05 kernel (csrc/attention_tc.cu: Lq == Lk in [64, 512], N*nhead >= 16, one score part, no weights output):
-             P = bf16(exp(s - rowmax)) un-normalised, O = (P V) / rowsum(fp32 exp); keys in tiles of 256 with a running max
-      "mma"  mma.sync kernel (csrc/attention_small_mma.cu: Lq, Lk <= 320, one part): P = bf16(softmax) then P V
+      "tc"   tcgen05 kernel (csrc/attention_tc.cu: Lq == Lk in [64, 512], one score part, no weights output; sequences of
+             <= 128 tokens only when N*nhead >= 16): P = bf16(exp(s - rowmax)) un-normalised, O = (P V) / rowsum(fp32 exp)
+      "mma"  mma.sync kernel (csrc/attention_small_mma.cu: Lq, Lk <= 128, one part): P = bf16(softmax) then P V
       "f32p" single-query / shared-memory / generic kernels: probabilities stay fp32
     In every variant q is NOT pre-scaled (the kernels scale the fp32 scores) and the output is stored as bf16."""
     if Lq == 1 and not need_weights and Lk <= 4096:
         return "f32p"
-    if not two_part and not need_weights and Lq == Lk and 64 <= Lq <= 512 and N * nhead >= 16:
+    if not two_part and not need_weights and Lq == Lk and 64 <= Lq <= 512 and (Lq > 128 or N * nhead >= 16):
         return "tc"
-    if not two_part and 2 <= Lq <= 320 and 1 <= Lk <= 320:
+    if not two_part and 2 <= Lq <= 128 and 1 <= Lk <= 128:
         return "mma"
     return "f32p"
 
 
-TC_KEY_TILE = 256  # keys per score tile of the tcgen05 kernel (csrc/attention_tc.cu AT_KT)
+TC_KEY_TILE = 512  # keys per softmax tile of the tcgen05 kernel: the whole row (csrc/attention_tc.cu AT_KMAX), one row max
 
 
 def attention_core(q: Tensor, k: Tensor, v: Tensor, nhead: int, key_padding_mask: Optional[Tensor],

@@ -1,37 +1,44 @@
 // tcgen05 self-attention core for the spatial encoder (reference modal_encoder.py:161-168 -> torch
 // nn.MultiheadAttention bmm/softmax/bmm, functional.py:6630-6665): B = T frames x H = 8 heads of
-// softmax(Q K^T * scale + key mask) V with head dim 32 and S = 1 + HW + L <= 256 tokens per frame.
+// softmax(Q K^T * scale + key mask) V with head dim 32 and S = 1 + HW + L <= 512 tokens per frame.
 //
 // Forward.  Work item = (frame, head, 128-query tile).  Per item
-//   TMA    : Q tile [128 x 32], K [256 x 32], V [256 x 32] bf16 head slices of the packed qkv buffer via 3-D
-//            tensor maps {cols, S, frames} (64B swizzle).  Rows >= S of a frame are out of bounds -> zero-filled,
+//   TMA    : Q tile [128 x 32], K [S x 32], V [S x 32] bf16 head slices of the packed qkv buffer via 3-D tensor maps
+//            {cols, S, frames} (64B swizzle, 256-row boxes).  Rows >= S of a frame are out of bounds -> zero-filled,
 //            so a tile never sees its neighbour frame and padded keys contribute exactly 0.
-//   MMA    : S = Q K^T        tcgen05.mma 128 x Npad x 16 (x2 for dh = 32) -> 256 fp32 TMEM columns
-//   softmax: one thread per query row (128 threads): tcgen05.ld the row, masked max, exp2, row sum, P as bf16 into
-//            a 128B-swizzled K-major smem tile [128 x 256]
+//   MMA    : S = Q K^T        tcgen05.mma 128 x Npad x 16 (x2 for dh = 32) -> up to 256 fp32 TMEM columns per MMA
+//   softmax: tcgen05.ld of the score row in 32-column chunks, masked max, exp2, row sum, P (un-normalised, relative to
+//            the row max) as bf16 into a 128B-swizzled K-major smem tile; the columns of a row are split over the 2 (4)
+//            softmax warpgroups of the item, which exchange their partial max / sum through shared memory
 //   MMA    : O = P V          tcgen05.mma 128 x 32 x 16, ceil(S/16) steps, V as MN-major operand (no transpose)
-//   epilog : tcgen05.ld O (32 columns), * 1/rowsum, bf16, 64 B per row straight to global; lse for the backward
-// Two buffer sets (smem Q/K/V/P + 256 TMEM columns each) ping-pong between two softmax warpgroups so the tensor
-// pipe and TMA run under the softmax of the other item (exp2 on the MUFU pipe is the bound: head dim 32 gives
-// only 64 MMA FLOP per exponential).
+//   epilog : tcgen05.ld O, * 1/rowsum, bf16, straight to global; lse for the backward
+// S <= 256: two buffer sets (smem Q/K/V/P + 256 TMEM columns each) ping-pong, two softmax warpgroups (256 threads, a
+// (row, column half) each) per set, so the tensor pipe and TMA run under the softmax of the other item.  exp2 on the
+// MUFU pipe is the bound (head dim 32 gives only 64 MMA FLOP per exponential): 16 softmax warps = 4 per SM sub-partition
+// keep that pipe fed (the round-1 kernel had 2 per sub-partition, one per set, and ran at a third of the MUFU rate).
+// 256 < S <= 512 (BIG): one item at a time uses both sets' buffers as one (K, V: 512 rows, P: 128 x 512, S: all 512
+// TMEM columns, two score MMAs) and all four softmax warpgroups (a (row, column quarter) each).
 //
 // Backward: see attn_tc_bwd_kernel below.
 #include "tc_common.cuh"
 #include <math.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace stcat {
 namespace tc {
 
 constexpr int AT_DH = 32;
 constexpr int AT_QT = 128;          // query rows per item
-constexpr int AT_KMAX = 256;        // max keys (= max S)
+constexpr int AT_KBOX = 256;        // key rows per TMA box / per buffer set
+constexpr int AT_KMAX = 512;        // max keys (= max S)
 constexpr int AT_Q_BYTES = AT_QT * AT_DH * 2;      // 8 KB
-constexpr int AT_KV_BYTES = AT_KMAX * AT_DH * 2;   // 16 KB
-constexpr int AT_P_BYTES = AT_QT * AT_KMAX * 2;    // 64 KB
+constexpr int AT_KV_BYTES = AT_KBOX * AT_DH * 2;   // 16 KB
+constexpr int AT_P_BYTES = AT_QT * AT_KBOX * 2;    // 64 KB
 constexpr int AT_SET_BYTES = AT_Q_BYTES + 2 * AT_KV_BYTES + AT_P_BYTES;  // 104 KB
-constexpr int AT_FWD_SMEM = 2 * AT_SET_BYTES + 1024 + 256;
-constexpr int AT_FWD_THREADS = 384;
+constexpr int AT_XCH_BYTES = 2 * 4 * AT_QT * 4;    // partial row max / row sum of the 4 softmax warpgroups
+constexpr int AT_FWD_SMEM = 2 * AT_SET_BYTES + 1024 + 256 + AT_XCH_BYTES;
+constexpr int AT_FWD_THREADS = 128 + 512;          // 4 control warps + 16 softmax warps
 
 struct AttnFwdParams {
     __nv_bfloat16* o;
@@ -45,19 +52,21 @@ struct AttnFwdParams {
 };
 
 // two finite floats -> packed bf16x2 with integer ops (round half away from zero: +0x8000 on the bit pattern grows the
-// magnitude of either sign; differs from round-to-nearest-even only on exact ties), which keeps the conversion off the XU
-// pipe that the exponentials saturate (profiles/r1_k_attn_fwd_timeline.md)
+// magnitude of either sign; differs from round-to-nearest-even only on exact ties)
 __device__ __forceinline__ uint32_t pack_prob_bf16x2(float lo, float hi) {
     return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
 }
 
-// V2 (staged for round 2, selected by STCAT_ATTN_FWD_V2=1, S <= 224): integer bf16 pack, and O in its own TMEM columns
-// (S: set * 224, O: 448 + set * 32) so that the score MMA of the set's next item is issued right behind the PV MMA instead
-// of after the epilogue.
-// STAG (with V2, STCAT_ATTN_FWD_V2=2): the two softmax warpgroups pass a token (named barriers 1 / 2) so that only one of them
-// is in the XU-bound pass 2 at a time, in the order A0 B0 A1 B1 ...: the other group's MMA hand-offs, epilogue and row-max
-// pass then run under it instead of both groups idling the XU pipe together (they otherwise run in lock step).
-template <bool DROP, bool V2, bool STAG = false>
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+template <bool DROP, bool BIG>
 __global__ void __launch_bounds__(AT_FWD_THREADS, 1)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
@@ -65,23 +74,23 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = base + 2 * AT_SET_BYTES;
     // per set: 0 qk_full (Q, K landed), 1 v_free (PV MMA done with V / P), 2 s_full (score MMA done: S readable, Q / K free),
-    //          3 p_full (P written), 4 o_full, 5 tmem_free (O read out), 6 v_full (V landed)
+    //          3 p_full (P written), 4 o_full, 5 tmem_free (O read out), 6 v_full (V landed).  BIG uses set 0's only.
     auto bar = [&](int set, int which) { return bar_base + 8u * (set * 7 + which); };
     const uint32_t tmem_slot = bar_base + 8u * 14;
+    const uint32_t xch = bar_base + 256;  // float [2][4][128]: partial row max, partial row sum per softmax warpgroup
     auto sQ = [&](int set) { return base + set * AT_SET_BYTES; };
     auto sK = [&](int set) { return base + set * AT_SET_BYTES + AT_Q_BYTES; };
     auto sV = [&](int set) { return base + set * AT_SET_BYTES + AT_Q_BYTES + AT_KV_BYTES; };
     auto sP = [&](int set) { return base + set * AT_SET_BYTES + AT_Q_BYTES + 2 * AT_KV_BYTES; };
-    // TMEM columns of a set's score tile and of its output accumulator
-    auto col_s = [&](int set) { return (uint32_t)(V2 ? set * 224 : set * 256); };
-    auto col_o = [&](int set) { return (uint32_t)(V2 ? 448 + set * 32 : set * 256); };
+    constexpr int NG = BIG ? 4 : 2;        // softmax warpgroups per item
+    constexpr int LAG = BIG ? 0 : 1;       // items between a score MMA and its PV MMA in the issue order
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total = p.B * p.H * p.nqt;
     const int n_mine = (total > (int)blockIdx.x) ? (total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int S = p.S;
-    const int nk16 = (S + 15) >> 4;          // PV contraction steps
-    const int npad = nk16 << 4;              // N of the score MMA
+    const int nk16 = (S + 15) >> 4;          // PV contraction steps = 16-column units of a score row
+    const int npad = nk16 << 4;              // N of the score MMA(s)
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
@@ -91,7 +100,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar(s, 0), 1); mbar_init(bar(s, 1), 1); mbar_init(bar(s, 2), 1);
-            mbar_init(bar(s, 3), 128); mbar_init(bar(s, 4), 1); mbar_init(bar(s, 5), 128);
+            mbar_init(bar(s, 3), NG * 128); mbar_init(bar(s, 4), 1); mbar_init(bar(s, 5), NG * 128);
             mbar_init(bar(s, 6), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -121,6 +130,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         h = t % p.H;
         b = t / p.H;
     };
+    // buffer set and per-set sequence number of item i
+    auto set_of = [&](int i) { return BIG ? 0 : (i & 1); };
+    auto seq_of = [&](int i) { return BIG ? i : (i >> 1); };
 
     // diagnostics: event ev of item i -> trace[i * 16 + ev] (CTA 0, first 8 items, one lane per role)
     auto T = [&](int i, int ev) {
@@ -132,14 +144,15 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         // (s_full), i.e. one whole softmax + PV + epilogue before they are needed again -> the load latency is hidden
         if (lane == 0) {
             for (int i = 0; i < n_mine; ++i) {
-                const int set = i & 1, k = i >> 1;
+                const int set = set_of(i), k = seq_of(i);
                 int b, h, qt;
                 decode(i, b, h, qt);
                 if (k > 0) mbar_wait(bar(set, 2), (k - 1) & 1);
                 T(i, 0);
-                mbar_expect_tx(bar(set, 0), AT_Q_BYTES + AT_KV_BYTES);
+                mbar_expect_tx(bar(set, 0), AT_Q_BYTES + (BIG ? 2 : 1) * AT_KV_BYTES);
                 tma_load_3d(sQ(set), &tmQ, bar(set, 0), h * AT_DH, qt * AT_QT, b);
                 tma_load_3d(sK(set), &tmK, bar(set, 0), h * AT_DH, 0, b);
+                if (BIG) tma_load_3d(sK(1), &tmK, bar(set, 0), h * AT_DH, AT_KBOX, b);
             }
         }
     } else if (warp == 3) {
@@ -147,49 +160,58 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         // is done) runs under the score MMA and the softmax of its own item
         if (lane == 0) {
             for (int i = 0; i < n_mine; ++i) {
-                const int set = i & 1, k = i >> 1;
+                const int set = set_of(i), k = seq_of(i);
                 int b, h, qt;
                 decode(i, b, h, qt);
                 mbar_wait(bar(set, 1), (k & 1) ^ 1);
                 T(i, 1);
-                mbar_expect_tx(bar(set, 6), AT_KV_BYTES);
+                mbar_expect_tx(bar(set, 6), (BIG ? 2 : 1) * AT_KV_BYTES);
                 tma_load_3d(sV(set), &tmV, bar(set, 6), h * AT_DH, 0, b);
+                if (BIG) tma_load_3d(sV(1), &tmV, bar(set, 6), h * AT_DH, AT_KBOX, b);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc_s = make_idesc(128, npad, false, false);
+            const uint32_t idesc_s0 = make_idesc(128, BIG ? 256 : npad, false, false);
+            const uint32_t idesc_s1 = make_idesc(128, BIG ? npad - 256 : 16, false, false);
             const uint32_t idesc_o = make_idesc(128, AT_DH, false, true);
-            for (int i = 0; i <= n_mine; ++i) {
-                if (i < n_mine) {
-                    const int set = i & 1, k = i >> 1;
+            for (int it = 0; it < n_mine + LAG; ++it) {
+                if (it < n_mine) {
+                    const int i = it, set = set_of(i), k = seq_of(i);
                     mbar_wait(bar(set, 0), k & 1);
                     T(i, 2);
-                    // V1: S and O share columns -> wait until the epilogue of the set's previous item has read O out.
-                    // V2: the S columns are free once the previous item's P is written (p_full, waited for before its PV)
-                    if (!V2) mbar_wait(bar(set, 5), (k & 1) ^ 1);
+                    // S and O share TMEM columns: wait until the epilogue of the set's previous item has read O out
+                    mbar_wait(bar(set, 5), (k & 1) ^ 1);
                     T(i, 3);
                     tc_fence_after();
 #pragma unroll
                     for (int kk = 0; kk < AT_DH / 16; ++kk) {
                         const uint64_t ad = make_desc(sQ(set) + kk * 32, 16, 512, LAYOUT_SW64);
                         const uint64_t bd = make_desc(sK(set) + kk * 32, 16, 512, LAYOUT_SW64);
-                        umma_bf16(tmem_base + col_s(set), ad, bd, idesc_s, kk > 0 ? 1u : 0u);
+                        umma_bf16(tmem_base + set * 256, ad, bd, idesc_s0, kk > 0 ? 1u : 0u);
+                    }
+                    if (BIG) {
+#pragma unroll
+                        for (int kk = 0; kk < AT_DH / 16; ++kk) {
+                            const uint64_t ad = make_desc(sQ(0) + kk * 32, 16, 512, LAYOUT_SW64);
+                            const uint64_t bd = make_desc(sK(1) + kk * 32, 16, 512, LAYOUT_SW64);
+                            umma_bf16(tmem_base + 256, ad, bd, idesc_s1, kk > 0 ? 1u : 0u);
+                        }
                     }
                     umma_commit(bar(set, 2));
                 }
-                if (i >= 1) {
-                    const int j = i - 1, set = j & 1, k = j >> 1;
+                if (it >= LAG) {
+                    const int j = it - LAG, set = set_of(j), k = seq_of(j);
                     mbar_wait(bar(set, 3), k & 1);
                     T(j, 4);
                     mbar_wait(bar(set, 6), k & 1);
-                    if (V2) mbar_wait(bar(set, 5), (k & 1) ^ 1);  // O columns of the set read out by the previous epilogue
                     T(j, 5);
                     tc_fence_after();
                     for (int t = 0; t < nk16; ++t) {
-                        const uint64_t ad = make_desc(sP(set) + (t >> 2) * 16384 + (t & 3) * 32, 16, 1024, LAYOUT_SW128);
-                        const uint64_t bd = make_desc(sV(set) + t * 1024, 512, 512, LAYOUT_SW64);
-                        umma_bf16(tmem_base + col_o(set), ad, bd, idesc_o, t > 0 ? 1u : 0u);
+                        const int ps = BIG ? (t >> 4) : set, tt = t & 15;  // 16 steps (256 keys) per buffer set
+                        const uint64_t ad = make_desc(sP(ps) + (tt >> 2) * 16384 + (tt & 3) * 32, 16, 1024, LAYOUT_SW128);
+                        const uint64_t bd = make_desc(sV(ps) + tt * 1024, 512, 512, LAYOUT_SW64);
+                        umma_bf16(tmem_base + set * 256, ad, bd, idesc_o, t > 0 ? 1u : 0u);
                     }
                     umma_commit(bar(set, 4));
                     umma_commit(bar(set, 1));
@@ -198,22 +220,31 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
         }
     } else if (warp >= 4) {
-        const int g = (warp - 4) >> 2;      // softmax warpgroup = buffer set
-        const int q4 = warp & 3;            // TMEM lane quadrant
+        const int w = warp - 4;
+        const int wg = w >> 2;               // softmax warpgroup
+        const int q4 = warp & 3;             // TMEM lane quadrant of this warp
         const int row = q4 * 32 + lane;
+        const int set = BIG ? 0 : (wg >> 1);
+        const int part = BIG ? wg : (wg & 1);          // which share of the row's columns
+        const int xbar = BIG ? 1 : 1 + set;            // named barrier of the item's softmax warpgroups
         const float sc = p.scale * 1.4426950408889634f;
-        const int nchunk = (S + 31) >> 5;
-        const bool tr = (q4 == 0 && lane == 0);
-        for (int i = g; i < n_mine; i += 2) {
-            const int set = g, k = i >> 1;
+        // this thread's columns: 16-column units [u0, u1) of the nk16 units of a row
+        const int u0 = (part * nk16) / NG, u1 = ((part + 1) * nk16) / NG;
+        const int c0 = u0 * 16, nfull = (u1 - u0) >> 1;
+        const bool tail = ((u1 - u0) & 1) != 0;
+        const bool tr = (w == 0 && lane == 0);
+        const uint32_t xmax = xch, xsum = xch + 4 * AT_QT * 4;
+        for (int i = BIG ? 0 : set; i < n_mine; i += (BIG ? 1 : 2)) {
+            const int k = seq_of(i);
             int b, h, qt;
             decode(i, b, h, qt);
             if (tr) T(i, 7);
-            // key mask -> one bit per key (1 = masked), 32 keys per word, identical in every warp
-            uint32_t mw[8];
+            const bool live = qt * AT_QT + q4 * 32 < S;   // warp-uniform: any valid query row in this warp's 32
+            // key mask -> one bit per key of this thread's chunks (1 = masked), identical in every lane
+            uint32_t mw[5];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int key = c * 32 + lane;
+            for (int c = 0; c < 5; ++c) {
+                const int key = c0 + c * 32 + lane;
                 bool m = key >= S;
                 if (!m && p.key_mask) m = p.key_mask[(int64_t)b * S + key] != 0;
                 mw[c] = __ballot_sync(0xffffffffu, m);
@@ -222,140 +253,148 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mbar_wait(bar(set, 2), k & 1);
             if (tr) T(i, 9);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + col_s(set) + ((uint32_t)(q4 * 32) << 16);
-            // Both passes read the score row from TMEM in 32-column chunks, double-buffered in registers (the load of
-            // chunk c+1 is in flight while chunk c is reduced), with four independent max / sum chains per thread.
-            uint32_t ra[32], rb[32];
-            // ---- pass 1: row max ----
+            const uint32_t t_row = tmem_base + set * 256 + c0 + ((uint32_t)(q4 * 32) << 16);
+            // ---- pass 1: row max over this thread's columns ----
             float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-            auto max_chunk = [&](const uint32_t (&r)[32], const uint32_t w) {  // w identical in every lane
-                if (w == 0u) {
+            if (live) {
 #pragma unroll
-                    for (int e = 0; e < 32; e += 4) {
-                        m0 = fmaxf(m0, __uint_as_float(r[e]));
-                        m1 = fmaxf(m1, __uint_as_float(r[e + 1]));
-                        m2 = fmaxf(m2, __uint_as_float(r[e + 2]));
-                        m3 = fmaxf(m3, __uint_as_float(r[e + 3]));
+                for (int c = 0; c < 4; ++c) {
+                    if (c < nfull) {  // warp-uniform
+                        uint32_t r[32];
+                        tmem_ld32(t_row + c * 32, r);
+                        tmem_ld_wait();
+                        const uint32_t wm = mw[c];
+                        if (wm == 0u) {
+#pragma unroll
+                            for (int e = 0; e < 32; e += 4) {
+                                m0 = fmaxf(m0, __uint_as_float(r[e]));
+                                m1 = fmaxf(m1, __uint_as_float(r[e + 1]));
+                                m2 = fmaxf(m2, __uint_as_float(r[e + 2]));
+                                m3 = fmaxf(m3, __uint_as_float(r[e + 3]));
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e)
+                                if (!((wm >> e) & 1u)) m0 = fmaxf(m0, __uint_as_float(r[e]));
+                        }
                     }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e)
-                        if (!((w >> e) & 1u)) m0 = fmaxf(m0, __uint_as_float(r[e]));
                 }
-            };
-            tmem_ld32(t_row, ra);
-            tmem_ld_wait();
+                if (tail) {
+                    uint32_t r[16];
+                    tmem_ld16(t_row + nfull * 32, r);
+                    tmem_ld_wait();
+                    const uint32_t wm = (nfull == 0 ? mw[0] : nfull == 1 ? mw[1] : nfull == 2 ? mw[2] : nfull == 3 ? mw[3] : mw[4]);
 #pragma unroll
-            for (int c = 0; c < 8; c += 2) {
-                if (c < nchunk) {  // warp-uniform
-                    if (c + 1 < nchunk) tmem_ld32(t_row + (c + 1) * 32, rb);
-                    max_chunk(ra, mw[c]);
-                    tmem_ld_wait();
-                }
-                if (c + 1 < nchunk) {
-                    if (c + 2 < nchunk) tmem_ld32(t_row + (c + 2) * 32, ra);
-                    max_chunk(rb, mw[c + 1]);
-                    tmem_ld_wait();
+                    for (int e = 0; e < 16; ++e)
+                        if (!((wm >> e) & 1u)) m1 = fmaxf(m1, __uint_as_float(r[e]));
                 }
             }
-            const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+            float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(xmax + (wg * AT_QT + row) * 4), "f"(mx) : "memory");
+            named_bar_sync(xbar, NG * 128);
+#pragma unroll
+            for (int g2 = 0; g2 < NG; ++g2) {
+                float o;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o) : "r"(xmax + (((BIG ? 0 : set * 2) + g2) * AT_QT + row) * 4));
+                mx = fmaxf(mx, o);
+            }
             if (tr) T(i, 10);
             const float ms = (mx == -INFINITY) ? 0.f : mx * sc;
-            // ---- pass 2: p = exp2(s * sc - ms), row sum, P as bf16 into the swizzled smem tile ----
+            // ---- pass 2: p = exp2(s * sc - ms), partial row sum, P as bf16 into the swizzled smem tile ----
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-            const uint32_t prow = sP(set) + row * 128;
             // dropout: element index of (b, h, query, key 0) in the [B, H, S, S] probability tensor; the row sum (and so
             // lse and the 1/sum of the epilogue) stays that of the undropped softmax
             const uint64_t drow = DROP ? (((uint64_t)b * p.H + h) * S + (qt * AT_QT + row)) * (uint64_t)S : 0ull;
-            auto exp_chunk = [&](const uint32_t (&r)[32], const int c, const uint32_t w) {
-                uint32_t pk[16];
+            auto exp_chunk = [&](auto wtag, const uint32_t* r, const int col, const uint32_t wm) {
+                constexpr int W = decltype(wtag)::value;
+                uint32_t pk[W / 2];
 #pragma unroll
-                for (int e = 0; e < 32; e += 4) {
+                for (int e = 0; e < W; e += 4) {
                     float p0 = ex2_approx(fmaf(__uint_as_float(r[e]), sc, -ms));
                     float p1 = ex2_approx(fmaf(__uint_as_float(r[e + 1]), sc, -ms));
                     float p2 = ex2_approx(fmaf(__uint_as_float(r[e + 2]), sc, -ms));
                     float p3 = ex2_approx(fmaf(__uint_as_float(r[e + 3]), sc, -ms));
-                    if (w != 0u) {  // a chunk with masked keys (warp-uniform; rare: the padded tail / text padding)
-                        p0 = ((w >> e) & 1u) ? 0.f : p0;
-                        p1 = ((w >> (e + 1)) & 1u) ? 0.f : p1;
-                        p2 = ((w >> (e + 2)) & 1u) ? 0.f : p2;
-                        p3 = ((w >> (e + 3)) & 1u) ? 0.f : p3;
+                    if (wm != 0u) {  // a chunk with masked keys (warp-uniform; rare: the padded tail / text padding)
+                        p0 = ((wm >> e) & 1u) ? 0.f : p0;
+                        p1 = ((wm >> (e + 1)) & 1u) ? 0.f : p1;
+                        p2 = ((wm >> (e + 2)) & 1u) ? 0.f : p2;
+                        p3 = ((wm >> (e + 3)) & 1u) ? 0.f : p3;
                     }
                     s0 += p0; s1 += p1; s2 += p2; s3 += p3;
                     if (DROP) {
-                        p0 *= drop_mult(p.drop, drow + c * 32 + e);
-                        p1 *= drop_mult(p.drop, drow + c * 32 + e + 1);
-                        p2 *= drop_mult(p.drop, drow + c * 32 + e + 2);
-                        p3 *= drop_mult(p.drop, drow + c * 32 + e + 3);
+                        p0 *= drop_mult(p.drop, drow + col + e);
+                        p1 *= drop_mult(p.drop, drow + col + e + 1);
+                        p2 *= drop_mult(p.drop, drow + col + e + 2);
+                        p3 *= drop_mult(p.drop, drow + col + e + 3);
                     }
-                    if (V2) {
-                        pk[e >> 1] = pack_prob_bf16x2(p0, p1);
-                        pk[(e >> 1) + 1] = pack_prob_bf16x2(p2, p3);
-                    } else {
-                        __nv_bfloat162 b01 = __floats2bfloat162_rn(p0, p1), b23 = __floats2bfloat162_rn(p2, p3);
-                        pk[e >> 1] = *reinterpret_cast<uint32_t*>(&b01);
-                        pk[(e >> 1) + 1] = *reinterpret_cast<uint32_t*>(&b23);
-                    }
+                    __nv_bfloat162 b01 = __floats2bfloat162_rn(p0, p1), b23 = __floats2bfloat162_rn(p2, p3);
+                    pk[e >> 1] = *reinterpret_cast<uint32_t*>(&b01);
+                    pk[(e >> 1) + 1] = *reinterpret_cast<uint32_t*>(&b23);
                 }
-                const uint32_t blk = prow + (c >> 1) * 16384;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int chunk = ((c & 1) * 4 + j) ^ (row & 7);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + chunk * 16), "r"(pk[4 * j]),
-                                 "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
+                for (int j = 0; j < W / 8; ++j) {  // 16-byte pieces = 8 keys; 64-key blocks of 16 KB, 4 per buffer set
+                    const int cc = col + j * 8, blk = cc >> 6;
+                    const uint32_t a = sP(BIG ? (blk >> 2) : set) + (blk & 3) * 16384 + row * 128 + ((((cc & 63) >> 3) ^ (row & 7)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
+                                 "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
                 }
             };
-            if (STAG) {  // wait for the token: group 0's item k follows group 1's item k-1, group 1's item k follows group 0's
-                if (g == 0) { if (k > 0) asm volatile("bar.sync 1, 256;" ::: "memory"); }
-                else asm volatile("bar.sync 2, 256;" ::: "memory");
-            }
-            tmem_ld32(t_row, ra);
-            tmem_ld_wait();
+            if (live) {
 #pragma unroll
-            for (int c = 0; c < 8; c += 2) {
-                if (c < nchunk) {
-                    if (c + 1 < nchunk) tmem_ld32(t_row + (c + 1) * 32, rb);
-                    exp_chunk(ra, c, mw[c]);
-                    tmem_ld_wait();
+                for (int c = 0; c < 4; ++c) {
+                    if (c < nfull) {
+                        uint32_t r[32];
+                        tmem_ld32(t_row + c * 32, r);
+                        tmem_ld_wait();
+                        exp_chunk(std::integral_constant<int, 32>(), r, c0 + c * 32, mw[c]);
+                    }
                 }
-                if (c + 1 < nchunk) {
-                    if (c + 2 < nchunk) tmem_ld32(t_row + (c + 2) * 32, ra);
-                    exp_chunk(rb, c + 1, mw[c + 1]);
+                if (tail) {
+                    uint32_t r[16];
+                    tmem_ld16(t_row + nfull * 32, r);
                     tmem_ld_wait();
+                    const uint32_t wm = (nfull == 0 ? mw[0] : nfull == 1 ? mw[1] : nfull == 2 ? mw[2] : nfull == 3 ? mw[3] : mw[4]);
+                    exp_chunk(std::integral_constant<int, 16>(), r, c0 + nfull * 32, wm);
                 }
             }
-            if (STAG) {  // pass the token on, if the other group still has an item that waits for it
-                const int n0 = (n_mine + 1) >> 1, n1 = n_mine >> 1;
-                if (g == 0) { if (k < n1) asm volatile("bar.arrive 2, 256;" ::: "memory"); }
-                else { if (k + 1 < n0) asm volatile("bar.arrive 1, 256;" ::: "memory"); }
-            }
-            const float sum = (s0 + s1) + (s2 + s3);
+            float sum = (s0 + s1) + (s2 + s3);
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(xsum + (wg * AT_QT + row) * 4), "f"(sum) : "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             tc_fence_before();
             if (tr) T(i, 11);
             mbar_arrive(bar(set, 3));
-            // ---- epilogue ----
+            named_bar_sync(xbar, NG * 128);
+            sum = 0.f;
+#pragma unroll
+            for (int g2 = 0; g2 < NG; ++g2) {  // same order in every thread of the row: identical sums
+                float o;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o) : "r"(xsum + (((BIG ? 0 : set * 2) + g2) * AT_QT + row) * 4));
+                sum += o;
+            }
+            // ---- epilogue: this thread's share of the 32 output columns ----
             mbar_wait(bar(set, 4), k & 1);
             if (tr) T(i, 12);
             tc_fence_after();
-            uint32_t r[32];
-            tmem_ld32(tmem_base + col_o(set) + ((uint32_t)(q4 * 32) << 16), r);
+            constexpr int OC = AT_DH / NG;  // 16 or 8 columns
+            uint32_t r[OC];
+            const uint32_t t_o = tmem_base + set * 256 + part * OC + ((uint32_t)(q4 * 32) << 16);
+            if constexpr (OC == 16) tmem_ld16(t_o, r); else tmem_ld8(t_o, r);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(bar(set, 5));
             const int q = qt * AT_QT + row;
             if (q < S) {
                 const float inv = sum > 0.f ? 1.f / sum : 0.f;
-                uint32_t ob[16];
+                uint32_t ob[OC / 2];
 #pragma unroll
-                for (int e = 0; e < 32; e += 2) {
+                for (int e = 0; e < OC; e += 2) {
                     __nv_bfloat162 bb = __floats2bfloat162_rn(__uint_as_float(r[e]) * inv, __uint_as_float(r[e + 1]) * inv);
                     ob[e >> 1] = *reinterpret_cast<uint32_t*>(&bb);
                 }
-                uint4* dst = reinterpret_cast<uint4*>(p.o + ((int64_t)b * S + q) * p.ldo + h * AT_DH);
+                uint4* dst = reinterpret_cast<uint4*>(p.o + ((int64_t)b * S + q) * p.ldo + h * AT_DH + part * OC);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dst[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
-                p.lse[((int64_t)b * p.H + h) * S + q] = sum > 0.f ? mx * p.scale + logf(sum) : -INFINITY;
+                for (int j = 0; j < OC / 8; ++j) dst[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
+                if (part == 0) p.lse[((int64_t)b * p.H + h) * S + q] = sum > 0.f ? mx * p.scale + logf(sum) : -INFINITY;
             }
             if (tr) T(i, 13);
         }
@@ -370,21 +409,25 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 
 // ==================================================================================================
-// Backward.  Work item = (frame, head): all S <= 256 queries and keys.  TMA brings Q, K, V, dO head slices
-// [256 x 32] (64B swizzle, rows >= S zero-filled).  For every (128-query tile qt, 128-key tile kt) block:
+// Backward.  Work item = (frame, head): all S <= 512 queries and keys.  TMA brings Q, K, V, dO head slices
+// [S x 32] (64B swizzle, rows >= S zero-filled).  For every (128-key tile kt, 128-query tile qt) block, kt outer:
 //   MMA     S  = Q_qt K_kt^T, dP = dO_qt V_kt^T                 2 x (128 x 128 x 32) -> 2 x 128 TMEM columns
 //   threads p  = exp2(s*scale*log2e - lse*log2e), ds = p (dp - delta) scale, delta_i = dO_i . O_i;
 //           256 threads: a (row, 64-column half) each; P and dS as bf16 into 128B-swizzled smem tiles [128 x 128]
 //   MMA     dV_kt += P^T dO_qt, dK_kt += dS^T Q_qt   (the P / dS tiles read as MN-major A operands: no transpose)
 //           dQ_qt += dS K_kt                           (the dS tile read as K-major A operand)
-// dQ (per qt) and dK, dV (per item) accumulate in TMEM and are written as bf16, 64 B per row, straight to global.
-// TMEM columns: S 0..127 | dP 128..255 | dQ 256..287 | dK 288..351 | dV 352..415.
+// dK, dV (per key tile) and dQ (per item, all query tiles) accumulate in TMEM and are written as bf16 straight to global.
+// TMEM columns: S 0..127 | dP 128..255 | dK 256..287 | dV 288..319 | dQ 320 + 32 qt (up to 4 query tiles).
+// Pipeline: the threads copy a block's S / dP into registers and release the columns at once, so the score MMAs of block
+// n+1 are issued before the gradient MMAs of block n and run under the threads' exp / pack work; the threads wait for the
+// gradient MMAs of block n-1 only just before they overwrite the P / dS tiles with block n.
+// S <= 256: two load-buffer sets (the next item's operands arrive under the current item).  BIG (S <= 512): one set.
 // ==================================================================================================
-constexpr int AB_LOAD_BYTES = 4 * AT_KV_BYTES;             // Q, K, V, dO: 64 KB per item
+constexpr int AB_LOAD_BYTES = 4 * AT_KV_BYTES;             // Q, K, V, dO of <= 256 rows: 64 KB per item
 constexpr int AB_TILE_BYTES = 128 * 128 * 2;               // P or dS tile: 32 KB
 constexpr int AB_SMEM = 2 * AB_LOAD_BYTES + 2 * AB_TILE_BYTES + 1024 + 256;
 constexpr int AB_THREADS = 384;
-constexpr uint32_t AB_COL_S = 0, AB_COL_DP = 128, AB_COL_DQ = 256, AB_COL_DK = 288, AB_COL_DV = 352;
+constexpr uint32_t AB_COL_S = 0, AB_COL_DP = 128, AB_COL_DK = 256, AB_COL_DV = 288, AB_COL_DQ = 320;
 
 struct AttnBwdParams {
     const __nv_bfloat16* o;    // forward output [B*S, ldo]
@@ -397,7 +440,7 @@ struct AttnBwdParams {
     int B, H, S;
     float scale;
     DropArgs drop;             // dropout on the probabilities (DROP instantiation only)
-    long long* trace;          // diagnostics (TRACE instantiation only): SM clock at the phase boundaries of CTA 0's first item
+    long long* trace;          // diagnostics (TRACE instantiation only): SM clock at the phase boundaries of CTA 0's first blocks
 };
 
 __device__ __forceinline__ void store_row_bf16x32(__nv_bfloat16* dst, const uint32_t (&r)[32]) {
@@ -412,19 +455,19 @@ __device__ __forceinline__ void store_row_bf16x32(__nv_bfloat16* dst, const uint
     for (int j = 0; j < 4; ++j) d4[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
 }
 
-// IPACK (staged, STCAT_ATTN_BWD_V2=1): P and dS are packed to bf16 with integer ops (round half away from zero) instead of
-// F2FP, which shares the XU pipe with the exponentials (see pack_prob_bf16x2 and profiles/r1_k_attn_fwd_timeline.md).
-template <bool DROP, bool TRACE, bool IPACK = false>
+template <bool DROP, bool TRACE, bool BIG>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                    const AttnBwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr int NT = BIG ? 4 : 2;                              // max 128-row tiles per item
+    constexpr uint32_t TEN = BIG ? 2 * AT_KV_BYTES : AT_KV_BYTES;  // bytes per operand tensor in a load buffer
     auto sQ = [&](int set) { return base + set * AB_LOAD_BYTES; };
-    auto sK = [&](int set) { return base + set * AB_LOAD_BYTES + AT_KV_BYTES; };
-    auto sV = [&](int set) { return base + set * AB_LOAD_BYTES + 2 * AT_KV_BYTES; };
-    auto sDO = [&](int set) { return base + set * AB_LOAD_BYTES + 3 * AT_KV_BYTES; };
+    auto sK = [&](int set) { return base + set * AB_LOAD_BYTES + TEN; };
+    auto sV = [&](int set) { return base + set * AB_LOAD_BYTES + 2 * TEN; };
+    auto sDO = [&](int set) { return base + set * AB_LOAD_BYTES + 3 * TEN; };
     const uint32_t sP = base + 2 * AB_LOAD_BYTES;
     const uint32_t sDS = sP + AB_TILE_BYTES;
     const uint32_t bar_base = sDS + AB_TILE_BYTES;
@@ -437,7 +480,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int total = p.B * p.H;
     const int n_mine = (total > (int)blockIdx.x) ? (total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int S = p.S;
-    const int nqt = (S + 127) >> 7;  // query tiles == key tiles
+    const int nt = (S + 127) >> 7;  // query tiles == key tiles
+    auto set_of = [&](int it) { return BIG ? 0 : (it & 1); };
+    auto seq_of = [&](int it) { return BIG ? it : (it >> 1); };
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
@@ -462,7 +507,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     pdl_launch_dependents();
     pdl_wait();
-    // diagnostics: event ev of block blk (CTA 0, its first two work items = 8 blocks) -> trace[blk * 8 + ev]
+    // diagnostics: event ev of block blk (CTA 0, its first 16 blocks) -> trace[blk * 8 + ev]
     auto T = [&](uint32_t blk, int ev) {
         if (TRACE && p.trace != nullptr && blockIdx.x == 0 && blk < 16) p.trace[blk * 8 + ev] = clock64();
     };
@@ -470,15 +515,21 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (warp == 0) {
         if (lane == 0) {
             for (int it = 0; it < n_mine; ++it) {
-                const int set = it & 1, k = it >> 1;
+                const int set = set_of(it), k = seq_of(it);
                 const int w = blockIdx.x + it * gridDim.x;
                 const int h = w % p.H, b = w / p.H;
                 mbar_wait(bar(2 + set), (k & 1) ^ 1);
-                mbar_expect_tx(bar(set), AB_LOAD_BYTES);
+                mbar_expect_tx(bar(set), (BIG ? 2 : 1) * AB_LOAD_BYTES);
                 tma_load_3d(sQ(set), &tmQ, bar(set), h * AT_DH, 0, b);
                 tma_load_3d(sK(set), &tmK, bar(set), h * AT_DH, 0, b);
                 tma_load_3d(sV(set), &tmV, bar(set), h * AT_DH, 0, b);
                 tma_load_3d(sDO(set), &tmDO, bar(set), h * AT_DH, 0, b);
+                if (BIG) {
+                    tma_load_3d(sQ(set) + AT_KV_BYTES, &tmQ, bar(set), h * AT_DH, AT_KBOX, b);
+                    tma_load_3d(sK(set) + AT_KV_BYTES, &tmK, bar(set), h * AT_DH, AT_KBOX, b);
+                    tma_load_3d(sV(set) + AT_KV_BYTES, &tmV, bar(set), h * AT_DH, AT_KBOX, b);
+                    tma_load_3d(sDO(set) + AT_KV_BYTES, &tmDO, bar(set), h * AT_DH, AT_KBOX, b);
+                }
             }
         }
     } else if (warp == 1) {
@@ -486,56 +537,63 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const uint32_t idesc_s = make_idesc(128, 128, false, false);   // S, dP: A K-major, B K-major
             const uint32_t idesc_t = make_idesc(128, AT_DH, true, true);   // dV, dK: A MN-major (tile^T), B MN-major
             const uint32_t idesc_q = make_idesc(128, AT_DH, false, true);  // dQ: A K-major, B MN-major
-            uint32_t nb = 0, nq = 0;
-            for (int it = 0; it < n_mine; ++it) {
-                const int set = it & 1;
-                mbar_wait(bar(set), (it >> 1) & 1);
-                for (int qt = 0; qt < nqt; ++qt) {
-                    const int nq16 = min(8, (S - qt * 128 + 15) >> 4);  // 16-row groups of valid queries
-                    for (int kt = 0; kt < nqt; ++kt) {
-                        const int nk16 = min(8, (S - kt * 128 + 15) >> 4);
-                        mbar_wait(bar(5), (nb & 1) ^ 1);
-                        T(nb, 0);  // S / dP columns free: score MMAs issued
-                        tc_fence_after();
+            const int nblk = nt * nt;
+            const int nsteps = n_mine * nblk;
+            // step s: score MMAs of block s, then gradient MMAs of block s - 1 (block = (item, kt, qt), kt outer).  BIG has one
+            // load buffer: the next item's operands can only be requested once the last gradient MMAs of the current item
+            // have been issued, so at an item boundary the order is reversed.
+            auto issue_scores = [&](int s) {
+                const int it = s / nblk, r = s - it * nblk, kt = r / nt, qt = r - kt * nt, set = set_of(it);
+                if (r == 0) mbar_wait(bar(set), seq_of(it) & 1);   // the item's operands have landed
+                mbar_wait(bar(5), (s & 1) ^ 1);                    // S / dP columns copied out by the threads
+                T(s, 0);
+                tc_fence_after();
 #pragma unroll
-                        for (int kk = 0; kk < 2; ++kk) {
-                            const uint64_t aq = make_desc(sQ(set) + qt * 8192 + kk * 32, 16, 512, LAYOUT_SW64);
-                            const uint64_t bk = make_desc(sK(set) + kt * 8192 + kk * 32, 16, 512, LAYOUT_SW64);
-                            umma_bf16(tmem_base + AB_COL_S, aq, bk, idesc_s, kk);
-                        }
-#pragma unroll
-                        for (int kk = 0; kk < 2; ++kk) {
-                            const uint64_t ad = make_desc(sDO(set) + qt * 8192 + kk * 32, 16, 512, LAYOUT_SW64);
-                            const uint64_t bv = make_desc(sV(set) + kt * 8192 + kk * 32, 16, 512, LAYOUT_SW64);
-                            umma_bf16(tmem_base + AB_COL_DP, ad, bv, idesc_s, kk);
-                        }
-                        umma_commit(bar(4));
-                        mbar_wait(bar(6), nb & 1);
-                        T(nb, 1);  // P / dS tiles written
-                        if (qt == 0 && kt == 0) mbar_wait(bar(11), (it & 1) ^ 1);
-                        if (kt == 0) mbar_wait(bar(9), (nq & 1) ^ 1);
-                        T(nb, 2);  // accumulators free: gradient MMAs issued
-                        tc_fence_after();
-                        for (int t = 0; t < nq16; ++t) {  // contraction over the queries of this tile
-                            const uint64_t ap = make_desc(sP + t * 2048, 16384, 1024, LAYOUT_SW128);
-                            const uint64_t bd = make_desc(sDO(set) + (qt * 128 + t * 16) * 64, 512, 512, LAYOUT_SW64);
-                            umma_bf16(tmem_base + AB_COL_DV + kt * 32, ap, bd, idesc_t, (qt > 0 || t > 0) ? 1u : 0u);
-                            const uint64_t as = make_desc(sDS + t * 2048, 16384, 1024, LAYOUT_SW128);
-                            const uint64_t bq = make_desc(sQ(set) + (qt * 128 + t * 16) * 64, 512, 512, LAYOUT_SW64);
-                            umma_bf16(tmem_base + AB_COL_DK + kt * 32, as, bq, idesc_t, (qt > 0 || t > 0) ? 1u : 0u);
-                        }
-                        for (int t = 0; t < nk16; ++t) {  // contraction over the keys of this tile
-                            const uint64_t as = make_desc(sDS + (t >> 2) * 16384 + (t & 3) * 32, 16, 1024, LAYOUT_SW128);
-                            const uint64_t bk = make_desc(sK(set) + (kt * 128 + t * 16) * 64, 512, 512, LAYOUT_SW64);
-                            umma_bf16(tmem_base + AB_COL_DQ, as, bk, idesc_q, (kt > 0 || t > 0) ? 1u : 0u);
-                        }
-                        umma_commit(bar(7));
-                        if (kt == nqt - 1) { umma_commit(bar(8)); ++nq; }
-                        ++nb;
-                    }
+                for (int kk = 0; kk < 2; ++kk) {
+                    const uint64_t aq = make_desc(sQ(set) + qt * 8192 + kk * 32, 16, 512, LAYOUT_SW64);
+                    const uint64_t bk = make_desc(sK(set) + kt * 8192 + kk * 32, 16, 512, LAYOUT_SW64);
+                    umma_bf16(tmem_base + AB_COL_S, aq, bk, idesc_s, kk);
                 }
-                umma_commit(bar(10));
-                umma_commit(bar(2 + set));
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    const uint64_t ad = make_desc(sDO(set) + qt * 8192 + kk * 32, 16, 512, LAYOUT_SW64);
+                    const uint64_t bv = make_desc(sV(set) + kt * 8192 + kk * 32, 16, 512, LAYOUT_SW64);
+                    umma_bf16(tmem_base + AB_COL_DP, ad, bv, idesc_s, kk);
+                }
+                umma_commit(bar(4));
+            };
+            auto issue_grads = [&](int g) {
+                const int it = g / nblk, r = g - it * nblk, kt = r / nt, qt = r - kt * nt, set = set_of(it);
+                const int nq16 = min(8, (S - qt * 128 + 15) >> 4);  // 16-row groups of valid queries
+                const int nk16 = min(8, (S - kt * 128 + 15) >> 4);
+                mbar_wait(bar(6), g & 1);
+                T(g, 1);  // P / dS tiles written
+                if (r == 0) mbar_wait(bar(9), (it & 1) ^ 1);                      // dQ columns read out (previous item)
+                if (qt == 0) mbar_wait(bar(11), ((it * nt + kt) & 1) ^ 1);        // dK / dV columns read out (previous key tile)
+                T(g, 2);  // accumulators free: gradient MMAs issued
+                tc_fence_after();
+                for (int t = 0; t < nq16; ++t) {  // contraction over the queries of this tile
+                    const uint64_t ap = make_desc(sP + t * 2048, 16384, 1024, LAYOUT_SW128);
+                    const uint64_t bd = make_desc(sDO(set) + (qt * 128 + t * 16) * 64, 512, 512, LAYOUT_SW64);
+                    umma_bf16(tmem_base + AB_COL_DV, ap, bd, idesc_t, (qt > 0 || t > 0) ? 1u : 0u);
+                    const uint64_t as = make_desc(sDS + t * 2048, 16384, 1024, LAYOUT_SW128);
+                    const uint64_t bq = make_desc(sQ(set) + (qt * 128 + t * 16) * 64, 512, 512, LAYOUT_SW64);
+                    umma_bf16(tmem_base + AB_COL_DK, as, bq, idesc_t, (qt > 0 || t > 0) ? 1u : 0u);
+                }
+                for (int t = 0; t < nk16; ++t) {  // contraction over the keys of this tile
+                    const uint64_t as = make_desc(sDS + (t >> 2) * 16384 + (t & 3) * 32, 16, 1024, LAYOUT_SW128);
+                    const uint64_t bk = make_desc(sK(set) + (kt * 128 + t * 16) * 64, 512, 512, LAYOUT_SW64);
+                    umma_bf16(tmem_base + AB_COL_DQ + qt * 32, as, bk, idesc_q, (kt > 0 || t > 0) ? 1u : 0u);
+                }
+                umma_commit(bar(7));
+                if (qt == nt - 1) umma_commit(bar(10));
+                if (r == nblk - 1) { umma_commit(bar(8)); umma_commit(bar(2 + set)); }
+            };
+            for (int s = 0; s <= nsteps; ++s) {
+                const bool late = BIG && s > 0 && (s % nblk) == 0;
+                if (s < nsteps && !late) issue_scores(s);
+                if (s >= 1) issue_grads(s - 1);
+                if (s < nsteps && late) issue_scores(s);
             }
         }
     } else if (warp >= 4) {
@@ -544,25 +602,28 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int row = q4 * 32 + lane;
         const float sc = p.scale * 1.4426950408889634f;
         const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
-        uint32_t nb = 0, nq = 0;
+        const bool tr = TRACE && warp == 4 && lane == 0;
+        uint32_t nb = 0, ndkv = 0;
         for (int it = 0; it < n_mine; ++it) {
             const int w = blockIdx.x + it * gridDim.x;
             const int h = w % p.H, b = w / p.H;
-            uint32_t mw[8];
+            // key mask: 32 keys per word; lane c keeps word c (NT * 4 <= 16 words), fetched with a shuffle per chunk
+            uint32_t myw = 0;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < NT * 4; ++c) {
                 const int key = c * 32 + lane;
                 bool m = key >= S;
                 if (!m && p.key_mask) m = p.key_mask[(int64_t)b * S + key] != 0;
-                mw[c] = __ballot_sync(0xffffffffu, m);
+                const uint32_t wd = __ballot_sync(0xffffffffu, m);
+                if (lane == c) myw = wd;
             }
+            // per query tile: lse (log2 units) and delta = dO . O of this thread's row
+            float lse2[NT], dlt[NT];
 #pragma unroll
-            for (int qt = 0; qt < 2; ++qt) {
-                if (qt >= nqt) break;
+            for (int qt = 0; qt < NT; ++qt) {
                 const int q = qt * 128 + row;
-                const bool qvalid = q < S;
-                float delta = 0.f, lse2 = 0.f;
-                if (qvalid) {
+                float delta = 0.f, l2 = -INFINITY;
+                if (qt < nt && q < S) {
                     const uint4* po = reinterpret_cast<const uint4*>(p.o + ((int64_t)b * S + q) * p.ldo + h * AT_DH);
                     const uint4* pg = reinterpret_cast<const uint4*>(p.d_o + ((int64_t)b * S + q) * p.lddo + h * AT_DH);
 #pragma unroll
@@ -577,22 +638,25 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                             delta = fmaf(fa.y, fg.y, delta);
                         }
                     }
-                    lse2 = p.lse[((int64_t)b * p.H + h) * S + q] * 1.4426950408889634f;
+                    l2 = p.lse[((int64_t)b * p.H + h) * S + q] * 1.4426950408889634f;
                 }
-                const bool dead = !qvalid || lse2 == -INFINITY;  // padded query row or fully masked row
-                // dropout (o = (P o M) V): delta = dO . O still equals sum_j P_ij (M o dP)_ij; the P tile feeding dV is
-                // P o M, and dS = P o (M o dP - delta) * scale
-                const uint64_t drow = DROP ? (((uint64_t)b * p.H + h) * S + q) * (uint64_t)S : 0ull;
+                lse2[qt] = l2;   // -inf: padded query row or fully masked row -> every p and ds of the row is 0
+                dlt[qt] = delta;
+            }
+            for (int kt = 0; kt < nt; ++kt) {
+                for (int qt = 0; qt < nt; ++qt) {
+                    float l2 = lse2[0], delta = dlt[0];
 #pragma unroll
-                for (int kt = 0; kt < 2; ++kt) {
-                    if (kt >= nqt) break;
-                    const bool tr = TRACE && warp == 4 && lane == 0;
+                    for (int j = 1; j < NT; ++j) { if (qt == j) { l2 = lse2[j]; delta = dlt[j]; } }
+                    const bool dead = l2 == -INFINITY;
+                    // dropout (o = (P o M) V): delta = dO . O still equals sum_j P_ij (M o dP)_ij; the P tile feeding dV is
+                    // P o M, and dS = P o (M o dP - delta) * scale
+                    const uint64_t drow = DROP ? (((uint64_t)b * p.H + h) * S + (qt * 128 + row)) * (uint64_t)S : 0ull;
                     if (tr) T(nb, 3);  // threads ready for the block
                     mbar_wait(bar(4), nb & 1);
                     if (tr) T(nb, 4);  // S / dP landed in TMEM
-                    mbar_wait(bar(7), (nb & 1) ^ 1);
-                    if (tr) T(nb, 5);  // P / dS tiles free (gradient MMAs of the previous block done)
                     tc_fence_after();
+                    uint32_t pp[2][16], pd[2][16];
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         uint32_t rs[32], rd[32];
@@ -600,13 +664,16 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         tmem_ld32(tmem_base + lane_off + AB_COL_S + col, rs);
                         tmem_ld32(tmem_base + lane_off + AB_COL_DP + col, rd);
                         tmem_ld_wait();
-                        const uint32_t mwv = wg ? mw[kt * 4 + 2 + c] : mw[kt * 4 + c];  // warp-uniform
-                        uint32_t pp[16], pd[16];
+                        if (c == 1) {  // both chunks are in registers: the score MMAs of the next block may overwrite the columns
+                            tc_fence_before();
+                            mbar_arrive(bar(5));
+                        }
+                        const uint32_t mwv = __shfl_sync(0xffffffffu, myw, kt * 4 + wg * 2 + c);  // warp-uniform
                         const uint64_t dcol = drow + kt * 128 + col;
                         if (mwv == 0u) {
                             // no masked key in this chunk (the common case): no per-element predicates; a dead row
                             // (padding / fully masked) has lse_eff = +inf, so every p and ds is exactly 0
-                            const float lse_eff = dead ? INFINITY : lse2;
+                            const float lse_eff = dead ? INFINITY : l2;
                             const float dsc = p.scale;
 #pragma unroll
                             for (int e = 0; e < 32; e += 2) {
@@ -616,14 +683,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                                 const float m1 = DROP ? drop_mult(p.drop, dcol + e + 1) : 1.f;
                                 const float d0 = dead ? 0.f : p0 * (__uint_as_float(rd[e]) * m0 - delta) * dsc;
                                 const float d1 = dead ? 0.f : p1 * (__uint_as_float(rd[e + 1]) * m1 - delta) * dsc;
-                                if (IPACK) {
-                                    pp[e >> 1] = pack_prob_bf16x2(p0 * m0, p1 * m1);
-                                    pd[e >> 1] = pack_prob_bf16x2(d0, d1);
-                                } else {
-                                    __nv_bfloat162 bp = __floats2bfloat162_rn(p0 * m0, p1 * m1), bd = __floats2bfloat162_rn(d0, d1);
-                                    pp[e >> 1] = *reinterpret_cast<uint32_t*>(&bp);
-                                    pd[e >> 1] = *reinterpret_cast<uint32_t*>(&bd);
-                                }
+                                __nv_bfloat162 bp = __floats2bfloat162_rn(p0 * m0, p1 * m1), bd = __floats2bfloat162_rn(d0, d1);
+                                pp[c][e >> 1] = *reinterpret_cast<uint32_t*>(&bp);
+                                pd[c][e >> 1] = *reinterpret_cast<uint32_t*>(&bd);
                             }
                         } else {
                             const uint32_t wmask = dead ? 0xffffffffu : mwv;
@@ -632,57 +694,74 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                                 float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
                                 if (!((wmask >> e) & 1u)) {
                                     const float m0 = DROP ? drop_mult(p.drop, dcol + e) : 1.f;
-                                    p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), sc, -lse2));
+                                    p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), sc, -l2));
                                     d0 = p0 * (__uint_as_float(rd[e]) * m0 - delta) * p.scale;
                                     p0 *= m0;
                                 }
                                 if (!((wmask >> (e + 1)) & 1u)) {
                                     const float m1 = DROP ? drop_mult(p.drop, dcol + e + 1) : 1.f;
-                                    p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), sc, -lse2));
+                                    p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), sc, -l2));
                                     d1 = p1 * (__uint_as_float(rd[e + 1]) * m1 - delta) * p.scale;
                                     p1 *= m1;
                                 }
-                                if (IPACK) {
-                                    pp[e >> 1] = pack_prob_bf16x2(p0, p1);
-                                    pd[e >> 1] = pack_prob_bf16x2(d0, d1);
-                                } else {
-                                    __nv_bfloat162 bp = __floats2bfloat162_rn(p0, p1), bd = __floats2bfloat162_rn(d0, d1);
-                                    pp[e >> 1] = *reinterpret_cast<uint32_t*>(&bp);
-                                    pd[e >> 1] = *reinterpret_cast<uint32_t*>(&bd);
-                                }
+                                __nv_bfloat162 bp = __floats2bfloat162_rn(p0, p1), bd = __floats2bfloat162_rn(d0, d1);
+                                pp[c][e >> 1] = *reinterpret_cast<uint32_t*>(&bp);
+                                pd[c][e >> 1] = *reinterpret_cast<uint32_t*>(&bd);
                             }
                         }
-                        const uint32_t off = wg * 16384 + row * 128;
+                    }
+                    // the P / dS tiles are free once the gradient MMAs of the previous block have completed
+                    mbar_wait(bar(7), (nb & 1) ^ 1);
+                    if (tr) T(nb, 5);
+                    const uint32_t off = wg * 16384 + row * 128;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int chunk = (c * 4 + j) ^ (row & 7);
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + off + chunk * 16), "r"(pp[4 * j]),
-                                         "r"(pp[4 * j + 1]), "r"(pp[4 * j + 2]), "r"(pp[4 * j + 3]) : "memory");
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off + chunk * 16), "r"(pd[4 * j]),
-                                         "r"(pd[4 * j + 1]), "r"(pd[4 * j + 2]), "r"(pd[4 * j + 3]) : "memory");
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + off + chunk * 16), "r"(pp[c][4 * j]),
+                                         "r"(pp[c][4 * j + 1]), "r"(pp[c][4 * j + 2]), "r"(pp[c][4 * j + 3]) : "memory");
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off + chunk * 16), "r"(pd[c][4 * j]),
+                                         "r"(pd[c][4 * j + 1]), "r"(pd[c][4 * j + 2]), "r"(pd[c][4 * j + 3]) : "memory");
                         }
                     }
-                    tc_fence_before();
-                    mbar_arrive(bar(5));
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     if (tr) T(nb, 6);  // P / dS written
                     mbar_arrive(bar(6));
                     ++nb;
                 }
-                // dQ of this query tile: wg 0 -> dims 0..15, wg 1 -> dims 16..31
-                mbar_wait(bar(8), nq & 1);
+                // dK (wg 0) and dV (wg 1) of this key tile: thread row = key
+                mbar_wait(bar(10), ndkv & 1);
                 tc_fence_after();
-                uint32_t r16[16];
-                tmem_ld16(tmem_base + lane_off + AB_COL_DQ + wg * 16, r16);
+                uint32_t r0[32];
+                tmem_ld32(tmem_base + lane_off + (wg ? AB_COL_DV : AB_COL_DK), r0);
                 tmem_ld_wait();
                 tc_fence_before();
-                mbar_arrive(bar(9));
-                ++nq;
-                if (qvalid) {
+                mbar_arrive(bar(11));
+                ++ndkv;
+                __nv_bfloat16* dst = wg ? p.dv : p.dk;
+                const int64_t ldd = wg ? p.lddv : p.lddk;
+                const int key = kt * 128 + row;
+                if (key < S) store_row_bf16x32(dst + ((int64_t)b * S + key) * ldd + h * AT_DH, r0);
+            }
+            // dQ of every query tile: wg 0 -> dims 0..15, wg 1 -> dims 16..31
+            mbar_wait(bar(8), it & 1);
+            tc_fence_after();
+            uint32_t r16[NT][16];
+#pragma unroll
+            for (int qt = 0; qt < NT; ++qt)
+                if (qt < nt) tmem_ld16(tmem_base + lane_off + AB_COL_DQ + qt * 32 + wg * 16, r16[qt]);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(bar(9));
+#pragma unroll
+            for (int qt = 0; qt < NT; ++qt) {
+                const int q = qt * 128 + row;
+                if (qt < nt && q < S) {
                     uint32_t ob[8];
 #pragma unroll
                     for (int e = 0; e < 16; e += 2) {
-                        __nv_bfloat162 bb = __floats2bfloat162_rn(__uint_as_float(r16[e]), __uint_as_float(r16[e + 1]));
+                        __nv_bfloat162 bb = __floats2bfloat162_rn(__uint_as_float(r16[qt][e]), __uint_as_float(r16[qt][e + 1]));
                         ob[e >> 1] = *reinterpret_cast<uint32_t*>(&bb);
                     }
                     uint4* dst = reinterpret_cast<uint4*>(p.dq + ((int64_t)b * S + q) * p.lddq + h * AT_DH + wg * 16);
@@ -690,19 +769,6 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     dst[1] = make_uint4(ob[4], ob[5], ob[6], ob[7]);
                 }
             }
-            // dK (wg 0) and dV (wg 1) of the whole item: thread row = key
-            mbar_wait(bar(10), it & 1);
-            tc_fence_after();
-            uint32_t r0[32], r1[32];
-            tmem_ld32(tmem_base + lane_off + (wg ? AB_COL_DV : AB_COL_DK), r0);
-            if (nqt > 1) tmem_ld32(tmem_base + lane_off + (wg ? AB_COL_DV : AB_COL_DK) + 32, r1);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(bar(11));
-            __nv_bfloat16* dst = wg ? p.dv : p.dk;
-            const int64_t ldd = wg ? p.lddv : p.lddk;
-            if (row < S) store_row_bf16x32(dst + ((int64_t)b * S + row) * ldd + h * AT_DH, r0);
-            if (nqt > 1 && 128 + row < S) store_row_bf16x32(dst + ((int64_t)b * S + 128 + row) * ldd + h * AT_DH, r1);
         }
     }
     tc_fence_before();
@@ -723,7 +789,9 @@ int attn_tc_fwd_supported(int dtype, const void* q2, const void* p_avg, int B, i
     if (getenv("STCAT_DISABLE_TC_ATTN")) return 0;
     if (dtype != STCAT_BF16 || q2 || p_avg) return 0;
     if (Lq != Lk || Lq < 64 || Lq > tc::AT_KMAX) return 0;
-    if (B * H < 16) return 0;
+    // few short sequences (the temporal layers: one video, T <= 128 tokens) are served better by the mma.sync kernel
+    // (attention_small_mma.cu, L <= 128); everything longer runs here whatever the batch
+    if (Lq <= 128 && B * H < 16) return 0;
     auto al = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
     if (!al(q) || !al(k) || !al(v) || !al(o)) return 0;
     if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return 0;
@@ -739,8 +807,8 @@ int attn_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
     CUtensorMap tmQ, tmK, tmV;
     int rc;
     if ((rc = make_map_3d(&tmQ, q, B, S, (int64_t)H * AT_DH, ldq, AT_DH, AT_QT, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-    if ((rc = make_map_3d(&tmK, k, B, S, (int64_t)H * AT_DH, ldk, AT_DH, AT_KMAX, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-    if ((rc = make_map_3d(&tmV, v, B, S, (int64_t)H * AT_DH, ldv, AT_DH, AT_KMAX, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_map_3d(&tmK, k, B, S, (int64_t)H * AT_DH, ldk, AT_DH, AT_KBOX, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_map_3d(&tmV, v, B, S, (int64_t)H * AT_DH, ldv, AT_DH, AT_KBOX, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     AttnFwdParams p;
     p.o = (__nv_bfloat16*)o;
     p.ldo = ldo;
@@ -757,20 +825,15 @@ int attn_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
         if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
         if (e != cudaSuccess) return set_err((int)e, "attn_tc_fwd: smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
     const int total = B * H * p.nqt;
     const int sms = num_sms();
     const int grid = total < sms ? total : sms;
-    // V2 is staged for validation (profiles/r1_k_attn_fwd_timeline.md): opt-in, and only when the padded key count fits 224
-    const char* v2env = getenv("STCAT_ATTN_FWD_V2");
-    const bool v2 = v2env != nullptr && ((S + 15) / 16) * 16 <= 224;
+    const bool big = S > AT_KBOX;
     auto go = [&](auto kern) { launch_pdl(kern, dim3(grid), dim3(AT_FWD_THREADS), AT_FWD_SMEM, st, tmQ, tmK, tmV, p); };
-    if (v2 && atoi(v2env) >= 2) { if (drop.thresh) go(attn_tc_fwd_kernel<true, true, true>); else go(attn_tc_fwd_kernel<false, true, true>); }
-    else if (v2) { if (drop.thresh) go(attn_tc_fwd_kernel<true, true>); else go(attn_tc_fwd_kernel<false, true>); }
+    if (big) { if (drop.thresh) go(attn_tc_fwd_kernel<true, true>); else go(attn_tc_fwd_kernel<false, true>); }
     else { if (drop.thresh) go(attn_tc_fwd_kernel<true, false>); else go(attn_tc_fwd_kernel<false, false>); }
     return check_launch("attn_tc_fwd_kernel");
 }
@@ -782,7 +845,7 @@ int attn_tc_bwd_supported(int dtype, const void* q2, const void* dp_avg, const v
     if (getenv("STCAT_DISABLE_TC_ATTN") || getenv("STCAT_DISABLE_TC_ATTN_BWD")) return 0;
     if (dtype != STCAT_BF16 || q2 || dp_avg || !o) return 0;
     if (Lq != Lk || Lq < 64 || Lq > tc::AT_KMAX) return 0;
-    if (B * H < 16) return 0;
+    if (Lq <= 128 && B * H < 16) return 0;  // see attn_tc_fwd_supported
     auto al = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
     if (!al(q) || !al(k) || !al(v) || !al(o) || !al(d_o) || !al(dq) || !al(dk) || !al(dv)) return 0;
     if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8) || (lddo % 8) || (lddq % 8) || (lddk % 8) || (lddv % 8)) return 0;
@@ -797,10 +860,10 @@ int attn_tc_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
     CUtensorMap tmQ, tmK, tmV, tmDO;
     int rc;
     const int64_t E = (int64_t)H * AT_DH;
-    if ((rc = make_map_3d(&tmQ, q, B, S, E, ldq, AT_DH, AT_KMAX, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-    if ((rc = make_map_3d(&tmK, k, B, S, E, ldk, AT_DH, AT_KMAX, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-    if ((rc = make_map_3d(&tmV, v, B, S, E, ldv, AT_DH, AT_KMAX, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-    if ((rc = make_map_3d(&tmDO, d_o, B, S, E, lddo, AT_DH, AT_KMAX, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_map_3d(&tmQ, q, B, S, E, ldq, AT_DH, AT_KBOX, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_map_3d(&tmK, k, B, S, E, ldk, AT_DH, AT_KBOX, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_map_3d(&tmV, v, B, S, E, ldv, AT_DH, AT_KBOX, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_map_3d(&tmDO, d_o, B, S, E, lddo, AT_DH, AT_KBOX, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     AttnBwdParams p;
     p.o = (const __nv_bfloat16*)o; p.d_o = (const __nv_bfloat16*)d_o;
     p.ldo = ldo; p.lddo = lddo;
@@ -814,9 +877,9 @@ int attn_tc_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
     p.trace = g_attn_trace;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_tc_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_bwd_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_bwd_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_bwd_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_bwd_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_bwd_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
         if (e != cudaSuccess) return set_err((int)e, "attn_tc_bwd: smem attribute: %s", cudaGetErrorString(e));
@@ -825,12 +888,12 @@ int attn_tc_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
     const int total = B * H;
     const int sms = num_sms();
     const int grid = total < sms ? total : sms;
-    const bool ipack = getenv("STCAT_ATTN_BWD_V2") != nullptr && !g_attn_trace;  // staged, opt-in
-    if (ipack && drop.thresh) launch_pdl(attn_tc_bwd_kernel<true, false, true>, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, p);
-    else if (ipack) launch_pdl(attn_tc_bwd_kernel<false, false, true>, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, p);
-    else if (drop.thresh) launch_pdl(attn_tc_bwd_kernel<true, false>, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, p);
-    else if (g_attn_trace) launch_pdl(attn_tc_bwd_kernel<false, true>, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, p);
-    else launch_pdl(attn_tc_bwd_kernel<false, false>, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, p);
+    const bool big = S > AT_KBOX;
+    auto go = [&](auto kern) { launch_pdl(kern, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, p); };
+    if (big) { if (drop.thresh) go(attn_tc_bwd_kernel<true, false, true>); else go(attn_tc_bwd_kernel<false, false, true>); }
+    else if (drop.thresh) go(attn_tc_bwd_kernel<true, false, false>);
+    else if (g_attn_trace) go(attn_tc_bwd_kernel<false, true, false>);
+    else go(attn_tc_bwd_kernel<false, false, false>);
     return check_launch("attn_tc_bwd_kernel");
 }
 

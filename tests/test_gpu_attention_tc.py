@@ -1,5 +1,5 @@
 """-m gpu: the tcgen05 attention kernels (bf16 operands, the spatial encoder's shape class: Lq = Lk = S in
-[64, 256], head dim 32) against a float64 reference evaluated on the same bf16-rounded inputs.
+[64, 512], head dim 32) against a float64 reference evaluated on the same bf16-rounded inputs.
 
 Tolerances: P and dS are rounded to bf16 before their second MMA (relative 2^-9 per element), so outputs /
 gradients are gated at 1e-2 relative to max|ref| (measured ~2e-3); lse is fp32 end to end: 1e-4."""
@@ -32,6 +32,14 @@ CASES = [
     (4, 8, 117, True),     # res=320
     (7, 8, 186, False),    # res=416, odd number of items per CTA
     (64, 8, 213, True),    # full size
+    (3, 8, 257, True),     # just past one 256-key buffer set: the BIG instantiations (both sets as one, 4 softmax warpgroups)
+    (12, 8, 339, True),    # 448 x 720 frames: 14 x 23 + 1 + 16 tokens (datasets/build.py:21-22)
+    (8, 8, 417, False),    # res = 640
+    (20, 8, 400, True),    # more items than a CTA's first: BIG item sequencing
+    (2, 8, 512, True),     # the maximum
+    (1, 8, 129, False),    # temporal encoder at T = 128 (one video): few items, B * H < 16
+    (1, 8, 301, True),     # temporal encoder at MAX_VIDEO_LEN = 300
+    (40, 8, 64, False),    # the minimum
 ]
 
 
@@ -196,7 +204,7 @@ def _dropout_case(be, B, H, Lq, Lk, two, use_mask, dt, p, seed, off, pass_o=True
 
 
 @pytest.mark.parametrize("B,H,S,use_mask", [(2, 8, 213, True), (3, 8, 128, False), (2, 8, 256, True), (5, 8, 66, False),
-                                            (16, 8, 213, True)])
+                                            (16, 8, 213, True), (3, 8, 339, True), (2, 8, 512, False)])
 def test_tcgen05_attention_with_dropout(be, B, H, S, use_mask, monkeypatch):
     """The DROP instantiations of the tcgen05 kernels (mask applied to P before the PV MMA; to dP and to the P tile feeding dV
     in the backward) vs the explicit-mask float64 reference, and vs the generic SIMT kernels on the same mask."""
