@@ -66,7 +66,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-template <bool DROP, bool BIG>
+// SEP (S <= 224, not BIG): the output accumulator has its own TMEM columns (S: set * 224, O: 448 + set * 32), so the score
+// MMA of the set's next item is issued as soon as the current item's P is written (before its PV MMA), and the softmax
+// threads read an item's O out one item later (between the row-max pass and the exp pass of the set's next item), when it
+// has long been complete: neither the PV MMA nor the epilogue sits on the softmax threads' critical path, and the two
+// sets' exp passes (the MUFU-bound part) interleave instead of idling the pipe together.
+template <bool DROP, bool BIG, bool SEP>
 __global__ void __launch_bounds__(AT_FWD_THREADS, 1)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
@@ -82,8 +87,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     auto sK = [&](int set) { return base + set * AT_SET_BYTES + AT_Q_BYTES; };
     auto sV = [&](int set) { return base + set * AT_SET_BYTES + AT_Q_BYTES + AT_KV_BYTES; };
     auto sP = [&](int set) { return base + set * AT_SET_BYTES + AT_Q_BYTES + 2 * AT_KV_BYTES; };
+    static_assert(!(BIG && SEP), "SEP needs two buffer sets");
     constexpr int NG = BIG ? 4 : 2;        // softmax warpgroups per item
     constexpr int LAG = BIG ? 0 : 1;       // items between a score MMA and its PV MMA in the issue order
+    // TMEM columns of a set's score tile and of its output accumulator
+    auto col_s = [&](int set) { return (uint32_t)(SEP ? set * 224 : set * 256); };
+    auto col_o = [&](int set) { return (uint32_t)(SEP ? 448 + set * 32 : set * 256); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total = p.B * p.H * p.nqt;
@@ -175,47 +184,83 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const uint32_t idesc_s0 = make_idesc(128, BIG ? 256 : npad, false, false);
             const uint32_t idesc_s1 = make_idesc(128, BIG ? npad - 256 : 16, false, false);
             const uint32_t idesc_o = make_idesc(128, AT_DH, false, true);
-            for (int it = 0; it < n_mine + LAG; ++it) {
-                if (it < n_mine) {
-                    const int i = it, set = set_of(i), k = seq_of(i);
-                    mbar_wait(bar(set, 0), k & 1);
-                    T(i, 2);
-                    // S and O share TMEM columns: wait until the epilogue of the set's previous item has read O out
-                    mbar_wait(bar(set, 5), (k & 1) ^ 1);
-                    T(i, 3);
-                    tc_fence_after();
+            auto issue_score = [&](int i) {
+                const int set = set_of(i);
+#pragma unroll
+                for (int kk = 0; kk < AT_DH / 16; ++kk) {
+                    const uint64_t ad = make_desc(sQ(set) + kk * 32, 16, 512, LAYOUT_SW64);
+                    const uint64_t bd = make_desc(sK(set) + kk * 32, 16, 512, LAYOUT_SW64);
+                    umma_bf16(tmem_base + col_s(set), ad, bd, idesc_s0, kk > 0 ? 1u : 0u);
+                }
+                if (BIG) {
 #pragma unroll
                     for (int kk = 0; kk < AT_DH / 16; ++kk) {
-                        const uint64_t ad = make_desc(sQ(set) + kk * 32, 16, 512, LAYOUT_SW64);
-                        const uint64_t bd = make_desc(sK(set) + kk * 32, 16, 512, LAYOUT_SW64);
-                        umma_bf16(tmem_base + set * 256, ad, bd, idesc_s0, kk > 0 ? 1u : 0u);
+                        const uint64_t ad = make_desc(sQ(0) + kk * 32, 16, 512, LAYOUT_SW64);
+                        const uint64_t bd = make_desc(sK(1) + kk * 32, 16, 512, LAYOUT_SW64);
+                        umma_bf16(tmem_base + 256, ad, bd, idesc_s1, kk > 0 ? 1u : 0u);
                     }
-                    if (BIG) {
-#pragma unroll
-                        for (int kk = 0; kk < AT_DH / 16; ++kk) {
-                            const uint64_t ad = make_desc(sQ(0) + kk * 32, 16, 512, LAYOUT_SW64);
-                            const uint64_t bd = make_desc(sK(1) + kk * 32, 16, 512, LAYOUT_SW64);
-                            umma_bf16(tmem_base + 256, ad, bd, idesc_s1, kk > 0 ? 1u : 0u);
-                        }
-                    }
-                    umma_commit(bar(set, 2));
                 }
-                if (it >= LAG) {
-                    const int j = it - LAG, set = set_of(j), k = seq_of(j);
-                    mbar_wait(bar(set, 3), k & 1);
+                umma_commit(bar(set, 2));
+            };
+            auto issue_pv = [&](int j) {
+                const int set = set_of(j);
+                for (int t = 0; t < nk16; ++t) {
+                    const int ps = BIG ? (t >> 4) : set, tt = t & 15;  // 16 steps (256 keys) per buffer set
+                    const uint64_t ad = make_desc(sP(ps) + (tt >> 2) * 16384 + (tt & 3) * 32, 16, 1024, LAYOUT_SW128);
+                    const uint64_t bd = make_desc(sV(ps) + tt * 1024, 512, 512, LAYOUT_SW64);
+                    umma_bf16(tmem_base + col_o(set), ad, bd, idesc_o, t > 0 ? 1u : 0u);
+                }
+                umma_commit(bar(set, 4));
+                umma_commit(bar(set, 1));
+            };
+            if (SEP) {
+                for (int i = 0; i < 2 && i < n_mine; ++i) {
+                    mbar_wait(bar(i, 0), 0);
+                    T(i, 2);
+                    T(i, 3);
+                    tc_fence_after();
+                    issue_score(i);
+                }
+                for (int j = 0; j < n_mine; ++j) {
+                    const int set = j & 1, k = j >> 1;
+                    mbar_wait(bar(set, 3), k & 1);   // P(j) written: the set's S columns are free
                     T(j, 4);
+                    if (j + 2 < n_mine) {
+                        mbar_wait(bar(set, 0), (k + 1) & 1);
+                        T(j + 2, 2);
+                        T(j + 2, 3);
+                        tc_fence_after();
+                        issue_score(j + 2);
+                    }
                     mbar_wait(bar(set, 6), k & 1);
+                    mbar_wait(bar(set, 5), (k & 1) ^ 1);  // O columns of the set read out by the (deferred) epilogue of item j - 2
                     T(j, 5);
                     tc_fence_after();
-                    for (int t = 0; t < nk16; ++t) {
-                        const int ps = BIG ? (t >> 4) : set, tt = t & 15;  // 16 steps (256 keys) per buffer set
-                        const uint64_t ad = make_desc(sP(ps) + (tt >> 2) * 16384 + (tt & 3) * 32, 16, 1024, LAYOUT_SW128);
-                        const uint64_t bd = make_desc(sV(ps) + tt * 1024, 512, 512, LAYOUT_SW64);
-                        umma_bf16(tmem_base + set * 256, ad, bd, idesc_o, t > 0 ? 1u : 0u);
-                    }
-                    umma_commit(bar(set, 4));
-                    umma_commit(bar(set, 1));
+                    issue_pv(j);
                     T(j, 6);
+                }
+            } else {
+                for (int it = 0; it < n_mine + LAG; ++it) {
+                    if (it < n_mine) {
+                        const int i = it, set = set_of(i), k = seq_of(i);
+                        mbar_wait(bar(set, 0), k & 1);
+                        T(i, 2);
+                        // S and O share TMEM columns: wait until the epilogue of the set's previous item has read O out
+                        mbar_wait(bar(set, 5), (k & 1) ^ 1);
+                        T(i, 3);
+                        tc_fence_after();
+                        issue_score(i);
+                    }
+                    if (it >= LAG) {
+                        const int j = it - LAG, set = set_of(j), k = seq_of(j);
+                        mbar_wait(bar(set, 3), k & 1);
+                        T(j, 4);
+                        mbar_wait(bar(set, 6), k & 1);
+                        T(j, 5);
+                        tc_fence_after();
+                        issue_pv(j);
+                        T(j, 6);
+                    }
                 }
             }
         }
@@ -234,6 +279,37 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const bool tail = ((u1 - u0) & 1) != 0;
         const bool tr = (w == 0 && lane == 0);
         const uint32_t xmax = xch, xsum = xch + 4 * AT_QT * 4;
+        // ---- epilogue of an item: this thread's share of the 32 output columns, 1 / rowsum, bf16, lse ----
+        auto epilogue = [&](int i, int b, int h, int qt, int k, float sum, float mx) {
+            mbar_wait(bar(set, 4), k & 1);
+            if (tr) T(i, 12);
+            tc_fence_after();
+            constexpr int OC = AT_DH / NG;  // 16 or 8 columns
+            uint32_t r[OC];
+            const uint32_t t_o = tmem_base + col_o(set) + part * OC + ((uint32_t)(q4 * 32) << 16);
+            if constexpr (OC == 16) tmem_ld16(t_o, r); else tmem_ld8(t_o, r);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(bar(set, 5));
+            const int q = qt * AT_QT + row;
+            if (q < S) {
+                const float inv = sum > 0.f ? 1.f / sum : 0.f;
+                uint32_t ob[OC / 2];
+#pragma unroll
+                for (int e = 0; e < OC; e += 2) {
+                    __nv_bfloat162 bb = __floats2bfloat162_rn(__uint_as_float(r[e]) * inv, __uint_as_float(r[e + 1]) * inv);
+                    ob[e >> 1] = *reinterpret_cast<uint32_t*>(&bb);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(p.o + ((int64_t)b * S + q) * p.ldo + h * AT_DH + part * OC);
+#pragma unroll
+                for (int j = 0; j < OC / 8; ++j) dst[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
+                if (part == 0) p.lse[((int64_t)b * p.H + h) * S + q] = sum > 0.f ? mx * p.scale + logf(sum) : -INFINITY;
+            }
+            if (tr) T(i, 13);
+        };
+        bool have_prev = false;   // SEP: the previous item of this set, whose epilogue is still to run
+        int pv_b = 0, pv_h = 0, pv_qt = 0, pv_k = 0, pv_i = 0;
+        float pv_sum = 0.f, pv_mx = 0.f;
         for (int i = BIG ? 0 : set; i < n_mine; i += (BIG ? 1 : 2)) {
             const int k = seq_of(i);
             int b, h, qt;
@@ -253,7 +329,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mbar_wait(bar(set, 2), k & 1);
             if (tr) T(i, 9);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + set * 256 + c0 + ((uint32_t)(q4 * 32) << 16);
+            const uint32_t t_row = tmem_base + col_s(set) + c0 + ((uint32_t)(q4 * 32) << 16);
             // ---- pass 1: row max over this thread's columns ----
             float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
             if (live) {
@@ -299,6 +375,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 mx = fmaxf(mx, o);
             }
             if (tr) T(i, 10);
+            if (SEP && have_prev) epilogue(pv_i, pv_b, pv_h, pv_qt, pv_k, pv_sum, pv_mx);
             const float ms = (mx == -INFINITY) ? 0.f : mx * sc;
             // ---- pass 2: p = exp2(s * sc - ms), partial row sum, P as bf16 into the swizzled smem tile ----
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -371,33 +448,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o) : "r"(xsum + (((BIG ? 0 : set * 2) + g2) * AT_QT + row) * 4));
                 sum += o;
             }
-            // ---- epilogue: this thread's share of the 32 output columns ----
-            mbar_wait(bar(set, 4), k & 1);
-            if (tr) T(i, 12);
-            tc_fence_after();
-            constexpr int OC = AT_DH / NG;  // 16 or 8 columns
-            uint32_t r[OC];
-            const uint32_t t_o = tmem_base + set * 256 + part * OC + ((uint32_t)(q4 * 32) << 16);
-            if constexpr (OC == 16) tmem_ld16(t_o, r); else tmem_ld8(t_o, r);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(bar(set, 5));
-            const int q = qt * AT_QT + row;
-            if (q < S) {
-                const float inv = sum > 0.f ? 1.f / sum : 0.f;
-                uint32_t ob[OC / 2];
-#pragma unroll
-                for (int e = 0; e < OC; e += 2) {
-                    __nv_bfloat162 bb = __floats2bfloat162_rn(__uint_as_float(r[e]) * inv, __uint_as_float(r[e + 1]) * inv);
-                    ob[e >> 1] = *reinterpret_cast<uint32_t*>(&bb);
-                }
-                uint4* dst = reinterpret_cast<uint4*>(p.o + ((int64_t)b * S + q) * p.ldo + h * AT_DH + part * OC);
-#pragma unroll
-                for (int j = 0; j < OC / 8; ++j) dst[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
-                if (part == 0) p.lse[((int64_t)b * p.H + h) * S + q] = sum > 0.f ? mx * p.scale + logf(sum) : -INFINITY;
-            }
-            if (tr) T(i, 13);
+            if (SEP) { pv_b = b; pv_h = h; pv_qt = qt; pv_k = k; pv_i = i; pv_sum = sum; pv_mx = mx; have_prev = true; }
+            else epilogue(i, b, h, qt, k, sum, mx);
         }
+        if (SEP && have_prev) epilogue(pv_i, pv_b, pv_h, pv_qt, pv_k, pv_sum, pv_mx);
     }
     tc_fence_before();
     __syncthreads();
@@ -425,7 +479,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // ==================================================================================================
 constexpr int AB_LOAD_BYTES = 4 * AT_KV_BYTES;             // Q, K, V, dO of <= 256 rows: 64 KB per item
 constexpr int AB_TILE_BYTES = 128 * 128 * 2;               // P or dS tile: 32 KB
-constexpr int AB_SMEM = 2 * AB_LOAD_BYTES + 2 * AB_TILE_BYTES + 1024 + 256;
+constexpr int AB_PRO_BYTES = 2 * (2 * 512 * 4 + 64);       // per item buffer: lse2[512], delta[512] floats + 16 key-mask words
+constexpr int AB_SMEM = 2 * AB_LOAD_BYTES + 2 * AB_TILE_BYTES + 1024 + 256 + AB_PRO_BYTES;
 constexpr int AB_THREADS = 384;
 constexpr uint32_t AB_COL_S = 0, AB_COL_DP = 128, AB_COL_DK = 256, AB_COL_DV = 288, AB_COL_DQ = 320;
 
@@ -472,9 +527,15 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t sDS = sP + AB_TILE_BYTES;
     const uint32_t bar_base = sDS + AB_TILE_BYTES;
     // 0,1 load_full[set]; 2,3 load_free[set]; 4 sd_full; 5 sd_free; 6 pds_full; 7 pds_free; 8 dq_full; 9 dq_free;
-    // 10 dkv_full; 11 dkv_free
+    // 10 dkv_full; 11 dkv_free; 12,13 pro_full[buf]; 14,15 pro_free[buf]
     auto bar = [&](int which) { return bar_base + 8u * which; };
-    const uint32_t tmem_slot = bar_base + 8u * 12;
+    const uint32_t tmem_slot = bar_base + 8u * 16;
+    // per-item row statistics prepared by warps 2, 3 one item ahead (buffer = item & 1): lse * log2e and delta = dO . O of
+    // every query row, and the key mask as 32-key words
+    const uint32_t pro_base = bar_base + 256;
+    auto sLse = [&](int buf) { return pro_base + buf * (AB_PRO_BYTES / 2); };
+    auto sDlt = [&](int buf) { return pro_base + buf * (AB_PRO_BYTES / 2) + 512 * 4; };
+    auto sMsk = [&](int buf) { return pro_base + buf * (AB_PRO_BYTES / 2) + 2 * 512 * 4; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total = p.B * p.H;
@@ -494,6 +555,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int i = 0; i < 4; ++i) mbar_init(bar(i), 1);
         mbar_init(bar(4), 1); mbar_init(bar(5), 256); mbar_init(bar(6), 256); mbar_init(bar(7), 1);
         mbar_init(bar(8), 1); mbar_init(bar(9), 256); mbar_init(bar(10), 1); mbar_init(bar(11), 256);
+        mbar_init(bar(12), 64); mbar_init(bar(13), 64); mbar_init(bar(14), 256); mbar_init(bar(15), 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -572,18 +634,21 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 if (qt == 0) mbar_wait(bar(11), ((it * nt + kt) & 1) ^ 1);        // dK / dV columns read out (previous key tile)
                 T(g, 2);  // accumulators free: gradient MMAs issued
                 tc_fence_after();
+                // descriptors differ per step only in the start-address field (bits 0..13, units of 16 bytes)
+                const uint64_t ap0 = make_desc(sP, 16384, 1024, LAYOUT_SW128), as0 = make_desc(sDS, 16384, 1024, LAYOUT_SW128);
+                const uint64_t bd0 = make_desc(sDO(set) + qt * 8192, 512, 512, LAYOUT_SW64);
+                const uint64_t bq0 = make_desc(sQ(set) + qt * 8192, 512, 512, LAYOUT_SW64);
+                const uint64_t bk0 = make_desc(sK(set) + kt * 8192, 512, 512, LAYOUT_SW64);
+                const uint64_t ak0 = make_desc(sDS, 16, 1024, LAYOUT_SW128);
+#pragma unroll 4
                 for (int t = 0; t < nq16; ++t) {  // contraction over the queries of this tile
-                    const uint64_t ap = make_desc(sP + t * 2048, 16384, 1024, LAYOUT_SW128);
-                    const uint64_t bd = make_desc(sDO(set) + (qt * 128 + t * 16) * 64, 512, 512, LAYOUT_SW64);
-                    umma_bf16(tmem_base + AB_COL_DV, ap, bd, idesc_t, (qt > 0 || t > 0) ? 1u : 0u);
-                    const uint64_t as = make_desc(sDS + t * 2048, 16384, 1024, LAYOUT_SW128);
-                    const uint64_t bq = make_desc(sQ(set) + (qt * 128 + t * 16) * 64, 512, 512, LAYOUT_SW64);
-                    umma_bf16(tmem_base + AB_COL_DK, as, bq, idesc_t, (qt > 0 || t > 0) ? 1u : 0u);
+                    umma_bf16(tmem_base + AB_COL_DV, ap0 + (uint64_t)(t * 128), bd0 + (uint64_t)(t * 64), idesc_t, (qt > 0 || t > 0) ? 1u : 0u);
+                    umma_bf16(tmem_base + AB_COL_DK, as0 + (uint64_t)(t * 128), bq0 + (uint64_t)(t * 64), idesc_t, (qt > 0 || t > 0) ? 1u : 0u);
                 }
+#pragma unroll 4
                 for (int t = 0; t < nk16; ++t) {  // contraction over the keys of this tile
-                    const uint64_t as = make_desc(sDS + (t >> 2) * 16384 + (t & 3) * 32, 16, 1024, LAYOUT_SW128);
-                    const uint64_t bk = make_desc(sK(set) + (kt * 128 + t * 16) * 64, 512, 512, LAYOUT_SW64);
-                    umma_bf16(tmem_base + AB_COL_DQ + qt * 32, as, bk, idesc_q, (kt > 0 || t > 0) ? 1u : 0u);
+                    umma_bf16(tmem_base + AB_COL_DQ + qt * 32, ak0 + (uint64_t)((t >> 2) * 1024 + (t & 3) * 2), bk0 + (uint64_t)(t * 64), idesc_q,
+                              (kt > 0 || t > 0) ? 1u : 0u);
                 }
                 umma_commit(bar(7));
                 if (qt == nt - 1) umma_commit(bar(10));
@@ -596,34 +661,17 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 if (s < nsteps && late) issue_scores(s);
             }
         }
-    } else if (warp >= 4) {
-        const int wg = (warp - 4) >> 2;   // column half of the block: keys [wg*64, wg*64+64)
-        const int q4 = warp & 3;
-        const int row = q4 * 32 + lane;
-        const float sc = p.scale * 1.4426950408889634f;
-        const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
-        const bool tr = TRACE && warp == 4 && lane == 0;
-        uint32_t nb = 0, ndkv = 0;
+    } else if (warp == 2 || warp == 3) {
+        // row statistics of the NEXT item while the threads below work on the current one
+        const int tid = (warp - 2) * 32 + lane;  // 0..63
         for (int it = 0; it < n_mine; ++it) {
+            const int buf = it & 1;
             const int w = blockIdx.x + it * gridDim.x;
             const int h = w % p.H, b = w / p.H;
-            // key mask: 32 keys per word; lane c keeps word c (NT * 4 <= 16 words), fetched with a shuffle per chunk
-            uint32_t myw = 0;
-#pragma unroll
-            for (int c = 0; c < NT * 4; ++c) {
-                const int key = c * 32 + lane;
-                bool m = key >= S;
-                if (!m && p.key_mask) m = p.key_mask[(int64_t)b * S + key] != 0;
-                const uint32_t wd = __ballot_sync(0xffffffffu, m);
-                if (lane == c) myw = wd;
-            }
-            // per query tile: lse (log2 units) and delta = dO . O of this thread's row
-            float lse2[NT], dlt[NT];
-#pragma unroll
-            for (int qt = 0; qt < NT; ++qt) {
-                const int q = qt * 128 + row;
+            mbar_wait(bar(14 + buf), ((it >> 1) & 1) ^ 1);
+            for (int q = tid; q < nt * 128; q += 64) {
                 float delta = 0.f, l2 = -INFINITY;
-                if (qt < nt && q < S) {
+                if (q < S) {
                     const uint4* po = reinterpret_cast<const uint4*>(p.o + ((int64_t)b * S + q) * p.ldo + h * AT_DH);
                     const uint4* pg = reinterpret_cast<const uint4*>(p.d_o + ((int64_t)b * S + q) * p.lddo + h * AT_DH);
 #pragma unroll
@@ -640,111 +688,50 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     }
                     l2 = p.lse[((int64_t)b * p.H + h) * S + q] * 1.4426950408889634f;
                 }
-                lse2[qt] = l2;   // -inf: padded query row or fully masked row -> every p and ds of the row is 0
-                dlt[qt] = delta;
+                // -inf: padded query row or fully masked row -> every p and ds of the row is 0
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(sLse(buf) + q * 4), "f"(l2) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(sDlt(buf) + q * 4), "f"(delta) : "memory");
             }
-            for (int kt = 0; kt < nt; ++kt) {
-                for (int qt = 0; qt < nt; ++qt) {
-                    float l2 = lse2[0], delta = dlt[0];
-#pragma unroll
-                    for (int j = 1; j < NT; ++j) { if (qt == j) { l2 = lse2[j]; delta = dlt[j]; } }
-                    const bool dead = l2 == -INFINITY;
-                    // dropout (o = (P o M) V): delta = dO . O still equals sum_j P_ij (M o dP)_ij; the P tile feeding dV is
-                    // P o M, and dS = P o (M o dP - delta) * scale
-                    const uint64_t drow = DROP ? (((uint64_t)b * p.H + h) * S + (qt * 128 + row)) * (uint64_t)S : 0ull;
-                    if (tr) T(nb, 3);  // threads ready for the block
-                    mbar_wait(bar(4), nb & 1);
-                    if (tr) T(nb, 4);  // S / dP landed in TMEM
-                    tc_fence_after();
-                    uint32_t pp[2][16], pd[2][16];
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t rs[32], rd[32];
-                        const uint32_t col = wg * 64 + c * 32;
-                        tmem_ld32(tmem_base + lane_off + AB_COL_S + col, rs);
-                        tmem_ld32(tmem_base + lane_off + AB_COL_DP + col, rd);
-                        tmem_ld_wait();
-                        if (c == 1) {  // both chunks are in registers: the score MMAs of the next block may overwrite the columns
-                            tc_fence_before();
-                            mbar_arrive(bar(5));
-                        }
-                        const uint32_t mwv = __shfl_sync(0xffffffffu, myw, kt * 4 + wg * 2 + c);  // warp-uniform
-                        const uint64_t dcol = drow + kt * 128 + col;
-                        if (mwv == 0u) {
-                            // no masked key in this chunk (the common case): no per-element predicates; a dead row
-                            // (padding / fully masked) has lse_eff = +inf, so every p and ds is exactly 0
-                            const float lse_eff = dead ? INFINITY : l2;
-                            const float dsc = p.scale;
-#pragma unroll
-                            for (int e = 0; e < 32; e += 2) {
-                                const float p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), sc, -lse_eff));
-                                const float p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), sc, -lse_eff));
-                                const float m0 = DROP ? drop_mult(p.drop, dcol + e) : 1.f;
-                                const float m1 = DROP ? drop_mult(p.drop, dcol + e + 1) : 1.f;
-                                const float d0 = dead ? 0.f : p0 * (__uint_as_float(rd[e]) * m0 - delta) * dsc;
-                                const float d1 = dead ? 0.f : p1 * (__uint_as_float(rd[e + 1]) * m1 - delta) * dsc;
-                                __nv_bfloat162 bp = __floats2bfloat162_rn(p0 * m0, p1 * m1), bd = __floats2bfloat162_rn(d0, d1);
-                                pp[c][e >> 1] = *reinterpret_cast<uint32_t*>(&bp);
-                                pd[c][e >> 1] = *reinterpret_cast<uint32_t*>(&bd);
-                            }
-                        } else {
-                            const uint32_t wmask = dead ? 0xffffffffu : mwv;
-#pragma unroll
-                            for (int e = 0; e < 32; e += 2) {
-                                float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
-                                if (!((wmask >> e) & 1u)) {
-                                    const float m0 = DROP ? drop_mult(p.drop, dcol + e) : 1.f;
-                                    p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), sc, -l2));
-                                    d0 = p0 * (__uint_as_float(rd[e]) * m0 - delta) * p.scale;
-                                    p0 *= m0;
-                                }
-                                if (!((wmask >> (e + 1)) & 1u)) {
-                                    const float m1 = DROP ? drop_mult(p.drop, dcol + e + 1) : 1.f;
-                                    p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), sc, -l2));
-                                    d1 = p1 * (__uint_as_float(rd[e + 1]) * m1 - delta) * p.scale;
-                                    p1 *= m1;
-                                }
-                                __nv_bfloat162 bp = __floats2bfloat162_rn(p0, p1), bd = __floats2bfloat162_rn(d0, d1);
-                                pp[c][e >> 1] = *reinterpret_cast<uint32_t*>(&bp);
-                                pd[c][e >> 1] = *reinterpret_cast<uint32_t*>(&bd);
-                            }
-                        }
-                    }
-                    // the P / dS tiles are free once the gradient MMAs of the previous block have completed
-                    mbar_wait(bar(7), (nb & 1) ^ 1);
-                    if (tr) T(nb, 5);
-                    const uint32_t off = wg * 16384 + row * 128;
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int chunk = (c * 4 + j) ^ (row & 7);
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + off + chunk * 16), "r"(pp[c][4 * j]),
-                                         "r"(pp[c][4 * j + 1]), "r"(pp[c][4 * j + 2]), "r"(pp[c][4 * j + 3]) : "memory");
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off + chunk * 16), "r"(pd[c][4 * j]),
-                                         "r"(pd[c][4 * j + 1]), "r"(pd[c][4 * j + 2]), "r"(pd[c][4 * j + 3]) : "memory");
-                        }
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    if (tr) T(nb, 6);  // P / dS written
-                    mbar_arrive(bar(6));
-                    ++nb;
-                }
-                // dK (wg 0) and dV (wg 1) of this key tile: thread row = key
-                mbar_wait(bar(10), ndkv & 1);
-                tc_fence_after();
-                uint32_t r0[32];
-                tmem_ld32(tmem_base + lane_off + (wg ? AB_COL_DV : AB_COL_DK), r0);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(bar(11));
-                ++ndkv;
-                __nv_bfloat16* dst = wg ? p.dv : p.dk;
-                const int64_t ldd = wg ? p.lddv : p.lddk;
-                const int key = kt * 128 + row;
-                if (key < S) store_row_bf16x32(dst + ((int64_t)b * S + key) * ldd + h * AT_DH, r0);
+            for (int c = warp - 2; c < nt * 4; c += 2) {  // 32 keys per word
+                const int key = c * 32 + lane;
+                bool m = key >= S;
+                if (!m && p.key_mask) m = p.key_mask[(int64_t)b * S + key] != 0;
+                const uint32_t wd = __ballot_sync(0xffffffffu, m);
+                if (lane == 0) asm volatile("st.shared.b32 [%0], %1;" ::"r"(sMsk(buf) + c * 4), "r"(wd) : "memory");
             }
-            // dQ of every query tile: wg 0 -> dims 0..15, wg 1 -> dims 16..31
+            mbar_arrive(bar(12 + buf));
+        }
+    } else if (warp >= 4) {
+        const int wg = (warp - 4) >> 2;   // column half of the block: keys [wg*64, wg*64+64)
+        const int q4 = warp & 3;
+        const int row = q4 * 32 + lane;
+        const float sc = p.scale * 1.4426950408889634f;
+        const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+        const bool tr = TRACE && warp == 4 && lane == 0;
+        const int nblk = nt * nt;
+        const int nsteps = n_mine * nblk;
+        uint32_t ndkv = 0;
+        // read-outs of the accumulators are deferred by one block: by then the gradient MMAs that complete them have long
+        // finished, and the score MMAs of the block in between were issued before them
+        auto dkv_out = [&](int it, int kt) {  // dK (wg 0) and dV (wg 1) of a key tile: thread row = key
+            const int w = blockIdx.x + it * gridDim.x;
+            const int h = w % p.H, b = w / p.H;
+            mbar_wait(bar(10), ndkv & 1);
+            tc_fence_after();
+            uint32_t r0[32];
+            tmem_ld32(tmem_base + lane_off + (wg ? AB_COL_DV : AB_COL_DK), r0);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(bar(11));
+            ++ndkv;
+            __nv_bfloat16* dst = wg ? p.dv : p.dk;
+            const int64_t ldd = wg ? p.lddv : p.lddk;
+            const int key = kt * 128 + row;
+            if (key < S) store_row_bf16x32(dst + ((int64_t)b * S + key) * ldd + h * AT_DH, r0);
+        };
+        auto dq_out = [&](int it) {  // dQ of every query tile: wg 0 -> dims 0..15, wg 1 -> dims 16..31
+            const int w = blockIdx.x + it * gridDim.x;
+            const int h = w % p.H, b = w / p.H;
             mbar_wait(bar(8), it & 1);
             tc_fence_after();
             uint32_t r16[NT][16];
@@ -754,6 +741,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(bar(9));
+            mbar_arrive(bar(14 + (it & 1)));  // the item's row statistics are no longer needed
 #pragma unroll
             for (int qt = 0; qt < NT; ++qt) {
                 const int q = qt * 128 + row;
@@ -769,7 +757,107 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     dst[1] = make_uint4(ob[4], ob[5], ob[6], ob[7]);
                 }
             }
+        };
+        auto deferred = [&](int g) {  // accumulators completed by the gradient MMAs of block g
+            const int it = g / nblk, r = g - it * nblk, kt = r / nt, qt = r - kt * nt;
+            if (qt == nt - 1) dkv_out(it, kt);
+            if (r == nblk - 1) dq_out(it);
+        };
+        for (int s2 = 0; s2 < nsteps; ++s2) {
+            const uint32_t nb = (uint32_t)s2;
+            const int it = s2 / nblk, r = s2 - it * nblk, kt = r / nt, qt = r - kt * nt;
+            const int buf = it & 1;
+            const int w = blockIdx.x + it * gridDim.x;
+            const int h = w % p.H, b = w / p.H;
+            if (r == 0) mbar_wait(bar(12 + buf), (it >> 1) & 1);
+            float l2, delta;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l2) : "r"(sLse(buf) + (qt * 128 + row) * 4));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(delta) : "r"(sDlt(buf) + (qt * 128 + row) * 4));
+            uint32_t mw2[2];
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(mw2[0]), "=r"(mw2[1]) : "r"(sMsk(buf) + (kt * 4 + wg * 2) * 4));
+            const bool dead = l2 == -INFINITY;
+            // dropout (o = (P o M) V): delta = dO . O still equals sum_j P_ij (M o dP)_ij; the P tile feeding dV is
+            // P o M, and dS = P o (M o dP - delta) * scale
+            const uint64_t drow = DROP ? (((uint64_t)b * p.H + h) * S + (qt * 128 + row)) * (uint64_t)S : 0ull;
+            if (tr) T(nb, 3);  // threads ready for the block
+            mbar_wait(bar(4), nb & 1);
+            if (tr) T(nb, 4);  // S / dP landed in TMEM
+            tc_fence_after();
+            uint32_t pp[2][16], pd[2][16];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t rs[32], rd[32];
+                const uint32_t col = wg * 64 + c * 32;
+                tmem_ld32(tmem_base + lane_off + AB_COL_S + col, rs);
+                tmem_ld32(tmem_base + lane_off + AB_COL_DP + col, rd);
+                tmem_ld_wait();
+                if (c == 1) {  // both chunks are in registers: the score MMAs of the next block may overwrite the columns
+                    tc_fence_before();
+                    mbar_arrive(bar(5));
+                }
+                const uint32_t mwv = mw2[c];  // warp-uniform
+                const uint64_t dcol = drow + kt * 128 + col;
+                if (mwv == 0u) {
+                    // no masked key in this chunk (the common case): no per-element predicates; a dead row
+                    // (padding / fully masked) has lse_eff = +inf, so every p and ds is exactly 0
+                    const float lse_eff = dead ? INFINITY : l2;
+                    const float dsc = p.scale;
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) {
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), sc, -lse_eff));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), sc, -lse_eff));
+                        const float m0 = DROP ? drop_mult(p.drop, dcol + e) : 1.f;
+                        const float m1 = DROP ? drop_mult(p.drop, dcol + e + 1) : 1.f;
+                        const float d0 = dead ? 0.f : p0 * (__uint_as_float(rd[e]) * m0 - delta) * dsc;
+                        const float d1 = dead ? 0.f : p1 * (__uint_as_float(rd[e + 1]) * m1 - delta) * dsc;
+                        __nv_bfloat162 bp = __floats2bfloat162_rn(p0 * m0, p1 * m1), bd = __floats2bfloat162_rn(d0, d1);
+                        pp[c][e >> 1] = *reinterpret_cast<uint32_t*>(&bp);
+                        pd[c][e >> 1] = *reinterpret_cast<uint32_t*>(&bd);
+                    }
+                } else {
+                    const uint32_t wmask = dead ? 0xffffffffu : mwv;
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) {
+                        float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
+                        if (!((wmask >> e) & 1u)) {
+                            const float m0 = DROP ? drop_mult(p.drop, dcol + e) : 1.f;
+                            p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), sc, -l2));
+                            d0 = p0 * (__uint_as_float(rd[e]) * m0 - delta) * p.scale;
+                            p0 *= m0;
+                        }
+                        if (!((wmask >> (e + 1)) & 1u)) {
+                            const float m1 = DROP ? drop_mult(p.drop, dcol + e + 1) : 1.f;
+                            p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), sc, -l2));
+                            d1 = p1 * (__uint_as_float(rd[e + 1]) * m1 - delta) * p.scale;
+                            p1 *= m1;
+                        }
+                        __nv_bfloat162 bp = __floats2bfloat162_rn(p0, p1), bd = __floats2bfloat162_rn(d0, d1);
+                        pp[c][e >> 1] = *reinterpret_cast<uint32_t*>(&bp);
+                        pd[c][e >> 1] = *reinterpret_cast<uint32_t*>(&bd);
+                    }
+                }
+            }
+            // the P / dS tiles are free once the gradient MMAs of the previous block have completed
+            mbar_wait(bar(7), (nb & 1) ^ 1);
+            if (tr) T(nb, 5);
+            const uint32_t off = wg * 16384 + row * 128;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int chunk = (c * 4 + j) ^ (row & 7);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + off + chunk * 16), "r"(pp[c][4 * j]),
+                                 "r"(pp[c][4 * j + 1]), "r"(pp[c][4 * j + 2]), "r"(pp[c][4 * j + 3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off + chunk * 16), "r"(pd[c][4 * j]),
+                                 "r"(pd[c][4 * j + 1]), "r"(pd[c][4 * j + 2]), "r"(pd[c][4 * j + 3]) : "memory");
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (tr) T(nb, 6);  // P / dS written
+            mbar_arrive(bar(6));
+            if (s2 >= 1) deferred(s2 - 1);
         }
+        if (nsteps >= 1) deferred(nsteps - 1);
     }
     tc_fence_before();
     __syncthreads();
@@ -821,10 +909,12 @@ int attn_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
     p.trace = g_attn_trace;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
         if (e != cudaSuccess) return set_err((int)e, "attn_tc_fwd: smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
@@ -833,8 +923,10 @@ int attn_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
     const int grid = total < sms ? total : sms;
     const bool big = S > AT_KBOX;
     auto go = [&](auto kern) { launch_pdl(kern, dim3(grid), dim3(AT_FWD_THREADS), AT_FWD_SMEM, st, tmQ, tmK, tmV, p); };
-    if (big) { if (drop.thresh) go(attn_tc_fwd_kernel<true, true>); else go(attn_tc_fwd_kernel<false, true>); }
-    else { if (drop.thresh) go(attn_tc_fwd_kernel<true, false>); else go(attn_tc_fwd_kernel<false, false>); }
+    const bool sep = !big && ((S + 15) / 16) * 16 <= 224 && !getenv("STCAT_ATTN_FWD_NOSEP");
+    if (big) { if (drop.thresh) go(attn_tc_fwd_kernel<true, true, false>); else go(attn_tc_fwd_kernel<false, true, false>); }
+    else if (sep) { if (drop.thresh) go(attn_tc_fwd_kernel<true, false, true>); else go(attn_tc_fwd_kernel<false, false, true>); }
+    else { if (drop.thresh) go(attn_tc_fwd_kernel<true, false, false>); else go(attn_tc_fwd_kernel<false, false, false>); }
     return check_launch("attn_tc_fwd_kernel");
 }
 
