@@ -55,6 +55,8 @@ def parse_args():
                          "reference's training default is 0.1, which routes attention through the dropout-capable SIMT kernels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step from a CUDA graph")
+    ap.add_argument("--no-optimizer", action="store_true",
+                    help="time fwd + loss + bwd only (default: + the optimizer-side step: global-norm clip, AdamW, EMA, bf16 weight refresh)")
     ap.add_argument("--cpu-steps", type=int, default=2, help="timed CPU-baseline steps (bounded sample)")
     ap.add_argument("--no-prefetch", dest="e2e_prefetch", action="store_false",
                     help="e2e: copy each step's inputs on the compute stream instead of prefetching them under the previous step")
@@ -169,6 +171,15 @@ def cpu_reference_step_fn(args):
     P = {k: v.clone().requires_grad_(not k.endswith(".te")) for k, v in P.items()}
     inp = synthetic.make_inputs([w["T"]], w["H"], w["W"], w["L"], seed=42)
     tg = synthetic.make_targets([w["T"]], seed=42)
+    # optimizer-side step as the reference does it (train_net.py:134-143, engine/optimizer.py:5-58): clip_grad_norm_,
+    # torch.optim.AdamW with the temp_decoder LR group, EMA copy updated tensor by tensor
+    with_opt = not getattr(args, "no_optimizer", False)
+    trainable = {k: v for k, v in P.items() if v.requires_grad}
+    temp = [v for k, v in trainable.items() if "ground_decoder.temp_decoder" in k]
+    rest = [v for k, v in trainable.items() if "ground_decoder.temp_decoder" not in k]
+    optim = torch.optim.AdamW([{"params": rest}, {"params": temp, "lr": float(cfg.SOLVER.TEMP_LR)}], lr=float(cfg.SOLVER.BASE_LR),
+                              weight_decay=float(cfg.SOLVER.WEIGHT_DECAY)) if with_opt else None
+    ema = {k: v.detach().clone() for k, v in trainable.items()} if with_opt else None
 
     def step():
         for v in P.values():
@@ -178,6 +189,13 @@ def cpu_reference_step_fn(args):
         out = O.hot_path_forward(P, cfg, vis, inp["vis_mask"], inp["durations"], inp["vis_pos"], inp["text_mask"], txt)
         total, _ = O.stg_loss(cfg, out, tg["boxes"], tg["actioness"], [w["T"]])
         total.backward()
+        if with_opt:
+            torch.nn.utils.clip_grad_norm_(list(trainable.values()), float(cfg.SOLVER.MAX_GRAD_NORM))
+            optim.step()
+            decay = float(cfg.MODEL.EMA_DECAY)
+            with torch.no_grad():
+                for k, e in ema.items():
+                    e.copy_(e * decay + (1.0 - decay) * trainable[k].detach())
         return float(total.detach())
 
     return step
@@ -205,12 +223,12 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"STCAT hot path fwd+bwd (ground_encoder+ground_decoder+heads+loss), 1 clip/GPU, "
+        "config": {"workload": f"STCAT hot path fwd+bwd{'' if args.no_optimizer else '+optimizer step (clip, AdamW, EMA)'} (ground_encoder+ground_decoder+heads+loss), 1 clip/GPU, "
                                f"T={w['T']} res={w['res']} ({w['H']}x{w['W']} tokens) L={w['L']}, dropout 0, exact fp32 on host CPU cores",
                    "note": "reference algorithm on host CPU cores (oracle port of the pure-PyTorch reference; "
                            "/root/reference itself cannot travel to the GPU box)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} full-size clips fwd+bwd after {args.warmup} warm-up"},
+                         "sample": f"{args.steps} full-size clips fwd+bwd{'' if args.no_optimizer else '+optimizer step'} after {args.warmup} warm-up"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -250,6 +268,14 @@ def build_b200(args, device):
 
         sync.extra_streams = _side_streams(device)
     ops.set_grad_fusion(True)  # wgrad kernels accumulate straight into the flat buffer (no per-parameter adds)
+    # optimizer-side step of the training loop (clips/s is over fwd + bwd + optimizer): the reference's
+    # clip_grad_norm_ + AdamW (2 LR groups on the hot path) + EMA, fused (stcat_b200/optim.py), with the bf16 weight
+    # shadows refreshed in the same pass
+    opt = None
+    if not getattr(args, "no_optimizer", False):
+        from stcat_b200.optim import make_optimizer
+
+        opt = make_optimizer(cfg, model, grads)
 
     def fwd_bwd(vis, pos, txt):
         grads.zero()
@@ -260,11 +286,13 @@ def build_b200(args, device):
         sync.begin_step()
         sync.attach(out)
         total.backward()
-        sync.finish()  # sum over ranks; the 1/world factor folds into the optimizer's lr / clip step
+        sync.finish()  # mean over ranks (GradSync averages, like the DDP wrapper it replaces)
+        if opt is not None:
+            opt.step()
         return total
 
     return {"model": model, "cfg": cfg, "host": host, "dev": dev, "grads": grads, "fwd_bwd": fwd_bwd, "ops": ops, "w": w,
-            "sync": sync}
+            "sync": sync, "opt": opt}
 
 
 def kernel_breakdown(ctx, device):
@@ -606,7 +634,7 @@ def run_b200_arm(args):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {
-                "workload": f"STCAT hot path fwd+bwd (ground_encoder+ground_decoder+heads+loss), 1 clip/GPU, "
+                "workload": f"STCAT hot path fwd+bwd{'' if args.no_optimizer else '+optimizer step (clip, AdamW, EMA)'} (ground_encoder+ground_decoder+heads+loss), 1 clip/GPU, "
                             f"T={w['T']} res={w['res']} ({w['H']}x{w['W']} tokens) L={w['L']}, dropout {args.dropout:g}, "
                             f"{'bf16 operands / fp32 accumulate+residual' if args.precision == 'bf16' else 'exact fp32'}",
                 "parallelism": f"dp{world}", "cuda_graph": graph is not None,

@@ -39,6 +39,9 @@ extern "C" {
 #define STCAT_ESHAPE (-2)   /* shape not supported by this build (message says which) */
 #define STCAT_EALIGN (-3)   /* pointer / leading dimension alignment requirement violated */
 
+/* Bumped whenever a signature or the meaning of an argument changes; stcat_b200/cabi.py refuses a library whose version
+ * differs from the one it was written against (a stale locally built .so would otherwise be called with new signatures). */
+#define STCAT_ABI_VERSION 3
 STCAT_API int stcat_abi_version(void);
 STCAT_API const char* stcat_last_error(void);
 /* compute capability major*10+minor of the current device, or <0; 100 expected */

@@ -71,6 +71,7 @@ SIGNATURES["stcat_box_refine_bwd"] = (c_int, [_P, _P, _P, _P, _P, _L, _F, _P])
 SIGNATURES["stcat_stg_loss"] = (c_int, [_P] * 12 + [ctypes.POINTER(c_float), _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P])
 SIGNATURES["stcat_linear_group"] = (c_int, [_I, _I, ctypes.POINTER(_Job), _I, _P])
 MAX_GROUP_JOBS = 12
+ABI_VERSION = 3  # include/stcat_b200.h STCAT_ABI_VERSION
 
 _lib = None
 
@@ -86,6 +87,11 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
             f"{LIB_NAME} not found at {path}: build it with `python -m stcat_b200.build` "
             "(there is no CPU / PyTorch fallback for the STCAT hot path)")
     lib = ctypes.CDLL(path)
+    lib.stcat_abi_version.restype = c_int
+    got = lib.stcat_abi_version()
+    if got != ABI_VERSION:
+        raise RuntimeError(f"{path} implements C-ABI version {got}, this package expects {ABI_VERSION}: rebuild it with "
+                           "`python -m stcat_b200.build --force`")
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res

@@ -47,7 +47,7 @@ int colsum_group(const void* const* dy, const int64_t* ld, float* const* db, con
 
 using namespace stcat;
 
-extern "C" int stcat_abi_version(void) { return 2; }
+extern "C" int stcat_abi_version(void) { return STCAT_ABI_VERSION; }
 extern "C" const char* stcat_last_error(void) { return err_buf(); }
 
 extern "C" int stcat_device_arch(void) {

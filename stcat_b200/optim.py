@@ -244,3 +244,20 @@ def unused_parameters(model, cfg=None):
             elif not from_scratch and ".cross_attn.out_proj." in name:
                 out.append(p)
     return out
+
+
+def make_optimizer(cfg, model, flat: FlatGrads, enable_shadows: bool = True) -> FusedAdamW:
+    """The hot-path part of the reference's ``make_optimizer`` (engine/optimizer.py:25-58) + ``clip_grad_norm_``
+    (train_net.py:139-140) + ``update_ema`` (:143) as one FusedAdamW: parameters under ``ground_decoder.temp_decoder`` at
+    SOLVER.TEMP_LR, every other hot-path parameter at SOLVER.BASE_LR, SOLVER.WEIGHT_DECAY, SOLVER.MAX_GRAD_NORM,
+    MODEL.EMA_DECAY.  (``vis_encoder`` / ``text_encoder`` parameters are outside the hot path; hand them to a torch
+    optimizer and list them as ``extra_norm_params`` so the clip covers them.)"""
+    temp = [p for n, p in model.named_parameters() if "ground_decoder.temp_decoder" in n and p.requires_grad]
+    rest = [p for n, p in model.named_parameters() if "ground_decoder.temp_decoder" not in n and p.requires_grad]
+    groups = [{"params": rest}, {"params": temp, "lr": float(cfg.SOLVER.TEMP_LR)}]
+    opt = FusedAdamW(flat, groups, lr=float(cfg.SOLVER.BASE_LR), weight_decay=float(cfg.SOLVER.WEIGHT_DECAY),
+                     max_grad_norm=float(cfg.SOLVER.MAX_GRAD_NORM),
+                     ema_decay=float(cfg.MODEL.EMA_DECAY) if cfg.MODEL.EMA else None, frozen=unused_parameters(model, cfg))
+    if enable_shadows and ops.get_precision() == "bf16":
+        opt.enable_shadows()
+    return opt

@@ -24,7 +24,8 @@ def test_library_exports_every_declared_symbol():
     lib = cabi.load_library()
     for name in declared_symbols():
         assert hasattr(lib, name), name
-    assert lib.stcat_abi_version() >= 1
+    assert lib.stcat_abi_version() == cabi.ABI_VERSION
+    assert f"#define STCAT_ABI_VERSION {cabi.ABI_VERSION}" in open(os.path.join(ROOT, "include", "stcat_b200.h")).read()
 
 
 def test_product_path_raises_without_library(tmp_path, monkeypatch):

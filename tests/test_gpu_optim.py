@@ -1,13 +1,12 @@
-"""Kernels written after this round's GPU budget was spent: they compile for sm_100a and their host side is covered on CPU,
-but they have not run on a B200 yet.  Marked ``gpu_staged`` (NOT ``gpu``) so that the round-end ``pytest -m gpu`` tier only
-contains tests that have passed on the hardware; run them with ``pytest tests -m gpu_staged`` (scripts/validate_staged.sh)
-and move them to ``-m gpu`` files once green."""
+"""-m gpu: the fused optimizer-side step (csrc/optim.cu: stcat_sumsq, stcat_adamw_step) and optim.FusedAdamW on the B200
+against their fp32 restatement / torch.optim.AdamW + clip_grad_norm_ + the reference's EMA (first run on hardware: round 2,
+profiles/r2_a_validate_staged.log)."""
 import pytest
 import torch
 
 from helpers import rel_err
 
-pytestmark = [pytest.mark.gpu_staged, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a B200")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
