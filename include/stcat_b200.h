@@ -41,7 +41,7 @@ extern "C" {
 
 /* Bumped whenever a signature or the meaning of an argument changes; stcat_b200/cabi.py refuses a library whose version
  * differs from the one it was written against (a stale locally built .so would otherwise be called with new signatures). */
-#define STCAT_ABI_VERSION 3
+#define STCAT_ABI_VERSION 4
 STCAT_API int stcat_abi_version(void);
 STCAT_API const char* stcat_last_error(void);
 /* compute capability major*10+minor of the current device, or <0; 100 expected */
@@ -180,6 +180,21 @@ STCAT_API int stcat_sumsq(const float* x, int64_t n, float* accum, void* stream)
 STCAT_API int stcat_adamw_step(float* p, const float* g, float* m, float* v, float* ema, void* shadow_bf16, int64_t n, float lr,
                                float beta1, float beta2, float eps, float weight_decay, int64_t step, const float* total_sumsq,
                                float max_norm, float ema_decay, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Either side of the hot path.
+ *   pos_sine   : the backbone's image positional encoding, vision_model/position_encoding.py:70-94
+ *                (PositionEmbeddingSine(num_pos_feats, normalize=True)): mask [n, H, W] uint8 (1 = padded) ->
+ *                out [n, H, W, 2 * num_pos_feats] fp32, CHANNELS-LAST (the token assembly of the encoder reads it row by
+ *                row; as an [n, 2F, H, W] tensor it is the permuted view).  Channels [0, F) = y, [F, 2F) = x.
+ *   box_interp : engine/evaluate.py:20-38 linear_interp on the device: frame_ids [m] int64 ascending, boxes [m, 4] ->
+ *                out [n_frames, 4] for the frames first .. first + n_frames - 1 (frames outside [frame_ids[0],
+ *                frame_ids[m-1]] get -1).
+ * ---------------------------------------------------------------------------------------------- */
+STCAT_API int stcat_pos_sine(const uint8_t* mask, float* out, int n, int H, int W, int num_pos_feats, float temperature, float scale,
+                             void* stream);
+STCAT_API int stcat_box_interp(const int64_t* frame_ids, const float* boxes, int m, float* out, int64_t first, int n_frames,
+                               void* stream);
 
 /* Diagnostics (not on the product path): SM-clock timestamps at the phase boundaries of the tcgen05 spatial-attention
  * forward: CTA 0, its first 8 work items, 16 event slots per item (buf: 128 int64 in device memory; NULL = off). */

@@ -814,3 +814,42 @@ def map2d_attn_head(P: Params, prefix: str, x: Tensor, cfg_stcat, training: bool
     s = F.conv2d(m, P[f"{prefix}.predictor.weight"], P[f"{prefix}.predictor.bias"]).squeeze(1)
     s = s.view(nl, b, N, N)
     return s if training else torch.sigmoid(s) * mask2d
+
+
+# ----------------------------------------------------------------------------------------------
+# either side of the hot path
+# ----------------------------------------------------------------------------------------------
+def input_proj(P: Params, prefix: str, feats: Tensor) -> Tensor:
+    """``nn.Conv2d(2048, 256, kernel_size=1)`` (pipeline.py:41,64): feats [n, C, H, W] -> [n, 256, H, W]."""
+    w = P[f"{prefix}.weight"]
+    y = torch.einsum("nchw,oc->nohw", feats, w.view(w.shape[0], -1))
+    return y + P[f"{prefix}.bias"].view(1, -1, 1, 1)
+
+
+def feature_resizer(P: Params, prefix: str, x: Tensor) -> Tensor:
+    """FeatureResizer.forward in eval mode (language_model/bert.py:91-110): Linear -> LayerNorm(eps 1e-12)."""
+    y = x @ P[f"{prefix}.fc.weight"].t() + P[f"{prefix}.fc.bias"]
+    return layer_norm(y, P[f"{prefix}.layer_norm.weight"], P[f"{prefix}.layer_norm.bias"], eps=1e-12)
+
+
+def linear_interp(bbox_dict: dict) -> dict:
+    """engine/evaluate.py:20-38: fill every frame id between two predicted ones with the linear blend of their boxes."""
+    frame_ids = sorted(bbox_dict)
+    if len(frame_ids) < 2:
+        return bbox_dict
+    out = dict(bbox_dict)
+    for left, right in zip(frame_ids[:-1], frame_ids[1:]):
+        interval = right - left
+        if interval > 1:
+            bl, br = bbox_dict[left][0], bbox_dict[right][0]
+            delta = [(br[c] - bl[c]) / interval for c in range(4)]
+            for step in range(1, interval):
+                out[left + step] = [[bl[c] + step * delta[c] for c in range(4)]]
+    return {fid: out[fid] for fid in sorted(out)}
+
+
+def merge_even_odd(pred1, sted1, pred2, sted2):
+    """engine/evaluate.py:112-121: boxes of the even and the odd pass merged and interpolated, union of the two segments."""
+    boxes = dict(pred1)
+    boxes.update(pred2)
+    return linear_interp(boxes), [min(sted1[0], sted2[0]), max(sted1[1], sted2[1])]

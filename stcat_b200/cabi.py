@@ -63,6 +63,8 @@ SIGNATURES["stcat_sumsq"] = (c_int, [_P, _L, _P, _P])
 SIGNATURES["stcat_adamw_step"] = (c_int, [_P, _P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _L, _P, _F, _F, _P])
 SIGNATURES["stcat_debug_attn_trace"] = (c_int, [_P])
 SIGNATURES["stcat_debug_gemm_trace"] = (c_int, [_P])
+SIGNATURES["stcat_pos_sine"] = (c_int, [_P, _P, _I, _I, _I, _I, _F, _F, _P])
+SIGNATURES["stcat_box_interp"] = (c_int, [_P, _P, _I, _P, _L, _I, _P])
 SIGNATURES["stcat_debug_attn_counts"] = (c_int, [ctypes.POINTER(ctypes.c_longlong)])
 SIGNATURES["stcat_anchor_sine_fwd"] = (c_int, [_P, _P, _P, _L, _P])
 SIGNATURES["stcat_anchor_sine_bwd"] = (c_int, [_P, _P, _P, _L, _P])
@@ -71,7 +73,7 @@ SIGNATURES["stcat_box_refine_bwd"] = (c_int, [_P, _P, _P, _P, _P, _L, _F, _P])
 SIGNATURES["stcat_stg_loss"] = (c_int, [_P] * 12 + [ctypes.POINTER(c_float), _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P])
 SIGNATURES["stcat_linear_group"] = (c_int, [_I, _I, ctypes.POINTER(_Job), _I, _P])
 MAX_GROUP_JOBS = 12
-ABI_VERSION = 3  # include/stcat_b200.h STCAT_ABI_VERSION
+ABI_VERSION = 4  # include/stcat_b200.h STCAT_ABI_VERSION
 
 _lib = None
 
@@ -331,6 +333,21 @@ class CudaBackend:
         self.launches += 1
 
     # -- anchor glue ---------------------------------------------------
+    def pos_sine(self, mask, out, num_pos_feats: int, temperature: float, scale: float):
+        """mask [n, H, W] uint8 -> out [n, H, W, 2F] fp32 (channels-last)"""
+        n, H, W = mask.shape
+        assert out.shape == (n, H, W, 2 * num_pos_feats)
+        self._rc(self.lib.stcat_pos_sine(self._flat(mask, "mask", torch.uint8), self._flat(out, "out", torch.float32), n, H, W,
+                                         int(num_pos_feats), float(temperature), float(scale), self._stream()), "pos_sine")
+        self.launches += 1
+
+    def box_interp(self, frame_ids, boxes, out, first: int):
+        """frame_ids [m] int64 ascending, boxes [m, 4] fp32 -> out [n_frames, 4] fp32"""
+        self._rc(self.lib.stcat_box_interp(self._flat(frame_ids, "frame_ids", torch.int64), self._flat(boxes, "boxes", torch.float32),
+                                           int(frame_ids.shape[0]), self._flat(out, "out", torch.float32), int(first), int(out.shape[0]),
+                                           self._stream()), "box_interp")
+        self.launches += 1
+
     def anchor_sine_fwd(self, anchor, out, out_bf16=None):
         f = torch.float32
         self._rc(self.lib.stcat_anchor_sine_fwd(self._flat(anchor, "anchor", f), self._flat(out, "out", f),

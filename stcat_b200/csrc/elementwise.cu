@@ -297,6 +297,61 @@ __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T
 
 using namespace stcat;
 
+// ---- image positional encoding (vision_model/position_encoding.py:70-94, PositionEmbeddingSine(128, normalize=True)) ----
+// mask [n, H, W] (1 = padded) -> pos [n, H, W, 2F] channels-last (the layout the token assembly reads row by row):
+// y_embed = cumsum_h(!mask) / (column total + 1e-6) * scale, x_embed likewise along w; channel c < F: y, else x;
+// value = embed / T^(2 floor(k/2) / F), sin for even k, cos for odd k.  One block per pixel, one thread per (y|x, k).
+__global__ void __launch_bounds__(256) pos_sine_kernel(const uint8_t* __restrict__ mask, float* __restrict__ out, int H, int W, int F,
+                                                       float temperature, float scale) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int pix = blockIdx.x, w = pix % W, h = (pix / W) % H, f = pix / (W * H);
+    const uint8_t* m = mask + (int64_t)f * H * W;
+    __shared__ float emb[2];
+    if (threadIdx.x < 2) {
+        float cum = 0.f, tot = 0.f;
+        if (threadIdx.x == 0) {  // along h at column w
+            for (int i = 0; i < H; ++i) { const float v = m[i * W + w] ? 0.f : 1.f; tot += v; if (i <= h) cum += v; }
+        } else {                 // along w at row h
+            for (int j = 0; j < W; ++j) { const float v = m[h * W + j] ? 0.f : 1.f; tot += v; if (j <= w) cum += v; }
+        }
+        emb[threadIdx.x] = cum / (tot + 1e-6f) * scale;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * F; c += blockDim.x) {
+        const int k = c < F ? c : c - F;
+        const float dim_t = powf(temperature, (float)(2 * (k >> 1)) / (float)F);
+        const float p = emb[c < F ? 0 : 1] / dim_t;
+        out[(int64_t)pix * 2 * F + c] = (k & 1) ? cosf(p) : sinf(p);
+    }
+}
+
+// ---- box interpolation of the evaluation path (engine/evaluate.py:20-38 linear_interp): sampled frames carry predicted
+// boxes, every frame between two sampled frames gets the linear blend, frames outside the sampled range are skipped (-1).
+// frame_ids [m] ascending sampled frame indices, boxes [m, 4]; out [n_frames, 4] for frames first..first+n_frames-1.
+__global__ void __launch_bounds__(256) box_interp_kernel(const int64_t* __restrict__ frame_ids, const float* __restrict__ boxes, int m,
+                                                         float* __restrict__ out, int64_t first, int n_frames) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_frames) return;
+    const int64_t fid = first + i;
+    int lo = 0, hi = m - 1;  // largest index with frame_ids[idx] <= fid
+    if (m == 0 || fid < frame_ids[0] || fid > frame_ids[m - 1]) {
+        out[i * 4] = out[i * 4 + 1] = out[i * 4 + 2] = out[i * 4 + 3] = -1.f;
+        return;
+    }
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (frame_ids[mid] <= fid) lo = mid; else hi = mid - 1;
+    }
+    const int nxt = lo + 1 < m ? lo + 1 : lo;
+    const float span = (float)(frame_ids[nxt] - frame_ids[lo]);
+    const float t = span > 0.f ? (float)(fid - frame_ids[lo]) / span : 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out[i * 4 + c] = boxes[lo * 4 + c] + t * (boxes[nxt * 4 + c] - boxes[lo * 4 + c]);
+}
+
 extern "C" int stcat_add(const float* a, const float* b, float* out, void* out_bf16, int64_t n, void* stream) {
     STCAT_REQUIRE(a && b && (out || out_bf16), STCAT_EINVAL, "add: null pointer");
     STCAT_REQUIRE(n >= 0, STCAT_EINVAL, "add: n<0");
@@ -358,6 +413,19 @@ extern "C" int stcat_map2d_pool(const float* x, const uint8_t* valid, float* map
     return check_launch("map2d_pool_kernel");
 }
 
+extern "C" int stcat_pos_sine(const uint8_t* mask, float* out, int n, int H, int W, int num_pos_feats, float temperature, float scale,
+                              void* stream) {
+    STCAT_REQUIRE(mask && out && n >= 0 && H > 0 && W > 0 && num_pos_feats > 0, STCAT_EINVAL, "pos_sine: bad arguments");
+    if (n == 0) return 0;
+    launch_pdl(pos_sine_kernel, dim3((unsigned)(n * H * W)), dim3(256), 0, (cudaStream_t)stream, mask, out, H, W, num_pos_feats, temperature, scale);
+    return check_launch("pos_sine_kernel");
+}
+extern "C" int stcat_box_interp(const int64_t* frame_ids, const float* boxes, int m, float* out, int64_t first, int n_frames, void* stream) {
+    STCAT_REQUIRE(frame_ids && boxes && out && m >= 0 && n_frames >= 0, STCAT_EINVAL, "box_interp: bad arguments");
+    if (n_frames == 0) return 0;
+    launch_pdl(box_interp_kernel, dim3((unsigned)((n_frames + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, frame_ids, boxes, m, out, first, n_frames);
+    return check_launch("box_interp_kernel");
+}
 extern "C" int stcat_anchor_sine_fwd(const float* anchor, float* out, void* out_bf16, int64_t n, void* stream) {
     STCAT_REQUIRE(anchor && out && n >= 0, STCAT_EINVAL, "anchor_sine_fwd: bad arguments");
     if (n == 0) return 0;

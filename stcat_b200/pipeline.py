@@ -94,6 +94,38 @@ class STCATHotPath(nn.Module):
         return self
 
 
+class STCATNet(STCATHotPath):
+    """The whole of the reference's ``STCATNet`` (models/pipeline.py:12-121) at its OUTER seam: ``model(videos, texts)`` with
+    ``videos`` a NestedTensor of frames [sum(T), 3, H, W] and ``texts`` a list of captions (or pre-tokenised tensors), the same
+    output dict, the same ``state_dict`` names (``vis_encoder.0.body.*``, ``text_encoder.body.*``, ``text_encoder.resizer.*``,
+    ``input_proj.*`` and the hot-path modules).  The backbone trunk and the language model are library code (torchvision /
+    cuDNN convolutions with FrozenBatchNorm folded, Hugging Face RobertaModel), as in the reference; ``input_proj``, the
+    positional encoding, the resizer and everything after them run on this package's C ABI.
+
+    ``text_body`` / ``tokenizer``: pass a constructed ``RobertaModel`` and tokenizer to build offline (no checkpoint
+    download); default loads ``cfg.MODEL.TEXT_MODEL.NAME`` like the reference."""
+
+    def __init__(self, cfg, text_body=None, tokenizer=None):
+        super().__init__(cfg)
+        from .text import TextEncoder
+        from .vision import InputProj, VisionEncoder
+
+        self.vis_encoder = VisionEncoder(cfg)
+        self.text_encoder = TextEncoder(cfg.MODEL.TEXT_MODEL.NAME, cfg.MODEL.STCAT.HIDDEN, bool(cfg.MODEL.TEXT_MODEL.FREEZE),
+                                        body=text_body, tokenizer=tokenizer)
+        self.input_proj = InputProj(self.vis_encoder.num_channels, cfg.MODEL.STCAT.HIDDEN)
+
+    def forward(self, videos, texts, logger=None) -> dict:  # pipeline.py:52-121
+        from .nested import NestedTensor
+
+        vis_outputs, vis_pos = self.vis_encoder(videos)
+        feats, vis_mask, durations = vis_outputs.decompose()
+        feats = self.input_proj(feats)
+        text_outputs, _text_cls = self.text_encoder(texts, feats.device)
+        out = super().forward(NestedTensor(feats, vis_mask, durations), vis_pos, text_outputs)
+        return out
+
+
 class PostProcess(nn.Module):
     """Mirror of models/post_processor.py:17-55 with the T x T start/end scoring on the device."""
 

@@ -378,6 +378,36 @@ class EmuBackend:
             best[v] = int(sc.flatten().argmax())
         self.launches += 1
 
+    def pos_sine(self, mask, out, num_pos_feats, temperature, scale):
+        import math
+
+        nm = ~mask.bool()
+        y = nm.cumsum(1, dtype=torch.float32)
+        x = nm.cumsum(2, dtype=torch.float32)
+        y = y / (y[:, -1:, :] + 1e-6) * scale
+        x = x / (x[:, :, -1:] + 1e-6) * scale
+        k = torch.arange(num_pos_feats, dtype=torch.float32)
+        dim_t = temperature ** (2 * torch.div(k, 2, rounding_mode="floor") / num_pos_feats)
+        px, py = x[..., None] / dim_t, y[..., None] / dim_t
+        px = torch.stack((px[..., 0::2].sin(), px[..., 1::2].cos()), 4).flatten(3)
+        py = torch.stack((py[..., 0::2].sin(), py[..., 1::2].cos()), 4).flatten(3)
+        out.copy_(torch.cat((py, px), 3))
+        self.launches += 1
+
+    def box_interp(self, frame_ids, boxes, out, first):
+        ids = [int(v) for v in frame_ids]
+        for i in range(out.shape[0]):
+            fid = first + i
+            if not ids or fid < ids[0] or fid > ids[-1]:
+                out[i] = -1.0
+                continue
+            lo = max(j for j, v in enumerate(ids) if v <= fid)
+            nx = min(lo + 1, len(ids) - 1)
+            span = ids[nx] - ids[lo]
+            t = (fid - ids[lo]) / span if span > 0 else 0.0
+            out[i] = boxes[lo] + t * (boxes[nx] - boxes[lo])
+        self.launches += 1
+
     def map2d_pool(self, x, valid, out):
         B, N, d = x.shape
         out.zero_()
