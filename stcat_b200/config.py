@@ -175,6 +175,8 @@ def get_default_cfg() -> CfgNode:
             "SOLVER": {
                 "BATCH_SIZE": 1,
                 "BASE_LR": 2e-5,
+                "VIS_BACKBONE_LR": 1e-5,
+                "TEXT_LR": 2e-5,
                 "TEMP_LR": 1e-4,
                 "WEIGHT_DECAY": 0.0001,
                 "MAX_GRAD_NORM": 0.1,
