@@ -472,49 +472,33 @@ def run_b200_arm(args):
     pos = d["vis_pos"]
     loss_out = torch.zeros((), device=device)
 
-    def step_eager():
-        total = ctx["fwd_bwd"](vis, pos, txt)  # includes the bucketed gradient all-reduce for world > 1
-        loss_out.copy_(total.detach())
+    # the step (fwd + loss + bwd [+ gradient all-reduce] + optimizer) as the package's replayable training step
+    from stcat_b200.train import GraphedStep
 
-    graph = None
-    launches_per_step = None
     use_graph = not args.no_graph
-    # warm-up (eager; also fills the bf16 weight cache and the index caches)
     n_eager_warm = max(3, min(args.warmup, 3)) if use_graph else args.warmup
-    for _ in range(n_eager_warm):
-        l0 = be.launches
-        step_eager()
-        launches_per_step = be.launches - l0
-    barrier()
-    if use_graph:
-        try:
-            graph = torch.cuda.CUDAGraph()
-            side = torch.cuda.Stream(device)
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                step_eager()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize(device)
-            # thread_local: the NCCL watchdog thread polls events while the collectives are being captured
-            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                total = ctx["fwd_bwd"](vis, pos, txt)
-                loss_out.copy_(total.detach())
-            torch.cuda.synchronize(device)
-        except Exception as e:  # capture is an optimisation of launch overhead, not of the math
-            if rank == 0:
-                import traceback
+    l0 = be.launches
+    ctx["fwd_bwd"](vis, pos, txt)  # one counted eager step: C-ABI calls (= kernels of this package) per step
+    launches_per_step = be.launches - l0
+    fn = lambda vis, pos, txt: ctx["fwd_bwd"](vis, pos, txt)
+    try:
+        gstep = GraphedStep(fn, {"vis": vis, "pos": pos, "txt": txt}, use_graph=use_graph, warmup=n_eager_warm)
+    except Exception as e:  # capture is an optimisation of launch overhead, not of the math
+        if rank == 0:
+            import traceback
 
-                print(f"[bench] CUDA-graph capture unavailable ({type(e).__name__}: {e}); running eager", file=sys.stderr)
-                if os.environ.get("STCAT_BENCH_DEBUG"):
-                    traceback.print_exc()
-            graph = None
-            torch.cuda.synchronize(device)
+            print(f"[bench] CUDA-graph capture unavailable ({type(e).__name__}: {e}); running eager", file=sys.stderr)
+            if os.environ.get("STCAT_BENCH_DEBUG"):
+                traceback.print_exc()
+        torch.cuda.synchronize(device)
+        gstep = GraphedStep(fn, {"vis": vis, "pos": pos, "txt": txt}, use_graph=False, warmup=1)
+    graph = gstep.graph
+    vis, pos, txt = gstep.static["vis"], gstep.static["pos"], gstep.static["txt"]  # the step's static inputs
+    loss_out = gstep.loss
+    barrier()
 
     def step():
-        if graph is not None:
-            graph.replay()  # the NCCL all-reduces were captured on their side stream with the rest of the step
-        else:
-            step_eager()
+        gstep.replay()  # the NCCL all-reduces were captured on their side stream with the rest of the step
 
     for _ in range(max(0, args.warmup - n_eager_warm) + (2 if graph is not None else 0)):
         step()

@@ -41,7 +41,7 @@ extern "C" {
 
 /* Bumped whenever a signature or the meaning of an argument changes; stcat_b200/cabi.py refuses a library whose version
  * differs from the one it was written against (a stale locally built .so would otherwise be called with new signatures). */
-#define STCAT_ABI_VERSION 4
+#define STCAT_ABI_VERSION 5
 STCAT_API int stcat_abi_version(void);
 STCAT_API const char* stcat_last_error(void);
 /* compute capability major*10+minor of the current device, or <0; 100 expected */
@@ -153,6 +153,12 @@ STCAT_API int stcat_attention_bwd(const void* q1, const void* q2, int64_t ldq, c
  * Kernel selection: the single-query and tcgen05 kernels apply the same mask for their shape classes, everything else runs
  * the generic SIMT kernels (the short-sequence kernels have no dropout yet). */
 STCAT_API int stcat_dropout(const void* x, void* out, int dtype, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+/* Optional device-resident step counter (one uint64 in device memory, NULL = off, the default) that every dropout site --
+ * stcat_dropout and the attention dropout entry points -- mixes into its seed when the kernel RUNS (not when it is
+ * launched): seed' = seed + *counter * 0xD1B54A32D192ED03.  A training step captured into a CUDA graph increments the
+ * counter once after its backward pass, so every replay draws fresh masks while forward and backward of one step still
+ * agree.  Process-global; set it before capturing. */
+STCAT_API int stcat_set_dropout_step(const void* counter);
 STCAT_API int stcat_attention_dropout_fwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2, int64_t ldk,
                                 const void* v, int64_t ldv, void* o, int64_t ldo, int dtype, const uint8_t* key_mask,
                                 float* lse, float* p_avg, int B, int H, int Lq, int Lk, int dh, float scale, float drop_p,

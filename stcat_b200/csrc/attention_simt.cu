@@ -36,7 +36,8 @@ __global__ void __launch_bounds__(WARPS * 32)
 attn_fwd_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t ldq, const T* __restrict__ k1,
                 const T* __restrict__ k2, int64_t ldk, const T* __restrict__ v, int64_t ldv, T* __restrict__ o,
                 int64_t ldo, const uint8_t* __restrict__ key_mask, float* __restrict__ lse, float* __restrict__ p_avg,
-                int H, int Lq, int Lk, float scale, const DropArgs drop) {
+                int H, int Lq, int Lk, float scale, const DropArgs drop_in) {
+    const DropArgs drop = drop_resolve(drop_in);
     __shared__ float Ks1[CH][DH + 1];
     __shared__ float Ks2[TWO ? CH : 1][DH + 1];
     __shared__ float Vs[CH][DH + 1];
@@ -150,7 +151,8 @@ attn_bwd_dq_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t l
                    const T* __restrict__ d_o, int64_t lddo, const uint8_t* __restrict__ key_mask,
                    const float* __restrict__ lse, const float* __restrict__ dp_avg, float* __restrict__ delta,
                    T* __restrict__ dq1, T* __restrict__ dq2, int64_t lddq, int H, int Lq, int Lk, float scale,
-                   const DropArgs drop) {
+                   const DropArgs drop_in) {
+    const DropArgs drop = drop_resolve(drop_in);
     __shared__ float Ks1[CH][DH + 1];
     __shared__ float Ks2[TWO ? CH : 1][DH + 1];
     __shared__ float Vs[CH][DH + 1];
@@ -266,7 +268,8 @@ attn_bwd_dkv_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t 
                     const T* __restrict__ d_o, int64_t lddo, const uint8_t* __restrict__ key_mask,
                     const float* __restrict__ lse, const float* __restrict__ dp_avg, const float* __restrict__ delta,
                     T* __restrict__ dk1, T* __restrict__ dk2, int64_t lddk, T* __restrict__ dv, int64_t lddv, int H,
-                    int Lq, int Lk, float scale, const DropArgs drop) {
+                    int Lq, int Lk, float scale, const DropArgs drop_in) {
+    const DropArgs drop = drop_resolve(drop_in);
     __shared__ float Qs1[CH][DH + 1];
     __shared__ float Qs2[TWO ? CH : 1][DH + 1];
     __shared__ float dOs[CH][DH + 1];

@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(SQ_THREADS)
 attn_sq_fwd_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t ldq, const T* __restrict__ k1,
                    const T* __restrict__ k2, int64_t ldk, const T* __restrict__ v, int64_t ldv, T* __restrict__ o,
                    int64_t ldo, const uint8_t* __restrict__ key_mask, float* __restrict__ lse, int H, int Lk, float scale,
-                   const DropArgs drop) {
+                   const DropArgs drop_in) {
+    const DropArgs drop = drop_resolve(drop_in);
     extern __shared__ float sm[];  // scores / probabilities [Lk]
     pdl_launch_dependents();
     pdl_wait();
@@ -142,7 +143,8 @@ attn_sq_bwd_kernel(const T* __restrict__ q1, const T* __restrict__ q2, int64_t l
                    int64_t lddo, const uint8_t* __restrict__ key_mask, const float* __restrict__ lse,
                    float* __restrict__ delta_out, T* __restrict__ dq1, T* __restrict__ dq2, int64_t lddq,
                    T* __restrict__ dk1, T* __restrict__ dk2, int64_t lddk, T* __restrict__ dv, int64_t lddv, int H, int Lk,
-                   float scale, const DropArgs drop) {
+                   float scale, const DropArgs drop_in) {
+    const DropArgs drop = drop_resolve(drop_in);
     extern __shared__ float sm[];  // p [Lk], dp [Lk]
     pdl_launch_dependents();
     pdl_wait();

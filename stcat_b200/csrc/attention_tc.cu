@@ -131,6 +131,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     pdl_launch_dependents();
     pdl_wait();
+    const DropArgs dr = DROP ? drop_resolve(p.drop) : p.drop;
 
     auto decode = [&](int i, int& b, int& h, int& qt) {
         const int w = blockIdx.x + i * gridDim.x;
@@ -399,10 +400,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     }
                     s0 += p0; s1 += p1; s2 += p2; s3 += p3;
                     if (DROP) {
-                        p0 *= drop_mult(p.drop, drow + col + e);
-                        p1 *= drop_mult(p.drop, drow + col + e + 1);
-                        p2 *= drop_mult(p.drop, drow + col + e + 2);
-                        p3 *= drop_mult(p.drop, drow + col + e + 3);
+                        p0 *= drop_mult(dr, drow + col + e);
+                        p1 *= drop_mult(dr, drow + col + e + 1);
+                        p2 *= drop_mult(dr, drow + col + e + 2);
+                        p3 *= drop_mult(dr, drow + col + e + 3);
                     }
                     __nv_bfloat162 b01 = __floats2bfloat162_rn(p0, p1), b23 = __floats2bfloat162_rn(p2, p3);
                     pk[e >> 1] = *reinterpret_cast<uint32_t*>(&b01);
@@ -569,6 +570,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     pdl_launch_dependents();
     pdl_wait();
+    const DropArgs dr = DROP ? drop_resolve(p.drop) : p.drop;
     // diagnostics: event ev of block blk (CTA 0, its first 16 blocks) -> trace[blk * 8 + ev]
     auto T = [&](uint32_t blk, int ev) {
         if (TRACE && p.trace != nullptr && blockIdx.x == 0 && blk < 16) p.trace[blk * 8 + ev] = clock64();
@@ -806,8 +808,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     for (int e = 0; e < 32; e += 2) {
                         const float p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), sc, -lse_eff));
                         const float p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), sc, -lse_eff));
-                        const float m0 = DROP ? drop_mult(p.drop, dcol + e) : 1.f;
-                        const float m1 = DROP ? drop_mult(p.drop, dcol + e + 1) : 1.f;
+                        const float m0 = DROP ? drop_mult(dr, dcol + e) : 1.f;
+                        const float m1 = DROP ? drop_mult(dr, dcol + e + 1) : 1.f;
                         const float d0 = dead ? 0.f : p0 * (__uint_as_float(rd[e]) * m0 - delta) * dsc;
                         const float d1 = dead ? 0.f : p1 * (__uint_as_float(rd[e + 1]) * m1 - delta) * dsc;
                         __nv_bfloat162 bp = __floats2bfloat162_rn(p0 * m0, p1 * m1), bd = __floats2bfloat162_rn(d0, d1);
@@ -820,13 +822,13 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     for (int e = 0; e < 32; e += 2) {
                         float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
                         if (!((wmask >> e) & 1u)) {
-                            const float m0 = DROP ? drop_mult(p.drop, dcol + e) : 1.f;
+                            const float m0 = DROP ? drop_mult(dr, dcol + e) : 1.f;
                             p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), sc, -l2));
                             d0 = p0 * (__uint_as_float(rd[e]) * m0 - delta) * p.scale;
                             p0 *= m0;
                         }
                         if (!((wmask >> (e + 1)) & 1u)) {
-                            const float m1 = DROP ? drop_mult(p.drop, dcol + e + 1) : 1.f;
+                            const float m1 = DROP ? drop_mult(dr, dcol + e + 1) : 1.f;
                             p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), sc, -l2));
                             d1 = p1 * (__uint_as_float(rd[e + 1]) * m1 - delta) * p.scale;
                             p1 *= m1;

@@ -47,6 +47,16 @@ int colsum_group(const void* const* dy, const int64_t* ld, float* const* db, con
 
 using namespace stcat;
 
+namespace stcat {
+static const uint64_t* g_dropout_step = nullptr;
+const uint64_t* dropout_step_ptr() { return g_dropout_step; }
+void set_dropout_step_ptr(const uint64_t* p) { g_dropout_step = p; }
+}  // namespace stcat
+
+extern "C" int stcat_set_dropout_step(const void* counter) {
+    stcat::set_dropout_step_ptr((const uint64_t*)counter);
+    return 0;
+}
 extern "C" int stcat_abi_version(void) { return STCAT_ABI_VERSION; }
 extern "C" const char* stcat_last_error(void) { return err_buf(); }
 

@@ -98,7 +98,13 @@ struct DropArgs {            // thresh == 0: no dropout
     uint32_t thresh = 0;
     float scale = 1.f;       // 1 / keep probability
     uint64_t seed = 0, offset = 0;
+    const uint64_t* step = nullptr;  // optional device-resident step counter (stcat_set_dropout_step): see drop_resolve
 };
+// Host state: the device counter every dropout site mixes into its seed.  With it, a CUDA-graph replay of a captured
+// training step draws fresh masks (the captured step increments the counter once, after its backward pass); without it
+// (NULL, the default) masks are a pure function of the (seed, offset) arguments.
+const uint64_t* dropout_step_ptr();
+void set_dropout_step_ptr(const uint64_t* p);
 inline DropArgs make_drop(float p, uint64_t seed, uint64_t offset) {
     DropArgs d;
     if (p > 0.f) {
@@ -107,9 +113,17 @@ inline DropArgs make_drop(float p, uint64_t seed, uint64_t offset) {
         d.scale = (float)(16777216.0 / (16777216.0 - (double)d.thresh));
         d.seed = seed;
         d.offset = offset;
+        d.step = dropout_step_ptr();
     }
     return d;
 }
+#ifdef __CUDACC__
+// First statement of every kernel that draws masks: fold the current value of the step counter into the seed.
+__device__ __forceinline__ DropArgs drop_resolve(DropArgs d) {
+    if (d.thresh != 0 && d.step != nullptr) d.seed += __ldg(d.step) * 0xD1B54A32D192ED03ull;
+    return d;
+}
+#endif
 __device__ __forceinline__ float drop_mult(const DropArgs& d, uint64_t idx) {  // the mask as a multiplier: 1/keep or 0
     return drop_bits24(d.seed, d.offset + idx) >= d.thresh ? d.scale : 0.f;
 }

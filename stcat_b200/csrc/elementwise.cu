@@ -286,9 +286,10 @@ __global__ void __launch_bounds__(256) box_refine_bwd_kernel(const float* __rest
 
 // out[i] = keep(i) ? x[i] / (1 - p) : 0  (forward and, with the same seed / offset on dy, backward of a dropout site)
 template <typename T>
-__global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n, const DropArgs d) {
+__global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n, const DropArgs d_in) {
     pdl_launch_dependents();
     pdl_wait();
+    const DropArgs d = drop_resolve(d_in);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = from_f32<T>(drop_apply(d, (uint64_t)i, to_f32<T>(x[i])));
 }
