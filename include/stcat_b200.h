@@ -41,7 +41,7 @@ extern "C" {
 
 /* Bumped whenever a signature or the meaning of an argument changes; stcat_b200/cabi.py refuses a library whose version
  * differs from the one it was written against (a stale locally built .so would otherwise be called with new signatures). */
-#define STCAT_ABI_VERSION 5
+#define STCAT_ABI_VERSION 6
 STCAT_API int stcat_abi_version(void);
 STCAT_API const char* stcat_last_error(void);
 /* compute capability major*10+minor of the current device, or <0; 100 expected */
@@ -97,6 +97,10 @@ typedef struct stcat_linear_job {
     int64_t ldo;
     float* dbias;      /* kind 2 only; ACCUMULATED; may be NULL */
 } stcat_linear_job;
+/* Upper bound on the CTAs (= SMs, the kernel is persistent) of the tcgen05 GEMM launches that follow; 0 = all SMs (default).
+ * Host-side launch state, read when a GEMM is launched (a captured launch keeps its grid).  Used for GEMMs that run on a side
+ * stream next to a latency-bound chain of small kernels (the decoder's memory-side projections). */
+STCAT_API int stcat_set_gemm_sm_limit(int n);
 STCAT_API int stcat_linear_group(int kind, int in_dtype, const stcat_linear_job* jobs, int njobs, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

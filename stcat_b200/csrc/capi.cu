@@ -53,6 +53,11 @@ const uint64_t* dropout_step_ptr() { return g_dropout_step; }
 void set_dropout_step_ptr(const uint64_t* p) { g_dropout_step = p; }
 }  // namespace stcat
 
+namespace stcat { void gemm_tc_set_sm_limit(int n); }
+extern "C" int stcat_set_gemm_sm_limit(int n) {
+    stcat::gemm_tc_set_sm_limit(n);
+    return 0;
+}
 extern "C" int stcat_set_dropout_step(const void* counter) {
     stcat::set_dropout_step_ptr((const uint64_t*)counter);
     return 0;

@@ -462,15 +462,26 @@ struct TcJob {
     GemmEpilogue epi;
 };
 
+// Upper bound on the CTAs of the following tcgen05 GEMM launches (0 = all SMs).  The decoder's memory-side key / value
+// projections run on a side stream next to the latency-bound query chains: a persistent GEMM on every SM leaves no SM for
+// the chains' small kernels (its CTAs hold all registers / shared memory of their SM), so those launches are capped.
+static int g_gemm_sm_limit = 0;
+void gemm_tc_set_sm_limit(int n) { g_gemm_sm_limit = n > 0 ? n : 0; }
+
 static long long* g_gemm_trace = nullptr;
 void gemm_tc_set_trace(long long* buf) { g_gemm_trace = buf; }
 
 template <bool AMN, bool BMN, bool OBF, int BN, int NJ>
-static int launch_tc(const tc::GroupParams<NJ>& gp, int grid, cudaStream_t st) {
+static int launch_tc(const tc::GroupParams<NJ>& gp, int grid, cudaStream_t st, bool short_k) {
     using namespace tc;
-    if constexpr (BN == 256 && NJ == 1) {
-        static const bool epi2 = getenv("STCAT_GEMM_EPI2") != nullptr;  // staged variant (two staging tiles per group), opt-in
-        if constexpr (!AMN && !BMN) {  // diagnostics: traced instantiations of the plain forward GEMM
+    if constexpr (BN == 256) {
+        // two staging tiles per epilogue group (EPI2, 3 operand stages instead of 4): the store drain of chunk c overlaps the
+        // conversion of chunk c+1.  Measured (profiles/r2_a_validate_staged.log): faster where the K loop is short (K = 256:
+        // FFN linear1 23.2 -> 19.9 us, its dgrad twin 22.5 -> 20.2, in/out projections -8..-14 %), slower by 3 % where the
+        // K loop is long (K = 2048) and the fourth operand stage matters more.  STCAT_GEMM_EPI2=0 / 1 forces it off / on.
+        static const char* epi2_env = getenv("STCAT_GEMM_EPI2");
+        const bool epi2 = epi2_env ? atoi(epi2_env) != 0 : short_k;
+        if constexpr (!AMN && !BMN && NJ == 1) {  // diagnostics: traced instantiations of the plain forward GEMM
             if (g_gemm_trace != nullptr) {
                 GroupParams<NJ> gt = gp;
                 gt.trace = g_gemm_trace;
@@ -580,14 +591,21 @@ static int gemm_tc_launch_jobs(const TcJob* jobs, int njobs, int a_mn_major, int
     gp.njobs = njobs;
     gp.total = work;
     gp.trace = nullptr;
-    const int sms = num_sms();
+    const int sms = (g_gemm_sm_limit > 0 && g_gemm_sm_limit < num_sms()) ? g_gemm_sm_limit : num_sms();
     const int grid = work < sms ? work : sms;
+    int kmax = 0;  // longest K loop of the launch
+    for (int j = 0; j < njobs; ++j) {
+        int k = 0;
+        for (int t = 0; t < jobs[j].nterms; ++t) k += jobs[j].term[t].K;
+        kmax = k > kmax ? k : kmax;
+    }
+    const bool short_k = kmax <= 512;
     if (!a_mn_major && !b_mn_major)
-        return out_bf16 ? launch_tc<false, false, true, BN, NJ>(gp, grid, st) : launch_tc<false, false, false, BN, NJ>(gp, grid, st);
+        return out_bf16 ? launch_tc<false, false, true, BN, NJ>(gp, grid, st, short_k) : launch_tc<false, false, false, BN, NJ>(gp, grid, st, short_k);
     if (!a_mn_major && b_mn_major)
-        return out_bf16 ? launch_tc<false, true, true, BN, NJ>(gp, grid, st) : launch_tc<false, true, false, BN, NJ>(gp, grid, st);
+        return out_bf16 ? launch_tc<false, true, true, BN, NJ>(gp, grid, st, short_k) : launch_tc<false, true, false, BN, NJ>(gp, grid, st, short_k);
     if (a_mn_major && b_mn_major)
-        return out_bf16 ? launch_tc<true, true, true, BN, NJ>(gp, grid, st) : launch_tc<true, true, false, BN, NJ>(gp, grid, st);
+        return out_bf16 ? launch_tc<true, true, true, BN, NJ>(gp, grid, st, short_k) : launch_tc<true, true, false, BN, NJ>(gp, grid, st, short_k);
     return set_err(STCAT_ESHAPE, "gemm_tc: A MN-major with B K-major is not instantiated");
 }
 

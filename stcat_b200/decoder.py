@@ -18,6 +18,8 @@ from __future__ import annotations
 import math
 from typing import Optional
 
+import os
+
 import torch
 from torch import nn
 
@@ -34,6 +36,9 @@ def set_multi_stream(on: bool):
     """Run the decoder's three independent branches on side streams (default on)."""
     global _MULTI_STREAM
     _MULTI_STREAM = bool(on)
+
+
+_MEMSIDE_SMS = int(os.environ.get("STCAT_MEMSIDE_SMS", "112"))
 
 
 def _side_streams(device):
@@ -493,11 +498,14 @@ class QueryDecoder(nn.Module):
             c = _Ctx(idx, mem, mem_pos, key_mask, M)
             ctx_ready = sM.record_event()
             box_kv, time_kv, ev_box, ev_time = [], [], [], []
-            for i in range(nl):
-                box_kv.append(self.decoder.layers[i].memory_side(c, i == 0))
-                ev_box.append(sM.record_event())
-                time_kv.append(self.temp_decoder.layers[i].memory_side(c))
-                ev_time.append(sM.record_event())
+            # these persistent GEMMs (and their backward) share the machine with the two query chains: keep some SMs free for
+            # the chains' small kernels (ops.sm_limit; STCAT_MEMSIDE_SMS overrides, 0 = no cap)
+            with ops.sm_limit(_MEMSIDE_SMS):
+                for i in range(nl):
+                    box_kv.append(self.decoder.layers[i].memory_side(c, i == 0))
+                    ev_box.append(sM.record_event())
+                    time_kv.append(self.temp_decoder.layers[i].memory_side(c))
+                    ev_time.append(sM.record_event())
 
         def waiter(stream, evs, vals):
             def mk(i):

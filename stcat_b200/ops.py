@@ -206,6 +206,39 @@ def dropout(x, p: float):
     return x if not p else DropoutFn.apply(x, float(p))
 
 
+# SM cap for the GEMMs of ops issued inside ``with sm_limit(n):`` -- and of their backward nodes, whenever autograd runs them
+# (the cap is recorded on the node).  See include/stcat_b200.h stcat_set_gemm_sm_limit.
+_sm_limit = 0
+
+
+class sm_limit:
+    def __init__(self, n: int):
+        self.n = int(n)
+
+    def __enter__(self):
+        global _sm_limit
+        self.prev, _sm_limit = _sm_limit, self.n
+
+    def __exit__(self, *exc):
+        global _sm_limit
+        _sm_limit = self.prev
+
+
+class _capped:
+    """applies a node's SM cap to the backend for the launches inside"""
+
+    def __init__(self, be, n):
+        self.be, self.n = be, n
+
+    def __enter__(self):
+        if self.n:
+            self.be.set_gemm_sm_limit(self.n)
+
+    def __exit__(self, *exc):
+        if self.n:
+            self.be.set_gemm_sm_limit(0)
+
+
 class LinearFn(Function):
     """y = act(x W[r0:r1]^T + b[r0:r1])  (r0/r1 = None: the whole parameter).  The row range lets the packed
     ``in_proj_weight`` of an MHA be used slice by slice without autograd slicing nodes."""
@@ -226,7 +259,9 @@ class LinearFn(Function):
         M = x2.shape[0]
         odt = torch.bfloat16 if (out_bf16 and _precision == "bf16") else torch.float32
         y = torch.empty(M, N, dtype=odt, device=x.device)
-        be.linear_fwd(xo, wo, bd, y, relu=relu)
+        ctx.sm_limit = _sm_limit
+        with _capped(be, ctx.sm_limit):
+            be.linear_fwd(xo, wo, bd, y, relu=relu)
         ctx.relu = relu
         ctx.x_shape = x.shape
         ctx.x_dtype = x.dtype
@@ -249,11 +284,12 @@ class LinearFn(Function):
         dyo = _operand(dy2)
         M = dy2.shape[0]
         dx = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty(M, K, dtype=ctx.x_dtype, device=dy.device)
-            be.linear_bwd_data(dyo, _operand(wd, True), dx)
-            dx = dx.view(ctx.x_shape)
-        dw, db = _wgrad(be, dyo, xo, weight, bias, ctx.needs_input_grad[1], ctx.needs_input_grad[2], r0, r1)
+        with _capped(be, ctx.sm_limit):
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty(M, K, dtype=ctx.x_dtype, device=dy.device)
+                be.linear_bwd_data(dyo, _operand(wd, True), dx)
+                dx = dx.view(ctx.x_shape)
+            dw, db = _wgrad(be, dyo, xo, weight, bias, ctx.needs_input_grad[1], ctx.needs_input_grad[2], r0, r1)
         return dx, dw, db, None, None, None, None, None
 
 
@@ -291,13 +327,15 @@ class LinearSumFn(Function):
         odt = torch.bfloat16 if (out_bf16 and _precision == "bf16") else torch.float32
         y = None
         saved = []
+        ctx.sm_limit = _sm_limit
         for i, (x, w, b) in enumerate(zip(xs, ws, bs)):
             K = w.shape[1]
             x2 = _rows(x.detach(), K)
             xo = _rows(x_ops[i].detach(), K) if (x_ops[i] is not None and _precision == "bf16") else _operand(x2)
             if y is None:
                 y = torch.empty(x2.shape[0], N, dtype=odt, device=x.device)
-            be.linear_fwd(xo, _operand(w.detach(), True), None if b is None else b.detach(), y, accumulate=i > 0)
+            with _capped(be, ctx.sm_limit):
+                be.linear_fwd(xo, _operand(w.detach(), True), None if b is None else b.detach(), y, accumulate=i > 0)
             saved += [xo, w]
         ctx.nterms = nterms
         ctx.biases = bs
@@ -317,6 +355,8 @@ class LinearSumFn(Function):
         dxs, dws, dbs = [], [], []
         db_shared = None
         biases = ctx.biases
+        if ctx.sm_limit:
+            be.set_gemm_sm_limit(ctx.sm_limit)
         for i in range(n):
             xo, w = saved[2 * i], saved[2 * i + 1]
             xshape, xdtype, has_b = ctx.meta[i]
@@ -343,6 +383,8 @@ class LinearSumFn(Function):
             dxs.append(dx)
             dws.append(dw)
             dbs.append(db)
+        if ctx.sm_limit:
+            be.set_gemm_sm_limit(0)
         return (None, None, *dxs, *dws, *dbs, *([None] * n))
 
 

@@ -378,6 +378,12 @@ class EmuBackend:
             best[v] = int(sc.flatten().argmax())
         self.launches += 1
 
+    def set_gemm_sm_limit(self, n):
+        pass
+
+    def set_dropout_step(self, counter):
+        pass
+
     def pos_sine(self, mask, out, num_pos_feats, temperature, scale):
         import math
 
