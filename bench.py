@@ -133,7 +133,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.01)
 
     def start(self):
         if self.nv is not None:
@@ -436,7 +436,9 @@ def dominant_kernel_roofline(ctx, device, peaks):
         except Exception:
             traffic = None
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": traffic, "kernel": "stcat_linear_fwd (FFN linear1 + bias + ReLU)",
+            "traffic": traffic, "traffic_source": "ncu --set full capture of this kernel at this shape, committed as "
+            "profiles/dominant_kernel_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch; not re-measured in this run)",
+            "kernel": "stcat_linear_fwd (FFN linear1 + bias + ReLU)",
             "shape": {"M": M, "N": N, "K": K, "dtype": "bf16" if bf else "f32"}, "us_per_launch": ms * 1e3,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, kernel timed alone)" if "bf16_tflops" in peaks
             else "fallback 1590 (B200_PROFILING.md)"}
@@ -605,6 +607,21 @@ def run_b200_arm(args):
         fl = flops_forward(w)
         breakdown = kernel_breakdown(ctx, device)
         roof = dominant_kernel_roofline(ctx, device, peaks)
+        gemm_family = None
+        if args.precision == "bf16":
+            try:  # time-weighted GEMM efficiency over the shapes of one spatial encoder layer (fwd + dgrad + wgrad)
+                sys.path.insert(0, os.path.join(ROOT, "scripts"))
+                import bench_gemm
+
+                rows = bench_gemm.time_shapes(bench_gemm.ENCODER_LAYER_FAMILY, 10, True, ns=w["T"] * (1 + w["H"] * w["W"] + w["L"]))
+                us, fl = sum(r["us"] for r in rows), sum(r["flops"] for r in rows)
+                pk = peaks.get("bf16_tflops", 1590.0)
+                gemm_family = {"what": "the 13 GEMMs of one spatial encoder layer, forward + data gradients + weight gradients, each "
+                                       "timed alone (CUDA-graph replay, rotating operands > L2)",
+                               "gflop": fl / 1e9, "us": us, "tflops": fl / us / 1e6, "frac_of_bf16_peak": fl / us / 1e6 / pk,
+                               "per_gemm_us": {r["name"]: round(r["us"], 2) for r in rows}}
+            except Exception as e:
+                gemm_family = {"error": f"{type(e).__name__}: {e}"}
         try:
             enc_attn = encoder_attention_block(ctx, device, peaks) if args.precision == "bf16" else None
         except Exception as e:  # a diagnostic, never fatal for the bench line
@@ -630,6 +647,7 @@ def run_b200_arm(args):
                                   + ("the copy of step k+1 overlaps step k on a copy stream (double-buffered staging)"
                                      if args.e2e_prefetch else "on the compute stream, not overlapped")},
             "gpu_launches": int(launches_per_step or 0) * args.steps,
+            "gemm_family": gemm_family,
             "clocks": sampler.summary(),
             "roofline": roof,
             "step_flops": {"forward": fl["total"], "fwd_bwd": 3 * fl["total"],

@@ -46,20 +46,20 @@ SHAPES = [
 ]
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default=None)
-    ap.add_argument("--iters", type=int, default=20)
-    ap.add_argument("--no-graph", action="store_true")
-    args = ap.parse_args()
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
+def time_shapes(names=None, iters=20, graph=True, ns=None, mm=None):
+    """Device time of the listed rows (all when None).  ``ns`` / ``mm`` rescale the token counts (other clip shapes).
+    Returns [{name, kind, M, N, K, out, us, tflops, gbs}]."""
+    dev = torch.device("cuda", torch.cuda.current_device())
     be = ops.get_backend()
     bf = torch.bfloat16
-    print(f"{'name':18s} {'kind':6s} {'M':>6s} {'N':>5s} {'K':>5s} {'out':>4s} {'us':>8s} {'TFLOP/s':>8s} {'GB/s(alg)':>9s}")
+    rows = []
     for name, kind, M, N, K, out, relu in SHAPES:
-        if args.only and name != args.only:
+        if names is not None and name not in names:
             continue
+        if ns is not None and M == NS:
+            M = ns
+        if mm is not None and M == MM:
+            M = mm
         odt = bf if out == "bf16" else torch.float32
         nbuf = 4 if M > 1000 else 2
         if kind == "fwd":
@@ -86,9 +86,9 @@ def main():
             fn(i)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if args.no_graph:
+        if not graph:
             e0.record()
-            for i in range(args.iters):
+            for i in range(iters):
                 fn(i)
             e1.record()
         else:  # replay from a CUDA graph: device time, not the host's launch rate (tensor-map encode + ctypes)
@@ -96,7 +96,7 @@ def main():
             side.wait_stream(torch.cuda.current_stream())
             gr = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gr, stream=side):
-                for i in range(args.iters):
+                for i in range(iters):
                     fn(i)
             gr.replay()
             torch.cuda.synchronize()
@@ -104,9 +104,33 @@ def main():
             gr.replay()
             e1.record()
         torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) / args.iters * 1e3
+        us = e0.elapsed_time(e1) / iters * 1e3
         fl = 2.0 * M * N * K
-        print(f"{name:18s} {kind:6s} {M:6d} {N:5d} {K:5d} {out:>4s} {us:8.1f} {fl / us / 1e6:8.1f} {nbytes / us / 1e3:9.1f}", flush=True)
+        rows.append({"name": name, "kind": kind, "M": M, "N": N, "K": K, "out": out, "us": us, "tflops": fl / us / 1e6,
+                     "gbs": nbytes / us / 1e3, "flops": fl})
+    return rows
+
+
+# the GEMMs of one spatial encoder layer, forward + backward, as the step issues them (weight gradients without the fused
+# bias column sum: the bias gradients come from the LayerNorm backward / the dgrad epilogue)
+ENCODER_LAYER_FAMILY = ["qk_fwd", "v_fwd", "out_fwd", "ffn1_fwd", "ffn2_fwd", "ffn2_dgrad", "ffn1_dgrad", "out_dgrad", "qk_dgrad",
+                        "ffn1_wgrad_nob", "ffn2_wgrad_nob", "out_wgrad_nob", "qk_wgrad"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    torch.cuda.set_device(0)
+    print(f"{'name':18s} {'kind':6s} {'M':>6s} {'N':>5s} {'K':>5s} {'out':>4s} {'us':>8s} {'TFLOP/s':>8s} {'GB/s(alg)':>9s}")
+    for r in time_shapes([args.only] if args.only else None, args.iters, not args.no_graph):
+        print(f"{r['name']:18s} {r['kind']:6s} {r['M']:6d} {r['N']:5d} {r['K']:5d} {r['out']:>4s} {r['us']:8.1f} {r['tflops']:8.1f} {r['gbs']:9.1f}", flush=True)
+    fam = time_shapes(ENCODER_LAYER_FAMILY, args.iters, not args.no_graph) if not args.only else []
+    if fam:
+        us, fl = sum(r["us"] for r in fam), sum(r["flops"] for r in fam)
+        print(f"encoder layer family (fwd + dgrad + wgrad, {len(fam)} GEMMs): {fl / 1e9:.1f} GFLOP in {us:.1f} us = {fl / us / 1e6:.1f} TFLOP/s")
 
 
 if __name__ == "__main__":
