@@ -472,7 +472,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 //   MMA     dV_kt += P^T dO_qt, dK_kt += dS^T Q_qt   (the P / dS tiles read as MN-major A operands: no transpose)
 //           dQ_qt += dS K_kt                           (the dS tile read as K-major A operand)
 // dK, dV (per key tile) and dQ (per item, all query tiles) accumulate in TMEM and are written as bf16 straight to global.
-// TMEM columns: S 0..127 | dP 128..255 | dK 256..287 | dV 288..319 | dQ 320 + 32 qt (up to 4 query tiles).
+// TMEM columns: S 0..127 | dP 128..255 | dK 256 + 32 buf | dV 320 + 32 buf | dQ 384 + 32 slot (all 512 columns).
 // Pipeline: the threads copy a block's S / dP into registers and release the columns at once, so the score MMAs of block
 // n+1 are issued before the gradient MMAs of block n and run under the threads' exp / pack work; the threads wait for the
 // gradient MMAs of block n-1 only just before they overwrite the P / dS tiles with block n.
@@ -483,7 +483,10 @@ constexpr int AB_TILE_BYTES = 128 * 128 * 2;               // P or dS tile: 32 K
 constexpr int AB_PRO_BYTES = 2 * (2 * 512 * 4 + 64);       // per item buffer: lse2[512], delta[512] floats + 16 key-mask words
 constexpr int AB_SMEM = 2 * AB_LOAD_BYTES + 2 * AB_TILE_BYTES + 1024 + 256 + AB_PRO_BYTES;
 constexpr int AB_THREADS = 384;
-constexpr uint32_t AB_COL_S = 0, AB_COL_DP = 128, AB_COL_DK = 256, AB_COL_DV = 288, AB_COL_DQ = 320;
+// S | dP | dK x 2 | dV x 2 | dQ: 4 tiles (BIG: one item's query tiles; else 2 tiles x 2 items).  dK / dV alternate between two
+// buffers per key tile and dQ (S <= 256) between two per item, so the first gradient MMAs of a key tile / an item never wait
+// for the read-out of the previous one.
+constexpr uint32_t AB_COL_S = 0, AB_COL_DP = 128, AB_COL_DK = 256, AB_COL_DV = 320, AB_COL_DQ = 384;
 
 struct AttnBwdParams {
     const __nv_bfloat16* o;    // forward output [B*S, ldo]
@@ -528,9 +531,17 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t sDS = sP + AB_TILE_BYTES;
     const uint32_t bar_base = sDS + AB_TILE_BYTES;
     // 0,1 load_full[set]; 2,3 load_free[set]; 4 sd_full; 5 sd_free; 6 pds_full; 7 pds_free; 8 dq_full; 9 dq_free;
-    // 10 dkv_full; 11 dkv_free; 12,13 pro_full[buf]; 14,15 pro_free[buf]
+    // 10 dkv_full; 11 dkv_free; 12,13 pro_full[buf]; 14,15 pro_free[buf]; 16..19: second dq_full, dq_free, dkv_full, dkv_free
     auto bar = [&](int which) { return bar_base + 8u * which; };
-    const uint32_t tmem_slot = bar_base + 8u * 16;
+    // accumulator buffers: dK / dV of key-tile sequence number j live in buffer j & 1; dQ of item `it` in buffer it & 1 (one
+    // buffer in BIG).  Each buffer has its own full / free barrier pair, used every other time.
+    constexpr int NDQ = BIG ? 1 : 2;
+    auto dq_full = [&](int buf) { return bar(buf ? 16 : 8); };
+    auto dq_free = [&](int buf) { return bar(buf ? 17 : 9); };
+    auto dkv_full = [&](int buf) { return bar(buf ? 18 : 10); };
+    auto dkv_free = [&](int buf) { return bar(buf ? 19 : 11); };
+    auto col_dq = [&](int it, int qt) { return AB_COL_DQ + (uint32_t)((BIG ? 0 : (it & 1) * 2) + qt) * 32u; };
+    const uint32_t tmem_slot = bar_base + 8u * 20;
     // per-item row statistics prepared by warps 2, 3 one item ahead (buffer = item & 1): lse * log2e and delta = dO . O of
     // every query row, and the key mask as 32-key words
     const uint32_t pro_base = bar_base + 256;
@@ -557,6 +568,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_init(bar(4), 1); mbar_init(bar(5), 256); mbar_init(bar(6), 256); mbar_init(bar(7), 1);
         mbar_init(bar(8), 1); mbar_init(bar(9), 256); mbar_init(bar(10), 1); mbar_init(bar(11), 256);
         mbar_init(bar(12), 64); mbar_init(bar(13), 64); mbar_init(bar(14), 256); mbar_init(bar(15), 256);
+        mbar_init(bar(16), 1); mbar_init(bar(17), 256); mbar_init(bar(18), 1); mbar_init(bar(19), 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -632,8 +644,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 const int nk16 = min(8, (S - kt * 128 + 15) >> 4);
                 mbar_wait(bar(6), g & 1);
                 T(g, 1);  // P / dS tiles written
-                if (r == 0) mbar_wait(bar(9), (it & 1) ^ 1);                      // dQ columns read out (previous item)
-                if (qt == 0) mbar_wait(bar(11), ((it * nt + kt) & 1) ^ 1);        // dK / dV columns read out (previous key tile)
+                const int jkv = it * nt + kt;   // key-tile sequence number of this CTA
+                if (r == 0) {                   // dQ buffer read out by the item that used it last (it - NDQ)
+                    const int u = it / NDQ;
+                    mbar_wait(dq_free(it % NDQ), (u & 1) ^ 1);
+                }
+                if (qt == 0) mbar_wait(dkv_free(jkv & 1), ((jkv >> 1) & 1) ^ 1);  // dK / dV buffer read out (key tile jkv - 2)
                 T(g, 2);  // accumulators free: gradient MMAs issued
                 tc_fence_after();
                 // descriptors differ per step only in the start-address field (bits 0..13, units of 16 bytes)
@@ -644,17 +660,17 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 const uint64_t ak0 = make_desc(sDS, 16, 1024, LAYOUT_SW128);
 #pragma unroll 4
                 for (int t = 0; t < nq16; ++t) {  // contraction over the queries of this tile
-                    umma_bf16(tmem_base + AB_COL_DV, ap0 + (uint64_t)(t * 128), bd0 + (uint64_t)(t * 64), idesc_t, (qt > 0 || t > 0) ? 1u : 0u);
-                    umma_bf16(tmem_base + AB_COL_DK, as0 + (uint64_t)(t * 128), bq0 + (uint64_t)(t * 64), idesc_t, (qt > 0 || t > 0) ? 1u : 0u);
+                    umma_bf16(tmem_base + AB_COL_DV + (jkv & 1) * 32, ap0 + (uint64_t)(t * 128), bd0 + (uint64_t)(t * 64), idesc_t, (qt > 0 || t > 0) ? 1u : 0u);
+                    umma_bf16(tmem_base + AB_COL_DK + (jkv & 1) * 32, as0 + (uint64_t)(t * 128), bq0 + (uint64_t)(t * 64), idesc_t, (qt > 0 || t > 0) ? 1u : 0u);
                 }
 #pragma unroll 4
                 for (int t = 0; t < nk16; ++t) {  // contraction over the keys of this tile
-                    umma_bf16(tmem_base + AB_COL_DQ + qt * 32, ak0 + (uint64_t)((t >> 2) * 1024 + (t & 3) * 2), bk0 + (uint64_t)(t * 64), idesc_q,
+                    umma_bf16(tmem_base + col_dq(it, qt), ak0 + (uint64_t)((t >> 2) * 1024 + (t & 3) * 2), bk0 + (uint64_t)(t * 64), idesc_q,
                               (kt > 0 || t > 0) ? 1u : 0u);
                 }
                 umma_commit(bar(7));
-                if (qt == nt - 1) umma_commit(bar(10));
-                if (r == nblk - 1) { umma_commit(bar(8)); umma_commit(bar(2 + set)); }
+                if (qt == nt - 1) umma_commit(dkv_full(jkv & 1));
+                if (r == nblk - 1) { umma_commit(dq_full(it % NDQ)); umma_commit(bar(2 + set)); }
             };
             for (int s = 0; s <= nsteps; ++s) {
                 const bool late = BIG && s > 0 && (s % nblk) == 0;
@@ -718,13 +734,13 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         auto dkv_out = [&](int it, int kt) {  // dK (wg 0) and dV (wg 1) of a key tile: thread row = key
             const int w = blockIdx.x + it * gridDim.x;
             const int h = w % p.H, b = w / p.H;
-            mbar_wait(bar(10), ndkv & 1);
+            mbar_wait(dkv_full(ndkv & 1), (ndkv >> 1) & 1);
             tc_fence_after();
             uint32_t r0[32];
-            tmem_ld32(tmem_base + lane_off + (wg ? AB_COL_DV : AB_COL_DK), r0);
+            tmem_ld32(tmem_base + lane_off + (wg ? AB_COL_DV : AB_COL_DK) + (ndkv & 1) * 32, r0);
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(bar(11));
+            mbar_arrive(dkv_free(ndkv & 1));
             ++ndkv;
             __nv_bfloat16* dst = wg ? p.dv : p.dk;
             const int64_t ldd = wg ? p.lddv : p.lddk;
@@ -734,15 +750,15 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         auto dq_out = [&](int it) {  // dQ of every query tile: wg 0 -> dims 0..15, wg 1 -> dims 16..31
             const int w = blockIdx.x + it * gridDim.x;
             const int h = w % p.H, b = w / p.H;
-            mbar_wait(bar(8), it & 1);
+            mbar_wait(dq_full(it % NDQ), (it / NDQ) & 1);
             tc_fence_after();
             uint32_t r16[NT][16];
 #pragma unroll
             for (int qt = 0; qt < NT; ++qt)
-                if (qt < nt) tmem_ld16(tmem_base + lane_off + AB_COL_DQ + qt * 32 + wg * 16, r16[qt]);
+                if (qt < nt) tmem_ld16(tmem_base + lane_off + col_dq(it, qt) + wg * 16, r16[qt]);
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(bar(9));
+            mbar_arrive(dq_free(it % NDQ));
             mbar_arrive(bar(14 + (it & 1)));  // the item's row statistics are no longer needed
 #pragma unroll
             for (int qt = 0; qt < NT; ++qt) {
