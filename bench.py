@@ -614,11 +614,12 @@ def run_b200_arm(args):
                 import bench_gemm
 
                 rows = bench_gemm.time_shapes(bench_gemm.ENCODER_LAYER_FAMILY, 10, True, ns=w["T"] * (1 + w["H"] * w["W"] + w["L"]))
-                us, fl = sum(r["us"] for r in rows), sum(r["flops"] for r in rows)
-                pk = peaks.get("bf16_tflops", 1590.0)
+                fam_us, fam_fl = sum(r["us"] for r in rows), sum(r["flops"] for r in rows)
+                fam_pk = peaks.get("bf16_tflops", 1590.0)
                 gemm_family = {"what": "the 13 GEMMs of one spatial encoder layer, forward + data gradients + weight gradients, each "
                                        "timed alone (CUDA-graph replay, rotating operands > L2)",
-                               "gflop": fl / 1e9, "us": us, "tflops": fl / us / 1e6, "frac_of_bf16_peak": fl / us / 1e6 / pk,
+                               "gflop": fam_fl / 1e9, "us": fam_us, "tflops": fam_fl / fam_us / 1e6,
+                               "frac_of_bf16_peak": fam_fl / fam_us / 1e6 / fam_pk,
                                "per_gemm_us": {r["name"]: round(r["us"], 2) for r in rows}}
             except Exception as e:
                 gemm_family = {"error": f"{type(e).__name__}: {e}"}
