@@ -268,6 +268,9 @@ def build_b200(args, device):
 
         sync.extra_streams = _side_streams(device)
     ops.set_grad_fusion(True)  # wgrad kernels accumulate straight into the flat buffer (no per-parameter adds)
+    # weight / bias gradients of small-row nodes (decoders, temporal layers) leave the dependent chain for a side stream
+    leaf_rows = int(os.environ.get("STCAT_LEAF_ROWS", "1024"))
+    ops.set_leaf_streams(leaf_rows > 0, leaf_rows)
     # optimizer-side step of the training loop (clips/s is over fwd + bwd + optimizer): the reference's
     # clip_grad_norm_ + AdamW (2 LR groups on the hot path) + EMA, fused (stcat_b200/optim.py), with the bf16 weight
     # shadows refreshed in the same pass
@@ -286,6 +289,7 @@ def build_b200(args, device):
         sync.begin_step()
         sync.attach(out)
         total.backward()
+        ops.join_leaf_streams()
         sync.finish()  # mean over ranks (GradSync averages, like the DDP wrapper it replaces)
         if opt is not None:
             opt.step()
@@ -665,7 +669,8 @@ def run_b200_arm(args):
             try:
                 v, sec = time_cpu(args, args.cpu_steps, 1)
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                        "sample": f"{args.cpu_steps} full-size clips (T={w['T']}, res={w['res']}) fwd+bwd "
+                                        "sample": f"{args.cpu_steps} full-size clips (T={w['T']}, res={w['res']}) fwd+bwd"
+                                                  f"{'' if args.no_optimizer else '+optimizer step'} "
                                                   f"after 1 warm-up, oracle port of the PyTorch reference, fp32"}
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",

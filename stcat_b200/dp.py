@@ -59,6 +59,9 @@ class FlatGrads:
         self.numel = n
 
     def zero(self):
+        from . import ops
+
+        ops.join_leaf_streams()  # leaf-stream weight gradients of the previous step must have landed
         self.buf.zero_()
 
     def all_reduce(self, average: bool = False):
@@ -133,9 +136,11 @@ class GradSync:
             if self.average:
                 chunk.div_(dist.get_world_size())
             return
+        from . import ops
+
         cur = torch.cuda.current_stream()
         self.stream.wait_stream(cur)
-        for st in self.extra_streams:  # gradient kernels of this range may have been enqueued on these too
+        for st in (*self.extra_streams, *ops.leaf_streams()):  # gradient kernels of this range may have been enqueued on these too
             self.stream.wait_stream(st)
         with torch.cuda.stream(self.stream):
             dist.all_reduce(chunk, op=dist.ReduceOp.AVG if self.average else dist.ReduceOp.SUM)
@@ -161,6 +166,9 @@ class GradSync:
             t.register_hook(hook)
 
     def finish(self):
+        from . import ops
+
+        ops.join_leaf_streams()
         for name in list(self.flat.ranges):
             self._reduce(name)
         if self.stream is not None:

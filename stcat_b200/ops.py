@@ -32,6 +32,67 @@ def set_grad_fusion(on: bool):
     _fuse_grads = bool(on)
 
 
+# ---- leaf streams --------------------------------------------------------------------------------------------------------
+# Weight / bias gradients are leaves of the backward pass: nothing downstream waits for them until the gradient exchange /
+# the optimizer.  With ``set_leaf_streams(True)`` (and in-place accumulation into .grad, ``set_grad_fusion``) the wgrad GEMMs
+# and bias column sums of an autograd node are issued on a side stream forked from the node's stream, so the dependent chain
+# of a decoder / temporal layer's backward (data gradients, attention, LayerNorm) no longer queues behind ~270 small leaf
+# kernels per step.  ``join_leaf_streams()`` makes the current stream wait for all of them: ``dp.GradSync`` (before a range is
+# reduced), ``optim.FusedAdamW.step`` and ``dp.FlatGrads.zero`` call it; call it yourself before reading ``.grad`` otherwise.
+_leaf = {"on": False, "streams": {}, "pending": [], "max_rows": 1 << 30}
+
+
+def set_leaf_streams(flag: bool, max_rows: int = 1 << 30):
+    """``max_rows``: only nodes whose operand has at most this many rows are off-loaded."""
+    _leaf["on"] = bool(flag)
+    _leaf["max_rows"] = int(max_rows)
+
+
+def leaf_streams():
+    """leaf streams with work issued since the last join (only these may be waited for: under CUDA-graph capture a stream that
+    was not forked from the capturing stream must not be touched)"""
+    return list(_leaf["pending"])
+
+
+def join_leaf_streams(stream=None):
+    if not _leaf["pending"]:
+        return
+    cur = stream if stream is not None else torch.cuda.current_stream()
+    for st in _leaf["pending"]:
+        cur.wait_stream(st)
+    _leaf["pending"] = []
+
+
+class _on_leaf:
+    """``with _on_leaf(t0, t1, ...):`` -- the launches inside read the given tensors and accumulate into .grad buffers; they
+    run on the leaf stream of the current stream (no-op when leaf streams are off or on the CPU)."""
+
+    def __init__(self, *tensors):
+        self.tensors = [t for t in tensors if t is not None]
+        self.ctx = None
+
+    def __enter__(self):
+        if not _leaf["on"] or not self.tensors or not self.tensors[0].is_cuda or self.tensors[0].shape[0] > _leaf["max_rows"]:
+            return self
+        cur = torch.cuda.current_stream()
+        side = _leaf["streams"].get(cur.cuda_stream)
+        if side is None:
+            side = _leaf["streams"][cur.cuda_stream] = torch.cuda.Stream(self.tensors[0].device)
+        side.wait_stream(cur)
+        if side not in _leaf["pending"]:
+            _leaf["pending"].append(side)
+        for t in self.tensors:
+            t.record_stream(side)
+        self.ctx = torch.cuda.stream(side)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+            self.ctx = None
+
+
 def _wgrad(be, dyo, xo, W, b, need_w, need_b, r0=None, r1=None):
     """dW (+)= dy^T x, db (+)= colsum(dy) for rows [r0, r1) of W / b.  Returns (dw, db) for autograd, or Nones when
     the result was accumulated in place into W.grad / b.grad."""
@@ -41,7 +102,8 @@ def _wgrad(be, dyo, xo, W, b, need_w, need_b, r0=None, r1=None):
     if _fuse_grads and W.grad is not None and (not want_b or b.grad is not None):
         gw = W.grad if r0 is None else W.grad[r0:r1]
         gb = None if not want_b else (b.grad if r0 is None else b.grad[r0:r1])
-        be.linear_bwd_weight(dyo, xo, gw, gb, accumulate=True)
+        with _on_leaf(dyo, xo):
+            be.linear_bwd_weight(dyo, xo, gw, gb, accumulate=True)
         return None, None
     if r0 is None:
         dw = torch.empty(W.shape, dtype=torch.float32, device=dyo.device)
@@ -370,7 +432,8 @@ class LinearSumFn(Function):
                 want_b = has_b and ctx.needs_input_grad[2 + 2 * n + i]
                 b = biases[i]
                 if _fuse_grads and w.grad is not None and (not want_b or b.grad is not None):
-                    be.linear_bwd_weight(dyo, xo, w.grad, b.grad if want_b else None, accumulate=True)
+                    with _on_leaf(dyo, xo):
+                        be.linear_bwd_weight(dyo, xo, w.grad, b.grad if want_b else None, accumulate=True)
                 else:
                     dw = torch.empty(N, K, dtype=torch.float32, device=dy.device)
                     if want_b and db_shared is None:
@@ -501,6 +564,7 @@ class LinearGroupFn(Function):
         # ---- wgrad + bias column sums ----
         dws, dbs = [None] * nt, [None] * nt
         wjobs = []
+        all_fused = True
         for tx, (jx, i, w, b, rows) in enumerate(table):
             if not ctx.needs_input_grad[1 + 2 * nin + tx]:
                 continue
@@ -509,6 +573,7 @@ class LinearGroupFn(Function):
                 gw = w.grad if rows is None else w.grad[rows[0]:rows[1]]
                 gb = None if not want_b else (b.grad if rows is None else b.grad[rows[0]:rows[1]])
             else:
+                all_fused = False
                 dws[tx] = torch.zeros(w.shape, dtype=f32, device=dev)
                 gw = dws[tx] if rows is None else dws[tx][rows[0]:rows[1]]
                 gb = None
@@ -516,8 +581,9 @@ class LinearGroupFn(Function):
                     dbs[tx] = torch.zeros(b.shape, dtype=f32, device=dev)
                     gb = dbs[tx] if rows is None else dbs[tx][rows[0]:rows[1]]
             wjobs.append(dict(terms=[(dyos[jx], xos[i], None)], out=gw, accumulate=True, dbias=gb))
-        for k in range(0, len(wjobs), 12):
-            be.linear_group(2, wjobs[k:k + 12])
+        with _on_leaf(*((dyos + [x for x in xos if x is not None]) if all_fused else [])):
+            for k in range(0, len(wjobs), 12):
+                be.linear_group(2, wjobs[k:k + 12])
         return (None, *dxs, *([None] * nin), *dws, *dbs)
 
 
@@ -840,8 +906,9 @@ class SelfAttnBlockFn(Function):
         else:
             gwi = dwi = torch.zeros(3 * d, d, dtype=f32, device=dy.device)
             gbi = dbi = torch.zeros(3 * d, dtype=f32, device=dy.device)
-        be.linear_group(2, [dict(terms=[(dqkv[:, : 2 * d], qk_in, None)], out=gwi[: 2 * d], accumulate=True, dbias=gbi[: 2 * d]),
-                            dict(terms=[(dqkv[:, 2 * d:], xo, None)], out=gwi[2 * d:], accumulate=True, dbias=gbi[2 * d:])])
+        with _on_leaf(*([dqkv, qk_in, xo] if dwi is None else [])):
+            be.linear_group(2, [dict(terms=[(dqkv[:, : 2 * d], qk_in, None)], out=gwi[: 2 * d], accumulate=True, dbias=gbi[: 2 * d]),
+                                dict(terms=[(dqkv[:, 2 * d:], xo, None)], out=gwi[2 * d:], accumulate=True, dbias=gbi[2 * d:])])
         need_pos = ctx.needs_input_grad[2]
         dpos = None
         if need_pos:

@@ -174,6 +174,7 @@ class FusedAdamW(torch.optim.Optimizer):
     def step(self, closure=None):
         assert closure is None
         be = ops.get_backend()
+        ops.join_leaf_streams()  # weight gradients issued on leaf streams (ops.set_leaf_streams)
         if self._runs is None:
             self._runs = self._build_runs()
         self._steps += 1
