@@ -45,7 +45,10 @@ def _side_streams(device):
     key = str(device)
     st = _stream_cache.get(key)
     if st is None:
-        st = tuple(torch.cuda.Stream(device) for _ in range(3))
+        # (M) memory-side GEMMs: default priority; (A), (B) the latency-bound query chains: high priority, so that their small
+        # kernels are scheduled ahead of pending CTAs of the big GEMMs / leaf-stream weight gradients (STCAT_CHAIN_PRIO=0: off)
+        prio = -1 if os.environ.get("STCAT_CHAIN_PRIO", "1") != "0" else 0
+        st = (torch.cuda.Stream(device), torch.cuda.Stream(device, priority=prio), torch.cuda.Stream(device, priority=prio))
         _stream_cache[key] = st
     return st
 

@@ -11,6 +11,7 @@ Precision:
 """
 from __future__ import annotations
 
+import os
 import weakref
 
 import torch
@@ -40,6 +41,7 @@ def set_grad_fusion(on: bool):
 # kernels per step.  ``join_leaf_streams()`` makes the current stream wait for all of them: ``dp.GradSync`` (before a range is
 # reduced), ``optim.FusedAdamW.step`` and ``dp.FlatGrads.zero`` call it; call it yourself before reading ``.grad`` otherwise.
 _leaf = {"on": False, "streams": {}, "pending": [], "max_rows": 1 << 30}
+_LEAF_SMS = int(os.environ.get("STCAT_LEAF_SMS", "0"))  # experiment: SM cap of the leaf-stream GEMMs (0 = none)
 
 
 def set_leaf_streams(flag: bool, max_rows: int = 1 << 30):
@@ -85,10 +87,14 @@ class _on_leaf:
             t.record_stream(side)
         self.ctx = torch.cuda.stream(side)
         self.ctx.__enter__()
+        if _LEAF_SMS:
+            get_backend().set_gemm_sm_limit(_LEAF_SMS)
         return self
 
     def __exit__(self, *exc):
         if self.ctx is not None:
+            if _LEAF_SMS:
+                get_backend().set_gemm_sm_limit(0)
             self.ctx.__exit__(*exc)
             self.ctx = None
 

@@ -50,8 +50,14 @@ class GraphedStep:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize(dev)
             g = torch.cuda.CUDAGraph()
+            # The step's main stream is a high-priority stream: the dependent chain of the backward pass (data gradients,
+            # attention, LayerNorm) is scheduled ahead of the weight gradients on the leaf streams (ops.set_leaf_streams) and of
+            # the collectives, which only have to be done by the end of the step.
             # thread_local: the NCCL watchdog thread polls events while the collectives are being captured
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            import os
+
+            main = torch.cuda.Stream(dev, priority=-1 if os.environ.get("STCAT_CHAIN_PRIO", "1") != "0" else 0)
+            with torch.cuda.graph(g, stream=main, capture_error_mode="thread_local"):
                 self._eager()
             torch.cuda.synchronize(dev)
             self.graph = g
