@@ -9,7 +9,7 @@ from stcat_b200 import ops
 pytestmark = pytest.mark.gpu
 
 
-def _setup(dropout, with_opt, lr=None):
+def _setup(dropout, with_opt, lr=None, train=True):
     from stcat_b200 import synthetic
     from stcat_b200.dp import FlatGrads, hot_path_groups
     from stcat_b200.loss import STGLossPlan
@@ -23,7 +23,7 @@ def _setup(dropout, with_opt, lr=None):
     if lr is not None:
         cfg.merge_from_list(["SOLVER.BASE_LR", lr, "SOLVER.TEMP_LR", lr, "SOLVER.MAX_GRAD_NORM", 1.0])
     T = 6
-    model = STCATHotPath(cfg).load_flat_params(synthetic_params(cfg, seed=0)).cuda().train()
+    model = STCATHotPath(cfg).load_flat_params(synthetic_params(cfg, seed=0)).cuda().train(train)
     inp = synthetic.make_inputs([T], 8, 8, 6, seed=3)
     tg = synthetic.make_targets([T], seed=3)
     plan = STGLossPlan(cfg, tg["boxes"], tg["actioness"], [T], "cuda")
@@ -117,7 +117,7 @@ def test_leaf_streams_give_the_same_gradients():
     the in-order backward, eagerly and under graph replay."""
     from stcat_b200.train import GraphedStep
 
-    fn, ex, grads, _ = _setup(0.0, False)
+    fn, ex, grads, _ = _setup(0.0, False, train=False)  # eval mode: no dropout anywhere, eager and replayed steps comparable
     ops.get_backend().set_dropout_step(None)
     try:
         ops.set_dropout_seed(7)
@@ -146,7 +146,7 @@ def test_leaf_streams_give_the_same_gradients():
         b = float(gs.replay())
         torch.cuda.synchronize()
         assert a == b and float((grads.buf - g1).abs().max()) <= 2e-3 * scale
-        assert float((g1 - ref).abs().max()) <= 5e-2 * scale  # other head-dropout masks than the eager reference: same scale
+        assert float((g1 - ref).abs().max()) <= 2e-3 * scale  # the replayed step equals the eager in-order step
         gs.close()
     finally:
         ops.set_leaf_streams(False)
