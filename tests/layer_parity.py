@@ -192,7 +192,7 @@ def _replay(kind, mod, ins, gseed):
         else:
             y, _, _ = mod.run(c, tgt, None, qpos, c.frames(qpos), qpos + c0._query_time, mod.memory_side(c))
     g = torch.randn(y.shape, generator=gen)
-    y.backward(g.to(y.device))
+    y.backward(g.to(y.device).clone())  # PutRowsFn edits its incoming gradient in place
     return g, {k: v.grad for k, v in leaves.items()}, {k: p.grad for k, p in mod.named_parameters() if p.grad is not None}
 
 
