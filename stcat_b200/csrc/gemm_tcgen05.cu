@@ -33,26 +33,48 @@ namespace tc {
 
 constexpr int BM = 128, BK = 64;  // BK * 2 B = 128 B = one swizzle row
 constexpr int A_BYTES = BM * BK * 2;   // 16 KB
-constexpr int EPI_BYTES = BM * 128;    // one staging chunk: 128 rows x 128 B
 constexpr int ACC_STAGES = 2;
-constexpr int THREADS = 384;
 
 // Two tile shapes.  BN = 256 is the throughput shape (128 x 256 accumulator, two epilogue groups).  BN = 64 is the
 // latency shape for GEMMs with so few 128 x 256 tiles that most SMs would idle (the decoder's [t, 256] query-side
 // layers): 4x as many CTAs, each with a short K loop, and -- unlike split-K -- a deterministic summation order.
-// EPI2 (staged, STCAT_GEMM_EPI2=1, BN = 256 only): two staging tiles per epilogue group, so the conversion of chunk c+1 runs
-// while the TMA store of chunk c still reads its tile (with one tile the group waits for every store to drain); paid for
-// with one operand stage (3 instead of 4).
-template <int BN, bool EPI2 = false> struct Cfg {
-    static constexpr int STAGES = BN >= 256 ? (EPI2 ? 3 : 4) : 8;   // ~192 KB of operands in flight (latency x bandwidth)
-    static constexpr int EPI_BUFS = EPI2 ? 2 : 1;
+// EPIMODE (BN = 256 only):
+//   0  two epilogue groups of 4 warps, one [128 x 128 B] staging tile per group;
+//   1  two staging tiles per group, so the conversion of chunk c+1 runs while the TMA store of chunk c still reads its tile
+//      (with one tile the group waits for every store to drain), paid for with one operand stage (3 instead of 4);
+//   3  "warp epilogue": 16 epilogue warps (4 per SM sub-partition), each an independent pipeline over its own 32 rows x 64
+//      columns of the accumulator with its own [32 x 64 B] staging tile (64B swizzle) and its own TMA stores: no barrier
+//      between warps inside a tile, latencies (TMEM load, store drain) hidden by the other three warps of the sub-partition,
+//      32 KB of staging instead of 64.
+//
+// BRES ("B resident", BN = 256, warp epilogue, single-term jobs with K <= 256): at K = 256 a 128 x 256 tile needs 16 MMAs
+// (2.1 k clocks) but 192 KB of operands, 128 KB of which is the weight tile that every tile of the same column block re-reads
+// (FFN linear1: 164 MB of operand loads + 56 MB of stores per launch; TMA load latency under that load is ~5 k clocks, so a
+// 3-stage ring cannot keep the MMAs fed).  With BRES the CTA keeps the whole [256 x K] weight tile in shared memory, takes a
+// CONTIGUOUS range of the work list (column-block-major, so the tile changes at most a few times per CTA) and streams only
+// the A tiles (64 KB per output tile) through a 4-stage ring: operand traffic drops 3x.
+template <int BN, int EPIMODE = 0, bool BRES = false> struct Cfg {
+    static constexpr bool WEPI = EPIMODE == 3;
+    static_assert(!BRES || (BN == 256 && WEPI), "BRES: 128 KB weight tile + 64 KB A ring + 32 KB warp-epilogue staging");
+    static_assert(!WEPI || BN == 256, "warp epilogue: 4 column groups of 64");
+    static constexpr int STAGES = BRES ? 4 : (BN >= 256 ? (EPIMODE == 1 ? 3 : 4) : 8);   // ~192 KB of operands in flight
+    static constexpr int EPI_BUFS = EPIMODE == 1 ? 2 : 1;
+    static constexpr int EPI_BYTES = BM * 128;                      // group epilogue: one staging tile, 128 rows x 128 B
     static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int GROUPS = BN >= 256 ? 2 : 1;   // epilogue groups (4 warps each)
-    static constexpr int GC = BN / GROUPS;             // accumulator columns per group
+    static constexpr int BRES_KB = 4;                               // k-blocks of the resident weight tile (K <= 256)
+    static constexpr int BRES_BYTES = BRES ? BRES_KB * B_BYTES : 0;
+    static constexpr int STAGE_BYTES = BRES ? A_BYTES : A_BYTES + B_BYTES;
+    static constexpr int GROUPS = WEPI ? 4 : (BN >= 256 ? 2 : 1);   // epilogue column groups (4 warps each)
+    static constexpr int GC = BN / GROUPS;                          // accumulator columns per group
+    static constexpr int EPI_WARPS = 4 * GROUPS;
+    static constexpr int THREADS = 128 + 32 * EPI_WARPS;            // 4 control warps + epilogue warps
+    static constexpr int WEPI_TILE = 32 * 64;                       // warp epilogue: [32 rows x 64 B] per warp
+    static constexpr int EPI_SMEM = WEPI ? EPI_WARPS * WEPI_TILE : GROUPS * EPI_BUFS * EPI_BYTES;
     static constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512 / 128 (power of two >= 32)
-    static constexpr int BIAS_BYTES = BN * 4;          // the tile's bias slice, staged once per tile
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GROUPS * EPI_BUFS * EPI_BYTES + BIAS_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int BIAS_BYTES = (WEPI ? 2 : 1) * BN * 4;      // the tile's bias slice (warp epilogue: double-buffered)
+    // the dynamic shared memory window starts 1024-aligned when the kernel has no static shared memory (checked at run
+    // time); the warp-epilogue configurations have no room for alignment slack
+    static constexpr int SMEM_BYTES = BRES_BYTES + STAGES * STAGE_BYTES + EPI_SMEM + BIAS_BYTES + (WEPI ? 0 : 1024) /*align slack*/ + 256 /*barriers*/;
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 };
 
@@ -82,24 +104,35 @@ template <int NJ> struct GroupParams {
     long long* trace;  // diagnostics (TRACE instantiation only): SM clock at the phase boundaries of CTA 0's first 8 tiles
 };
 
-template <bool A_MN, bool B_MN, bool OUT_BF16, int BN, int NJ, bool TRACE = false, bool EPI2 = false>
-__global__ void __launch_bounds__(THREADS, 1)
+template <bool A_MN, bool B_MN, bool OUT_BF16, int BN, int NJ, bool TRACE = false, int EPIMODE = 0, bool BRES = false>
+__global__ void __launch_bounds__((Cfg<BN, EPIMODE, BRES>::THREADS), 1)
 gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B-swizzle atoms need 1024 B alignment
-    using C = Cfg<BN, EPI2>;
+    const uint32_t bres_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B-swizzle atoms need 1024 B alignment
+    using C = Cfg<BN, EPIMODE, BRES>;
+    constexpr bool EPI2 = EPIMODE == 1;  // two staging tiles per group
+    constexpr bool WEPI = C::WEPI;
+    if (WEPI && (bres_base != smem_u32(smem_raw))) asm volatile("trap;");  // no alignment slack in these configurations
     constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, GROUPS = C::GROUPS, GC = C::GC, TMEM_COLS = C::TMEM_COLS;
+    constexpr int EPI_BYTES = C::EPI_BYTES, B_BYTES = C::B_BYTES;
+    const uint32_t base = bres_base + C::BRES_BYTES;  // operand ring
     const uint32_t epi_base = base + STAGES * STAGE_BYTES;
-    const uint32_t bias_base = epi_base + GROUPS * C::EPI_BUFS * EPI_BYTES;
+    const uint32_t bias_base = epi_base + C::EPI_SMEM;
     const uint32_t bar_base = bias_base + C::BIAS_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto accf_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
     auto acce_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + s); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES);
+    const uint32_t bfull_bar = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES);  // BRES: the resident weight tile has landed
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total = gp.total;
+    // work items of this CTA: w_lo, w_lo + w_step, ... < w_hi.  Strided over the grid by default; BRES: a contiguous range of the
+    // (job, column block, row block)-ordered list, so that successive items share the weight tile.
+    const int w_lo = BRES ? (int)(((long long)total * blockIdx.x) / gridDim.x) : (int)blockIdx.x;
+    const int w_hi = BRES ? (int)(((long long)total * (blockIdx.x + 1)) / gridDim.x) : total;
+    const int w_step = BRES ? 1 : (int)gridDim.x;
     // work item -> (job, split, m_blk, n_blk); jobs are few, a linear scan of the prefix table is enough
     auto find_job = [&](int w) {
         int j = 0;
@@ -114,7 +147,8 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(accf_bar(s), 1); mbar_init(acce_bar(s), 4 * GROUPS); }
+        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(accf_bar(s), 1); mbar_init(acce_bar(s), C::EPI_WARPS); }
+        mbar_init(bfull_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -139,14 +173,42 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int w = blockIdx.x; w < total; w += gridDim.x) {
-                const int ti = TRACE ? (w - (int)blockIdx.x) / (int)gridDim.x : 0;
+            int b_key = -1;                  // BRES: (job, column block) of the weight tile in shared memory
+            int tiles_done = 0;              // BRES: tiles issued so far (selects the accumulator stage / phase of the last one)
+            for (int w = w_lo; w < w_hi; w += w_step) {
+                const int ti = TRACE ? (w - w_lo) / w_step : 0;
                 bool first = true;
-                const Job& J = gp.jobs[find_job(w)];
+                const int ji = find_job(w);
+                const Job& J = gp.jobs[ji];
                 const int lw = w - J.work0;
                 const int split = lw % J.splits;
                 const int t = lw / J.splits;
                 const int m_blk = t % J.tiles_m, n_blk = t / J.tiles_m;
+                if (BRES) {
+                    const int key = ji * 65536 + n_blk;
+                    if (key != b_key) {
+                        if (tiles_done > 0) {
+                            // the MMAs of the previous tile (the last readers of the old weight tile) must have completed:
+                            // their commit is what the epilogue waits for, too
+                            const int pt = tiles_done - 1;
+                            mbar_wait(accf_bar(pt % ACC_STAGES), (uint32_t)(pt / ACC_STAGES) & 1u);
+                        }
+                        const int kbs = J.kb[0];
+                        mbar_expect_tx(bfull_bar, (uint32_t)(kbs * B_BYTES));
+                        for (int kb = 0; kb < kbs; ++kb) {
+                            const uint32_t sb = bres_base + kb * B_BYTES;
+                            if (!B_MN) {
+                                tma_load_2d(sb, &J.tmB[0], bfull_bar, kb * BK, n_blk * BN);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < BN / 64; ++j)
+                                    tma_load_2d(sb + j * (BK * 128), &J.tmB[0], bfull_bar, n_blk * BN + j * 64, kb * BK);
+                            }
+                        }
+                        b_key = key;
+                    }
+                    ++tiles_done;
+                }
                 for (int term = 0; term < J.nterms; ++term) {
                     const int kb0 = split * J.kb_per_split;  // splits == 1 for multi-term jobs: kb0 = 0
                     const int kb1 = min(J.kb[term], kb0 + J.kb_per_split);
@@ -164,12 +226,14 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
                             for (int j = 0; j < BM / 64; ++j)
                                 tma_load_2d(sa + j * (BK * 128), tmA, full_bar(stage), m_blk * BM + j * 64, kb * BK);
                         }
-                        if (!B_MN) {
-                            tma_load_2d(sb, tmB, full_bar(stage), kb * BK, n_blk * BN);
-                        } else {
+                        if (!BRES) {
+                            if (!B_MN) {
+                                tma_load_2d(sb, tmB, full_bar(stage), kb * BK, n_blk * BN);
+                            } else {
 #pragma unroll
-                            for (int j = 0; j < BN / 64; ++j)
-                                tma_load_2d(sb + j * (BK * 128), tmB, full_bar(stage), n_blk * BN + j * 64, kb * BK);
+                                for (int j = 0; j < BN / 64; ++j)
+                                    tma_load_2d(sb + j * (BK * 128), tmB, full_bar(stage), n_blk * BN + j * 64, kb * BK);
+                            }
                         }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -184,11 +248,22 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
             const uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
-            for (int w = blockIdx.x; w < total; w += gridDim.x) {
-                const int ti = TRACE ? (w - (int)blockIdx.x) / (int)gridDim.x : 0;
+            int b_key = -1;
+            uint32_t bphase = 0;
+            for (int w = w_lo; w < w_hi; w += w_step) {
+                const int ti = TRACE ? (w - w_lo) / w_step : 0;
                 bool first = true;
-                const Job& J = gp.jobs[find_job(w)];
+                const int ji = find_job(w);
+                const Job& J = gp.jobs[ji];
                 const int split = (w - J.work0) % J.splits;
+                if (BRES) {
+                    const int key = ji * 65536 + ((w - J.work0) / J.splits) / J.tiles_m;
+                    if (key != b_key) {  // a new weight tile: wait for it once
+                        mbar_wait(bfull_bar, bphase);
+                        bphase ^= 1;
+                        b_key = key;
+                    }
+                }
                 mbar_wait(acce_bar(as), aphase ^ 1);  // epilogue has drained this accumulator stage
                 T(ti, 2);  // accumulator stage free
                 tc_fence_after();
@@ -201,7 +276,7 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
                         mbar_wait(full_bar(stage), phase);
                         if (TRACE && first) { T(ti, 3); first = false; }  // first k-block landed
                         tc_fence_after();
-                        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                        const uint32_t sa = base + stage * STAGE_BYTES, sb = BRES ? bres_base + kb * B_BYTES : sa + A_BYTES;
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             // K-major: 16 bf16 = 32 B inside the 128 B swizzle row; 8-row groups 1024 B apart (SBO).
@@ -221,7 +296,172 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
                 if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
             }
         }
-    } else if (warp >= 4 && warp < 4 + 4 * GROUPS) {
+    } else if (WEPI && warp >= 4) {
+        // ================= warp epilogue: 16 independent warps, (TMEM lane quadrant q) x (64-column group cg) =================
+        const int ew = warp - 4;
+        const int q = ew & 3;                       // the hardware ties a warp to TMEM lanes [32 (warp % 4), +32)
+        const int cg = ew >> 2;
+        const int gt = (int)threadIdx.x - 128 - cg * 128;  // thread index inside the column group (4 warps)
+        const uint32_t sbuf = epi_base + ew * C::WEPI_TILE;
+        constexpr int CHUNK_COLS = OUT_BF16 ? 32 : 16;    // 64 B of output per row per chunk
+        constexpr int NCHUNK = GC / CHUNK_COLS;
+        // 16-byte unit j of row r in the 64B-swizzled staging tile (CU_TENSOR_MAP_SWIZZLE_64B: address bits [4,6) ^= bits [7,9))
+        auto swz = [](int j, int r) { return j ^ ((r >> 1) & 3); };
+        int as = 0;
+        uint32_t aphase = 0;
+        // Bias slice of the column group (GC floats), staged in shared memory by the group's 4 warps.  It only depends on (job,
+        // column block): restaged when that changes (BRES: a few times per CTA), from a register loaded one tile ahead so that
+        // the global-load latency is off the tile's critical path.  Double-buffered by restage count: one barrier of the group
+        // per restage (a warp can run at most one restage ahead of the slowest warp of its group, which then still reads the
+        // other buffer).
+        auto bias_key = [&](int w) {
+            const int ji = find_job(w);
+            const Job& J = gp.jobs[ji];
+            const int lw = w - J.work0;
+            return (ji << 20) | (((lw / J.splits) / J.tiles_m) << 1) | ((lw % J.splits) == 0 ? 1 : 0);
+        };
+        auto bias_load = [&](int w) {
+            const Job& J = gp.jobs[find_job(w)];
+            const int lw = w - J.work0;
+            const int col = ((lw / J.splits) / J.tiles_m) * BN + cg * GC + gt;
+            float bv = 0.f;
+            if ((lw % J.splits) == 0 && gt < GC && col < J.N)
+                for (int term = 0; term < J.nterms; ++term)
+                    if (J.bias[term] != nullptr) bv += __ldg(J.bias[term] + col);
+            return bv;
+        };
+        int staged_key = -1, next_key = w_lo < w_hi ? bias_key(w_lo) : -1;
+        float bv_next = w_lo < w_hi ? bias_load(w_lo) : 0.f;
+        uint32_t nstaged = 0;
+        uint32_t sbias = bias_base + cg * GC * 4;
+        for (int w = w_lo; w < w_hi; w += w_step) {
+            const int ti = TRACE ? (w - w_lo) / w_step : 0;
+            const bool tr = TRACE && ew == 0 && lane == 0;
+            const Job& p = gp.jobs[find_job(w)];
+            const CUtensorMap& tmC = p.tmC;
+            const int lw = w - p.work0;
+            const int t = lw / p.splits;
+            const int m_blk = t % p.tiles_m, n_blk = t / p.tiles_m;
+            const int col0 = n_blk * BN + cg * GC;        // first output column of this warp
+            const int row0 = m_blk * BM + q * 32;         // first output row of this warp
+            const int n_valid = p.N - col0;               // valid columns of this warp's share (<= 0: none)
+            const int job_relu = p.relu, job_reduce = p.reduce_add, job_N = p.N, job_M = p.M;
+            const __nv_bfloat16* const job_mask = p.mask;
+            const int64_t job_ld_mask = p.ld_mask;
+            float* const job_colsum = p.colsum;
+            if (next_key != staged_key) {
+                sbias = bias_base + (nstaged & 1u) * (BN * 4) + cg * GC * 4;
+                if (gt < GC) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + gt * 4), "f"(bv_next) : "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + cg) : "memory");
+                staged_key = next_key;
+                ++nstaged;
+            }
+            if (w + w_step < w_hi) {
+                next_key = bias_key(w + w_step);
+                if (next_key != staged_key) bv_next = bias_load(w + w_step);
+            }
+            if (tr) T(ti, 5);  // epilogue ready for the tile
+            mbar_wait(accf_bar(as), aphase);
+            if (tr) T(ti, 6);  // accumulator complete
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + as * BN + cg * GC + ((uint32_t)(q * 32) << 16);
+            const bool live = row0 < job_M && n_valid > 0;  // warp-uniform: anything of this warp's share inside the output?
+            if (live) {
+#pragma unroll 1
+                for (int c = 0; c < NCHUNK; ++c) {
+                    if (c * CHUNK_COLS >= n_valid) break;
+                    uint32_t r[CHUNK_COLS];
+                    if constexpr (CHUNK_COLS == 32) tmem_ld32(t_row + c * CHUNK_COLS, r);
+                    else tmem_ld16(t_row + c * CHUNK_COLS, r);
+                    uint4 mk[CHUNK_COLS / 8];  // this row's slice of the ReLU mask (bf16), in flight with the TMEM load
+                    if (job_mask) {
+                        const int gr = row0 + lane;
+                        const uint4* mp = reinterpret_cast<const uint4*>(job_mask + (int64_t)gr * job_ld_mask + col0 + c * CHUNK_COLS);
+#pragma unroll
+                        for (int j = 0; j < CHUNK_COLS / 8; ++j) mk[j] = gr < job_M ? __ldg(mp + j) : make_uint4(0, 0, 0, 0);
+                    }
+                    if (lane == 0) tma_wait_read<0>();  // this warp's previous store has read the staging tile
+                    __syncwarp();
+                    tmem_ld_wait();
+                    const uint32_t sb = sbias + c * CHUNK_COLS * 4;
+#pragma unroll
+                    for (int j = 0; j < CHUNK_COLS / 4; ++j) {
+                        float b0, b1, b2, b3;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(sb + j * 16));
+                        float x0 = __uint_as_float(r[4 * j + 0]) + b0, x1 = __uint_as_float(r[4 * j + 1]) + b1;
+                        float x2 = __uint_as_float(r[4 * j + 2]) + b2, x3 = __uint_as_float(r[4 * j + 3]) + b3;
+                        if (job_relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+                        r[4 * j + 0] = __float_as_uint(x0); r[4 * j + 1] = __float_as_uint(x1);
+                        r[4 * j + 2] = __float_as_uint(x2); r[4 * j + 3] = __float_as_uint(x3);
+                    }
+                    if (job_mask) {  // y > 0 for a bf16 y  <=>  its bits, read as int16, are > 0
+#pragma unroll
+                        for (int j = 0; j < CHUNK_COLS / 8; ++j) {
+                            const uint32_t w4[4] = {mk[j].x, mk[j].y, mk[j].z, mk[j].w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                if ((int16_t)(w4[e] & 0xffffu) <= 0) r[8 * j + 2 * e] = 0u;
+                                if ((int16_t)(w4[e] >> 16) <= 0) r[8 * j + 2 * e + 1] = 0u;
+                            }
+                        }
+                    }
+                    const uint32_t srow = sbuf + lane * 64;
+                    if (OUT_BF16) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {  // 16 B = 8 bf16 per store
+                            uint32_t wv[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                __nv_bfloat162 bb = __floats2bfloat162_rn(__uint_as_float(r[8 * j + 2 * e]), __uint_as_float(r[8 * j + 2 * e + 1]));
+                                wv[e] = *reinterpret_cast<uint32_t*>(&bb);
+                            }
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + swz(j, lane) * 16), "r"(wv[0]), "r"(wv[1]), "r"(wv[2]), "r"(wv[3]) : "memory");
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)  // 16 B = 4 fp32 per store
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + swz(j, lane) * 16), "r"(r[4 * j + 0]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    const int c0 = col0 + c * CHUNK_COLS;
+                    if (lane == 0) {
+                        if (job_reduce) tma_reduce_add_2d(&tmC, sbuf, c0, row0);
+                        else tma_store_2d(&tmC, sbuf, c0, row0);
+                        tma_commit();
+                    }
+                    if (job_colsum) {
+                        // column sums of this warp's staged (rounded) 32-row tile; rows past M hold zeros (TMA zero-fills A, the
+                        // fused column sum is only used without a bias).  The next chunk overwrites the tile after the __syncwarp
+                        // that follows lane 0's wait, which every lane reaches after these reads.
+                        if (lane < CHUNK_COLS) {
+                            float sum = 0.f;
+#pragma unroll 8
+                            for (int rr = 0; rr < 32; ++rr) {
+                                if (OUT_BF16) {
+                                    uint16_t hv;
+                                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(sbuf + rr * 64 + (swz(lane >> 3, rr) << 4) + (lane & 7) * 2));
+                                    sum += __uint_as_float((uint32_t)hv << 16);
+                                } else {
+                                    float fv;
+                                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(fv) : "r"(sbuf + rr * 64 + (swz(lane >> 2, rr) << 4) + (lane & 3) * 4));
+                                    sum += fv;
+                                }
+                            }
+                            if (c0 + lane < job_N) atomicAdd(job_colsum + c0 + lane, sum);
+                        }
+                    }
+                }
+            }
+            // all TMEM reads of this warp are complete (tmem_ld_wait above): hand the accumulator stage back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acce_bar(as));
+            if (tr) T(ti, 7);  // last store of the tile issued
+            if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+        }
+        if (lane == 0) tma_wait_all();
+    } else if (!WEPI && warp >= 4 && warp < 4 + 4 * GROUPS) {
         // ================= epilogue: GROUPS column groups x 4 TMEM lane quadrants =================
         // Group g (warps 4+4g .. 7+4g) drains columns [GC g, GC g + GC) of the accumulator; warp (q = warp & 3)
         // of a group reads TMEM lanes [32 q, 32 q + 32) (the hardware ties a warp to lane quadrant warp % 4).
@@ -234,12 +474,15 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
         const uint32_t sbuf_group = epi_base + g * C::EPI_BUFS * EPI_BYTES;  // the group's 128 x 128 B staging tile(s)
         uint32_t nchunk_done = 0;  // running chunk count of this group (EPI2: selects the staging tile)
         const uint32_t sbias = bias_base + g * GC * 4;  // this group's GC bias values (fp32)
-        constexpr int CHUNK_COLS = OUT_BF16 ? 64 : 32;        // 128 B of output per row per chunk
+        constexpr int ROWB = 128;                             // bytes of output per row per chunk (= the staging tile's row)
+        constexpr int CHUNK_COLS = OUT_BF16 ? ROWB / 2 : ROWB / 4;
+        // 16-byte unit j of row `row` inside the swizzled staging tile (CU_TENSOR_MAP_SWIZZLE_128B: address bits [4,7) ^= [7,10))
+        auto swz = [](int j, int row) { return j ^ (row & 7); };
         constexpr int NCHUNK = GC / CHUNK_COLS;               // chunks per group
         int as = 0;
         uint32_t aphase = 0;
-        for (int w = blockIdx.x; w < total; w += gridDim.x) {
-            const int ti = TRACE ? (w - (int)blockIdx.x) / (int)gridDim.x : 0;
+        for (int w = w_lo; w < w_hi; w += w_step) {
+            const int ti = TRACE ? (w - w_lo) / w_step : 0;
             const bool tr = TRACE && ew == 0 && lane == 0;
             const Job& p = gp.jobs[find_job(w)];
             const CUtensorMap& tmC = p.tmC;
@@ -300,7 +543,7 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 tmem_ld_wait();
-                const uint32_t srow = sbuf_base + row * 128;
+                const uint32_t srow = sbuf_base + row * ROWB;
                 const uint32_t sb = sbias + c * CHUNK_COLS * 4;
 #pragma unroll
                 for (int j = 0; j < CHUNK_COLS / 4; ++j) {
@@ -332,13 +575,13 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
                             __nv_bfloat162 bb = __floats2bfloat162_rn(__uint_as_float(r[8 * j + 2 * e]), __uint_as_float(r[8 * j + 2 * e + 1]));
                             wv[e] = *reinterpret_cast<uint32_t*>(&bb);
                         }
-                        const int chunk = j ^ (row & 7);
+                        const int chunk = swz(j, row);
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + chunk * 16), "r"(wv[0]), "r"(wv[1]), "r"(wv[2]), "r"(wv[3]) : "memory");
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < CHUNK_COLS / 4; ++j) {  // 16 B = 4 fp32 per store
-                        const int chunk = j ^ (row & 7);
+                        const int chunk = swz(j, row);
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + chunk * 16), "r"(r[4 * j + 0]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
                     }
                 }
@@ -361,11 +604,11 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
                     for (int rr = r0; rr < r0 + ROWS; ++rr) {
                         if (OUT_BF16) {
                             uint16_t hv;
-                            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(sbuf_base + rr * 128 + (((cc >> 3) ^ (rr & 7)) << 4) + (cc & 7) * 2));
+                            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(sbuf_base + rr * ROWB + (swz(cc >> 3, rr) << 4) + (cc & 7) * 2));
                             sum += __uint_as_float((uint32_t)hv << 16);
                         } else {
                             float fv;
-                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(fv) : "r"(sbuf_base + rr * 128 + (((cc >> 2) ^ (rr & 7)) << 4) + (cc & 3) * 4));
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(fv) : "r"(sbuf_base + rr * ROWB + (swz(cc >> 2, rr) << 4) + (cc & 3) * 4));
                             sum += fv;
                         }
                     }
@@ -405,7 +648,7 @@ EncodeTiledFn get_encode() {
 }
 
 int make_map(CUtensorMap* tm, const void* ptr, bool bf16, int64_t rows, int64_t cols, int64_t ld, int box_cols,
-             int box_rows) {
+             int box_rows, bool swizzle64) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return set_err(STCAT_EINVAL, "tensor map: cuTensorMapEncodeTiled not available from the driver");
     const int es = bf16 ? 2 : 4;
@@ -414,7 +657,8 @@ int make_map(CUtensorMap* tm, const void* ptr, bool bf16, int64_t rows, int64_t 
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr),
-                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(STCAT_EINVAL, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, (long long)rows, (long long)cols, (long long)ld);
     return 0;
@@ -471,58 +715,61 @@ void gemm_tc_set_sm_limit(int n) { g_gemm_sm_limit = n > 0 ? n : 0; }
 static long long* g_gemm_trace = nullptr;
 void gemm_tc_set_trace(long long* buf) { g_gemm_trace = buf; }
 
-template <bool AMN, bool BMN, bool OBF, int BN, int NJ>
-static int launch_tc(const tc::GroupParams<NJ>& gp, int grid, cudaStream_t st, bool short_k) {
+// one instantiation: shared-memory attribute once, programmatic dependent launch
+template <bool AMN, bool BMN, bool OBF, int BN, int NJ, bool TRACE, int EPIMODE, bool BRES>
+static int launch_inst(const tc::GroupParams<NJ>& gp, int grid, cudaStream_t st) {
     using namespace tc;
-    if constexpr (BN == 256) {
-        // two staging tiles per epilogue group (EPI2, 3 operand stages instead of 4): the store drain of chunk c overlaps the
-        // conversion of chunk c+1.  Measured (profiles/r2_a_validate_staged.log): faster where the K loop is short (K = 256:
-        // FFN linear1 23.2 -> 19.9 us, its dgrad twin 22.5 -> 20.2, in/out projections -8..-14 %), slower by 3 % where the
-        // K loop is long (K = 2048) and the fourth operand stage matters more.  STCAT_GEMM_EPI2=0 / 1 forces it off / on.
-        static const char* epi2_env = getenv("STCAT_GEMM_EPI2");
-        const bool epi2 = epi2_env ? atoi(epi2_env) != 0 : short_k;
-        if constexpr (!AMN && !BMN && NJ == 1) {  // diagnostics: traced instantiations of the plain forward GEMM
-            if (g_gemm_trace != nullptr) {
-                GroupParams<NJ> gt = gp;
-                gt.trace = g_gemm_trace;
-                cudaError_t le;
-                if (epi2) {
-                    cudaFuncSetAttribute(gemm_tc_kernel<AMN, BMN, OBF, BN, NJ, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, true>::SMEM_BYTES);
-                    le = launch_pdl(gemm_tc_kernel<AMN, BMN, OBF, BN, NJ, true, true>, dim3(grid), dim3(THREADS), Cfg<BN, true>::SMEM_BYTES, st, gt);
-                } else {
-                    cudaFuncSetAttribute(gemm_tc_kernel<AMN, BMN, OBF, BN, NJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
-                    le = launch_pdl(gemm_tc_kernel<AMN, BMN, OBF, BN, NJ, true>, dim3(grid), dim3(THREADS), Cfg<BN>::SMEM_BYTES, st, gt);
-                }
-                if (le != cudaSuccess) return set_err((int)le, "gemm_tc_kernel<trace> launch: %s", cudaGetErrorString(le));
-                return check_launch("gemm_tc_kernel<trace>");
-            }
-        }
-        if (epi2) {
-            static bool attr2 = false;
-            if (!attr2) {
-                cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AMN, BMN, OBF, BN, NJ, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, true>::SMEM_BYTES);
-                if (e != cudaSuccess) return set_err((int)e, "gemm_tc<epi2>: smem attribute: %s", cudaGetErrorString(e));
-                attr2 = true;
-            }
-            cudaError_t le = launch_pdl(gemm_tc_kernel<AMN, BMN, OBF, BN, NJ, false, true>, dim3(grid), dim3(THREADS), Cfg<BN, true>::SMEM_BYTES, st, gp);
-            if (le != cudaSuccess) return set_err((int)le, "gemm_tc_kernel<epi2> launch: %s", cudaGetErrorString(le));
-            return check_launch("gemm_tc_kernel<epi2>");
-        }
-    }
+    constexpr int SMEM = Cfg<BN, EPIMODE, BRES>::SMEM_BYTES;
+    auto kern = gemm_tc_kernel<AMN, BMN, OBF, BN, NJ, TRACE, EPIMODE, BRES>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AMN, BMN, OBF, BN, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return set_err((int)e, "gemm_tc: smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    cudaError_t le = launch_pdl(gemm_tc_kernel<AMN, BMN, OBF, BN, NJ>, dim3(grid), dim3(THREADS), Cfg<BN>::SMEM_BYTES, st, gp);
+    cudaError_t le = launch_pdl(kern, dim3(grid), dim3(Cfg<BN, EPIMODE, BRES>::THREADS), SMEM, st, gp);
     if (le != cudaSuccess) return set_err((int)le, "gemm_tc_kernel launch: %s", cudaGetErrorString(le));
     return check_launch("gemm_tc_kernel");
 }
 
+// epilogue / operand-residency variant of a launch (see Cfg)
+enum TcMode { TC_PLAIN = 0, TC_EPI2 = 1, TC_BRES = 2, TC_WEPI = 3 };
+
+template <bool AMN, bool BMN, bool OBF, int BN, int NJ>
+static int launch_tc(const tc::GroupParams<NJ>& gp, int grid, cudaStream_t st, int mode) {
+    using namespace tc;
+    if constexpr (BN == 256) {
+        if constexpr (!AMN && OBF) {
+            if (mode == TC_BRES) {
+                if constexpr (!BMN && NJ == 1) {  // diagnostics: traced instantiation of the plain forward GEMM
+                    if (g_gemm_trace != nullptr) {
+                        GroupParams<NJ> gt = gp;
+                        gt.trace = g_gemm_trace;
+                        return launch_inst<AMN, BMN, OBF, BN, NJ, true, 3, true>(gt, grid, st);
+                    }
+                }
+                return launch_inst<AMN, BMN, OBF, BN, NJ, false, 3, true>(gp, grid, st);
+            }
+        }
+        if constexpr (!AMN && !BMN && NJ == 1) {  // diagnostics: traced instantiations of the plain forward GEMM
+            if (g_gemm_trace != nullptr) {
+                GroupParams<NJ> gt = gp;
+                gt.trace = g_gemm_trace;
+                if (mode == TC_WEPI) return launch_inst<AMN, BMN, OBF, BN, NJ, true, 3, false>(gt, grid, st);
+                if (mode == TC_EPI2) return launch_inst<AMN, BMN, OBF, BN, NJ, true, 1, false>(gt, grid, st);
+                return launch_inst<AMN, BMN, OBF, BN, NJ, true, 0, false>(gt, grid, st);
+            }
+        }
+        if (mode == TC_WEPI) return launch_inst<AMN, BMN, OBF, BN, NJ, false, 3, false>(gp, grid, st);
+        if (mode == TC_EPI2) return launch_inst<AMN, BMN, OBF, BN, NJ, false, 1, false>(gp, grid, st);
+    }
+    return launch_inst<AMN, BMN, OBF, BN, NJ, false, 0, false>(gp, grid, st);
+}
+
 // Fills one device-side Job.  `work0` is the running prefix of work items; returns <0 on error via set_err code.
 template <int BN>
-static int fill_job(tc::Job& J, const TcJob& in, int a_mn_major, int b_mn_major, bool out_bf16, int& work, cudaStream_t st) {
+static int fill_job(tc::Job& J, const TcJob& in, int a_mn_major, int b_mn_major, bool out_bf16, int& work, cudaStream_t st,
+                    bool warp_epi) {
     using namespace tc;
     int rc;
     const int M = in.M, N = in.N;
@@ -539,7 +786,8 @@ static int fill_job(tc::Job& J, const TcJob& in, int a_mn_major, int b_mn_major,
         J.kb[t] = (T.K + BK - 1) / BK;
         kb_max = J.kb[t] > kb_max ? J.kb[t] : kb_max;
     }
-    rc = make_map(&J.tmC, in.C, out_bf16, M, N, in.ldc, out_bf16 ? 64 : 32, BM);
+    // output staging tile: [BM rows x 128 B] (128B swizzle) per epilogue group or, for the warp epilogue, [32 x 64 B] (64B swizzle)
+    rc = make_map(&J.tmC, in.C, out_bf16, M, N, in.ldc, (out_bf16 ? 64 : 32) / (warp_epi ? 2 : 1), warp_epi ? 32 : BM, warp_epi);
     if (rc) return rc;
     J.nterms = in.nterms;
     J.M = M; J.N = N;
@@ -583,29 +831,47 @@ static int gemm_tc_launch_jobs(const TcJob* jobs, int njobs, int a_mn_major, int
     using namespace tc;
     const bool out_bf16 = out_dtype == STCAT_BF16;
     static thread_local GroupParams<NJ> gp;  // ~1 KB per job: kept off the stack, rebuilt per call
+    int kmax = 0;  // longest K loop of the launch
+    bool single_short = true;  // every job: one term with K <= 256 (its [256 x K] weight tile fits the resident region)
+    long tiles256 = 0;
+    for (int j = 0; j < njobs; ++j) {
+        int k = 0;
+        for (int t = 0; t < jobs[j].nterms; ++t) k += jobs[j].term[t].K;
+        kmax = k > kmax ? k : kmax;
+        if (jobs[j].nterms != 1 || jobs[j].term[0].K > Cfg<256, 3, true>::BRES_KB * BK) single_short = false;
+        tiles256 += (long)((jobs[j].M + BM - 1) / BM) * ((jobs[j].N + 255) / 256);
+    }
+    const int sms = (g_gemm_sm_limit > 0 && g_gemm_sm_limit < num_sms()) ? g_gemm_sm_limit : num_sms();
+    // Variant (BN = 256): weight-resident (BRES) when every job is a single K <= 256 product with a bf16 output and each CTA
+    // gets at least two tiles (else nothing is re-used); otherwise two staging tiles (EPI2) for short K loops -- measured
+    // (profiles/r2_a_validate_staged.log): K = 256: FFN linear1 23.2 -> 19.9 us, slower by 3 % where the K loop is long
+    // (K = 2048) and the fourth operand stage matters more.  STCAT_GEMM_EPI2 / STCAT_GEMM_BRES = 0 / 1 force them off / on.
+    static const char* epi2_env = getenv("STCAT_GEMM_EPI2");
+    static const char* bres_env = getenv("STCAT_GEMM_BRES");
+    int mode = TC_PLAIN;
+    if (BN == 256) {
+        const bool bres_ok = single_short && out_bf16 && !a_mn_major;
+        const bool bres = bres_ok && (bres_env ? atoi(bres_env) != 0 : tiles256 >= 2L * sms);
+        const bool epi2 = epi2_env ? atoi(epi2_env) != 0 : kmax <= 512;
+        static const char* wepi_env = getenv("STCAT_GEMM_WEPI");
+        const bool wepi = wepi_env ? atoi(wepi_env) != 0 : true;
+        mode = bres ? TC_BRES : (wepi ? TC_WEPI : (epi2 ? TC_EPI2 : TC_PLAIN));
+    }
     int work = 0;
     for (int j = 0; j < njobs; ++j) {
-        int rc = fill_job<BN>(gp.jobs[j], jobs[j], a_mn_major, b_mn_major, out_bf16, work, st);
+        int rc = fill_job<BN>(gp.jobs[j], jobs[j], a_mn_major, b_mn_major, out_bf16, work, st, mode == TC_BRES || mode == TC_WEPI);
         if (rc) return rc;
     }
     gp.njobs = njobs;
     gp.total = work;
     gp.trace = nullptr;
-    const int sms = (g_gemm_sm_limit > 0 && g_gemm_sm_limit < num_sms()) ? g_gemm_sm_limit : num_sms();
     const int grid = work < sms ? work : sms;
-    int kmax = 0;  // longest K loop of the launch
-    for (int j = 0; j < njobs; ++j) {
-        int k = 0;
-        for (int t = 0; t < jobs[j].nterms; ++t) k += jobs[j].term[t].K;
-        kmax = k > kmax ? k : kmax;
-    }
-    const bool short_k = kmax <= 512;
     if (!a_mn_major && !b_mn_major)
-        return out_bf16 ? launch_tc<false, false, true, BN, NJ>(gp, grid, st, short_k) : launch_tc<false, false, false, BN, NJ>(gp, grid, st, short_k);
+        return out_bf16 ? launch_tc<false, false, true, BN, NJ>(gp, grid, st, mode) : launch_tc<false, false, false, BN, NJ>(gp, grid, st, mode);
     if (!a_mn_major && b_mn_major)
-        return out_bf16 ? launch_tc<false, true, true, BN, NJ>(gp, grid, st, short_k) : launch_tc<false, true, false, BN, NJ>(gp, grid, st, short_k);
+        return out_bf16 ? launch_tc<false, true, true, BN, NJ>(gp, grid, st, mode) : launch_tc<false, true, false, BN, NJ>(gp, grid, st, mode);
     if (a_mn_major && b_mn_major)
-        return out_bf16 ? launch_tc<true, true, true, BN, NJ>(gp, grid, st, short_k) : launch_tc<true, true, false, BN, NJ>(gp, grid, st, short_k);
+        return out_bf16 ? launch_tc<true, true, true, BN, NJ>(gp, grid, st, mode) : launch_tc<true, true, false, BN, NJ>(gp, grid, st, mode);
     return set_err(STCAT_ESHAPE, "gemm_tc: A MN-major with B K-major is not instantiated");
 }
 

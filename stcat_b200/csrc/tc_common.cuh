@@ -129,7 +129,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode();
 // 2-D row-major tensor [rows, cols] with leading dimension ld (elements); box = {box_cols, box_rows}; 128B swizzle
-int make_map(CUtensorMap* tm, const void* ptr, bool bf16, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows);
+int make_map(CUtensorMap* tm, const void* ptr, bool bf16, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+             bool swizzle64 = false);  // 64B swizzle: box rows of 64 bytes
 // 3-D bf16 view [batch, rows, cols] of a row-major 2-D buffer whose batches are `rows` consecutive rows; box =
 // {box_cols, box_rows, 1}.  Rows >= `rows` inside a box are out of bounds (zero-filled on load), which is what keeps
 // a frame's tile from reading its neighbour frame.

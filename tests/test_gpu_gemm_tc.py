@@ -185,3 +185,43 @@ def test_tensor_core_kernel_is_what_runs(be):
     tflops = 2.0 * M * N * K / (us * 1e-6) / 1e12
     print(f"FFN linear1 fwd bf16: {us:.1f} us/launch, {tflops:.0f} TFLOP/s")
     assert tflops > 150, "tcgen05 path not active (SIMT fp32 peaks far below this)"
+
+
+@pytest.mark.parametrize("M,N,K", [(13632, 2048, 256), (20000, 1000, 200), (40000, 264, 72), (19000, 512, 256)])
+def test_weight_resident_variant(be, M, N, K):
+    """K <= 256, bf16 output and >= 2 tiles per SM: the launch takes the weight-resident variant (gemm_tcgen05.cu BRES: the
+    [256 x K] weight tile stays in shared memory, CTAs walk contiguous column-block-major tile ranges, half-width 64B-swizzled
+    staging tiles).  Forward with bias + ReLU and the data gradient (MN-major weight tile), tails in every dimension."""
+    x, w = g(M, K, seed=1), g(N, K, seed=2, scale=K ** -0.5)
+    b = torch.randn(N, generator=torch.Generator().manual_seed(3))
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    ref = (xd.double() @ wd.double().t() + bd.double()).relu()
+    yb = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    be.linear_fwd(xd, wd, bd, yb, relu=True)
+    assert rel_err(yb, ref) < TOL_BF16
+    # exact check of the tile bookkeeping: against the fp32-output launch (plain variant) rounded once
+    yf = torch.empty(M, N, device="cuda")
+    be.linear_fwd(xd, wd, bd, yf, relu=True)
+    assert torch.equal(yb, yf.to(torch.bfloat16))
+    # data gradient: dx[M, N] = dy[M, K] . W[K, N] with the roles swapped (contraction over the K <= 256 side)
+    w2 = g(K, N, seed=5, scale=K ** -0.5).cuda()  # Linear(N -> K): weight [K, N]
+    dxb = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    be.linear_bwd_data(xd, w2, dxb)
+    dxf = torch.empty(M, N, device="cuda")
+    be.linear_bwd_data(xd, w2, dxf)
+    assert rel_err(dxf, xd.double() @ w2.double()) < TOL_F32
+    assert torch.equal(dxb, dxf.to(torch.bfloat16))
+
+
+def test_weight_resident_variant_grouped(be):
+    """three independent [M, 256] x [256, 256]^T projections with bf16 outputs in one launch (the decoder's memory-side K / V
+    projections): each CTA's contiguous range crosses job boundaries, i.e. the resident weight tile is replaced mid-range."""
+    M, d = 13568, 256
+    xs = [g(M, d, seed=20 + i).cuda() for i in range(2)]
+    ws = [g(d, d, seed=30 + i, scale=1 / 16).cuda() for i in range(3)]
+    bs = [torch.randn(d, generator=torch.Generator().manual_seed(40 + i)).cuda() for i in range(3)]
+    outs = [torch.full((M, d), float("nan"), device="cuda", dtype=torch.bfloat16) for _ in range(3)]
+    be.linear_group(0, [dict(terms=[(xs[i % 2], ws[i], bs[i])], out=outs[i]) for i in range(3)])
+    for i in range(3):
+        ref = xs[i % 2].double() @ ws[i].double().t() + bs[i].double()
+        assert rel_err(outs[i], ref) < TOL_BF16, i
