@@ -461,6 +461,9 @@ def run_b200_arm(args):
     device = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the gradient all-reduces run next to the backward pass: bound the SMs NCCL's resident CTAs take, and have the
+        # persistent kernels leave exactly those free while a collective is in flight (stcat_b200/dp.py GradSync)
+        os.environ.setdefault("NCCL_MAX_CTAS", "24")
         dist.init_process_group("nccl", device_id=device)
     ctx = build_b200(args, device)
     be = ctx["ops"].get_backend()

@@ -41,7 +41,7 @@ extern "C" {
 
 /* Bumped whenever a signature or the meaning of an argument changes; stcat_b200/cabi.py refuses a library whose version
  * differs from the one it was written against (a stale locally built .so would otherwise be called with new signatures). */
-#define STCAT_ABI_VERSION 6
+#define STCAT_ABI_VERSION 7
 STCAT_API int stcat_abi_version(void);
 STCAT_API const char* stcat_last_error(void);
 /* compute capability major*10+minor of the current device, or <0; 100 expected */
@@ -101,6 +101,12 @@ typedef struct stcat_linear_job {
  * Host-side launch state, read when a GEMM is launched (a captured launch keeps its grid).  Used for GEMMs that run on a side
  * stream next to a latency-bound chain of small kernels (the decoder's memory-side projections). */
 STCAT_API int stcat_set_gemm_sm_limit(int n);
+/* SMs that EVERY persistent kernel of the library (tcgen05 GEMM and attention) sizes its grid for; 0 = all (default).  Host-side
+ * launch state like the limit above.  For the window in which a collective with resident CTAs (the NCCL all-reduce of the
+ * gradient ranges, stcat_b200/dp.py GradSync -- the reference's DistributedDataParallel buckets, scripts/train_net.py:31-36)
+ * runs next to the backward pass: a persistent CTA whose SM is held by the collective cannot become resident, and its
+ * statically assigned tiles would wait until the collective ends. */
+STCAT_API int stcat_set_sm_cap(int n);
 STCAT_API int stcat_linear_group(int kind, int in_dtype, const stcat_linear_job* jobs, int njobs, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

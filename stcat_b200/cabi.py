@@ -65,6 +65,7 @@ SIGNATURES["stcat_debug_attn_trace"] = (c_int, [_P])
 SIGNATURES["stcat_debug_gemm_trace"] = (c_int, [_P])
 SIGNATURES["stcat_set_dropout_step"] = (c_int, [_P])
 SIGNATURES["stcat_set_gemm_sm_limit"] = (c_int, [_I])
+SIGNATURES["stcat_set_sm_cap"] = (c_int, [_I])
 SIGNATURES["stcat_pos_sine"] = (c_int, [_P, _P, _I, _I, _I, _I, _F, _F, _P])
 SIGNATURES["stcat_box_interp"] = (c_int, [_P, _P, _I, _P, _L, _I, _P])
 SIGNATURES["stcat_debug_attn_counts"] = (c_int, [ctypes.POINTER(ctypes.c_longlong)])
@@ -75,7 +76,7 @@ SIGNATURES["stcat_box_refine_bwd"] = (c_int, [_P, _P, _P, _P, _P, _L, _F, _P])
 SIGNATURES["stcat_stg_loss"] = (c_int, [_P] * 12 + [ctypes.POINTER(c_float), _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P])
 SIGNATURES["stcat_linear_group"] = (c_int, [_I, _I, ctypes.POINTER(_Job), _I, _P])
 MAX_GROUP_JOBS = 12
-ABI_VERSION = 6  # include/stcat_b200.h STCAT_ABI_VERSION
+ABI_VERSION = 7  # include/stcat_b200.h STCAT_ABI_VERSION
 
 _lib = None
 
@@ -147,6 +148,10 @@ class CudaBackend:
 
     def set_gemm_sm_limit(self, n: int):
         self._rc(self.lib.stcat_set_gemm_sm_limit(int(n)), "set_gemm_sm_limit")
+
+    def set_sm_cap(self, n: int):
+        """SMs the persistent kernels size their grids for (0 = all); see include/stcat_b200.h stcat_set_sm_cap."""
+        self._rc(self.lib.stcat_set_sm_cap(int(n)), "set_sm_cap")
 
     def attn_counts(self):
         """launches of the attention entry points per kernel family (stcat_debug_attn_counts)"""

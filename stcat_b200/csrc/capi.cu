@@ -58,6 +58,11 @@ extern "C" int stcat_set_gemm_sm_limit(int n) {
     stcat::gemm_tc_set_sm_limit(n);
     return 0;
 }
+namespace stcat { int g_sm_cap = 0; }
+extern "C" int stcat_set_sm_cap(int n) {
+    stcat::g_sm_cap = n > 0 ? n : 0;
+    return 0;
+}
 extern "C" int stcat_set_dropout_step(const void* counter) {
     stcat::set_dropout_step_ptr((const uint64_t*)counter);
     return 0;

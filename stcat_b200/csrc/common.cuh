@@ -131,6 +131,10 @@ __device__ __forceinline__ float drop_apply(const DropArgs& d, uint64_t idx, flo
     return drop_bits24(d.seed, d.offset + idx) >= d.thresh ? v * d.scale : 0.f;
 }
 
+// SMs the persistent kernels (tcgen05 GEMM, tcgen05 attention) size their grids for: all of them, or the cap set by
+// stcat_set_sm_cap (capi.cu) while a collective that keeps CTAs resident runs next to them -- a persistent CTA that cannot
+// become resident because an NCCL CTA holds its SM would keep its statically assigned tiles waiting until the collective ends.
+extern int g_sm_cap;
 inline int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -139,7 +143,7 @@ inline int num_sms() {
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
     }
-    return n;
+    return (g_sm_cap > 0 && g_sm_cap < n) ? g_sm_cap : n;
 }
 
 }  // namespace stcat

@@ -109,6 +109,14 @@ class GradSync:
         self.stream = torch.cuda.Stream(device) if (self.active and flat.buf.is_cuda) else None
         self.done = set()
         self.extra_streams = ()
+        # While an all-reduce is in flight the persistent kernels of the backward pass leave ``nccl_ctas`` SMs to it
+        # (include/stcat_b200.h stcat_set_sm_cap): NCCL's CTAs stay resident for the whole collective, and a persistent GEMM /
+        # attention CTA that cannot become resident next to one would hold its share of the tiles until the collective ends.
+        # Keep NCCL_MAX_CTAS (read by NCCL when the communicator is created; bench.py sets it) at this value.  0 = no cap.
+        import os
+
+        self.nccl_ctas = int(os.environ.get("STCAT_NCCL_CTAS", os.environ.get("NCCL_MAX_CTAS", "24") or 0))
+        self._capped = False
 
     def prepare(self, model):
         """Observe the encoder's block inputs (call once, before the first forward)."""
@@ -144,6 +152,10 @@ class GradSync:
             self.stream.wait_stream(st)
         with torch.cuda.stream(self.stream):
             dist.all_reduce(chunk, op=dist.ReduceOp.AVG if self.average else dist.ReduceOp.SUM)
+        if self.nccl_ctas > 0 and not self._capped:
+            sms = torch.cuda.get_device_properties(chunk.device).multi_processor_count
+            ops.get_backend().set_sm_cap(max(sms - self.nccl_ctas, sms // 2))
+            self._capped = True
 
     def attach(self, out: dict):
         """Hook for one forward pass (``out`` = STCATHotPath's output dict): the decoder + heads range is complete
@@ -171,5 +183,8 @@ class GradSync:
         ops.join_leaf_streams()
         for name in list(self.flat.ranges):
             self._reduce(name)
+        if self._capped:
+            ops.get_backend().set_sm_cap(0)
+            self._capped = False
         if self.stream is not None:
             torch.cuda.current_stream().wait_stream(self.stream)

@@ -965,20 +965,10 @@ class FFNBlockFn(Function):
         be.linear_fwd(xo, w1o, b1.detach(), h, relu=True)
         if ctx.drop_h:
             be.dropout(h, h, *ctx.drop_h)
-        if bf and R <= 128 and F_ >= 1024 and F_ % 256 == 0 and F_ // 256 <= 12:
-            # few rows, long contraction (decoder / temporal FFN: [t, 2048] x [2048, 256]): one CTA per output tile would
-            # walk 32 k-blocks alone.  Split the contraction into 256-wide slices, one job each in ONE grouped launch
-            # (all slices run concurrently), and add the partial products in a fixed order: deterministic, unlike
-            # split-K with atomics.
-            nsp = F_ // 256
-            parts = torch.empty(nsp, R, d, dtype=torch.float32, device=x.device)
-            b2d = b2.detach()
-            be.linear_group(0, [dict(terms=[(h[:, s * 256:(s + 1) * 256], w2o[:, s * 256:(s + 1) * 256], b2d if s == 0 else None)],
-                                     out=parts[s]) for s in range(nsp)])
-            yl = parts.sum(0)
-        else:
-            yl = _new(R, d, torch.float32, x)
-            be.linear_fwd(h, w2o, b2.detach(), yl)
+        # (few rows, long contraction -- decoder / temporal FFN, [t, 2048] x [2048, 256]: the GEMM entry point splits the
+        # contraction over a thread-block cluster and sums the partial tiles in rank order, gemm_tcgen05.cu CLK)
+        yl = _new(R, d, torch.float32, x)
+        be.linear_fwd(h, w2o, b2.detach(), yl)
         if ctx.drop_out:
             be.dropout(yl, yl, *ctx.drop_out)
         y = _new(R, d, torch.float32, x)
@@ -1034,15 +1024,7 @@ class FFNBlockFn(Function):
             db1 = torch.zeros(F_, dtype=f32, device=dy.device)
             be.linear_bwd_data(dz_op, w2o, dh, relu_y=h, dbias=db1)
         dw1, _ = _wgrad(be, dh, xo, w1, None, True, False)
-        if bf and R <= 128 and F_ >= 1024 and F_ % 256 == 0 and F_ // 256 <= 12:
-            # same contraction split as the forward's linear2: dz += dh W1 as 256-wide slices of one grouped launch
-            nsp = F_ // 256
-            parts = torch.empty(nsp, R, d, dtype=f32, device=dy.device)
-            be.linear_group(1, [dict(terms=[(dh[:, s * 256:(s + 1) * 256], w1o[s * 256:(s + 1) * 256], None)], out=parts[s])
-                                for s in range(nsp)])
-            dz += parts.sum(0)
-        else:
-            be.linear_bwd_data(dh, w1o, dz, accumulate=True)
+        be.linear_bwd_data(dh, w1o, dz, accumulate=True)
         return dz, None, dw1, db1, dw2, db2, dg, dbt, None, None
 
 

@@ -381,6 +381,9 @@ class EmuBackend:
     def set_gemm_sm_limit(self, n):
         pass
 
+    def set_sm_cap(self, n):
+        pass
+
     def set_dropout_step(self, counter):
         pass
 
