@@ -140,17 +140,20 @@ class SpatialTemporalEncoder(nn.Module):
             if on_input is not None:
                 on_input(li, X)
             X, X_op = sp.run(X, X_op, POS, key_mask, n, S_len, pos_cls=pos_cls)
-            X3, cls = ops.take_rows(X.view(n, S_len, d), 0)  # frame-CLS rows (copy) + the stream itself
             if idx["identity"]:
-                Y = torch.cat([video_src, cls], 0)  # [(t+1), d]
+                # one un-padded video: the frame-CLS exchange with the temporal layer as two row-sized nodes
+                X3, Y = ops.cls_gather(X.view(n, S_len, d), video_src, 0)  # Y = [video token ; frame-CLS rows]
+                Y, _ = tp.run(Y, None, temp_pos, idx["temp_mask"], b, t + 1)
+                X3, video_src = ops.cls_scatter(X3, Y, 0)  # the reference's in-place row replacement (modal_encoder.py:191-195)
+                cls_new = Y.detach()[1:]
             else:
+                X3, cls = ops.take_rows(X.view(n, S_len, d), 0)  # frame-CLS rows (copy) + the stream itself
                 Y = torch.cat([video_src, cls, cls.new_zeros(1, d)], 0).index_select(0, idx["enc_gather"])
-            Y, _ = tp.run(Y, None, temp_pos, idx["temp_mask"], b, t + 1)
-            Y3 = Y.view(b, t + 1, d)
-            video_src = Y3[:, 0, :]
-            cls_new = Y3[0, 1:, :] if idx["identity"] else Y.index_select(0, idx["enc_scatter"])
-            # the reference's in-place row replacement (modal_encoder.py:191-195)
-            X = ops.put_rows(X3, cls_new, 0).view(n * S_len, d)
+                Y, _ = tp.run(Y, None, temp_pos, idx["temp_mask"], b, t + 1)
+                video_src = Y.view(b, t + 1, d)[:, 0, :]
+                cls_new = Y.index_select(0, idx["enc_scatter"])
+                X3 = ops.put_rows(X3, cls_new, 0)  # modal_encoder.py:191-195
+            X = X3.view(n * S_len, d)
             if X_op is not None:
                 X_op.view(n, S_len, d)[:, 0, :] = cls_new.detach()
         return X, video_src

@@ -866,6 +866,7 @@ class SelfAttnBlockFn(Function):
         ctx.set_materialize_grads(False)  # no full-size zero tensor for the non-differentiable y_op output
         ctx.save_for_backward(xd, xo, qk_in, qkv, o, lse, a, mean, rstd, key_mask, w_in, w_out, gamma)
         ctx.extra = (b_in, b_out, beta)
+        ctx.pos_cls = pos_cls
         ctx.dims = (B, L, H, scale)
         if bf:
             ctx.mark_non_differentiable(y_op)
@@ -930,10 +931,17 @@ class SelfAttnBlockFn(Function):
         if ctx.has_pos_cls and ctx.needs_input_grad[14]:
             # pos is constant except its row 0 of every sequence, which is the learned token `pos_cls` ([1, d]):
             # d pos_cls = (sum over sequences of dq,dk at row 0) . Wqk -- a [1, 512] x [512, 256] product instead of a
-            # full-size dpos GEMM, add and gradient accumulation per layer
-            srow = dqkv.view(B, L, 3 * d)[:, 0, : 2 * d].float().sum(0, keepdim=True)
-            dpc = torch.empty(1, d, dtype=f32, device=dy.device)
-            be.linear_bwd_data(srow, w_in.detach()[: 2 * d], dpc)
+            # full-size dpos GEMM, add and gradient accumulation per layer.  It is a leaf gradient: with the flat gradient
+            # buffer it is accumulated in place on the leaf stream, off the dependent chain of the backward pass.
+            pc = ctx.pos_cls
+            fused = _fuse_grads and pc is not None and pc.grad is not None and pc.grad.is_contiguous()
+            with _on_leaf(*([dqkv] if fused else [])):
+                srow = dqkv.view(B, L, 3 * d)[:, 0, : 2 * d].float().sum(0, keepdim=True)
+                if fused:
+                    be.linear_bwd_data(srow, w_in.detach()[: 2 * d], pc.grad.view(1, d), accumulate=True)
+                else:
+                    dpc = torch.empty(1, d, dtype=f32, device=dy.device)
+                    be.linear_bwd_data(srow, w_in.detach()[: 2 * d], dpc)
         return dz, None, dpos, None, dwi, dbi, dwo, dbo, dg, dbt, None, None, None, None, dpc, None
 
 
@@ -1081,6 +1089,62 @@ class PutRowsFn(Function):
         g_rows = g[:, ctx.r, :].clone()
         g[:, ctx.r, :] = 0  # g is the gradient tensor produced for this node by the next block's backward: ours to edit
         return g, g_rows, None
+
+
+class ClsGatherFn(Function):
+    """(x alias, Y) with Y = [video ; x[:, r, :]]: ``take_rows`` + ``torch.cat`` of the temporal layer's input for ONE
+    un-padded video (x [n, S, d], video [1, d] -> Y [1 + n, d]; modal_encoder.py:170-177).  Backward: the row gradient is
+    added onto the stream's gradient in place (row-sized), the video token's gradient is a view."""
+
+    @staticmethod
+    def forward(ctx, x, video, r: int):
+        ctx.r = r
+        ctx.set_materialize_grads(False)
+        xd = x.detach()
+        return xd, torch.cat([video.detach(), xd[:, r, :]], 0)
+
+    @staticmethod
+    def backward(ctx, g_base, g_y):
+        if g_base is None:
+            if g_y is None:
+                return None, None, None
+            raise RuntimeError("ClsGatherFn: the base output must be used (it carries the sequence's gradient)")
+        if g_y is None:
+            return g_base, None, None
+        g_base = g_base if g_base.is_contiguous() else g_base.contiguous()
+        g_base[:, ctx.r, :] += g_y[1:]  # g_base is ours: produced for this node alone by ClsScatterFn / the next block
+        return g_base, g_y[:1], None
+
+
+class ClsScatterFn(Function):
+    """x[:, r, :] = Y[1:] in place on x's storage, video' = Y[:1] (``put_rows`` + the two slices of the temporal layer's
+    output, modal_encoder.py:191-195).  Backward: one concatenation builds dY, the replaced rows of dx are zeroed in place."""
+
+    @staticmethod
+    def forward(ctx, x, y, r: int):
+        ctx.r = r
+        ctx.set_materialize_grads(False)
+        out, yd = x.detach(), y.detach()
+        out[:, r, :] = yd[1:]
+        return out, yd[:1]
+
+    @staticmethod
+    def backward(ctx, g, g_video):
+        if g is None:
+            raise RuntimeError("ClsScatterFn: the sequence output must be used")
+        g = g if g.is_contiguous() else g.contiguous()
+        gv = g_video if g_video is not None else g.new_zeros(1, g.shape[2])
+        g_y = torch.cat([gv, g[:, ctx.r, :]], 0)
+        g[:, ctx.r, :] = 0  # g is the gradient tensor produced for this node by the next block's backward: ours to edit
+        return g, g_y, None
+
+
+def cls_gather(x, video, r: int = 0):
+    return ClsGatherFn.apply(x, video, r)
+
+
+def cls_scatter(x, y, r: int = 0):
+    return ClsScatterFn.apply(x, y, r)
 
 
 def take_rows(x, r: int = 0):
