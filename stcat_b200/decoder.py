@@ -336,8 +336,11 @@ class TransformerDecoder(nn.Module):
                 if li != self.num_layers - 1:
                     refs.append(new_anchor)
                 anchor = new_anchor.detach()
-            inter.append(ops.layer_norm(out, None, self.norm.weight, self.norm.bias, self.norm.eps))
-        hs = torch.stack(inter).view(self.num_layers, c.b, c.t, d)
+            inter.append(out)
+        # the shared output norm of every layer's queries (query_decoder.py:222) as ONE launch over the stacked outputs, after
+        # the loop: it is not an input of the next layer, so it does not belong on the layers' dependent chain
+        hs = ops.layer_norm(torch.stack(inter).view(self.num_layers * c.b * c.t, d), None, self.norm.weight, self.norm.bias,
+                            self.norm.eps).view(self.num_layers, c.b, c.t, d)
         if self.bbox_embed is not None:
             ref = torch.stack(refs).view(len(refs), c.b, c.t, -1)
         else:
@@ -405,9 +408,12 @@ class TimeDecoder(nn.Module):
         qpf = c.frames(query_pos)
         for li, layer in enumerate(self.layers):
             out, out_op, w = layer.run(c, out, out_op, query_pos, qpf, qpt, mem_kv[li])
-            inter.append(ops.layer_norm(out, None, self.norm.weight, self.norm.bias, self.norm.eps))
+            inter.append(out)
             ws.append(w)
-        return torch.stack(inter).view(self.num_layers, c.b, c.t, self.d_model), torch.stack(ws)
+        # one launch for the shared output norm of all layers (query_decoder.py:527), off the layers' dependent chain
+        hs = ops.layer_norm(torch.stack(inter).view(self.num_layers * c.b * c.t, self.d_model), None, self.norm.weight,
+                            self.norm.bias, self.norm.eps)
+        return hs.view(self.num_layers, c.b, c.t, self.d_model), torch.stack(ws)
 
 
 class TemplateGenerator(nn.Module):
