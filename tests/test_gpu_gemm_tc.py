@@ -40,6 +40,11 @@ SHAPES = [
     (300, 104, 1024),     # cluster split-K with row / column tails (clusters of 8)
     (64, 2048, 256),      # bwd: dx[64, 256] = dy[64, 2048] . W: the FFN linear1 data gradient
     (129, 2048, 256),
+    # few rows, contraction <= 768: the low-latency mma.sync kernel of the dependent chains (csrc/gemm_small.cu)
+    (65, 256, 512),       # two 256-wide chunks (ref_point_head layer 1)
+    (17, 104, 72),        # tails in every dimension
+    (128, 2048, 256),     # 64 CTAs
+    (100, 768, 200),
 ]
 
 
