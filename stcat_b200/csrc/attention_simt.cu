@@ -421,10 +421,11 @@ int attn_small_bwd(int dtype, const void* q, int64_t ldq, const void* k, int64_t
 // attention_small_mma.cu: the same short sequences for bf16 operands on mma.sync tensor cores
 int attn_mma_supported(int dtype, const void* q2, int B, int H, int Lq, int Lk, const void* const* ptrs, const int64_t* lds, int n);
 int attn_mma_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
-                 const uint8_t* key_mask, float* lse, float* p_avg, int B, int H, int Lq, int Lk, float scale, cudaStream_t st);
+                 const uint8_t* key_mask, float* lse, float* p_avg, int B, int H, int Lq, int Lk, float scale, cudaStream_t st,
+                 const DropArgs& drop);
 int attn_mma_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o, int64_t lddo,
                  const uint8_t* key_mask, const float* lse, const float* dp_avg, void* dq, int64_t lddq, void* dk, int64_t lddk,
-                 void* dv, int64_t lddv, int B, int H, int Lq, int Lk, float scale, cudaStream_t st);
+                 void* dv, int64_t lddv, int B, int H, int Lq, int Lk, float scale, cudaStream_t st, const DropArgs& drop);
 
 // attention_sq.cu: single-query (Lq = 1) kernels for the decoders' time-aligned cross attention
 int attn_sq_supported(int dtype, int Lq, int Lk, const void* p_avg, const void* dp_avg, const void* const* ptrs,
@@ -476,7 +477,7 @@ extern "C" int stcat_debug_attn_counts(long long* out5) {
 }
 
 // Kernel selection shared by the plain and the dropout entry points.  With dropout (drop.thresh != 0) the single-query,
-// tcgen05 and generic kernels apply the counter-based mask of common.cuh; the short-sequence kernels have no dropout.
+// tcgen05, mma.sync and generic kernels apply the counter-based mask of common.cuh; the fp32 shared-memory kernel has none.
 static int attention_fwd_impl(const char* who, const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2,
                               int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo, int dtype, const uint8_t* key_mask,
                               float* lse, float* p_avg, int B, int H, int Lq, int Lk, int dh, float scale, void* stream,
@@ -498,11 +499,11 @@ static int attention_fwd_impl(const char* who, const void* q1, const void* q2, i
     }
     if (attn_tc_fwd_supported(dtype, q2, p_avg, B, H, Lq, Lk, q1, k1, v, o, ldq, ldk, ldv, ldo))
         return ++g_attn_counts[1], attn_tc_fwd(q1, ldq, k1, ldk, v, ldv, o, ldo, key_mask, lse, B, H, Lq, scale, st, drop);
-    if (nodrop) {
+    {
         const void* ptrs[4] = {q1, k1, v, o};
         const int64_t lds[4] = {ldq, ldk, ldv, ldo};
         if (attn_mma_supported(dtype, q2, B, H, Lq, Lk, ptrs, lds, 4))
-            return ++g_attn_counts[2], attn_mma_fwd(q1, ldq, k1, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st);
+            return ++g_attn_counts[2], attn_mma_fwd(q1, ldq, k1, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st, drop);
     }
     if (nodrop && attn_small_supported(q2, B, H, Lq, Lk))
         return ++g_attn_counts[3], attn_small_fwd(dtype, q1, ldq, k1, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st);
@@ -540,12 +541,12 @@ static int attention_bwd_impl(const char* who, const void* q1, const void* q2, i
                               lddq, lddk, lddv))
         return ++g_attn_counts[1], attn_tc_bwd(q1, ldq, k1, ldk, v, ldv, o, ldo, d_o, lddo, key_mask, lse, dq1, lddq, dk1, lddk, dv, lddv, B, H,
                            Lq, scale, st, drop);
-    if (nodrop) {
+    {
         const void* ptrs[7] = {q1, k1, v, d_o, dq1, dk1, dv};
         const int64_t lds[7] = {ldq, ldk, ldv, lddo, lddq, lddk, lddv};
         if (attn_mma_supported(dtype, q2, B, H, Lq, Lk, ptrs, lds, 7))
             return ++g_attn_counts[2], attn_mma_bwd(q1, ldq, k1, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, dq1, lddq, dk1, lddk, dv, lddv, B, H,
-                                Lq, Lk, scale, st);
+                                Lq, Lk, scale, st, drop);
     }
     if (nodrop && attn_small_supported(q2, B, H, Lq, Lk))
         return ++g_attn_counts[3], attn_small_bwd(dtype, q1, ldq, k1, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, dq1, lddq, dk1, lddk, dv, lddv,

@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(256)
 attn_mma_fwd_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k, int64_t ldk,
                     const __nv_bfloat16* __restrict__ v, int64_t ldv, __nv_bfloat16* __restrict__ o, int64_t ldo,
                     const uint8_t* __restrict__ key_mask, float* __restrict__ lse, float* __restrict__ p_avg, int H, int Lq,
-                    int Lk, float scale) {
+                    int Lk, float scale, const DropArgs drop_in) {
+    const DropArgs drop = drop_resolve(drop_in);
     extern __shared__ __align__(16) uint8_t mm_smem[];
     pdl_launch_dependents();
     pdl_wait();
@@ -135,6 +136,16 @@ attn_mma_fwd_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
         s[j][0] *= inv0; s[j][1] *= inv0; s[j][2] *= inv1; s[j][3] *= inv1;
+        if (drop.thresh) {
+            // train-mode dropout on the normalised probabilities, element (b, h, i, j) of [B, H, Lq, Lk] (the same counter-based
+            // mask as every other attention kernel): the head-averaged weights and P V both see the dropped values, like torch
+            const int c = j * 8 + 2 * t;
+            const uint64_t r0 = (((uint64_t)b * H + h) * Lq + i0) * (uint64_t)Lk, r1 = (((uint64_t)b * H + h) * Lq + i1) * (uint64_t)Lk;
+            if (i0 < Lq && c < Lk) s[j][0] = drop_apply(drop, r0 + c, s[j][0]);
+            if (i0 < Lq && c + 1 < Lk) s[j][1] = drop_apply(drop, r0 + c + 1, s[j][1]);
+            if (i1 < Lq && c < Lk) s[j][2] = drop_apply(drop, r1 + c, s[j][2]);
+            if (i1 < Lq && c + 1 < Lk) s[j][3] = drop_apply(drop, r1 + c + 1, s[j][3]);
+        }
         if (p_avg) {
             const int c = j * 8 + 2 * t;
             if (i0 < Lq && c < Lk) atomicAdd(p_avg + ((int64_t)b * Lq + i0) * Lk + c, s[j][0] * invH);
@@ -176,7 +187,8 @@ attn_mma_bwd_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv
                     const __nv_bfloat16* __restrict__ v, int64_t ldv, const __nv_bfloat16* __restrict__ d_o, int64_t lddo,
                     const uint8_t* __restrict__ key_mask, const float* __restrict__ lse, const float* __restrict__ dp_avg,
                     __nv_bfloat16* __restrict__ dq, int64_t lddq, __nv_bfloat16* __restrict__ dk, int64_t lddk,
-                    __nv_bfloat16* __restrict__ dv, int64_t lddv, int H, int Lq, int Lk, float scale) {
+                    __nv_bfloat16* __restrict__ dv, int64_t lddv, int H, int Lq, int Lk, float scale, const DropArgs drop_in) {
+    const DropArgs drop = drop_resolve(drop_in);
     extern __shared__ __align__(16) uint8_t mm_smem[];
     pdl_launch_dependents();
     pdl_wait();
@@ -246,6 +258,13 @@ attn_mma_bwd_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv
                     if (!d10) dp[j][2] += dp_avg[((int64_t)b * Lq + i1) * Lk + c] * invH;
                     if (!d11) dp[j][3] += dp_avg[((int64_t)b * Lq + i1) * Lk + c + 1] * invH;
                 }
+                if (drop.thresh) {  // o (and the weights output) were formed from the DROPPED probabilities: dP passes the mask
+                    const uint64_t r0 = (((uint64_t)b * H + h) * Lq + i0) * (uint64_t)Lk, r1 = (((uint64_t)b * H + h) * Lq + i1) * (uint64_t)Lk;
+                    if (!d00) dp[j][0] = drop_apply(drop, r0 + c, dp[j][0]);
+                    if (!d01) dp[j][1] = drop_apply(drop, r0 + c + 1, dp[j][1]);
+                    if (!d10) dp[j][2] = drop_apply(drop, r1 + c, dp[j][2]);
+                    if (!d11) dp[j][3] = drop_apply(drop, r1 + c + 1, dp[j][3]);
+                }
                 D0 += s[j][0] * dp[j][0] + s[j][1] * dp[j][1];
                 D1 += s[j][2] * dp[j][2] + s[j][3] * dp[j][3];
             }
@@ -256,6 +275,13 @@ attn_mma_bwd_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv
                 dp[j][0] = s[j][0] * (dp[j][0] - D0) * scale; dp[j][1] = s[j][1] * (dp[j][1] - D0) * scale;
                 dp[j][2] = s[j][2] * (dp[j][2] - D1) * scale; dp[j][3] = s[j][3] * (dp[j][3] - D1) * scale;
                 const int c = j * 8 + 2 * t;
+                if (drop.thresh) {  // dV = Pm^T dO with Pm the dropped probabilities (what multiplied V in the forward)
+                    const uint64_t r0 = (((uint64_t)b * H + h) * Lq + i0) * (uint64_t)Lk, r1 = (((uint64_t)b * H + h) * Lq + i1) * (uint64_t)Lk;
+                    if (s[j][0] != 0.f) s[j][0] = drop_apply(drop, r0 + c, s[j][0]);
+                    if (s[j][1] != 0.f) s[j][1] = drop_apply(drop, r0 + c + 1, s[j][1]);
+                    if (s[j][2] != 0.f) s[j][2] = drop_apply(drop, r1 + c, s[j][2]);
+                    if (s[j][3] != 0.f) s[j][3] = drop_apply(drop, r1 + c + 1, s[j][3]);
+                }
                 PT[c * PQ + i0] = __float2bfloat16_rn(s[j][0]); PT[(c + 1) * PQ + i0] = __float2bfloat16_rn(s[j][1]);
                 PT[c * PQ + i1] = __float2bfloat16_rn(s[j][2]); PT[(c + 1) * PQ + i1] = __float2bfloat16_rn(s[j][3]);
                 dST[c * PQ + i0] = __float2bfloat16_rn(dp[j][0]); dST[(c + 1) * PQ + i0] = __float2bfloat16_rn(dp[j][1]);
@@ -345,7 +371,8 @@ int attn_mma_supported(int dtype, const void* q2, int B, int H, int Lq, int Lk, 
 
 template <int NT>
 static int mma_fwd_launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
-                          const uint8_t* key_mask, float* lse, float* p_avg, int B, int H, int Lq, int Lk, float scale, cudaStream_t st) {
+                          const uint8_t* key_mask, float* lse, float* p_avg, int B, int H, int Lq, int Lk, float scale, cudaStream_t st,
+                          const DropArgs& drop) {
     const size_t smem = mma_fwd_bytes(Lq, NT * 8);
     static bool attr = false;
     if (!attr) {
@@ -356,7 +383,7 @@ static int mma_fwd_launch(const void* q, int64_t ldq, const void* k, int64_t ldk
     const int warps = ((Lq + 15) / 16);
     cudaError_t le = launch_pdl(attn_mma_fwd_kernel<NT>, dim3(H, B), dim3(warps * 32), smem, st, (const __nv_bfloat16*)q, ldq,
                                 (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv, (__nv_bfloat16*)o, ldo, key_mask, lse, p_avg, H,
-                                Lq, Lk, scale);
+                                Lq, Lk, scale, drop);
     if (le != cudaSuccess) return set_err((int)le, "attn_mma_fwd launch: %s", cudaGetErrorString(le));
     return check_launch("attn_mma_fwd_kernel");
 }
@@ -364,7 +391,8 @@ static int mma_fwd_launch(const void* q, int64_t ldq, const void* k, int64_t ldk
 template <int NT>
 static int mma_bwd_launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
                           int64_t lddo, const uint8_t* key_mask, const float* lse, const float* dp_avg, void* dq, int64_t lddq,
-                          void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int Lq, int Lk, float scale, cudaStream_t st) {
+                          void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int Lq, int Lk, float scale, cudaStream_t st,
+                          const DropArgs& drop) {
     const size_t smem = mma_bwd_bytes(Lq, NT * 8);
     static bool attr = false;
     if (!attr) {
@@ -376,7 +404,7 @@ static int mma_bwd_launch(const void* q, int64_t ldq, const void* k, int64_t ldk
     const int warps = ((lmax + 15) / 16);
     cudaError_t le = launch_pdl(attn_mma_bwd_kernel<NT>, dim3(H, B), dim3(warps * 32), smem, st, (const __nv_bfloat16*)q, ldq,
                                 (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv, (const __nv_bfloat16*)d_o, lddo, key_mask, lse,
-                                dp_avg, (__nv_bfloat16*)dq, lddq, (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv, lddv, H, Lq, Lk, scale);
+                                dp_avg, (__nv_bfloat16*)dq, lddq, (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv, lddv, H, Lq, Lk, scale, drop);
     if (le != cudaSuccess) return set_err((int)le, "attn_mma_bwd launch: %s", cudaGetErrorString(le));
     return check_launch("attn_mma_bwd_kernel");
 }
@@ -394,15 +422,16 @@ static int mma_bwd_launch(const void* q, int64_t ldq, const void* k, int64_t ldk
     }
 
 int attn_mma_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
-                 const uint8_t* key_mask, float* lse, float* p_avg, int B, int H, int Lq, int Lk, float scale, cudaStream_t st) {
-    STCAT_MMA_DISPATCH(mma_fwd_launch, q, ldq, k, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st)
+                 const uint8_t* key_mask, float* lse, float* p_avg, int B, int H, int Lq, int Lk, float scale, cudaStream_t st,
+                 const DropArgs& drop) {
+    STCAT_MMA_DISPATCH(mma_fwd_launch, q, ldq, k, ldk, v, ldv, o, ldo, key_mask, lse, p_avg, B, H, Lq, Lk, scale, st, drop)
 }
 
 int attn_mma_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o, int64_t lddo,
                  const uint8_t* key_mask, const float* lse, const float* dp_avg, void* dq, int64_t lddq, void* dk, int64_t lddk,
-                 void* dv, int64_t lddv, int B, int H, int Lq, int Lk, float scale, cudaStream_t st) {
+                 void* dv, int64_t lddv, int B, int H, int Lq, int Lk, float scale, cudaStream_t st, const DropArgs& drop) {
     STCAT_MMA_DISPATCH(mma_bwd_launch, q, ldq, k, ldk, v, ldv, d_o, lddo, key_mask, lse, dp_avg, dq, lddq, dk, lddk, dv, lddv, B, H,
-                       Lq, Lk, scale, st)
+                       Lq, Lk, scale, st, drop)
 }
 
 }  // namespace stcat
