@@ -41,7 +41,7 @@ extern "C" {
 
 /* Bumped whenever a signature or the meaning of an argument changes; stcat_b200/cabi.py refuses a library whose version
  * differs from the one it was written against (a stale locally built .so would otherwise be called with new signatures). */
-#define STCAT_ABI_VERSION 7
+#define STCAT_ABI_VERSION 8
 STCAT_API int stcat_abi_version(void);
 STCAT_API const char* stcat_last_error(void);
 /* compute capability major*10+minor of the current device, or <0; 100 expected */
@@ -124,6 +124,17 @@ STCAT_API int stcat_layernorm_fwd(const float* x, const float* res, const float*
 STCAT_API int stcat_layernorm_bwd(const float* dy, const float* x, const float* res, const float* gamma, const float* mean,
                         const float* rstd, float* dz, void* dz_bf16, float* dgamma, float* dbeta, float* dbias, int rows,
                         int d, void* stream);
+/* The same pair with train-mode dropout on x folded in (the `dropout1/3/4(block output)` in front of every residual + norm of the
+ * reference, modal_encoder.py:237-241; query_decoder.py:344,431-437,612,653-659): y = LayerNorm(drop(x) + res), element index of
+ * the mask = row * d + column, (p, seed, offset) as in stcat_dropout below.  Backward: dz = gradient w.r.t. drop(x) + res (what
+ * the residual branch receives, unmasked); dz_bf16 and dbias receive mask(dz), the gradient w.r.t. x (operand copy / bias
+ * gradient of the Linear that produced x).  Replaces a separate dropout pass over x forward and over dz backward. */
+STCAT_API int stcat_layernorm_dropout_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y,
+                        void* y_bf16, float* mean, float* rstd, int rows, int d, float eps, float p, uint64_t seed,
+                        uint64_t offset, void* stream);
+STCAT_API int stcat_layernorm_dropout_bwd(const float* dy, const float* x, const float* res, const float* gamma, const float* mean,
+                        const float* rstd, float* dz, void* dz_bf16, float* dgamma, float* dbeta, float* dbias, int rows,
+                        int d, float p, uint64_t seed, uint64_t offset, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-head attention core, batch-major (torch functional.py:6630-6665 bmm/softmax/bmm; reference
@@ -154,14 +165,16 @@ STCAT_API int stcat_attention_bwd(const void* q1, const void* q2, int64_t ldq, c
 
 /* Train-mode dropout (nn.Dropout / F.dropout sites: modal_encoder.py:237-240; query_decoder.py:344,431-436,612,653-658;
  * attention.py:381; nn.MultiheadAttention(dropout=p)).  Counter-based and stateless: element idx of a site that drew
- * (seed, offset) is kept iff the top 24 bits of splitmix64(offset + idx + seed * 0x9E3779B97F4A7C15) are >= p * 2^24, and
+ * (seed, offset) is kept iff bits24(offset + idx + seed * 0x9E3779B97F4A7C15) >= p * 2^24 (bits24: the 64-bit counter folded to
+ * 32 bits, lo ^ hi * 0x9E3779B1, then the multiply-xorshift mixer x ^= x>>16; x *= 0x21f0aaad; x ^= x>>15; x *= 0x735a2d97;
+ * x ^= x>>15; top 24 bits -- stcat_b200/csrc/common.cuh drop_bits24), and
  * kept values are scaled by 1 / (keep probability).  The backward of a site is the same call on the gradient.
  *   stcat_dropout               : out[i] = keep(i) ? x[i] * scale : 0   (fp32 or bf16, in place allowed)
  *   stcat_attention_dropout_fwd : stcat_attention_fwd with dropout on the normalised probabilities, element index
  *                                 ((b*H + h)*Lq + i)*Lk + j; p_avg is the head average of the DROPPED probabilities
  *   stcat_attention_dropout_bwd : its backward (same seed / offset; `o` = the forward output, optional like stcat_attention_bwd's)
- * Kernel selection: the single-query and tcgen05 kernels apply the same mask for their shape classes, everything else runs
- * the generic SIMT kernels (the short-sequence kernels have no dropout yet). */
+ * Kernel selection: the single-query, tcgen05 and mma.sync kernels apply the same mask for their shape classes, everything
+ * else runs the generic SIMT kernels. */
 STCAT_API int stcat_dropout(const void* x, void* out, int dtype, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
 /* Optional device-resident step counter (one uint64 in device memory, NULL = off, the default) that every dropout site --
  * stcat_dropout and the attention dropout entry points -- mixes into its seed when the kernel RUNS (not when it is

@@ -55,6 +55,8 @@ class _Job(ctypes.Structure):
 
 _U64 = ctypes.c_uint64
 SIGNATURES["stcat_dropout"] = (c_int, [_P, _P, _I, _L, _F, _U64, _U64, _P])
+SIGNATURES["stcat_layernorm_dropout_fwd"] = (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _U64, _U64, _P])
+SIGNATURES["stcat_layernorm_dropout_bwd"] = (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _U64, _U64, _P])
 SIGNATURES["stcat_attention_dropout_fwd"] = (c_int, [_P, _P, _L, _P, _P, _L, _P, _L, _P, _L, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F,
                                                      _F, _U64, _U64, _P])
 SIGNATURES["stcat_attention_dropout_bwd"] = (c_int, [_P, _P, _L, _P, _P, _L, _P, _L, _P, _L, _P, _L, _I, _P, _P, _P, _P, _P, _P, _L,
@@ -76,7 +78,7 @@ SIGNATURES["stcat_box_refine_bwd"] = (c_int, [_P, _P, _P, _P, _P, _L, _F, _P])
 SIGNATURES["stcat_stg_loss"] = (c_int, [_P] * 12 + [ctypes.POINTER(c_float), _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P])
 SIGNATURES["stcat_linear_group"] = (c_int, [_I, _I, ctypes.POINTER(_Job), _I, _P])
 MAX_GROUP_JOBS = 12
-ABI_VERSION = 7  # include/stcat_b200.h STCAT_ABI_VERSION
+ABI_VERSION = 8  # include/stcat_b200.h STCAT_ABI_VERSION
 
 _lib = None
 
@@ -249,26 +251,32 @@ class CudaBackend:
         self.launches += 1 + (kind == 2 and any(j.get("dbias") is not None for j in jobs))
 
     # -- layernorm -----------------------------------------------------
-    def layernorm_fwd(self, x, res, gamma, beta, y, y_bf16, mean, rstd, eps=1e-5):
+    def layernorm_fwd(self, x, res, gamma, beta, y, y_bf16, mean, rstd, eps=1e-5, drop=None):
+        """``drop`` = (p, seed, offset): train-mode dropout on x folded into the kernel (stcat_layernorm_dropout_fwd)"""
         rows, d = x.shape
         f = torch.float32
-        self._rc(self.lib.stcat_layernorm_fwd(self._flat(x, "x", f), self._flat(res, "res", f), self._flat(gamma, "gamma", f),
-                                              self._flat(beta, "beta", f), self._flat(y, "y", f),
-                                              self._flat(y_bf16, "y_bf16", torch.bfloat16), self._flat(mean, "mean", f),
-                                              self._flat(rstd, "rstd", f), rows, d, float(eps), self._stream()),
-                 "layernorm_fwd")
+        args = (self._flat(x, "x", f), self._flat(res, "res", f), self._flat(gamma, "gamma", f), self._flat(beta, "beta", f),
+                self._flat(y, "y", f), self._flat(y_bf16, "y_bf16", torch.bfloat16), self._flat(mean, "mean", f),
+                self._flat(rstd, "rstd", f), rows, d, float(eps))
+        if drop is not None and drop[0] > 0:
+            self._rc(self.lib.stcat_layernorm_dropout_fwd(*args, float(drop[0]), int(drop[1]), int(drop[2]), self._stream()),
+                     "layernorm_dropout_fwd")
+        else:
+            self._rc(self.lib.stcat_layernorm_fwd(*args, self._stream()), "layernorm_fwd")
         self.launches += 1
 
-    def layernorm_bwd(self, dy, x, res, gamma, mean, rstd, dz, dgamma, dbeta, dz_bf16=None, dbias=None):
+    def layernorm_bwd(self, dy, x, res, gamma, mean, rstd, dz, dgamma, dbeta, dz_bf16=None, dbias=None, drop=None):
         rows, d = x.shape
         f = torch.float32
-        self._rc(self.lib.stcat_layernorm_bwd(self._flat(dy, "dy", f), self._flat(x, "x", f), self._flat(res, "res", f),
-                                              self._flat(gamma, "gamma", f), self._flat(mean, "mean", f),
-                                              self._flat(rstd, "rstd", f), self._flat(dz, "dz", f),
-                                              self._flat(dz_bf16, "dz_bf16", torch.bfloat16),
-                                              self._flat(dgamma, "dgamma", f), self._flat(dbeta, "dbeta", f),
-                                              self._flat(dbias, "dbias", f), rows, d,
-                                              self._stream()), "layernorm_bwd")
+        args = (self._flat(dy, "dy", f), self._flat(x, "x", f), self._flat(res, "res", f), self._flat(gamma, "gamma", f),
+                self._flat(mean, "mean", f), self._flat(rstd, "rstd", f), self._flat(dz, "dz", f),
+                self._flat(dz_bf16, "dz_bf16", torch.bfloat16), self._flat(dgamma, "dgamma", f), self._flat(dbeta, "dbeta", f),
+                self._flat(dbias, "dbias", f), rows, d)
+        if drop is not None and drop[0] > 0:
+            self._rc(self.lib.stcat_layernorm_dropout_bwd(*args, float(drop[0]), int(drop[1]), int(drop[2]), self._stream()),
+                     "layernorm_dropout_bwd")
+        else:
+            self._rc(self.lib.stcat_layernorm_bwd(*args, self._stream()), "layernorm_bwd")
         self.launches += 1
 
     # -- attention -----------------------------------------------------

@@ -84,15 +84,22 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 // ---- train-mode dropout (nn.Dropout / F.dropout sites of the reference, modal_encoder.py:237-240, query_decoder.py:344,
 // 431-436, 612, 653-658, attention.py:381) ---------------------------------------------------------------------------
-// Counter-based: element `idx` of a site whose forward drew (seed, offset) is kept iff the top 24 bits of
-// splitmix64(offset + idx + seed * golden) are >= thresh = p * 2^24.  Stateless, so the backward regenerates the mask of
-// the forward from the same (seed, offset) -- no mask tensors in HBM.  tests/emu_backend.py restates it bit for bit.
+// Counter-based: element `idx` of a site whose forward drew (seed, offset) is kept iff drop_bits24(seed, offset + idx)
+// >= thresh = p * 2^24.  Stateless, so the backward regenerates the mask of the forward from the same (seed, offset) -- no
+// mask tensors in HBM.  tests/emu_backend.py restates it bit for bit.
+// The hash: z = idx + seed * golden (64-bit counter), folded to 32 bits (lo ^ hi * 0x9E3779B1) and finished with a 32-bit
+// multiply-xorshift mixer (hash-prospector "lowbias32" family: 16 / 0x21f0aaad / 15 / 0x735a2d97 / 15): ~10 integer
+// instructions per element.  Round 1 used a full splitmix64 (two 64-bit multiplies, ~25 instructions), which made the
+// dropout instantiations of the tcgen05 attention kernels ALU-bound on the hash (forward 21 -> 55 us at T = 64 / S = 213).
 __host__ __device__ __forceinline__ uint32_t drop_bits24(uint64_t seed, uint64_t idx) {
-    uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z = z ^ (z >> 31);
-    return (uint32_t)(z >> 40);
+    const uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull;
+    uint32_t x = (uint32_t)z ^ ((uint32_t)(z >> 32) * 0x9E3779B1u);
+    x ^= x >> 16;
+    x *= 0x21f0aaadu;
+    x ^= x >> 15;
+    x *= 0x735a2d97u;
+    x ^= x >> 15;
+    return x >> 8;
 }
 struct DropArgs {            // thresh == 0: no dropout
     uint32_t thresh = 0;

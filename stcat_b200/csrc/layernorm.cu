@@ -25,7 +25,8 @@ __device__ __forceinline__ void store_row(float* __restrict__ p, int lane, const
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16,
-                     float* __restrict__ mean, float* __restrict__ rstd, int rows, float eps) {
+                     float* __restrict__ mean, float* __restrict__ rstd, int rows, float eps, const DropArgs drop_in) {
+    const DropArgs drop = drop_resolve(drop_in);
     pdl_launch_dependents();
     pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -35,6 +36,11 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ res,
     for (int row = blockIdx.x * LN_ROWS_PER_BLOCK + warp; row < rows; row += gridDim.x * LN_ROWS_PER_BLOCK) {
         float z[8];
         load_row(x + (int64_t)row * LN_D, lane, z);
+        if (drop.thresh) {  // train-mode dropout on x (the block output in front of the residual), element index row * d + col
+            const uint64_t e0 = (uint64_t)row * LN_D + lane * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { z[i] = drop_apply(drop, e0 + i, z[i]); z[4 + i] = drop_apply(drop, e0 + 128 + i, z[4 + i]); }
+        }
         if (res) {
             float r[8];
             load_row(res + (int64_t)row * LN_D, lane, r);
@@ -69,7 +75,8 @@ __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ res,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                      float* __restrict__ dz, __nv_bfloat16* __restrict__ dz_bf16, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta, float* __restrict__ dbias, int rows) {
+                     float* __restrict__ dbeta, float* __restrict__ dbias, int rows, const DropArgs drop_in) {
+    const DropArgs drop = drop_resolve(drop_in);
     __shared__ float sg[LN_ROWS_PER_BLOCK][LN_D];
     __shared__ float sb[LN_ROWS_PER_BLOCK][LN_D];
     __shared__ float sz[LN_ROWS_PER_BLOCK][LN_D];
@@ -82,8 +89,17 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 #pragma unroll
     for (int i = 0; i < 8; ++i) { ag[i] = 0.f; ab[i] = 0.f; az[i] = 0.f; }
     for (int row = blockIdx.x * LN_ROWS_PER_BLOCK + warp; row < rows; row += gridDim.x * LN_ROWS_PER_BLOCK) {
-        float z[8], d[8];
+        float z[8], d[8], mk[8];
         load_row(x + (int64_t)row * LN_D, lane, z);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mk[i] = 1.f;
+        if (drop.thresh) {  // the forward normalised drop(x) + res: the same mask gates the gradient that reaches x
+            const uint64_t e0 = (uint64_t)row * LN_D + lane * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { mk[i] = drop_mult(drop, e0 + i); mk[4 + i] = drop_mult(drop, e0 + 128 + i); }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z[i] *= mk[i];
+        }
         if (res) {
             float r[8];
             load_row(res + (int64_t)row * LN_D, lane, r);
@@ -107,8 +123,10 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
         s2 = warp_sum(s2) * (1.f / LN_D);
         float o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { o[i] = rs * (dg[i] - s1 - xh[i] * s2); az[i] += o[i]; }
-        store_row(dz + (int64_t)row * LN_D, lane, o);
+        for (int i = 0; i < 8; ++i) o[i] = rs * (dg[i] - s1 - xh[i] * s2);
+        store_row(dz + (int64_t)row * LN_D, lane, o);  // gradient w.r.t. (drop(x) + res): what the residual branch receives
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { o[i] *= mk[i]; az[i] += o[i]; }  // gradient w.r.t. x: operand copy and bias column sums
         if (dz_bf16) {  // GEMM-operand copy for the dgrad / wgrad that consume dz next
             __nv_bfloat16* zb = dz_bf16 + (int64_t)row * LN_D;
             __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
@@ -139,8 +157,8 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 
 using namespace stcat;
 
-extern "C" int stcat_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y,
-                                   void* y_bf16, float* mean, float* rstd, int rows, int d, float eps, void* stream) {
+static int ln_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y, void* y_bf16, float* mean,
+                  float* rstd, int rows, int d, float eps, const DropArgs& drop, void* stream) {
     STCAT_REQUIRE(x && gamma && beta && y && mean && rstd, STCAT_EINVAL, "layernorm_fwd: null pointer");
     STCAT_REQUIRE(d == LN_D, STCAT_ESHAPE, "layernorm_fwd: d=%d unsupported (HIDDEN must be 256)", d);
     STCAT_REQUIRE(rows >= 0, STCAT_EINVAL, "layernorm_fwd: rows=%d", rows);
@@ -149,13 +167,25 @@ extern "C" int stcat_layernorm_fwd(const float* x, const float* res, const float
     int cap = num_sms() * 8;
     if (blocks > cap) blocks = cap;
     launch_pdl(layernorm_fwd_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, res, gamma, beta, y, (__nv_bfloat16*)y_bf16, mean,
-               rstd, rows, eps);
+               rstd, rows, eps, drop);
     return check_launch("layernorm_fwd_kernel");
 }
 
-extern "C" int stcat_layernorm_bwd(const float* dy, const float* x, const float* res, const float* gamma,
-                                   const float* mean, const float* rstd, float* dz, void* dz_bf16, float* dgamma,
-                                   float* dbeta, float* dbias, int rows, int d, void* stream) {
+extern "C" int stcat_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y,
+                                   void* y_bf16, float* mean, float* rstd, int rows, int d, float eps, void* stream) {
+    return ln_fwd(x, res, gamma, beta, y, y_bf16, mean, rstd, rows, d, eps, DropArgs(), stream);
+}
+
+extern "C" int stcat_layernorm_dropout_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y,
+                                           void* y_bf16, float* mean, float* rstd, int rows, int d, float eps, float p,
+                                           uint64_t seed, uint64_t offset, void* stream) {
+    STCAT_REQUIRE(p >= 0.f && p < 1.f, STCAT_EINVAL, "layernorm_dropout_fwd: p=%f", (double)p);
+    return ln_fwd(x, res, gamma, beta, y, y_bf16, mean, rstd, rows, d, eps, make_drop(p, seed, offset), stream);
+}
+
+static int ln_bwd(const float* dy, const float* x, const float* res, const float* gamma, const float* mean, const float* rstd,
+                  float* dz, void* dz_bf16, float* dgamma, float* dbeta, float* dbias, int rows, int d, const DropArgs& drop,
+                  void* stream) {
     STCAT_REQUIRE(dy && x && gamma && mean && rstd && dz && dgamma && dbeta, STCAT_EINVAL, "layernorm_bwd: null pointer");
     STCAT_REQUIRE(d == LN_D, STCAT_ESHAPE, "layernorm_bwd: d=%d unsupported (HIDDEN must be 256)", d);
     if (rows <= 0) return rows == 0 ? 0 : set_err(STCAT_EINVAL, "layernorm_bwd: rows=%d", rows);
@@ -163,6 +193,20 @@ extern "C" int stcat_layernorm_bwd(const float* dy, const float* x, const float*
     int cap = num_sms() * 2;
     if (blocks > cap) blocks = cap;
     launch_pdl(layernorm_bwd_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, dy, x, res, gamma, mean, rstd, dz,
-               (__nv_bfloat16*)dz_bf16, dgamma, dbeta, dbias, rows);
+               (__nv_bfloat16*)dz_bf16, dgamma, dbeta, dbias, rows, drop);
     return check_launch("layernorm_bwd_kernel");
+}
+
+extern "C" int stcat_layernorm_bwd(const float* dy, const float* x, const float* res, const float* gamma,
+                                   const float* mean, const float* rstd, float* dz, void* dz_bf16, float* dgamma,
+                                   float* dbeta, float* dbias, int rows, int d, void* stream) {
+    return ln_bwd(dy, x, res, gamma, mean, rstd, dz, dz_bf16, dgamma, dbeta, dbias, rows, d, DropArgs(), stream);
+}
+
+extern "C" int stcat_layernorm_dropout_bwd(const float* dy, const float* x, const float* res, const float* gamma,
+                                           const float* mean, const float* rstd, float* dz, void* dz_bf16, float* dgamma,
+                                           float* dbeta, float* dbias, int rows, int d, float p, uint64_t seed,
+                                           uint64_t offset, void* stream) {
+    STCAT_REQUIRE(p >= 0.f && p < 1.f, STCAT_EINVAL, "layernorm_dropout_bwd: p=%f", (double)p);
+    return ln_bwd(dy, x, res, gamma, mean, rstd, dz, dz_bf16, dgamma, dbeta, dbias, rows, d, make_drop(p, seed, offset), stream);
 }

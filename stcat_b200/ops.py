@@ -122,7 +122,7 @@ def _wgrad(be, dyo, xo, W, b, need_w, need_b, r0=None, r1=None):
     return dw, db
 
 
-def _ln_bwd(be, dy, x, res, gamma, beta, mean, rstd, dz, dz_op=None, lin_bias=None):
+def _ln_bwd(be, dy, x, res, gamma, beta, mean, rstd, dz, dz_op=None, lin_bias=None, drop=None):
     """LayerNorm backward; returns (dgamma, dbeta, dbias) for autograd, each None when it was accumulated into
     .grad.  ``dz_op`` (bf16 [rows, d]) receives the GEMM-operand copy of dz; ``lin_bias`` is the bias parameter of
     the Linear whose output is ``x``: its gradient is colsum(dz), which the kernel sums anyway."""
@@ -131,12 +131,12 @@ def _ln_bwd(be, dy, x, res, gamma, beta, mean, rstd, dz, dz_op=None, lin_bias=No
         (lin_bias is None or lin_bias.grad is not None)
     if fused:
         be.layernorm_bwd(dy, x, res, gamma.detach(), mean, rstd, dz, gamma.grad, beta.grad, dz_bf16=dz_op,
-                         dbias=None if lin_bias is None else lin_bias.grad)
+                         dbias=None if lin_bias is None else lin_bias.grad, drop=drop)
         return None, None, None
     dg = torch.zeros(d, dtype=torch.float32, device=dy.device)
     dbt = torch.zeros(d, dtype=torch.float32, device=dy.device)
     dlb = None if lin_bias is None else torch.zeros(d, dtype=torch.float32, device=dy.device)
-    be.layernorm_bwd(dy, x, res, gamma.detach(), mean, rstd, dz, dg, dbt, dz_bf16=dz_op, dbias=dlb)
+    be.layernorm_bwd(dy, x, res, gamma.detach(), mean, rstd, dz, dg, dbt, dz_bf16=dz_op, dbias=dlb, drop=drop)
     return dg, dbt, dlb
 
 
@@ -856,13 +856,16 @@ class SelfAttnBlockFn(Function):
                          scale, drop=ctx.drop_attn)
         a = _new(R, d, torch.float32, x)
         be.linear_fwd(o, wo, b_out.detach(), a)
-        if ctx.drop_out:
+        # the block-output dropout rides in the LayerNorm kernels in bf16 mode (mask on load forward; masked operand copy and
+        # bias column sums backward): no separate pass over a / dz.  ``a`` is saved UNdropped in that case.
+        ctx.ln_drop = ctx.drop_out if bf else None
+        if ctx.drop_out and not bf:
             be.dropout(a, a, *ctx.drop_out)
         y = _new(R, d, torch.float32, x)
         y_op = _new(R, d, od, x) if bf else None
         mean = torch.empty(R, dtype=torch.float32, device=x.device)
         rstd = torch.empty(R, dtype=torch.float32, device=x.device)
-        be.layernorm_fwd(a, xd, gamma.detach(), beta.detach(), y, y_op, mean, rstd, eps)
+        be.layernorm_fwd(a, xd, gamma.detach(), beta.detach(), y, y_op, mean, rstd, eps, drop=ctx.ln_drop)
         ctx.set_materialize_grads(False)  # no full-size zero tensor for the non-differentiable y_op output
         ctx.save_for_backward(xd, xo, qk_in, qkv, o, lse, a, mean, rstd, key_mask, w_in, w_out, gamma)
         ctx.extra = (b_in, b_out, beta)
@@ -889,7 +892,7 @@ class SelfAttnBlockFn(Function):
         b_in, b_out, beta = ctx.extra
         dz = _new(R, d, f32, dy)  # grad wrt (a) and wrt the residual x
         bf = od == torch.bfloat16
-        if ctx.drop_out:
+        if ctx.drop_out and not ctx.ln_drop:
             # the out-projection branch sees dz through the dropout mask of the forward; the residual branch sees dz itself
             dg, dbt, _ = _ln_bwd(be, dy, a, xd, gamma, beta, mean, rstd, dz)
             dza = _new(R, d, f32, dy)
@@ -897,8 +900,9 @@ class SelfAttnBlockFn(Function):
             dz_op = _cast_op(be, dza)
             dwo, dbo = _wgrad(be, dz_op, o, w_out, b_out, True, True)
         else:
-            dz_op = _new(R, d, od, dy) if bf else dz  # LayerNorm backward writes the bf16 operand copy itself
-            dg, dbt, dbo = _ln_bwd(be, dy, a, xd, gamma, beta, mean, rstd, dz, dz_op if bf else None, b_out)
+            # LayerNorm backward writes the bf16 operand copy itself (masked, with fused dropout: dz_op = mask(dz))
+            dz_op = _new(R, d, od, dy) if bf else dz
+            dg, dbt, dbo = _ln_bwd(be, dy, a, xd, gamma, beta, mean, rstd, dz, dz_op if bf else None, b_out, drop=ctx.ln_drop)
             dwo, _ = _wgrad(be, dz_op, o, w_out, None, True, False)
         d_o = _new(R, d, od, dy)
         be.linear_bwd_data(dz_op, wo, d_o)
@@ -977,13 +981,14 @@ class FFNBlockFn(Function):
         # contraction over a thread-block cluster and sums the partial tiles in rank order, gemm_tcgen05.cu CLK)
         yl = _new(R, d, torch.float32, x)
         be.linear_fwd(h, w2o, b2.detach(), yl)
-        if ctx.drop_out:
+        ctx.ln_drop = ctx.drop_out if bf else None  # bf16 mode: the output dropout rides in the LayerNorm kernels (yl saved undropped)
+        if ctx.drop_out and not bf:
             be.dropout(yl, yl, *ctx.drop_out)
         y = _new(R, d, torch.float32, x)
         y_op = _new(R, d, od, x) if bf else None
         mean = torch.empty(R, dtype=torch.float32, device=x.device)
         rstd = torch.empty(R, dtype=torch.float32, device=x.device)
-        be.layernorm_fwd(yl, xd, gamma.detach(), beta.detach(), y, y_op, mean, rstd, eps)
+        be.layernorm_fwd(yl, xd, gamma.detach(), beta.detach(), y, y_op, mean, rstd, eps, drop=ctx.ln_drop)
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(xd, xo, h, yl, mean, rstd, w1, w2, gamma)
         ctx.extra = (b1, b2, beta)
@@ -1010,12 +1015,17 @@ class FFNBlockFn(Function):
         dh = _new(R, F_, od, dy)
         if ctx.drop_out:
             # dropout mode: the linear2 branch sees dz through the output mask; dh = (dza W2) * relu mask, then the
-            # hidden mask; bias gradients from the masked tensors (no fused column sums)
-            dg, dbt, _ = _ln_bwd(be, dy, yl, xd, gamma, beta, mean, rstd, dz)
-            dza = _new(R, d, f32, dy)
-            be.dropout(dz, dza, *ctx.drop_out)
-            dz_op = _cast_op(be, dza)
-            dw2, db2 = _wgrad(be, dz_op, h, w2, b2, True, True)
+            # hidden mask; the hidden-side bias gradient comes from the masked tensor (no fused column sum)
+            if ctx.ln_drop:
+                dz_op = _new(R, d, od, dy)  # LayerNorm backward applies the output mask: dz_op = bf16(mask(dz)), db2 fused
+                dg, dbt, db2 = _ln_bwd(be, dy, yl, xd, gamma, beta, mean, rstd, dz, dz_op, b2, drop=ctx.ln_drop)
+                dw2, _ = _wgrad(be, dz_op, h, w2, None, True, False)
+            else:
+                dg, dbt, _ = _ln_bwd(be, dy, yl, xd, gamma, beta, mean, rstd, dz)
+                dza = _new(R, d, f32, dy)
+                be.dropout(dz, dza, *ctx.drop_out)
+                dz_op = _cast_op(be, dza)
+                dw2, db2 = _wgrad(be, dz_op, h, w2, b2, True, True)
             be.linear_bwd_data(dz_op, w2o, dh, relu_y=h)
             be.dropout(dh, dh, *ctx.drop_h)
             dw1, db1 = _wgrad(be, dh, xo, w1, b1, True, True)

@@ -36,11 +36,16 @@ def drop_keep_scale(n, p, seed, offset, device="cpu"):
     t = int(float(torch.tensor(p, dtype=torch.float32)) * 16777216.0)  # the C ABI takes p as a float
     t = min(t, 16777215)
     idx = torch.arange(n, dtype=torch.int64, device=device)
-    z = idx + _s64(offset + seed * 0x9E3779B97F4A7C15)
-    z = (z ^ _lsr(z, 30)) * _s64(0xBF58476D1CE4E5B9)
-    z = (z ^ _lsr(z, 27)) * _s64(0x94D049BB133111EB)
-    z = z ^ _lsr(z, 31)
-    bits = _lsr(z, 40)
+    z = idx + _s64(offset + seed * 0x9E3779B97F4A7C15)  # 64-bit counter (wraps like the device's uint64 arithmetic)
+    m32 = 0xFFFFFFFF
+    lo, hi = z & m32, _lsr(z, 32)
+    x = lo ^ ((hi * 0x9E3779B1) & m32)  # uint32 arithmetic carried in int64 lanes: every product stays below 2^64
+    x = x ^ (x >> 16)
+    x = (x * 0x21F0AAAD) & m32
+    x = x ^ (x >> 15)
+    x = (x * 0x735A2D97) & m32
+    x = x ^ (x >> 15)
+    bits = x >> 8
     return bits >= t, float(16777216.0 / (16777216.0 - t))
 
 
@@ -159,10 +164,20 @@ class EmuBackend:
         self.launches += 1
 
     # -- layernorm -----------------------------------------------------
-    def layernorm_fwd(self, x, res, gamma, beta, y, y_bf16, mean, rstd, eps=1e-5):
+    @staticmethod
+    def _ln_mask(x, drop):
+        """keep-mask * scale of the fused dropout (element index row * d + column), or None"""
+        if drop is None or drop[0] <= 0:
+            return None
+        keep, sc = drop_keep_scale(x.numel(), drop[0], drop[1], drop[2], x.device)
+        return keep.reshape(x.shape).float() * sc
+
+    def layernorm_fwd(self, x, res, gamma, beta, y, y_bf16, mean, rstd, eps=1e-5, drop=None):
         for t, nm in ((x, "x"), (res, "res"), (gamma, "gamma"), (beta, "beta"), (y, "y"), (mean, "mean"), (rstd, "rstd")):
             _flat(t, nm, F32)
         _flat(y_bf16, "y_bf16", BF16)
+        mk = self._ln_mask(x, drop)
+        x = x if mk is None else x * mk
         z = x if res is None else x + res
         mu = z.mean(-1)
         var = ((z - mu[:, None]) ** 2).mean(-1)
@@ -175,11 +190,13 @@ class EmuBackend:
         rstd.copy_(rs)
         self.launches += 1
 
-    def layernorm_bwd(self, dy, x, res, gamma, mean, rstd, dz, dgamma, dbeta, dz_bf16=None, dbias=None):
+    def layernorm_bwd(self, dy, x, res, gamma, mean, rstd, dz, dgamma, dbeta, dz_bf16=None, dbias=None, drop=None):
         for t, nm in ((dy, "dy"), (x, "x"), (res, "res"), (gamma, "gamma"), (mean, "mean"), (rstd, "rstd"), (dz, "dz"),
                       (dgamma, "dgamma"), (dbeta, "dbeta"), (dbias, "dbias")):
             _flat(t, nm, F32)
         _flat(dz_bf16, "dz_bf16", BF16)
+        mk = self._ln_mask(x, drop)
+        x = x if mk is None else x * mk
         z = x if res is None else x + res
         xh = (z - mean[:, None]) * rstd[:, None]
         dg = dy * gamma
@@ -188,10 +205,11 @@ class EmuBackend:
         dz.copy_(rstd[:, None] * (dg - s1 - xh * s2))
         dgamma.add_((dy * xh).sum(0))
         dbeta.add_(dy.sum(0))
+        dzx = dz if mk is None else dz * mk  # gradient w.r.t. x (dz itself stays the residual branch's gradient)
         if dz_bf16 is not None:
-            dz_bf16.copy_(dz.to(torch.bfloat16))
+            dz_bf16.copy_(dzx.to(torch.bfloat16))
         if dbias is not None:
-            dbias.add_(dz.sum(0))
+            dbias.add_(dzx.sum(0))
         self.launches += 1
 
     # -- attention -----------------------------------------------------

@@ -103,6 +103,39 @@ def test_layernorm(be, rows):
     assert rel_err(y, torch.nn.functional.layer_norm(x.double(), (d,), gm.double(), bt.double(), 1e-5)) < TOL32
 
 
+@pytest.mark.parametrize("rows", [1, 65, 1000])
+def test_layernorm_with_fused_dropout(be, rows):
+    """stcat_layernorm_dropout_fwd/_bwd: y = LayerNorm(drop(x) + res) with the counter-based mask (element index row * d + col)
+    against float64 with the explicit keep mask; the backward's operand copy and bias column sums carry mask(dz), dz itself
+    (the residual branch's gradient) does not."""
+    from emu_backend import drop_keep_scale
+
+    d, p, seed, off = 256, 0.1, 4321, (1 << 35) + 17
+    x, r = g(rows, d, seed=1), g(rows, d, seed=2)
+    gm, bt = 1 + 0.1 * g(d, seed=3), 0.1 * g(d, seed=4)
+    dy = g(rows, d, seed=5)
+    keep, sc = drop_keep_scale(rows * d, p, seed, off)
+    mk = (keep.double() * sc).view(rows, d)
+    xd, rd = x.double().requires_grad_(True), r.double().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xd * mk + rd, (d,), gm.double(), bt.double(), 1e-5)
+    ref.backward(dy.double())
+    y = torch.empty(rows, d, device="cuda")
+    yb = torch.empty(rows, d, device="cuda", dtype=torch.bfloat16)
+    mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    drop = (p, seed, off)
+    be.layernorm_fwd(x.cuda(), r.cuda(), gm.cuda(), bt.cuda(), y, yb, mean, rstd, drop=drop)
+    assert rel_err(y, ref) < TOL32 and torch.equal(yb, y.to(torch.bfloat16))
+    dz = torch.empty(rows, d, device="cuda")
+    dzb = torch.empty(rows, d, device="cuda", dtype=torch.bfloat16)
+    dlb = torch.zeros(d, device="cuda")
+    dg, dbt = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+    be.layernorm_bwd(dy.cuda(), x.cuda(), r.cuda(), gm.cuda(), mean, rstd, dz, dg, dbt, dz_bf16=dzb, dbias=dlb, drop=drop)
+    assert rel_err(dz, rd.grad) < TOL32              # residual branch: unmasked
+    assert rel_err(dzb, xd.grad) < 4e-3              # gradient w.r.t. x: masked, one bf16 rounding
+    assert torch.equal(dzb == 0, (dz * mk.float().cuda()).to(torch.bfloat16) == 0)
+    assert rel_err(dlb, xd.grad.sum(0)) < 1e-4
+
+
 def attn_ref(q1, q2, k1, k2, v, mask, B, H, Lq, Lk, scale):
     """float64 batch-major reference with the same contract as stcat_attention_fwd"""
     def heads(t, L):
@@ -305,8 +338,8 @@ def test_map2d_pool(be):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_dropout_mask_is_the_counter_based_stream(be, dtype):
-    """stcat_dropout keeps element i iff the top 24 bits of splitmix64(seed + offset + i) reach p * 2^24: bit-for-bit the
-    mask tests/emu_backend.drop_keep_scale builds on the host (which is checked against a pure-python splitmix64)."""
+    """stcat_dropout keeps element i iff drop_bits24(seed, offset + i) (csrc/common.cuh) reaches p * 2^24: bit-for-bit the
+    mask tests/emu_backend.drop_keep_scale builds on the host (which is checked against a pure-python restatement on the CPU)."""
     from emu_backend import drop_keep_scale
 
     n, p, seed, off = 100003, 0.1, 0x1234567, 987654321

@@ -426,3 +426,79 @@ def test_unused_parameters_are_exactly_the_gradless_ones():
         gradless = {k for k, p in model.named_parameters() if p.grad is None}
         listed = {k for k, p in model.named_parameters() if any(p is q for q in unused_parameters(model, cfg))}
         assert listed == gradless, (fs, sorted(listed ^ gradless))
+
+
+def test_dropout_hash_restatement_matches_pure_python():
+    """tests/emu_backend.drop_keep_scale (vectorised, int64 lanes) against a scalar restatement of csrc/common.cuh
+    drop_bits24: 64-bit counter, folded to 32 bits, multiply-xorshift mixer, top 24 bits against p * 2^24."""
+    from emu_backend import drop_keep_scale
+
+    def bits24(seed, idx):
+        z = (idx + seed * 0x9E3779B97F4A7C15) & ((1 << 64) - 1)
+        x = (z & 0xFFFFFFFF) ^ (((z >> 32) * 0x9E3779B1) & 0xFFFFFFFF)
+        x ^= x >> 16
+        x = (x * 0x21F0AAAD) & 0xFFFFFFFF
+        x ^= x >> 15
+        x = (x * 0x735A2D97) & 0xFFFFFFFF
+        x ^= x >> 15
+        return x >> 8
+
+    for p, seed, off in [(0.1, 0x1234567, 987654321), (0.3, (1 << 62) + 12345, (1 << 40) + 7), (0.5, 7, 0)]:
+        keep, sc = drop_keep_scale(3000, p, seed, off)
+        t = min(int(float(torch.tensor(p, dtype=torch.float32)) * 16777216.0), 16777215)
+        assert torch.equal(keep, torch.tensor([bits24(seed, off + i) >= t for i in range(3000)]))
+        assert abs(sc - 16777216.0 / (16777216.0 - t)) < 1e-12
+    keep, _ = drop_keep_scale(2_000_000, 0.1, 99, 1 << 33)
+    k = keep.float()
+    assert abs(float(k.mean()) - 0.9) < 1e-3
+    assert abs(float(((k[1:] - k.mean()) * (k[:-1] - k.mean())).mean() / k.var())) < 5e-3  # neighbours are uncorrelated
+
+
+@pytest.mark.parametrize("block", ["ffn", "attn"])
+def test_block_dropout_in_bf16_mode_uses_the_fused_layernorm_mask(block):
+    """bf16 mode: the block-output dropout is folded into the LayerNorm kernels (stcat_layernorm_dropout_fwd/_bwd: mask on
+    load, masked operand copy and bias column sums in the backward).  Same masks, same offsets as the unfused fp32 mode: the
+    two modes agree to bf16 operand rounding, and no stand-alone dropout launch is left for that site."""
+    R, d, p = 10, 256, 0.2
+    B, L, H = 2, 5, 8
+    go = torch.randn(R, d, generator=torch.Generator().manual_seed(8))
+
+    def run(precision):
+        ops.set_precision(precision)
+        ops.clear_weight_cache()
+        x, pos = _leaf(R, d, seed=1), _leaf(R, d, seed=2)
+        gm, bt = _leaf(d, seed=6), _leaf(d, seed=7)
+        if block == "ffn":
+            w1, b1, w2, b2 = _leaf(512, d, seed=2), _leaf(512, seed=3), _leaf(d, 512, seed=4), _leaf(d, seed=5)
+            with torch.no_grad():
+                w1.mul_(d ** -0.5); w2.mul_(512 ** -0.5)
+            leaves = (x, w1, b1, w2, b2, gm, bt)
+            fn = lambda: ops.ffn_block(x, None, w1, b1, w2, b2, gm, bt, drop_p=p)
+        else:
+            wi, bi, wo, bo = _leaf(3 * d, d, seed=3), _leaf(3 * d, seed=4), _leaf(d, d, seed=5), _leaf(d, seed=6)
+            with torch.no_grad():
+                wi.mul_(d ** -0.5); wo.mul_(d ** -0.5)
+            leaves = (x, wi, bi, wo, bo, gm, bt)
+            fn = lambda: ops.self_attn_block(x, None, pos, None, wi, bi, wo, bo, gm, bt, B, L, H, drop_p=p)
+        ops.set_dropout_seed(21)
+        be = ops.get_backend()
+        calls = []
+        orig = be.dropout
+        be.dropout = lambda *a, **k: (calls.append(a[0].shape), orig(*a, **k))[1]
+        try:
+            y, _ = fn()
+            (y * go).sum().backward()
+        finally:
+            be.dropout = orig
+        return [y.detach()] + [t.grad.clone() for t in leaves], calls
+
+    try:
+        ref, calls32 = run("fp32")
+        got, calls16 = run("bf16")
+    finally:
+        ops.set_precision("fp32")
+        ops.clear_weight_cache()
+    # fp32 mode: stand-alone dropout on the [R, d] block output forward and on dz backward; bf16 mode: none of those
+    assert sum(1 for s in calls32 if tuple(s) == (R, d)) == 2 and sum(1 for s in calls16 if tuple(s) == (R, d)) == 0
+    for a_, b_ in zip(got, ref):
+        assert rel_err(a_, b_) < 3e-2
