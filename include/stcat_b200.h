@@ -41,7 +41,7 @@ extern "C" {
 
 /* Bumped whenever a signature or the meaning of an argument changes; stcat_b200/cabi.py refuses a library whose version
  * differs from the one it was written against (a stale locally built .so would otherwise be called with new signatures). */
-#define STCAT_ABI_VERSION 8
+#define STCAT_ABI_VERSION 9
 STCAT_API int stcat_abi_version(void);
 STCAT_API const char* stcat_last_error(void);
 /* compute capability major*10+minor of the current device, or <0; 100 expected */
@@ -67,6 +67,20 @@ STCAT_API int stcat_linear_fwd(const void* x, int64_t ldx, int x_dtype, const vo
 STCAT_API int stcat_linear_bwd_data(const void* dy, int64_t lddy, int dy_dtype, const void* w, int64_t ldw, int w_dtype,
                           void* dx, int64_t lddx, int dx_dtype, const void* relu_y, int64_t ldy, int y_dtype,
                           float* dbias, int M, int N, int K, int accumulate, void* stream);
+/* The FFN's inner dropout (`dropout(relu(linear1(x)))`, modal_encoder.py:239; query_decoder.py:435,657) without a pass of its own:
+ *   stcat_linear_dropout_fwd     : y = drop(act(x W^T + b)); the mask (element index row * N + col, y contiguous: ldy == N; p, seed,
+ *                                  offset as in stcat_dropout) is drawn in the GEMM epilogue.  Shapes the tensor-core kernel does not
+ *                                  take run stcat_linear_fwd + stcat_dropout.
+ *   stcat_linear_bwd_data_scaled : dx = alpha * (dy W) where relu_y > 0, else 0; dbias += colsum(dx).  With relu_y = the DROPPED
+ *                                  forward activation (zero where the ReLU clamped or the mask dropped) and alpha = 1 / keep this is
+ *                                  the backward of dropout and ReLU in one epilogue: no mask has to be regenerated.  bf16 operands,
+ *                                  K % 64 == 0 (the fused tensor-core epilogue); STCAT_ESHAPE otherwise. */
+STCAT_API int stcat_linear_dropout_fwd(const void* x, int64_t ldx, int x_dtype, const void* w, int64_t ldw, int w_dtype,
+                        const float* bias, void* y, int64_t ldy, int y_dtype, int M, int N, int K, int relu, float p,
+                        uint64_t seed, uint64_t offset, void* stream);
+STCAT_API int stcat_linear_bwd_data_scaled(const void* dy, int64_t lddy, int dy_dtype, const void* w, int64_t ldw, int w_dtype,
+                        void* dx, int64_t lddx, int dx_dtype, const void* relu_y, int64_t ldy, int y_dtype, float* dbias,
+                        int M, int N, int K, float alpha, void* stream);
 STCAT_API int stcat_linear_bwd_weight(const void* dy, int64_t lddy, int dy_dtype, const void* x, int64_t ldx, int x_dtype,
                             float* dw, int64_t lddw, float* db, int M, int N, int K, int accumulate, void* stream);
 

@@ -55,6 +55,8 @@ class _Job(ctypes.Structure):
 
 _U64 = ctypes.c_uint64
 SIGNATURES["stcat_dropout"] = (c_int, [_P, _P, _I, _L, _F, _U64, _U64, _P])
+SIGNATURES["stcat_linear_dropout_fwd"] = (c_int, [_P, _L, _I, _P, _L, _I, _P, _P, _L, _I, _I, _I, _I, _I, _F, _U64, _U64, _P])
+SIGNATURES["stcat_linear_bwd_data_scaled"] = (c_int, [_P, _L, _I, _P, _L, _I, _P, _L, _I, _P, _L, _I, _P, _I, _I, _I, _F, _P])
 SIGNATURES["stcat_layernorm_dropout_fwd"] = (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _U64, _U64, _P])
 SIGNATURES["stcat_layernorm_dropout_bwd"] = (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _U64, _U64, _P])
 SIGNATURES["stcat_attention_dropout_fwd"] = (c_int, [_P, _P, _L, _P, _P, _L, _P, _L, _P, _L, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F,
@@ -78,7 +80,7 @@ SIGNATURES["stcat_box_refine_bwd"] = (c_int, [_P, _P, _P, _P, _P, _L, _F, _P])
 SIGNATURES["stcat_stg_loss"] = (c_int, [_P] * 12 + [ctypes.POINTER(c_float), _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P])
 SIGNATURES["stcat_linear_group"] = (c_int, [_I, _I, ctypes.POINTER(_Job), _I, _P])
 MAX_GROUP_JOBS = 12
-ABI_VERSION = 8  # include/stcat_b200.h STCAT_ABI_VERSION
+ABI_VERSION = 9  # include/stcat_b200.h STCAT_ABI_VERSION
 
 _lib = None
 
@@ -190,18 +192,36 @@ class CudaBackend:
                                            yd, M, N, K, int(relu), int(accumulate), self._stream()), "linear_fwd")
         self.launches += 1
 
-    def linear_bwd_data(self, dy, w, dx, accumulate=False, relu_y=None, dbias=None):
+    def linear_dropout_fwd(self, x, w, bias, y, relu, drop):
+        """y = drop(act(x w^T + bias)), the mask drawn in the GEMM epilogue; ``drop`` = (p, seed, offset), y contiguous"""
+        (xp, ldx, xd), (wp, ldw, wd), (yp, ldy, yd) = self._mat(x, "x"), self._mat(w, "w"), self._mat(y, "y")
+        M, K = x.shape
+        N = w.shape[0]
+        assert w.shape[1] == K and tuple(y.shape) == (M, N)
+        self._rc(self.lib.stcat_linear_dropout_fwd(xp, ldx, xd, wp, ldw, wd, self._flat(bias, "bias", torch.float32), yp, ldy, yd,
+                                                   M, N, K, int(relu), float(drop[0]), int(drop[1]), int(drop[2]),
+                                                   self._stream()), "linear_dropout_fwd")
+        self.launches += 1
+
+    def linear_bwd_data(self, dy, w, dx, accumulate=False, relu_y=None, dbias=None, alpha=1.0):
         """dx = dy . w (+ dx); with relu_y ([M, K], the forward activation of the layer below) the result is zeroed
-        where relu_y <= 0, and with dbias ([K] fp32) the column sums of the stored dx are accumulated into it."""
+        where relu_y <= 0, and with dbias ([K] fp32) the column sums of the stored dx are accumulated into it.
+        ``alpha`` != 1 (with relu_y, no accumulate): dx is scaled by it -- the 1 / keep factor of a dropout behind the ReLU."""
         (gp, ldg, gd), (wp, ldw, wd), (xp, ldx, xd) = self._mat(dy, "dy"), self._mat(w, "w"), self._mat(dx, "dx")
         M, N = dy.shape
         K = w.shape[1]
         assert w.shape[0] == N and tuple(dx.shape) == (M, K)
         yp, ldy, yd = (None, 0, F32) if relu_y is None else self._mat(relu_y, "relu_y")
         assert relu_y is None or tuple(relu_y.shape) == (M, K)
-        self._rc(self.lib.stcat_linear_bwd_data(gp, ldg, gd, wp, ldw, wd, xp, ldx, xd, yp, ldy, yd,
-                                                self._flat(dbias, "dbias", torch.float32), M, N, K, int(accumulate),
-                                                self._stream()), "linear_bwd_data")
+        if alpha != 1.0:
+            assert relu_y is not None and not accumulate
+            self._rc(self.lib.stcat_linear_bwd_data_scaled(gp, ldg, gd, wp, ldw, wd, xp, ldx, xd, yp, ldy, yd,
+                                                           self._flat(dbias, "dbias", torch.float32), M, N, K, float(alpha),
+                                                           self._stream()), "linear_bwd_data_scaled")
+        else:
+            self._rc(self.lib.stcat_linear_bwd_data(gp, ldg, gd, wp, ldw, wd, xp, ldx, xd, yp, ldy, yd,
+                                                    self._flat(dbias, "dbias", torch.float32), M, N, K, int(accumulate),
+                                                    self._stream()), "linear_bwd_data")
         self.launches += 1
 
     def linear_bwd_weight(self, dy, x, dw, db, accumulate=False):

@@ -96,9 +96,31 @@ extern "C" int stcat_linear_fwd(const void* x, int64_t ldx, int x_dtype, const v
     return gemm_simt(x, ldx, 1, w, ldw, 1, x_dtype, y, ldy, y_dtype, bias, M, N, K, relu, accumulate, st);
 }
 
-extern "C" int stcat_linear_bwd_data(const void* dy, int64_t lddy, int dy_dtype, const void* w, int64_t ldw,
-                                     int w_dtype, void* dx, int64_t lddx, int dx_dtype, const void* relu_y, int64_t ldy,
-                                     int y_dtype, float* dbias, int M, int N, int K, int accumulate, void* stream) {
+extern "C" int stcat_dropout(const void* x, void* out, int dtype, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+
+extern "C" int stcat_linear_dropout_fwd(const void* x, int64_t ldx, int x_dtype, const void* w, int64_t ldw, int w_dtype,
+                                        const float* bias, void* y, int64_t ldy, int y_dtype, int M, int N, int K, int relu,
+                                        float p, uint64_t seed, uint64_t offset, void* stream) {
+    STCAT_REQUIRE(x && w && y, STCAT_EINVAL, "linear_dropout_fwd: null pointer");
+    STCAT_REQUIRE(M >= 0 && N > 0 && K > 0, STCAT_EINVAL, "linear_dropout_fwd: bad sizes M=%d N=%d K=%d", M, N, K);
+    STCAT_REQUIRE(x_dtype == w_dtype && dtype_ok(x_dtype) && dtype_ok(y_dtype), STCAT_EINVAL, "linear_dropout_fwd: dtypes");
+    STCAT_REQUIRE(ldx >= K && ldw >= K && ldy == N, STCAT_EINVAL, "linear_dropout_fwd: y must be contiguous (ldy == N), ldx / ldw >= K");
+    STCAT_REQUIRE(p >= 0.f && p < 1.f, STCAT_EINVAL, "linear_dropout_fwd: p=%f", (double)p);
+    if (M == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p > 0.f && x_dtype == STCAT_BF16 && gemm_tc_supported(M, N, K, ldx, ldw, ldy, x, w, y, 0, 0)) {
+        GemmEpilogue epi;  // the mask is drawn in the GEMM epilogue: no second pass over y
+        epi.drop = make_drop(p, seed, offset);
+        return gemm_tc(x, ldx, 0, w, ldw, 0, y, ldy, y_dtype, bias, M, N, K, relu, 0, st, &epi);
+    }
+    int rc = stcat_linear_fwd(x, ldx, x_dtype, w, ldw, w_dtype, bias, y, ldy, y_dtype, M, N, K, relu, 0, stream);
+    if (rc || p == 0.f) return rc;
+    return stcat_dropout(y, y, y_dtype, (int64_t)M * N, p, seed, offset, stream);
+}
+
+static int linear_bwd_data_impl(const void* dy, int64_t lddy, int dy_dtype, const void* w, int64_t ldw,
+                                int w_dtype, void* dx, int64_t lddx, int dx_dtype, const void* relu_y, int64_t ldy,
+                                int y_dtype, float* dbias, int M, int N, int K, int accumulate, float alpha, void* stream) {
     STCAT_REQUIRE(dy && w && dx, STCAT_EINVAL, "linear_bwd_data: null pointer");
     STCAT_REQUIRE(M >= 0 && N > 0 && K > 0, STCAT_EINVAL, "linear_bwd_data: bad sizes M=%d N=%d K=%d", M, N, K);
     STCAT_REQUIRE(dy_dtype == w_dtype && dtype_ok(dy_dtype) && dtype_ok(dx_dtype), STCAT_EINVAL, "linear_bwd_data: dtypes");
@@ -113,12 +135,14 @@ extern "C" int stcat_linear_bwd_data(const void* dy, int64_t lddy, int dy_dtype,
                           (!relu_y || (y_dtype == STCAT_BF16 && ((uintptr_t)relu_y & 15) == 0 && ldy % 8 == 0));
         if (fuse) {
             GemmEpilogue epi;
-            epi.relu_mask = relu_y; epi.ld_mask = ldy; epi.colsum = dbias;
+            epi.relu_mask = relu_y; epi.ld_mask = ldy; epi.colsum = dbias; epi.alpha = alpha;
             return gemm_tc(dy, lddy, 0, w, ldw, 1, dx, lddx, dx_dtype, nullptr, M, K, N, 0, accumulate, st, &epi);
         }
+        STCAT_REQUIRE(alpha == 1.f, STCAT_ESHAPE, "linear_bwd_data_scaled: alpha needs the fused tensor-core epilogue (bf16, K %% 64 == 0, relu_y or dbias, no accumulate)");
         int rc = gemm_tc(dy, lddy, 0, w, ldw, 1, dx, lddx, dx_dtype, nullptr, M, K, N, 0, accumulate, st);
         if (rc) return rc;
     } else {
+        STCAT_REQUIRE(alpha == 1.f, STCAT_ESHAPE, "linear_bwd_data_scaled: alpha needs the fused tensor-core epilogue");
         int rc = gemm_simt(dy, lddy, 1, w, 1, ldw, dy_dtype, dx, lddx, dx_dtype, nullptr, M, K, N, 0, accumulate, st);
         if (rc) return rc;
     }
@@ -129,6 +153,21 @@ extern "C" int stcat_linear_bwd_data(const void* dy, int64_t lddy, int dy_dtype,
     }
     if (dbias) return colsum(dx, lddx, dx_dtype, dbias, M, K, 1, st);
     return 0;
+}
+
+extern "C" int stcat_linear_bwd_data(const void* dy, int64_t lddy, int dy_dtype, const void* w, int64_t ldw,
+                                     int w_dtype, void* dx, int64_t lddx, int dx_dtype, const void* relu_y, int64_t ldy,
+                                     int y_dtype, float* dbias, int M, int N, int K, int accumulate, void* stream) {
+    return linear_bwd_data_impl(dy, lddy, dy_dtype, w, ldw, w_dtype, dx, lddx, dx_dtype, relu_y, ldy, y_dtype, dbias, M, N, K,
+                                accumulate, 1.f, stream);
+}
+
+extern "C" int stcat_linear_bwd_data_scaled(const void* dy, int64_t lddy, int dy_dtype, const void* w, int64_t ldw,
+                                            int w_dtype, void* dx, int64_t lddx, int dx_dtype, const void* relu_y, int64_t ldy,
+                                            int y_dtype, float* dbias, int M, int N, int K, float alpha, void* stream) {
+    STCAT_REQUIRE(relu_y != nullptr, STCAT_EINVAL, "linear_bwd_data_scaled: relu_y required");
+    return linear_bwd_data_impl(dy, lddy, dy_dtype, w, ldw, w_dtype, dx, lddx, dx_dtype, relu_y, ldy, y_dtype, dbias, M, N, K, 0,
+                                alpha, stream);
 }
 
 extern "C" int stcat_linear_bwd_weight(const void* dy, int64_t lddy, int dy_dtype, const void* x, int64_t ldx,

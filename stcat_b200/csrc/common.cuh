@@ -45,13 +45,6 @@ template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
-// optional epilogue extras of the tensor-core GEMM (gemm_tcgen05.cu), used by stcat_linear_bwd_data
-struct GemmEpilogue {
-    const void* relu_mask = nullptr;   // bf16 [M, N]: C is zeroed where relu_mask <= 0
-    int64_t ld_mask = 0;
-    float* colsum = nullptr;           // [N] fp32: accumulated with the column sums of the stored C
-};
-
 // ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
 // One step is a dependent chain of ~10^3 short kernels; at a kernel boundary the GPU otherwise drains the grid, then
 // launches, then the next grid runs its prologue (barrier init, TMEM allocation, descriptor prefetch) before it touches
@@ -124,6 +117,15 @@ inline DropArgs make_drop(float p, uint64_t seed, uint64_t offset) {
     }
     return d;
 }
+// optional epilogue extras of the tensor-core GEMM (gemm_tcgen05.cu), used by stcat_linear_bwd_data / stcat_linear_dropout_fwd
+struct GemmEpilogue {
+    const void* relu_mask = nullptr;   // bf16 [M, N]: C is zeroed where relu_mask <= 0
+    int64_t ld_mask = 0;
+    float* colsum = nullptr;           // [N] fp32: accumulated with the column sums of the stored C
+    float alpha = 1.f;                 // C is scaled by alpha before the mask (the 1 / keep factor of a dropout behind the ReLU)
+    DropArgs drop;                     // train-mode dropout on C after bias / ReLU, element index row * N + col (contiguous C)
+};
+
 #ifdef __CUDACC__
 // First statement of every kernel that draws masks: fold the current value of the step counter into the seed.
 __device__ __forceinline__ DropArgs drop_resolve(DropArgs d) {

@@ -100,6 +100,8 @@ struct alignas(64) Job {
     void* c_ptr;                   // CLK (cluster split-K): the output is written with plain stores by the row owners
     int64_t ldc;
     int accumulate;
+    float alpha;                   // scale applied before the ReLU-backward mask (1 = none)
+    DropArgs drop;                 // dropout on the output after bias / ReLU (thresh == 0: none); index row * N + col
 };
 template <int NJ> struct GroupParams {
     Job jobs[NJ];
@@ -113,10 +115,15 @@ template <int NJ> struct GroupParams {
 // a cluster barrier CTA r sums rows [128 r / S, 128 (r+1) / S) over the S partials through distributed shared memory in rank
 // order (a fixed summation order: bit-reproducible, unlike a reduce-add split-K), applies bias / ReLU / accumulate and writes
 // them with plain stores.
-template <bool A_MN, bool B_MN, bool OUT_BF16, int BN, int NJ, bool TRACE = false, int EPIMODE = 0, bool BRES = false, bool CLK = false>
+// EPIX ("epilogue extras", single-job bf16-output instantiations only): the output is scaled by Job::alpha and / or passed
+// through the train-mode dropout mask of Job::drop -- the FFN's inner dropout in the linear1 epilogue, its backward (with the
+// ReLU mask) in the linear2 data-gradient epilogue.  A template parameter, so that the default instantiations carry none of it.
+template <bool A_MN, bool B_MN, bool OUT_BF16, int BN, int NJ, bool TRACE = false, int EPIMODE = 0, bool BRES = false, bool CLK = false,
+          bool EPIX = false>
 __global__ void __launch_bounds__((Cfg<BN, EPIMODE, BRES>::THREADS), 1)
 gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
     static_assert(!CLK || (BN == 64 && NJ == 1 && EPIMODE == 0 && !BRES && !A_MN), "CLK: skinny tile, one job");
+    static_assert(!EPIX || (NJ == 1 && OUT_BF16 && !A_MN && !CLK && !TRACE), "EPIX: one job, bf16 output");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t bres_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B-swizzle atoms need 1024 B alignment
     using C = Cfg<BN, EPIMODE, BRES>;
@@ -364,6 +371,8 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
             const __nv_bfloat16* const job_mask = p.mask;
             const int64_t job_ld_mask = p.ld_mask;
             float* const job_colsum = p.colsum;
+            const float job_alpha = EPIX ? p.alpha : 1.f;
+            const DropArgs job_drop = (EPIX && p.drop.thresh) ? drop_resolve(p.drop) : DropArgs();
             if (next_key != staged_key) {
                 sbias = bias_base + (nstaged & 1u) * (BN * 4) + cg * GC * 4;
                 if (gt < GC) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + gt * 4), "f"(bv_next) : "memory");
@@ -406,6 +415,12 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
                         float x0 = __uint_as_float(r[4 * j + 0]) + b0, x1 = __uint_as_float(r[4 * j + 1]) + b1;
                         float x2 = __uint_as_float(r[4 * j + 2]) + b2, x3 = __uint_as_float(r[4 * j + 3]) + b3;
                         if (job_relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+                        if (EPIX && job_alpha != 1.f) { x0 *= job_alpha; x1 *= job_alpha; x2 *= job_alpha; x3 *= job_alpha; }
+                        if (EPIX && job_drop.thresh) {  // dropout behind the ReLU (the FFN's inner dropout): element row * N + col
+                            const uint64_t e0 = (uint64_t)(row0 + lane) * (uint64_t)job_N + (uint64_t)(col0 + c * CHUNK_COLS + 4 * j);
+                            x0 = drop_apply(job_drop, e0, x0); x1 = drop_apply(job_drop, e0 + 1, x1);
+                            x2 = drop_apply(job_drop, e0 + 2, x2); x3 = drop_apply(job_drop, e0 + 3, x3);
+                        }
                         r[4 * j + 0] = __float_as_uint(x0); r[4 * j + 1] = __float_as_uint(x1);
                         r[4 * j + 2] = __float_as_uint(x2); r[4 * j + 3] = __float_as_uint(x3);
                     }
@@ -572,6 +587,8 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
             const __nv_bfloat16* const job_mask = p.mask;
             const int64_t job_ld_mask = p.ld_mask;
             float* const job_colsum = p.colsum;
+            const float job_alpha = EPIX ? p.alpha : 1.f;
+            const DropArgs job_drop = (EPIX && p.drop.thresh) ? drop_resolve(p.drop) : DropArgs();
             {   // stage the bias slice (zero where there is none / out of range): no per-element predicates below.
                 // Safe to overwrite: every thread of the group passed the previous tile's last bar.sync, which
                 // follows all of that tile's bias reads.
@@ -628,6 +645,12 @@ gemm_tc_kernel(const __grid_constant__ GroupParams<NJ> gp) {
                     float x0 = __uint_as_float(r[4 * j + 0]) + b0, x1 = __uint_as_float(r[4 * j + 1]) + b1;
                     float x2 = __uint_as_float(r[4 * j + 2]) + b2, x3 = __uint_as_float(r[4 * j + 3]) + b3;
                     if (job_relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+                    if (EPIX && job_alpha != 1.f) { x0 *= job_alpha; x1 *= job_alpha; x2 *= job_alpha; x3 *= job_alpha; }
+                    if (EPIX && job_drop.thresh) {  // dropout behind the ReLU (the FFN's inner dropout): element row * N + col
+                        const uint64_t e0 = (uint64_t)(m_blk * BM + row) * (uint64_t)job_N + (uint64_t)(n_blk * BN + g * GC + c * CHUNK_COLS + 4 * j);
+                        x0 = drop_apply(job_drop, e0, x0); x1 = drop_apply(job_drop, e0 + 1, x1);
+                        x2 = drop_apply(job_drop, e0 + 2, x2); x3 = drop_apply(job_drop, e0 + 3, x3);
+                    }
                     r[4 * j + 0] = __float_as_uint(x0); r[4 * j + 1] = __float_as_uint(x1);
                     r[4 * j + 2] = __float_as_uint(x2); r[4 * j + 3] = __float_as_uint(x3);
                 }
@@ -799,11 +822,11 @@ static long long* g_gemm_trace = nullptr;
 void gemm_tc_set_trace(long long* buf) { g_gemm_trace = buf; }
 
 // one instantiation: shared-memory attribute once, programmatic dependent launch
-template <bool AMN, bool BMN, bool OBF, int BN, int NJ, bool TRACE, int EPIMODE, bool BRES>
+template <bool AMN, bool BMN, bool OBF, int BN, int NJ, bool TRACE, int EPIMODE, bool BRES, bool EPIX = false>
 static int launch_inst(const tc::GroupParams<NJ>& gp, int grid, cudaStream_t st) {
     using namespace tc;
     constexpr int SMEM = Cfg<BN, EPIMODE, BRES>::SMEM_BYTES;
-    auto kern = gemm_tc_kernel<AMN, BMN, OBF, BN, NJ, TRACE, EPIMODE, BRES>;
+    auto kern = gemm_tc_kernel<AMN, BMN, OBF, BN, NJ, TRACE, EPIMODE, BRES, false, EPIX>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -852,6 +875,20 @@ enum TcMode { TC_PLAIN = 0, TC_EPI2 = 1, TC_BRES = 2, TC_WEPI = 3 };
 template <bool AMN, bool BMN, bool OBF, int BN, int NJ>
 static int launch_tc(const tc::GroupParams<NJ>& gp, int grid, cudaStream_t st, int mode) {
     using namespace tc;
+    bool extras = false;
+    for (int j = 0; j < gp.njobs; ++j) extras = extras || gp.jobs[j].alpha != 1.f || gp.jobs[j].drop.thresh != 0;
+    if (extras) {
+        if constexpr (NJ == 1 && OBF && !AMN) {
+            if constexpr (BN == 256) {
+                if (mode == TC_BRES) return launch_inst<AMN, BMN, OBF, BN, NJ, false, 3, true, true>(gp, grid, st);
+                return launch_inst<AMN, BMN, OBF, BN, NJ, false, 3, false, true>(gp, grid, st);
+            } else {
+                return launch_inst<AMN, BMN, OBF, BN, NJ, false, 0, false, true>(gp, grid, st);
+            }
+        } else {
+            return set_err(STCAT_ESHAPE, "gemm_tc: the scaled / dropout epilogue is instantiated for single launches with a bf16 output only");
+        }
+    }
     if constexpr (BN == 256) {
         if constexpr (!AMN && OBF) {
             if (mode == TC_BRES) {
@@ -927,6 +964,10 @@ static int fill_job(tc::Job& J, const TcJob& in, int a_mn_major, int b_mn_major,
     J.mask = (const __nv_bfloat16*)in.epi.relu_mask;
     J.ld_mask = in.epi.ld_mask;
     J.colsum = in.epi.colsum;
+    J.alpha = in.epi.alpha;
+    J.drop = in.epi.drop;
+    if (J.drop.thresh && (in.ldc != N || in.accumulate || J.splits > 1))
+        return set_err(STCAT_ESHAPE, "gemm_tc: fused dropout epilogue needs a contiguous output, no accumulate, no split-K");
     if ((J.mask || J.colsum) && (a_mn_major || in.accumulate || N % 64 != 0))
         return set_err(STCAT_ESHAPE, "gemm_tc: fused ReLU-mask / column-sum epilogue needs N %% 64 == 0, no accumulate, K-major A");
     if (in.relu && in.accumulate) return set_err(STCAT_ESHAPE, "gemm_tc: relu with accumulate is not supported");
@@ -973,6 +1014,8 @@ static int gemm_tc_launch_jobs(const TcJob* jobs, int njobs, int a_mn_major, int
         static const char* wepi_env = getenv("STCAT_GEMM_WEPI");
         const bool wepi = wepi_env ? atoi(wepi_env) != 0 : true;
         mode = bres ? TC_BRES : (wepi ? TC_WEPI : (epi2 ? TC_EPI2 : TC_PLAIN));
+        for (int j = 0; j < njobs; ++j)  // the scaled / dropout epilogue exists in the warp epilogue only
+            if ((jobs[j].epi.alpha != 1.f || jobs[j].epi.drop.thresh) && mode != TC_BRES) mode = TC_WEPI;
     }
     int work = 0;
     for (int j = 0; j < njobs; ++j) {
@@ -987,7 +1030,8 @@ static int gemm_tc_launch_jobs(const TcJob* jobs, int njobs, int a_mn_major, int
         static const bool clk_on = !(getenv("STCAT_GEMM_CLK") && atoi(getenv("STCAT_GEMM_CLK")) == 0);
         const TcJob& j0 = jobs[0];
         const int kb = (j0.term[0].K + BK - 1) / BK;
-        if (clk_on && !a_mn_major && j0.nterms == 1 && !j0.epi.relu_mask && !j0.epi.colsum && kb >= 16 && gp.jobs[0].splits == 1) {
+        if (clk_on && !a_mn_major && j0.nterms == 1 && !j0.epi.relu_mask && !j0.epi.colsum && j0.epi.alpha == 1.f && !j0.epi.drop.thresh &&
+            kb >= 16 && gp.jobs[0].splits == 1) {
             int clk = 0;
             for (int sft = 3; sft >= 1 && !clk; --sft)
                 if (kb % (1 << sft) == 0 && work * (1 << sft) <= sms) clk = 1 << sft;

@@ -237,6 +237,12 @@ def set_dropout_seed(seed: int):
     _drop_state["offset"] = 0
 
 
+def _drop_scale(p: float) -> float:
+    """1 / keep as the kernels compute it (csrc/common.cuh make_drop): 2^24 / (2^24 - floor(float32(p) * 2^24))"""
+    t = min(int(float(torch.tensor(p, dtype=torch.float32)) * 16777216.0), 16777215)
+    return float(torch.tensor(16777216.0 / (16777216.0 - t), dtype=torch.float32))
+
+
 def _drop_reserve(n: int):
     if _drop_state["seed"] is None:
         set_dropout_seed(torch.initial_seed())
@@ -974,9 +980,12 @@ class FFNBlockFn(Function):
             xo = xd
         w1o, w2o = _operand(w1.detach(), True), _operand(w2.detach(), True)
         h = _new(R, F_, od, x)
-        be.linear_fwd(xo, w1o, b1.detach(), h, relu=True)
-        if ctx.drop_h:
-            be.dropout(h, h, *ctx.drop_h)
+        if ctx.drop_h and bf:
+            be.linear_dropout_fwd(xo, w1o, b1.detach(), h, True, ctx.drop_h)  # the inner dropout's mask is drawn in the GEMM epilogue
+        else:
+            be.linear_fwd(xo, w1o, b1.detach(), h, relu=True)
+            if ctx.drop_h:
+                be.dropout(h, h, *ctx.drop_h)
         # (few rows, long contraction -- decoder / temporal FFN, [t, 2048] x [2048, 256]: the GEMM entry point splits the
         # contraction over a thread-block cluster and sums the partial tiles in rank order, gemm_tcgen05.cu CLK)
         yl = _new(R, d, torch.float32, x)
@@ -1013,34 +1022,35 @@ class FFNBlockFn(Function):
         dz = _new(R, d, f32, dy)
         bf = od == torch.bfloat16
         dh = _new(R, F_, od, dy)
-        if ctx.drop_out:
-            # dropout mode: the linear2 branch sees dz through the output mask; dh = (dza W2) * relu mask, then the
-            # hidden mask; the hidden-side bias gradient comes from the masked tensor (no fused column sum)
-            if ctx.ln_drop:
-                dz_op = _new(R, d, od, dy)  # LayerNorm backward applies the output mask: dz_op = bf16(mask(dz)), db2 fused
-                dg, dbt, db2 = _ln_bwd(be, dy, yl, xd, gamma, beta, mean, rstd, dz, dz_op, b2, drop=ctx.ln_drop)
-                dw2, _ = _wgrad(be, dz_op, h, w2, None, True, False)
-            else:
-                dg, dbt, _ = _ln_bwd(be, dy, yl, xd, gamma, beta, mean, rstd, dz)
-                dza = _new(R, d, f32, dy)
-                be.dropout(dz, dza, *ctx.drop_out)
-                dz_op = _cast_op(be, dza)
-                dw2, db2 = _wgrad(be, dz_op, h, w2, b2, True, True)
+        alpha = 1.0
+        if ctx.drop_out and not ctx.ln_drop:
+            # dropout in exact-fp32 mode, unfused: the linear2 branch sees dz through the output mask; dh = (dza W2) * relu
+            # mask, then the hidden mask; bias gradients from the masked tensors
+            dg, dbt, _ = _ln_bwd(be, dy, yl, xd, gamma, beta, mean, rstd, dz)
+            dza = _new(R, d, f32, dy)
+            be.dropout(dz, dza, *ctx.drop_out)
+            dz_op = _cast_op(be, dza)
+            dw2, db2 = _wgrad(be, dz_op, h, w2, b2, True, True)
             be.linear_bwd_data(dz_op, w2o, dh, relu_y=h)
             be.dropout(dh, dh, *ctx.drop_h)
             dw1, db1 = _wgrad(be, dh, xo, w1, b1, True, True)
             be.linear_bwd_data(dh, w1o, dz, accumulate=True)
             return dz, None, dw1, db1, dw2, db2, dg, dbt, None, None
+        if ctx.drop_out:
+            # dropout in bf16 mode rides in the kernels of the dropout-free path: the LayerNorm backward applies the output mask
+            # (dz_op = bf16(mask(dz)), db2 fused); the saved h is the DROPPED activation, so the dgrad epilogue's ReLU mask is
+            # already the product of both masks and only the 1 / keep factor is left (alpha): no mask is regenerated
+            alpha = _drop_scale(ctx.drop_h[0])
         dz_op = _new(R, d, od, dy) if bf else dz
-        dg, dbt, db2 = _ln_bwd(be, dy, yl, xd, gamma, beta, mean, rstd, dz, dz_op if bf else None, b2)
+        dg, dbt, db2 = _ln_bwd(be, dy, yl, xd, gamma, beta, mean, rstd, dz, dz_op if bf else None, b2, drop=ctx.ln_drop)
         dw2, _ = _wgrad(be, dz_op, h, w2, None, True, False)
         # dh = (dz W2) * (h > 0) with db1 = colsum(dh): ReLU backward and the bias gradient ride in the dgrad epilogue
         if _fuse_grads and b1.grad is not None:
             db1 = None
-            be.linear_bwd_data(dz_op, w2o, dh, relu_y=h, dbias=b1.grad)
+            be.linear_bwd_data(dz_op, w2o, dh, relu_y=h, dbias=b1.grad, alpha=alpha)
         else:
             db1 = torch.zeros(F_, dtype=f32, device=dy.device)
-            be.linear_bwd_data(dz_op, w2o, dh, relu_y=h, dbias=db1)
+            be.linear_bwd_data(dz_op, w2o, dh, relu_y=h, dbias=db1, alpha=alpha)
         dw1, _ = _wgrad(be, dh, xo, w1, None, True, False)
         be.linear_bwd_data(dh, w1o, dz, accumulate=True)
         return dz, None, dw1, db1, dw2, db2, dg, dbt, None, None

@@ -96,8 +96,21 @@ class EmuBackend:
         _store(y, v)
         self.launches += 1
 
-    def linear_bwd_data(self, dy, w, dx, accumulate=False, relu_y=None, dbias=None):
+    def linear_dropout_fwd(self, x, w, bias, y, relu, drop):
+        _mat(x, "x"), _mat(w, "w"), _mat(y, "y"), _flat(bias, "bias", F32)
+        assert w.shape[1] == x.shape[1] and tuple(y.shape) == (x.shape[0], w.shape[0]) and y.is_contiguous()
+        v = _f(x) @ _f(w).t()
+        if bias is not None:
+            v = v + bias
+        if relu:
+            v = v.relu()
+        keep, sc = drop_keep_scale(v.numel(), drop[0], drop[1], drop[2], v.device)
+        _store(y, v * (keep.reshape(v.shape).float() * sc))
+        self.launches += 1
+
+    def linear_bwd_data(self, dy, w, dx, accumulate=False, relu_y=None, dbias=None, alpha=1.0):
         _mat(dy, "dy"), _mat(w, "w"), _mat(dx, "dx"), _flat(dbias, "dbias", F32)
+        assert alpha == 1.0 or (relu_y is not None and not accumulate)
         assert w.shape[0] == dy.shape[1] and tuple(dx.shape) == (dy.shape[0], w.shape[1])
         if relu_y is not None:
             _mat(relu_y, "relu_y")
@@ -105,6 +118,8 @@ class EmuBackend:
         v = _f(dy) @ _f(w)
         if accumulate:
             v = v + _f(dx)
+        if alpha != 1.0:
+            v = v * alpha
         if relu_y is not None:
             v = v * (_f(relu_y) > 0)
         _store(dx, v)

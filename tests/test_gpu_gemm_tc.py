@@ -246,3 +246,31 @@ def test_cluster_split_k_is_bit_reproducible(be):
     for _ in range(5):
         be.linear_fwd(x, w, None, y2)
         assert torch.equal(y1, y2)
+
+
+@pytest.mark.parametrize("M,N,K", [(13632, 2048, 256), (64, 2048, 256), (1000, 512, 256), (300, 264, 72)])
+def test_dropout_in_the_epilogue_and_scaled_relu_backward(be, M, N, K):
+    """stcat_linear_dropout_fwd: y = drop(relu(x W^T + b)) with the mask drawn in the GEMM epilogue == the plain launch followed
+    by stcat_dropout, bit for bit (warp epilogue, weight-resident and skinny-tile variants).  stcat_linear_bwd_data_scaled:
+    dx = alpha (dy W) where the DROPPED activation is > 0 == ReLU mask, then dropout, of the unscaled product."""
+    p, seed, off = 0.1, 777, (1 << 34) + 5
+    x, w = g(M, K, seed=1).cuda(), g(N, K, seed=2, scale=K ** -0.5).cuda()
+    b = torch.randn(N, generator=torch.Generator().manual_seed(3)).cuda()
+    y = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    be.linear_dropout_fwd(x, w, b, y, True, (p, seed, off))
+    y0 = torch.empty(M, N, device="cuda")
+    be.linear_fwd(x, w, b, y0, relu=True)          # fp32 result of the same accumulation
+    be.dropout(y0, y0, p, seed, off)
+    assert torch.equal(y, y0.to(torch.bfloat16))
+    assert abs(float((y == 0).float().mean()) - float(((y0 == 0)).float().mean())) == 0
+    if N % 64 == 0:
+        # backward of the pair: h = y (dropped activation), dz [M, K2] with the second Linear's weight [K2, N]
+        K2 = 256
+        dz, w2 = g(M, K2, seed=4).cuda(), g(K2, N, seed=5, scale=K2 ** -0.5).cuda()
+        alpha = 16777216.0 / (16777216.0 - int(float(torch.tensor(p)) * 16777216.0))
+        dh = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+        db = torch.zeros(N, device="cuda")
+        be.linear_bwd_data(dz, w2, dh, relu_y=y, dbias=db, alpha=alpha)
+        ref = (dz.double() @ w2.double()) * (y.double() > 0) * alpha
+        assert rel_err(dh, ref) < TOL_BF16
+        assert rel_err(db, dh.double().sum(0)) < 1e-4
