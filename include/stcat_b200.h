@@ -41,7 +41,7 @@ extern "C" {
 
 /* Bumped whenever a signature or the meaning of an argument changes; stcat_b200/cabi.py refuses a library whose version
  * differs from the one it was written against (a stale locally built .so would otherwise be called with new signatures). */
-#define STCAT_ABI_VERSION 9
+#define STCAT_ABI_VERSION 10
 STCAT_API int stcat_abi_version(void);
 STCAT_API const char* stcat_last_error(void);
 /* compute capability major*10+minor of the current device, or <0; 100 expected */
@@ -199,13 +199,19 @@ STCAT_API int stcat_set_dropout_step(const void* counter);
 STCAT_API int stcat_attention_dropout_fwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2, int64_t ldk,
                                 const void* v, int64_t ldv, void* o, int64_t ldo, int dtype, const uint8_t* key_mask,
                                 float* lse, float* p_avg, int B, int H, int Lq, int Lk, int dh, float scale, float drop_p,
-                                uint64_t seed, uint64_t offset, void* stream);
+                                uint64_t seed, uint64_t offset, const void* keep_bits, int bits_wpr, void* stream);
 STCAT_API int stcat_attention_dropout_bwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2, int64_t ldk,
                                 const void* v, int64_t ldv, const void* o, int64_t ldo, const void* d_o, int64_t lddo, int dtype,
                                 const uint8_t* key_mask,
                                 const float* lse, const float* dp_avg, float* delta, void* dq1, void* dq2, int64_t lddq,
                                 void* dk1, void* dk2, int64_t lddk, void* dv, int64_t lddv, int B, int H, int Lq, int Lk, int dh,
-                                float scale, float drop_p, uint64_t seed, uint64_t offset, void* stream);
+                                float scale, float drop_p, uint64_t seed, uint64_t offset, const void* keep_bits, int bits_wpr,
+                                void* stream);
+/* keep_bits (optional, NULL = every kernel hashes per probability): the site's keep mask precomputed by stcat_dropout_bits with
+ * rows = B*H*Lq, cols = Lk and bits_wpr >= Lk / 32 + 1 words per row (bit j of word w of row r = keep(r * Lk + 32 w + j), same
+ * (p, seed, offset), same dropout step).  The tcgen05 kernels then read one word per 32 probabilities instead of hashing inside
+ * their MUFU-bound loops; the generator is one HBM-light kernel that can run on a side stream under the projection GEMMs. */
+STCAT_API int stcat_dropout_bits(void* bits, int64_t rows, int cols, int wpr, float p, uint64_t seed, uint64_t offset, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Optimizer-side step over a contiguous fp32 range of flat parameter / gradient / state buffers.

@@ -11,7 +11,7 @@ d = json.load(open("gpurun_out/r2_ai_bench_$i.json"))
 print("dropout 0 step: ms", round(d["ms_per_step"], 3), "clips/s", round(d["value"], 1), d["clocks"])
 PY
 done
-timeout 600 python -m pytest tests/test_gpu_gemm_tc.py tests/test_gpu_hotpath.py tests/test_gpu_train_step.py -q -m gpu -k "dropout or train or fwd_bf16 or relu_mask" 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_gpu_attention_tc.py tests/test_gpu_kernels.py tests/test_gpu_hotpath.py tests/test_gpu_train_step.py -q -m gpu -k "dropout or train" 2>&1 | tail -3
 timeout 400 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --dropout 0.1 > gpurun_out/r2_ai_bench_dropout01.json 2> gpurun_out/r2_ai_bench_dropout01.err
 python - <<PY
 import json

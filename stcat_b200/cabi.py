@@ -60,9 +60,10 @@ SIGNATURES["stcat_linear_bwd_data_scaled"] = (c_int, [_P, _L, _I, _P, _L, _I, _P
 SIGNATURES["stcat_layernorm_dropout_fwd"] = (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _U64, _U64, _P])
 SIGNATURES["stcat_layernorm_dropout_bwd"] = (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _U64, _U64, _P])
 SIGNATURES["stcat_attention_dropout_fwd"] = (c_int, [_P, _P, _L, _P, _P, _L, _P, _L, _P, _L, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F,
-                                                     _F, _U64, _U64, _P])
+                                                     _F, _U64, _U64, _P, _I, _P])
 SIGNATURES["stcat_attention_dropout_bwd"] = (c_int, [_P, _P, _L, _P, _P, _L, _P, _L, _P, _L, _P, _L, _I, _P, _P, _P, _P, _P, _P, _L,
-                                                     _P, _P, _L, _P, _L, _I, _I, _I, _I, _I, _F, _F, _U64, _U64, _P])
+                                                     _P, _P, _L, _P, _L, _I, _I, _I, _I, _I, _F, _F, _U64, _U64, _P, _I, _P])
+SIGNATURES["stcat_dropout_bits"] = (c_int, [_P, _L, _I, _I, _F, _U64, _U64, _P])
 SIGNATURES["stcat_sumsq"] = (c_int, [_P, _L, _P, _P])
 SIGNATURES["stcat_adamw_step"] = (c_int, [_P, _P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _L, _P, _F, _F, _P])
 SIGNATURES["stcat_debug_attn_trace"] = (c_int, [_P])
@@ -80,7 +81,7 @@ SIGNATURES["stcat_box_refine_bwd"] = (c_int, [_P, _P, _P, _P, _P, _L, _F, _P])
 SIGNATURES["stcat_stg_loss"] = (c_int, [_P] * 12 + [ctypes.POINTER(c_float), _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P])
 SIGNATURES["stcat_linear_group"] = (c_int, [_I, _I, ctypes.POINTER(_Job), _I, _P])
 MAX_GROUP_JOBS = 12
-ABI_VERSION = 9  # include/stcat_b200.h STCAT_ABI_VERSION
+ABI_VERSION = 10  # include/stcat_b200.h STCAT_ABI_VERSION
 
 _lib = None
 
@@ -307,8 +308,22 @@ class CudaBackend:
                                         self._stream()), "dropout")
         self.launches += 1
 
-    def attention_fwd(self, q1, q2, k1, k2, v, o, key_mask, lse, p_avg, B, H, Lq, Lk, scale, drop=None):
-        """q*: [B*Lq, H*32] views, k*/v: [B*Lk, H*32] views, o: [B*Lq, H*32]; q2/k2 share q1/k1's leading dim."""
+    def dropout_bits(self, bits, cols, p, seed, offset):
+        """bits [rows, wpr] int32: the keep mask of a [rows, cols] dropout site, one bit per element (stcat_dropout_bits)"""
+        assert bits.dtype == torch.int32 and bits.is_contiguous() and bits.shape[1] * 32 >= cols
+        self._rc(self.lib.stcat_dropout_bits(bits.data_ptr(), bits.shape[0], int(cols), bits.shape[1], float(p), int(seed), int(offset),
+                                             self._stream()), "dropout_bits")
+        self.launches += 1
+
+    def _bits(self, bits, rows):
+        if bits is None:
+            return None, 0
+        assert bits.is_cuda and bits.dtype == torch.int32 and bits.is_contiguous() and bits.shape[0] == rows
+        return bits.data_ptr(), bits.shape[1]
+
+    def attention_fwd(self, q1, q2, k1, k2, v, o, key_mask, lse, p_avg, B, H, Lq, Lk, scale, drop=None, bits=None):
+        """q*: [B*Lq, H*32] views, k*/v: [B*Lk, H*32] views, o: [B*Lq, H*32]; q2/k2 share q1/k1's leading dim.
+        ``bits``: optional precomputed keep bits of the dropout site (dropout_bits with rows = B*H*Lq, cols = Lk)."""
         (qp, ldq, qd) = self._mat(q1, "q1")
         (kp, ldk, _), (vp, ldv, _), (op, ldo, _) = self._mat(k1, "k1"), self._mat(v, "v"), self._mat(o, "o")
         q2p = k2p = None
@@ -321,7 +336,7 @@ class CudaBackend:
             self._rc(self.lib.stcat_attention_dropout_fwd(
                 qp, q2p, ldq, kp, k2p, ldk, vp, ldv, op, ldo, qd, self._flat(key_mask, "key_mask", torch.uint8),
                 self._flat(lse, "lse", torch.float32), self._flat(p_avg, "p_avg", torch.float32), B, H, Lq, Lk, 32, float(scale),
-                float(drop[0]), int(drop[1]), int(drop[2]), self._stream()), "attention_dropout_fwd")
+                float(drop[0]), int(drop[1]), int(drop[2]), *self._bits(bits, B * H * Lq), self._stream()), "attention_dropout_fwd")
             self.launches += 1
             return
         self._rc(self.lib.stcat_attention_fwd(qp, q2p, ldq, kp, k2p, ldk, vp, ldv, op, ldo, qd,
@@ -331,7 +346,7 @@ class CudaBackend:
         self.launches += 1
 
     def attention_bwd(self, q1, q2, k1, k2, v, d_o, key_mask, lse, dp_avg, delta, dq1, dq2, dk1, dk2, dv, B, H, Lq, Lk,
-                      scale, o=None, drop=None):
+                      scale, o=None, drop=None, bits=None):
         (qp, ldq, qd) = self._mat(q1, "q1")
         (kp, ldk, _), (vp, ldv, _), (gp, ldg, _) = self._mat(k1, "k1"), self._mat(v, "v"), self._mat(d_o, "d_o")
         (dqp, lddq, _), (dkp, lddk, _), (dvp, lddv, _) = self._mat(dq1, "dq1"), self._mat(dk1, "dk1"), self._mat(dv, "dv")
@@ -348,7 +363,8 @@ class CudaBackend:
                 qp, q2p, ldq, kp, k2p, ldk, vp, ldv, op, ldo, gp, ldg, qd, self._flat(key_mask, "key_mask", torch.uint8),
                 self._flat(lse, "lse", torch.float32), self._flat(dp_avg, "dp_avg", torch.float32),
                 self._flat(delta, "delta", torch.float32), dqp, dq2p, lddq, dkp, dk2p, lddk, dvp, lddv, B, H, Lq, Lk, 32,
-                float(scale), float(drop[0]), int(drop[1]), int(drop[2]), self._stream()), "attention_dropout_bwd")
+                float(scale), float(drop[0]), int(drop[1]), int(drop[2]), *self._bits(bits, B * H * Lq), self._stream()),
+                "attention_dropout_bwd")
             self.launches += 2
             return
         self._rc(self.lib.stcat_attention_bwd(qp, q2p, ldq, kp, k2p, ldk, vp, ldv, op, ldo, gp, ldg, qd,

@@ -585,10 +585,14 @@ extern "C" int stcat_attention_bwd(const void* q1, const void* q2, int64_t ldq, 
 extern "C" int stcat_attention_dropout_fwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2,
                                            int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo, int dtype,
                                            const uint8_t* key_mask, float* lse, float* p_avg, int B, int H, int Lq, int Lk,
-                                           int dh, float scale, float drop_p, uint64_t seed, uint64_t offset, void* stream) {
+                                           int dh, float scale, float drop_p, uint64_t seed, uint64_t offset,
+                                           const void* keep_bits, int bits_wpr, void* stream) {
     STCAT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, STCAT_EINVAL, "attention_dropout_fwd: p=%f", (double)drop_p);
+    STCAT_REQUIRE(!keep_bits || bits_wpr * 32 >= Lk + 32, STCAT_EINVAL, "attention_dropout_fwd: keep_bits needs Lk / 32 + 1 words per row");
+    DropArgs d = make_drop(drop_p, seed, offset);
+    if (d.thresh) { d.bits = (const uint32_t*)keep_bits; d.wpr = bits_wpr; }
     return attention_fwd_impl("attention_dropout_fwd", q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, dtype, key_mask, lse, p_avg, B,
-                              H, Lq, Lk, dh, scale, stream, make_drop(drop_p, seed, offset));
+                              H, Lq, Lk, dh, scale, stream, d);
 }
 
 extern "C" int stcat_attention_dropout_bwd(const void* q1, const void* q2, int64_t ldq, const void* k1, const void* k2,
@@ -597,9 +601,11 @@ extern "C" int stcat_attention_dropout_bwd(const void* q1, const void* q2, int64
                                            const uint8_t* key_mask, const float* lse, const float* dp_avg, float* delta,
                                            void* dq1, void* dq2, int64_t lddq, void* dk1, void* dk2, int64_t lddk, void* dv,
                                            int64_t lddv, int B, int H, int Lq, int Lk, int dh, float scale, float drop_p,
-                                           uint64_t seed, uint64_t offset, void* stream) {
+                                           uint64_t seed, uint64_t offset, const void* keep_bits, int bits_wpr, void* stream) {
     STCAT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, STCAT_EINVAL, "attention_dropout_bwd: p=%f", (double)drop_p);
+    STCAT_REQUIRE(!keep_bits || bits_wpr * 32 >= Lk + 32, STCAT_EINVAL, "attention_dropout_bwd: keep_bits needs Lk / 32 + 1 words per row");
+    DropArgs d = make_drop(drop_p, seed, offset);
+    if (d.thresh) { d.bits = (const uint32_t*)keep_bits; d.wpr = bits_wpr; }
     return attention_bwd_impl("attention_dropout_bwd", q1, q2, ldq, k1, k2, ldk, v, ldv, o, ldo, d_o, lddo, dtype, key_mask, lse,
-                              dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, dh, scale, stream,
-                              make_drop(drop_p, seed, offset));
+                              dp_avg, delta, dq1, dq2, lddq, dk1, dk2, lddk, dv, lddv, B, H, Lq, Lk, dh, scale, stream, d);
 }

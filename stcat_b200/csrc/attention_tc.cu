@@ -326,6 +326,18 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 if (!m && p.key_mask) m = p.key_mask[(int64_t)b * S + key] != 0;
                 mw[c] = __ballot_sync(0xffffffffu, m);
             }
+            // dropout with precomputed keep bits (DropArgs::bits): the words covering this thread's columns of its row, loaded
+            // here so that their latency hides behind the wait for the score MMA
+            uint32_t kwr[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+            if (DROP && dr.bits != nullptr) {
+                const int qrow = qt * AT_QT + row;
+                if (qrow < S) {
+                    const uint32_t* rb = dr.bits + (((int64_t)b * p.H + h) * S + qrow) * dr.wpr + (c0 >> 5);
+                    const int nw = dr.wpr - (c0 >> 5);
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) kwr[j] = j < nw ? __ldg(rb + j) : 0u;
+                }
+            }
             if (tr) T(i, 8);
             mbar_wait(bar(set, 2), k & 1);
             if (tr) T(i, 9);
@@ -383,8 +395,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             // dropout: element index of (b, h, query, key 0) in the [B, H, S, S] probability tensor; the row sum (and so
             // lse and the 1/sum of the epilogue) stays that of the undropped softmax
             const uint64_t drow = DROP ? (((uint64_t)b * p.H + h) * S + (qt * AT_QT + row)) * (uint64_t)S : 0ull;
-            auto exp_chunk = [&](auto wtag, const uint32_t* r, const int col, const uint32_t wm) {
-                constexpr int W = decltype(wtag)::value;
+            auto exp_chunk = [&](auto wtag, const uint32_t* r, const int col, const uint32_t wm, const uint32_t kw) {
+                constexpr int W = decltype(wtag)::value;  // kw: keep bits of the chunk's columns (bit e = column col + e)
                 uint32_t pk[W / 2];
 #pragma unroll
                 for (int e = 0; e < W; e += 4) {
@@ -400,10 +412,17 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     }
                     s0 += p0; s1 += p1; s2 += p2; s3 += p3;
                     if (DROP) {
-                        p0 *= drop_mult(dr, drow + col + e);
-                        p1 *= drop_mult(dr, drow + col + e + 1);
-                        p2 *= drop_mult(dr, drow + col + e + 2);
-                        p3 *= drop_mult(dr, drow + col + e + 3);
+                        if (dr.bits != nullptr) {
+                            p0 = ((kw >> e) & 1u) ? p0 * dr.scale : 0.f;
+                            p1 = ((kw >> (e + 1)) & 1u) ? p1 * dr.scale : 0.f;
+                            p2 = ((kw >> (e + 2)) & 1u) ? p2 * dr.scale : 0.f;
+                            p3 = ((kw >> (e + 3)) & 1u) ? p3 * dr.scale : 0.f;
+                        } else {
+                            p0 *= drop_mult(dr, drow + col + e);
+                            p1 *= drop_mult(dr, drow + col + e + 1);
+                            p2 *= drop_mult(dr, drow + col + e + 2);
+                            p3 *= drop_mult(dr, drow + col + e + 3);
+                        }
                     }
                     __nv_bfloat162 b01 = __floats2bfloat162_rn(p0, p1), b23 = __floats2bfloat162_rn(p2, p3);
                     pk[e >> 1] = *reinterpret_cast<uint32_t*>(&b01);
@@ -424,7 +443,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         uint32_t r[32];
                         tmem_ld32(t_row + c * 32, r);
                         tmem_ld_wait();
-                        exp_chunk(std::integral_constant<int, 32>(), r, c0 + c * 32, mw[c]);
+                        // chunk c starts (c0 & 31) bits into word c of kwr (c0 is a multiple of 16)
+                        exp_chunk(std::integral_constant<int, 32>(), r, c0 + c * 32, mw[c], __funnelshift_r(kwr[c], kwr[c + 1], c0 & 31));
                     }
                 }
                 if (tail) {
@@ -432,7 +452,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     tmem_ld16(t_row + nfull * 32, r);
                     tmem_ld_wait();
                     const uint32_t wm = (nfull == 0 ? mw[0] : nfull == 1 ? mw[1] : nfull == 2 ? mw[2] : nfull == 3 ? mw[3] : mw[4]);
-                    exp_chunk(std::integral_constant<int, 16>(), r, c0 + nfull * 32, wm);
+                    const uint32_t ka = (nfull == 0 ? kwr[0] : nfull == 1 ? kwr[1] : nfull == 2 ? kwr[2] : nfull == 3 ? kwr[3] : kwr[4]);
+                    const uint32_t kb = (nfull == 0 ? kwr[1] : nfull == 1 ? kwr[2] : nfull == 2 ? kwr[3] : nfull == 3 ? kwr[4] : kwr[5]);
+                    exp_chunk(std::integral_constant<int, 16>(), r, c0 + nfull * 32, wm, __funnelshift_r(ka, kb, c0 & 31));
                 }
             }
             float sum = (s0 + s1) + (s2 + s3);
@@ -797,6 +819,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             // dropout (o = (P o M) V): delta = dO . O still equals sum_j P_ij (M o dP)_ij; the P tile feeding dV is
             // P o M, and dS = P o (M o dP - delta) * scale
             const uint64_t drow = DROP ? (((uint64_t)b * p.H + h) * S + (qt * 128 + row)) * (uint64_t)S : 0ull;
+            // precomputed keep bits (DropArgs::bits) of this thread's two 32-key chunks of the block: loaded before the wait for
+            // the score MMAs; key column kt * 128 + wg * 64 + c * 32 is word-aligned
+            uint32_t kbw[2] = {0u, 0u};
+            if (DROP && dr.bits != nullptr && qt * 128 + row < S) {
+                const uint32_t* rb = dr.bits + (((int64_t)b * p.H + h) * S + (qt * 128 + row)) * dr.wpr + kt * 4 + wg * 2;
+                kbw[0] = kt * 4 + wg * 2 < dr.wpr ? __ldg(rb) : 0u;
+                kbw[1] = kt * 4 + wg * 2 + 1 < dr.wpr ? __ldg(rb + 1) : 0u;
+            }
             if (tr) T(nb, 3);  // threads ready for the block
             mbar_wait(bar(4), nb & 1);
             if (tr) T(nb, 4);  // S / dP landed in TMEM
@@ -824,8 +854,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     for (int e = 0; e < 32; e += 2) {
                         const float p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), sc, -lse_eff));
                         const float p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), sc, -lse_eff));
-                        const float m0 = DROP ? drop_mult(dr, dcol + e) : 1.f;
-                        const float m1 = DROP ? drop_mult(dr, dcol + e + 1) : 1.f;
+                        const float m0 = !DROP ? 1.f : dr.bits != nullptr ? (((kbw[c] >> e) & 1u) ? dr.scale : 0.f) : drop_mult(dr, dcol + e);
+                        const float m1 = !DROP ? 1.f : dr.bits != nullptr ? (((kbw[c] >> (e + 1)) & 1u) ? dr.scale : 0.f) : drop_mult(dr, dcol + e + 1);
                         const float d0 = dead ? 0.f : p0 * (__uint_as_float(rd[e]) * m0 - delta) * dsc;
                         const float d1 = dead ? 0.f : p1 * (__uint_as_float(rd[e + 1]) * m1 - delta) * dsc;
                         __nv_bfloat162 bp = __floats2bfloat162_rn(p0 * m0, p1 * m1), bd = __floats2bfloat162_rn(d0, d1);
@@ -838,13 +868,13 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     for (int e = 0; e < 32; e += 2) {
                         float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
                         if (!((wmask >> e) & 1u)) {
-                            const float m0 = DROP ? drop_mult(dr, dcol + e) : 1.f;
+                            const float m0 = !DROP ? 1.f : dr.bits != nullptr ? (((kbw[c] >> e) & 1u) ? dr.scale : 0.f) : drop_mult(dr, dcol + e);
                             p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), sc, -l2));
                             d0 = p0 * (__uint_as_float(rd[e]) * m0 - delta) * p.scale;
                             p0 *= m0;
                         }
                         if (!((wmask >> (e + 1)) & 1u)) {
-                            const float m1 = DROP ? drop_mult(dr, dcol + e + 1) : 1.f;
+                            const float m1 = !DROP ? 1.f : dr.bits != nullptr ? (((kbw[c] >> (e + 1)) & 1u) ? dr.scale : 0.f) : drop_mult(dr, dcol + e + 1);
                             p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), sc, -l2));
                             d1 = p1 * (__uint_as_float(rd[e + 1]) * m1 - delta) * p.scale;
                             p1 *= m1;

@@ -99,6 +99,11 @@ struct DropArgs {            // thresh == 0: no dropout
     float scale = 1.f;       // 1 / keep probability
     uint64_t seed = 0, offset = 0;
     const uint64_t* step = nullptr;  // optional device-resident step counter (stcat_set_dropout_step): see drop_resolve
+    // optional precomputed keep bits of an attention site (stcat_dropout_bits): row r of the [B*H*Lq, Lk] probability matrix owns
+    // `wpr` 32-bit words, bit j of word w = keep(r * Lk + 32 w + j).  The tcgen05 attention kernels read them instead of hashing
+    // (the hash is ~10 integer instructions per probability inside MUFU-bound loops); every other kernel ignores them.
+    const uint32_t* bits = nullptr;
+    int wpr = 0;
 };
 // Host state: the device counter every dropout site mixes into its seed.  With it, a CUDA-graph replay of a captured
 // training step draws fresh masks (the captured step increments the counter once, after its backward pass); without it

@@ -453,6 +453,38 @@ extern "C" int stcat_box_refine_bwd(const float* out, const float* anchor, const
     return check_launch("box_refine_bwd_kernel");
 }
 
+// keep bits of a [rows, cols] dropout site, one thread per 32-bit word (see DropArgs::bits)
+__global__ void __launch_bounds__(256)
+drop_bits_kernel(uint32_t* __restrict__ bits, int64_t rows, int cols, int wpr, const DropArgs drop_in) {
+    const DropArgs drop = drop_resolve(drop_in);
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t total = rows * wpr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / wpr;
+        const int w = (int)(i - r * wpr);
+        uint32_t word = 0;
+        const int c0 = w * 32;
+        if (c0 < cols) {
+            const uint64_t e0 = (uint64_t)r * (uint64_t)cols + c0;
+            const int n = min(32, cols - c0);
+            const uint64_t z0 = drop.offset + e0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)  // 32 independent hashes
+                word |= ((j < n && drop_bits24(drop.seed, z0 + j) >= drop.thresh) ? 1u : 0u) << j;
+        }
+        bits[i] = word;
+    }
+}
+
+extern "C" int stcat_dropout_bits(void* bits, int64_t rows, int cols, int wpr, float p, uint64_t seed, uint64_t offset, void* stream) {
+    STCAT_REQUIRE(bits && rows >= 0 && cols > 0 && wpr * 32 >= cols && p > 0.f && p < 1.f, STCAT_EINVAL, "dropout_bits: bad arguments");
+    if (rows == 0) return 0;
+    const DropArgs d = make_drop(p, seed, offset);
+    launch_pdl(drop_bits_kernel, dim3(grid_for(rows * wpr)), dim3(256), 0, (cudaStream_t)stream, (uint32_t*)bits, rows, cols, wpr, d);
+    return check_launch("drop_bits_kernel");
+}
+
 extern "C" int stcat_dropout(const void* x, void* out, int dtype, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
     STCAT_REQUIRE(x && out && n >= 0 && p >= 0.f && p < 1.f, STCAT_EINVAL, "dropout: bad arguments (p=%f)", (double)p);
     if (n == 0) return 0;

@@ -243,6 +243,29 @@ def _drop_scale(p: float) -> float:
     return float(torch.tensor(16777216.0 / (16777216.0 - t), dtype=torch.float32))
 
 
+_bits_streams = {}
+
+
+def _attn_keep_bits(be, B, H, L, drop, like):
+    """Keep bits of an attention dropout site [B*H*L, L] for the tcgen05 kernels (include/stcat_b200.h stcat_dropout_bits): one
+    word per 32 probabilities instead of a hash per probability inside the kernels' MUFU-bound loops.  Generated on a side
+    stream forked here (the caller joins with the returned stream before the attention launch), so the generator runs under the
+    projection GEMMs in front of the attention.  Returns (bits or None, side stream or None); None for shapes the tcgen05 kernels
+    do not take (every other kernel hashes)."""
+    if not (like.is_cuda and _opdtype() == torch.bfloat16 and 64 <= L <= 512 and (L > 128 or B * H >= 16)):
+        return None, None
+    bits = torch.empty(B * H * L, L // 32 + 2, dtype=torch.int32, device=like.device)
+    cur = torch.cuda.current_stream()
+    side = _bits_streams.get(cur.cuda_stream)
+    if side is None:
+        side = _bits_streams[cur.cuda_stream] = torch.cuda.Stream(like.device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        bits.record_stream(side)
+        be.dropout_bits(bits, L, *drop)
+    return bits, side
+
+
 def _drop_reserve(n: int):
     if _drop_state["seed"] is None:
         set_dropout_seed(torch.initial_seed())
@@ -840,6 +863,9 @@ class SelfAttnBlockFn(Function):
         bf = od == torch.bfloat16
         xd, posd = x.detach(), pos.detach()
         posd = posd if posd.is_contiguous() else posd.contiguous()
+        bits = side = None
+        if ctx.drop_attn:  # forked first: the (ALU-bound) generator runs under the HBM-bound add and the projection GEMMs
+            bits, side = _attn_keep_bits(be, B, H, L, ctx.drop_attn, xd)
         if bf:
             qk_in = _new(R, d, od, x)
             be.add(xd, posd, None, qk_in)
@@ -858,8 +884,15 @@ class SelfAttnBlockFn(Function):
         o = _new(R, d, od, x)
         lse = torch.empty(B, H, L, dtype=torch.float32, device=x.device)
         scale = float(d // H) ** -0.5
-        be.attention_fwd(qkv[:, :d], None, qkv[:, d:2 * d], None, qkv[:, 2 * d:], o, key_mask, lse, None, B, H, L, L,
-                         scale, drop=ctx.drop_attn)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        if bits is not None:
+            be.attention_fwd(qkv[:, :d], None, qkv[:, d:2 * d], None, qkv[:, 2 * d:], o, key_mask, lse, None, B, H, L, L,
+                             scale, drop=ctx.drop_attn, bits=bits)
+        else:
+            be.attention_fwd(qkv[:, :d], None, qkv[:, d:2 * d], None, qkv[:, 2 * d:], o, key_mask, lse, None, B, H, L, L,
+                             scale, drop=ctx.drop_attn)
+        ctx.keep_bits = bits
         a = _new(R, d, torch.float32, x)
         be.linear_fwd(o, wo, b_out.detach(), a)
         # the block-output dropout rides in the LayerNorm kernels in bf16 mode (mask on load forward; masked operand copy and
@@ -914,9 +947,14 @@ class SelfAttnBlockFn(Function):
         be.linear_bwd_data(dz_op, wo, d_o)
         dqkv = _new(R, 3 * d, od, dy)
         delta = torch.empty(B, H, L, dtype=f32, device=dy.device)
-        be.attention_bwd(qkv[:, :d], None, qkv[:, d:2 * d], None, qkv[:, 2 * d:], d_o, key_mask, lse, None, delta,
-                         dqkv[:, :d], None, dqkv[:, d:2 * d], None, dqkv[:, 2 * d:], B, H, L, L, scale, o=o,
-                         drop=ctx.drop_attn)
+        if ctx.keep_bits is not None:
+            be.attention_bwd(qkv[:, :d], None, qkv[:, d:2 * d], None, qkv[:, 2 * d:], d_o, key_mask, lse, None, delta,
+                             dqkv[:, :d], None, dqkv[:, d:2 * d], None, dqkv[:, 2 * d:], B, H, L, L, scale, o=o,
+                             drop=ctx.drop_attn, bits=ctx.keep_bits)
+        else:
+            be.attention_bwd(qkv[:, :d], None, qkv[:, d:2 * d], None, qkv[:, 2 * d:], d_o, key_mask, lse, None, delta,
+                             dqkv[:, :d], None, dqkv[:, d:2 * d], None, dqkv[:, 2 * d:], B, H, L, L, scale, o=o,
+                             drop=ctx.drop_attn)
         if _fuse_grads and w_in.grad is not None and b_in.grad is not None:
             gwi, gbi = w_in.grad, b_in.grad
             dwi = dbi = None

@@ -272,7 +272,18 @@ class EmuBackend:
 
         return kernel_attention_variant(B, H, Lq, Lk, q2 is not None, want_pavg)
 
-    def attention_fwd(self, q1, q2, k1, k2, v, o, key_mask, lse, p_avg, B, H, Lq, Lk, scale, drop=None):
+    def dropout_bits(self, bits, cols, p, seed, offset):
+        """the keep mask of a [rows, cols] site packed one bit per element (stcat_dropout_bits)"""
+        rows, wpr = bits.shape
+        assert bits.dtype == torch.int32 and wpr * 32 >= cols
+        keep, _ = drop_keep_scale(rows * cols, p, seed, offset, bits.device)
+        k = torch.zeros(rows, wpr * 32, dtype=torch.int64, device=bits.device)
+        k[:, :cols] = keep.reshape(rows, cols).to(torch.int64)
+        w = (k.view(rows, wpr, 32) << torch.arange(32, dtype=torch.int64, device=bits.device)).sum(-1)
+        bits.copy_(torch.where(w >= (1 << 31), w - (1 << 32), w).to(torch.int32))
+        self.launches += 1
+
+    def attention_fwd(self, q1, q2, k1, k2, v, o, key_mask, lse, p_avg, B, H, Lq, Lk, scale, drop=None, bits=None):
         self._attn_layout(q1, q2, k1, k2, B, H, Lq, Lk, ((v, "v", Lk), (o, "o", Lq)))
         _flat(key_mask, "key_mask", torch.uint8), _flat(lse, "lse", F32), _flat(p_avg, "p_avg", F32)
         s, hd = self._scores(q1, q2, k1, k2, key_mask, B, H, Lq, Lk, scale)
@@ -314,7 +325,7 @@ class EmuBackend:
         self.launches += 1
 
     def attention_bwd(self, q1, q2, k1, k2, v, d_o, key_mask, lse, dp_avg, delta, dq1, dq2, dk1, dk2, dv, B, H, Lq, Lk,
-                      scale, o=None, drop=None):
+                      scale, o=None, drop=None, bits=None):
         oth = [(v, "v", Lk), (d_o, "d_o", Lq), (dq1, "dq1", Lq), (dk1, "dk1", Lk), (dv, "dv", Lk)] + ([(o, "o", Lq)] if o is not None else [])
         self._attn_layout(q1, q2, k1, k2, B, H, Lq, Lk, oth)
         if q2 is not None:

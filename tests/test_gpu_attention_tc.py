@@ -157,7 +157,7 @@ def test_single_query_attention(be, B, H, Lk, two, use_mask, dt):
         assert rel_err(dk2, leaves[3].grad) < tol
 
 
-def _dropout_case(be, B, H, Lq, Lk, two, use_mask, dt, p, seed, off, pass_o=True):
+def _dropout_case(be, B, H, Lq, Lk, two, use_mask, dt, p, seed, off, pass_o=True, use_bits=False):
     """attention with dropout through the C ABI vs float64 attention with the explicit keep mask (emu_backend.drop_keep_scale
     restates the device hash bit for bit).  Returns the relative errors (o, lse, dq1, dk1, dv[, dq2, dk2])."""
     from emu_backend import drop_keep_scale
@@ -190,12 +190,20 @@ def _dropout_case(be, B, H, Lq, Lk, two, use_mask, dt, p, seed, off, pass_o=True
     o = torch.full((B * Lq, E), float("nan"), device="cuda", dtype=dt)
     lse = torch.empty(B, H, Lq, device="cuda")
     drop = (p, seed, off)
-    be.attention_fwd(c(q1), c(q2), c(k1), c(k2), c(v), o, c(mask), lse, None, B, H, Lq, Lk, scale, drop=drop)
+    bits = None
+    if use_bits:  # the site's keep mask precomputed, one bit per probability (stcat_dropout_bits)
+        bits = torch.full((B * H * Lq, Lk // 32 + 2), -1, dtype=torch.int32, device="cuda")
+        be.dropout_bits(bits, Lk, p, seed, off)
+        want = torch.zeros(B * H * Lq, (Lk // 32 + 2) * 32, dtype=torch.bool)
+        want[:, :Lk] = keep.view(B * H * Lq, Lk)
+        got = ((bits.cpu().to(torch.int64)[:, :, None] >> torch.arange(32)) & 1).bool().view(B * H * Lq, -1)
+        assert torch.equal(got, want)
+    be.attention_fwd(c(q1), c(q2), c(k1), c(k2), c(v), o, c(mask), lse, None, B, H, Lq, Lk, scale, drop=drop, bits=bits)
     e = lambda L: torch.full((B * L, E), float("nan"), device="cuda", dtype=dt)
     dq1, dk1, dv = e(Lq), e(Lk), e(Lk)
     dq2, dk2 = (e(Lq), e(Lk)) if two else (None, None)
     be.attention_bwd(c(q1), c(q2), c(k1), c(k2), c(v), c(d_o), c(mask), lse, None, torch.empty(B, H, Lq, device="cuda"),
-                     dq1, dq2, dk1, dk2, dv, B, H, Lq, Lk, scale, o=o if pass_o else None, drop=drop)
+                     dq1, dq2, dk1, dk2, dv, B, H, Lq, Lk, scale, o=o if pass_o else None, drop=drop, bits=bits)
     errs = [rel_err(o, o_ref), rel_err(lse, torch.logsumexp(s, -1)), rel_err(dq1, leaves[0].grad), rel_err(dk1, leaves[2].grad),
             rel_err(dv, leaves[4].grad)]
     if two:
@@ -212,6 +220,10 @@ def test_tcgen05_attention_with_dropout(be, B, H, S, use_mask, monkeypatch):
     errs, tc_out = _dropout_case(be, B, H, S, S, False, use_mask, torch.bfloat16, p, seed, off)
     print(f"tcgen05+dropout B={B} S={S}: o {errs[0]:.2e} lse {errs[1]:.2e} dq/dk/dv {errs[2]:.2e} {errs[3]:.2e} {errs[4]:.2e}")
     assert errs[1] < 1e-4 and errs[0] < 1e-2 and max(errs[2:]) < 1.5e-2
+    # the same masks read from precomputed keep bits instead of hashed in the kernels: identical results
+    errs_b, bits_out = _dropout_case(be, B, H, S, S, False, use_mask, torch.bfloat16, p, seed, off, use_bits=True)
+    for a, b in zip(tc_out, bits_out):
+        assert torch.equal(a, b)
     monkeypatch.setenv("STCAT_DISABLE_TC_ATTN", "1")  # read per call by the dispatcher: same problem through the SIMT kernels
     errs2, simt_out = _dropout_case(be, B, H, S, S, False, use_mask, torch.bfloat16, p, seed, off)
     assert errs2[1] < 1e-4 and errs2[0] < 1e-2 and max(errs2[2:]) < 1.5e-2
