@@ -265,8 +265,7 @@ class TransformerDecoderLayer(nn.Module):
             [(q, None), (k, None), (v, None)],
             [{"terms": [(i, sa.in_proj_weight, sa.in_proj_bias, (i * d, (i + 1) * d))], "out_bf16": True} for i in range(3)])
         o, _ = ops.attention(Q, K, V, c.b, H, c.t, c.t, float(d // H) ** -0.5, key_mask=c.query_mask, drop_p=p)
-        a = ops.dropout(_lin(self.self_attn.out_proj, o), p)
-        tgt, tgt_op = ops.layer_norm(a, tgt, self.norm1.weight, self.norm1.bias, self.norm1.eps, want_op=True)
+        tgt, tgt_op = ops.out_ln(o, tgt, sa.out_proj.weight, sa.out_proj.bias, self.norm1.weight, self.norm1.bias, self.norm1.eps, p)
         # ---- time-aligned cross attention: query of frame f sees only frame f's tokens (:350-429) ----
         kc, kp, vv = mem_kv() if callable(mem_kv) else mem_kv
         qc_terms = [(0, *L(self.ca_qcontent_proj))] + ([(1, *L(self.ca_qpos_proj))] if is_first else [])
@@ -276,7 +275,7 @@ class TransformerDecoderLayer(nn.Module):
                 [{"terms": qc_terms, "out_bf16": True}, {"terms": [(2, *L(self.ca_qpos_sine_proj))], "out_bf16": True}])
             o, _ = ops.attention(c.frames(qc), kc, vv, c.n, H, 1, c.M, float(2 * d // H) ** -0.5, key_mask=c.key_mask,
                                  q2=c.frames(qs), k2=kp, drop_p=p)
-            o = ops.dropout(_lin(self.cross_attn.out_proj, o), p)
+            cross_out = self.cross_attn.out_proj
         else:
             # q = ca_qcontent(tgt) [+ ca_qpos(query_pos)] + ca_qpos_sine(sine) + ca_qtime(time) (:355-376: the per-head views
             # of :371-375 add element-wise), then nn.MultiheadAttention: in-projection, one query per frame, out-projection
@@ -286,8 +285,12 @@ class TransformerDecoderLayer(nn.Module):
             ca = self.cross_attn_image
             Q = _mha_proj(ca, 0, c.frames(ops.add(qa, qt)), out_bf16=True)
             o, _ = ops.attention(Q, kc, vv, c.n, H, 1, c.M, float(d // H) ** -0.5, key_mask=c.key_mask, drop_p=p)
-            o = ops.dropout(_lin(ca.out_proj, o), p)
-        tgt, tgt_op = ops.layer_norm(c.padded(o), tgt, self.norm3.weight, self.norm3.bias, self.norm3.eps, want_op=True)
+            cross_out = ca.out_proj
+        if c.idx["identity"]:  # frames == query slots: out-projection + dropout + residual + norm as one node
+            tgt, tgt_op = ops.out_ln(o, tgt, cross_out.weight, cross_out.bias, self.norm3.weight, self.norm3.bias, self.norm3.eps, p)
+        else:
+            o = ops.dropout(_lin(cross_out, o), p)
+            tgt, tgt_op = ops.layer_norm(c.padded(o), tgt, self.norm3.weight, self.norm3.bias, self.norm3.eps, want_op=True)
         # ---- FFN (:435-437) ----
         return ops.ffn_block(tgt, tgt_op, self.linear1.weight, self.linear1.bias, self.linear2.weight,
                              self.linear2.bias, self.norm4.weight, self.norm4.bias, self.norm4.eps, drop_p=p)
@@ -380,14 +383,17 @@ class TimeDecoderLayer(nn.Module):
             [{"terms": [(0 if i < 2 else 1, sa.in_proj_weight, sa.in_proj_bias, (i * d, (i + 1) * d))], "out_bf16": True}
              for i in range(3)])
         o, weights = ops.attention(Q, K, V, c.b, H, c.t, c.t, scale, key_mask=c.query_mask, need_pavg=True, drop_p=p)
-        a = ops.dropout(_lin(self.self_attn.out_proj, o), p)
-        tgt = ops.layer_norm(a, tgt, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        tgt, _ = ops.out_ln(o, tgt, sa.out_proj.weight, sa.out_proj.bias, self.norm1.weight, self.norm1.bias, self.norm1.eps, p)
         # cross attention, one query per frame (:615-651)
         Q = _mha_proj(self.cross_attn_image, 0, c.frames(tgt) + query_pos_frames, out_bf16=True)
         K, V = mem_kv() if callable(mem_kv) else mem_kv
         o, _ = ops.attention(Q, K, V, c.n, H, 1, c.M, scale, key_mask=c.key_mask, drop_p=p)
-        o = ops.dropout(_lin(self.cross_attn_image.out_proj, o), p)
-        tgt, tgt_op = ops.layer_norm(c.padded(o), tgt, self.norm3.weight, self.norm3.bias, self.norm3.eps, want_op=True)
+        ca_out = self.cross_attn_image.out_proj
+        if c.idx["identity"]:
+            tgt, tgt_op = ops.out_ln(o, tgt, ca_out.weight, ca_out.bias, self.norm3.weight, self.norm3.bias, self.norm3.eps, p)
+        else:
+            o = ops.dropout(_lin(ca_out, o), p)
+            tgt, tgt_op = ops.layer_norm(c.padded(o), tgt, self.norm3.weight, self.norm3.bias, self.norm3.eps, want_op=True)
         tgt, tgt_op = ops.ffn_block(tgt, tgt_op, self.linear1.weight, self.linear1.bias, self.linear2.weight,
                                     self.linear2.bias, self.norm4.weight, self.norm4.bias, self.norm4.eps, drop_p=p)
         return tgt, tgt_op, weights

@@ -376,7 +376,11 @@ class LinearFn(Function):
         N, K = wd.shape
         dy2 = _rows(dy, N)
         if ctx.relu:
-            dy2 = dy2.clone() if dy2.data_ptr() == dy.data_ptr() else dy2
+            # A bf16 ReLU output is a hidden activation that feeds exactly one GEMM (callers pass out_bf16 only then): its gradient
+            # was produced for this node alone by that GEMM's data-gradient launch, so the mask is applied in place.  Otherwise
+            # (fp32 outputs may be user-visible) the incoming gradient is left untouched.
+            if not (y.dtype == torch.bfloat16 and dy2.dtype == torch.bfloat16):
+                dy2 = dy2.clone() if dy2.data_ptr() == dy.data_ptr() else dy2
             be.relu_bwd(y, dy2)
         dyo = _operand(dy2)
         M = dy2.shape[0]
@@ -563,7 +567,8 @@ class LinearGroupFn(Function):
             N = dy.shape[-1]
             dy2 = _rows(dy, N)
             if j.get("relu"):
-                dy2 = dy2.clone() if dy2.data_ptr() == dy.data_ptr() else dy2
+                if not (relu_ys[jx].dtype == torch.bfloat16 and dy2.dtype == torch.bfloat16):  # see LinearFn.backward
+                    dy2 = dy2.clone() if dy2.data_ptr() == dy.data_ptr() else dy2
                 be.relu_bwd(relu_ys[jx], dy2)
             dyos.append(_operand(dy2))
         # term table: (job index, input index, weight slice view, bias, rows)
@@ -991,6 +996,80 @@ class SelfAttnBlockFn(Function):
                     dpc = torch.empty(1, d, dtype=f32, device=dy.device)
                     be.linear_bwd_data(srow, w_in.detach()[: 2 * d], dpc)
         return dz, None, dpos, None, dwi, dbi, dwo, dbo, dg, dbt, None, None, None, None, dpc, None
+
+
+class OutLNFn(Function):
+    """y = LayerNorm(res + drop(o W^T + b)): out-projection of an attention block + block-output dropout + residual + norm
+    (query_decoder.py:342-345, 430-432, 610-613, 652-654) as one autograd node, like the tail of SelfAttnBlockFn: the
+    LayerNorm backward hands the (masked) bf16 operand copy of dz straight to the out-projection's gradient GEMMs and sums its
+    bias gradient -- no cast, no column-sum and, in train mode, no stand-alone dropout launches on the decoders' chains.
+    o [R, d] (operand dtype or fp32), res [R, d] fp32.  Returns (y fp32, y_op)."""
+
+    @staticmethod
+    def forward(ctx, o, res, w, b, gamma, beta, eps, drop_p=0.0):
+        be = get_backend()
+        R, d = res.shape
+        od = _opdtype()
+        bf = od == torch.bfloat16
+        o2 = o.detach()
+        o2 = o2 if o2.is_contiguous() else o2.contiguous()
+        oo = o2 if o2.dtype == od else _operand(o2)
+        resd = res.detach()
+        resd = resd if (resd.is_contiguous() and resd.dtype == torch.float32) else resd.contiguous().float()
+        wo = _operand(w.detach(), True)
+        a = _new(R, d, torch.float32, resd)
+        be.linear_fwd(oo, wo, b.detach(), a)
+        ctx.drop = ((float(drop_p),) + _drop_reserve(R * d)) if drop_p else None
+        ctx.ln_drop = ctx.drop if bf else None
+        if ctx.drop and not bf:
+            be.dropout(a, a, *ctx.drop)
+        y = _new(R, d, torch.float32, resd)
+        y_op = _new(R, d, od, resd) if bf else None
+        mean = torch.empty(R, dtype=torch.float32, device=resd.device)
+        rstd = torch.empty(R, dtype=torch.float32, device=resd.device)
+        be.layernorm_fwd(a, resd, gamma.detach(), beta.detach(), y, y_op, mean, rstd, eps, drop=ctx.ln_drop)
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(oo, a, resd, mean, rstd, w, gamma)
+        ctx.extra = (b, beta)
+        ctx.o_dtype = o.dtype
+        if bf:
+            ctx.mark_non_differentiable(y_op)
+        return y, y_op
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy, _unused):
+        if dy is None:
+            return (None,) * 8
+        be = get_backend()
+        oo, a, resd, mean, rstd, w, gamma = ctx.saved_tensors
+        b, beta = ctx.extra
+        R, d = resd.shape
+        f32 = torch.float32
+        bf = oo.dtype == torch.bfloat16
+        dy = dy if (dy.is_contiguous() and dy.dtype == f32) else dy.contiguous().float()
+        wo = _operand(w.detach(), True)
+        dz = _new(R, d, f32, dy)
+        if ctx.drop and not ctx.ln_drop:
+            dg, dbt, _ = _ln_bwd(be, dy, a, resd, gamma, beta, mean, rstd, dz)
+            dza = _new(R, d, f32, dy)
+            be.dropout(dz, dza, *ctx.drop)
+            dz_op = _cast_op(be, dza)
+            dw, db = _wgrad(be, dz_op, oo, w, b, True, True)
+        else:
+            dz_op = _new(R, d, oo.dtype, dy) if bf else dz
+            dg, dbt, db = _ln_bwd(be, dy, a, resd, gamma, beta, mean, rstd, dz, dz_op if bf else None, b, drop=ctx.ln_drop)
+            dw, _ = _wgrad(be, dz_op, oo, w, None, True, False)
+        d_o = None
+        if ctx.needs_input_grad[0]:
+            d_o = _new(R, d, ctx.o_dtype, dy)
+            be.linear_bwd_data(dz_op, wo, d_o)
+        return d_o, dz, dw, db, dg, dbt, None, None
+
+
+def out_ln(o, res, w, b, gamma, beta, eps: float = 1e-5, drop_p: float = 0.0):
+    """(y, y_op) = LayerNorm(res + dropout(o W^T + b)) -- see OutLNFn."""
+    return OutLNFn.apply(o, res, w, b, gamma, beta, eps, float(drop_p))
 
 
 class FFNBlockFn(Function):
