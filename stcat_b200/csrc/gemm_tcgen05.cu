@@ -10,16 +10,19 @@
 //   bwd_weight dw = dy^T . x       A(n,m) = dy[m,n] MN-major B(k,m) = x[m,k]      MN-major
 // so no transposed copies of activations are ever materialised.
 //
-// Structure (persistent, warp-specialised, 384 threads, 1 CTA / SM):
+// Structure (persistent, warp-specialised, 1 CTA / SM; 640 threads for the 128 x 256 tile, 256 for the 128 x 64 tile):
 //   warp 0      TMA producer  : 4-stage ring of {A 128x64, B 256x64} bf16 tiles (48 KB / stage), mbarrier full/empty
+//                               (weight-resident variant: the [256 x K] weight tile stays in shared memory, the ring holds A only)
 //   warp 1      MMA issuer    : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 128x256x16, 4 per stage;
 //                               tcgen05.commit releases the stage / publishes the accumulator
 //   warp 2      TMEM allocator: 512 columns = 2 accumulator stages of 128 lanes x 256 fp32 columns
-//   warps 4..11 epilogue      : two groups of 4 warps, one per 128-column half of the accumulator; each warp
-//                               tcgen05.ld's 32 lanes x 32 columns at a time, adds the bias slice staged in shared
-//                               memory, ReLU, converts, st.shared into the group's 128B-swizzled [128 x 128 B]
-//                               staging tile, one thread issues the TMA store / reduce-add; the next chunk's
-//                               TMEM loads are in flight while the previous store drains the staging tile
+//   warps 4..19 epilogue      : 128 x 256 tile ("warp epilogue"): 16 independent warps, (TMEM lane quadrant) x (64-column
+//                               group); each tcgen05.ld's 32 lanes x 32 columns at a time, adds the bias slice staged in shared
+//                               memory, ReLU / mask / dropout, converts, st.shared into ITS OWN 64B-swizzled [32 x 64 B] staging
+//                               tile and issues its own TMA store / reduce-add -- no barrier between warps inside a tile.
+//   warps 4..7  epilogue      : 128 x 64 tile: one group of 4 warps with a shared 128B-swizzled [128 x 128 B] staging tile
+//                               (also the former epilogue of the wide tile, kept behind STCAT_GEMM_WEPI=0);
+//                               cluster split-K variant: partial tiles parked in shared memory, reduced through DSMEM
 // M/N/K tails need no code: TMA zero-fills out-of-bounds loads and clips out-of-bounds stores.
 // Split-K (needed by bwd_weight, whose contraction runs over all M = T*S tokens while the output is one
 // or a few tiles) uses the TMA reduce-add epilogue on a pre-zeroed fp32 output.
