@@ -502,3 +502,55 @@ def test_block_dropout_in_bf16_mode_uses_the_fused_layernorm_mask(block):
     assert sum(1 for s in calls32 if tuple(s) == (R, d)) == 2 and sum(1 for s in calls16 if tuple(s) == (R, d)) == 0
     for a_, b_ in zip(got, ref):
         assert rel_err(a_, b_) < 3e-2
+
+
+@pytest.mark.parametrize("p", [0.0, 0.25])
+def test_out_ln_equals_linear_dropout_layernorm(p):
+    """ops.out_ln (out-projection + block-output dropout + residual + LayerNorm as one autograd node, the decoders' sites
+    query_decoder.py:342-345, 430-432, 610-613, 652-654) == the composition of the stand-alone ops on the same mask offsets:
+    outputs and every gradient."""
+    R, d = 12, 256
+    go = torch.randn(R, d, generator=torch.Generator().manual_seed(8))
+    res = {}
+    for fused in (True, False):
+        o, tgt = _leaf(R, d, seed=1), _leaf(R, d, seed=2)
+        w, b = _leaf(d, d, seed=3), _leaf(d, seed=4)
+        gm, bt = _leaf(d, seed=5), _leaf(d, seed=6)
+        with torch.no_grad():
+            w.mul_(d ** -0.5)
+        ops.set_dropout_seed(5)
+        if fused:
+            y, _ = ops.out_ln(o, tgt, w, b, gm, bt, 1e-5, p)
+        else:
+            y = ops.layer_norm(ops.dropout(ops.linear(o, w, b), p), tgt, gm, bt, 1e-5)
+        (y * go).sum().backward()
+        res[fused] = [y.detach()] + [t.grad.clone() for t in (o, tgt, w, b, gm, bt)]
+    for a_, b_ in zip(res[True], res[False]):
+        assert rel_err(a_, b_) < 1e-5
+
+
+def test_cls_gather_scatter_equal_take_put_rows():
+    """ops.cls_gather / cls_scatter (the frame-CLS exchange with the temporal layer for one un-padded video, two row-sized
+    nodes) == take_rows + cat + slices + put_rows (modal_encoder.py:170-195): values and gradients."""
+    n, S, d = 5, 7, 16
+    g1 = torch.randn(n, S, d, generator=torch.Generator().manual_seed(1))
+    g2 = torch.randn(1, d, generator=torch.Generator().manual_seed(2))
+    W = torch.randn(d, d, generator=torch.Generator().manual_seed(3))
+    res = {}
+    for fused in (True, False):
+        x = _leaf(n * S, d, seed=4)
+        video = _leaf(1, d, seed=5)
+        X = (x * 1.5).view(n, S, d)  # a non-leaf stream, like a layer output
+        if fused:
+            X3, Y = ops.cls_gather(X, video, 0)
+            Y = torch.tanh(Y @ W)  # stands in for the temporal layer
+            X3, vs = ops.cls_scatter(X3, Y, 0)
+        else:
+            X3, cls = ops.take_rows(X, 0)
+            Y = torch.tanh(torch.cat([video, cls], 0) @ W)
+            vs = Y[:1]
+            X3 = ops.put_rows(X3, Y[1:], 0)
+        ((X3 * g1).sum() + (vs * g2).sum()).backward()
+        res[fused] = [X3.detach().clone(), vs.detach().clone(), x.grad.clone(), video.grad.clone()]
+    for a_, b_ in zip(res[True], res[False]):
+        assert rel_err(a_, b_) < 1e-6
