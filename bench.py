@@ -281,14 +281,20 @@ def build_b200(args, device):
 
         opt = make_optimizer(cfg, model, grads)
 
+    zero_async = os.environ.get("STCAT_ZERO_ASYNC", "1") != "0"
+
     def fwd_bwd(vis, pos, txt):
-        grads.zero()
+        if zero_async:
+            grads.zero_async()  # the fill of the flat gradient buffer runs under the forward pass (joined before backward)
+        else:
+            grads.zero()
         vis.grad = None
         txt.grad = None
         out = model(NestedTensor(vis, vis_mask, [w["T"]]), pos, (text_mask, txt, None))
         total, _ = plan(out)
         sync.begin_step()
         sync.attach(out)
+        grads.wait_zero()
         total.backward()
         ops.join_leaf_streams()
         sync.finish()  # mean over ranks (GradSync averages, like the DDP wrapper it replaces)

@@ -41,7 +41,7 @@ extern "C" {
 
 /* Bumped whenever a signature or the meaning of an argument changes; stcat_b200/cabi.py refuses a library whose version
  * differs from the one it was written against (a stale locally built .so would otherwise be called with new signatures). */
-#define STCAT_ABI_VERSION 10
+#define STCAT_ABI_VERSION 11
 STCAT_API int stcat_abi_version(void);
 STCAT_API const char* stcat_last_error(void);
 /* compute capability major*10+minor of the current device, or <0; 100 expected */
@@ -265,6 +265,57 @@ STCAT_API int stcat_debug_attn_counts(long long* out5);
 STCAT_API int stcat_add(const float* a, const float* b, float* out, void* out_bf16, int64_t n, void* stream);
 STCAT_API int stcat_relu_bwd(const void* y, int y_dtype, void* dy_inout, int dy_dtype, int64_t n, void* stream);
 STCAT_API int stcat_cast_bf16(const float* x, void* out_bf16, int64_t rows, int64_t cols, int transpose, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Layout glue either side of the encoder and between encoder and decoder, one launch each way (replaces the torch.cat /
+ * transpose / expand / slice chains of modal_encoder.py:40-72 and query_decoder.py:83-120 and their autograd backward).
+ * fp32 [n, S, d] is the frame-major token stream, S = 1 + HW + L (row 0 of a frame = its CLS slot); d % 4 == 0.
+ *   token_assembly     : X[f] = [frame_cls ; vis[f]^T ; text[:, v(f)]], POS[f] = [local_pos ; vpos[f]^T ; 0] from
+ *                        vis / vpos [n, d, HW] (NCHW feature maps), text [L, b, d], f2v [n] int64 (video of frame f; NULL
+ *                        allowed iff b == 1); qk_op / x_op (bf16 [n, S, d], may be NULL) = bf16(X + POS), bf16(X): the GEMM
+ *                        operands of the first spatial layer's q/k and v projections.
+ *   token_assembly_bwd : from dX [n, S, d]: dvis [n, d, HW], dtext [L, b, d] (sum over the frames of each video, frames of a
+ *                        video are consecutive: vid_start [b + 1] int64, NULL allowed iff b == 1), dcls [d] (sum over all
+ *                        frames); every output is optional (NULL) and fully overwritten; sums run in frame order.
+ *   mem_operands       : the decoder's operands of the encoder memory: mem_op = bf16(X[:, 1:]), pos_op = bf16(POS[:, 1:]),
+ *                        mempos_op = bf16(X[:, 1:] + POS[:, 1:]), each [n (S - 1), d], and cls [n, d] = X[:, 0] (fp32).
+ *                        pos_op / mempos_op / cls may be NULL; POS may be NULL when both of the former are.
+ *   mem_operands_bwd   : dX [n, S, d] = [g_cls ; g_mem + g_mempos]; g_mem / g_mempos [n (S - 1), d] fp32 or bf16 (dtype codes),
+ *                        g_cls [n, d] fp32; each may be NULL (= zero).  dX is fully overwritten.
+ * ---------------------------------------------------------------------------------------------- */
+STCAT_API int stcat_token_assembly(const float* vis, const float* vpos, const float* text, const int64_t* f2v, const float* frame_cls,
+                                   const float* local_pos, float* X, float* POS, void* qk_op, void* x_op, int n, int d, int HW, int L,
+                                   int b, void* stream);
+STCAT_API int stcat_token_assembly_bwd(const float* dX, float* dvis, float* dtext, float* dcls, const int64_t* vid_start, int n, int d,
+                                       int HW, int L, int b, void* stream);
+STCAT_API int stcat_mem_operands(const float* X, const float* POS, void* mem_op, void* pos_op, void* mempos_op, float* cls, int n, int S,
+                                 int d, void* stream);
+STCAT_API int stcat_mem_operands_bwd(const void* g_mem, int g_mem_dtype, const void* g_mempos, int g_mempos_dtype, const float* g_cls,
+                                     float* dX, int n, int S, int d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * TemplateGenerator (query_decoder.py:441-475) as two small launches forward and three backward (the reference issues
+ * 4 Linears + 2 tanh + mul + add + sigmoid, ~14 kernels forward and ~20 backward, on the decoder's dependent chain).
+ * Weights W* are bf16 [d, d] (Wa: [q, d], q <= 8), biases fp32; GEMM operands (the video token, mod, the incoming
+ * gradients) are rounded to bf16 exactly where the Linear entry points round theirs; accumulation is fp32.
+ *   fwd: content [b, d] = Wc v + bc; gamma = tanh(Wg v + bg); beta = tanh(Wb v + bb)  (v = videos_cls [b, d]);
+ *        mod[f] = gamma[v(f)] * frames_cls[f] + beta[v(f)] -> mod_op bf16 [n, d]; anchor [n, q] = sigmoid(Wa mod + ba);
+ *        temp_query [n, d] (may be NULL) = content[v(f)], the temporal decoder's content query expanded to the frames.
+ *   bwd: g_anchor [n, q] (gradient w.r.t. anchor), g_temp [n, d] or NULL (gradient w.r.t. content expanded to the
+ *        frames).  Workspaces: dpq_op bf16 [n, q], dmod [n, d], dpre [3, b, d].  Outputs: d_frames_cls [n, d] and
+ *        d_videos_cls [b, d] (overwritten); dWa [q, d], dba [q] and the optional dW{c,g,b} [d, d] / db{c,g,b} [d] are
+ *        ACCUMULATED (+=).  f2v [n] / vid_start [b + 1] int64: NULL allowed iff b == 1.
+ * ---------------------------------------------------------------------------------------------- */
+STCAT_API int stcat_template_fwd(const float* videos_cls, const float* frames_cls, const int64_t* f2v, const void* Wc, const float* bc,
+                                 const void* Wg, const float* bg, const void* Wb, const float* bb, const void* Wa, const float* ba,
+                                 float* content, float* gamma, float* beta, void* mod_op, float* anchor, float* temp_query, int n, int b,
+                                 int d, int q, void* stream);
+STCAT_API int stcat_template_bwd(const float* g_anchor, const float* g_temp, const float* anchor, const float* videos_cls,
+                                 const float* frames_cls, const int64_t* f2v, const int64_t* vid_start, const float* gamma,
+                                 const float* beta, const void* mod_op, const void* Wc, const void* Wg, const void* Wb, const void* Wa,
+                                 void* dpq_op, float* dmod, float* dpre, float* d_frames_cls, float* d_videos_cls, float* dWc, float* dbc,
+                                 float* dWg, float* dbg, float* dWb, float* dbb, float* dWa, float* dba, int n, int b, int d, int q,
+                                 void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Anchor glue of the box decoder (query_decoder.py:188-219; net_utils.py:29-63), fp32, one launch each:

@@ -1,0 +1,20 @@
+#!/bin/bash
+# fused layout glue: kernel tests of the restructured template backward + per-kernel profile / trace of the fused step
+mkdir -p gpurun_out
+export PYTHONPATH=.
+timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_hotpath.py -q -m gpu -k "assembly or mem_operands or template or fused_glue" > gpurun_out/r2_ap_pytest.log 2>&1; echo "pytest rc=$?"; grep -v Warning gpurun_out/r2_ap_pytest.log | tail -8
+run() {
+tag=$1; shift
+env "$@" timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --profile gpurun_out/r2_ap_profile_$tag.md > gpurun_out/r2_ap_bench_$tag.json 2> gpurun_out/r2_ap_bench_$tag.err
+python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/r2_ap_bench_$tag.json"))
+    print("$tag step: ms", round(d["ms_per_step"], 3), "clips/s", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "launches/step", d["gpu_launches"] / d["steps"], "loss", d["e2e"].get("loss"))
+except Exception as ex:
+    print("failed", ex); print(open("gpurun_out/r2_ap_bench_$tag.err").read()[-1500:])
+PY
+}
+run fused STCAT_FUSED_GLUE=1 STCAT_TRACE=gpurun_out/r2_ap_trace_fused.json
+run base STCAT_FUSED_GLUE=0 STCAT_TRACE=gpurun_out/r2_ap_trace_base.json
+gzip -f gpurun_out/r2_ap_trace_fused.json gpurun_out/r2_ap_trace_base.json

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libstcat_sm100.so")
-SOURCES = ["capi.cu", "gemm_simt.cu", "gemm_tcgen05.cu", "attention_tc.cu", "attention_sq.cu", "attention_small.cu", "attention_small_mma.cu", "layernorm.cu", "stg_loss.cu", "attention_simt.cu", "elementwise.cu", "optim.cu"]
+SOURCES = ["capi.cu", "gemm_simt.cu", "gemm_tcgen05.cu", "attention_tc.cu", "attention_sq.cu", "attention_small.cu", "attention_small_mma.cu", "layernorm.cu", "stg_loss.cu", "attention_simt.cu", "elementwise.cu", "optim.cu", "assembly.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -80,8 +80,14 @@ SIGNATURES["stcat_box_refine_fwd"] = (c_int, [_P, _P, _P, _L, _F, _P])
 SIGNATURES["stcat_box_refine_bwd"] = (c_int, [_P, _P, _P, _P, _P, _L, _F, _P])
 SIGNATURES["stcat_stg_loss"] = (c_int, [_P] * 12 + [ctypes.POINTER(c_float), _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P])
 SIGNATURES["stcat_linear_group"] = (c_int, [_I, _I, ctypes.POINTER(_Job), _I, _P])
+SIGNATURES["stcat_token_assembly"] = (c_int, [_P] * 10 + [_I] * 5 + [_P])
+SIGNATURES["stcat_token_assembly_bwd"] = (c_int, [_P] * 5 + [_I] * 5 + [_P])
+SIGNATURES["stcat_mem_operands"] = (c_int, [_P] * 6 + [_I] * 3 + [_P])
+SIGNATURES["stcat_mem_operands_bwd"] = (c_int, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _P])
+SIGNATURES["stcat_template_fwd"] = (c_int, [_P] * 17 + [_I] * 4 + [_P])
+SIGNATURES["stcat_template_bwd"] = (c_int, [_P] * 27 + [_I] * 4 + [_P])
 MAX_GROUP_JOBS = 12
-ABI_VERSION = 10  # include/stcat_b200.h STCAT_ABI_VERSION
+ABI_VERSION = 11  # include/stcat_b200.h STCAT_ABI_VERSION
 
 _lib = None
 
@@ -484,3 +490,71 @@ class CudaBackend:
         self._rc(self.lib.stcat_map2d_pool(self._flat(x, "x", torch.float32), self._flat(valid, "valid", torch.uint8),
                                            self._flat(out, "map", torch.float32), B, N, d, self._stream()), "map2d_pool")
         self.launches += 1
+
+    # -- layout glue (csrc/assembly.cu) ----------------------------------
+    def token_assembly(self, vis, vpos, text, f2v, frame_cls, local_pos, X, POS, qk_op, x_op):
+        """vis / vpos [n, d, H, W] fp32, text [L, b, d] fp32 -> X / POS [n, S, d] fp32 (+ bf16 operand copies or None)"""
+        f, bf = torch.float32, torch.bfloat16
+        n, d = vis.shape[0], vis.shape[1]
+        HW = vis[0, 0].numel()
+        L, b = text.shape[0], text.shape[1]
+        assert tuple(X.shape) == (n, 1 + HW + L, d) and X.shape == POS.shape and vpos.shape == vis.shape
+        self._rc(self.lib.stcat_token_assembly(
+            self._flat(vis, "vis", f), self._flat(vpos, "vpos", f), self._flat(text, "text", f), self._flat(f2v, "f2v", torch.int64),
+            self._flat(frame_cls, "frame_cls", f), self._flat(local_pos, "local_pos", f), self._flat(X, "X", f), self._flat(POS, "POS", f),
+            self._flat(qk_op, "qk_op", bf), self._flat(x_op, "x_op", bf), n, d, HW, L, b, self._stream()), "token_assembly")
+        self.launches += 1
+
+    def token_assembly_bwd(self, dX, dvis, dtext, dcls, vid_start, HW, L, b):
+        f = torch.float32
+        n, S, d = dX.shape
+        assert S == 1 + HW + L
+        self._rc(self.lib.stcat_token_assembly_bwd(
+            self._flat(dX, "dX", f), self._flat(dvis, "dvis", f), self._flat(dtext, "dtext", f), self._flat(dcls, "dcls", f),
+            self._flat(vid_start, "vid_start", torch.int64), n, d, HW, L, b, self._stream()), "token_assembly_bwd")
+        self.launches += 1
+
+    def mem_operands(self, X, POS, mem_op, pos_op, mempos_op, cls):
+        """X / POS [n, S, d] fp32 -> bf16 [n (S-1), d] operands of rows 1.. and the fp32 CLS rows [n, d]"""
+        f, bf = torch.float32, torch.bfloat16
+        n, S, d = X.shape
+        self._rc(self.lib.stcat_mem_operands(
+            self._flat(X, "X", f), self._flat(POS, "POS", f), self._flat(mem_op, "mem_op", bf), self._flat(pos_op, "pos_op", bf),
+            self._flat(mempos_op, "mempos_op", bf), self._flat(cls, "cls", f), n, S, d, self._stream()), "mem_operands")
+        self.launches += 1
+
+    def mem_operands_bwd(self, g_mem, g_mempos, g_cls, dX):
+        n, S, d = dX.shape
+        self._rc(self.lib.stcat_mem_operands_bwd(
+            self._flat(g_mem, "g_mem"), F32 if g_mem is None else _dt(g_mem), self._flat(g_mempos, "g_mempos"),
+            F32 if g_mempos is None else _dt(g_mempos), self._flat(g_cls, "g_cls", torch.float32), self._flat(dX, "dX", torch.float32),
+            n, S, d, self._stream()), "mem_operands_bwd")
+        self.launches += 1
+
+    def template_fwd(self, videos_cls, frames_cls, f2v, Wc, bc, Wg, bg, Wb, bb, Wa, ba, content, gamma, beta, mod_op, anchor, temp_query):
+        f, bf = torch.float32, torch.bfloat16
+        n, d = frames_cls.shape
+        b, q = videos_cls.shape[0], Wa.shape[0]
+        self._rc(self.lib.stcat_template_fwd(
+            self._flat(videos_cls, "videos_cls", f), self._flat(frames_cls, "frames_cls", f), self._flat(f2v, "f2v", torch.int64),
+            self._flat(Wc, "Wc", bf), self._flat(bc, "bc", f), self._flat(Wg, "Wg", bf), self._flat(bg, "bg", f),
+            self._flat(Wb, "Wb", bf), self._flat(bb, "bb", f), self._flat(Wa, "Wa", bf), self._flat(ba, "ba", f),
+            self._flat(content, "content", f), self._flat(gamma, "gamma", f), self._flat(beta, "beta", f),
+            self._flat(mod_op, "mod_op", bf), self._flat(anchor, "anchor", f), self._flat(temp_query, "temp_query", f), n, b, d, q,
+            self._stream()), "template_fwd")
+        self.launches += 2
+
+    def template_bwd(self, g_anchor, g_temp, anchor, videos_cls, frames_cls, f2v, vid_start, gamma, beta, mod_op, Wc, Wg, Wb, Wa,
+                     dpq_op, dmod, dpre, d_frames_cls, d_videos_cls, dWc, dbc, dWg, dbg, dWb, dbb, dWa, dba):
+        f, bf, i64 = torch.float32, torch.bfloat16, torch.int64
+        n, d = frames_cls.shape
+        b, q = videos_cls.shape[0], Wa.shape[0]
+        F_ = lambda t, nm: self._flat(t, nm, f)
+        self._rc(self.lib.stcat_template_bwd(
+            F_(g_anchor, "g_anchor"), F_(g_temp, "g_temp"), F_(anchor, "anchor"), F_(videos_cls, "videos_cls"),
+            F_(frames_cls, "frames_cls"), self._flat(f2v, "f2v", i64), self._flat(vid_start, "vid_start", i64), F_(gamma, "gamma"),
+            F_(beta, "beta"), self._flat(mod_op, "mod_op", bf), self._flat(Wc, "Wc", bf), self._flat(Wg, "Wg", bf),
+            self._flat(Wb, "Wb", bf), self._flat(Wa, "Wa", bf), self._flat(dpq_op, "dpq_op", bf), F_(dmod, "dmod"), F_(dpre, "dpre"),
+            F_(d_frames_cls, "d_frames_cls"), F_(d_videos_cls, "d_videos_cls"), F_(dWc, "dWc"), F_(dbc, "dbc"), F_(dWg, "dWg"),
+            F_(dbg, "dbg"), F_(dWb, "dWb"), F_(dbb, "dbb"), F_(dWa, "dWa"), F_(dba, "dba"), n, b, d, q, self._stream()), "template_bwd")
+        self.launches += 3

@@ -24,7 +24,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .encoder import batch_indices, _check_cfg
+from .encoder import batch_indices, fused_glue, _check_cfg
 from .params import LinearP, MHAP, MLPP, NormP, OutProjOnly, SineTable, LearnedTable, xavier_reset
 
 _const_cache = {}
@@ -178,12 +178,15 @@ class _Ctx:
     """Per-forward shared tensors of the decoder (memory-side operands are built once and reused by all
     12 layers)."""
 
-    def __init__(self, idx, mem, mem_pos, key_mask, n_mem_tokens):
+    def __init__(self, idx, mem, mem_pos, key_mask, n_mem_tokens, operands=None, stream=None):
         self.idx = idx
         self.b, self.t, self.n = idx["b"], idx["t"], idx["n"]
         self.M = n_mem_tokens
         self.key_mask = key_mask
         self.query_mask = idx["query_mask"]
+        if operands is not None:  # written by ops.mem_operands straight from the encoder stream ``stream`` = (X, POS) [n, 1 + M, d]
+            self.mem_op, self.pos_op, self.mempos_op = operands
+            return
         self.mem_op = ops.to_operand(mem)  # [n*M, d]
         self.pos_op = ops.to_operand(mem_pos)
         self.mempos_op = ops.add(mem, mem_pos, as_operand=True)
@@ -445,6 +448,13 @@ class TemplateGenerator(nn.Module):
             temp_query = content.index_select(0, f2v)
         return _lin(self.anchor_proj, mod), temp_query
 
+    def run_fused(self, idx, frames_cls, videos_cls):
+        """(sigmoid(anchor_proj(mod)) [n, query_dim], temp_query [n, d]) in two launches (ops.template); bf16 mode."""
+        one = idx["identity"]
+        L = lambda p: (p.weight, p.bias)
+        return ops.template(videos_cls, frames_cls, *L(self.content_proj), *L(self.gamma_proj), *L(self.beta_proj),
+                            *L(self.anchor_proj), None if one else idx["f2v"], None if one else idx["vid_start"])
+
 
 class QueryDecoder(nn.Module):
     def __init__(self, cfg):
@@ -479,20 +489,38 @@ class QueryDecoder(nn.Module):
         b, t = idx["b"], idx["t"]
         if t > self.video_max_len + 1:
             raise ValueError(f"clip of {t} frames exceeds INPUT.MAX_VIDEO_LEN={self.video_max_len}")
-        mem = mem_sf.transpose(0, 1).reshape(n * M, d).float()  # frame-major copy (one pass over 14 MB)
-        p_v = vis_pos.flatten(2).transpose(1, 2)  # [n, HW, d]
-        mem_pos = torch.cat([p_v, p_v.new_zeros(n, M - n_vis, d)], 1).reshape(n * M, d).float()
         key_mask = memory_mask.to(torch.uint8).contiguous()
-        # templates (:97-120)
-        pos_query, temp_query = self.template_generator.run(idx, memory_cache["frames_cls"], memory_cache["videos_cls"])
+        enc_stream = memory_cache.get("_stream") if fused_glue() else None
+        if enc_stream is not None and (vis_pos is None or enc_stream[2] != vis_pos.data_ptr()
+                                       or tuple(enc_stream[0].shape) != (n, M + 1, d)
+                                       or self.template_generator.anchor_proj.weight.shape[0] > 8):
+            enc_stream = None
+        if enc_stream is not None:
+            # this package's encoder handed over its frame-major stream: the three memory-side GEMM operands and the frame-CLS
+            # rows in one launch, the template generator in two (csrc/assembly.cu); one / three launches in the backward pass
+            operands = ops.mem_operands(enc_stream[0], enc_stream[1])
+            frames_cls = operands[3]
+            operands = operands[:3]
+            mem = mem_pos = None
+            anchor_frames, temp_query = self.template_generator.run_fused(idx, frames_cls, memory_cache["videos_cls"])
+            like = frames_cls
+        else:
+            operands = None
+            mem = mem_sf.transpose(0, 1).reshape(n * M, d).float()  # frame-major copy (one pass over 14 MB)
+            p_v = vis_pos.flatten(2).transpose(1, 2)  # [n, HW, d]
+            mem_pos = torch.cat([p_v, p_v.new_zeros(n, M - n_vis, d)], 1).reshape(n * M, d).float()
+            # templates (:97-120)
+            pos_query, temp_query = self.template_generator.run(idx, memory_cache["frames_cls"], memory_cache["videos_cls"])
+            anchor_frames = torch.sigmoid(pos_query)
+            like = mem
         qt = self.time_embed.rows(t)
         query_time = (qt if b == 1 else qt.repeat(b, 1)).contiguous()
-        tgt = mem.new_zeros(b * t, d)
+        tgt = like.new_zeros(b * t, d)
         nl = self.decoder.num_layers
-        use_streams = mem.is_cuda and _MULTI_STREAM
+        use_streams = like.is_cuda and _MULTI_STREAM
         if not use_streams:
-            c = _Ctx(idx, mem, mem_pos, key_mask, M)
-            anchors = c.padded(torch.sigmoid(pos_query))  # [b*t, 4]
+            c = _Ctx(idx, mem, mem_pos, key_mask, M, operands, enc_stream)
+            anchors = c.padded(anchor_frames)  # [b*t, 4]
             query_temporal = c.padded(temp_query)  # [b*t, d]
             box_kv = [(lambda l=l, i=i: l.memory_side(c, i == 0)) for i, l in enumerate(self.decoder.layers)]
             time_kv = [(lambda l=l: l.memory_side(c)) for l in self.temp_decoder.layers]
@@ -505,12 +533,12 @@ class QueryDecoder(nn.Module):
         # by side with M fills the machine.  autograd replays each node's backward on its forward stream, so the
         # backward pass has the same concurrency.
         cur = torch.cuda.current_stream()
-        sM, sA, sB = _side_streams(mem.device)
+        sM, sA, sB = _side_streams(like.device)
         fork = cur.record_event()
         for st_ in (sM, sA, sB):
             st_.wait_event(fork)
         with torch.cuda.stream(sM):
-            c = _Ctx(idx, mem, mem_pos, key_mask, M)
+            c = _Ctx(idx, mem, mem_pos, key_mask, M, operands, enc_stream)
             ctx_ready = sM.record_event()
             box_kv, time_kv, ev_box, ev_time = [], [], [], []
             # these persistent GEMMs (and their backward) share the machine with the two query chains: keep some SMs free for
@@ -533,15 +561,15 @@ class QueryDecoder(nn.Module):
                 return get
             return [mk(i) for i in range(len(vals))]
 
-        for tns in (pos_query, temp_query, query_time, tgt):  # allocated on `cur`, consumed on the side streams
+        for tns in (anchor_frames, temp_query, query_time, tgt):  # allocated on `cur`, consumed on the side streams
             tns.record_stream(sA)
             tns.record_stream(sB)
-        for tns in (mem, mem_pos):
+        for tns in ((mem, mem_pos) if operands is None else operands):
             tns.record_stream(sM)
 
         with torch.cuda.stream(sA):
             sA.wait_event(ctx_ready)
-            anchors = c.padded(torch.sigmoid(pos_query))
+            anchors = c.padded(anchor_frames)
             outputs = self.decoder.run(c, tgt, anchors, query_time, waiter(sA, ev_box, box_kv))
         with torch.cuda.stream(sB):
             sB.wait_event(ctx_ready)

@@ -64,6 +64,30 @@ class FlatGrads:
         ops.join_leaf_streams()  # leaf-stream weight gradients of the previous step must have landed
         self.buf.zero_()
 
+    def zero_async(self):
+        """``zero()`` on a side stream forked from the current one: the fill (180 MB, ~25 us) runs under the forward pass, which
+        never touches the gradient buffer.  ``wait_zero()`` must be called on the stream that starts the backward pass."""
+        from . import ops
+
+        ops.join_leaf_streams()
+        if not self.buf.is_cuda:
+            self.buf.zero_()
+            return
+        cur = torch.cuda.current_stream()
+        side = getattr(self, "_zero_stream", None)
+        if side is None:
+            side = self._zero_stream = torch.cuda.Stream(self.buf.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self.buf.zero_()
+            self._zero_event = side.record_event()
+
+    def wait_zero(self):
+        ev = getattr(self, "_zero_event", None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            self._zero_event = None
+
     def all_reduce(self, average: bool = False):
         """Sum (or mean) of the flat buffer over the default process group; no-op without one."""
         import torch.distributed as dist

@@ -18,6 +18,8 @@ from __future__ import annotations
 
 from typing import Optional, Sequence, Tuple
 
+import os
+
 import torch
 from torch import nn
 
@@ -33,6 +35,18 @@ def _check_cfg(cfg):
 
 
 _index_cache = {}
+# fused layout glue (ops.token_assembly / mem_operands / template: csrc/assembly.cu) in bf16 mode; STCAT_FUSED_GLUE=0 keeps the
+# torch.cat / slice composition (the only path in exact-fp32 mode)
+_FUSED_GLUE = os.environ.get("STCAT_FUSED_GLUE", "1") != "0"
+
+
+def set_fused_glue(on: bool):
+    global _FUSED_GLUE
+    _FUSED_GLUE = bool(on)
+
+
+def fused_glue() -> bool:
+    return _FUSED_GLUE and ops.get_precision() == "bf16"
 
 
 def batch_indices(durations: Sequence[int], device) -> dict:
@@ -66,8 +80,9 @@ def batch_indices(durations: Sequence[int], device) -> dict:
     query_mask = torch.ones(b, t, dtype=torch.uint8)
     query_mask[:, 0] = 0
     query_mask[f2v_t, f2i_t] = 0
+    vid_start = torch.tensor([0] + [sum(durations[: j + 1]) for j in range(b)], dtype=torch.long)
     out = {
-        "b": b, "n": n, "t": t, "identity": b == 1,
+        "b": b, "n": n, "t": t, "identity": b == 1, "vid_start": vid_start.to(device),
         "f2v": f2v_t.to(device), "enc_gather": enc_gather.flatten().to(device), "enc_scatter": enc_scatter.to(device),
         "temp_mask": temp_mask.to(device), "dec_gather": dec_gather.flatten().to(device),
         "dec_scatter": dec_scatter.to(device), "query_mask": query_mask.to(device),
@@ -89,14 +104,14 @@ class TransformerEncoderLayer(nn.Module):
         self.nhead = nhead
         self.dropout_p = dropout
 
-    def run(self, x, x_op, pos, key_mask, B: int, L: int, pos_cls=None):
+    def run(self, x, x_op, pos, key_mask, B: int, L: int, pos_cls=None, qk_op=None):
         """x, pos: [B*L, d] batch-major rows.  Returns (y, y_op).  In train mode the four dropout sites of the reference
         layer (attention probabilities, dropout1, the FFN's inner dropout, dropout2; modal_encoder.py:212-241) are active."""
         a = self.self_attn
         p = self.dropout_p if self.training else 0.0
         x, x_op = ops.self_attn_block(x, x_op, pos, key_mask, a.in_proj_weight, a.in_proj_bias, a.out_proj.weight,
                                       a.out_proj.bias, self.norm1.weight, self.norm1.bias, B, L, self.nhead,
-                                      self.norm1.eps, pos_cls=pos_cls, drop_p=p)
+                                      self.norm1.eps, pos_cls=pos_cls, drop_p=p, qk_op=qk_op)
         return ops.ffn_block(x, x_op, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias,
                              self.norm2.weight, self.norm2.bias, self.norm2.eps, drop_p=p)
 
@@ -119,9 +134,10 @@ class SpatialTemporalEncoder(nn.Module):
         self.num_layers = num_layers
         self.d_model = d
 
-    def run(self, X, POS, key_mask, n: int, S_len: int, durations, pos_cls=None):
+    def run(self, X, POS, key_mask, n: int, S_len: int, durations, pos_cls=None, first_ops=None):
         """X, POS: [n*S, d] frame-major (row 0 of every frame = CLS slot).  Returns (X, video_src [b, d]).
-        ``pos_cls``: see ops.self_attn_block (POS is then a constant whose CLS rows equal this parameter)."""
+        ``pos_cls``: see ops.self_attn_block (POS is then a constant whose CLS rows equal this parameter).
+        ``first_ops``: (bf16(X + POS), bf16(X)) when the token assembly already wrote the first layer's GEMM operands."""
         d = self.d_model
         idx = batch_indices(durations, X.device)
         b, t = idx["b"], idx["t"]
@@ -132,14 +148,14 @@ class SpatialTemporalEncoder(nn.Module):
         temp_pos = self.time_embed.rows(t + 1)  # [t+1, d]
         temp_pos = temp_pos if b == 1 else temp_pos.repeat(b, 1)
         temp_pos = temp_pos.contiguous()
-        X_op = None
+        qk_op, X_op = first_ops if first_ops is not None else (None, None)
         # optional observer of every block's input (dp.GradSync hangs its bucketed all-reduce on their gradients);
         # nothing is stored here: holding these tensors would keep the step's autograd graph alive
         on_input = getattr(self, "layer_input_callback", None)
         for li, (sp, tp) in enumerate(zip(self.spatial_layers, self.temporal_layers)):
             if on_input is not None:
                 on_input(li, X)
-            X, X_op = sp.run(X, X_op, POS, key_mask, n, S_len, pos_cls=pos_cls)
+            X, X_op = sp.run(X, X_op, POS, key_mask, n, S_len, pos_cls=pos_cls, qk_op=qk_op if li == 0 else None)
             if idx["identity"]:
                 # one un-padded video: the frame-CLS exchange with the temporal layer as two row-sized nodes
                 X3, Y = ops.cls_gather(X.view(n, S_len, d), video_src, 0)  # Y = [video token ; frame-CLS rows]
@@ -185,6 +201,26 @@ class CrossModalEncoder(nn.Module):
         S_len = 1 + HW + L
         idx = batch_indices(durations, vis_features.device)
         enc = self.encoder
+        pos_const = not (vis_pos.requires_grad and torch.is_grad_enabled())
+        mask = None
+        if fused_glue() and pos_const and L > 0 and all(t_.dtype == torch.float32 for t_ in (vis_features, vis_pos, text_memory)):
+            # one launch: X, POS and the first layer's operand copies (ops.token_assembly); backward: one launch
+            m_t = text_mask.expand(n, L) if idx["identity"] else text_mask.index_select(0, idx["f2v"])
+            mask = torch.cat([vis_mask.flatten(1), m_t], 1)  # [n, HW+L] bool (returned)
+            key_mask = torch.cat([mask.new_zeros(n, 1), mask], 1).to(torch.uint8).contiguous()  # [n, S]
+            X3, POS3, qk_op, x_op = ops.token_assembly(vis_features, vis_pos, text_memory, enc.frame_cls.weight,
+                                                       enc.local_pos_embed.weight.detach(),
+                                                       None if idx["identity"] else idx["f2v"],
+                                                       None if idx["identity"] else idx["vid_start"])
+            X, video_src = enc.run(X3.view(n * S_len, d), POS3.view(n * S_len, d), key_mask, n, S_len, durations,
+                                   pos_cls=enc.local_pos_embed.weight, first_ops=(qk_op.view(n * S_len, d), x_op.view(n * S_len, d)))
+            X3 = X.view(n, S_len, d)
+            return {
+                "encoded_memory": X3[:, 1:, :].transpose(0, 1), "mask": mask, "frames_cls": X3[:, 0, :], "videos_cls": video_src,
+                "durations": durations, "fea_map_size": (H, W),
+                # private: the frame-major stream and its positional stream for this package's decoder (ops.mem_operands)
+                "_stream": (X3, POS3, vis_pos.data_ptr()),
+            }
         # ---- token assembly, frame-major: [cls ; HW visual tokens ; L text tokens] per frame ----
         x_v = vis_features.flatten(2).transpose(1, 2)  # [n, HW, d] view
         p_v = vis_pos.flatten(2).transpose(1, 2)

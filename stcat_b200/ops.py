@@ -336,6 +336,53 @@ class _capped:
             self.be.set_gemm_sm_limit(0)
 
 
+_GRAD_SINK = os.environ.get("STCAT_GRAD_SINK", "1") != "0"
+
+
+def set_grad_sink(on: bool):
+    """Data gradients of the decoder's memory operands accumulate inside the GEMM launches (default on; see _GradSink)."""
+    global _GRAD_SINK
+    _GRAD_SINK = bool(on)
+
+
+class _GradSink:
+    """Accumulation target for the data gradient of a GEMM operand that MANY Linear nodes read (the encoder memory: 24
+    memory-side projections of the two decoders).  autograd would sum their 24 [n M, d] gradients with 22 element-wise add
+    kernels, issued on the consumer's stream -- measured as a ~75 us serial chain in front of the encoder's backward pass.
+    A Linear node whose input carries a sink (attribute ``_stcat_sink``, set by ``mem_operands``) instead lets its
+    data-gradient GEMM accumulate into the sink's buffer (``accumulate`` epilogue: one rounding per contribution instead of
+    two) and returns None for that input; the producer of the operand (``MemOperandsFn.backward``), which the engine runs
+    after every consumer taking part in this backward pass, collects the buffer.  No counting: a backward pass that reaches
+    only some consumers just finds fewer contributions."""
+
+    def __init__(self):
+        self.buf = None
+        self.event = None
+
+    def accumulate(self, fn, shape, dtype, device):
+        """fn(buf, accumulate: bool) launches the GEMM"""
+        first = self.buf is None
+        if first:
+            self.buf = torch.empty(shape, dtype=dtype, device=device)
+        fn(self.buf, not first)
+        if self.buf.is_cuda:
+            self.event = torch.cuda.current_stream().record_event()
+
+    def take(self):
+        """the accumulated gradient (or None), made safe to read on the current stream; the sink is empty afterwards"""
+        buf, ev = self.buf, self.event
+        self.buf = self.event = None
+        if buf is not None and ev is not None:
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev)
+            buf.record_stream(cur)
+        return buf
+
+
+def _sink_of(x):
+    return getattr(x, "_stcat_sink", None) if _GRAD_SINK else None
+
+
 class LinearFn(Function):
     """y = act(x W[r0:r1]^T + b[r0:r1])  (r0/r1 = None: the whole parameter).  The row range lets the packed
     ``in_proj_weight`` of an MHA be used slice by slice without autograd slicing nodes."""
@@ -363,6 +410,7 @@ class LinearFn(Function):
         ctx.x_shape = x.shape
         ctx.x_dtype = x.dtype
         ctx.rows = (r0, r1)
+        ctx.sink = _sink_of(x) if x.dim() == 2 else None
         ctx.save_for_backward(xo, weight, bias, y if relu else None)
         return y.view(*x.shape[:-1], N)
 
@@ -386,7 +434,10 @@ class LinearFn(Function):
         M = dy2.shape[0]
         dx = None
         with _capped(be, ctx.sm_limit):
-            if ctx.needs_input_grad[0]:
+            if ctx.needs_input_grad[0] and ctx.sink is not None:
+                ctx.sink.accumulate(lambda buf, acc: be.linear_bwd_data(dyo, _operand(wd, True), buf, accumulate=acc),
+                                    (M, K), ctx.x_dtype, dy.device)
+            elif ctx.needs_input_grad[0]:
                 dx = torch.empty(M, K, dtype=ctx.x_dtype, device=dy.device)
                 be.linear_bwd_data(dyo, _operand(wd, True), dx)
                 dx = dx.view(ctx.x_shape)
@@ -440,6 +491,7 @@ class LinearSumFn(Function):
             saved += [xo, w]
         ctx.nterms = nterms
         ctx.biases = bs
+        ctx.sinks = [(_sink_of(x) if x.dim() == 2 else None) for x in xs]
         ctx.meta = [(x.shape, x.dtype, b is not None) for x, b in zip(xs, bs)]
         ctx.save_for_backward(*saved)
         return y.view(*lead, N)
@@ -463,7 +515,10 @@ class LinearSumFn(Function):
             xshape, xdtype, has_b = ctx.meta[i]
             K = w.shape[1]
             dx = dw = db = None
-            if ctx.needs_input_grad[2 + i]:
+            if ctx.needs_input_grad[2 + i] and ctx.sinks[i] is not None:
+                ctx.sinks[i].accumulate(lambda buf, acc, w=w: be.linear_bwd_data(dyo, _operand(w.detach(), True), buf, accumulate=acc),
+                                        (M, K), xdtype, dy.device)
+            elif ctx.needs_input_grad[2 + i]:
                 dx = torch.empty(M, K, dtype=xdtype, device=dy.device)
                 be.linear_bwd_data(dyo, _operand(w.detach(), True), dx)
                 dx = dx.view(xshape)
@@ -852,7 +907,7 @@ class SelfAttnBlockFn(Function):
     """
 
     @staticmethod
-    def forward(ctx, x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps, pos_cls=None, drop_p=0.0):
+    def forward(ctx, x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps, pos_cls=None, drop_p=0.0, qk_op=None):
         be = get_backend()
         ctx.has_pos_cls = pos_cls is not None
         # train-mode dropout (modal_encoder.py:212,237): on the attention probabilities and on the block output before
@@ -872,8 +927,11 @@ class SelfAttnBlockFn(Function):
         if ctx.drop_attn:  # forked first: the (ALU-bound) generator runs under the HBM-bound add and the projection GEMMs
             bits, side = _attn_keep_bits(be, B, H, L, ctx.drop_attn, xd)
         if bf:
-            qk_in = _new(R, d, od, x)
-            be.add(xd, posd, None, qk_in)
+            if qk_op is not None and qk_op.dtype == od:  # the producer of x already wrote bf16(x + pos) (ops.token_assembly)
+                qk_in = qk_op.detach().view(R, d)
+            else:
+                qk_in = _new(R, d, od, x)
+                be.add(xd, posd, None, qk_in)
             xo = x_op.detach() if (x_op is not None and x_op.dtype == od) else _cast_op(be, xd)
         else:
             qk_in = _new(R, d, od, x)
@@ -923,7 +981,7 @@ class SelfAttnBlockFn(Function):
     @once_differentiable
     def backward(ctx, dy, _unused):
         if dy is None:
-            return (None,) * 16
+            return (None,) * 17
         be = get_backend()
         xd, xo, qk_in, qkv, o, lse, a, mean, rstd, key_mask, w_in, w_out, gamma = ctx.saved_tensors
         B, L, H, scale = ctx.dims
@@ -995,7 +1053,7 @@ class SelfAttnBlockFn(Function):
                 else:
                     dpc = torch.empty(1, d, dtype=f32, device=dy.device)
                     be.linear_bwd_data(srow, w_in.detach()[: 2 * d], dpc)
-        return dz, None, dpos, None, dwi, dbi, dwo, dbo, dg, dbt, None, None, None, None, dpc, None
+        return dz, None, dpos, None, dwi, dbi, dwo, dbo, dg, dbt, None, None, None, None, dpc, None, None
 
 
 class OutLNFn(Function):
@@ -1173,10 +1231,13 @@ class FFNBlockFn(Function):
         return dz, None, dw1, db1, dw2, db2, dg, dbt, None, None
 
 
-def self_attn_block(x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps=1e-5, pos_cls=None, drop_p=0.0):
+def self_attn_block(x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps=1e-5, pos_cls=None, drop_p=0.0,
+                    qk_op=None):
     """``pos_cls`` ([1, d], optional): the parameter that row 0 of every sequence of ``pos`` was copied from; when
-    given, ``pos`` itself is treated as a constant and the gradient goes to ``pos_cls`` directly."""
-    return SelfAttnBlockFn.apply(x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps, pos_cls, float(drop_p))
+    given, ``pos`` itself is treated as a constant and the gradient goes to ``pos_cls`` directly.  ``qk_op`` (optional): the
+    bf16 operand copy of ``x + pos`` when the producer of ``x`` already wrote it."""
+    return SelfAttnBlockFn.apply(x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps, pos_cls, float(drop_p),
+                                 qk_op)
 
 
 def ffn_block(x, x_op, w1, b1, w2, b2, gamma, beta, eps=1e-5, drop_p=0.0):
@@ -1290,6 +1351,172 @@ def take_rows(x, r: int = 0):
 
 def put_rows(x, rows, r: int = 0):
     return PutRowsFn.apply(x, rows, r)
+
+
+class TokenAssemblyFn(Function):
+    """Encoder input assembly (modal_encoder.py:40-72) as one launch each way: X[f] = [frame_cls ; vis[f]^T ; text[:, v(f)]],
+    POS[f] = [local_pos ; vis_pos[f]^T ; 0] in the frame-major layout [n, S, d], plus the first spatial layer's two GEMM-operand
+    copies (bf16(X + POS), bf16(X)).  POS and the operand copies are non-differentiable: the caller routes the gradient of
+    ``local_pos`` through ``self_attn_block(pos_cls=...)`` and uses this node only when ``vis_pos`` needs no gradient.
+    Backward: d vis (transposed back), d text (sum over the frames of each video), d frame_cls (sum over all frames)."""
+
+    @staticmethod
+    def forward(ctx, vis, vis_pos, text, frame_cls, local_pos, f2v, vid_start):
+        be = get_backend()
+        n, d = vis.shape[0], vis.shape[1]
+        HW = vis[0, 0].numel()
+        L, b = text.shape[0], text.shape[1]
+        S = 1 + HW + L
+        dev = vis.device
+        X = torch.empty(n, S, d, dtype=torch.float32, device=dev)
+        POS = torch.empty(n, S, d, dtype=torch.float32, device=dev)
+        qk_op = torch.empty(n, S, d, dtype=torch.bfloat16, device=dev)
+        x_op = torch.empty(n, S, d, dtype=torch.bfloat16, device=dev)
+        be.token_assembly(vis.detach().contiguous(), vis_pos.detach().contiguous(), text.detach().contiguous(), f2v,
+                          frame_cls.detach().contiguous(), local_pos.detach().contiguous(), X, POS, qk_op, x_op)
+        ctx.dims = (tuple(vis.shape), tuple(text.shape), tuple(frame_cls.shape), HW, L, b)
+        ctx.vid_start = vid_start
+        ctx.mark_non_differentiable(POS, qk_op, x_op)
+        ctx.set_materialize_grads(False)
+        return X, POS, qk_op, x_op
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gX, *_unused):
+        if gX is None:
+            return (None,) * 7
+        vis_shape, text_shape, cls_shape, HW, L, b = ctx.dims
+        gX = gX if (gX.is_contiguous() and gX.dtype == torch.float32) else gX.contiguous().float()
+        need_vis, _, need_text, need_cls = ctx.needs_input_grad[:4]
+        dev = gX.device
+        dvis = torch.empty(vis_shape, dtype=torch.float32, device=dev) if need_vis else None
+        dtext = torch.empty(text_shape, dtype=torch.float32, device=dev) if (need_text and L > 0) else None
+        dcls = torch.empty(cls_shape, dtype=torch.float32, device=dev) if need_cls else None
+        if dvis is not None or dtext is not None or dcls is not None:
+            get_backend().token_assembly_bwd(gX, dvis, dtext, dcls, ctx.vid_start, HW, L, b)
+        if need_text and dtext is None:
+            dtext = torch.zeros(text_shape, dtype=torch.float32, device=dev)
+        return dvis, None, dtext, dcls, None, None, None
+
+
+def token_assembly(vis, vis_pos, text, frame_cls, local_pos, f2v=None, vid_start=None):
+    return TokenAssemblyFn.apply(vis, vis_pos, text, frame_cls, local_pos, f2v, vid_start)
+
+
+class MemOperandsFn(Function):
+    """The decoder's views of the encoder stream X [n, S, d] (query_decoder.py:83-96, 355-366, 633-639) in one launch:
+    (bf16(X[:, 1:]), bf16(POS[:, 1:]), bf16(X[:, 1:] + POS[:, 1:])) as [n (S-1), d] GEMM operands and the fp32 frame-CLS rows
+    X[:, 0].  Backward: dX = [g_cls ; g_mem + g_mempos] in one launch (the reference layout's slice / select / transpose
+    nodes cost two full-size zero fills, two copies, two casts and two adds).  POS is a constant here."""
+
+    @staticmethod
+    def forward(ctx, X, POS, sinks=None):
+        be = get_backend()
+        ctx.sinks = sinks
+        n, S, d = X.shape
+        M = S - 1
+        dev = X.device
+        bf = torch.bfloat16
+        mem_op = torch.empty(n * M, d, dtype=bf, device=dev)
+        pos_op = torch.empty(n * M, d, dtype=bf, device=dev)
+        mempos_op = torch.empty(n * M, d, dtype=bf, device=dev)
+        cls = torch.empty(n, d, dtype=torch.float32, device=dev)
+        Xd = X.detach()
+        be.mem_operands(Xd if Xd.is_contiguous() else Xd.contiguous(), POS.detach().contiguous(), mem_op, pos_op, mempos_op, cls)
+        ctx.shape = (n, S, d)
+        ctx.mark_non_differentiable(pos_op)
+        ctx.set_materialize_grads(False)
+        return mem_op, pos_op, mempos_op, cls
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_mem, _g_pos, g_mempos, g_cls):
+        if ctx.sinks is not None:  # contributions the consumers accumulated in their GEMMs (_GradSink)
+            s_mem, s_mempos = ctx.sinks[0].take(), ctx.sinks[1].take()
+            g_mem = s_mem if g_mem is None else (g_mem if s_mem is None else g_mem.float() + s_mem.float())
+            g_mempos = s_mempos if g_mempos is None else (g_mempos if s_mempos is None else g_mempos.float() + s_mempos.float())
+        if g_mem is None and g_mempos is None and g_cls is None:
+            return None, None, None
+        n, S, d = ctx.shape
+        ref = g_mem if g_mem is not None else (g_mempos if g_mempos is not None else g_cls)
+        fix = lambda g: None if g is None else (g if g.is_contiguous() else g.contiguous())
+        g_cls = None if g_cls is None else fix(g_cls.float() if g_cls.dtype != torch.float32 else g_cls)
+        dX = torch.empty(n, S, d, dtype=torch.float32, device=ref.device)
+        get_backend().mem_operands_bwd(fix(g_mem), fix(g_mempos), g_cls, dX)
+        return dX, None, None
+
+
+def mem_operands(X, POS):
+    """(mem_op, pos_op, mempos_op, cls); mem_op / mempos_op carry a gradient sink (_GradSink) for their Linear consumers."""
+    sinks = (_GradSink(), _GradSink()) if _GRAD_SINK else None
+    out = MemOperandsFn.apply(X, POS, sinks)
+    if sinks is not None:
+        out[0]._stcat_sink, out[2]._stcat_sink = sinks
+    return out
+
+
+class TemplateFn(Function):
+    """TemplateGenerator.forward (query_decoder.py:441-475) + the sigmoid of :105: (anchor [n, q], temp_query [n, d]) from the
+    video tokens [b, d] and the frame-CLS tokens [n, d]; two launches forward, three backward (bf16 mode)."""
+
+    @staticmethod
+    def forward(ctx, videos_cls, frames_cls, Wc, bc, Wg, bg, Wb, bb, Wa, ba, f2v, vid_start):
+        be = get_backend()
+        n, d = frames_cls.shape
+        b, q = videos_cls.shape[0], Wa.shape[0]
+        dev = frames_cls.device
+        f32 = torch.float32
+        v = videos_cls.detach().float().contiguous()
+        fc = frames_cls.detach().float().contiguous()
+        content = torch.empty(b, d, dtype=f32, device=dev)
+        gamma = torch.empty(b, d, dtype=f32, device=dev)
+        beta = torch.empty(b, d, dtype=f32, device=dev)
+        mod_op = torch.empty(n, d, dtype=torch.bfloat16, device=dev)
+        anchor = torch.empty(n, q, dtype=f32, device=dev)
+        temp = torch.empty(n, d, dtype=f32, device=dev)
+        be.template_fwd(v, fc, f2v, _operand(Wc.detach(), True), bc.detach(), _operand(Wg.detach(), True), bg.detach(),
+                        _operand(Wb.detach(), True), bb.detach(), _operand(Wa.detach(), True), ba.detach(), content, gamma, beta,
+                        mod_op, anchor, temp)
+        ctx.save_for_backward(v, fc, gamma, beta, mod_op, anchor, Wc, Wg, Wb, Wa)
+        ctx.extra = (bc, bg, bb, ba, f2v, vid_start)
+        ctx.set_materialize_grads(False)
+        return anchor, temp
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_anchor, g_temp):
+        if g_anchor is None and g_temp is None:
+            return (None,) * 12
+        be = get_backend()
+        v, fc, gamma, beta, mod_op, anchor, Wc, Wg, Wb, Wa = ctx.saved_tensors
+        bc, bg, bb, ba, f2v, vid_start = ctx.extra
+        n, d = fc.shape
+        b, q = v.shape[0], Wa.shape[0]
+        dev = fc.device
+        f32 = torch.float32
+        fix = lambda g: g if (g.is_contiguous() and g.dtype == f32) else g.contiguous().float()
+        g_anchor = torch.zeros(n, q, dtype=f32, device=dev) if g_anchor is None else fix(g_anchor)
+        g_temp = None if g_temp is None else fix(g_temp)
+        params = (Wc, bc, Wg, bg, Wb, bb, Wa, ba)
+        fused = _fuse_grads and all(p_.grad is not None and p_.grad.is_contiguous() for p_ in params)
+        if fused:
+            gs = [p_.grad for p_ in params]
+        else:
+            gs = [torch.zeros(p_.shape, dtype=f32, device=dev) for p_ in params]
+        dpq_op = torch.empty(n, q, dtype=torch.bfloat16, device=dev)
+        dmod = torch.empty(n, d, dtype=f32, device=dev)
+        dpre = torch.empty(3, b, d, dtype=f32, device=dev)
+        dfc = torch.empty(n, d, dtype=f32, device=dev)
+        dv = torch.empty(b, d, dtype=f32, device=dev)
+        be.template_bwd(g_anchor, g_temp, anchor, v, fc, f2v, vid_start, gamma, beta, mod_op, _operand(Wc.detach(), True),
+                        _operand(Wg.detach(), True), _operand(Wb.detach(), True), _operand(Wa.detach(), True), dpq_op, dmod, dpre,
+                        dfc, dv, gs[0], gs[1], gs[2], gs[3], gs[4], gs[5], gs[6], gs[7])
+        out = (None,) * 8 if fused else tuple(gs)
+        return (dv, dfc) + out + (None, None)
+
+
+def template(videos_cls, frames_cls, Wc, bc, Wg, bg, Wb, bb, Wa, ba, f2v=None, vid_start=None):
+    return TemplateFn.apply(videos_cls, frames_cls, Wc, bc, Wg, bg, Wb, bb, Wa, ba, f2v, vid_start)
 
 
 def sted_score(pred_sted: torch.Tensor, durations, return_map: bool = False):

@@ -471,3 +471,113 @@ class EmuBackend:
                 if valid.view(N, N)[i, j]:
                     out[:, :, i, j] = run
         self.launches += 1
+
+    # -- layout glue (csrc/assembly.cu) ----------------------------------
+    def token_assembly(self, vis, vpos, text, f2v, frame_cls, local_pos, X, POS, qk_op, x_op):
+        for t, nm in ((vis, "vis"), (vpos, "vpos"), (text, "text"), (frame_cls, "frame_cls"), (local_pos, "local_pos"), (X, "X"),
+                      (POS, "POS")):
+            _flat(t, nm, F32)
+        _flat(qk_op, "qk_op", BF16), _flat(x_op, "x_op", BF16), _flat(f2v, "f2v", torch.int64)
+        n, d = vis.shape[0], vis.shape[1]
+        L, b = text.shape[0], text.shape[1]
+        assert b == 1 or f2v is not None
+        xv = vis.flatten(2).transpose(1, 2)
+        pv = vpos.flatten(2).transpose(1, 2)
+        xt = text.transpose(0, 1)
+        xt = xt.expand(n, L, d) if b == 1 else xt.index_select(0, f2v)
+        X.copy_(torch.cat([frame_cls.view(1, 1, d).expand(n, 1, d), xv, xt], 1))
+        POS.copy_(torch.cat([local_pos.view(1, 1, d).expand(n, 1, d), pv, pv.new_zeros(n, L, d)], 1))
+        if qk_op is not None:
+            _store(qk_op, X + POS)
+        if x_op is not None:
+            _store(x_op, X)
+        self.launches += 1
+
+    def token_assembly_bwd(self, dX, dvis, dtext, dcls, vid_start, HW, L, b):
+        _flat(dX, "dX", F32), _flat(dvis, "dvis", F32), _flat(dtext, "dtext", F32), _flat(dcls, "dcls", F32)
+        _flat(vid_start, "vid_start", torch.int64)
+        n, S, d = dX.shape
+        assert S == 1 + HW + L and (b == 1 or vid_start is not None)
+        if dvis is not None:
+            dvis.copy_(dX[:, 1:1 + HW].transpose(1, 2).reshape(dvis.shape))
+        if dtext is not None and L > 0:
+            st = [0, n] if b == 1 else [int(v) for v in vid_start]
+            for v in range(b):
+                dtext[:, v] = dX[st[v]:st[v + 1], 1 + HW:].sum(0)
+        if dcls is not None:
+            dcls.copy_(dX[:, 0].sum(0).view(dcls.shape))
+        self.launches += 1
+
+    def mem_operands(self, X, POS, mem_op, pos_op, mempos_op, cls):
+        _flat(X, "X", F32), _flat(POS, "POS", F32), _flat(mem_op, "mem_op", BF16), _flat(pos_op, "pos_op", BF16)
+        _flat(mempos_op, "mempos_op", BF16), _flat(cls, "cls", F32)
+        n, S, d = X.shape
+        _store(mem_op, X[:, 1:].reshape(n * (S - 1), d))
+        if pos_op is not None:
+            _store(pos_op, POS[:, 1:].reshape(n * (S - 1), d))
+        if mempos_op is not None:
+            _store(mempos_op, (X[:, 1:] + POS[:, 1:]).reshape(n * (S - 1), d))
+        if cls is not None:
+            cls.copy_(X[:, 0])
+        self.launches += 1
+
+    def mem_operands_bwd(self, g_mem, g_mempos, g_cls, dX):
+        _flat(g_mem, "g_mem"), _flat(g_mempos, "g_mempos"), _flat(g_cls, "g_cls", F32), _flat(dX, "dX", F32)
+        n, S, d = dX.shape
+        dX.zero_()
+        if g_cls is not None:
+            dX[:, 0] = g_cls
+        if g_mem is not None:
+            dX[:, 1:] += _f(g_mem).view(n, S - 1, d)
+        if g_mempos is not None:
+            dX[:, 1:] += _f(g_mempos).view(n, S - 1, d)
+        self.launches += 1
+
+    def template_fwd(self, videos_cls, frames_cls, f2v, Wc, bc, Wg, bg, Wb, bb, Wa, ba, content, gamma, beta, mod_op, anchor, temp_query):
+        for t, nm in ((Wc, "Wc"), (Wg, "Wg"), (Wb, "Wb"), (Wa, "Wa"), (mod_op, "mod_op")):
+            _flat(t, nm, BF16)
+        for t, nm in ((videos_cls, "videos_cls"), (frames_cls, "frames_cls"), (bc, "bc"), (bg, "bg"), (bb, "bb"), (ba, "ba"),
+                      (content, "content"), (gamma, "gamma"), (beta, "beta"), (anchor, "anchor")):
+            _flat(t, nm, F32)
+        b = videos_cls.shape[0]
+        assert b == 1 or f2v is not None
+        v = videos_cls.to(BF16).float()
+        content.copy_(v @ _f(Wc).t() + bc)
+        gamma.copy_(torch.tanh(v @ _f(Wg).t() + bg))
+        beta.copy_(torch.tanh(v @ _f(Wb).t() + bb))
+        g, bt = (gamma, beta) if b == 1 else (gamma.index_select(0, f2v), beta.index_select(0, f2v))
+        _store(mod_op, g * frames_cls + bt)
+        anchor.copy_(torch.sigmoid(_f(mod_op) @ _f(Wa).t() + ba))
+        if temp_query is not None:
+            _flat(temp_query, "temp_query", F32)
+            temp_query.copy_(content.expand(frames_cls.shape[0], -1) if b == 1 else content.index_select(0, f2v))
+        self.launches += 2
+
+    def template_bwd(self, g_anchor, g_temp, anchor, videos_cls, frames_cls, f2v, vid_start, gamma, beta, mod_op, Wc, Wg, Wb, Wa,
+                     dpq_op, dmod, dpre, d_frames_cls, d_videos_cls, dWc, dbc, dWg, dbg, dWb, dbb, dWa, dba):
+        n, d = frames_cls.shape
+        b = videos_cls.shape[0]
+        assert b == 1 or (f2v is not None and vid_start is not None)
+        _store(dpq_op, g_anchor * anchor * (1 - anchor))
+        dmod.copy_(_f(dpq_op) @ _f(Wa))
+        g = gamma if b == 1 else gamma.index_select(0, f2v)
+        d_frames_cls.copy_(dmod * g)
+        st = [0, n] if b == 1 else [int(v) for v in vid_start]
+        for v in range(b):
+            sl = slice(st[v], st[v + 1])
+            dpre[0, v] = g_temp[sl].sum(0) if g_temp is not None else 0.0
+            dpre[1, v] = (dmod[sl] * frames_cls[sl]).sum(0) * (1 - gamma[v] ** 2)
+            dpre[2, v] = dmod[sl].sum(0) * (1 - beta[v] ** 2)
+        dWa += _f(dpq_op).t() @ _f(mod_op)
+        dba += _f(dpq_op).sum(0)
+        vb = videos_cls.to(BF16).float()
+        dv = torch.zeros_like(d_videos_cls)
+        for which, (W, dW, db) in enumerate(((Wc, dWc, dbc), (Wg, dWg, dbg), (Wb, dWb, dbb))):
+            dp = dpre[which].to(BF16).float()
+            dv += dp @ _f(W)
+            if dW is not None:
+                dW += dp.t() @ vb
+            if db is not None:
+                db += dp.sum(0)
+        d_videos_cls.copy_(dv)
+        self.launches += 3

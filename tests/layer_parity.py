@@ -58,14 +58,17 @@ def record_layers(records):
     td_run = dec.TimeDecoder.run
     cl = lambda t: None if t is None else t.detach().clone()
 
-    def e_wrap(self, x, x_op, pos, key_mask, B, L, pos_cls=None):
+    def e_wrap(self, x, x_op, pos, key_mask, B, L, pos_cls=None, qk_op=None):
         x_in = cl(x)  # the stream is edited in place afterwards (frame-CLS row exchange): keep copies
-        out = e_run(self, x, x_op, pos, key_mask, B, L, pos_cls=pos_cls)
+        out = e_run(self, x, x_op, pos, key_mask, B, L, pos_cls=pos_cls, qk_op=qk_op)
         records.append(("enc", self, dict(x=x_in, pos=cl(pos), key_mask=key_mask, B=B, L=L), dict(y=cl(out[0]))))
         return out
 
-    def c_wrap(self, idx, mem, mem_pos, key_mask, n_mem_tokens):
-        c_init(self, idx, mem, mem_pos, key_mask, n_mem_tokens)
+    def c_wrap(self, idx, mem, mem_pos, key_mask, n_mem_tokens, operands=None, stream=None):
+        c_init(self, idx, mem, mem_pos, key_mask, n_mem_tokens, operands, stream)
+        if mem is None:  # fused glue (ops.mem_operands): the fp32 memory / positions are rows 1.. of the encoder stream
+            d = stream[0].shape[-1]
+            mem, mem_pos = stream[0][:, 1:].reshape(-1, d), stream[1][:, 1:].reshape(-1, d)
         self._mem, self._mem_pos = cl(mem), cl(mem_pos)
 
     def b_wrap(self, c, tgt, tgt_op, query_pos, query_time, time_op, query_sine, sine_op, is_first, mem_kv):

@@ -38,6 +38,7 @@ SHAPES = [
     (64, 256, 2048),      # decoder FFN linear2: 4 tiles x 32 k-blocks -> cluster split-K (8 CTAs per tile)
     (65, 256, 2048),      # temporal encoder layer (T + 1 rows)
     (300, 104, 1024),     # cluster split-K with row / column tails (clusters of 8)
+    (13568, 256, 256),    # memory-side projections of the decoder (64 frames x 212 tokens): bf16 dgrad with accumulate
     (64, 2048, 256),      # bwd: dx[64, 256] = dy[64, 2048] . W: the FFN linear1 data gradient
     (129, 2048, 256),
     # few rows, contraction <= 768: the low-latency mma.sync kernel of the dependent chains (csrc/gemm_small.cu)
@@ -78,6 +79,9 @@ def test_bwd_bf16(be, M, N, K):
     assert rel_err(dxb, ref_dx) < TOL_BF16
     be.linear_bwd_data(dyd, wd, dx, accumulate=True)
     assert rel_err(dx, 2 * ref_dx) < TOL_F32
+    # bf16 output with accumulate: the gradient sink of the decoder's memory operands (ops._GradSink)
+    be.linear_bwd_data(dyd, wd, dxb, accumulate=True)
+    assert rel_err(dxb, 2 * ref_dx) < 2 * TOL_BF16
     dw = torch.full((N, K), float("nan"), device="cuda")
     db = torch.empty(N, device="cuda")
     be.linear_bwd_weight(dyd, xd, dw, db)

@@ -425,3 +425,98 @@ def test_attention_with_dropout(be, B, H, Lq, Lk, two, use_mask, use_pavg, bf16)
     if two:
         assert rel_err(dq2, leaves[1].grad) < tol_g
         assert rel_err(dk2, leaves[3].grad) < tol_g
+
+
+# ---- layout glue (csrc/assembly.cu): the CUDA kernels against the plain-torch restatement of tests/emu_backend.py ---------
+def _emu():
+    from emu_backend import EmuBackend
+
+    return EmuBackend()
+
+
+@pytest.mark.parametrize("n,H,W,L,durs", [(5, 7, 7, 8, None), (8, 14, 14, 16, None), (8, 5, 9, 3, [5, 3]), (4, 14, 23, 16, [1, 3])])
+def test_token_assembly_and_backward(be, n, H, W, L, durs):
+    d = 256
+    b = 1 if durs is None else len(durs)
+    vis, vpos, text = g(n, d, H, W, seed=1), g(n, d, H, W, seed=2), g(L, b, d, seed=3)
+    cls, lpos = g(1, d, seed=4), g(1, d, seed=5)
+    f2v = vid_start = None
+    if durs is not None:
+        f2v = torch.tensor([j for j, t in enumerate(durs) for _ in range(t)], dtype=torch.long)
+        vid_start = torch.tensor([0] + [sum(durs[: j + 1]) for j in range(b)], dtype=torch.long)
+    S = 1 + H * W + L
+    mk = lambda dt: torch.empty(n, S, d, dtype=dt)
+    X, POS, qk, xo = mk(torch.float32), mk(torch.float32), mk(torch.bfloat16), mk(torch.bfloat16)
+    _emu().token_assembly(vis, vpos, text, f2v, cls, lpos, X, POS, qk, xo)
+    c = lambda t: None if t is None else t.cuda()
+    Xd, POSd, qkd, xod = (torch.empty_like(t, device="cuda") for t in (X, POS, qk, xo))
+    be.token_assembly(c(vis), c(vpos), c(text), c(f2v), c(cls), c(lpos), Xd, POSd, qkd, xod)
+    assert torch.equal(Xd.cpu(), X) and torch.equal(POSd.cpu(), POS)  # pure data movement: bit-exact
+    assert torch.equal(qkd.cpu(), qk) and torch.equal(xod.cpu(), xo)  # one fp32 add + round-to-nearest-even: bit-exact
+    dX = g(n, S, d, seed=6)
+    dvis, dtext, dcls = torch.empty(n, d, H, W), torch.empty(L, b, d), torch.empty(1, d)
+    _emu().token_assembly_bwd(dX, dvis, dtext, dcls, vid_start, H * W, L, b)
+    dvd, dtd, dcd = (torch.full_like(t, float("nan"), device="cuda") for t in (dvis, dtext, dcls))
+    be.token_assembly_bwd(c(dX), dvd, dtd, dcd, c(vid_start), H * W, L, b)
+    assert torch.equal(dvd.cpu(), dvis)
+    assert rel_err(dtd, dtext) < TOL32 and rel_err(dcd, dcls) < TOL32  # sums over frames: summation order only
+    be.token_assembly_bwd(c(dX), None, dtd, None, c(vid_start), H * W, L, b)  # every output is optional
+    assert rel_err(dtd, dtext) < TOL32
+
+
+@pytest.mark.parametrize("n,S", [(3, 9), (64, 213), (5, 340)])
+@pytest.mark.parametrize("gdt", [torch.bfloat16, torch.float32])
+def test_mem_operands_and_backward(be, n, S, gdt):
+    d = 256
+    X, POS = g(n, S, d, seed=1), g(n, S, d, seed=2)
+    M = S - 1
+    ref = [torch.empty(n * M, d, dtype=torch.bfloat16) for _ in range(3)] + [torch.empty(n, d)]
+    _emu().mem_operands(X, POS, *ref)
+    got = [torch.empty_like(t, device="cuda") for t in ref]
+    be.mem_operands(X.cuda(), POS.cuda(), *got)
+    for a, r in zip(got, ref):
+        assert torch.equal(a.cpu(), r)
+    g1, g2, gc = g(n * M, d, seed=3).to(gdt), g(n * M, d, seed=4).to(gdt), g(n, d, seed=5)
+    for use in ((True, True, True), (True, False, True), (False, True, False), (True, True, False)):
+        a1, a2, ac = (t if u else None for t, u in zip((g1, g2, gc), use))
+        dX = torch.empty(n, S, d)
+        _emu().mem_operands_bwd(a1, a2, ac, dX)
+        dXd = torch.full((n, S, d), float("nan"), device="cuda")
+        cu = lambda t: None if t is None else t.cuda()
+        be.mem_operands_bwd(cu(a1), cu(a2), cu(ac), dXd)
+        assert torch.equal(dXd.cpu(), dX), use
+
+
+@pytest.mark.parametrize("durs", [[64], [5, 3], [1, 7, 2]])
+def test_template_generator_kernels(be, durs):
+    d, q = 256, 4
+    b, n = len(durs), sum(durs)
+    bf = torch.bfloat16
+    v, fc = g(b, d, seed=1), g(n, d, seed=2)
+    W = [g(d, d, seed=10 + i, scale=d ** -0.5).to(bf) for i in range(3)] + [g(q, d, seed=13, scale=d ** -0.5).to(bf)]
+    bias = [g(d, seed=20 + i, scale=0.1) for i in range(3)] + [g(q, seed=23, scale=0.1)]
+    f2v = vid_start = None
+    if b > 1:
+        f2v = torch.tensor([j for j, t in enumerate(durs) for _ in range(t)], dtype=torch.long)
+        vid_start = torch.tensor([0] + [sum(durs[: j + 1]) for j in range(b)], dtype=torch.long)
+
+    def run(bk, dev):
+        mv = lambda t: None if t is None else t.to(dev)
+        e = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)
+        content, gamma, beta, mod, anchor, temp = e(b, d), e(b, d), e(b, d), e(n, d, dt=bf), e(n, q), e(n, d)
+        Wd, bd = [mv(w) for w in W], [mv(x) for x in bias]
+        bk.template_fwd(mv(v), mv(fc), mv(f2v), Wd[0], bd[0], Wd[1], bd[1], Wd[2], bd[2], Wd[3], bd[3], content, gamma, beta, mod, anchor, temp)
+        ga, gt = mv(g(n, q, seed=30)), mv(g(n, d, seed=31))
+        dpq, dmod, dpre, dfc, dv = e(n, q, dt=bf), e(n, d), e(3, b, d), e(n, d), e(b, d)
+        dW = [torch.ones(d, d, device=dev) for _ in range(3)] + [torch.ones(q, d, device=dev)]  # accumulated: start from 1
+        db = [torch.ones(d, device=dev) for _ in range(3)] + [torch.ones(q, device=dev)]
+        bk.template_bwd(ga, gt, anchor, mv(v), mv(fc), mv(f2v), mv(vid_start), gamma, beta, mod, Wd[0], Wd[1], Wd[2], Wd[3], dpq, dmod,
+                        dpre, dfc, dv, dW[0], db[0], dW[1], db[1], dW[2], db[2], dW[3], db[3])
+        return dict(content=content, gamma=gamma, beta=beta, mod=mod.float(), anchor=anchor, temp=temp, dfc=dfc, dv=dv,
+                    **{f"dW{i}": t for i, t in enumerate(dW)}, **{f"db{i}": t for i, t in enumerate(db)})
+
+    ref, got = run(_emu(), "cpu"), run(be, "cuda")
+    for k in ref:
+        # fp32 accumulation of bf16 products in another order; bf16-rounded intermediates (mod, dpq) may flip one ulp (2^-8)
+        tol = 1e-2 if k in ("mod", "dfc", "dv") or k.startswith(("dW", "db")) else 1e-4
+        assert rel_err(got[k], ref[k]) < tol, (k, rel_err(got[k], ref[k]))
