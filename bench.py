@@ -60,6 +60,9 @@ def parse_args():
     ap.add_argument("--cpu-steps", type=int, default=2, help="timed CPU-baseline steps (bounded sample)")
     ap.add_argument("--no-prefetch", dest="e2e_prefetch", action="store_false",
                     help="e2e: copy each step's inputs on the compute stream instead of prefetching them under the previous step")
+    ap.add_argument("--phases", action="store_true",
+                    help="record external timing events at the phase boundaries inside the captured step and report the phase "
+                         "durations of un-profiled graph replays (fused-glue path, 1 GPU)")
     ap.add_argument("--profile", default=None, help="write a per-kernel device-time table of 3 steps to this file")
     return ap.parse_args()
 
@@ -284,6 +287,7 @@ def build_b200(args, device):
     zero_async = os.environ.get("STCAT_ZERO_ASYNC", "1") != "0"
 
     def fwd_bwd(vis, pos, txt):
+        ops.mark_phase("step_start")
         if zero_async:
             grads.zero_async()  # the fill of the flat gradient buffer runs under the forward pass (joined before backward)
         else:
@@ -291,15 +295,19 @@ def build_b200(args, device):
         vis.grad = None
         txt.grad = None
         out = model(NestedTensor(vis, vis_mask, [w["T"]]), pos, (text_mask, txt, None))
+        ops.mark_phase("decoder_fwd_end")
         total, _ = plan(out)
+        ops.mark_phase("loss_end")
         sync.begin_step()
         sync.attach(out)
         grads.wait_zero()
         total.backward()
         ops.join_leaf_streams()
         sync.finish()  # mean over ranks (GradSync averages, like the DDP wrapper it replaces)
+        ops.mark_phase("backward_end")
         if opt is not None:
             opt.step()
+        ops.mark_phase("step_end")
         return total
 
     return {"model": model, "cfg": cfg, "host": host, "dev": dev, "grads": grads, "fwd_bwd": fwd_bwd, "ops": ops, "w": w,
@@ -471,6 +479,10 @@ def run_b200_arm(args):
         # persistent kernels leave exactly those free while a collective is in flight (stcat_b200/dp.py GradSync)
         os.environ.setdefault("NCCL_MAX_CTAS", "24")
         dist.init_process_group("nccl", device_id=device)
+    if getattr(args, "phases", False):
+        from stcat_b200 import ops as _ops
+
+        _ops.enable_phase_marks(True)
     ctx = build_b200(args, device)
     be = ctx["ops"].get_backend()
     grads = ctx["grads"]
@@ -591,6 +603,22 @@ def run_b200_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * args.steps / (float(t.item()) * 1e-3)
 
+    phases = None
+    if getattr(args, "phases", False) and rank == 0 and world == 1:
+        # un-profiled replays; the external event nodes of the last replay hold the phase boundaries
+        names = ["step_start", "encoder_fwd_end", "decoder_fwd_end", "loss_end", "decoder_bwd_end", "backward_end", "step_end"]
+        evs = ctx["ops"].phase_events() or {}
+        acc = {}
+        reps = 10
+        for _ in range(reps):
+            step()
+            torch.cuda.synchronize(device)
+            have = [n_ for n_ in names if n_ in evs]
+            for a_, b_ in zip(have[:-1], have[1:]):
+                acc[f"{a_}->{b_}"] = acc.get(f"{a_}->{b_}", 0.0) + evs[a_].elapsed_time(evs[b_]) / reps
+        phases = {k: round(v, 4) for k, v in acc.items()}
+        sys.stderr.write("phases (ms, un-profiled graph replay): " + json.dumps(phases) + "\n")
+
     if args.profile and rank == 0 and world == 1:  # (the captured step holds collectives: never replay it on one rank alone)
         from torch.profiler import profile, ProfilerActivity
 
@@ -671,6 +699,7 @@ def run_b200_arm(args):
                            "encoder_attn_block_fwd": fl["encoder_attn_block"]},
             "encoder_attention": enc_attn,
             "kernel_breakdown": breakdown,
+            **({"phases_ms": phases} if phases else {}),
             # shares of the device time of the instrumented C-ABI calls (the instrumented step itself is host-bound)
             "kernel_share": {"gemm": gemm_ms / max(sum(v["ms"] for v in breakdown["calls"].values()), 1e-9),
                              "attention": attn_ms / max(sum(v["ms"] for v in breakdown["calls"].values()), 1e-9)},

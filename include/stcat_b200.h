@@ -318,6 +318,28 @@ STCAT_API int stcat_template_bwd(const float* g_anchor, const float* g_temp, con
                                  void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Anchor-update chain between two box-decoder layers (query_decoder.py:205-219, 188-199):
+ *   box_head_fwd : out[R,4] = sigmoid(W3 h + b3 + inverse_sigmoid(anchor, eps)) -- the last Linear of bbox_embed (h bf16 [R,K]
+ *                  with leading dimension ldh, W3 bf16 [4,K]), the anchor refinement and, when sine != NULL, the sine
+ *                  embedding of the refined anchor (anchor_sine of `out`; sine fp32 [R,512], sine_op optional bf16 copy) in
+ *                  one launch.
+ *   box_head_bwd : from g = d loss / d out: dd_op bf16 [R,4] = bf16(g out (1 - out)) (operand of the W3 weight gradient),
+ *                  danchor [R,4] (optional, through the clamped logit) and dh bf16 [R,K] = (dd_op W3) * (h > 0): the data
+ *                  gradient of the last Linear with the ReLU mask of its input h folded in.
+ *   mul_cast     : out_f32[r,c] (may be NULL) = a[r,c] * b[r,c] and out_bf16 = its bf16 copy, c < cols; a has leading dimension
+ *                  lda (query_sine = sine[:, :d] * query_scale(out) with its GEMM-operand copy in one launch); optionally
+ *                  c_out_bf16[r,c] = bf16(c_in[r,c]) in the same launch (the operand copy of query_pos);
+ *                  mul_cast_bwd: db = g * a (g fp32 or bf16).
+ * ---------------------------------------------------------------------------------------------- */
+STCAT_API int stcat_box_head_fwd(const void* h, int64_t ldh, const void* W, const float* bias, const float* anchor, float* out, float* sine,
+                                 void* sine_op, int R, int K, float eps, void* stream);
+STCAT_API int stcat_box_head_bwd(const float* g, const float* out, const float* anchor, const void* W, const void* h, int64_t ldh,
+                                 void* dd_op, void* dh, float* danchor, int R, int K, float eps, void* stream);
+STCAT_API int stcat_mul_cast(const float* a, int64_t lda, const float* b, float* out_f32, void* out_bf16, const float* c_in,
+                             void* c_out_bf16, int64_t rows, int cols, void* stream);
+STCAT_API int stcat_mul_cast_bwd(const void* g, int g_dtype, const float* a, int64_t lda, float* db, int64_t rows, int cols, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Anchor glue of the box decoder (query_decoder.py:188-219; net_utils.py:29-63), fp32, one launch each:
  *   anchor_sine : out[n,512] = gen_sineembed_for_position(anchor[n,4]) (order y,x,w,h; 128 dims per coordinate;
  *                 sin on even / cos on odd dims of 2 pi c / 10000^(2 floor(k/2)/128)); out_bf16 optional operand copy.

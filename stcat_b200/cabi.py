@@ -86,6 +86,10 @@ SIGNATURES["stcat_mem_operands"] = (c_int, [_P] * 6 + [_I] * 3 + [_P])
 SIGNATURES["stcat_mem_operands_bwd"] = (c_int, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _P])
 SIGNATURES["stcat_template_fwd"] = (c_int, [_P] * 17 + [_I] * 4 + [_P])
 SIGNATURES["stcat_template_bwd"] = (c_int, [_P] * 27 + [_I] * 4 + [_P])
+SIGNATURES["stcat_box_head_fwd"] = (c_int, [_P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P])
+SIGNATURES["stcat_box_head_bwd"] = (c_int, [_P, _P, _P, _P, _P, _L, _P, _P, _P, _I, _I, _F, _P])
+SIGNATURES["stcat_mul_cast"] = (c_int, [_P, _L, _P, _P, _P, _P, _P, _L, _I, _P])
+SIGNATURES["stcat_mul_cast_bwd"] = (c_int, [_P, _I, _P, _L, _P, _L, _I, _P])
 MAX_GROUP_JOBS = 12
 ABI_VERSION = 11  # include/stcat_b200.h STCAT_ABI_VERSION
 
@@ -558,3 +562,43 @@ class CudaBackend:
             F_(d_frames_cls, "d_frames_cls"), F_(d_videos_cls, "d_videos_cls"), F_(dWc, "dWc"), F_(dbc, "dbc"), F_(dWg, "dWg"),
             F_(dbg, "dbg"), F_(dWb, "dWb"), F_(dbb, "dbb"), F_(dWa, "dWa"), F_(dba, "dba"), n, b, d, q, self._stream()), "template_bwd")
         self.launches += 3
+
+    def box_head_fwd(self, h, W, bias, anchor, out, sine, sine_op, eps=1e-3):
+        """h bf16 [R, K] (row-major view), W bf16 [4, K], anchor / out fp32 [R, 4]; sine fp32 [R, 512] + bf16 copy, or None"""
+        hp, ldh, hdt = self._mat(h, "h")
+        assert hdt == BF16 and W.shape[0] == 4 and W.shape[1] == h.shape[1]
+        R, K = h.shape
+        self._rc(self.lib.stcat_box_head_fwd(hp, ldh, self._flat(W, "W", torch.bfloat16), self._flat(bias, "bias", torch.float32),
+                                             self._flat(anchor, "anchor", torch.float32), self._flat(out, "out", torch.float32),
+                                             self._flat(sine, "sine", torch.float32), self._flat(sine_op, "sine_op", torch.bfloat16),
+                                             R, K, float(eps), self._stream()), "box_head_fwd")
+        self.launches += 1
+
+    def mul_cast(self, a, b, out_f32, out_bf16, c_in=None, c_out=None):
+        """out_f32 (or None) = a[:, :c] * b and out_bf16 [R, c] its bf16 copy; a fp32 [R, >= c] row-major view, b fp32 [R, c]"""
+        ap, lda, adt = self._mat(a, "a")
+        assert adt == F32
+        R, c = b.shape
+        self._rc(self.lib.stcat_mul_cast(ap, lda, self._flat(b, "b", torch.float32), self._flat(out_f32, "out_f32", torch.float32),
+                                         self._flat(out_bf16, "out", torch.bfloat16), self._flat(c_in, "c_in", torch.float32),
+                                         self._flat(c_out, "c_out", torch.bfloat16), R, c,
+                                         self._stream()), "mul_cast")
+        self.launches += 1
+
+    def mul_cast_bwd(self, g, a, db):
+        ap, lda, adt = self._mat(a, "a")
+        assert adt == F32
+        R, c = db.shape
+        self._rc(self.lib.stcat_mul_cast_bwd(self._flat(g, "g"), _dt(g), ap, lda, self._flat(db, "db", torch.float32), R, c,
+                                             self._stream()), "mul_cast_bwd")
+        self.launches += 1
+
+    def box_head_bwd(self, g, out, anchor, W, h, dd_op, dh, danchor, eps=1e-3):
+        f, bf = torch.float32, torch.bfloat16
+        hp, ldh, hdt = self._mat(h, "h")
+        assert hdt == BF16
+        R, K = h.shape
+        self._rc(self.lib.stcat_box_head_bwd(self._flat(g, "g", f), self._flat(out, "out", f), self._flat(anchor, "anchor", f),
+                                             self._flat(W, "W", bf), hp, ldh, self._flat(dd_op, "dd_op", bf), self._flat(dh, "dh", bf),
+                                             self._flat(danchor, "danchor", f), R, K, float(eps), self._stream()), "box_head_bwd")
+        self.launches += 1

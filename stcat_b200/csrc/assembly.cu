@@ -510,6 +510,139 @@ __global__ void __launch_bounds__(256) template_film_bwd_kernel(TplWArgs a) {
     }
 }
 
+// ---- box head + anchor refinement + sine embedding of the refined anchor (query_decoder.py:205-219, net_utils.py:29-63) ----
+// One block per query row: delta = W3 h + b3 (q = 4 outputs), a' = sigmoid(delta + logit_clamped(anchor)), then the 512-wide sine
+// embedding of a' (the next layer's positional input; a' is detached there) -- three dependent launches of the anchor-update
+// chain between two box-decoder layers as one.
+__device__ __forceinline__ float logit_clamped_(float x, float eps) {
+    x = fminf(fmaxf(x, 0.f), 1.f);
+    return logf(fmaxf(x, eps) / fmaxf(1.f - x, eps));
+}
+__global__ void __launch_bounds__(128)
+box_head_kernel(const __nv_bfloat16* __restrict__ h, int64_t ldh, const __nv_bfloat16* __restrict__ W, const float* __restrict__ bias,
+                const float* __restrict__ anchor, float* __restrict__ out, float* __restrict__ sine, __nv_bfloat16* __restrict__ sine_op,
+                int R, int K, float eps) {
+    __shared__ float red[4][4];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = blockIdx.x;  // one block of 4 warps per query row: the 512 sine / cosine evaluations are 4 per thread
+    float pre[4];  // bias + inverse_sigmoid(anchor): loaded up front, off the dependent chain behind the reduction
+#pragma unroll
+    for (int o = 0; o < 4; ++o) pre[o] = bias[o] + logit_clamped_(anchor[(int64_t)r * 4 + o], eps);
+    const float freq = powf(10000.f, (float)(2 * (tid >> 1)) / 128.f);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = tid * 2; k < K; k += 256) {  // K is even
+        const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(h + (int64_t)r * ldh + k));
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const float2 w = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(W + (int64_t)o * K + k));
+            acc[o] += x.x * w.x + x.y * w.y;
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        const float sum = warp_sum(acc[o]);
+        if (lane == 0) red[warp][o] = sum;
+    }
+    __syncthreads();
+    float a[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        const float z = ((red[0][o] + red[1][o]) + (red[2][o] + red[3][o])) + pre[o];
+        a[o] = 1.f / (1.f + expf(-z));
+    }
+    if (tid < 4) out[(int64_t)r * 4 + tid] = a[tid];
+    if (sine) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int j = tid + 128 * i, k = tid;  // j >> 7 == i: output block i = (y, x, w, h)[i] (anchor_sine_fwd_kernel)
+            const float ac = i == 0 ? a[1] : (i == 1 ? a[0] : (i == 2 ? a[2] : a[3]));
+            const float ph = ac * 6.283185307179586f / freq;
+            const float v = (k & 1) ? cosf(ph) : sinf(ph);
+            sine[(int64_t)r * 512 + j] = v;
+            if (sine_op) sine_op[(int64_t)r * 512 + j] = __float2bfloat16_rn(v);
+        }
+    }
+}
+
+// backward of box_head_kernel up to the hidden activation: dz = g s (1 - s) (s = the refined anchor) -> dd_op = bf16(dz) [R, 4]
+// (the operand of the W3 weight gradient), danchor (optional) through the clamped logit, and the data gradient of the last
+// Linear with the ReLU mask of its input folded in: dh[r, k] = (sum_o dd_op[r, o] W3[o, k]) * (h[r, k] > 0), bf16.
+__global__ void __launch_bounds__(128)
+box_head_bwd_kernel(const float* __restrict__ g, const float* __restrict__ out, const float* __restrict__ anchor,
+                    const __nv_bfloat16* __restrict__ W, const __nv_bfloat16* __restrict__ h, int64_t ldh, __nv_bfloat16* __restrict__ dd_op,
+                    __nv_bfloat16* __restrict__ dh, float* __restrict__ danchor, int R, int K, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int tid = threadIdx.x;
+    const int r = blockIdx.x;
+    float dd[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        const float sgm = out[(int64_t)r * 4 + o];
+        const float dz = g[(int64_t)r * 4 + o] * sgm * (1.f - sgm);
+        const __nv_bfloat16 q = __float2bfloat16_rn(dz);
+        dd[o] = __bfloat162float(q);
+        if (tid == o) {
+            dd_op[(int64_t)r * 4 + o] = q;
+            if (danchor) {
+                const float x = anchor[(int64_t)r * 4 + o];
+                float d = 0.f;
+                if (x > 0.f && x < 1.f) {
+                    if (x > eps) d += 1.f / x;
+                    if (1.f - x > eps) d += 1.f / (1.f - x);
+                }
+                danchor[(int64_t)r * 4 + o] = dz * d;
+            }
+        }
+    }
+    for (int k = tid * 2; k < K; k += 256) {
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const float2 w = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(W + (int64_t)o * K + k));
+            acc.x += dd[o] * w.x;
+            acc.y += dd[o] * w.y;
+        }
+        const float2 hv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(h + (int64_t)r * ldh + k));
+        if (!(hv.x > 0.f)) acc.x = 0.f;
+        if (!(hv.y > 0.f)) acc.y = 0.f;
+        *reinterpret_cast<__nv_bfloat162*>(dh + (int64_t)r * K + k) = __floats2bfloat162_rn(acc.x, acc.y);
+    }
+}
+
+// out_bf16[r, c] = bf16(a[r, c] * b[r, c]) for c < cols (a has leading dimension lda: the first `cols` columns of the sine
+// embedding); backward: db[r, c] = g[r, c] * a[r, c]
+__global__ void __launch_bounds__(256)
+mul_cast_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ b, float* __restrict__ out_f32,
+                __nv_bfloat16* __restrict__ out, const float* __restrict__ c_in, __nv_bfloat16* __restrict__ c_out, int64_t rows, int cols) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t total = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols;
+        const int c = (int)(i - r * cols);
+        const float v = a[r * lda + c] * b[i];
+        if (out_f32) out_f32[i] = v;
+        out[i] = __float2bfloat16_rn(v);
+        if (c_out) c_out[i] = __float2bfloat16_rn(c_in[i]);  // a second operand copy riding in the same launch (query_pos)
+    }
+}
+__global__ void __launch_bounds__(256)
+mul_cast_bwd_kernel(const void* __restrict__ g, int g_dtype, const float* __restrict__ a, int64_t lda, float* __restrict__ db,
+                    int64_t rows, int cols) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t total = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols;
+        const int c = (int)(i - r * cols);
+        const float gv = g_dtype == STCAT_F32 ? reinterpret_cast<const float*>(g)[i] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(g)[i]);
+        db[i] = gv * a[r * lda + c];
+    }
+}
+
 int grid_cap(int64_t blocks) {
     const int64_t cap = (int64_t)num_sms() * 8;
     if (blocks > cap) blocks = cap;
@@ -639,6 +772,51 @@ STCAT_API int stcat_template_bwd(const float* g_anchor, const float* g_temp, con
     e = launch_pdl(template_film_bwd_kernel, dim3((unsigned)(w.w_blocks + b * w.kchunks)), dim3(256), 0, st, w);
     if (e != cudaSuccess) return set_err((int)e, "template_bwd(film): %s", cudaGetErrorString(e));
     return check_launch("template_bwd");
+}
+
+STCAT_API int stcat_box_head_fwd(const void* h, int64_t ldh, const void* W, const float* bias, const float* anchor, float* out, float* sine,
+                                 void* sine_op, int R, int K, float eps, void* stream) {
+    STCAT_REQUIRE(h && W && bias && anchor && out, STCAT_EINVAL, "box_head_fwd: null pointer");
+    STCAT_REQUIRE(R >= 0 && K > 0 && K % 2 == 0 && ldh >= K && ldh % 2 == 0, STCAT_ESHAPE, "box_head_fwd: bad shape R=%d K=%d ldh=%lld", R, K, (long long)ldh);
+    STCAT_REQUIRE(sine || !sine_op, STCAT_EINVAL, "box_head_fwd: sine_op needs sine");
+    if (R == 0) return 0;
+    cudaError_t e = launch_pdl(box_head_kernel, dim3((unsigned)R), dim3(128), 0, (cudaStream_t)stream, (const __nv_bfloat16*)h, ldh,
+                               (const __nv_bfloat16*)W, bias, anchor, out, sine, (__nv_bfloat16*)sine_op, R, K, eps);
+    if (e != cudaSuccess) return set_err((int)e, "box_head_fwd: %s", cudaGetErrorString(e));
+    return check_launch("box_head_fwd");
+}
+
+STCAT_API int stcat_mul_cast(const float* a, int64_t lda, const float* b, float* out_f32, void* out_bf16, const float* c_in,
+                             void* c_out_bf16, int64_t rows, int cols, void* stream) {
+    STCAT_REQUIRE(a && b && out_bf16, STCAT_EINVAL, "mul_cast: null pointer");
+    STCAT_REQUIRE(rows >= 0 && cols > 0 && lda >= cols, STCAT_ESHAPE, "mul_cast: bad shape");
+    STCAT_REQUIRE(c_in || !c_out_bf16, STCAT_EINVAL, "mul_cast: c_out needs c_in");
+    if (rows == 0) return 0;
+    cudaError_t e = launch_pdl(mul_cast_kernel, dim3(grid_cap((rows * cols + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, a, lda, b,
+                               out_f32, (__nv_bfloat16*)out_bf16, c_in, (__nv_bfloat16*)c_out_bf16, rows, cols);
+    if (e != cudaSuccess) return set_err((int)e, "mul_cast: %s", cudaGetErrorString(e));
+    return check_launch("mul_cast");
+}
+
+STCAT_API int stcat_mul_cast_bwd(const void* g, int g_dtype, const float* a, int64_t lda, float* db, int64_t rows, int cols, void* stream) {
+    STCAT_REQUIRE(g && a && db, STCAT_EINVAL, "mul_cast_bwd: null pointer");
+    STCAT_REQUIRE(rows >= 0 && cols > 0 && lda >= cols && (g_dtype == STCAT_F32 || g_dtype == STCAT_BF16), STCAT_ESHAPE, "mul_cast_bwd: bad shape / dtype");
+    if (rows == 0) return 0;
+    cudaError_t e = launch_pdl(mul_cast_bwd_kernel, dim3(grid_cap((rows * cols + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, g, g_dtype,
+                               a, lda, db, rows, cols);
+    if (e != cudaSuccess) return set_err((int)e, "mul_cast_bwd: %s", cudaGetErrorString(e));
+    return check_launch("mul_cast_bwd");
+}
+
+STCAT_API int stcat_box_head_bwd(const float* g, const float* out, const float* anchor, const void* W, const void* h, int64_t ldh,
+                                 void* dd_op, void* dh, float* danchor, int R, int K, float eps, void* stream) {
+    STCAT_REQUIRE(g && out && anchor && W && h && dd_op && dh, STCAT_EINVAL, "box_head_bwd: null pointer");
+    STCAT_REQUIRE(R >= 0 && K > 0 && K % 2 == 0 && ldh >= K && ldh % 2 == 0, STCAT_ESHAPE, "box_head_bwd: bad shape R=%d K=%d", R, K);
+    if (R == 0) return 0;
+    cudaError_t e = launch_pdl(box_head_bwd_kernel, dim3((unsigned)R), dim3(128), 0, (cudaStream_t)stream, g, out, anchor,
+                               (const __nv_bfloat16*)W, (const __nv_bfloat16*)h, ldh, (__nv_bfloat16*)dd_op, (__nv_bfloat16*)dh, danchor, R, K, eps);
+    if (e != cudaSuccess) return set_err((int)e, "box_head_bwd: %s", cudaGetErrorString(e));
+    return check_launch("box_head_bwd");
 }
 
 }  // extern "C"

@@ -28,7 +28,7 @@ from .encoder import batch_indices, fused_glue, _check_cfg
 from .params import LinearP, MHAP, MLPP, NormP, OutProjOnly, SineTable, LearnedTable, xavier_reset
 
 _const_cache = {}
-_MULTI_STREAM = True
+_MULTI_STREAM = os.environ.get("STCAT_SINGLE_STREAM", "0") == "0"
 _stream_cache = {}
 
 
@@ -39,6 +39,7 @@ def set_multi_stream(on: bool):
 
 
 _MEMSIDE_SMS = int(os.environ.get("STCAT_MEMSIDE_SMS", "112"))
+_FUSED_HEAD = os.environ.get("STCAT_FUSED_HEAD", "1") != "0"  # ops.box_head / mul_operand in the anchor-update chain (A/B switch)
 
 
 def _side_streams(device):
@@ -249,13 +250,13 @@ class TransformerDecoderLayer(nn.Module):
             kc = _lin(self.ca_kcontent_proj, c.mem_op, out_bf16=True)
         return kc, kp, vv
 
-    def run(self, c: _Ctx, tgt, tgt_op, query_pos, query_time, time_op, query_sine, sine_op, is_first: bool, mem_kv):
+    def run(self, c: _Ctx, tgt, tgt_op, query_pos, query_time, time_op, query_sine, sine_op, is_first: bool, mem_kv, pos_op=None):
         """``*_op`` are the (non-differentiable) GEMM-operand copies of the tensors before them: every activation is
         cast once, by its producer where possible, not once per consuming Linear.  Intermediates that feed exactly
         one GEMM / attention (q, k, v, qc, qs) are written in the operand dtype by the producing epilogue."""
         d, H = self.d, self.nhead
         p = self.dropout_p if self.training else 0.0  # query_decoder.py:269,286,293-303: attention, dropout1/3/4, FFN inner
-        pos_op = ops.operand_copy(query_pos)
+        pos_op = pos_op if pos_op is not None else ops.operand_copy(query_pos)
         # ---- temporal self attention over the t queries of each video (:329-345) ----
         L = lambda p: (p.weight, p.bias)
         q, k, v = ops.linear_group(
@@ -299,6 +300,31 @@ class TransformerDecoderLayer(nn.Module):
                              self.linear2.bias, self.norm4.weight, self.norm4.bias, self.norm4.eps, drop_p=p)
 
 
+_GROUP_MEMSIDE = os.environ.get("STCAT_GROUP_MEMSIDE", "1") != "0"
+
+
+def memory_side_pair(c: _Ctx, box: "TransformerDecoderLayer", tim: "TimeDecoderLayer", is_first: bool):
+    """The memory-side key / value projections of one box-decoder layer and one time-decoder layer (query_decoder.py:355-366,
+    633-639) as ONE grouped launch: five [n M, 256] x [256, 256] GEMMs of one tile wave each become 5 x 106 tiles of one
+    persistent launch (tile pipelining across jobs); backward: one grouped data-gradient launch (three terms accumulate in
+    TMEM for the memory operand), one grouped weight-gradient launch, one grouped column-sum launch instead of 14 launches.
+    Returns ((kc, kp, vv), (K, V))."""
+    if not (_GROUP_MEMSIDE and box.from_scratch):
+        return box.memory_side(c, is_first), tim.memory_side(c)
+    d = box.d
+    L = lambda p: (p.weight, p.bias)
+    ca = tim.cross_attn_image
+    kc_terms = [(0, *L(box.ca_kcontent_proj))] + ([(1, *L(box.ca_kpos_proj))] if is_first else [])
+    kc, kp, vv, K, V = ops.linear_group(
+        [(c.mem_op, None), (c.pos_op, None), (c.mempos_op, None)],
+        [{"terms": kc_terms, "out_bf16": True},
+         {"terms": [(1, *L(box.ca_kpos_proj))], "out_bf16": True},
+         {"terms": [(0, *L(box.ca_v_proj))], "out_bf16": True},
+         {"terms": [(2, ca.in_proj_weight, ca.in_proj_bias, (d, 2 * d))], "out_bf16": True},
+         {"terms": [(0, ca.in_proj_weight, ca.in_proj_bias, (2 * d, 3 * d))], "out_bf16": True}])
+    return (kc, kp, vv), (K, V)
+
+
 class TransformerDecoder(nn.Module):
     """Anchor-refining box decoder (query_decoder.py:150-247)."""
 
@@ -319,8 +345,18 @@ class TransformerDecoder(nn.Module):
         out, out_op = tgt, None
         inter, refs = [], [anchor]
         time_op = ops.operand_copy(query_time)
+        # bf16 mode on the device: the last Linear of bbox_embed + anchor refinement + the next layer's sine embedding are one
+        # launch (ops.box_head) and query_sine is written directly as a GEMM operand (ops.mul_operand)
+        be_ = self.bbox_embed
+        fuse_head = (_FUSED_HEAD and fused_glue() and be_ is not None and self.query_dim == 4 and anchor.shape[-1] == 4 and len(be_.layers) >= 2
+                     and be_.layers[-1].weight.shape[0] == 4 and all(l_.bias is not None for l_ in be_.layers))
+        nxt = None  # (sine, sine_op) of the refined anchor, from the previous layer's box head
         for li, layer in enumerate(self.layers):
-            sine, sine_op = anchor_sine_embed_op(anchor[..., : self.query_dim])  # [b*t, 512] (+ operand copy)
+            qpos_op = None
+            if nxt is not None:
+                sine, sine_op = nxt
+            else:
+                sine, sine_op = anchor_sine_embed_op(anchor[..., : self.query_dim])  # [b*t, 512] (+ operand copy)
             if sine_op is None:
                 sine_op = ops.operand_copy(sine)
             rp, qsc = self.ref_point_head.layers, self.query_scale.layers
@@ -335,10 +371,20 @@ class TransformerDecoder(nn.Module):
                 query_pos, scale = ops.linear_group([(h1, None), (h2, None)],
                                                     [{"terms": [(0, rp[1].weight, rp[1].bias)]},
                                                      {"terms": [(1, qsc[1].weight, qsc[1].bias)]}])
-                qsine, qsine_op = sine[..., :d] * scale, None
-            out, out_op = layer.run(c, out, out_op, query_pos, query_time, time_op, qsine, qsine_op, li == 0, mem_kv[li])
+                if fuse_head and not sine.requires_grad and sine.dim() == 2:
+                    qsine, qsine_op, qpos_op = ops.mul_operand(sine, scale, query_pos)  # + the operand copy of query_pos
+                else:
+                    qsine, qsine_op = sine[..., :d] * scale, None
+            out, out_op = layer.run(c, out, out_op, query_pos, query_time, time_op, qsine, qsine_op, li == 0, mem_kv[li],
+                                    pos_op=qpos_op)
+            nxt = None
             if self.bbox_embed is not None:
-                new_anchor = box_refine(run_mlp(self.bbox_embed, out, x_op=out_op), anchor)
+                if fuse_head and out.dim() == 2:
+                    last = li == self.num_layers - 1
+                    new_anchor, s_, so_ = ops.box_mlp_head(be_.layers, out, out_op, anchor, want_sine=not last)
+                    nxt = None if last else (s_, so_)
+                else:
+                    new_anchor = box_refine(run_mlp(self.bbox_embed, out, x_op=out_op), anchor)
                 if li != self.num_layers - 1:
                     refs.append(new_anchor)
                 anchor = new_anchor.detach()
@@ -522,8 +568,9 @@ class QueryDecoder(nn.Module):
             c = _Ctx(idx, mem, mem_pos, key_mask, M, operands, enc_stream)
             anchors = c.padded(anchor_frames)  # [b*t, 4]
             query_temporal = c.padded(temp_query)  # [b*t, d]
-            box_kv = [(lambda l=l, i=i: l.memory_side(c, i == 0)) for i, l in enumerate(self.decoder.layers)]
-            time_kv = [(lambda l=l: l.memory_side(c)) for l in self.temp_decoder.layers]
+            pairs = [memory_side_pair(c, self.decoder.layers[i], self.temp_decoder.layers[i], i == 0) for i in range(nl)]
+            box_kv = [p_[0] for p_ in pairs]
+            time_kv = [p_[1] for p_ in pairs]
             outputs = self.decoder.run(c, tgt, anchors, query_time, box_kv)
             outputs_temp = self.temp_decoder.run(c, tgt.clone(), query_temporal, query_time, time_kv)
             return outputs, outputs_temp
@@ -545,10 +592,12 @@ class QueryDecoder(nn.Module):
             # the chains' small kernels (ops.sm_limit; STCAT_MEMSIDE_SMS overrides, 0 = no cap)
             with ops.sm_limit(_MEMSIDE_SMS):
                 for i in range(nl):
-                    box_kv.append(self.decoder.layers[i].memory_side(c, i == 0))
-                    ev_box.append(sM.record_event())
-                    time_kv.append(self.temp_decoder.layers[i].memory_side(c))
-                    ev_time.append(sM.record_event())
+                    bkv, tkv = memory_side_pair(c, self.decoder.layers[i], self.temp_decoder.layers[i], i == 0)
+                    box_kv.append(bkv)
+                    time_kv.append(tkv)
+                    ev = sM.record_event()
+                    ev_box.append(ev)
+                    ev_time.append(ev)
 
         def waiter(stream, evs, vals):
             def mk(i):

@@ -336,6 +336,29 @@ class _capped:
             self.be.set_gemm_sm_limit(0)
 
 
+# Phase marks (measurement only, bench.py --phases): timing events recorded inside a captured step as EXTERNAL event nodes, so
+# the phase boundaries of a graph replay can be read without a profiler attached.  None = off.
+_phase_events = None
+
+
+def enable_phase_marks(on: bool = True):
+    global _phase_events
+    _phase_events = {} if on else None
+
+
+def phase_events():
+    return _phase_events
+
+
+def mark_phase(name: str):
+    if _phase_events is None or not torch.cuda.is_available():
+        return
+    ev = _phase_events.get(name)
+    if ev is None:
+        ev = _phase_events[name] = torch.cuda.Event(enable_timing=True, external=True)
+    ev.record()
+
+
 _GRAD_SINK = os.environ.get("STCAT_GRAD_SINK", "1") != "0"
 
 
@@ -594,10 +617,13 @@ class LinearGroupFn(Function):
             y = torch.empty(M, N, dtype=odt, device=xs[0].device)
             outs.append(y)
             calls.setdefault(odt, []).append(dict(terms=terms, out=y, relu=bool(j.get("relu"))))
-        for group in calls.values():
-            be.linear_group(0, group)
+        ctx.sm_limit = _sm_limit
+        with _capped(be, ctx.sm_limit):
+            for group in calls.values():
+                be.linear_group(0, group)
         ctx.spec = spec
         ctx.biases = bs
+        ctx.sinks = [(_sink_of(x) if x.dim() == 2 else None) for x in xs]
         ctx.x_meta = [(x.shape, x.dtype) for x in xs]
         ctx.save_for_backward(*xos, *ws, *[y if j.get("relu") else None for y, j in zip(outs, jobs)])
         lead = xs[0].shape[:-1]
@@ -640,6 +666,7 @@ class LinearGroupFn(Function):
         # ---- dgrad: dx_i = sum over terms reading x_i of dy_j . W_t ----
         dxs = [None] * nin
         dcalls = {}
+        sinks_used = []
         for i in range(nin):
             if not ctx.needs_input_grad[1 + i]:
                 continue
@@ -647,15 +674,28 @@ class LinearGroupFn(Function):
             if not terms:
                 continue
             shape, xdt = ctx.x_meta[i]
-            dx = torch.empty(M, shape[-1], dtype=xdt, device=dev)
-            dxs[i] = dx.view(shape)
-            first = True
+            sink = ctx.sinks[i]
+            if sink is not None:
+                # the input is read by many Linear nodes (_GradSink): accumulate into its buffer, hand autograd nothing
+                first = sink.buf is None
+                if first:
+                    sink.buf = torch.empty(M, shape[-1], dtype=xdt, device=dev)
+                dx = sink.buf
+                sinks_used.append(sink)
+            else:
+                dx = torch.empty(M, shape[-1], dtype=xdt, device=dev)
+                dxs[i] = dx.view(shape)
+                first = True
             while terms:  # more than three readers of one input: further launches accumulate
                 dcalls.setdefault((xdt, first), []).append(dict(terms=terms[:3], out=dx, accumulate=not first))
                 terms = terms[3:]
                 first = False
-        for (_, first), group in sorted(dcalls.items(), key=lambda kv: not kv[0][1]):
-            be.linear_group(1, group)
+        with _capped(be, ctx.sm_limit):
+            for (_, first), group in sorted(dcalls.items(), key=lambda kv: not kv[0][1]):
+                be.linear_group(1, group)
+        for sink in sinks_used:
+            if sink.buf.is_cuda:
+                sink.event = torch.cuda.current_stream().record_event()
         # ---- wgrad + bias column sums ----
         dws, dbs = [None] * nt, [None] * nt
         wjobs = []
@@ -676,7 +716,7 @@ class LinearGroupFn(Function):
                     dbs[tx] = torch.zeros(b.shape, dtype=f32, device=dev)
                     gb = dbs[tx] if rows is None else dbs[tx][rows[0]:rows[1]]
             wjobs.append(dict(terms=[(dyos[jx], xos[i], None)], out=gw, accumulate=True, dbias=gb))
-        with _on_leaf(*((dyos + [x for x in xos if x is not None]) if all_fused else [])):
+        with _on_leaf(*((dyos + [x for x in xos if x is not None]) if all_fused else [])), _capped(be, ctx.sm_limit):
             for k in range(0, len(wjobs), 12):
                 be.linear_group(2, wjobs[k:k + 12])
         return (None, *dxs, *([None] * nin), *dws, *dbs)
@@ -1422,6 +1462,7 @@ class MemOperandsFn(Function):
         mempos_op = torch.empty(n * M, d, dtype=bf, device=dev)
         cls = torch.empty(n, d, dtype=torch.float32, device=dev)
         Xd = X.detach()
+        mark_phase("encoder_fwd_end")
         be.mem_operands(Xd if Xd.is_contiguous() else Xd.contiguous(), POS.detach().contiguous(), mem_op, pos_op, mempos_op, cls)
         ctx.shape = (n, S, d)
         ctx.mark_non_differentiable(pos_op)
@@ -1443,6 +1484,7 @@ class MemOperandsFn(Function):
         g_cls = None if g_cls is None else fix(g_cls.float() if g_cls.dtype != torch.float32 else g_cls)
         dX = torch.empty(n, S, d, dtype=torch.float32, device=ref.device)
         get_backend().mem_operands_bwd(fix(g_mem), fix(g_mempos), g_cls, dX)
+        mark_phase("decoder_bwd_end")
         return dX, None, None
 
 
@@ -1517,6 +1559,174 @@ class TemplateFn(Function):
 
 def template(videos_cls, frames_cls, Wc, bc, Wg, bg, Wb, bb, Wa, ba, f2v=None, vid_start=None):
     return TemplateFn.apply(videos_cls, frames_cls, Wc, bc, Wg, bg, Wb, bb, Wa, ba, f2v, vid_start)
+
+
+class BoxHeadFn(Function):
+    """(new_anchor, sine, sine_op) = the last Linear of ``bbox_embed`` on the bf16 hidden activation ``h``, the anchor refinement
+    sigmoid(delta + inverse_sigmoid(anchor)) and the sine embedding of the (detached) refined anchor in ONE launch
+    (query_decoder.py:205-219, 188-199; net_utils.py:29-63).  The sine outputs are constants for autograd, exactly as in the
+    reference, where the next layer embeds ``new_reference_points.detach()``.  Backward: box_refine_bwd, then the data / weight
+    gradients of the Linear as in LinearFn."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, anchor, want_sine: bool, eps: float):
+        be = get_backend()
+        R, K = h.shape
+        dev = h.device
+        a = anchor.detach().float().contiguous()
+        out = torch.empty(R, 4, dtype=torch.float32, device=dev)
+        sine = torch.empty(R, 512, dtype=torch.float32, device=dev) if want_sine else None
+        sine_op = torch.empty(R, 512, dtype=torch.bfloat16, device=dev) if want_sine else None
+        hd = h.detach()
+        be.box_head_fwd(hd, _operand(weight.detach(), True), bias.detach(), a, out, sine, sine_op, eps)
+        ctx.save_for_backward(hd, weight, bias, out, a)
+        ctx.eps = eps
+        ctx.set_materialize_grads(False)
+        if want_sine:
+            ctx.mark_non_differentiable(sine, sine_op)
+        return out, sine, sine_op
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g, _s, _so):
+        if g is None:
+            return (None,) * 6
+        be = get_backend()
+        hd, weight, bias, out, a = ctx.saved_tensors
+        R, K = hd.shape
+        g = g if (g.is_contiguous() and g.dtype == torch.float32) else g.contiguous().float()
+        dd = torch.empty_like(out)
+        da = torch.empty_like(out) if ctx.needs_input_grad[3] else None
+        be.box_refine_bwd(out, a, g, dd, da, ctx.eps)
+        dyo = _operand(dd)
+        dh = None
+        if ctx.needs_input_grad[0]:
+            dh = torch.empty(R, K, dtype=hd.dtype, device=hd.device)
+            be.linear_bwd_data(dyo, _operand(weight.detach(), True), dh)
+        dw, db = _wgrad(be, dyo, hd, weight, bias, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
+        return dh, dw, db, da, None, None
+
+
+def box_head(h, weight, bias, anchor, want_sine: bool = True, eps: float = 1e-3):
+    return BoxHeadFn.apply(h, weight, bias, anchor, want_sine, eps)
+
+
+class BoxMLPHeadFn(Function):
+    """``bbox_embed`` (Linear-ReLU stack, net_utils.py:7-26) + anchor refinement + the next layer's sine embedding as ONE
+    autograd node (query_decoder.py:205-219): forward = the hidden Linears (bf16 outputs) and ops.box_head's kernel; backward =
+    stcat_box_head_bwd (refinement gradient, data gradient of the last Linear, ReLU mask) and one data-gradient GEMM per
+    hidden layer with the ReLU mask of ITS input in the epilogue -- 3 dependent launches where the per-Linear nodes need 7
+    (refine_bwd, cast, dgrad, relu_bwd, dgrad, relu_bwd, dgrad); weight / bias gradients go to the leaf streams."""
+
+    @staticmethod
+    def forward(ctx, x, x_op, anchor, want_sine, eps, nl, *wb):
+        be = get_backend()
+        ws, bs = wb[:nl], wb[nl:]
+        xd = x.detach()
+        xo = x_op.detach() if (x_op is not None and x_op.dtype == torch.bfloat16) else _cast_op(be, xd if xd.is_contiguous() else xd.contiguous())
+        R = xo.shape[0]
+        dev = xo.device
+        acts = [xo]
+        for i in range(nl - 1):
+            hdn = torch.empty(R, ws[i].shape[0], dtype=torch.bfloat16, device=dev)
+            be.linear_fwd(acts[-1], _operand(ws[i].detach(), True), bs[i].detach(), hdn, relu=True)
+            acts.append(hdn)
+        a = anchor.detach().float().contiguous()
+        out = torch.empty(R, 4, dtype=torch.float32, device=dev)
+        sine = torch.empty(R, 512, dtype=torch.float32, device=dev) if want_sine else None
+        sine_op = torch.empty(R, 512, dtype=torch.bfloat16, device=dev) if want_sine else None
+        be.box_head_fwd(acts[-1], _operand(ws[-1].detach(), True), bs[-1].detach(), a, out, sine, sine_op, eps)
+        ctx.save_for_backward(out, a, *acts, *ws)
+        ctx.biases = bs
+        ctx.nl, ctx.eps = nl, eps
+        ctx.x_dtype = x.dtype
+        ctx.set_materialize_grads(False)
+        if want_sine:
+            ctx.mark_non_differentiable(sine, sine_op)
+        return out, sine, sine_op
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g, _s, _so):
+        nl = ctx.nl
+        if g is None:
+            return (None,) * (6 + 2 * nl)
+        be = get_backend()
+        saved = ctx.saved_tensors
+        out, a = saved[0], saved[1]
+        acts, ws = saved[2:2 + nl], saved[2 + nl:]
+        bs = ctx.biases
+        R = out.shape[0]
+        dev = out.device
+        g = g if (g.is_contiguous() and g.dtype == torch.float32) else g.contiguous().float()
+        need = ctx.needs_input_grad
+        da = torch.empty_like(out) if need[2] else None
+        dd_op = torch.empty(R, 4, dtype=torch.bfloat16, device=dev)
+        cur = torch.empty(R, ws[-1].shape[1], dtype=torch.bfloat16, device=dev)
+        be.box_head_bwd(g, out, a, _operand(ws[-1].detach(), True), acts[-1], dd_op, cur, da, ctx.eps)
+        dws, dbs = [None] * nl, [None] * nl
+        dws[-1], dbs[-1] = _wgrad(be, dd_op, acts[-1], ws[-1], bs[-1], need[6 + nl - 1], need[6 + 2 * nl - 1])
+        dx = None
+        for i in range(nl - 2, -1, -1):  # cur = gradient w.r.t. the pre-activation of hidden layer i (bf16 [R, N_i])
+            dws[i], dbs[i] = _wgrad(be, cur, acts[i], ws[i], bs[i], need[6 + i], need[6 + nl + i])
+            wo = _operand(ws[i].detach(), True)
+            if i > 0:
+                prev = torch.empty(R, ws[i].shape[1], dtype=torch.bfloat16, device=dev)
+                be.linear_bwd_data(cur, wo, prev, relu_y=acts[i])  # acts[i] = ReLU output of hidden layer i - 1: mask in the epilogue
+                cur = prev
+            elif need[0]:
+                dx = torch.empty(R, ws[0].shape[1], dtype=ctx.x_dtype, device=dev)
+                be.linear_bwd_data(cur, wo, dx)
+        return (dx, None, da, None, None, None, *dws, *dbs)
+
+
+def box_mlp_head(mlp_layers, x, x_op, anchor, want_sine: bool = True, eps: float = 1e-3):
+    """(refined anchor [R, 4], sine [R, 512] or None, its bf16 copy or None) from the query activations ``x`` [R, d]"""
+    ws = [l.weight for l in mlp_layers]
+    bs = [l.bias for l in mlp_layers]
+    return BoxMLPHeadFn.apply(x, x_op, anchor, want_sine, eps, len(ws), *ws, *bs)
+
+
+class MulOperandFn(Function):
+    """(a[:, :c] * b, its bf16 GEMM-operand copy) in one launch (query_sine = sine[..., :d] * query_scale(out),
+    query_decoder.py:196-199); ``a`` is a constant (the sine embedding of a detached anchor).  Backward: d b = g * a[:, :c]."""
+
+    @staticmethod
+    def forward(ctx, a, b, c):
+        be = get_backend()
+        bd = b.detach().float().contiguous()
+        ad = a.detach()
+        out = torch.empty(bd.shape, dtype=torch.float32, device=bd.device)
+        out_op = torch.empty(bd.shape, dtype=torch.bfloat16, device=bd.device)
+        c_op = None
+        if c is not None and c.dtype == torch.float32 and c.shape == bd.shape and c.is_contiguous():
+            c_op = torch.empty(bd.shape, dtype=torch.bfloat16, device=bd.device)
+            be.mul_cast(ad, bd, out, out_op, c.detach(), c_op)
+        else:
+            be.mul_cast(ad, bd, out, out_op)
+        ctx.save_for_backward(ad)
+        ctx.shape = bd.shape
+        ctx.mark_non_differentiable(*([out_op] if c_op is None else [out_op, c_op]))
+        ctx.set_materialize_grads(False)
+        return out, out_op, c_op
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g, _unused, _unused2):
+        if g is None:
+            return None, None, None
+        (ad,) = ctx.saved_tensors
+        g = g if g.is_contiguous() else g.contiguous()
+        db = torch.empty(ctx.shape, dtype=torch.float32, device=g.device)
+        get_backend().mul_cast_bwd(g, ad, db)
+        return None, db, None
+
+
+def mul_operand(a, b, c=None):
+    """a fp32 [R, >= k] (row-major, constant), b fp32 [R, k] -> (a[:, :k] * b fp32, its bf16 copy, bf16(c) or None): ``c``
+    (fp32 [R, k], optional) is a second tensor whose GEMM-operand copy rides in the same launch"""
+    assert not a.requires_grad
+    return MulOperandFn.apply(a, b, c)
 
 
 def sted_score(pred_sted: torch.Tensor, durations, return_map: bool = False):

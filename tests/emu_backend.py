@@ -581,3 +581,60 @@ class EmuBackend:
                 db += dp.sum(0)
         d_videos_cls.copy_(dv)
         self.launches += 3
+
+    def box_head_fwd(self, h, W, bias, anchor, out, sine, sine_op, eps=1e-3):
+        import math
+
+        _mat(h, "h"), _flat(W, "W", BF16), _flat(bias, "bias", F32), _flat(anchor, "anchor", F32), _flat(out, "out", F32)
+        _flat(sine, "sine", F32), _flat(sine_op, "sine_op", BF16)
+        assert h.dtype == BF16 and W.shape[0] == 4
+        delta = _f(h) @ _f(W).t() + bias
+        x = anchor.clamp(0, 1)
+        out.copy_(torch.sigmoid(delta + torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))))
+        if sine is not None:
+            k = torch.arange(128, dtype=torch.float32)
+            p = (out * (2 * math.pi))[..., None] / (10000 ** (2 * torch.div(k, 2, rounding_mode="floor") / 128))
+            e = torch.stack((p[..., 0::2].sin(), p[..., 1::2].cos()), dim=-1).flatten(-2)
+            sine.copy_(torch.cat((e[..., 1, :], e[..., 0, :], e[..., 2, :], e[..., 3, :]), dim=-1))
+            if sine_op is not None:
+                _store(sine_op, sine)
+        self.launches += 1
+
+    def mul_cast(self, a, b, out_f32, out_bf16, c_in=None, c_out=None):
+        _mat(a, "a"), _flat(b, "b", F32), _flat(out_f32, "out_f32", F32), _flat(out_bf16, "out", BF16)
+        v = a[:, : b.shape[1]] * b
+        if out_f32 is not None:
+            out_f32.copy_(v)
+        _store(out_bf16, v)
+        if c_out is not None:
+            _flat(c_in, "c_in", F32), _flat(c_out, "c_out", BF16)
+            assert c_in.shape == b.shape
+            _store(c_out, c_in)
+        self.launches += 1
+
+    def mul_cast_bwd(self, g, a, db):
+        _mat(a, "a"), _flat(g, "g"), _flat(db, "db", F32)
+        db.copy_(_f(g) * a[:, : db.shape[1]])
+        self.launches += 1
+
+    def box_refine_bwd(self, out, anchor, g, ddelta, danchor, eps=1e-3):
+        dz = g * out * (1 - out)
+        ddelta.copy_(dz)
+        if danchor is not None:
+            x = anchor
+            d = torch.zeros_like(x)
+            inside = (x > 0) & (x < 1)
+            d = d + torch.where(inside & (x > eps), 1.0 / x.clamp(min=1e-30), torch.zeros_like(x))
+            d = d + torch.where(inside & (1 - x > eps), 1.0 / (1 - x).clamp(min=1e-30), torch.zeros_like(x))
+            danchor.copy_(dz * d)
+        self.launches += 1
+
+    def box_head_bwd(self, g, out, anchor, W, h, dd_op, dh, danchor, eps=1e-3):
+        _mat(h, "h"), _flat(g, "g", F32), _flat(out, "out", F32), _flat(anchor, "anchor", F32), _flat(W, "W", BF16)
+        _flat(dd_op, "dd_op", BF16), _flat(dh, "dh", BF16), _flat(danchor, "danchor", F32)
+        dz = torch.empty_like(out)
+        self.box_refine_bwd(out, anchor, g, dz, danchor, eps)
+        self.launches -= 1
+        _store(dd_op, dz)
+        _store(dh, (_f(dd_op) @ _f(W)) * (_f(h) > 0))
+        self.launches += 1

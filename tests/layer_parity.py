@@ -71,10 +71,10 @@ def record_layers(records):
             mem, mem_pos = stream[0][:, 1:].reshape(-1, d), stream[1][:, 1:].reshape(-1, d)
         self._mem, self._mem_pos = cl(mem), cl(mem_pos)
 
-    def b_wrap(self, c, tgt, tgt_op, query_pos, query_time, time_op, query_sine, sine_op, is_first, mem_kv):
+    def b_wrap(self, c, tgt, tgt_op, query_pos, query_time, time_op, query_sine, sine_op, is_first, mem_kv, pos_op=None):
         ins = dict(c=c, tgt=cl(tgt), query_pos=cl(query_pos), query_time=cl(query_time), query_sine=cl(query_sine),
                    is_first=is_first)
-        out = b_run(self, c, tgt, tgt_op, query_pos, query_time, time_op, query_sine, sine_op, is_first, mem_kv)
+        out = b_run(self, c, tgt, tgt_op, query_pos, query_time, time_op, query_sine, sine_op, is_first, mem_kv, pos_op=pos_op)
         records.append(("box", self, ins, dict(y=cl(out[0]))))
         return out
 

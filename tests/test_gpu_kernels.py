@@ -520,3 +520,51 @@ def test_template_generator_kernels(be, durs):
         # fp32 accumulation of bf16 products in another order; bf16-rounded intermediates (mod, dpq) may flip one ulp (2^-8)
         tol = 1e-2 if k in ("mod", "dfc", "dv") or k.startswith(("dW", "db")) else 1e-4
         assert rel_err(got[k], ref[k]) < tol, (k, rel_err(got[k], ref[k]))
+
+
+@pytest.mark.parametrize("R", [1, 64, 201])
+def test_box_head_and_mul_cast(be, R):
+    """stcat_box_head_fwd (last bbox_embed Linear + anchor refinement + sine embedding) and stcat_mul_cast(_bwd) against the
+    plain-torch restatement; the sine embedding of an anchor that differs by fp32 summation order in the box head is compared
+    through the anchor (2 pi a / 10000^0 ... amplifies an anchor difference by at most 2 pi)."""
+    K = 256
+    bf = torch.bfloat16
+    h = g(R, 2 * K, seed=1).to(bf)[:, :K]  # a row-major view with a leading dimension
+    W, bias, anchor = g(4, K, seed=2, scale=K ** -0.5).to(bf), g(4, seed=3, scale=0.1), torch.rand(R, 4, generator=torch.Generator().manual_seed(4))
+    anchor[0, 0], anchor[-1, 3] = 0.0, 1.0  # the clamped ends of inverse_sigmoid
+    ref = [torch.empty(R, 4), torch.empty(R, 512), torch.empty(R, 512, dtype=bf)]
+    _emu().box_head_fwd(h, W, bias, anchor, *ref)
+    got = [torch.empty_like(t, device="cuda") for t in ref]
+    be.box_head_fwd(h.cuda(), W.cuda(), bias.cuda(), anchor.cuda(), *got)
+    assert rel_err(got[0], ref[0]) < 1e-5
+    assert float((got[1].cpu() - ref[1]).abs().max()) < 1e-4
+    assert float((got[2].float().cpu() - ref[2].float()).abs().max()) < 1e-2  # one bf16 ulp at |v| <= 1
+    out_only = torch.empty(R, 4, device="cuda")
+    be.box_head_fwd(h.cuda(), W.cuda(), bias.cuda(), anchor.cuda(), out_only, None, None)
+    assert torch.equal(out_only, got[0])
+    # backward: refinement gradient, bf16 operand copy, data gradient of the last Linear with the ReLU mask of h
+    hr = h.float().relu().to(bf).contiguous()
+    gg = g(R, 4, seed=9)
+    rdd, rdh, rda = torch.empty(R, 4, dtype=bf), torch.empty(R, K, dtype=bf), torch.empty(R, 4)
+    _emu().box_head_bwd(gg, ref[0], anchor, W, hr, rdd, rdh, rda)
+    gdd, gdh, gda = (torch.empty_like(t, device="cuda") for t in (rdd, rdh, rda))
+    be.box_head_bwd(gg.cuda(), ref[0].cuda(), anchor.cuda(), W.cuda(), hr.cuda(), gdd, gdh, gda)
+    assert rel_err(gdd.float(), rdd.float()) < 1e-2 and rel_err(gda, rda) < 1e-5
+    assert rel_err(gdh.float(), rdh.float()) < 1e-2  # bf16 outputs: a one-ulp flip of dd_op moves dh by 2^-8 relative
+    assert torch.equal(gdh.cpu() == 0, rdh == 0) or float(((gdh.cpu() == 0) != (rdh == 0)).float().mean()) < 1e-3
+    be.box_head_bwd(gg.cuda(), ref[0].cuda(), anchor.cuda(), W.cuda(), hr.cuda(), gdd, gdh, None)
+    a, b = g(R, 512, seed=5), g(R, 256, seed=6)
+    rf, rb = torch.empty(R, 256), torch.empty(R, 256, dtype=bf)
+    _emu().mul_cast(a, b, rf, rb)
+    gf, gb = torch.empty(R, 256, device="cuda"), torch.empty(R, 256, device="cuda", dtype=bf)
+    be.mul_cast(a.cuda(), b.cuda(), gf, gb)
+    assert torch.equal(gf.cpu(), rf) and torch.equal(gb.cpu(), rb)
+    c_in, c_out = g(R, 256, seed=8), torch.empty(R, 256, device="cuda", dtype=bf)
+    be.mul_cast(a.cuda(), b.cuda(), None, gb, c_in.cuda(), c_out)  # fp32 product optional; second operand copy in the same launch
+    assert torch.equal(gb.cpu(), rb) and torch.equal(c_out.cpu(), c_in.to(bf))
+    for gdt in (torch.float32, bf):
+        gr = g(R, 256, seed=7).to(gdt)
+        rd, gd = torch.empty(R, 256), torch.empty(R, 256, device="cuda")
+        _emu().mul_cast_bwd(gr, a, rd)
+        be.mul_cast_bwd(gr.cuda(), a.cuda(), gd)
+        assert torch.equal(gd.cpu(), rd)
