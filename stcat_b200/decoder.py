@@ -545,6 +545,7 @@ class QueryDecoder(nn.Module):
             # this package's encoder handed over its frame-major stream: the three memory-side GEMM operands and the frame-CLS
             # rows in one launch, the template generator in two (csrc/assembly.cu); one / three launches in the backward pass
             operands = ops.mem_operands(enc_stream[0], enc_stream[1])
+            memory_cache["_stream_used"] = True  # dp.GradSync.attach: the gradient boundary is the stream, not its views
             frames_cls = operands[3]
             operands = operands[:3]
             mem = mem_pos = None

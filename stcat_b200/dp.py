@@ -190,7 +190,11 @@ class GradSync:
         if not self.active:
             return
         mc = out["_memory_cache"]
-        boundary = [t for t in (mc["encoded_memory"], mc["frames_cls"], mc["videos_cls"]) if t.requires_grad]
+        if mc.get("_stream_used"):
+            # the decoder read the encoder's frame-major stream itself (ops.mem_operands): the views below receive no gradient
+            boundary = [t for t in (mc["_stream"][0], mc["videos_cls"]) if t.requires_grad]
+        else:
+            boundary = [t for t in (mc["encoded_memory"], mc["frames_cls"], mc["videos_cls"]) if t.requires_grad]
         state = {"seen": 0, "need": len(boundary)}
 
         def hook(g):

@@ -27,7 +27,7 @@ def _free_port():
     return p
 
 
-def _clip_grads(rank_seed, fused_flat, overlapped=False):
+def _clip_grads(rank_seed, fused_flat, overlapped=False, precision="fp32"):
     from helpers import cfg_for
     from emu_backend import EmuBackend
     from stcat_b200 import ops, synthetic
@@ -38,7 +38,8 @@ def _clip_grads(rank_seed, fused_flat, overlapped=False):
     from stcat_b200.pipeline import STCATHotPath
 
     ops.set_backend(EmuBackend())
-    ops.set_precision("fp32")
+    ops.set_precision(precision)
+    ops.clear_weight_cache()
     cfg = cfg_for({"max_video_len": 16})
     model = STCATHotPath(cfg).load_flat_params(synthetic_params(cfg, seed=0)).eval()  # same weights on every rank
     T = 5
@@ -67,6 +68,7 @@ def _clip_grads(rank_seed, fused_flat, overlapped=False):
             assert "decoder" in order and "enc0" in order, order  # the hooks fired (not just finish())
     finally:
         ops.set_grad_fusion(False)
+        ops.set_precision("fp32")
     return model, grads, float(total.detach())
 
 
@@ -91,6 +93,15 @@ def _worker(rank, world, port, outdir):
         # GradSync averages over the ranks (what the DistributedDataParallel wrapper it replaces does); (a) summed
         assert torch.allclose(grads.buf * world, grads_a.buf, rtol=1e-6, atol=1e-7)
         assert set(grads.ranges) >= {"decoder", "enc0", "enc5", "rest"}
+        # (c) bf16 operand mode: fused layout glue (the decoder reads the encoder stream itself) + gradient sink: the decoder
+        # range is still reduced from a hook during backward (asserted inside), and the result is the mean of the local sums
+        _, grads_c0, loss_c0 = _clip_grads(42 + rank, fused_flat=True, precision="bf16")
+        local_c = grads_c0.buf.clone()
+        gathered_c = [torch.zeros_like(local_c) for _ in range(world)]
+        dist.all_gather(gathered_c, local_c)
+        _, grads_c, loss_c = _clip_grads(42 + rank, fused_flat=True, overlapped=True, precision="bf16")
+        assert loss_c == loss_c0
+        assert torch.allclose(grads_c.buf * world, sum(gathered_c), rtol=1e-5, atol=1e-6)
         # every .grad is still a view of the reduced buffer
         for p in grads.params:
             assert p.grad.untyped_storage().data_ptr() == grads.buf.untyped_storage().data_ptr()
