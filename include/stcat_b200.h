@@ -294,6 +294,19 @@ STCAT_API int stcat_mem_operands_bwd(const void* g_mem, int g_mem_dtype, const v
                                      float* dX, int n, int S, int d, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Frame-CLS exchange between a spatial and a temporal encoder layer (modal_encoder.py:170-195), one un-padded video:
+ *   cls_gather  : Y[1 + n, d] = [video ; X[:, r, :]] from the stream X [n, S, d] and the video token [1, d]; qk_op / y_op (bf16
+ *                 [1 + n, d], may be NULL) = bf16(Y + pos), bf16(Y): the temporal layer's q/k and v operands (pos [1 + n, d]).
+ *   cls_scatter : X[:, r, :] = Y[1:] in place; X_op (bf16 [n, S, d], may be NULL) receives the same rows; qk_next (bf16 [n, S, d],
+ *                 may be NULL) receives bf16(Y[1:] + pos[:, r, :]) (pos fp32 [n, S, d]): the rows of the next spatial layer's q/k
+ *                 operand, when that operand was projected early from the stream as it was before the temporal layer.
+ * ---------------------------------------------------------------------------------------------- */
+STCAT_API int stcat_cls_gather(const float* X, const float* video, const float* pos, float* Y, void* qk_op, void* y_op, int n, int S, int r,
+                               int d, void* stream);
+STCAT_API int stcat_cls_scatter(const float* Y, float* X, void* X_op, void* qk_next, const float* pos, int n, int S, int r, int d,
+                                void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * TemplateGenerator (query_decoder.py:441-475) as two small launches forward and three backward (the reference issues
  * 4 Linears + 2 tanh + mul + add + sigmoid, ~14 kernels forward and ~20 backward, on the decoder's dependent chain).
  * Weights W* are bf16 [d, d] (Wa: [q, d], q <= 8), biases fp32; GEMM operands (the video token, mod, the incoming

@@ -90,6 +90,8 @@ SIGNATURES["stcat_box_head_fwd"] = (c_int, [_P, _L, _P, _P, _P, _P, _P, _P, _I, 
 SIGNATURES["stcat_box_head_bwd"] = (c_int, [_P, _P, _P, _P, _P, _L, _P, _P, _P, _I, _I, _F, _P])
 SIGNATURES["stcat_mul_cast"] = (c_int, [_P, _L, _P, _P, _P, _P, _P, _L, _I, _P])
 SIGNATURES["stcat_mul_cast_bwd"] = (c_int, [_P, _I, _P, _L, _P, _L, _I, _P])
+SIGNATURES["stcat_cls_gather"] = (c_int, [_P] * 6 + [_I] * 4 + [_P])
+SIGNATURES["stcat_cls_scatter"] = (c_int, [_P] * 5 + [_I] * 4 + [_P])
 MAX_GROUP_JOBS = 12
 ABI_VERSION = 11  # include/stcat_b200.h STCAT_ABI_VERSION
 
@@ -601,4 +603,21 @@ class CudaBackend:
         self._rc(self.lib.stcat_box_head_bwd(self._flat(g, "g", f), self._flat(out, "out", f), self._flat(anchor, "anchor", f),
                                              self._flat(W, "W", bf), hp, ldh, self._flat(dd_op, "dd_op", bf), self._flat(dh, "dh", bf),
                                              self._flat(danchor, "danchor", f), R, K, float(eps), self._stream()), "box_head_bwd")
+        self.launches += 1
+
+    def cls_gather(self, X, video, pos, Y, qk_op, y_op, r):
+        """X fp32 [n, S, d], video fp32 [1, d], pos fp32 [1 + n, d] or None -> Y fp32 [1 + n, d] (+ bf16 operands or None)"""
+        f, bf = torch.float32, torch.bfloat16
+        n, S, d = X.shape
+        self._rc(self.lib.stcat_cls_gather(self._flat(X, "X", f), self._flat(video, "video", f), self._flat(pos, "pos", f),
+                                           self._flat(Y, "Y", f), self._flat(qk_op, "qk_op", bf), self._flat(y_op, "y_op", bf), n, S,
+                                           int(r), d, self._stream()), "cls_gather")
+        self.launches += 1
+
+    def cls_scatter(self, Y, X, X_op, r, qk_next=None, pos=None):
+        f, bf = torch.float32, torch.bfloat16
+        n, S, d = X.shape
+        self._rc(self.lib.stcat_cls_scatter(self._flat(Y, "Y", f), self._flat(X, "X", f), self._flat(X_op, "X_op", bf),
+                                            self._flat(qk_next, "qk_next", bf), self._flat(pos, "pos", f), n, S, int(r), d,
+                                            self._stream()), "cls_scatter")
         self.launches += 1

@@ -250,6 +250,46 @@ mem_operands_bwd_kernel(const void* __restrict__ g_mem, int dt_mem, const void* 
     }
 }
 
+// ---- frame-CLS exchange with the temporal encoder layer (modal_encoder.py:170-195) ------------------------------------------
+// gather : Y = [video ; X[:, r, :]] ([1 + n, d]) with the temporal layer's two GEMM operands bf16(Y + pos), bf16(Y) in one launch
+// scatter: X[:, r, :] = Y[1:] in place, and the same rows of the stream's bf16 operand copy
+__global__ void __launch_bounds__(256)
+cls_gather_kernel(const float* __restrict__ X, const float* __restrict__ video, const float* __restrict__ pos, float* __restrict__ Y,
+                  __nv_bfloat16* __restrict__ qk_op, __nv_bfloat16* __restrict__ y_op, int n, int S, int r, int d4) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t total = (int64_t)(1 + n) * d4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = i / d4, c4 = i - j * d4;
+        const float4 v = j == 0 ? reinterpret_cast<const float4*>(video)[c4]
+                                : reinterpret_cast<const float4*>(X)[((j - 1) * S + r) * d4 + c4];
+        reinterpret_cast<float4*>(Y)[i] = v;
+        if (qk_op) {
+            const float4 p = reinterpret_cast<const float4*>(pos)[i];
+            reinterpret_cast<uint2*>(qk_op)[i] = pack4(v.x + p.x, v.y + p.y, v.z + p.z, v.w + p.w);
+        }
+        if (y_op) reinterpret_cast<uint2*>(y_op)[i] = pack4(v.x, v.y, v.z, v.w);
+    }
+}
+__global__ void __launch_bounds__(256)
+cls_scatter_kernel(const float* __restrict__ Y, float* __restrict__ X, __nv_bfloat16* __restrict__ X_op,
+                   __nv_bfloat16* __restrict__ qk_next, const float* __restrict__ pos, int n, int S, int r, int d4) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t total = (int64_t)n * d4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f = i / d4, c4 = i - f * d4;
+        const float4 v = reinterpret_cast<const float4*>(Y)[(1 + f) * d4 + c4];
+        const int64_t dst = (f * S + r) * d4 + c4;
+        reinterpret_cast<float4*>(X)[dst] = v;
+        if (X_op) reinterpret_cast<uint2*>(X_op)[dst] = pack4(v.x, v.y, v.z, v.w);
+        if (qk_next) {  // the next spatial layer's q/k operand bf16(X + POS) was written early from the stale rows: patch them
+            const float4 p = reinterpret_cast<const float4*>(pos)[dst];
+            reinterpret_cast<uint2*>(qk_next)[dst] = pack4(v.x + p.x, v.y + p.y, v.z + p.z, v.w + p.w);
+        }
+    }
+}
+
 // ---- template generator (query_decoder.py:441-475) ---------------------------------------------------------------------------
 // film:   for the b video tokens: content = Wc v + bc, gamma = tanh(Wg v + bg), beta = tanh(Wb v + bb); v rounded to bf16 like
 //         every GEMM operand, bf16 weights, fp32 accumulation.  One warp per output element.
@@ -817,6 +857,30 @@ STCAT_API int stcat_box_head_bwd(const float* g, const float* out, const float* 
                                (const __nv_bfloat16*)W, (const __nv_bfloat16*)h, ldh, (__nv_bfloat16*)dd_op, (__nv_bfloat16*)dh, danchor, R, K, eps);
     if (e != cudaSuccess) return set_err((int)e, "box_head_bwd: %s", cudaGetErrorString(e));
     return check_launch("box_head_bwd");
+}
+
+STCAT_API int stcat_cls_gather(const float* X, const float* video, const float* pos, float* Y, void* qk_op, void* y_op, int n, int S, int r,
+                               int d, void* stream) {
+    STCAT_REQUIRE(X && video && Y, STCAT_EINVAL, "cls_gather: null pointer");
+    STCAT_REQUIRE(pos || !qk_op, STCAT_EINVAL, "cls_gather: qk_op needs pos");
+    STCAT_REQUIRE(n > 0 && S > 0 && r >= 0 && r < S && d > 0 && d % 4 == 0, STCAT_ESHAPE, "cls_gather: bad shape n=%d S=%d r=%d d=%d", n, S, r, d);
+    const int64_t items = (int64_t)(1 + n) * (d / 4);
+    cudaError_t e = launch_pdl(cls_gather_kernel, dim3(grid_cap((items + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, X, video, pos, Y,
+                               (__nv_bfloat16*)qk_op, (__nv_bfloat16*)y_op, n, S, r, d / 4);
+    if (e != cudaSuccess) return set_err((int)e, "cls_gather: %s", cudaGetErrorString(e));
+    return check_launch("cls_gather");
+}
+
+STCAT_API int stcat_cls_scatter(const float* Y, float* X, void* X_op, void* qk_next, const float* pos, int n, int S, int r, int d,
+                                void* stream) {
+    STCAT_REQUIRE(Y && X, STCAT_EINVAL, "cls_scatter: null pointer");
+    STCAT_REQUIRE(pos || !qk_next, STCAT_EINVAL, "cls_scatter: qk_next needs pos");
+    STCAT_REQUIRE(n > 0 && S > 0 && r >= 0 && r < S && d > 0 && d % 4 == 0, STCAT_ESHAPE, "cls_scatter: bad shape n=%d S=%d r=%d d=%d", n, S, r, d);
+    const int64_t items = (int64_t)n * (d / 4);
+    cudaError_t e = launch_pdl(cls_scatter_kernel, dim3(grid_cap((items + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, Y, X,
+                               (__nv_bfloat16*)X_op, (__nv_bfloat16*)qk_next, pos, n, S, r, d / 4);
+    if (e != cudaSuccess) return set_err((int)e, "cls_scatter: %s", cudaGetErrorString(e));
+    return check_launch("cls_scatter");
 }
 
 }  // extern "C"

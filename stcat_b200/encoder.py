@@ -38,6 +38,8 @@ _index_cache = {}
 # fused layout glue (ops.token_assembly / mem_operands / template: csrc/assembly.cu) in bf16 mode; STCAT_FUSED_GLUE=0 keeps the
 # torch.cat / slice composition (the only path in exact-fp32 mode)
 _FUSED_GLUE = os.environ.get("STCAT_FUSED_GLUE", "1") != "0"
+_EARLY_QKV = os.environ.get("STCAT_EARLY_QKV", "1") != "0"  # ops.qkv_early: next layer's in-projection under the temporal layer
+_CLS_KERNELS = os.environ.get("STCAT_CLS_KERNELS", "1") != "0"  # ops.cls_gather / cls_scatter with fused operand copies (A/B switch)
 
 
 def set_fused_glue(on: bool):
@@ -104,14 +106,14 @@ class TransformerEncoderLayer(nn.Module):
         self.nhead = nhead
         self.dropout_p = dropout
 
-    def run(self, x, x_op, pos, key_mask, B: int, L: int, pos_cls=None, qk_op=None):
+    def run(self, x, x_op, pos, key_mask, B: int, L: int, pos_cls=None, qk_op=None, pre=None):
         """x, pos: [B*L, d] batch-major rows.  Returns (y, y_op).  In train mode the four dropout sites of the reference
         layer (attention probabilities, dropout1, the FFN's inner dropout, dropout2; modal_encoder.py:212-241) are active."""
         a = self.self_attn
         p = self.dropout_p if self.training else 0.0
         x, x_op = ops.self_attn_block(x, x_op, pos, key_mask, a.in_proj_weight, a.in_proj_bias, a.out_proj.weight,
                                       a.out_proj.bias, self.norm1.weight, self.norm1.bias, B, L, self.nhead,
-                                      self.norm1.eps, pos_cls=pos_cls, drop_p=p, qk_op=qk_op)
+                                      self.norm1.eps, pos_cls=pos_cls, drop_p=p, qk_op=qk_op, pre=pre)
         return ops.ffn_block(x, x_op, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias,
                              self.norm2.weight, self.norm2.bias, self.norm2.eps, drop_p=p)
 
@@ -149,19 +151,29 @@ class SpatialTemporalEncoder(nn.Module):
         temp_pos = temp_pos if b == 1 else temp_pos.repeat(b, 1)
         temp_pos = temp_pos.contiguous()
         qk_op, X_op = first_ops if first_ops is not None else (None, None)
+        pre = None
         # optional observer of every block's input (dp.GradSync hangs its bucketed all-reduce on their gradients);
         # nothing is stored here: holding these tensors would keep the step's autograd graph alive
         on_input = getattr(self, "layer_input_callback", None)
         for li, (sp, tp) in enumerate(zip(self.spatial_layers, self.temporal_layers)):
             if on_input is not None:
                 on_input(li, X)
-            X, X_op = sp.run(X, X_op, POS, key_mask, n, S_len, pos_cls=pos_cls, qk_op=qk_op if li == 0 else None)
+            X, X_op = sp.run(X, X_op, POS, key_mask, n, S_len, pos_cls=pos_cls, qk_op=qk_op if li == 0 else None, pre=pre)
+            pre = None
             if idx["identity"]:
                 # one un-padded video: the frame-CLS exchange with the temporal layer as two row-sized nodes
-                X3, Y = ops.cls_gather(X.view(n, S_len, d), video_src, 0)  # Y = [video token ; frame-CLS rows]
-                Y, _ = tp.run(Y, None, temp_pos, idx["temp_mask"], b, t + 1)
-                X3, video_src = ops.cls_scatter(X3, Y, 0)  # the reference's in-place row replacement (modal_encoder.py:191-195)
-                cls_new = Y.detach()[1:]
+                # Y = [video token ; frame-CLS rows]; in bf16 mode the same launch writes the temporal layer's GEMM operands and
+                # the scatter refreshes the CLS rows of the stream's operand copy (3 launches fewer per block on the chain)
+                fuse = _CLS_KERNELS and fused_glue()
+                if (fuse and _EARLY_QKV and X_op is not None and pos_cls is not None and li + 1 < self.num_layers
+                        and POS.dtype == torch.float32):
+                    # the next spatial layer's q/k/v projection of every row the temporal layer does not touch, on a side stream
+                    nxt = self.spatial_layers[li + 1].self_attn
+                    pre = ops.qkv_early(X, X_op, POS, nxt.in_proj_weight, nxt.in_proj_bias)
+                X3, Y, tq_op, ty_op = ops.cls_gather(X.view(n, S_len, d), video_src, 0, pos=temp_pos if fuse else None)
+                Y, _ = tp.run(Y, ty_op, temp_pos, idx["temp_mask"], b, t + 1, qk_op=tq_op)
+                X3, video_src = ops.cls_scatter(X3, Y, 0, x_op=X_op if fuse else None, pre=pre, pos=POS)  # modal_encoder.py:191-195
+                cls_new = None if (fuse and X_op is not None) else Y.detach()[1:]
             else:
                 X3, cls = ops.take_rows(X.view(n, S_len, d), 0)  # frame-CLS rows (copy) + the stream itself
                 Y = torch.cat([video_src, cls, cls.new_zeros(1, d)], 0).index_select(0, idx["enc_gather"])
@@ -170,7 +182,7 @@ class SpatialTemporalEncoder(nn.Module):
                 cls_new = Y.index_select(0, idx["enc_scatter"])
                 X3 = ops.put_rows(X3, cls_new, 0)  # modal_encoder.py:191-195
             X = X3.view(n * S_len, d)
-            if X_op is not None:
+            if X_op is not None and cls_new is not None:
                 X_op.view(n, S_len, d)[:, 0, :] = cls_new.detach()
         return X, video_src
 

@@ -947,7 +947,8 @@ class SelfAttnBlockFn(Function):
     """
 
     @staticmethod
-    def forward(ctx, x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps, pos_cls=None, drop_p=0.0, qk_op=None):
+    def forward(ctx, x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps, pos_cls=None, drop_p=0.0, qk_op=None,
+                pre=None):
         be = get_backend()
         ctx.has_pos_cls = pos_cls is not None
         # train-mode dropout (modal_encoder.py:212,237): on the attention probabilities and on the block output before
@@ -966,7 +967,15 @@ class SelfAttnBlockFn(Function):
         bits = side = None
         if ctx.drop_attn:  # forked first: the (ALU-bound) generator runs under the HBM-bound add and the projection GEMMs
             bits, side = _attn_keep_bits(be, B, H, L, ctx.drop_attn, xd)
-        if bf:
+        use_pre = bf and pre is not None and x_op is not None and x_op.dtype == od
+        if use_pre:
+            # q/k/v of every row but row 0 of each sequence were projected EARLY (qkv_early: on a side stream, under the temporal
+            # layer that only rewrites those rows); cls_scatter has patched row 0 of qk_in and of x_op: project those B rows now
+            qk_in, qkv_pre = pre["qk_in"], pre["qkv"]
+            xo = x_op.detach()
+            if pre["done"] is not None:
+                torch.cuda.current_stream().wait_event(pre["done"])
+        elif bf:
             if qk_op is not None and qk_op.dtype == od:  # the producer of x already wrote bf16(x + pos) (ops.token_assembly)
                 qk_in = qk_op.detach().view(R, d)
             else:
@@ -980,10 +989,16 @@ class SelfAttnBlockFn(Function):
         wi = _operand(w_in.detach(), True)
         wo = _operand(w_out.detach(), True)
         bi = b_in.detach()
-        qkv = _new(R, 3 * d, od, x)
-        # q, k from x + pos (one N = 512 GEMM) and v from x: two jobs of one grouped launch
-        be.linear_group(0, [dict(terms=[(qk_in, wi[: 2 * d], bi[: 2 * d])], out=qkv[:, : 2 * d]),
-                            dict(terms=[(xo, wi[2 * d:], bi[2 * d:])], out=qkv[:, 2 * d:])])
+        if use_pre:
+            qkv = qkv_pre
+            q3, x3, o3 = qk_in.view(B, L, d)[:, 0, :], xo.view(B, L, d)[:, 0, :], qkv.view(B, L, 3 * d)[:, 0, :]
+            be.linear_group(0, [dict(terms=[(q3, wi[: 2 * d], bi[: 2 * d])], out=o3[:, : 2 * d]),
+                                dict(terms=[(x3, wi[2 * d:], bi[2 * d:])], out=o3[:, 2 * d:])])
+        else:
+            qkv = _new(R, 3 * d, od, x)
+            # q, k from x + pos (one N = 512 GEMM) and v from x: two jobs of one grouped launch
+            be.linear_group(0, [dict(terms=[(qk_in, wi[: 2 * d], bi[: 2 * d])], out=qkv[:, : 2 * d]),
+                                dict(terms=[(xo, wi[2 * d:], bi[2 * d:])], out=qkv[:, 2 * d:])])
         o = _new(R, d, od, x)
         lse = torch.empty(B, H, L, dtype=torch.float32, device=x.device)
         scale = float(d // H) ** -0.5
@@ -1021,7 +1036,7 @@ class SelfAttnBlockFn(Function):
     @once_differentiable
     def backward(ctx, dy, _unused):
         if dy is None:
-            return (None,) * 17
+            return (None,) * 18
         be = get_backend()
         xd, xo, qk_in, qkv, o, lse, a, mean, rstd, key_mask, w_in, w_out, gamma = ctx.saved_tensors
         B, L, H, scale = ctx.dims
@@ -1093,7 +1108,7 @@ class SelfAttnBlockFn(Function):
                 else:
                     dpc = torch.empty(1, d, dtype=f32, device=dy.device)
                     be.linear_bwd_data(srow, w_in.detach()[: 2 * d], dpc)
-        return dz, None, dpos, None, dwi, dbi, dwo, dbo, dg, dbt, None, None, None, None, dpc, None, None
+        return dz, None, dpos, None, dwi, dbi, dwo, dbo, dg, dbt, None, None, None, None, dpc, None, None, None
 
 
 class OutLNFn(Function):
@@ -1272,12 +1287,58 @@ class FFNBlockFn(Function):
 
 
 def self_attn_block(x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps=1e-5, pos_cls=None, drop_p=0.0,
-                    qk_op=None):
+                    qk_op=None, pre=None):
     """``pos_cls`` ([1, d], optional): the parameter that row 0 of every sequence of ``pos`` was copied from; when
     given, ``pos`` itself is treated as a constant and the gradient goes to ``pos_cls`` directly.  ``qk_op`` (optional): the
     bf16 operand copy of ``x + pos`` when the producer of ``x`` already wrote it."""
     return SelfAttnBlockFn.apply(x, x_op, pos, key_mask, w_in, b_in, w_out, b_out, gamma, beta, B, L, H, eps, pos_cls, float(drop_p),
-                                 qk_op)
+                                 qk_op, pre)
+
+
+_early_streams = {}
+
+
+@torch.no_grad()
+def qkv_early(x, x_op, pos, w_in, b_in):
+    """The packed q/k/v in-projection of a spatial encoder layer, issued on a side stream BEFORE the temporal layer in front of
+    it has run (bf16 mode; x [R, d] fp32, x_op its bf16 copy, pos [R, d]).  The temporal layer only rewrites row 0 of every
+    sequence (the frame-CLS rows, modal_encoder.py:191-195), so every other row of bf16(x + pos) and of q/k/v is final; the
+    caller hands ``pre["qk_in"]`` to ``cls_scatter`` (which patches its CLS rows after ``pre["added"]``) and ``pre`` to
+    ``self_attn_block``, which projects the B patched rows and waits for ``pre["done"]``: the 20 us add + GEMM of every layer
+    hide under the latency-bound temporal chain.  Not an autograd node: the block function saves these tensors itself."""
+    be = get_backend()
+    R, d = x.shape
+    xd, xo, posd = x.detach(), x_op.detach(), pos.detach()
+    cuda = xd.is_cuda
+    if cuda:
+        cur = torch.cuda.current_stream()
+        side = _early_streams.get(xd.device)
+        if side is None:
+            side = _early_streams[xd.device] = torch.cuda.Stream(xd.device)
+        side.wait_stream(cur)
+        ctxm = torch.cuda.stream(side)
+    else:
+        import contextlib
+
+        ctxm = contextlib.nullcontext()
+    added = done = None
+    with ctxm:
+        qk_in = torch.empty(R, d, dtype=torch.bfloat16, device=xd.device)
+        be.add(xd, posd, None, qk_in)
+        if cuda:
+            added = side.record_event()
+        wi, bi = _operand(w_in.detach(), True), b_in.detach()
+        qkv = torch.empty(R, 3 * d, dtype=torch.bfloat16, device=xd.device)
+        be.linear_group(0, [dict(terms=[(qk_in, wi[: 2 * d], bi[: 2 * d])], out=qkv[:, : 2 * d]),
+                            dict(terms=[(xo, wi[2 * d:], bi[2 * d:])], out=qkv[:, 2 * d:])])
+        if cuda:
+            done = side.record_event()
+    if cuda:
+        for t in (qk_in, qkv):
+            t.record_stream(cur)
+        for t in (xd, xo, posd):
+            t.record_stream(side)
+    return {"qk_in": qk_in, "qkv": qkv, "added": added, "done": done}
 
 
 def ffn_block(x, x_op, w1, b1, w2, b2, gamma, beta, eps=1e-5, drop_p=0.0):
@@ -1331,39 +1392,61 @@ class PutRowsFn(Function):
 
 class ClsGatherFn(Function):
     """(x alias, Y) with Y = [video ; x[:, r, :]]: ``take_rows`` + ``torch.cat`` of the temporal layer's input for ONE
-    un-padded video (x [n, S, d], video [1, d] -> Y [1 + n, d]; modal_encoder.py:170-177).  Backward: the row gradient is
-    added onto the stream's gradient in place (row-sized), the video token's gradient is a view."""
+    un-padded video (x [n, S, d], video [1, d] -> Y [1 + n, d]; modal_encoder.py:170-177).  With ``pos`` ([1 + n, d], bf16 mode)
+    one kernel also writes the temporal layer's two GEMM operands bf16(Y + pos) and bf16(Y) (returned as constants).
+    Backward: the row gradient is added onto the stream's gradient in place (row-sized), the video token's gradient is a view."""
 
     @staticmethod
-    def forward(ctx, x, video, r: int):
+    def forward(ctx, x, video, r: int, pos=None):
         ctx.r = r
         ctx.set_materialize_grads(False)
         xd = x.detach()
-        return xd, torch.cat([video.detach(), xd[:, r, :]], 0)
+        if pos is not None and _precision == "bf16" and xd.is_contiguous() and xd.dtype == torch.float32:
+            n, S, d = xd.shape
+            Y = torch.empty(1 + n, d, dtype=torch.float32, device=xd.device)
+            qk_op = torch.empty(1 + n, d, dtype=torch.bfloat16, device=xd.device)
+            y_op = torch.empty(1 + n, d, dtype=torch.bfloat16, device=xd.device)
+            get_backend().cls_gather(xd, video.detach().float().contiguous(), pos.detach().contiguous(), Y, qk_op, y_op, r)
+            ctx.mark_non_differentiable(qk_op, y_op)
+            return xd, Y, qk_op, y_op
+        return xd, torch.cat([video.detach(), xd[:, r, :]], 0), None, None
 
     @staticmethod
-    def backward(ctx, g_base, g_y):
+    def backward(ctx, g_base, g_y, *_unused):
         if g_base is None:
             if g_y is None:
-                return None, None, None
+                return None, None, None, None
             raise RuntimeError("ClsGatherFn: the base output must be used (it carries the sequence's gradient)")
         if g_y is None:
-            return g_base, None, None
+            return g_base, None, None, None
         g_base = g_base if g_base.is_contiguous() else g_base.contiguous()
         g_base[:, ctx.r, :] += g_y[1:]  # g_base is ours: produced for this node alone by ClsScatterFn / the next block
-        return g_base, g_y[:1], None
+        return g_base, g_y[:1], None, None
 
 
 class ClsScatterFn(Function):
     """x[:, r, :] = Y[1:] in place on x's storage, video' = Y[:1] (``put_rows`` + the two slices of the temporal layer's
-    output, modal_encoder.py:191-195).  Backward: one concatenation builds dY, the replaced rows of dx are zeroed in place."""
+    output, modal_encoder.py:191-195); with ``x_op`` (the stream's bf16 operand copy, bf16 mode) the same kernel refreshes
+    its rows too.  Backward: one concatenation builds dY, the replaced rows of dx are zeroed in place."""
 
     @staticmethod
-    def forward(ctx, x, y, r: int):
+    def forward(ctx, x, y, r: int, x_op=None, pre=None, pos=None):
         ctx.r = r
         ctx.set_materialize_grads(False)
         out, yd = x.detach(), y.detach()
-        out[:, r, :] = yd[1:]
+        if x_op is not None and _precision == "bf16" and out.is_contiguous() and yd.is_contiguous() and x_op.is_contiguous():
+            qk_next = None
+            if pre is not None:  # ops.qkv_early: its bf16(x + pos) holds the stale rows r; patch them once its add has run
+                qk_next = pre["qk_in"].view(out.shape)
+                if pre["added"] is not None:
+                    torch.cuda.current_stream().wait_event(pre["added"])
+            get_backend().cls_scatter(yd, out, x_op.detach().view(out.shape), r, qk_next,
+                                      None if qk_next is None else pos.detach().view(out.shape))
+        else:
+            assert pre is None
+            out[:, r, :] = yd[1:]
+            if x_op is not None:
+                x_op.detach().view(out.shape)[:, r, :] = yd[1:]
         return out, yd[:1]
 
     @staticmethod
@@ -1374,15 +1457,18 @@ class ClsScatterFn(Function):
         gv = g_video if g_video is not None else g.new_zeros(1, g.shape[2])
         g_y = torch.cat([gv, g[:, ctx.r, :]], 0)
         g[:, ctx.r, :] = 0  # g is the gradient tensor produced for this node by the next block's backward: ours to edit
-        return g, g_y, None
+        return g, g_y, None, None, None, None
 
 
-def cls_gather(x, video, r: int = 0):
-    return ClsGatherFn.apply(x, video, r)
+def cls_gather(x, video, r: int = 0, pos=None):
+    """(x alias, Y, bf16(Y + pos) or None, bf16(Y) or None)"""
+    return ClsGatherFn.apply(x, video, r, pos)
 
 
-def cls_scatter(x, y, r: int = 0):
-    return ClsScatterFn.apply(x, y, r)
+def cls_scatter(x, y, r: int = 0, x_op=None, pre=None, pos=None):
+    """(x with rows r replaced by Y[1:], Y[:1]); ``x_op``: the bf16 operand copy of x, refreshed in the same launch; ``pre`` /
+    ``pos``: the next layer's early projection (ops.qkv_early), whose bf16(x + pos) rows r are patched in the same launch"""
+    return ClsScatterFn.apply(x, y, r, x_op, pre, pos)
 
 
 def take_rows(x, r: int = 0):

@@ -638,3 +638,22 @@ class EmuBackend:
         _store(dd_op, dz)
         _store(dh, (_f(dd_op) @ _f(W)) * (_f(h) > 0))
         self.launches += 1
+
+    def cls_gather(self, X, video, pos, Y, qk_op, y_op, r):
+        _flat(X, "X", F32), _flat(video, "video", F32), _flat(pos, "pos", F32), _flat(Y, "Y", F32)
+        _flat(qk_op, "qk_op", BF16), _flat(y_op, "y_op", BF16)
+        Y.copy_(torch.cat([video, X[:, r, :]], 0))
+        if qk_op is not None:
+            _store(qk_op, Y + pos)
+        if y_op is not None:
+            _store(y_op, Y)
+        self.launches += 1
+
+    def cls_scatter(self, Y, X, X_op, r, qk_next=None, pos=None):
+        _flat(Y, "Y", F32), _flat(X, "X", F32), _flat(X_op, "X_op", BF16), _flat(qk_next, "qk_next", BF16), _flat(pos, "pos", F32)
+        X[:, r, :] = Y[1:]
+        if X_op is not None:
+            X_op[:, r, :] = Y[1:].to(BF16)
+        if qk_next is not None:
+            qk_next[:, r, :] = (Y[1:] + pos[:, r, :]).to(BF16)
+        self.launches += 1

@@ -58,9 +58,9 @@ def record_layers(records):
     td_run = dec.TimeDecoder.run
     cl = lambda t: None if t is None else t.detach().clone()
 
-    def e_wrap(self, x, x_op, pos, key_mask, B, L, pos_cls=None, qk_op=None):
+    def e_wrap(self, x, x_op, pos, key_mask, B, L, pos_cls=None, qk_op=None, pre=None):
         x_in = cl(x)  # the stream is edited in place afterwards (frame-CLS row exchange): keep copies
-        out = e_run(self, x, x_op, pos, key_mask, B, L, pos_cls=pos_cls, qk_op=qk_op)
+        out = e_run(self, x, x_op, pos, key_mask, B, L, pos_cls=pos_cls, qk_op=qk_op, pre=pre)
         records.append(("enc", self, dict(x=x_in, pos=cl(pos), key_mask=key_mask, B=B, L=L), dict(y=cl(out[0]))))
         return out
 

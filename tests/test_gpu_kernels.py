@@ -568,3 +568,24 @@ def test_box_head_and_mul_cast(be, R):
         _emu().mul_cast_bwd(gr, a, rd)
         be.mul_cast_bwd(gr.cuda(), a.cuda(), gd)
         assert torch.equal(gd.cpu(), rd)
+
+
+@pytest.mark.parametrize("n,S", [(5, 7), (64, 213)])
+def test_cls_gather_scatter_kernels(be, n, S):
+    d = 256
+    bf = torch.bfloat16
+    X, video, pos = g(n, S, d, seed=1), g(1, d, seed=2), g(1 + n, d, seed=3)
+    ref = [torch.empty(1 + n, d), torch.empty(1 + n, d, dtype=bf), torch.empty(1 + n, d, dtype=bf)]
+    _emu().cls_gather(X, video, pos, *ref, 0)
+    got = [torch.empty_like(t, device="cuda") for t in ref]
+    be.cls_gather(X.cuda(), video.cuda(), pos.cuda(), *got, 0)
+    for a, r in zip(got, ref):
+        assert torch.equal(a.cpu(), r)
+    Y, P = g(1 + n, d, seed=4), g(n, S, d, seed=5)
+    Xr, Xo, Qn = X.clone(), X.to(bf), g(n, S, d, seed=6).to(bf)
+    Xd, Xod, Qnd = Xr.cuda(), Xo.cuda(), Qn.cuda()
+    _emu().cls_scatter(Y, Xr, Xo, 0, Qn, P)
+    be.cls_scatter(Y.cuda(), Xd, Xod, 0, Qnd, P.cuda())
+    assert torch.equal(Xd.cpu(), Xr) and torch.equal(Xod.cpu(), Xo) and torch.equal(Qnd.cpu(), Qn)
+    be.cls_scatter(Y.cuda(), Xd, None, 0)  # operand copies are optional
+    assert torch.equal(Xd.cpu(), Xr)

@@ -542,7 +542,8 @@ def test_cls_gather_scatter_equal_take_put_rows():
         video = _leaf(1, d, seed=5)
         X = (x * 1.5).view(n, S, d)  # a non-leaf stream, like a layer output
         if fused:
-            X3, Y = ops.cls_gather(X, video, 0)
+            X3, Y, q_op, y_op = ops.cls_gather(X, video, 0)
+            assert q_op is None and y_op is None  # operand copies only with ``pos`` in bf16 mode
             Y = torch.tanh(Y @ W)  # stands in for the temporal layer
             X3, vs = ops.cls_scatter(X3, Y, 0)
         else:
@@ -554,3 +555,21 @@ def test_cls_gather_scatter_equal_take_put_rows():
         res[fused] = [X3.detach().clone(), vs.detach().clone(), x.grad.clone(), video.grad.clone()]
     for a_, b_ in zip(res[True], res[False]):
         assert rel_err(a_, b_) < 1e-6
+    # bf16 mode: the same launches also write the temporal layer's GEMM operands and refresh the stream's operand copy
+    ops.set_precision("bf16")
+    try:
+        x = _leaf(n * S, d, seed=4)
+        video = _leaf(1, d, seed=5)
+        pos = torch.randn(1 + n, d, generator=torch.Generator().manual_seed(6))
+        X = (x * 1.5).view(n, S, d)
+        X_op = X.detach().to(torch.bfloat16).clone()
+        X3, Y, q_op, y_op = ops.cls_gather(X, video, 0, pos=pos)
+        assert torch.equal(Y.detach(), torch.cat([video.detach(), X.detach()[:, 0, :]], 0))
+        assert torch.equal(q_op, (Y.detach() + pos).to(torch.bfloat16)) and torch.equal(y_op, Y.detach().to(torch.bfloat16))
+        Y2 = torch.tanh(Y @ W)
+        X3, vs = ops.cls_scatter(X3, Y2, 0, x_op=X_op)
+        assert torch.equal(X_op[:, 0, :], Y2.detach()[1:].to(torch.bfloat16)) and torch.equal(X_op[:, 1:, :], X.detach()[:, 1:, :].to(torch.bfloat16))
+        ((X3 * g1).sum() + (vs * g2).sum()).backward()
+        assert rel_err(x.grad, res[True][2]) < 1e-6 and rel_err(video.grad, res[True][3]) < 1e-6
+    finally:
+        ops.set_precision("fp32")
