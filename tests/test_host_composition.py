@@ -377,3 +377,40 @@ def test_gradient_sink_with_a_partial_backward_pass():
     for a, b in zip(res[False], res[True]):
         assert rel_err(b, a) < 2e-2, rel_err(b, a)  # same terms; bf16 rounding of the accumulated memory gradient differs
     assert rel_err(res[True][0], res[True][1]) > 1e-3  # the two passes really are different gradients
+
+
+@pytest.mark.parametrize("name", ["b1_T8_res224_L8", "b1_T12_res320_L16"])
+def test_early_in_projection_is_bit_identical(name):
+    """ops.qkv_early (bf16 mode, one un-padded video): projecting the next spatial layer's q/k/v before the temporal layer and
+    re-projecting only the patched frame-CLS rows gives exactly the tensors of the one-shot projection -- outputs and every
+    gradient are bit-identical on the emulation backend (same products, same accumulation per row)."""
+    from stcat_b200 import encoder as E
+
+    fx = load_golden(name)
+    spec = fx["spec"]
+    cfg = cfg_for(spec)
+    inp = case_inputs(spec)
+    assert len(spec["durations"]) == 1
+    ops.set_precision("bf16")
+    res = []
+    old = (E._EARLY_QKV, E._CLS_KERNELS)
+    try:
+        for early, cls_k in ((False, False), (False, True), (True, True)):
+            E._EARLY_QKV, E._CLS_KERNELS = early, cls_k
+            ops.clear_weight_cache()
+            m = build(cfg, case_params(cfg, spec)).eval()
+            be = ops.get_backend()
+            n0 = be.launches
+            out, vis, txt = run_model(m, inp, grad=True)
+            (out["pred_boxes"].square().sum() + out["pred_sted"].square().sum()).backward()
+            g = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+            res.append((out, g, vis.grad.clone(), be.launches - n0))
+    finally:
+        E._EARLY_QKV, E._CLS_KERNELS = old
+    for o1, g1, v1, _ in res[1:]:
+        for k in ("pred_boxes", "pred_sted", "pred_actioness", "weights"):
+            assert torch.equal(o1[k], res[0][0][k]), k
+        assert torch.equal(v1, res[0][2])
+        assert set(g1) == set(res[0][1])
+        for k, g in g1.items():
+            assert torch.equal(g, res[0][1][k]), k
