@@ -573,3 +573,171 @@ def test_cls_gather_scatter_equal_take_put_rows():
         assert rel_err(x.grad, res[True][2]) < 1e-6 and rel_err(video.grad, res[True][3]) < 1e-6
     finally:
         ops.set_precision("fp32")
+
+
+# ---- the layout-glue / anchor-chain autograd nodes (csrc/assembly.cu) against plain torch autograd -------------------------
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("durs", [[6], [3, 2, 4]])
+def test_token_assembly_matches_torch_autograd(durs):
+    """ops.token_assembly == the reference's cat / transpose / expand assembly (modal_encoder.py:40-72): X, POS, the two operand
+    copies, and the gradients of vis / text / frame_cls (the text token is read by every frame of its video)."""
+    ops.set_precision("bf16")
+    n, b, d, H, W, L = sum(durs), len(durs), 16, 3, 2, 4
+    vis, txt, cls = _leaf(n, d, H, W, seed=1), _leaf(L, b, d, seed=2), _leaf(1, d, seed=3)
+    vpos, lpos = torch.randn(n, d, H, W, generator=torch.Generator().manual_seed(4)), torch.randn(1, d, generator=torch.Generator().manual_seed(5))
+    f2v = torch.tensor([j for j, t in enumerate(durs) for _ in range(t)])
+    vid_start = torch.tensor([0] + [sum(durs[: j + 1]) for j in range(b)])
+    gX = torch.randn(n, 1 + H * W + L, d, generator=torch.Generator().manual_seed(6))
+    Xr = torch.cat([cls.expand(n, 1, d), vis.flatten(2).transpose(1, 2), txt.transpose(0, 1).index_select(0, f2v)], 1)
+    Pr = torch.cat([lpos.expand(n, 1, d), vpos.flatten(2).transpose(1, 2), torch.zeros(n, L, d)], 1)
+    (Xr * gX).sum().backward()
+    want = [t.grad.clone() for t in (vis, txt, cls)]
+    for t in (vis, txt, cls):
+        t.grad = None
+    one = b == 1
+    X, POS, qk, xo = ops.token_assembly(vis, vpos, txt, cls, lpos, None if one else f2v, None if one else vid_start)
+    assert torch.equal(X, Xr.detach()) and torch.equal(POS, Pr)
+    assert torch.equal(qk, (Xr.detach() + Pr).to(torch.bfloat16)) and torch.equal(xo, Xr.detach().to(torch.bfloat16))
+    assert not POS.requires_grad and not qk.requires_grad
+    (X * gX).sum().backward()
+    for t, w in zip((vis, txt, cls), want):
+        assert rel_err(t.grad, w) < 1e-6
+
+
+def test_mem_operands_matches_torch_autograd():
+    """ops.mem_operands: operands of rows 1.. and the CLS rows; backward = [g_cls ; g_mem + g_mempos] with bf16 or missing parts."""
+    ops.set_precision("bf16")
+    n, S, d = 4, 6, 8
+    X = _leaf(n, S, d, seed=1)
+    POS = torch.randn(n, S, d, generator=torch.Generator().manual_seed(2))
+    mem_op, pos_op, mempos_op, cls = ops.mem_operands(X * 1.0, POS)
+    assert torch.equal(mem_op, X.detach()[:, 1:].reshape(-1, d).to(torch.bfloat16))
+    assert torch.equal(pos_op, POS[:, 1:].reshape(-1, d).to(torch.bfloat16))
+    assert torch.equal(mempos_op, (X.detach() + POS)[:, 1:].reshape(-1, d).to(torch.bfloat16))
+    assert torch.equal(cls, X.detach()[:, 0])
+    g1 = torch.randn(n * (S - 1), d, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16)
+    g3 = torch.randn(n, d, generator=torch.Generator().manual_seed(4))
+    ((mem_op.float() * g1.float()).sum() + (cls * g3).sum()).backward()  # mempos_op unused: its gradient is None
+    want = torch.cat([g3[:, None, :], g1.float().view(n, S - 1, d)], 1)
+    assert rel_err(X.grad, want) < 1e-6
+
+
+@pytest.mark.parametrize("durs", [[5], [2, 3]])
+@pytest.mark.parametrize("fused", [False, True])
+def test_template_matches_torch_autograd(durs, fused):
+    """ops.template == TemplateGenerator.forward + sigmoid (query_decoder.py:441-475, :105) with bf16-rounded GEMM operands: values
+    and every gradient (video token, frame-CLS rows, 4 weights, 4 biases), with autograd accumulation and with grad fusion."""
+    ops.set_precision("bf16")
+    n, b, d, q = sum(durs), len(durs), 16, 4
+    v, fc = _leaf(b, d, seed=1), _leaf(n, d, seed=2)
+    Ws = [_leaf(d, d, seed=10 + i) for i in range(3)] + [_leaf(q, d, seed=13)]
+    bs = [_leaf(d, seed=20 + i) for i in range(3)] + [_leaf(q, seed=23)]
+    with torch.no_grad():
+        for w in Ws:
+            w.mul_(d ** -0.5)
+            w.copy_(_bf(w))  # weights exactly representable: the reference below needs no weight rounding
+    f2v = torch.tensor([j for j, t in enumerate(durs) for _ in range(t)])
+    vid_start = torch.tensor([0] + [sum(durs[: j + 1]) for j in range(b)])
+    ga = torch.randn(n, q, generator=torch.Generator().manual_seed(30))
+    gt = torch.randn(n, d, generator=torch.Generator().manual_seed(31))
+
+    class R(torch.autograd.Function):  # bf16 rounding of a GEMM operand, straight-through (the kernels round forward and backward operands)
+        @staticmethod
+        def forward(ctx, x):
+            return _bf(x)
+
+        @staticmethod
+        def backward(ctx, g):
+            return g
+
+    lin = lambda x, W, bb: R.apply(x) @ W.t() + bb
+    content = lin(v, Ws[0], bs[0])
+    gamma, beta = torch.tanh(lin(v, Ws[1], bs[1])), torch.tanh(lin(v, Ws[2], bs[2]))
+    mod = gamma.index_select(0, f2v) * fc + beta.index_select(0, f2v)
+    anchor_r = torch.sigmoid(lin(mod, Ws[3], bs[3]))
+    temp_r = content.index_select(0, f2v)
+    ((anchor_r * ga).sum() + (temp_r * gt).sum()).backward()
+    leaves = (v, fc, *Ws, *bs)
+    want = [t.grad.clone() for t in leaves]
+    for t in leaves:
+        t.grad = None
+    if fused:
+        for t in (*Ws, *bs):
+            t.grad = torch.zeros_like(t)
+        ops.set_grad_fusion(True)
+    one = b == 1
+    anchor, temp = ops.template(v, fc, Ws[0], bs[0], Ws[1], bs[1], Ws[2], bs[2], Ws[3], bs[3], None if one else f2v, None if one else vid_start)
+    assert rel_err(anchor, anchor_r) < 1e-5 and rel_err(temp, temp_r) < 1e-6
+    ((anchor * ga).sum() + (temp * gt).sum()).backward()
+    # the kernels round the incoming gradients of the Linears to bf16 as GEMM operands (like every Linear of the package); the
+    # straight-through reference does not: 2^-8 relative per operand
+    for t, w in zip(leaves, want):
+        assert t.grad is not None and rel_err(t.grad, w) < 1.5e-2, rel_err(t.grad, w)
+
+
+def test_box_mlp_head_and_mul_operand_match_torch_autograd():
+    """ops.box_mlp_head (bbox_embed + refinement + sine of the detached result) and ops.mul_operand against torch autograd."""
+    import math
+
+    ops.set_precision("bf16")
+    R_, d = 7, 16
+
+    class Lyr:
+        def __init__(self, o, i, seed):
+            self.weight, self.bias = _leaf(o, i, seed=seed), _leaf(o, seed=seed + 50)
+            with torch.no_grad():
+                self.weight.mul_(i ** -0.5)
+                self.weight.copy_(_bf(self.weight))
+
+    layers = [Lyr(d, d, 1), Lyr(d, d, 2), Lyr(4, d, 3)]
+    x = _leaf(R_, d, seed=4)
+    anchor = torch.rand(R_, 4, generator=torch.Generator().manual_seed(5)).requires_grad_(True)
+    g = torch.randn(R_, 4, generator=torch.Generator().manual_seed(6))
+    h = _bf(x)
+    for lyr in layers[:-1]:
+        h = _bf((h @ lyr.weight.t() + lyr.bias).relu())
+    delta = h @ layers[-1].weight.t() + layers[-1].bias
+    a = anchor.clamp(0, 1)
+    ref = torch.sigmoid(delta + torch.log(a.clamp(min=1e-3) / (1 - a).clamp(min=1e-3)))
+    out, sine, sine_op = ops.box_mlp_head(layers, x, None, anchor, want_sine=True)
+    assert rel_err(out, ref) < 1e-5
+    k = torch.arange(128, dtype=torch.float32)
+    p = (out.detach() * (2 * math.pi))[..., None] / (10000 ** (2 * torch.div(k, 2, rounding_mode="floor") / 128))
+    e = torch.stack((p[..., 0::2].sin(), p[..., 1::2].cos()), dim=-1).flatten(-2)
+    assert rel_err(sine, torch.cat((e[..., 1, :], e[..., 0, :], e[..., 2, :], e[..., 3, :]), dim=-1)) < 1e-5
+    assert not sine.requires_grad and torch.equal(sine_op, sine.to(torch.bfloat16))
+    (out * g).sum().backward()
+    got = [t.grad.clone() for t in (x, anchor, *[l.weight for l in layers], *[l.bias for l in layers])]
+    # reference gradients: straight-through roundings, plain autograd
+    for t in (x, anchor, *[l.weight for l in layers], *[l.bias for l in layers]):
+        t.grad = None
+
+    class ST(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, t):
+            return _bf(t)
+
+        @staticmethod
+        def backward(ctx, gg):
+            return gg
+
+    h = ST.apply(x)
+    for lyr in layers[:-1]:
+        h = ST.apply((h @ lyr.weight.t() + lyr.bias).relu())
+    delta = h @ layers[-1].weight.t() + layers[-1].bias
+    a = anchor.clamp(0, 1)
+    (torch.sigmoid(delta + torch.log(a.clamp(min=1e-3) / (1 - a).clamp(min=1e-3))) * g).sum().backward()
+    want = [t.grad.clone() for t in (x, anchor, *[l.weight for l in layers], *[l.bias for l in layers])]
+    for a_, b_ in zip(got, want):
+        assert rel_err(a_, b_) < 1.5e-2, rel_err(a_, b_)
+    # mul_operand: product, its operand copy, the operand copy of a second tensor; gradient of the differentiable factor
+    s_ = torch.randn(R_, 2 * d, generator=torch.Generator().manual_seed(7))
+    sc, qp = _leaf(R_, d, seed=8), torch.randn(R_, d, generator=torch.Generator().manual_seed(9))
+    prod, prod_op, qp_op = ops.mul_operand(s_, sc, qp)
+    assert torch.equal(prod, s_[:, :d] * sc.detach()) and torch.equal(prod_op, prod.to(torch.bfloat16)) and torch.equal(qp_op, qp.to(torch.bfloat16))
+    gp = torch.randn(R_, d, generator=torch.Generator().manual_seed(10))
+    (prod * gp).sum().backward()
+    assert rel_err(sc.grad, gp * s_[:, :d]) < 1e-6
